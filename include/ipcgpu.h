@@ -1,0 +1,119 @@
+/*
+ * ipcgpu.h -- C ABI of the B200-native IPC Newton hot path (libipcgpu.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch/Eigen types.  Each entry point
+ * names the reference interface (ipc-sim/IPC @ 573d2c7, paths relative to the reference root) that a
+ * maintainer would rebind to it; INTEGRATION.md shows the adapter classes.
+ *
+ * Conventions
+ *  - One context per process per GPU (one rank = one GPU); multi-GPU runs are N processes that share
+ *    an NCCL communicator handed in through ipcgpu_comm_init.
+ *  - All reals are double, all indices int32.  Layouts are exactly what the reference's Eigen objects
+ *    expose through .data():
+ *       V, V_rest  : column-major nV x 3  => SoA [x(nV) | y(nV) | z(nV)]        (Mesh.hpp:61)
+ *       F (tets)   : column-major nT x 4  => SoA [v0(nT) | v1 | v2 | v3]         (Mesh.hpp:64)
+ *       SF         : column-major nSF x 3 => SoA                                 (Mesh.hpp:70)
+ *       restTriInv : nT matrices 3x3, each column-major (9 doubles)              (Mesh.hpp:90)
+ *       gradient / searchDir : interleaved [x0 y0 z0 x1 ...]                     (Energy.cpp:275)
+ *       CSR        : upper-triangular ia/ja/a of LinSysSolver                    (LinSysSolver.hpp:34-37)
+ *  - Every function returns 0 on success, otherwise an IPCGPU_ERR_* code; nothing here calls exit().
+ *    ipcgpu_last_error() gives a human-readable message for the last failure on that context.
+ *  - Host output pointers may be NULL: the result then stays device-resident (no D2H copy) and can be
+ *    consumed by a later call or fetched with ipcgpu_download().  This is how a device-side solver
+ *    (cuDSS) or the benchmark's HBM-resident mode avoids PCIe traffic.
+ */
+#ifndef IPCGPU_H
+#define IPCGPU_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ipcgpu_ctx ipcgpu_ctx;
+
+enum {
+    IPCGPU_OK = 0,
+    IPCGPU_ERR_CUDA = 1,
+    IPCGPU_ERR_ARG = 2,
+    IPCGPU_ERR_PATTERN = 3,
+    IPCGPU_ERR_NONPOSITIVE_DISTANCE = 4, /* Optimizer.cpp:3296-3306 would exit(0) */
+    IPCGPU_ERR_CAPACITY = 5,
+    IPCGPU_ERR_NCCL = 6,
+    IPCGPU_ERR_STATE = 7
+};
+
+enum { IPCGPU_NEOHOOKEAN = 0, IPCGPU_FIXED_COROT = 1 };
+
+/* device-resident result buffers that ipcgpu_download() can fetch */
+enum {
+    IPCGPU_BUF_GRADIENT = 0,      /* 3*nV doubles, interleaved */
+    IPCGPU_BUF_CSR_VALUES = 1,    /* nnz doubles */
+    IPCGPU_BUF_ENERGY_PER_TET = 2,/* nT doubles */
+    IPCGPU_BUF_TET_HESSIANS = 3,  /* 78*nT doubles (block layout) */
+    IPCGPU_BUF_TET_GRADIENTS = 4, /* 12*nT doubles */
+    IPCGPU_BUF_INVERSION_STEPS = 5/* nT doubles */
+};
+
+/* ---- lifetime ---------------------------------------------------------------------------------- */
+int ipcgpu_create(int device, ipcgpu_ctx** out);
+void ipcgpu_destroy(ipcgpu_ctx* ctx);
+const char* ipcgpu_last_error(const ipcgpu_ctx* ctx);
+/* pinned host allocations so that host<->device copies of the big result arrays run at PCIe speed */
+int ipcgpu_host_alloc(void** ptr, uint64_t bytes);
+int ipcgpu_host_free(void* ptr);
+int ipcgpu_sync(ipcgpu_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t ipcgpu_launch_count(const ipcgpu_ctx* ctx);
+
+/* ---- multi-GPU (tet / pair partition + NCCL) ------------------------------------------------------ */
+/* 128-byte ncclUniqueId created on rank 0 and broadcast by the host (torch.distributed / MPI / file). */
+int ipcgpu_comm_unique_id(void* id128);
+int ipcgpu_comm_init(ipcgpu_ctx* ctx, int rank, int nranks, const void* id128);
+
+/* ---- scene (once per scene; replaces what Mesh<3> precomputes, Mesh.cpp:415-527, :661-671) ------- */
+int ipcgpu_set_mesh(ipcgpu_ctx* ctx, int nV, int nT,
+    const double* V_rest_soa, const int* tets_soa,
+    const double* restTriInv /* 9*nT */, const double* vol /* triArea */,
+    const double* mu, const double* lam,
+    const double* mass_diag /* nV, may be NULL */,
+    const uint8_t* dbc_type /* nV: 0 NOT_DBC, 1 ZERO, 2 NONZERO; may be NULL */,
+    int energy);
+/* LinSysSolver::set_pattern result (LinSysSolver.hpp:46-150): ia has n_rows+1 entries.
+ * Must be called again whenever the contact stencil changes the pattern (Optimizer.cpp:3556-3595). */
+int ipcgpu_set_csr(ipcgpu_ctx* ctx, int n_rows, const int* ia, const int* ja, int index_base);
+/* current positions (mesh.V); NULL keeps the device copy (after ipcgpu_step_forward) */
+int ipcgpu_set_state(ipcgpu_ctx* ctx, const double* V_soa);
+/* x = x0 + alpha*p on the device (Optimizer::stepForward, Optimizer.cpp:2919-2938); x0 = state at the
+ * time of ipcgpu_save_state */
+int ipcgpu_save_state(ipcgpu_ctx* ctx);
+int ipcgpu_step_forward(ipcgpu_ctx* ctx, const double* p_interleaved /* NULL = last search dir */, double alpha);
+
+/* ---- elastic plug-in: Energy<3> virtuals (Energy.hpp:42-131) ---------------------------------------- */
+/* Energy::computeEnergyVal (Energy.cpp:232-242): E = coef * sum_t psi_t * vol_t */
+int ipcgpu_elastic_energy(ipcgpu_ctx* ctx, double coef, int redoSVD, double* E);
+/* Energy::computeGradient (Energy.cpp:245-289): g (3nV interleaved) is overwritten */
+int ipcgpu_elastic_gradient(ipcgpu_ctx* ctx, double coef, int redoSVD, int projectDBC, double* g);
+/* Energy::computeHessian (Energy.cpp:292-331) into the CSR value array.
+ * a_inout != NULL: host array is uploaded, accumulated into and downloaded (addCoeff semantics);
+ * a_inout == NULL: device-resident values are accumulated (zero them with ipcgpu_csr_set_zero). */
+int ipcgpu_elastic_hessian(ipcgpu_ctx* ctx, double coef, int redoSVD, int projectSPD, int projectDBC, double* a_inout);
+/* fused variant for the Newton loop: computeGradient + computePrecondMtr's elastic and mass terms in one
+ * pass over the tets (Optimizer.cpp:3416, 3439-3450, 3619-3668). Results stay on the device when NULL. */
+int ipcgpu_elastic_grad_hess(ipcgpu_ctx* ctx, double coef, int projectSPD, int projectDBC, int add_mass,
+    double* g, double* a);
+/* Energy::filterStepSize (Energy.cpp:565-581) */
+int ipcgpu_inversion_step(ipcgpu_ctx* ctx, const double* p_interleaved, double slack, double* alpha_inout);
+
+/* LinSysSolver::setZero (LinSysSolver.hpp:348) on the device-resident value array */
+int ipcgpu_csr_set_zero(ipcgpu_ctx* ctx);
+/* cross-rank reductions over NVLink (no-ops on a single rank): sum of [gradient, CSR values], min of step */
+int ipcgpu_allreduce_grad_hess(ipcgpu_ctx* ctx, int with_gradient, int with_hessian);
+int ipcgpu_download(ipcgpu_ctx* ctx, int which, double* dst, uint64_t count);
+/* raw device pointer of a result buffer (for a device-side linear solver) */
+void* ipcgpu_device_ptr(ipcgpu_ctx* ctx, int which);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

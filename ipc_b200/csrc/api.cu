@@ -1,0 +1,474 @@
+// api.cu -- extern "C" entry points declared in include/ipcgpu.h
+#include "../../include/ipcgpu.h"
+#include "context.h"
+#include <algorithm>
+#include <cstring>
+#include <dlfcn.h>
+#include <numeric>
+
+using namespace ipcgpu;
+
+#define CK(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                        \
+            return IPCGPU_ERR_CUDA;                                                               \
+        }                                                                                         \
+    } while (0)
+#define REQUIRE(cond, code, msg)                                                                  \
+    do {                                                                                          \
+        if (!(cond)) {                                                                            \
+            ctx->err = (msg);                                                                     \
+            return (code);                                                                        \
+        }                                                                                         \
+    } while (0)
+#define ALLOC(buf, count) REQUIRE((buf).reserve(count), IPCGPU_ERR_CUDA, "cudaMalloc failed for " #buf)
+
+// ---------------------------------------------------------------------------------------------------
+// NCCL through dlopen: the library that torch already loaded (libnccl.so.2) is reused when present.
+// ---------------------------------------------------------------------------------------------------
+namespace {
+struct Id128 {
+    char b[128];
+};
+struct Nccl {
+    void* h = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, /* ncclUniqueId by value: 128 bytes */ Id128, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+Nccl g_nccl;
+bool nccl_load(std::string& err)
+{
+    if (g_nccl.h) return true;
+    const char* names[] = { "libnccl.so.2", "libnccl.so" };
+    for (const char* n : names) {
+        g_nccl.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.h) break;
+    }
+    if (!g_nccl.h) {
+        err = "dlopen(libnccl.so.2) failed";
+        return false;
+    }
+    g_nccl.GetUniqueId = (int (*)(void*))dlsym(g_nccl.h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(g_nccl.h, "ncclCommInitRank");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.h, "ncclAllReduce");
+    g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.h, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce) {
+        err = "NCCL symbols missing";
+        return false;
+    }
+    return true;
+}
+constexpr int kNcclFloat64 = 8; // ncclDouble
+constexpr int kNcclUint64 = 5;  // ncclUint64
+constexpr int kNcclSum = 0, kNcclMin = 3;
+} // namespace
+
+// ---------------------------------------------------------------------------------------------------
+// map building (host, once per mesh/partition): vertex->incident (tet,local) lists and Hessian slots
+// ---------------------------------------------------------------------------------------------------
+static int build_maps(ipcgpu_ctx* ctx)
+{
+    const int nT = ctx->nT, nV = ctx->nV;
+    const int tb = ctx->t_begin, te = ctx->t_end, nL = te - tb;
+    const std::vector<int>& T = ctx->h_T;
+    // incidence: counting sort by vertex; entries 4*localTet+loc ascending
+    std::vector<int> ptr(nV + 1, 0);
+    for (int k = 0; k < 4; ++k)
+        for (int t = tb; t < te; ++t) ++ptr[T[(size_t)k * nT + t] + 1];
+    for (int v = 0; v < nV; ++v) ptr[v + 1] += ptr[v];
+    std::vector<int> inc((size_t)4 * nL), cur(ptr.begin(), ptr.end() - 1);
+    for (int t = tb; t < te; ++t)
+        for (int k = 0; k < 4; ++k) inc[cur[T[(size_t)k * nT + t]]++] = 4 * (t - tb) + k;
+    if (!ctx->inc_ptr.upload(ptr.data(), ptr.size(), ctx->stream) || !ctx->inc.upload(inc.data(), inc.size(), ctx->stream)) {
+        ctx->err = "upload of incidence map failed";
+        return IPCGPU_ERR_CUDA;
+    }
+    // slots: (v<=u) pairs; contributions (key, src) sorted by key then tet (src ascending == tet ascending)
+    REQUIRE((uint64_t)nL * 78ull < 0xffffffffull, IPCGPU_ERR_CAPACITY, "local tet count too large for 32-bit block offsets");
+    struct KS {
+        uint64_t key;
+        unsigned src;
+    };
+    std::vector<KS> ks((size_t)10 * nL);
+    static const int pa[6] = { 0, 0, 0, 1, 1, 2 }, pb[6] = { 1, 2, 3, 2, 3, 3 };
+    for (int t = tb; t < te; ++t) {
+        int v[4];
+        for (int k = 0; k < 4; ++k) v[k] = T[(size_t)k * nT + t];
+        const unsigned base = (unsigned)(t - tb) * 78u;
+        KS* o = &ks[(size_t)10 * (t - tb)];
+        for (int a = 0; a < 4; ++a) o[a] = { ((uint64_t)v[a] << 32) | (uint32_t)v[a], base + 6u * a };
+        for (int q = 0; q < 6; ++q) {
+            int lo = std::min(v[pa[q]], v[pb[q]]), hi = std::max(v[pa[q]], v[pb[q]]);
+            o[4 + q] = { ((uint64_t)lo << 32) | (uint32_t)hi, base + 24u + 9u * q };
+        }
+    }
+    std::sort(ks.begin(), ks.end(), [](const KS& a, const KS& b) { return a.key < b.key || (a.key == b.key && a.src < b.src); });
+    std::vector<int> sv, su, cptr;
+    std::vector<unsigned> csrc(ks.size());
+    for (size_t i = 0; i < ks.size(); ++i) {
+        if (i == 0 || ks[i].key != ks[i - 1].key) {
+            sv.push_back((int)(ks[i].key >> 32));
+            su.push_back((int)(ks[i].key & 0xffffffffu));
+            cptr.push_back((int)i);
+        }
+        csrc[i] = ks[i].src;
+    }
+    cptr.push_back((int)ks.size());
+    ctx->nSlots = (int)sv.size();
+    bool ok = ctx->slot_v.upload(sv.data(), sv.size(), ctx->stream) && ctx->slot_u.upload(su.data(), su.size(), ctx->stream)
+        && ctx->con_ptr.upload(cptr.data(), cptr.size(), ctx->stream) && ctx->con_src.upload(csrc.data(), csrc.size(), ctx->stream)
+        && ctx->slot_off.reserve((size_t)3 * std::max(1, ctx->nSlots));
+    REQUIRE(ok, IPCGPU_ERR_CUDA, "upload of Hessian scatter map failed");
+    ALLOC(ctx->gcont, (size_t)12 * std::max(1, nL));
+    ALLOC(ctx->hblk, (size_t)78 * std::max(1, nL));
+    ALLOC(ctx->partials, (size_t)std::max(1, elastic_energy_blocks(nL)) + 8);
+    CK(cudaStreamSynchronize(ctx->stream)); // host vectors go out of scope
+    ctx->maps_ready = true;
+    ctx->offsets_ready = false;
+    return IPCGPU_OK;
+}
+
+static int ensure_offsets(ipcgpu_ctx* ctx)
+{
+    if (ctx->offsets_ready) return IPCGPU_OK;
+    REQUIRE(ctx->maps_ready, IPCGPU_ERR_STATE, "ipcgpu_set_mesh must precede Hessian assembly");
+    REQUIRE(ctx->n_rows == 3 * ctx->nV, IPCGPU_ERR_STATE, "ipcgpu_set_csr must be called with n_rows = 3*nV");
+    CK(cudaMemsetAsync(ctx->flag.p, 0, sizeof(int), ctx->stream));
+    slot_offsets(ctx->nSlots, ctx->slot_v.p, ctx->slot_u.p, ctx->ia.p, ctx->ja.p, ctx->index_base, ctx->slot_off.p, ctx->flag.p, ctx->stream);
+    ++ctx->launches;
+    int h = 0;
+    CK(cudaMemcpyAsync(&h, ctx->flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    REQUIRE(h == 0, IPCGPU_ERR_PATTERN, "CSR pattern misses a block of the mesh topology (row<=col entries of every tet vertex pair are required)");
+    ctx->offsets_ready = true;
+    return IPCGPU_OK;
+}
+
+extern "C" {
+
+int ipcgpu_create(int device, ipcgpu_ctx** out)
+{
+    if (!out) return IPCGPU_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return IPCGPU_ERR_CUDA; // no CPU fallback by design
+    if (device < 0 || device >= ndev) return IPCGPU_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return IPCGPU_ERR_CUDA;
+    ipcgpu_ctx* ctx = new ipcgpu_ctx();
+    ctx->device = device;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess || cudaMallocHost(&ctx->h_scalar, 64) != cudaSuccess
+        || !ctx->flag.reserve(4) || !ctx->scalar_out.reserve(8) || !ctx->min_ord.reserve(4)) {
+        delete ctx;
+        return IPCGPU_ERR_CUDA;
+    }
+    *out = ctx;
+    return IPCGPU_OK;
+}
+
+void ipcgpu_destroy(ipcgpu_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->nccl_comm);
+    if (ctx->stream) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+    }
+    if (ctx->h_scalar) cudaFreeHost(ctx->h_scalar);
+    delete ctx;
+}
+
+const char* ipcgpu_last_error(const ipcgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int ipcgpu_host_alloc(void** ptr, uint64_t bytes) { return cudaMallocHost(ptr, bytes) == cudaSuccess ? IPCGPU_OK : IPCGPU_ERR_CUDA; }
+int ipcgpu_host_free(void* ptr) { return cudaFreeHost(ptr) == cudaSuccess ? IPCGPU_OK : IPCGPU_ERR_CUDA; }
+int ipcgpu_sync(ipcgpu_ctx* ctx)
+{
+    CK(cudaStreamSynchronize(ctx->stream));
+    return IPCGPU_OK;
+}
+uint64_t ipcgpu_launch_count(const ipcgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int ipcgpu_comm_unique_id(void* id128)
+{
+    std::string err;
+    if (!id128 || !nccl_load(err)) return IPCGPU_ERR_NCCL;
+    return g_nccl.GetUniqueId(id128) == 0 ? IPCGPU_OK : IPCGPU_ERR_NCCL;
+}
+
+int ipcgpu_comm_init(ipcgpu_ctx* ctx, int rank, int nranks, const void* id128)
+{
+    REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, IPCGPU_ERR_ARG, "bad rank/nranks");
+    CK(cudaSetDevice(ctx->device));
+    ctx->rank = rank;
+    ctx->nranks = nranks;
+    if (nranks > 1) {
+        REQUIRE(id128 != nullptr, IPCGPU_ERR_ARG, "nccl unique id required for nranks>1");
+        REQUIRE(nccl_load(ctx->err), IPCGPU_ERR_NCCL, ctx->err);
+        Id128 id;
+        std::memcpy(id.b, id128, 128);
+        int r = g_nccl.CommInitRank(&ctx->nccl_comm, nranks, id, rank);
+        REQUIRE(r == 0, IPCGPU_ERR_NCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+    }
+    if (ctx->nT > 0) { // re-partition an already loaded mesh
+        ctx->t_begin = (int)((int64_t)ctx->nT * rank / nranks);
+        ctx->t_end = (int)((int64_t)ctx->nT * (rank + 1) / nranks);
+        return build_maps(ctx);
+    }
+    return IPCGPU_OK;
+}
+
+int ipcgpu_set_mesh(ipcgpu_ctx* ctx, int nV, int nT, const double* Vrest, const int* tets, const double* restTriInv, const double* vol,
+    const double* mu, const double* lam, const double* mass, const uint8_t* dbc, int energy)
+{
+    REQUIRE(nV > 0 && nT >= 0 && Vrest && tets && restTriInv && vol && mu && lam, IPCGPU_ERR_ARG, "ipcgpu_set_mesh: null or empty input");
+    REQUIRE(energy == IPCGPU_NEOHOOKEAN || energy == IPCGPU_FIXED_COROT, IPCGPU_ERR_ARG, "unknown energy type");
+    CK(cudaSetDevice(ctx->device));
+    for (size_t i = 0; i < (size_t)4 * nT; ++i) REQUIRE(tets[i] >= 0 && tets[i] < nV, IPCGPU_ERR_ARG, "tet vertex index out of range");
+    ctx->nV = nV;
+    ctx->nT = nT;
+    ctx->energy = energy;
+    ctx->h_T.assign(tets, tets + (size_t)4 * nT);
+    // Dm^-1: reference layout is per-tet column-major; device layout is SoA over the row-major index q=3i+j
+    std::vector<double> A((size_t)9 * std::max(nT, 1));
+    for (int t = 0; t < nT; ++t)
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) A[(size_t)(3 * i + j) * nT + t] = restTriInv[(size_t)9 * t + i + 3 * j];
+    bool ok = ctx->Vrest.upload(Vrest, (size_t)3 * nV, ctx->stream) && ctx->V.upload(Vrest, (size_t)3 * nV, ctx->stream)
+        && ctx->Vsaved.reserve((size_t)3 * nV) && ctx->T.upload(tets, (size_t)4 * nT, ctx->stream)
+        && ctx->Ainv.upload(A.data(), (size_t)9 * nT, ctx->stream) && ctx->vol.upload(vol, nT, ctx->stream)
+        && ctx->mu.upload(mu, nT, ctx->stream) && ctx->lam.upload(lam, nT, ctx->stream);
+    REQUIRE(ok, IPCGPU_ERR_CUDA, "mesh upload failed");
+    ctx->has_mass = mass != nullptr;
+    if (mass) REQUIRE(ctx->mass.upload(mass, nV, ctx->stream), IPCGPU_ERR_CUDA, "mass upload failed");
+    ctx->has_dbc = dbc != nullptr;
+    if (dbc) REQUIRE(ctx->dbc.upload(dbc, nV, ctx->stream), IPCGPU_ERR_CUDA, "dbc upload failed");
+    ALLOC(ctx->g, (size_t)3 * nV);
+    ALLOC(ctx->dir, (size_t)3 * nV);
+    ALLOC(ctx->e_per_tet, (size_t)std::max(nT, 1));
+    ALLOC(ctx->inv_steps, (size_t)std::max(nT, 1));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->t_begin = (int)((int64_t)nT * ctx->rank / ctx->nranks);
+    ctx->t_end = (int)((int64_t)nT * (ctx->rank + 1) / ctx->nranks);
+    return build_maps(ctx);
+}
+
+int ipcgpu_set_csr(ipcgpu_ctx* ctx, int n_rows, const int* ia, const int* ja, int index_base)
+{
+    REQUIRE(n_rows > 0 && ia && ja && (index_base == 0 || index_base == 1), IPCGPU_ERR_ARG, "ipcgpu_set_csr: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    const int nnz = ia[n_rows] - index_base;
+    REQUIRE(nnz >= 0, IPCGPU_ERR_ARG, "ipcgpu_set_csr: negative nnz");
+    ctx->n_rows = n_rows;
+    ctx->nnz = nnz;
+    ctx->index_base = index_base;
+    bool ok = ctx->ia.upload(ia, (size_t)n_rows + 1, ctx->stream) && ctx->ja.upload(ja, (size_t)nnz, ctx->stream) && ctx->a.reserve((size_t)std::max(nnz, 1));
+    REQUIRE(ok, IPCGPU_ERR_CUDA, "CSR upload failed");
+    CK(cudaMemsetAsync(ctx->a.p, 0, (size_t)nnz * sizeof(double), ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->offsets_ready = false;
+    return IPCGPU_OK;
+}
+
+int ipcgpu_set_state(ipcgpu_ctx* ctx, const double* V)
+{
+    REQUIRE(ctx->nV > 0, IPCGPU_ERR_STATE, "ipcgpu_set_mesh first");
+    CK(cudaSetDevice(ctx->device));
+    if (V) CK(cudaMemcpyAsync(ctx->V.p, V, (size_t)3 * ctx->nV * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    return IPCGPU_OK;
+}
+
+int ipcgpu_save_state(ipcgpu_ctx* ctx)
+{
+    REQUIRE(ctx->nV > 0, IPCGPU_ERR_STATE, "ipcgpu_set_mesh first");
+    CK(cudaMemcpyAsync(ctx->Vsaved.p, ctx->V.p, (size_t)3 * ctx->nV * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    return IPCGPU_OK;
+}
+
+int ipcgpu_step_forward(ipcgpu_ctx* ctx, const double* p, double alpha)
+{
+    REQUIRE(ctx->nV > 0, IPCGPU_ERR_STATE, "ipcgpu_set_mesh first");
+    CK(cudaSetDevice(ctx->device));
+    if (p) CK(cudaMemcpyAsync(ctx->dir.p, p, (size_t)3 * ctx->nV * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    step_forward(ctx->nV, ctx->Vsaved.p, ctx->dir.p, alpha, ctx->V.p, ctx->stream);
+    ++ctx->launches;
+    CK(cudaGetLastError());
+    return IPCGPU_OK;
+}
+
+int ipcgpu_elastic_energy(ipcgpu_ctx* ctx, double coef, int /*redoSVD*/, double* E)
+{
+    REQUIRE(ctx->maps_ready, IPCGPU_ERR_STATE, "ipcgpu_set_mesh first");
+    CK(cudaSetDevice(ctx->device));
+    elastic_energy(ctx->eargs(), ctx->e_per_tet.p, ctx->partials.p, coef, ctx->scalar_out.p, ctx->stream);
+    ctx->launches += 2;
+    if (ctx->nranks > 1) {
+        int r = g_nccl.AllReduce(ctx->scalar_out.p, ctx->scalar_out.p, 1, kNcclFloat64, kNcclSum, ctx->nccl_comm, ctx->stream);
+        REQUIRE(r == 0, IPCGPU_ERR_NCCL, "ncclAllReduce(energy) failed");
+    }
+    CK(cudaGetLastError());
+    if (E) {
+        CK(cudaMemcpyAsync(ctx->h_scalar, ctx->scalar_out.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        *E = ctx->h_scalar[0];
+    }
+    return IPCGPU_OK;
+}
+
+static int run_grad_hess(ipcgpu_ctx* ctx, double coef, int projectSPD, int projectDBC, bool need_g, bool need_h, int add_mass, bool accumulate_a)
+{
+    REQUIRE(ctx->maps_ready, IPCGPU_ERR_STATE, "ipcgpu_set_mesh first");
+    if (need_h) {
+        int rc = ensure_offsets(ctx);
+        if (rc) return rc;
+    }
+    elastic_grad_hess(ctx->eargs(), coef, projectSPD, need_g, need_h, ctx->gcont.p, ctx->hblk.p, ctx->stream);
+    ++ctx->launches;
+    if (need_g) {
+        gather_gradient(ctx->nV, ctx->inc_ptr.p, ctx->inc.p, ctx->gcont.p, ctx->has_dbc ? ctx->dbc.p : nullptr, projectDBC, 0, ctx->g.p, ctx->stream);
+        ++ctx->launches;
+    }
+    if (need_h) {
+        // the mass term is added by rank 0 only so that the cross-rank sum counts it once
+        const double* m = (add_mass && ctx->has_mass && ctx->rank == 0) ? ctx->mass.p : nullptr;
+        assemble_csr(ctx->nSlots, ctx->slot_v.p, ctx->slot_u.p, ctx->slot_off.p, ctx->con_ptr.p, ctx->con_src.p, ctx->hblk.p,
+            ctx->has_dbc ? ctx->dbc.p : nullptr, projectDBC, m, accumulate_a ? 1 : 0, ctx->a.p, ctx->stream);
+        ++ctx->launches;
+    }
+    CK(cudaGetLastError());
+    return IPCGPU_OK;
+}
+
+int ipcgpu_elastic_gradient(ipcgpu_ctx* ctx, double coef, int /*redoSVD*/, int projectDBC, double* g)
+{
+    CK(cudaSetDevice(ctx->device));
+    int rc = run_grad_hess(ctx, coef, 1, projectDBC, true, false, 0, false);
+    if (rc) return rc;
+    if (ctx->nranks > 1) {
+        rc = ipcgpu_allreduce_grad_hess(ctx, 1, 0);
+        if (rc) return rc;
+    }
+    if (g) {
+        CK(cudaMemcpyAsync(g, ctx->g.p, (size_t)3 * ctx->nV * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return IPCGPU_OK;
+}
+
+int ipcgpu_elastic_hessian(ipcgpu_ctx* ctx, double coef, int /*redoSVD*/, int projectSPD, int projectDBC, double* a_inout)
+{
+    CK(cudaSetDevice(ctx->device));
+    REQUIRE(ctx->nnz > 0, IPCGPU_ERR_STATE, "ipcgpu_set_csr first");
+    if (a_inout) CK(cudaMemcpyAsync(ctx->a.p, a_inout, (size_t)ctx->nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = run_grad_hess(ctx, coef, projectSPD, projectDBC, false, true, 0, true);
+    if (rc) return rc;
+    if (ctx->nranks > 1) {
+        rc = ipcgpu_allreduce_grad_hess(ctx, 0, 1);
+        if (rc) return rc;
+    }
+    if (a_inout) {
+        CK(cudaMemcpyAsync(a_inout, ctx->a.p, (size_t)ctx->nnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return IPCGPU_OK;
+}
+
+int ipcgpu_elastic_grad_hess(ipcgpu_ctx* ctx, double coef, int projectSPD, int projectDBC, int add_mass, double* g, double* a)
+{
+    CK(cudaSetDevice(ctx->device));
+    REQUIRE(ctx->nnz > 0, IPCGPU_ERR_STATE, "ipcgpu_set_csr first");
+    int rc = run_grad_hess(ctx, coef, projectSPD, projectDBC, true, true, add_mass, false);
+    if (rc) return rc;
+    if (ctx->nranks > 1) {
+        rc = ipcgpu_allreduce_grad_hess(ctx, 1, 1);
+        if (rc) return rc;
+    }
+    if (g) CK(cudaMemcpyAsync(g, ctx->g.p, (size_t)3 * ctx->nV * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (a) CK(cudaMemcpyAsync(a, ctx->a.p, (size_t)ctx->nnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (g || a) CK(cudaStreamSynchronize(ctx->stream));
+    return IPCGPU_OK;
+}
+
+int ipcgpu_inversion_step(ipcgpu_ctx* ctx, const double* p, double slack, double* alpha_inout)
+{
+    REQUIRE(ctx->maps_ready, IPCGPU_ERR_STATE, "ipcgpu_set_mesh first");
+    REQUIRE(alpha_inout != nullptr, IPCGPU_ERR_ARG, "alpha_inout is null");
+    CK(cudaSetDevice(ctx->device));
+    if (p) CK(cudaMemcpyAsync(ctx->dir.p, p, (size_t)3 * ctx->nV * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    const unsigned long long init = 0x7ff0000000000000ull; // +inf
+    CK(cudaMemcpyAsync(ctx->min_ord.p, &init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    inversion_step(ctx->eargs(), ctx->dir.p, slack, ctx->inv_steps.p, ctx->min_ord.p, ctx->stream);
+    ++ctx->launches;
+    if (ctx->nranks > 1) {
+        int r = g_nccl.AllReduce(ctx->min_ord.p, ctx->min_ord.p, 1, kNcclUint64, kNcclMin, ctx->nccl_comm, ctx->stream);
+        REQUIRE(r == 0, IPCGPU_ERR_NCCL, "ncclAllReduce(min step) failed");
+    }
+    unsigned long long* h = reinterpret_cast<unsigned long long*>(ctx->h_scalar);
+    CK(cudaMemcpyAsync(h, ctx->min_ord.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    double m;
+    std::memcpy(&m, h, sizeof(double));
+    if (ctx->nT > 0 && m > 0.0 && m < *alpha_inout) *alpha_inout = m; // Energy.cpp:576-579
+    return IPCGPU_OK;
+}
+
+int ipcgpu_csr_set_zero(ipcgpu_ctx* ctx)
+{
+    REQUIRE(ctx->nnz > 0, IPCGPU_ERR_STATE, "ipcgpu_set_csr first");
+    CK(cudaMemsetAsync(ctx->a.p, 0, (size_t)ctx->nnz * sizeof(double), ctx->stream));
+    return IPCGPU_OK;
+}
+
+int ipcgpu_allreduce_grad_hess(ipcgpu_ctx* ctx, int with_gradient, int with_hessian)
+{
+    if (ctx->nranks <= 1) return IPCGPU_OK;
+    REQUIRE(ctx->nccl_comm != nullptr, IPCGPU_ERR_STATE, "ipcgpu_comm_init first");
+    if (with_gradient) {
+        int r = g_nccl.AllReduce(ctx->g.p, ctx->g.p, (size_t)3 * ctx->nV, kNcclFloat64, kNcclSum, ctx->nccl_comm, ctx->stream);
+        REQUIRE(r == 0, IPCGPU_ERR_NCCL, "ncclAllReduce(gradient) failed");
+    }
+    if (with_hessian) {
+        int r = g_nccl.AllReduce(ctx->a.p, ctx->a.p, (size_t)ctx->nnz, kNcclFloat64, kNcclSum, ctx->nccl_comm, ctx->stream);
+        REQUIRE(r == 0, IPCGPU_ERR_NCCL, "ncclAllReduce(csr values) failed");
+    }
+    return IPCGPU_OK;
+}
+
+static int buf_info(ipcgpu_ctx* ctx, int which, double** p, uint64_t* n)
+{
+    const uint64_t nL = (uint64_t)(ctx->t_end - ctx->t_begin);
+    switch (which) {
+    case IPCGPU_BUF_GRADIENT: *p = ctx->g.p; *n = (uint64_t)3 * ctx->nV; return 0;
+    case IPCGPU_BUF_CSR_VALUES: *p = ctx->a.p; *n = (uint64_t)ctx->nnz; return 0;
+    case IPCGPU_BUF_ENERGY_PER_TET: *p = ctx->e_per_tet.p; *n = (uint64_t)ctx->nT; return 0;
+    case IPCGPU_BUF_TET_HESSIANS: *p = ctx->hblk.p; *n = 78 * nL; return 0;
+    case IPCGPU_BUF_TET_GRADIENTS: *p = ctx->gcont.p; *n = 12 * nL; return 0;
+    case IPCGPU_BUF_INVERSION_STEPS: *p = ctx->inv_steps.p; *n = (uint64_t)ctx->nT; return 0;
+    default: return 1;
+    }
+}
+
+int ipcgpu_download(ipcgpu_ctx* ctx, int which, double* dst, uint64_t count)
+{
+    double* p;
+    uint64_t n;
+    REQUIRE(buf_info(ctx, which, &p, &n) == 0, IPCGPU_ERR_ARG, "unknown buffer id");
+    REQUIRE(dst && count <= n, IPCGPU_ERR_ARG, "download: bad destination or count");
+    CK(cudaMemcpyAsync(dst, p, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return IPCGPU_OK;
+}
+
+void* ipcgpu_device_ptr(ipcgpu_ctx* ctx, int which)
+{
+    double* p;
+    uint64_t n;
+    return buf_info(ctx, which, &p, &n) == 0 ? p : nullptr;
+}
+
+} // extern "C"

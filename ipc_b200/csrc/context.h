@@ -1,0 +1,90 @@
+// context.h -- the ipcgpu_ctx object behind the C ABI: device buffers, scatter maps, streams, NCCL.
+#pragma once
+#include "kernels.h"
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace ipcgpu {
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    ~DevBuf() { release(); }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    // grow-only allocation; returns false on CUDA failure
+    bool reserve(size_t count)
+    {
+        if (count <= n) return true;
+        release();
+        if (cudaMalloc(&p, count * sizeof(T)) != cudaSuccess) {
+            p = nullptr;
+            return false;
+        }
+        n = count;
+        return true;
+    }
+    bool upload(const T* h, size_t count, cudaStream_t st)
+    {
+        if (!reserve(count)) return false;
+        return count == 0 || cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, st) == cudaSuccess;
+    }
+};
+
+struct NcclApi; // dlopen'ed subset of NCCL (comm.cu)
+
+} // namespace ipcgpu
+
+struct ipcgpu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+
+    // partition
+    int rank = 0, nranks = 1;
+    void* nccl_comm = nullptr;
+
+    // mesh
+    int nV = 0, nT = 0, energy = 0;
+    int t_begin = 0, t_end = 0;
+    ipcgpu::DevBuf<double> V, Vsaved, Vrest, Ainv, vol, mu, lam, mass;
+    ipcgpu::DevBuf<int> T;
+    ipcgpu::DevBuf<uint8_t> dbc;
+    bool has_mass = false, has_dbc = false;
+    std::vector<int> h_T; // host copy of tets (maps are rebuilt when the partition changes)
+
+    // gradient gather map (local tets)
+    ipcgpu::DevBuf<int> inc_ptr, inc;
+    // Hessian slots (mesh-topology vertex pairs v<=u touched by local tets) and contributions
+    int nSlots = 0;
+    ipcgpu::DevBuf<int> slot_v, slot_u, slot_off, con_ptr;
+    ipcgpu::DevBuf<unsigned> con_src;
+    bool maps_ready = false, offsets_ready = false;
+
+    // CSR
+    int n_rows = 0, nnz = 0, index_base = 0;
+    ipcgpu::DevBuf<int> ia, ja;
+    ipcgpu::DevBuf<double> a;
+    ipcgpu::DevBuf<int> flag; // device error flag
+
+    // work / result buffers
+    ipcgpu::DevBuf<double> gcont, hblk, g, e_per_tet, partials, scalar_out, inv_steps, dir;
+    ipcgpu::DevBuf<unsigned long long> min_ord;
+    double* h_scalar = nullptr; // pinned staging for scalars (4 doubles)
+
+    ipcgpu::ElasticArgs eargs() const
+    {
+        ipcgpu::ElasticArgs p;
+        p.nV = nV; p.nT = nT; p.t_begin = t_begin; p.t_end = t_end;
+        p.V = V.p; p.T = T.p; p.Ainv = Ainv.p; p.vol = vol.p; p.mu = mu.p; p.lam = lam.p; p.energy = energy;
+        return p;
+    }
+};

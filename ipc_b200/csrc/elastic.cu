@@ -1,0 +1,591 @@
+// elastic.cu -- per-tetrahedron elastic energy / gradient / PSD-projected Hessian kernels (sm_100a).
+//
+// Reference path being replaced: Energy<3>::getEnergyValPerElemBySVD / computeGradientByPK /
+// computeHessianByPK (src/Energy/Energy.cpp:195-242, 245-289, 292-331, 334-408, 448-562) and
+// computeInjectiveStepSize_3d (src/Utils/get_feasible_steps.cpp:110-172).
+//
+// Design (not a translation): one thread per tet, everything in registers.
+//  * loads: SoA tet indices / Dm^-1 / vol / mu / lam are fully coalesced; the 4-vertex stencil is
+//    a gather from the SoA position array (L2-resident: 24 B/vertex).
+//  * the 9x9 dP/dF of the reference is never formed.  With G the 4x3 shape-gradient matrix
+//    (G[i+1][j] = Dm^-1(i,j), G[0] = -sum) and W = G V, every 3x3 vertex block is
+//        H_ab = U * Ht_ab * U^T,
+//        Ht_ab[k][m] = a_km W_ak W_bm + [k!=m] o_km W_am W_bk + [k==m] sum_{l!=k} d_kl W_al W_bl
+//    where a = projected d2psi/dsigma2 (A block), and d/o the diagonal/off-diagonal entries of the
+//    three projected 2x2 B blocks -- ~0.9 kflop instead of the ~5 kflop 21-term contraction, which
+//    keeps the kernel on the HBM side of the FP64 ridge.
+//  * output: only the 78 upper-triangular scalars per tet (what the CSR sink accepts), as 4 diagonal
+//    blocks (6 each) + 6 off-diagonal blocks (9 each, oriented so rows belong to the smaller global
+//    vertex id).  Each CTA stages its 64 x 624 B tile in shared memory and ships it with ONE TMA bulk
+//    store (cp.async.bulk.global.shared::cta), so HBM sees only full-line writes.
+#include "elastic.cuh"
+#include "kernels.h"
+
+namespace ipcgpu {
+
+constexpr int kHessTile = 64; // tets per CTA in the gradient/Hessian kernel
+
+struct TetIn {
+    int v[4];
+    double x[4][3];
+    M3 A; // Dm^-1 row-major
+    double vol, mu, lam;
+};
+
+DEV void load_tet(const ElasticArgs& p, int t, TetIn& in)
+{
+#pragma unroll
+    for (int k = 0; k < 4; ++k) in.v[k] = __ldg(p.T + (size_t)k * p.nT + t);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) in.x[k][c] = __ldg(p.V + (size_t)c * p.nV + in.v[k]);
+#pragma unroll
+    for (int q = 0; q < 9; ++q) in.A.m[q] = __ldg(p.Ainv + (size_t)q * p.nT + t);
+    in.vol = __ldg(p.vol + t);
+    in.mu = __ldg(p.mu + t);
+    in.lam = __ldg(p.lam + t);
+}
+
+DEV void def_grad(const TetIn& in, M3& F)
+{
+    double e[3][3]; // e[c] = x_{c+1} - x_0
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) e[c][r] = in.x[c + 1][r] - in.x[0][r];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) F(i, j) = e[0][i] * in.A(0, j) + e[1][i] * in.A(1, j) + e[2][i] * in.A(2, j);
+}
+
+// ---------------------------------------------------------------------------------------------
+// energy: per-tet psi*vol (optional) + deterministic two-level sum
+// ---------------------------------------------------------------------------------------------
+template <int ENERGY>
+__global__ void __launch_bounds__(256) k_elastic_energy(ElasticArgs p, double* __restrict__ e_per_tet, double* __restrict__ partials)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    double e = 0.0;
+    if (t < p.t_end - p.t_begin) {
+        const int tt = p.t_begin + t;
+        TetIn in;
+        load_tet(p, tt, in);
+        M3 F, U, V;
+        double s[3];
+        def_grad(in, F);
+        svd3<false>(F, U, s, V);
+        e = psi<ENERGY>(s, in.mu, in.lam) * in.vol;
+        if (e_per_tet) e_per_tet[tt] = e;
+    }
+    __shared__ double sm[8];
+    double w = warp_sum(e);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = w;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += sm[i];
+        partials[blockIdx.x] = s;
+    }
+}
+
+// single-CTA fixed-order reduction of the per-CTA partials: out[0] = scale * sum
+__global__ void __launch_bounds__(1024) k_reduce_sum(const double* __restrict__ partials, int n, double scale, double* __restrict__ out)
+{
+    __shared__ double sm[32];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += partials[i];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = (threadIdx.x < (blockDim.x >> 5)) ? sm[threadIdx.x] : 0.0;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) out[0] = scale * v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// gradient + Hessian
+// ---------------------------------------------------------------------------------------------
+DEV void tma_store_tile(void* gdst, const void* ssrc, unsigned bytes)
+{
+    // make the generic-proxy smem writes visible to the async proxy, then one bulk copy
+    unsigned saddr = (unsigned)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(saddr), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+}
+
+template <int ENERGY, bool NEED_G, bool NEED_H>
+__global__ void __launch_bounds__(kHessTile) k_elastic_grad_hess(ElasticArgs p, double coef, int projectSPD,
+    double* __restrict__ gcont /* 12 per LOCAL tet */, double* __restrict__ hblk /* 78 per LOCAL tet */)
+{
+    extern __shared__ __align__(128) double smem[];
+    double* sH = smem;                                   // kHessTile * 78
+    double* sG = smem + (NEED_H ? kHessTile * 78 : 0);   // kHessTile * 12
+    const int nLocal = p.t_end - p.t_begin;
+    const int tile0 = blockIdx.x * kHessTile;
+    const int t = tile0 + threadIdx.x;
+    if (t < nLocal) {
+        const int tt = p.t_begin + t;
+        TetIn in;
+        load_tet(p, tt, in);
+        M3 F, U, V;
+        double s[3];
+        def_grad(in, F);
+        svd3<true>(F, U, s, V);
+        const double w = coef * in.vol;
+
+        if (NEED_G) {
+            M3 P;
+            pk1<ENERGY>(F, U, s, V, in.mu, in.lam, P);
+            // g[3(i+1)+k] = w * sum_j A(i,j) P(k,j) ; g[k] = -sum_i   (IglUtils.cpp:656-667)
+            double* g = sG + threadIdx.x * 12;
+            double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                double a = w * (in.A(i, 0) * P(0, 0) + in.A(i, 1) * P(0, 1) + in.A(i, 2) * P(0, 2));
+                double b = w * (in.A(i, 0) * P(1, 0) + in.A(i, 1) * P(1, 1) + in.A(i, 2) * P(1, 2));
+                double c = w * (in.A(i, 0) * P(2, 0) + in.A(i, 1) * P(2, 1) + in.A(i, 2) * P(2, 2));
+                g[3 + 3 * i] = a;
+                g[4 + 3 * i] = b;
+                g[5 + 3 * i] = c;
+                g0 -= a;
+                g1 -= b;
+                g2 -= c;
+            }
+            g[0] = g0;
+            g[1] = g1;
+            g[2] = g2;
+        }
+
+        if (NEED_H) {
+            SigmaDerivs sd;
+            sigma_derivs<ENERGY>(s, in.mu, in.lam, sd);
+            if (projectSPD) make_pd3(sd.A);
+            // B blocks for sigma pairs (0,1), (1,2), (2,0)   [Energy.cpp:468-491]
+            double bd0[3], bd1[3], bo[3]; // B(0,0), B(1,1), B(0,1)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int cp = (c + 1) % 3;
+                double right = sd.dE[c] + sd.dE[cp];
+                const double sum = s[c] + s[cp];
+                right /= 2.0 * ((sum < 1.0e-6) ? 1.0e-6 : sum);
+                double pp = sd.BL[c] + right, qq = sd.BL[c] - right, rr = pp;
+                if (projectSPD) make_pd2(pp, qq, rr);
+                bd0[c] = pp;
+                bd1[c] = rr;
+                bo[c] = qq;
+            }
+            // weights in (k,l) index space   [Energy.cpp:497-528; note the transposed (2,0) block]
+            //   d[k][l] = M(kl,kl), o[k][m] = M(km,mk)
+            const double a00 = w * sd.A[0], a01 = w * sd.A[1], a02 = w * sd.A[2], a11 = w * sd.A[3], a12 = w * sd.A[4], a22 = w * sd.A[5];
+            const double d01 = w * bd0[0], d10 = w * bd1[0], o01 = w * bo[0];
+            const double d12 = w * bd0[1], d21 = w * bd1[1], o12 = w * bo[1];
+            const double d20 = w * bd0[2], d02 = w * bd1[2], o02 = w * bo[2];
+            // W = G V
+            double W[4][3];
+#pragma unroll
+            for (int l = 0; l < 3; ++l) {
+                double s0 = 0.0;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    double v = in.A(a, 0) * V(0, l) + in.A(a, 1) * V(1, l) + in.A(a, 2) * V(2, l);
+                    W[a + 1][l] = v;
+                    s0 -= v;
+                }
+                W[0][l] = s0;
+            }
+            double* out = sH + threadIdx.x * 78;
+            int off = 24;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+#pragma unroll
+                for (int b = a; b < 4; ++b) {
+                    const double wa0 = W[a][0], wa1 = W[a][1], wa2 = W[a][2];
+                    const double wb0 = W[b][0], wb1 = W[b][1], wb2 = W[b][2];
+                    // Ht (U-frame) 3x3
+                    M3 Ht;
+                    Ht(0, 0) = a00 * wa0 * wb0 + d01 * wa1 * wb1 + d02 * wa2 * wb2;
+                    Ht(1, 1) = a11 * wa1 * wb1 + d10 * wa0 * wb0 + d12 * wa2 * wb2;
+                    Ht(2, 2) = a22 * wa2 * wb2 + d20 * wa0 * wb0 + d21 * wa1 * wb1;
+                    Ht(0, 1) = a01 * wa0 * wb1 + o01 * wa1 * wb0;
+                    Ht(1, 0) = a01 * wa1 * wb0 + o01 * wa0 * wb1;
+                    Ht(0, 2) = a02 * wa0 * wb2 + o02 * wa2 * wb0;
+                    Ht(2, 0) = a02 * wa2 * wb0 + o02 * wa0 * wb2;
+                    Ht(1, 2) = a12 * wa1 * wb2 + o12 * wa2 * wb1;
+                    Ht(2, 1) = a12 * wa2 * wb1 + o12 * wa1 * wb2;
+                    // T = U * Ht ; H = T * U^T
+                    M3 Tm;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+#pragma unroll
+                        for (int m = 0; m < 3; ++m) Tm(i, m) = U(i, 0) * Ht(0, m) + U(i, 1) * Ht(1, m) + U(i, 2) * Ht(2, m);
+                    if (a == b) {
+                        double* o = out + 6 * a;
+                        int q = 0;
+#pragma unroll
+                        for (int i = 0; i < 3; ++i)
+#pragma unroll
+                            for (int r = i; r < 3; ++r) o[q++] = Tm(i, 0) * U(r, 0) + Tm(i, 1) * U(r, 1) + Tm(i, 2) * U(r, 2);
+                    }
+                    else {
+                        double* o = out + off;
+                        off += 9;
+                        const bool flip = in.v[a] > in.v[b]; // rows must belong to the smaller global vertex
+#pragma unroll
+                        for (int i = 0; i < 3; ++i)
+#pragma unroll
+                            for (int r = 0; r < 3; ++r) {
+                                double h = Tm(i, 0) * U(r, 0) + Tm(i, 1) * U(r, 1) + Tm(i, 2) * U(r, 2);
+                                o[flip ? (3 * r + i) : (3 * i + r)] = h;
+                            }
+                    }
+                }
+            }
+        }
+    }
+    // ship the tile: generic-proxy writes -> async proxy fence -> CTA barrier -> one elected TMA store
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int n = min(kHessTile, nLocal - tile0);
+        if (NEED_H) tma_store_tile(hblk + (size_t)tile0 * 78, sH, (unsigned)n * 78u * 8u);
+        if (NEED_G) tma_store_tile(gcont + (size_t)tile0 * 12, sG, (unsigned)n * 12u * 8u);
+        asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// vertex gather of the per-tet gradients (Energy.cpp:270-282): ascending (tet, local) order
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gather_gradient(int nV, const int* __restrict__ inc_ptr, const int* __restrict__ inc /* 4*tet+loc */,
+    const double* __restrict__ gcont, const uint8_t* __restrict__ dbc, int projectDBC, int accumulate, double* __restrict__ g)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nV) return;
+    double gx = 0.0, gy = 0.0, gz = 0.0;
+    const int e = inc_ptr[v + 1];
+    for (int q = inc_ptr[v]; q < e; ++q) {
+        const int id = __ldg(inc + q);
+        const double* s = gcont + (size_t)(id >> 2) * 12 + 3 * (id & 3);
+        gx += s[0];
+        gy += s[1];
+        gz += s[2];
+    }
+    if (projectDBC && dbc && dbc[v]) gx = gy = gz = 0.0; // Energy.cpp:284-288
+    if (accumulate) {
+        g[3 * (size_t)v] += gx;
+        g[3 * (size_t)v + 1] += gy;
+        g[3 * (size_t)v + 2] += gz;
+    }
+    else {
+        g[3 * (size_t)v] = gx;
+        g[3 * (size_t)v + 1] = gy;
+        g[3 * (size_t)v + 2] = gz;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CSR assembly (Energy.cpp:317-330 -> IglUtils::addBlockToMatrix -> LinSysSolver::addCoeff):
+// one thread per block-slot (vertex pair v<=u of the mesh topology); contributions are summed in
+// ascending tet order (the reference's vFLoc order), then written to the three CSR rows.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_assemble_csr(int nSlots, const int* __restrict__ slot_v, const int* __restrict__ slot_u,
+    const int* __restrict__ slot_off /* 3 per slot */, const int* __restrict__ con_ptr, const unsigned* __restrict__ con_src,
+    const double* __restrict__ hblk, const uint8_t* __restrict__ dbc, int projectDBC, const double* __restrict__ mass,
+    int accumulate, double* __restrict__ a)
+{
+    const int sIdx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sIdx >= nSlots) return;
+    const int v = slot_v[sIdx], u = slot_u[sIdx];
+    const int o0 = slot_off[3 * sIdx], o1 = slot_off[3 * sIdx + 1], o2 = slot_off[3 * sIdx + 2];
+    const bool pv = dbc && (dbc[v] == 1 || (dbc[v] == 2 && projectDBC));
+    const bool pu = dbc && (dbc[u] == 1 || (dbc[u] == 2 && projectDBC));
+    const int b = con_ptr[sIdx], e = con_ptr[sIdx + 1];
+    if (v == u) {
+        double h[6] = { 0, 0, 0, 0, 0, 0 };
+        if (pv) { // identity rows for projected Dirichlet vertices (IglUtils.hpp:44-53)
+            h[0] = h[3] = h[5] = 1.0;
+        }
+        else {
+            for (int q = b; q < e; ++q) {
+                const double* s = hblk + __ldg(con_src + q);
+#pragma unroll
+                for (int k = 0; k < 6; ++k) h[k] += s[k];
+            }
+            if (mass) {
+                h[0] += mass[v];
+                h[3] += mass[v];
+                h[5] += mass[v];
+            }
+        }
+        if (accumulate && !pv) {
+            a[o0] += h[0]; a[o0 + 1] += h[1]; a[o0 + 2] += h[2];
+            a[o1] += h[3]; a[o1 + 1] += h[4];
+            a[o2] += h[5];
+        }
+        else {
+            a[o0] = h[0]; a[o0 + 1] = h[1]; a[o0 + 2] = h[2];
+            a[o1] = h[3]; a[o1 + 1] = h[4];
+            a[o2] = h[5];
+        }
+    }
+    else {
+        double h[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+        if (!pv && !pu) {
+            for (int q = b; q < e; ++q) {
+                const double* s = hblk + __ldg(con_src + q);
+#pragma unroll
+                for (int k = 0; k < 9; ++k) h[k] += s[k];
+            }
+        }
+        if (accumulate) {
+            if (!pv && !pu) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    a[o0 + c] += h[c];
+                    a[o1 + c] += h[3 + c];
+                    a[o2 + c] += h[6 + c];
+                }
+            }
+        }
+        else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                a[o0 + c] = h[c];
+                a[o1 + c] = h[3 + c];
+                a[o2 + c] = h[6 + c];
+            }
+        }
+    }
+}
+
+// slot -> CSR offsets (binary search of column 3u in rows 3v, 3v+1, 3v+2)
+__global__ void __launch_bounds__(256) k_slot_offsets(int nSlots, const int* __restrict__ slot_v, const int* __restrict__ slot_u,
+    const int* __restrict__ ia, const int* __restrict__ ja, int base, int* __restrict__ slot_off, int* __restrict__ err)
+{
+    const int sIdx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sIdx >= nSlots) return;
+    const int v = slot_v[sIdx], u = slot_u[sIdx];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int row = 3 * v + r;
+        const int col = (v == u) ? row : 3 * u;
+        int lo = ia[row] - base, hi = ia[row + 1] - base;
+        const int target = col + base;
+        int found = -1;
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            int c = ja[mid];
+            if (c < target) lo = mid + 1;
+            else hi = mid;
+        }
+        if (lo < ia[row + 1] - base && ja[lo] == target) found = lo;
+        if (found < 0) atomicExch(err, 1);
+        slot_off[3 * sIdx + r] = found;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// inversion step bound (get_feasible_steps.cpp:75-172 + Energy.cpp:565-581)
+// ---------------------------------------------------------------------------------------------
+struct Cplx {
+    double re, im;
+};
+DEV Cplx cmul(Cplx a, Cplx b) { return { a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re }; }
+DEV Cplx cdiv(Cplx a, Cplx b)
+{
+    // Smith's algorithm (the scaling libgcc's __divdc3 effectively provides for finite operands)
+    if (fabs(b.re) >= fabs(b.im)) {
+        double r = b.im / b.re, den = b.re + b.im * r;
+        return { (a.re + a.im * r) / den, (a.im - a.re * r) / den };
+    }
+    else {
+        double r = b.re / b.im, den = b.re * r + b.im;
+        return { (a.re * r + a.im) / den, (a.im * r - a.re) / den };
+    }
+}
+DEV Cplx csqrt_(Cplx z)
+{
+    if (z.re == 0.0 && z.im == 0.0) return { 0.0, z.im };
+    double m = hypot(z.re, z.im);
+    if (z.re >= 0.0) {
+        double t = sqrt(0.5 * (m + z.re));
+        return { t, z.im / (2.0 * t) };
+    }
+    else {
+        double t = sqrt(0.5 * (m - z.re));
+        return { fabs(z.im) / (2.0 * t), copysign(t, z.im) };
+    }
+}
+DEV Cplx cpow_third(Cplx z)
+{
+    if (z.im == 0.0 && z.re > 0.0) return { pow(z.re, 1.0 / 3.0), 0.0 };
+    if (z.re == 0.0 && z.im == 0.0) return { 0.0, 0.0 };
+    double lr = log(hypot(z.re, z.im)), th = atan2(z.im, z.re);
+    double rho = exp((1.0 / 3.0) * lr), ang = (1.0 / 3.0) * th;
+    return { rho * cos(ang), rho * sin(ang) };
+}
+DEV double quad_root(double a, double b, double c, double tol)
+{
+    double t;
+    if (fabs(a) <= tol) t = -c / b;
+    else {
+        double desc = b * b - 4 * a * c;
+        if (desc > 0) {
+            t = (-b - sqrt(desc)) / (2 * a);
+            if (t < 0) t = (-b + sqrt(desc)) / (2 * a);
+        }
+        else t = -1;
+    }
+    return t;
+}
+DEV double cubic_root(double a, double b, double c, double d, double tol)
+{
+    double t = -1;
+    if (fabs(a) <= tol) return quad_root(b, c, d, tol);
+    const double delta0 = b * b - 3 * a * c;
+    const double delta1 = 2 * b * b * b - 9 * a * b * c + 27 * a * a * d;
+    Cplx rad = csqrt_({ delta1 * delta1 - 4.0 * delta0 * delta0 * delta0, 0.0 });
+    Cplx C = cpow_third({ (delta1 + rad.re) / 2.0, rad.im / 2.0 });
+    if (hypot(C.re, C.im) == 0.0) C = cpow_third({ (delta1 - rad.re) / 2.0, -rad.im / 2.0 });
+    const double h = sqrt(3.0) / 2.0;
+    const Cplx u2 = { -0.5, h }, u3 = { -0.5, -h };
+    const Cplx d0 = { delta0, 0.0 };
+    const double den = -3.0 * a;
+    Cplx q1 = cdiv(d0, C);
+    Cplx t1 = { (b + C.re + q1.re) / den, (C.im + q1.im) / den };
+    Cplx c2 = cmul(u2, C), q2 = cdiv(d0, c2);
+    Cplx t2 = { (b + c2.re + q2.re) / den, (c2.im + q2.im) / den };
+    Cplx c3 = cmul(u3, C), q3 = cdiv(d0, c3);
+    Cplx t3 = { (b + c3.re + q3.re) / den, (c3.im + q3.im) / den };
+    if (fabs(t1.im) < tol && t1.re > 0) t = t1.re;
+    if (fabs(t2.im) < tol && t2.re > 0 && (t2.re < t || t < 0)) t = t2.re;
+    if (fabs(t3.im) < tol && t3.re > 0 && (t3.re < t || t < 0)) t = t3.re;
+    return t;
+}
+DEV double det3v(const double* a, const double* b, const double* c)
+{
+    return a[0] * (b[1] * c[2] - b[2] * c[1]) - a[1] * (b[0] * c[2] - b[2] * c[0]) + a[2] * (b[0] * c[1] - b[1] * c[0]);
+}
+
+__global__ void __launch_bounds__(256) k_inversion_step(ElasticArgs p, const double* __restrict__ dir /* interleaved 3nV */, double slack,
+    double* __restrict__ per_tet, unsigned long long* __restrict__ min_ord)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    double out = 1e300;
+    if (t < p.t_end - p.t_begin) {
+        const int tt = p.t_begin + t;
+        int v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = __ldg(p.T + (size_t)k * p.nT + tt);
+        double x[4][3], d[4][3];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                x[k][c] = __ldg(p.V + (size_t)c * p.nV + v[k]);
+                d[k][c] = __ldg(dir + 3 * (size_t)v[k] + c);
+            }
+        double e[3][3], f[3][3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                e[k][c] = x[k + 1][c] - x[0][c];
+                f[k][c] = d[k + 1][c] - d[0][c];
+            }
+        const double ca = det3v(f[0], f[1], f[2]);
+        const double cb = det3v(e[0], f[1], f[2]) + det3v(f[0], e[1], f[2]) + det3v(f[0], f[1], e[2]);
+        const double cc = det3v(f[0], e[1], e[2]) + det3v(e[0], f[1], e[2]) + det3v(e[0], e[1], f[2]);
+        const double cd = (1.0 - slack) * det3v(e[0], e[1], e[2]);
+        const double r = cubic_root(ca, cb, cc, cd, 1.0e-6);
+        out = (r >= 0) ? r : 1e20;
+        if (per_tet) per_tet[tt] = out;
+    }
+    // min over the CTA; negative/zero roots are impossible here (r>=0 or 1e20), so the ordered-uint trick is valid
+    double m = warp_min(out);
+    __shared__ double sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double mm = sm[0];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) mm = fmin(mm, sm[i]);
+        atomicMin(min_ord, dbl_to_ord(mm));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+template <int ENERGY>
+static void launch_energy(const ElasticArgs& p, double* e_per_tet, double* partials, double coef, double* out, cudaStream_t st)
+{
+    const int n = p.t_end - p.t_begin;
+    const int nb = (n + 255) / 256;
+    if (nb > 0) k_elastic_energy<ENERGY><<<nb, 256, 0, st>>>(p, e_per_tet, partials);
+    k_reduce_sum<<<1, 1024, 0, st>>>(partials, nb, coef, out);
+}
+void elastic_energy(const ElasticArgs& p, double* e_per_tet, double* partials, double coef, double* out, cudaStream_t st)
+{
+    if (p.energy == 0) launch_energy<0>(p, e_per_tet, partials, coef, out, st);
+    else launch_energy<1>(p, e_per_tet, partials, coef, out, st);
+}
+int elastic_energy_blocks(int nTets) { return (nTets + 255) / 256; }
+
+template <int ENERGY, bool G, bool H>
+static void launch_gh(const ElasticArgs& p, double coef, int projectSPD, double* gcont, double* hblk, cudaStream_t st)
+{
+    const int n = p.t_end - p.t_begin;
+    if (n <= 0) return;
+    const int nb = (n + kHessTile - 1) / kHessTile;
+    const size_t smem = (size_t)kHessTile * 8 * ((H ? 78 : 0) + (G ? 12 : 0));
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_elastic_grad_hess<ENERGY, G, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    k_elastic_grad_hess<ENERGY, G, H><<<nb, kHessTile, smem, st>>>(p, coef, projectSPD, gcont, hblk);
+}
+void elastic_grad_hess(const ElasticArgs& p, double coef, int projectSPD, bool need_g, bool need_h, double* gcont, double* hblk, cudaStream_t st)
+{
+    if (p.energy == 0) {
+        if (need_g && need_h) launch_gh<0, true, true>(p, coef, projectSPD, gcont, hblk, st);
+        else if (need_g) launch_gh<0, true, false>(p, coef, projectSPD, gcont, hblk, st);
+        else if (need_h) launch_gh<0, false, true>(p, coef, projectSPD, gcont, hblk, st);
+    }
+    else {
+        if (need_g && need_h) launch_gh<1, true, true>(p, coef, projectSPD, gcont, hblk, st);
+        else if (need_g) launch_gh<1, true, false>(p, coef, projectSPD, gcont, hblk, st);
+        else if (need_h) launch_gh<1, false, true>(p, coef, projectSPD, gcont, hblk, st);
+    }
+}
+
+void gather_gradient(int nV, const int* inc_ptr, const int* inc, const double* gcont, const uint8_t* dbc, int projectDBC, int accumulate, double* g, cudaStream_t st)
+{
+    if (nV <= 0) return;
+    k_gather_gradient<<<(nV + 255) / 256, 256, 0, st>>>(nV, inc_ptr, inc, gcont, dbc, projectDBC, accumulate, g);
+}
+void assemble_csr(int nSlots, const int* slot_v, const int* slot_u, const int* slot_off, const int* con_ptr, const unsigned* con_src,
+    const double* hblk, const uint8_t* dbc, int projectDBC, const double* mass, int accumulate, double* a, cudaStream_t st)
+{
+    if (nSlots <= 0) return;
+    k_assemble_csr<<<(nSlots + 255) / 256, 256, 0, st>>>(nSlots, slot_v, slot_u, slot_off, con_ptr, con_src, hblk, dbc, projectDBC, mass, accumulate, a);
+}
+void slot_offsets(int nSlots, const int* slot_v, const int* slot_u, const int* ia, const int* ja, int base, int* slot_off, int* err, cudaStream_t st)
+{
+    if (nSlots <= 0) return;
+    k_slot_offsets<<<(nSlots + 255) / 256, 256, 0, st>>>(nSlots, slot_v, slot_u, ia, ja, base, slot_off, err);
+}
+void inversion_step(const ElasticArgs& p, const double* dir, double slack, double* per_tet, unsigned long long* min_ord, cudaStream_t st)
+{
+    const int n = p.t_end - p.t_begin;
+    if (n <= 0) return;
+    k_inversion_step<<<(n + 255) / 256, 256, 0, st>>>(p, dir, slack, per_tet, min_ord);
+}
+
+} // namespace ipcgpu

@@ -1,0 +1,34 @@
+// kernels.h -- launcher declarations shared between the .cu translation units and the C-ABI (api.cu)
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace ipcgpu {
+
+struct ElasticArgs {
+    int nV, nT;
+    int t_begin, t_end;      // this rank's tet range (multi-GPU partition)
+    const double* V;         // SoA [x|y|z] current positions
+    const int* T;            // SoA [v0|v1|v2|v3]
+    const double* Ainv;      // SoA 9 x nT, q = 3*i+j row-major index of Dm^-1
+    const double* vol;
+    const double* mu;
+    const double* lam;
+    int energy;              // 0 NH, 1 FCR
+};
+
+// elastic.cu
+void elastic_energy(const ElasticArgs& p, double* e_per_tet, double* partials, double coef, double* out, cudaStream_t st);
+int elastic_energy_blocks(int nTets);
+void elastic_grad_hess(const ElasticArgs& p, double coef, int projectSPD, bool need_g, bool need_h, double* gcont, double* hblk, cudaStream_t st);
+void gather_gradient(int nV, const int* inc_ptr, const int* inc, const double* gcont, const uint8_t* dbc, int projectDBC, int accumulate, double* g, cudaStream_t st);
+void assemble_csr(int nSlots, const int* slot_v, const int* slot_u, const int* slot_off, const int* con_ptr, const unsigned* con_src,
+    const double* hblk, const uint8_t* dbc, int projectDBC, const double* mass, int accumulate, double* a, cudaStream_t st);
+void slot_offsets(int nSlots, const int* slot_v, const int* slot_u, const int* ia, const int* ja, int base, int* slot_off, int* err, cudaStream_t st);
+void inversion_step(const ElasticArgs& p, const double* dir, double slack, double* per_tet, unsigned long long* min_ord, cudaStream_t st);
+
+
+// misc.cu
+void step_forward(int nV, const double* x0_soa, const double* p_interleaved, double alpha, double* x_soa, cudaStream_t st);
+
+} // namespace ipcgpu

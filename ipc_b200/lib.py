@@ -1,0 +1,207 @@
+"""ctypes binding of the C ABI in include/ipcgpu.h (libipcgpu.so).
+
+The product path has NO CPU fallback: if the CUDA library is missing or no GPU is visible, construction
+fails loudly.  torch is used nowhere here; device memory is owned by the context behind the C ABI.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libipcgpu.so")
+
+ERR_NAMES = {0: "OK", 1: "CUDA", 2: "ARG", 3: "PATTERN", 4: "NONPOSITIVE_DISTANCE", 5: "CAPACITY", 6: "NCCL", 7: "STATE"}
+
+BUF_GRADIENT, BUF_CSR_VALUES, BUF_ENERGY_PER_TET, BUF_TET_HESSIANS, BUF_TET_GRADIENTS, BUF_INVERSION_STEPS = range(6)
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_u8p = C.POINTER(C.c_uint8)
+_ctxp = C.c_void_p
+
+# name -> (restype, argtypes); tests check that every symbol of include/ipcgpu.h is exported
+SIGNATURES = {
+    "ipcgpu_create": (C.c_int, [C.c_int, C.POINTER(_ctxp)]),
+    "ipcgpu_destroy": (None, [_ctxp]),
+    "ipcgpu_last_error": (C.c_char_p, [_ctxp]),
+    "ipcgpu_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint64]),
+    "ipcgpu_host_free": (C.c_int, [C.c_void_p]),
+    "ipcgpu_sync": (C.c_int, [_ctxp]),
+    "ipcgpu_launch_count": (C.c_uint64, [_ctxp]),
+    "ipcgpu_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "ipcgpu_comm_init": (C.c_int, [_ctxp, C.c_int, C.c_int, C.c_void_p]),
+    "ipcgpu_set_mesh": (C.c_int, [_ctxp, C.c_int, C.c_int, _dp, _ip, _dp, _dp, _dp, _dp, _dp, _u8p, C.c_int]),
+    "ipcgpu_set_csr": (C.c_int, [_ctxp, C.c_int, _ip, _ip, C.c_int]),
+    "ipcgpu_set_state": (C.c_int, [_ctxp, _dp]),
+    "ipcgpu_save_state": (C.c_int, [_ctxp]),
+    "ipcgpu_step_forward": (C.c_int, [_ctxp, _dp, C.c_double]),
+    "ipcgpu_elastic_energy": (C.c_int, [_ctxp, C.c_double, C.c_int, _dp]),
+    "ipcgpu_elastic_gradient": (C.c_int, [_ctxp, C.c_double, C.c_int, C.c_int, _dp]),
+    "ipcgpu_elastic_hessian": (C.c_int, [_ctxp, C.c_double, C.c_int, C.c_int, C.c_int, _dp]),
+    "ipcgpu_elastic_grad_hess": (C.c_int, [_ctxp, C.c_double, C.c_int, C.c_int, C.c_int, _dp, _dp]),
+    "ipcgpu_inversion_step": (C.c_int, [_ctxp, _dp, C.c_double, _dp]),
+    "ipcgpu_csr_set_zero": (C.c_int, [_ctxp]),
+    "ipcgpu_allreduce_grad_hess": (C.c_int, [_ctxp, C.c_int, C.c_int]),
+    "ipcgpu_download": (C.c_int, [_ctxp, C.c_int, _dp, C.c_uint64]),
+    "ipcgpu_device_ptr": (C.c_void_p, [_ctxp, C.c_int]),
+}
+
+_lib = None
+
+
+class IpcGpuError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libipcgpu.so and declare signatures. Raises if the library is missing (never falls back)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise IpcGpuError(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a)")
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return None if a is None else a.ctypes.data_as(_ip)
+
+
+def f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def i32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+
+
+class PinnedArray:
+    """numpy view over cudaMallocHost memory (so D2H/H2D of the big arrays runs at PCIe speed)."""
+
+    def __init__(self, n, dtype=np.float64):
+        lib = load()
+        self._ptr = C.c_void_p()
+        nbytes = int(n) * np.dtype(dtype).itemsize
+        rc = lib.ipcgpu_host_alloc(C.byref(self._ptr), max(nbytes, 8))
+        if rc:
+            raise IpcGpuError("ipcgpu_host_alloc failed")
+        buf = (C.c_char * max(nbytes, 8)).from_address(self._ptr.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(n))
+
+    def free(self):
+        if self._ptr:
+            load().ipcgpu_host_free(self._ptr)
+            self._ptr = None
+
+
+class Context:
+    """Thin OO wrapper: one context per process per GPU."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        self.h = _ctxp()
+        rc = self.lib.ipcgpu_create(int(device), C.byref(self.h))
+        if rc:
+            raise IpcGpuError(f"ipcgpu_create(device={device}) failed with {ERR_NAMES.get(rc, rc)}: a CUDA device is required (no CPU fallback)")
+        self.nV = self.nT = self.nnz = 0
+        self._keep = []
+
+    def close(self):
+        if self.h:
+            self.lib.ipcgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            msg = self.lib.ipcgpu_last_error(self.h)
+            raise IpcGpuError(f"{ERR_NAMES.get(rc, rc)}: {msg.decode() if msg else ''}")
+
+    # ---- scene --------------------------------------------------------------------------------
+    def comm_init(self, rank, nranks, unique_id):
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id)) if unique_id is not None else None
+        self._ck(self.lib.ipcgpu_comm_init(self.h, rank, nranks, buf))
+
+    @staticmethod
+    def comm_unique_id():
+        buf = (C.c_char * 128)()
+        rc = load().ipcgpu_comm_unique_id(buf)
+        if rc:
+            raise IpcGpuError("ipcgpu_comm_unique_id failed")
+        return bytes(buf)
+
+    def set_mesh(self, Vrest_soa, tets_soa, restTriInv, vol, mu, lam, mass=None, dbc=None, energy=0):
+        Vr, T = f64(Vrest_soa).ravel(), i32(tets_soa).ravel()
+        self.nV, self.nT = Vr.size // 3, T.size // 4
+        A, vol, mu, lam, mass = f64(restTriInv).ravel(), f64(vol), f64(mu), f64(lam), f64(mass)
+        dbc = None if dbc is None else np.ascontiguousarray(dbc, dtype=np.uint8)
+        self._ck(self.lib.ipcgpu_set_mesh(self.h, self.nV, self.nT, _d(Vr), _i(T), _d(A), _d(vol), _d(mu), _d(lam), _d(mass),
+                                          None if dbc is None else dbc.ctypes.data_as(_u8p), int(energy)))
+
+    def set_csr(self, ia, ja, index_base):
+        ia, ja = i32(ia), i32(ja)
+        self.nnz = int(ia[-1]) - index_base
+        self._ck(self.lib.ipcgpu_set_csr(self.h, ia.size - 1, _i(ia), _i(ja), index_base))
+
+    def set_state(self, V_soa):
+        self._ck(self.lib.ipcgpu_set_state(self.h, _d(f64(V_soa).ravel()) if V_soa is not None else None))
+
+    def save_state(self):
+        self._ck(self.lib.ipcgpu_save_state(self.h))
+
+    def step_forward(self, p, alpha):
+        self._ck(self.lib.ipcgpu_step_forward(self.h, _d(f64(p)) if p is not None else None, float(alpha)))
+
+    def sync(self):
+        self._ck(self.lib.ipcgpu_sync(self.h))
+
+    def launch_count(self):
+        return int(self.lib.ipcgpu_launch_count(self.h))
+
+    # ---- elastic ------------------------------------------------------------------------------
+    def elastic_energy(self, coef, redoSVD=1, want=True):
+        E = C.c_double(0.0)
+        self._ck(self.lib.ipcgpu_elastic_energy(self.h, coef, redoSVD, C.byref(E) if want else None))
+        return E.value
+
+    def elastic_gradient(self, coef, redoSVD=1, projectDBC=1, out=None, want=True):
+        if want and out is None:
+            out = np.empty(3 * self.nV)
+        self._ck(self.lib.ipcgpu_elastic_gradient(self.h, coef, redoSVD, projectDBC, _d(out) if want else None))
+        return out
+
+    def elastic_hessian(self, coef, redoSVD=1, projectSPD=1, projectDBC=1, a_inout=None):
+        self._ck(self.lib.ipcgpu_elastic_hessian(self.h, coef, redoSVD, projectSPD, projectDBC, _d(a_inout)))
+        return a_inout
+
+    def elastic_grad_hess(self, coef, projectSPD=1, projectDBC=1, add_mass=0, g=None, a=None):
+        self._ck(self.lib.ipcgpu_elastic_grad_hess(self.h, coef, projectSPD, projectDBC, add_mass, _d(g), _d(a)))
+
+    def inversion_step(self, p, slack, alpha):
+        a = C.c_double(alpha)
+        self._ck(self.lib.ipcgpu_inversion_step(self.h, _d(f64(p)) if p is not None else None, slack, C.byref(a)))
+        return a.value
+
+    def csr_set_zero(self):
+        self._ck(self.lib.ipcgpu_csr_set_zero(self.h))
+
+    def download(self, which, count):
+        out = np.empty(int(count))
+        self._ck(self.lib.ipcgpu_download(self.h, which, _d(out), int(count)))
+        return out

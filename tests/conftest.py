@@ -1,0 +1,22 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def gpu_ctx():
+    """One C-ABI context on cuda:0; fails loudly (no CPU fallback) when the library or GPU is missing."""
+    from ipc_b200 import lib
+    ctx = lib.Context(0)
+    yield ctx
+    ctx.close()

@@ -1,0 +1,160 @@
+"""ctypes wrapper of the CPU oracle (oracle/liboracle.so). TEST INFRASTRUCTURE ONLY -- never imported by
+the product package (ipc_b200/)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+LIB = os.path.join(ORACLE_DIR, "liboracle.so")
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_u8p = C.POINTER(C.c_uint8)
+
+
+def build():
+    srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith((".cpp", ".h"))]
+    if os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in srcs):
+        return
+    subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(LIB)
+    return _lib
+
+
+class OrcMesh(C.Structure):
+    _fields_ = [("nV", C.c_int), ("nT", C.c_int), ("V", _dp), ("T", _ip), ("Ainv", _dp), ("vol", _dp),
+                ("mu", _dp), ("lam", _dp), ("dbc", _u8p), ("energy_type", C.c_int)]
+
+
+def d(a):
+    return a.ctypes.data_as(_dp)
+
+
+def i(a):
+    return a.ctypes.data_as(_ip)
+
+
+class Elastic:
+    """Keeps numpy buffers alive next to the C struct."""
+
+    def __init__(self, mesh, V=None, energy=None, dbc=None):
+        self.nV, self.nT = mesh.nV, mesh.nT
+        self.V = np.ascontiguousarray((mesh.V if V is None else V).T).ravel().astype(np.float64)
+        self.T = np.ascontiguousarray(mesh.T.T).ravel().astype(np.int32)
+        self.A = np.ascontiguousarray(mesh.restTriInv, dtype=np.float64).ravel()
+        self.vol, self.mu, self.lam = (np.ascontiguousarray(x, dtype=np.float64) for x in (mesh.vol, mesh.mu, mesh.lam))
+        self.dbc = np.ascontiguousarray(mesh.dbc if dbc is None else dbc, dtype=np.uint8)
+        et = mesh.energy if energy is None else energy
+        self.m = OrcMesh(self.nV, self.nT, d(self.V), i(self.T), d(self.A), d(self.vol), d(self.mu), d(self.lam),
+                         self.dbc.ctypes.data_as(_u8p), et)
+
+    def energy(self, coef, nthreads=1):
+        E = C.c_double()
+        per = np.empty(self.nT)
+        lib().orc_elastic_energy(C.byref(self.m), C.c_double(coef), d(per), C.byref(E), nthreads)
+        return E.value, per
+
+    def gradient(self, coef, projectDBC=1, nthreads=1):
+        g = np.empty(3 * self.nV)
+        lib().orc_elastic_gradient(C.byref(self.m), C.c_double(coef), projectDBC, d(g), nthreads)
+        return g
+
+    def hessian_blocks(self, coef, projectSPD=1, nthreads=1):
+        H = np.empty((self.nT, 12, 12))
+        lib().orc_elastic_hessian_blocks(C.byref(self.m), C.c_double(coef), projectSPD, d(H), nthreads)
+        return H
+
+    def hessian_csr(self, coef, ia, ja, base, projectSPD=1, projectDBC=1, a=None, nthreads=1):
+        ia = np.ascontiguousarray(ia, dtype=np.int32)
+        ja = np.ascontiguousarray(ja, dtype=np.int32)
+        if a is None:
+            a = np.zeros(ja.size)
+        lib().orc_elastic_hessian_csr(C.byref(self.m), C.c_double(coef), projectSPD, projectDBC, i(ia), i(ja), base, d(a), nthreads)
+        return a
+
+    def inversion_step(self, p, slack, alpha):
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        per = np.empty(self.nT)
+        a = C.c_double(alpha)
+        lib().orc_inversion_step(C.byref(self.m), d(p), C.c_double(slack), d(per), C.byref(a))
+        return a.value, per
+
+
+def svd3(F):
+    F = np.ascontiguousarray(F, dtype=np.float64).ravel()
+    U, S, V = np.empty(9), np.empty(3), np.empty(9)
+    lib().orc_svd3(d(F), d(U), d(S), d(V))
+    return U.reshape(3, 3), S, V.reshape(3, 3)
+
+
+def psi(et, S, mu, lam):
+    S = np.ascontiguousarray(S, dtype=np.float64)
+    E = C.c_double()
+    lib().orc_psi(et, d(S), C.c_double(mu), C.c_double(lam), C.byref(E))
+    return E.value
+
+
+def dpsi(et, S, mu, lam):
+    S = np.ascontiguousarray(S, dtype=np.float64)
+    out = np.empty(3)
+    lib().orc_dpsi(et, d(S), C.c_double(mu), C.c_double(lam), d(out))
+    return out
+
+
+def d2psi(et, S, mu, lam):
+    S = np.ascontiguousarray(S, dtype=np.float64)
+    out = np.empty(9)
+    lib().orc_d2psi(et, d(S), C.c_double(mu), C.c_double(lam), d(out))
+    return out.reshape(3, 3)
+
+
+def pk1(et, F, mu, lam):
+    U, S, V = svd3(F)
+    P = np.empty(9)
+    lib().orc_pk1(et, d(np.ascontiguousarray(F).ravel()), d(U.ravel().copy()), d(S), d(V.ravel().copy()), C.c_double(mu), C.c_double(lam), d(P))
+    return P.reshape(3, 3)
+
+
+def dPdF(et, F, mu, lam, w=1.0, projectSPD=0):
+    U, S, V = svd3(F)
+    out = np.empty(81)
+    lib().orc_dPdF(et, d(U.ravel().copy()), d(S), d(V.ravel().copy()), C.c_double(mu), C.c_double(lam), C.c_double(w), projectSPD, d(out))
+    return out.reshape(9, 9)
+
+
+def makePD(M):
+    M = np.ascontiguousarray(M, dtype=np.float64).copy()
+    lib().orc_makePD(M.shape[0], d(M))
+    return M
+
+
+def blocks78_to_dense(h78, tet):
+    """Rebuild the dense symmetric 12x12 from the kernel's 78-scalar block layout."""
+    H = np.zeros((12, 12))
+    k = 0
+    for a in range(4):
+        for i_ in range(3):
+            for r in range(i_, 3):
+                H[3 * a + i_, 3 * a + r] = H[3 * a + r, 3 * a + i_] = h78[k]
+                k += 1
+    for a in range(4):
+        for b in range(a + 1, 4):
+            blk = h78[k:k + 9].reshape(3, 3)
+            k += 9
+            if tet[a] > tet[b]:
+                blk = blk.T
+            H[3 * a:3 * a + 3, 3 * b:3 * b + 3] = blk
+            H[3 * b:3 * b + 3, 3 * a:3 * a + 3] = blk.T
+    return H
