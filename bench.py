@@ -1,0 +1,270 @@
+#!/usr/bin/env python
+"""bench.py -- Newton-iteration hot path (assembly + CCD) on the synthetic 1M-tet ball pile.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line on rank 0.
+  metric  : BASELINE.json's "Newton-iteration wall ms (assembly+CCD) @1M tets" -> value in ms (lower is better)
+  value   : device-timed (CUDA events on the launching stream), inputs/outputs resident in HBM
+  e2e     : same step through the C ABI with HOST buffers (pinned), H2D/D2H inside the timed region
+  roofline: dominant kernel (per-tet gradient/Hessian) algorithmic bytes / event time vs MEASURED_PEAKS.json
+  cpu_baseline / --impl reference: the oracle restatement of the reference CPU path (OpenMP over the reference's
+            TBB index spaces) on the box's host cores, on a bounded sample of the same workload.
+A "step" = one Newton iteration's hot stages at a fixed state:
+  computeEnergyVal + computeGradient + computePrecondMtr (elastic + mass [+ barrier]) + step-size bounds
+  (inversion filter [+ CCD]).  Stages in brackets join as their kernels land; `config.stages` lists what ran.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALG_BYTES_PER_TET = 208 + 624 + 96  # read stencil+material, write 78 upper-triangular scalars + 12 gradient scalars
+DT2 = 0.025 ** 2
+
+
+def build_scene(args):
+    from ipc_b200 import scenes
+    n_balls = max(1, int(round(args.tets / (6 * args.res ** 3))))
+    m, info = scenes.ball_pile(n_balls, res=args.res, seed=5, energy=0)
+    return m, info
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons during the timed region."""
+
+    def __init__(self, device):
+        super().__init__(daemon=True)
+        self.device = device
+        self.samples = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.samples.append([x.strip() for x in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for k, nm in enumerate(names):
+                if len(s) > 3 + k and s[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_step(m, info, nthreads):
+    """One Newton-iteration hot path on the CPU oracle (same stages as the GPU step)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle as orc
+    o = orc.Elastic(m)
+    ia, ja = m.csr_pattern(1)
+    t0 = time.perf_counter()
+    o.energy(DT2, nthreads)
+    o.gradient(DT2, 1, nthreads)
+    o.hessian_csr(DT2, ia, ja, 1, 1, 1, nthreads=nthreads)
+    o.inversion_step(info["p"], 0.2, 1.0)
+    return (time.perf_counter() - t0) * 1e3
+
+
+def cpu_baseline(args, full_tets):
+    """Bounded sample of the same workload on the host cores; linear extrapolation to the full tet count."""
+    from ipc_b200 import scenes
+    cores = os.cpu_count() or 1
+    n_balls = max(1, int(round(args.cpu_sample_tets / (6 * args.res ** 3))))
+    m, info = scenes.ball_pile(n_balls, res=args.res, seed=5, energy=0)
+    oracle_step(m, info, cores)  # warm-up (page-in, thread pool)
+    ms = min(oracle_step(m, info, cores) for _ in range(2))
+    scale = full_tets / m.nT
+    return {"value": ms * scale, "unit": "ms", "cores": cores, "kind": "port",
+            "sample": f"{m.nT} of {full_tets} tets ({n_balls} balls), measured {ms:.1f} ms, extrapolated x{scale:.2f}; "
+                      f"oracle restatement of the reference CPU path, OpenMP over the reference's TBB loops (assembly scatter serial as in the reference)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    full_tets = int(round(args.tets / (6 * args.res ** 3))) * 6 * args.res ** 3
+    from ipc_b200 import scenes
+    cores = os.cpu_count() or 1
+    n_balls = max(1, int(round(args.cpu_sample_tets / (6 * args.res ** 3))))
+    m, info = scenes.ball_pile(n_balls, res=args.res, seed=5, energy=0)
+    for _ in range(args.warmup):
+        oracle_step(m, info, cores)
+    t = [oracle_step(m, info, cores) for _ in range(args.steps)]
+    scale = full_tets / m.nT
+    ms = float(np.mean(t)) * scale
+    line = {"impl": "reference", "metric": "newton_iteration_ms_assembly_ccd", "value": ms, "unit": "ms", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": f"synthetic 1M-tet ball pile ({full_tets} tets), NeoHookean", "stages": STAGES_RUN},
+            "cpu_baseline": {"value": ms, "unit": "ms", "cores": cores, "kind": "port",
+                             "sample": f"each step = {m.nT} of {full_tets} tets, extrapolated x{scale:.2f}"},
+            "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+STAGES_RUN = ["elastic_energy", "elastic_gradient", "elastic_hessian+mass->CSR", "inversion_step_bound"]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--tets", type=int, default=1_000_000)
+    ap.add_argument("--res", type=int, default=10, help="ball resolution: 6*res^3 tets per ball")
+    ap.add_argument("--cpu-sample-tets", type=int, default=120_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from ipc_b200 import lib as L
+    m, info = build_scene(args)
+    ctx = L.Context(local_rank)
+    if world > 1:
+        ids = [L.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.comm_init(rank, world, ids[0])
+    ctx.set_mesh(m.V_rest_soa, m.T_soa, m.restTriInv, m.vol, m.mu, m.lam, m.mass, m.dbc, m.energy)
+    ia, ja = m.csr_pattern(1)
+    ctx.set_csr(ia, ja, 1)
+    nnz = ja.size
+
+    # pinned host buffers for the e2e path
+    hV = L.PinnedArray(3 * m.nV); hV.array[:] = m.V_soa
+    hp = L.PinnedArray(3 * m.nV); hp.array[:] = info["p"]
+    hg = L.PinnedArray(3 * m.nV)
+    ha = L.PinnedArray(nnz)
+    ctx.set_state(hV.array)
+    ctx.step_forward(hp.array, 0.0)  # uploads the search direction once (device-resident for the HBM mode)
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            import torch
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step_device():
+        ctx.elastic_energy(DT2, 1, want=False)
+        ctx.elastic_grad_hess(DT2, 1, 1, 1, None, None)
+        ctx.inversion_step(None, 0.2, 1.0)
+
+    def step_e2e():
+        ctx.set_state(hV.array)
+        ctx.elastic_energy(DT2, 1, want=True)
+        ctx.elastic_grad_hess(DT2, 1, 1, 1, hg.array, ha.array)
+        ctx.inversion_step(hp.array, 0.2, 1.0)
+
+    # ---- device-resident timing --------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    n0 = ctx.launch_count()
+    ctx.profile(1)
+    barrier()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        step_device()
+    ms_total = ctx.timer_stop()
+    barrier()
+    launches = ctx.launch_count() - n0
+    prof = ctx.profile_read()
+    ctx.profile(0)
+    clocks = sampler.finish() if sampler else None
+    ms_step = ms_total / args.steps
+
+    # ---- end-to-end timing (host buffers through the C ABI) -----------------------------------------
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        step_e2e()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms_step, e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        tet_ms, tet_n = prof.get("elastic_tet", (0.0, 1))
+        local_tets = m.nT // world
+        per_launch_s = tet_ms / max(tet_n, 1) * 1e-3
+        achieved = ALG_BYTES_PER_TET * local_tets / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
+        line = {
+            "metric": "newton_iteration_ms_assembly_ccd", "value": ms_step, "unit": "ms", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"synthetic 1M-tet ball pile ({m.nT} tets, {m.nV} verts, {info['n_balls']} balls), NeoHookean, dt=0.025",
+                       "stages": STAGES_RUN, "csr_nnz": int(nnz), "l2": "working set (78 doubles/tet = %.0f MB + CSR %.0f MB) exceeds the 126 MB L2" % (m.nT * 624 / 1e6, nnz * 8 / 1e6),
+                       "partition": f"tets block-partitioned over {world} rank(s); NCCL sum-allreduce of [gradient, CSR values], min-allreduce of the step"},
+            "stage_ms": {k: v[0] / args.steps for k, v in prof.items()},
+            "roofline": {"bound": "hbm", "kernel": "k_elastic_grad_hess<NH,g,H>", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                         "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_tet": ALG_BYTES_PER_TET, "kernel_ms": tet_ms / max(tet_n, 1)},
+            "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(2 * 3 * m.nV * 8), "d2h_bytes_per_step": int((3 * m.nV + nnz) * 8 + 16)},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args, m.nT)
+        print(json.dumps(line))
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

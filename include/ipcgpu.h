@@ -113,6 +113,29 @@ int ipcgpu_download(ipcgpu_ctx* ctx, int which, double* dst, uint64_t count);
 /* raw device pointer of a result buffer (for a device-side linear solver) */
 void* ipcgpu_device_ptr(ipcgpu_ctx* ctx, int which);
 
+/* ---- device-side timing (CUDA events on the context's own stream; bench.py's roofline numbers) ---------- */
+enum {
+    IPCGPU_STAGE_ELASTIC_ENERGY = 0,
+    IPCGPU_STAGE_ELASTIC_TET = 1,     /* per-tet gradient/Hessian kernel */
+    IPCGPU_STAGE_GATHER_GRADIENT = 2,
+    IPCGPU_STAGE_ASSEMBLE_CSR = 3,
+    IPCGPU_STAGE_INVERSION = 4,
+    IPCGPU_STAGE_HASH = 5,
+    IPCGPU_STAGE_CONSTRAINT_SET = 6,
+    IPCGPU_STAGE_BARRIER = 7,
+    IPCGPU_STAGE_CCD_BROAD = 8,
+    IPCGPU_STAGE_CCD_NARROW = 9,
+    IPCGPU_STAGE_ALLREDUCE = 10,
+    IPCGPU_STAGE_COUNT = 11
+};
+/* enable=1 starts recording an event pair around every stage launch (and clears old records) */
+int ipcgpu_profile(ipcgpu_ctx* ctx, int enable);
+/* synchronises, then returns the summed device time and launch count of one stage since ipcgpu_profile(ctx,1) */
+int ipcgpu_profile_read(ipcgpu_ctx* ctx, int stage, double* total_ms, int* count);
+/* whole-region device timer on the context stream */
+int ipcgpu_timer_start(ipcgpu_ctx* ctx);
+int ipcgpu_timer_stop(ipcgpu_ctx* ctx, double* ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -305,7 +305,9 @@ int ipcgpu_elastic_energy(ipcgpu_ctx* ctx, double coef, int /*redoSVD*/, double*
 {
     REQUIRE(ctx->maps_ready, IPCGPU_ERR_STATE, "ipcgpu_set_mesh first");
     CK(cudaSetDevice(ctx->device));
+    cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_ELASTIC_ENERGY);
     elastic_energy(ctx->eargs(), ctx->e_per_tet.p, ctx->partials.p, coef, ctx->scalar_out.p, ctx->stream);
+    ctx->prof_end(pe);
     ctx->launches += 2;
     if (ctx->nranks > 1) {
         int r = g_nccl.AllReduce(ctx->scalar_out.p, ctx->scalar_out.p, 1, kNcclFloat64, kNcclSum, ctx->nccl_comm, ctx->stream);
@@ -327,17 +329,23 @@ static int run_grad_hess(ipcgpu_ctx* ctx, double coef, int projectSPD, int proje
         int rc = ensure_offsets(ctx);
         if (rc) return rc;
     }
+    cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_ELASTIC_TET);
     elastic_grad_hess(ctx->eargs(), coef, projectSPD, need_g, need_h, ctx->gcont.p, ctx->hblk.p, ctx->stream);
+    ctx->prof_end(pe);
     ++ctx->launches;
     if (need_g) {
+        pe = ctx->prof_begin(IPCGPU_STAGE_GATHER_GRADIENT);
         gather_gradient(ctx->nV, ctx->inc_ptr.p, ctx->inc.p, ctx->gcont.p, ctx->has_dbc ? ctx->dbc.p : nullptr, projectDBC, 0, ctx->g.p, ctx->stream);
+        ctx->prof_end(pe);
         ++ctx->launches;
     }
     if (need_h) {
         // the mass term is added by rank 0 only so that the cross-rank sum counts it once
         const double* m = (add_mass && ctx->has_mass && ctx->rank == 0) ? ctx->mass.p : nullptr;
+        pe = ctx->prof_begin(IPCGPU_STAGE_ASSEMBLE_CSR);
         assemble_csr(ctx->nSlots, ctx->slot_v.p, ctx->slot_u.p, ctx->slot_off.p, ctx->con_ptr.p, ctx->con_src.p, ctx->hblk.p,
             ctx->has_dbc ? ctx->dbc.p : nullptr, projectDBC, m, accumulate_a ? 1 : 0, ctx->a.p, ctx->stream);
+        ctx->prof_end(pe);
         ++ctx->launches;
     }
     CK(cudaGetLastError());
@@ -402,7 +410,9 @@ int ipcgpu_inversion_step(ipcgpu_ctx* ctx, const double* p, double slack, double
     if (p) CK(cudaMemcpyAsync(ctx->dir.p, p, (size_t)3 * ctx->nV * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     const unsigned long long init = 0x7ff0000000000000ull; // +inf
     CK(cudaMemcpyAsync(ctx->min_ord.p, &init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_INVERSION);
     inversion_step(ctx->eargs(), ctx->dir.p, slack, ctx->inv_steps.p, ctx->min_ord.p, ctx->stream);
+    ctx->prof_end(pe);
     ++ctx->launches;
     if (ctx->nranks > 1) {
         int r = g_nccl.AllReduce(ctx->min_ord.p, ctx->min_ord.p, 1, kNcclUint64, kNcclMin, ctx->nccl_comm, ctx->stream);
@@ -428,6 +438,7 @@ int ipcgpu_allreduce_grad_hess(ipcgpu_ctx* ctx, int with_gradient, int with_hess
 {
     if (ctx->nranks <= 1) return IPCGPU_OK;
     REQUIRE(ctx->nccl_comm != nullptr, IPCGPU_ERR_STATE, "ipcgpu_comm_init first");
+    cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_ALLREDUCE);
     if (with_gradient) {
         int r = g_nccl.AllReduce(ctx->g.p, ctx->g.p, (size_t)3 * ctx->nV, kNcclFloat64, kNcclSum, ctx->nccl_comm, ctx->stream);
         REQUIRE(r == 0, IPCGPU_ERR_NCCL, "ncclAllReduce(gradient) failed");
@@ -436,6 +447,57 @@ int ipcgpu_allreduce_grad_hess(ipcgpu_ctx* ctx, int with_gradient, int with_hess
         int r = g_nccl.AllReduce(ctx->a.p, ctx->a.p, (size_t)ctx->nnz, kNcclFloat64, kNcclSum, ctx->nccl_comm, ctx->stream);
         REQUIRE(r == 0, IPCGPU_ERR_NCCL, "ncclAllReduce(csr values) failed");
     }
+    ctx->prof_end(pe);
+    return IPCGPU_OK;
+}
+
+int ipcgpu_profile(ipcgpu_ctx* ctx, int enable)
+{
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int s = 0; s < IPCGPU_STAGE_COUNT; ++s) {
+        for (auto& pr : ctx->prof[s]) {
+            cudaEventDestroy(pr.first);
+            cudaEventDestroy(pr.second);
+        }
+        ctx->prof[s].clear();
+    }
+    ctx->profiling = enable != 0;
+    return IPCGPU_OK;
+}
+
+int ipcgpu_profile_read(ipcgpu_ctx* ctx, int stage, double* total_ms, int* count)
+{
+    REQUIRE(stage >= 0 && stage < IPCGPU_STAGE_COUNT && total_ms && count, IPCGPU_ERR_ARG, "bad stage");
+    CK(cudaStreamSynchronize(ctx->stream));
+    double tot = 0.0;
+    for (auto& pr : ctx->prof[stage]) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        tot += ms;
+    }
+    *total_ms = tot;
+    *count = (int)ctx->prof[stage].size();
+    return IPCGPU_OK;
+}
+
+int ipcgpu_timer_start(ipcgpu_ctx* ctx)
+{
+    if (!ctx->timer_a) {
+        CK(cudaEventCreate(&ctx->timer_a));
+        CK(cudaEventCreate(&ctx->timer_b));
+    }
+    CK(cudaEventRecord(ctx->timer_a, ctx->stream));
+    return IPCGPU_OK;
+}
+
+int ipcgpu_timer_stop(ipcgpu_ctx* ctx, double* ms)
+{
+    REQUIRE(ctx->timer_a && ms, IPCGPU_ERR_STATE, "ipcgpu_timer_start first");
+    CK(cudaEventRecord(ctx->timer_b, ctx->stream));
+    CK(cudaEventSynchronize(ctx->timer_b));
+    float f = 0.f;
+    CK(cudaEventElapsedTime(&f, ctx->timer_a, ctx->timer_b));
+    *ms = f;
     return IPCGPU_OK;
 }
 

@@ -80,6 +80,25 @@ struct ipcgpu_ctx {
     ipcgpu::DevBuf<unsigned long long> min_ord;
     double* h_scalar = nullptr; // pinned staging for scalars (4 doubles)
 
+    // profiling: event pairs per stage (only when enabled)
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof[16];
+    cudaEvent_t timer_a = nullptr, timer_b = nullptr;
+    cudaEvent_t prof_begin(int stage)
+    {
+        if (!profiling) return nullptr;
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        prof[stage].emplace_back(a, b);
+        cudaEventRecord(a, stream);
+        return b;
+    }
+    void prof_end(cudaEvent_t b)
+    {
+        if (b) cudaEventRecord(b, stream);
+    }
+
     ipcgpu::ElasticArgs eargs() const
     {
         ipcgpu::ElasticArgs p;

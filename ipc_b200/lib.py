@@ -45,7 +45,14 @@ SIGNATURES = {
     "ipcgpu_allreduce_grad_hess": (C.c_int, [_ctxp, C.c_int, C.c_int]),
     "ipcgpu_download": (C.c_int, [_ctxp, C.c_int, _dp, C.c_uint64]),
     "ipcgpu_device_ptr": (C.c_void_p, [_ctxp, C.c_int]),
+    "ipcgpu_profile": (C.c_int, [_ctxp, C.c_int]),
+    "ipcgpu_profile_read": (C.c_int, [_ctxp, C.c_int, _dp, _ip]),
+    "ipcgpu_timer_start": (C.c_int, [_ctxp]),
+    "ipcgpu_timer_stop": (C.c_int, [_ctxp, _dp]),
 }
+
+STAGES = ["elastic_energy", "elastic_tet", "gather_gradient", "assemble_csr", "inversion", "hash", "constraint_set", "barrier",
+          "ccd_broad", "ccd_narrow", "allreduce"]
 
 _lib = None
 
@@ -197,6 +204,26 @@ class Context:
         a = C.c_double(alpha)
         self._ck(self.lib.ipcgpu_inversion_step(self.h, _d(f64(p)) if p is not None else None, slack, C.byref(a)))
         return a.value
+
+    def profile(self, enable):
+        self._ck(self.lib.ipcgpu_profile(self.h, int(enable)))
+
+    def profile_read(self):
+        out = {}
+        for k, name in enumerate(STAGES):
+            ms, n = C.c_double(), C.c_int()
+            self._ck(self.lib.ipcgpu_profile_read(self.h, k, C.byref(ms), C.byref(n)))
+            if n.value:
+                out[name] = (ms.value, n.value)
+        return out
+
+    def timer_start(self):
+        self._ck(self.lib.ipcgpu_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._ck(self.lib.ipcgpu_timer_stop(self.h, C.byref(ms)))
+        return ms.value
 
     def csr_set_zero(self):
         self._ck(self.lib.ipcgpu_csr_set_zero(self.h))
