@@ -158,3 +158,118 @@ def blocks78_to_dense(h78, tet):
             H[3 * a:3 * a + 3, 3 * b:3 * b + 3] = blk
             H[3 * b:3 * b + 3, 3 * a:3 * a + 3] = blk.T
     return H
+
+
+# ---- contact pair math -------------------------------------------------------------------------------------------
+def _vec(name, v, n):
+    v = np.ascontiguousarray(v, dtype=np.float64).ravel()
+    out = np.empty(n)
+    getattr(lib(), name)(d(v), d(out))
+    return out
+
+
+def d_pair(kind, v):
+    return float(_vec("orc_d_" + kind, v, 1)[0])
+
+
+def g_pair(kind, v):
+    return _vec("orc_g_" + kind, v, {"PP": 6, "PE": 9, "PT": 12, "EE": 12}[kind])
+
+
+def H_pair(kind, v):
+    n = {"PP": 6, "PE": 9, "PT": 12, "EE": 12}[kind]
+    return _vec("orc_H_" + kind, v, n * n).reshape(n, n)
+
+
+def dType_PT(v):
+    return lib().orc_dType_PT(d(np.ascontiguousarray(v, dtype=np.float64).ravel()))
+
+
+def dType_EE(v):
+    return lib().orc_dType_EE(d(np.ascontiguousarray(v, dtype=np.float64).ravel()))
+
+
+def point_tri_d(v):
+    return float(_vec("orc_point_tri_d", v, 1)[0])
+
+
+def edge_edge_d(v):
+    return float(_vec("orc_edge_edge_d", v, 1)[0])
+
+
+def barrier(dist, dHat):
+    b, g, H = C.c_double(), C.c_double(), C.c_double()
+    lib().orc_barrier(C.c_double(dist), C.c_double(dHat), C.byref(b), C.byref(g), C.byref(H))
+    return b.value, g.value, H.value
+
+
+def ee_cross(v):
+    v = np.ascontiguousarray(v, dtype=np.float64).ravel()
+    c = C.c_double()
+    g, H = np.empty(12), np.empty(144)
+    lib().orc_ee_cross(d(v), C.byref(c), d(g), d(H))
+    return c.value, g, H.reshape(12, 12)
+
+
+def mollifier(v, eps_x):
+    v = np.ascontiguousarray(v, dtype=np.float64).ravel()
+    e = C.c_double()
+    g, H = np.empty(12), np.empty(144)
+    lib().orc_mollifier(d(v), C.c_double(eps_x), C.byref(e), d(g), d(H))
+    return e.value, g, H.reshape(12, 12)
+
+
+class OrcSurf(C.Structure):
+    _fields_ = [("nV", C.c_int), ("V", _dp), ("Vrest", _dp), ("dbc", _u8p), ("nSV", C.c_int), ("SVI", _ip), ("nSE", C.c_int), ("SE", _ip),
+                ("nSF", C.c_int), ("SF", _ip), ("vCoDim", _ip)]
+
+
+class Surf:
+    def __init__(self, mesh, V=None):
+        self.mesh = mesh
+        self.V = np.ascontiguousarray((mesh.V if V is None else V).T).ravel().astype(np.float64)
+        self.Vr = np.ascontiguousarray(mesh.V_rest.T).ravel().astype(np.float64)
+        self.dbc = np.ascontiguousarray(mesh.dbc, dtype=np.uint8)
+        self.SVI = np.ascontiguousarray(mesh.SVI, dtype=np.int32)
+        self.SE = np.ascontiguousarray(mesh.SFEdges, dtype=np.int32).ravel()
+        self.SF = np.ascontiguousarray(mesh.SF.T, dtype=np.int32).ravel()
+        self.cod = np.ascontiguousarray(mesh.vCoDim, dtype=np.int32)
+        self.s = OrcSurf(mesh.nV, d(self.V), d(self.Vr), self.dbc.ctypes.data_as(_u8p), self.SVI.size, i(self.SVI), self.SE.size // 2, i(self.SE),
+                         self.SF.size // 3, i(self.SF), i(self.cod))
+
+    def constraint_set(self, dHat, nthreads=1, cap=1 << 20):
+        mm = np.empty((cap, 4), dtype=np.int32); pa = np.empty((cap, 4), dtype=np.int32); pe = np.empty((cap, 2), dtype=np.int32)
+        cand = np.empty((4 * cap, 2), dtype=np.int32)
+        nC, nP, nK = C.c_int(), C.c_int(), C.c_int()
+        rc = lib().orc_constraint_set(C.byref(self.s), C.c_double(dHat), cap, i(mm), C.byref(nC), cap, i(pa), i(pe), C.byref(nP),
+                                      4 * cap, i(cand), C.byref(nK), nthreads)
+        assert rc == 0, "oracle constraint-set capacity exceeded"
+        return mm[:nC.value].copy(), pa[:nP.value].copy(), pe[:nP.value].copy(), cand[:nK.value].copy()
+
+    def barrier_energy(self, mm, pa, pe, dHat, kappa):
+        E = C.c_double()
+        mm, pa, pe = (np.ascontiguousarray(x, dtype=np.int32) for x in (mm, pa, pe))
+        bad = lib().orc_barrier_energy(C.byref(self.s), i(mm), len(mm), i(pa), i(pe), len(pa), C.c_double(dHat), C.c_double(kappa), C.byref(E))
+        return E.value, bad
+
+    def barrier_gradient(self, mm, pa, pe, dHat, kappa, g=None):
+        if g is None:
+            g = np.zeros(3 * self.mesh.nV)
+        mm, pa, pe = (np.ascontiguousarray(x, dtype=np.int32) for x in (mm, pa, pe))
+        lib().orc_barrier_gradient(C.byref(self.s), i(mm), len(mm), i(pa), i(pe), len(pa), C.c_double(dHat), C.c_double(kappa), 1, d(g))
+        return g
+
+    def barrier_hessian_csr(self, mm, pa, pe, dHat, kappa, ia, ja, base, projectDBC=1, a=None, nthreads=1):
+        ia = np.ascontiguousarray(ia, dtype=np.int32); ja = np.ascontiguousarray(ja, dtype=np.int32)
+        if a is None:
+            a = np.zeros(ja.size)
+        mm, pa, pe = (np.ascontiguousarray(x, dtype=np.int32) for x in (mm, pa, pe))
+        lib().orc_barrier_hessian_csr(C.byref(self.s), i(mm), len(mm), i(pa), i(pe), len(pa), C.c_double(dHat), C.c_double(kappa), projectDBC,
+                                      i(ia), i(ja), base, d(a), nthreads)
+        return a
+
+    def pair_hessian(self, mm4, dHat, kappa):
+        H = np.empty(144); nv = C.c_int()
+        mm4 = np.ascontiguousarray(mm4, dtype=np.int32)
+        lib().orc_barrier_pair_hessian(C.byref(self.s), i(mm4), C.c_double(dHat), C.c_double(kappa), d(H), C.byref(nv))
+        return H.reshape(12, 12), nv.value
