@@ -105,6 +105,29 @@ int ipcgpu_elastic_grad_hess(ipcgpu_ctx* ctx, double coef, int projectSPD, int p
 /* Energy::filterStepSize (Energy.cpp:565-581) */
 int ipcgpu_inversion_step(ipcgpu_ctx* ctx, const double* p_interleaved, double slack, double* alpha_inout);
 
+/* ---- contact plug-in: SelfCollisionHandler<3> statics (SelfCollisionHandler.hpp:23-232) ------------------- */
+/* Surface arrays of Mesh<3>: SVI (Mesh.hpp:72), SFEdges as interleaved (first,second) pairs (Mesh.hpp:74), SF column-major
+ * (Mesh.hpp:70), optional per-vertex codimension (Mesh::vICoDim; NULL = all 3). */
+int ipcgpu_set_surface(ipcgpu_ctx* ctx, int nSV, const int* SVI, int nSE, const int* SFEdges, int nSF, const int* SF_soa, const int* vCoDim);
+/* capacity (entries) of the device-side pair lists; default 2^20. IPCGPU_ERR_CAPACITY is returned when exceeded. */
+int ipcgpu_set_pair_capacity(ipcgpu_ctx* ctx, int capacity);
+/* SelfCollisionHandler::computeConstraintSet (SelfCollisionHandler.cpp:2149-2478) with the broad phase of
+ * SpatialHash::build/query* (SpatialHash.hpp:46-229, 375-421) done on the device. The sets stay on the device (they feed the
+ * barrier_* calls and the partial CCD); sizes are returned.  Output order is canonical: every list sorted lexicographically. */
+int ipcgpu_constraint_set(ipcgpu_ctx* ctx, double dHat, int getPTEE, int* nC, int* nPara, int* nCand);
+/* copies of constraintSet (4 ints each, MMCVID encoding), paraEEMMCVIDSet (4), paraEEeIeJSet (2), cs_PTEE (2); any may be NULL */
+int ipcgpu_get_constraint_set(ipcgpu_ctx* ctx, int* mmcvid4, int* para4, int* para_eIeJ2, int* cand2);
+/* upload host-built sets instead (drop-in use of only the per-pair kernels) */
+int ipcgpu_set_constraint_set(ipcgpu_ctx* ctx, int nC, const int* mmcvid4, int nPara, const int* para4, const int* para_eIeJ2, int nCand, const int* cand2);
+/* kappa * [ sum mult*b(d) + sum e*b(d) ]  (evaluateConstraints :64-81 + Optimizer.cpp:3290-3353).
+ * Returns IPCGPU_ERR_NONPOSITIVE_DISTANCE where the reference would exit(0) (Optimizer.cpp:3296-3306). */
+int ipcgpu_barrier_energy(ipcgpu_ctx* ctx, double dHat, double kappa, double* E);
+/* g += kappa*J^T b' (+ mollified terms)  (leftMultiplyConstraintJacobianT :84-148, augmentParaEEGradient :2990-3045).
+ * g_inout != NULL: host vector uploaded, accumulated, downloaded; NULL: the device-resident gradient is accumulated. */
+int ipcgpu_barrier_gradient(ipcgpu_ctx* ctx, double dHat, double kappa, double* g_inout);
+/* CSR += makePD(kappa*mult*(b'' grad d grad d^T + b' hess d))  (augmentIPHessian :418-561, augmentParaEEHessian :3049-3201) */
+int ipcgpu_barrier_hessian(ipcgpu_ctx* ctx, double dHat, double kappa, int projectDBC, double* a_inout);
+
 /* LinSysSolver::setZero (LinSysSolver.hpp:348) on the device-resident value array */
 int ipcgpu_csr_set_zero(ipcgpu_ctx* ctx);
 /* cross-rank reductions over NVLink (no-ops on a single rank): sum of [gradient, CSR values], min of step */

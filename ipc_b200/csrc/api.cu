@@ -427,6 +427,143 @@ int ipcgpu_inversion_step(ipcgpu_ctx* ctx, const double* p, double slack, double
     return IPCGPU_OK;
 }
 
+// ---- contact ---------------------------------------------------------------------------------------------
+int contact_alloc(ipcgpu_ctx* ctx);                                                                 // constraint.cu
+int contact_constraint_set(ipcgpu_ctx* ctx, double dHat, int wantCand, int* nC, int* nPara, int* nCand); // constraint.cu
+
+int ipcgpu_set_surface(ipcgpu_ctx* ctx, int nSV, const int* SVI, int nSE, const int* SE, int nSF, const int* SF, const int* vCoDim)
+{
+    REQUIRE(ctx->nV > 0, IPCGPU_ERR_STATE, "ipcgpu_set_mesh first");
+    REQUIRE(nSV >= 0 && nSE >= 0 && nSF >= 0 && (nSV == 0 || SVI) && (nSE == 0 || SE) && (nSF == 0 || SF), IPCGPU_ERR_ARG, "ipcgpu_set_surface: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    for (int i = 0; i < nSV; ++i) REQUIRE(SVI[i] >= 0 && SVI[i] < ctx->nV, IPCGPU_ERR_ARG, "SVI out of range");
+    for (int i = 0; i < 2 * nSE; ++i) REQUIRE(SE[i] >= 0 && SE[i] < ctx->nV, IPCGPU_ERR_ARG, "SFEdges out of range");
+    for (size_t i = 0; i < (size_t)3 * nSF; ++i) REQUIRE(SF[i] >= 0 && SF[i] < ctx->nV, IPCGPU_ERR_ARG, "SF out of range");
+    ctx->nSV = nSV; ctx->nSE = nSE; ctx->nSF = nSF;
+    bool ok = ctx->SVI.upload(SVI, std::max(nSV, 0), ctx->stream) && ctx->SE.upload(SE, (size_t)2 * nSE, ctx->stream) && ctx->SF.upload(SF, (size_t)3 * nSF, ctx->stream);
+    REQUIRE(ok, IPCGPU_ERR_CUDA, "surface upload failed");
+    ctx->has_codim = vCoDim != nullptr;
+    if (vCoDim) REQUIRE(ctx->vCoDim.upload(vCoDim, ctx->nV, ctx->stream), IPCGPU_ERR_CUDA, "codim upload failed");
+    CK(cudaStreamSynchronize(ctx->stream));
+    int rc = contact_alloc(ctx);
+    if (rc) return rc;
+    ctx->surface_ready = true;
+    return IPCGPU_OK;
+}
+
+int ipcgpu_set_pair_capacity(ipcgpu_ctx* ctx, int capacity)
+{
+    REQUIRE(capacity > 0, IPCGPU_ERR_ARG, "capacity must be positive");
+    ctx->pair_capacity = capacity;
+    if (ctx->surface_ready) return contact_alloc(ctx);
+    return IPCGPU_OK;
+}
+
+int ipcgpu_constraint_set(ipcgpu_ctx* ctx, double dHat, int getPTEE, int* nC, int* nPara, int* nCand)
+{
+    REQUIRE(ctx->surface_ready, IPCGPU_ERR_STATE, "ipcgpu_set_surface first");
+    REQUIRE(dHat > 0.0, IPCGPU_ERR_ARG, "dHat must be positive");
+    CK(cudaSetDevice(ctx->device));
+    return contact_constraint_set(ctx, dHat, getPTEE, nC, nPara, nCand);
+}
+
+int ipcgpu_get_constraint_set(ipcgpu_ctx* ctx, int* mm, int* para, int* para_e, int* cand)
+{
+    REQUIRE(ctx->surface_ready, IPCGPU_ERR_STATE, "ipcgpu_set_surface first");
+    ContactWork& w = ctx->cw;
+    if (mm && w.nC) CK(cudaMemcpyAsync(mm, w.act.p, (size_t)w.nC * sizeof(int4), cudaMemcpyDeviceToHost, ctx->stream));
+    if (para && w.nP) CK(cudaMemcpyAsync(para, w.para.p, (size_t)w.nP * sizeof(int4), cudaMemcpyDeviceToHost, ctx->stream));
+    if (para_e && w.nP) CK(cudaMemcpyAsync(para_e, w.para_e.p, (size_t)w.nP * sizeof(int2), cudaMemcpyDeviceToHost, ctx->stream));
+    if (cand && w.nK) CK(cudaMemcpyAsync(cand, w.cand.p, (size_t)w.nK * sizeof(int2), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return IPCGPU_OK;
+}
+
+int ipcgpu_set_constraint_set(ipcgpu_ctx* ctx, int nC, const int* mm, int nP, const int* para, const int* para_e, int nK, const int* cand)
+{
+    REQUIRE(ctx->surface_ready, IPCGPU_ERR_STATE, "ipcgpu_set_surface first");
+    ContactWork& w = ctx->cw;
+    REQUIRE(nC >= 0 && nP >= 0 && nK >= 0 && nC <= w.cap && nP <= w.cap && nK <= 4 * w.cap, IPCGPU_ERR_CAPACITY, "set exceeds the pair capacity");
+    if (nC) CK(cudaMemcpyAsync(w.act.p, mm, (size_t)nC * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
+    if (nP) CK(cudaMemcpyAsync(w.para.p, para, (size_t)nP * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
+    if (nP) CK(cudaMemcpyAsync(w.para_e.p, para_e, (size_t)nP * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+    if (nK) CK(cudaMemcpyAsync(w.cand.p, cand, (size_t)nK * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    w.nC = nC; w.nP = nP; w.nK = nK;
+    return IPCGPU_OK;
+}
+
+static BarrierArgs barrier_args(ipcgpu_ctx* ctx, double dHat, double kappa, int projectDBC)
+{
+    BarrierArgs p;
+    p.nV = ctx->nV; p.V = ctx->V.p; p.Vrest = ctx->Vrest.p; p.dbc = ctx->has_dbc ? ctx->dbc.p : nullptr; p.SE = ctx->SE.p;
+    p.cs = ctx->cw.act.p; p.nC = ctx->cw.nC; p.para = ctx->cw.para.p; p.para_e = ctx->cw.para_e.p; p.nP = ctx->cw.nP;
+    p.dHat = dHat; p.kappa = kappa; p.projectDBC = projectDBC;
+    p.ia = ctx->ia.p; p.ja = ctx->ja.p; p.base = ctx->index_base;
+    return p;
+}
+
+int ipcgpu_barrier_energy(ipcgpu_ctx* ctx, double dHat, double kappa, double* E)
+{
+    REQUIRE(ctx->surface_ready, IPCGPU_ERR_STATE, "ipcgpu_set_surface first");
+    CK(cudaSetDevice(ctx->device));
+    BarrierArgs p = barrier_args(ctx, dHat, kappa, 0);
+    const int n = p.nC + p.nP;
+    const int nb = barrier_energy_blocks(n);
+    ALLOC(ctx->bpartials, (size_t)std::max(nb, 1));
+    CK(cudaMemsetAsync(ctx->flag.p, 0, sizeof(int), ctx->stream));
+    cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_BARRIER);
+    barrier_energy(p, ctx->bpartials.p, ctx->flag.p, ctx->stream);
+    reduce_sum(ctx->bpartials.p, nb, kappa, ctx->scalar_out.p + 1, ctx->stream);
+    ctx->prof_end(pe);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    int* hf = reinterpret_cast<int*>(ctx->h_scalar + 4);
+    CK(cudaMemcpyAsync(ctx->h_scalar, ctx->scalar_out.p + 1, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hf, ctx->flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (E) *E = ctx->h_scalar[0];
+    REQUIRE(*hf == 0, IPCGPU_ERR_NONPOSITIVE_DISTANCE, "a constraint has d <= 0 (the reference exits here, Optimizer.cpp:3296-3306)");
+    return IPCGPU_OK;
+}
+
+int ipcgpu_barrier_gradient(ipcgpu_ctx* ctx, double dHat, double kappa, double* g_inout)
+{
+    REQUIRE(ctx->surface_ready, IPCGPU_ERR_STATE, "ipcgpu_set_surface first");
+    CK(cudaSetDevice(ctx->device));
+    if (g_inout) CK(cudaMemcpyAsync(ctx->g.p, g_inout, (size_t)3 * ctx->nV * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_BARRIER);
+    barrier_gradient(barrier_args(ctx, dHat, kappa, 0), ctx->g.p, ctx->stream);
+    ctx->prof_end(pe);
+    ++ctx->launches;
+    CK(cudaGetLastError());
+    if (g_inout) {
+        CK(cudaMemcpyAsync(g_inout, ctx->g.p, (size_t)3 * ctx->nV * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return IPCGPU_OK;
+}
+
+int ipcgpu_barrier_hessian(ipcgpu_ctx* ctx, double dHat, double kappa, int projectDBC, double* a_inout)
+{
+    REQUIRE(ctx->surface_ready, IPCGPU_ERR_STATE, "ipcgpu_set_surface first");
+    REQUIRE(ctx->nnz > 0, IPCGPU_ERR_STATE, "ipcgpu_set_csr first");
+    CK(cudaSetDevice(ctx->device));
+    if (a_inout) CK(cudaMemcpyAsync(ctx->a.p, a_inout, (size_t)ctx->nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->flag.p, 0, sizeof(int), ctx->stream));
+    cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_BARRIER);
+    barrier_hessian(barrier_args(ctx, dHat, kappa, projectDBC), ctx->a.p, ctx->flag.p, ctx->stream);
+    ctx->prof_end(pe);
+    ++ctx->launches;
+    CK(cudaGetLastError());
+    int* hf = reinterpret_cast<int*>(ctx->h_scalar + 4);
+    CK(cudaMemcpyAsync(hf, ctx->flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (a_inout) CK(cudaMemcpyAsync(a_inout, ctx->a.p, (size_t)ctx->nnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    REQUIRE(*hf == 0, IPCGPU_ERR_PATTERN, "CSR pattern misses a contact block: call ipcgpu_set_csr with the augmented pattern (augmentConnectivity, SelfCollisionHandler.cpp:330-415)");
+    return IPCGPU_OK;
+}
+
 int ipcgpu_csr_set_zero(ipcgpu_ctx* ctx)
 {
     REQUIRE(ctx->nnz > 0, IPCGPU_ERR_STATE, "ipcgpu_set_csr first");

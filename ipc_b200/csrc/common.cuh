@@ -4,14 +4,6 @@
 #include <cstdint>
 #include <cstdio>
 
-#define IPCGPU_OK 0
-#define IPCGPU_ERR_CUDA 1
-#define IPCGPU_ERR_ARG 2
-#define IPCGPU_ERR_PATTERN 3   // CSR pattern lacks an entry the assembly needs
-#define IPCGPU_ERR_NONPOSITIVE_DISTANCE 4
-#define IPCGPU_ERR_CAPACITY 5
-#define IPCGPU_ERR_NCCL 6
-#define IPCGPU_ERR_STATE 7
 
 #define HD __host__ __device__ __forceinline__
 #define DEV __device__ __forceinline__

@@ -1,0 +1,529 @@
+// constraint.cu -- barrier constraint-set build on the device (sm_100a).
+//
+// Replaces SelfCollisionHandler<3>::computeConstraintSet (src/CollisionObject/SelfCollisionHandler.cpp:2149-2478):
+// PT loop over surface vertices (:2168-2260), EE loop over surface edges (:2271-2407), candidate list cs_PTEE
+// (:2411-2424) and the serial std::map merge with PP/PE multiplicities (:2434-2476), including the three sentinel
+// encodings for nearly parallel edge pairs (:2305-2311, :2383-2388, :2455-2468).
+//
+// Pipeline (one stream, one host sync at the end to return the counts):
+//   boxes+bounds -> grid params -> emit (cell,id) -> CUB radix sort -> PT / EE queries (atomic append)
+//   -> run-length merge of PP/PE duplicates -> canonical lexicographic sort of every output list.
+// The output ORDER is canonical (sorted), unlike the reference whose order depends on unordered_set iteration and TBB
+// scheduling (:2176, :2282 "different constraint order will result in numerically different results").
+#include "broadphase.cuh"
+#include "context.h"
+#include "../../include/ipcgpu.h"
+#include <cub/cub.cuh>
+
+namespace ipcgpu {
+
+// ------------------------------------------------------------------------------------------------------------
+// boxes + global bounds.  bounds[0..2] = min (flipped order), bounds[3..5] = max, bounds[6] = max extent
+// ------------------------------------------------------------------------------------------------------------
+DEV V3 moved(const SurfArgs& s, const double* __restrict__ dir, double alpha, int v)
+{
+    V3 x = load_vertex(s.V, s.nV, v);
+    if (dir) x = x + alpha * V3{ __ldg(dir + 3 * (size_t)v), __ldg(dir + 3 * (size_t)v + 1), __ldg(dir + 3 * (size_t)v + 2) };
+    return x;
+}
+DEV void grow(Box& b, V3 x)
+{
+    b.lo[0] = fmin(b.lo[0], x.x); b.hi[0] = fmax(b.hi[0], x.x);
+    b.lo[1] = fmin(b.lo[1], x.y); b.hi[1] = fmax(b.hi[1], x.y);
+    b.lo[2] = fmin(b.lo[2], x.z); b.hi[2] = fmax(b.hi[2], x.z);
+}
+DEV Box empty_box()
+{
+    Box b;
+    for (int a = 0; a < 3; ++a) { b.lo[a] = 1e300; b.hi[a] = -1e300; }
+    return b;
+}
+
+// prim: 0 = surface vertices, 1 = edges, 2 = triangles.  swept: include x + alpha*dir
+__global__ void __launch_bounds__(256) k_boxes(SurfArgs s, int prim, const double* __restrict__ dir, double alpha, Box* __restrict__ boxes,
+    unsigned long long* __restrict__ bounds)
+{
+    const int n = prim == 0 ? s.nSV : (prim == 1 ? s.nSE : s.nSF);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    Box b = empty_box();
+    double ext = 0.0;
+    if (i < n) {
+        int v[3], nv;
+        if (prim == 0) { v[0] = s.SVI[i]; nv = 1; }
+        else if (prim == 1) { v[0] = s.SE[2 * i]; v[1] = s.SE[2 * i + 1]; nv = 2; }
+        else { v[0] = s.SF[i]; v[1] = s.SF[(size_t)s.nSF + i]; v[2] = s.SF[(size_t)2 * s.nSF + i]; nv = 3; }
+        for (int k = 0; k < nv; ++k) {
+            grow(b, load_vertex(s.V, s.nV, v[k]));
+            if (dir) grow(b, moved(s, dir, alpha, v[k]));
+        }
+        boxes[i] = b;
+        ext = fmax(fmax(b.hi[0] - b.lo[0], b.hi[1] - b.lo[1]), b.hi[2] - b.lo[2]);
+    }
+    // CTA reduction then one atomic per CTA per value
+    __shared__ double sm[7][8];
+    double vals[7] = { b.lo[0], b.lo[1], b.lo[2], b.hi[0], b.hi[1], b.hi[2], ext };
+#pragma unroll
+    for (int q = 0; q < 7; ++q) {
+        double x = vals[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double y = __shfl_xor_sync(0xffffffffu, x, o);
+            x = (q < 3) ? fmin(x, y) : fmax(x, y);
+        }
+        if ((threadIdx.x & 31) == 0) sm[q][threadIdx.x >> 5] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < 7) {
+        const int q = threadIdx.x;
+        double x = sm[q][0];
+        for (int w = 1; w < 8; ++w) x = (q < 3) ? fmin(x, sm[q][w]) : fmax(x, sm[q][w]);
+        if (q < 3) atomicMin(bounds + q, flip_ord(x));
+        else atomicMax(bounds + q, flip_ord(x));
+    }
+}
+
+__global__ void k_bounds_init(unsigned long long* bounds)
+{
+    if (threadIdx.x < 3) bounds[threadIdx.x] = ~0ull;
+    else if (threadIdx.x < 7) bounds[threadIdx.x] = 0ull;
+}
+
+__global__ void k_grid_params(const unsigned long long* __restrict__ bounds, double radius, Grid* __restrict__ g)
+{
+    if (threadIdx.x != 0) return;
+    double lo[3], hi[3];
+    for (int a = 0; a < 3; ++a) { lo[a] = unflip_ord(bounds[a]) - radius; hi[a] = unflip_ord(bounds[3 + a]) + radius; }
+    double ext = unflip_ord(bounds[6]);
+    double h = (ext + 2.0 * radius) * (1.0 + 1e-9);
+    const double span = fmax(fmax(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
+    h = fmax(h, span / 1024.0); // at most 1024 cells per axis
+    if (!(h > 0.0)) h = 1.0;
+    g->ox = lo[0]; g->oy = lo[1]; g->oz = lo[2];
+    g->inv_h = 1.0 / h;
+    g->nx = max(1, (int)floor((hi[0] - lo[0]) * g->inv_h) + 1);
+    g->ny = max(1, (int)floor((hi[1] - lo[1]) * g->inv_h) + 1);
+    g->nz = max(1, (int)floor((hi[2] - lo[2]) * g->inv_h) + 1);
+}
+
+// 8 slots per primitive; unused slots get the all-ones key so that they sort to the end
+__global__ void __launch_bounds__(256) k_emit(int n, const Box* __restrict__ boxes, const Grid* __restrict__ gp, unsigned long long* __restrict__ keys,
+    int* __restrict__ vals)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Grid g = *gp;
+    int c0[3], c1[3];
+    cell_range(g, boxes[i], c0, c1);
+    int k = 0;
+    for (int iz = c0[2]; iz <= c1[2] && iz <= c0[2] + 1; ++iz)
+        for (int iy = c0[1]; iy <= c1[1] && iy <= c0[1] + 1; ++iy)
+            for (int ix = c0[0]; ix <= c1[0] && ix <= c0[0] + 1; ++ix) {
+                keys[(size_t)8 * i + k] = cell_key(g, ix, iy, iz);
+                vals[(size_t)8 * i + k] = i;
+                ++k;
+            }
+    for (; k < 8; ++k) {
+        keys[(size_t)8 * i + k] = ~0ull;
+        vals[(size_t)8 * i + k] = -1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// queries
+// ------------------------------------------------------------------------------------------------------------
+struct CsOut {
+    int4* act; int* nAct; int capAct;     // PT / EE entries (slot3 >= 0)
+    int4* dup; int* nDup; int capDup;     // PP / PE entries to be counted (slot3 = -1)
+    int4* para; int2* para_e; int* nPara; int capPara;
+    int2* cand; int* nCand; int capCand;  // cs_PTEE (only when wanted)
+    int* overflow;
+};
+
+DEV void push4(int4* arr, int* cnt, int cap, int* overflow, int4 v)
+{
+    int i = atomicAdd(cnt, 1);
+    if (i < cap) arr[i] = v;
+    else atomicExch(overflow, 1);
+}
+
+DEV double box_gap2(const Box& a, const Box& b)
+{
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        double g = fmax(fmax(a.lo[k] - b.hi[k], b.lo[k] - a.hi[k]), 0.0);
+        s += g * g;
+    }
+    return s;
+}
+DEV bool is_dbc_v(const SurfArgs& s, int v) { return s.dbc && s.dbc[v] != 0; }
+DEV int codim_v(const SurfArgs& s, int v) { return s.vCoDim ? s.vCoDim[v] : 3; }
+
+// one thread per surface vertex  (:2168-2260)
+__global__ void __launch_bounds__(128) k_query_pt(SurfArgs s, const Grid* __restrict__ gp, const Box* __restrict__ tri_boxes,
+    const unsigned long long* __restrict__ keys, const int* __restrict__ vals, int nEntries, double dHat, double radius, int wantCand, CsOut out)
+{
+    const int svI = blockIdx.x * blockDim.x + threadIdx.x;
+    if (svI >= s.nSV) return;
+    const Grid g = *gp;
+    const int vI = s.SVI[svI];
+    const V3 p = load_vertex(s.V, s.nV, vI);
+    Box qb;
+    qb.lo[0] = p.x - radius; qb.lo[1] = p.y - radius; qb.lo[2] = p.z - radius;
+    qb.hi[0] = p.x + radius; qb.hi[1] = p.y + radius; qb.hi[2] = p.z + radius;
+    int c0[3], c1[3];
+    cell_range(g, qb, c0, c1);
+    const int vcod = codim_v(s, vI);
+    const bool vdbc = is_dbc_v(s, vI);
+    const double cull = dHat * (1.0 + 1e-9) + 1e-300;
+    for (int iz = c0[2]; iz <= c1[2]; ++iz)
+        for (int iy = c0[1]; iy <= c1[1]; ++iy)
+            for (int ix = c0[0]; ix <= c1[0]; ++ix) {
+                const unsigned long long key = cell_key(g, ix, iy, iz);
+                for (int e = lower_bound_u64(keys, nEntries, key); e < nEntries && keys[e] == key; ++e) {
+                    const int sfI = vals[e];
+                    const Box tb = tri_boxes[sfI];
+                    int t0[3], t1[3];
+                    cell_range(g, tb, t0, t1);
+                    if (max(t0[0], c0[0]) != ix || max(t0[1], c0[1]) != iy || max(t0[2], c0[2]) != iz) continue; // not the canonical cell
+                    Box pb;
+                    pb.lo[0] = pb.hi[0] = p.x; pb.lo[1] = pb.hi[1] = p.y; pb.lo[2] = pb.hi[2] = p.z;
+                    if (box_gap2(pb, tb) > cull) continue;
+                    const int a = s.SF[sfI], b = s.SF[(size_t)s.nSF + sfI], c = s.SF[(size_t)2 * s.nSF + sfI];
+                    if (vI == a || vI == b || vI == c) continue;
+                    if ((vcod < 3 && codim_v(s, a) < 3) || (vdbc && is_dbc_v(s, a) && is_dbc_v(s, b) && is_dbc_v(s, c))) continue;
+                    const V3 ta = load_vertex(s.V, s.nV, a), tb_ = load_vertex(s.V, s.nV, b), tc = load_vertex(s.V, s.nV, c);
+                    const int ty = dType_PT(p, ta, tb_, tc);
+                    double d;
+                    int4 q;
+                    switch (ty) {
+                    case 0: d = d_PP(p, ta); q = make_int4(-vI - 1, a, -1, -1); break;
+                    case 1: d = d_PP(p, tb_); q = make_int4(-vI - 1, b, -1, -1); break;
+                    case 2: d = d_PP(p, tc); q = make_int4(-vI - 1, c, -1, -1); break;
+                    case 3: d = d_PE(p, ta, tb_); q = make_int4(-vI - 1, a, b, -1); break;
+                    case 4: d = d_PE(p, tb_, tc); q = make_int4(-vI - 1, b, c, -1); break;
+                    case 5: d = d_PE(p, tc, ta); q = make_int4(-vI - 1, c, a, -1); break;
+                    default: d = d_PT(p, ta, tb_, tc); q = make_int4(-vI - 1, a, b, c);
+                    }
+                    if (d < dHat) {
+                        if (q.w >= 0) push4(out.act, out.nAct, out.capAct, out.overflow, q);
+                        else push4(out.dup, out.nDup, out.capDup, out.overflow, q);
+                        if (wantCand) {
+                            int i = atomicAdd(out.nCand, 1);
+                            if (i < out.capCand) out.cand[i] = make_int2(-svI - 1, sfI);
+                            else atomicExch(out.overflow, 1);
+                        }
+                    }
+                }
+            }
+}
+
+// one thread per surface edge eI; partners eJ > eI  (:2271-2407)
+__global__ void __launch_bounds__(128) k_query_ee(SurfArgs s, const Grid* __restrict__ gp, const Box* __restrict__ edge_boxes,
+    const unsigned long long* __restrict__ keys, const int* __restrict__ vals, int nEntries, double dHat, double radius, int wantCand, CsOut out)
+{
+    const int eI = blockIdx.x * blockDim.x + threadIdx.x;
+    if (eI >= s.nSE) return;
+    const Grid g = *gp;
+    const int a0 = s.SE[2 * eI], a1 = s.SE[2 * eI + 1];
+    const Box eb = edge_boxes[eI];
+    Box qb = eb;
+    for (int k = 0; k < 3; ++k) { qb.lo[k] -= radius; qb.hi[k] += radius; }
+    int c0[3], c1[3];
+    cell_range(g, qb, c0, c1);
+    const V3 xa0 = load_vertex(s.V, s.nV, a0), xa1 = load_vertex(s.V, s.nV, a1);
+    const int ecod = codim_v(s, a0);
+    const bool edbc = is_dbc_v(s, a0) && is_dbc_v(s, a1);
+    const double cull = dHat * (1.0 + 1e-9) + 1e-300;
+    for (int iz = c0[2]; iz <= c1[2]; ++iz)
+        for (int iy = c0[1]; iy <= c1[1]; ++iy)
+            for (int ix = c0[0]; ix <= c1[0]; ++ix) {
+                const unsigned long long key = cell_key(g, ix, iy, iz);
+                for (int e = lower_bound_u64(keys, nEntries, key); e < nEntries && keys[e] == key; ++e) {
+                    const int eJ = vals[e];
+                    if (eJ <= eI) continue;
+                    const Box jb = edge_boxes[eJ];
+                    int t0[3], t1[3];
+                    cell_range(g, jb, t0, t1);
+                    if (max(t0[0], c0[0]) != ix || max(t0[1], c0[1]) != iy || max(t0[2], c0[2]) != iz) continue;
+                    if (box_gap2(eb, jb) > cull) continue;
+                    const int b0 = s.SE[2 * eJ], b1 = s.SE[2 * eJ + 1];
+                    if (a0 == b0 || a0 == b1 || a1 == b0 || a1 == b1) continue;
+                    if ((ecod < 3 && codim_v(s, b0) < 3) || (edbc && is_dbc_v(s, b0) && is_dbc_v(s, b1))) continue;
+                    const V3 xb0 = load_vertex(s.V, s.nV, b0), xb1 = load_vertex(s.V, s.nV, b1);
+                    const int ty = dType_EE(xa0, xa1, xb0, xb1);
+                    const double cr = norm2(cross(xa1 - xa0, xb1 - xb0));
+                    const int add_e = (cr < eps_x_rest(s.Vrest, s.nV, a0, a1, b0, b1)) ? (-eJ - 2) : -1;
+                    double d;
+                    int4 q;
+                    switch (ty) {
+                    case 0: d = d_PP(xa0, xb0); q = make_int4(-a0 - 1, b0, -1, add_e); break;
+                    case 1: d = d_PP(xa0, xb1); q = make_int4(-a0 - 1, b1, -1, add_e); break;
+                    case 2: d = d_PE(xa0, xb0, xb1); q = make_int4(-a0 - 1, b0, b1, add_e); break;
+                    case 3: d = d_PP(xa1, xb0); q = make_int4(-a1 - 1, b0, -1, add_e); break;
+                    case 4: d = d_PP(xa1, xb1); q = make_int4(-a1 - 1, b1, -1, add_e); break;
+                    case 5: d = d_PE(xa1, xb0, xb1); q = make_int4(-a1 - 1, b0, b1, add_e); break;
+                    case 6: d = d_PE(xb0, xa0, xa1); q = make_int4(-b0 - 1, a0, a1, add_e); break;
+                    case 7: d = d_PE(xb1, xa0, xa1); q = make_int4(-b1 - 1, a0, a1, add_e); break;
+                    default: d = d_EE(xa0, xa1, xb0, xb1); q = make_int4(a0, a1, b0, b1);
+                    }
+                    if (d < dHat) {
+                        if (ty == 8) {
+                            if (add_e <= -2) { // nearly parallel EE: mollified set, keeps its own stencil (:2464-2467)
+                                int i = atomicAdd(out.nPara, 1);
+                                if (i < out.capPara) { out.para[i] = q; out.para_e[i] = make_int2(-1, -1); }
+                                else atomicExch(out.overflow, 1);
+                            }
+                            else push4(out.act, out.nAct, out.capAct, out.overflow, q);
+                        }
+                        else if (add_e == -1) push4(out.dup, out.nDup, out.capDup, out.overflow, q);
+                        else { // PP / PE that came from a nearly parallel edge pair (:2459-2462)
+                            int i = atomicAdd(out.nPara, 1);
+                            if (i < out.capPara) { out.para[i] = make_int4(q.x, q.y, q.z, -1); out.para_e[i] = make_int2(eI, eJ); }
+                            else atomicExch(out.overflow, 1);
+                        }
+                        if (wantCand) {
+                            int i = atomicAdd(out.nCand, 1);
+                            if (i < out.capCand) out.cand[i] = make_int2(eI, eJ);
+                            else atomicExch(out.overflow, 1);
+                        }
+                    }
+                }
+            }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// lexicographic sorts (signed int components) via stable LSD radix passes on packed 64-bit keys
+// ------------------------------------------------------------------------------------------------------------
+DEV unsigned long long pack2(int hi, int lo) { return ((unsigned long long)((unsigned)hi ^ 0x80000000u) << 32) | (unsigned long long)((unsigned)lo ^ 0x80000000u); }
+
+__global__ void k_iota(int n, int* idx)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) idx[i] = i;
+}
+__global__ void k_key_from4(int n, const int4* __restrict__ data, const int* __restrict__ idx, int which, unsigned long long* __restrict__ keys)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int4 v = data[idx[i]];
+    keys[i] = which ? pack2(v.x, v.y) : pack2(v.z, v.w);
+}
+__global__ void k_key_from2(int n, const int2* __restrict__ data, const int* __restrict__ idx, unsigned long long* __restrict__ keys)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int2 v = data[idx[i]];
+    keys[i] = pack2(v.x, v.y);
+}
+template <typename T>
+__global__ void k_gather(int n, const T* __restrict__ src, const int* __restrict__ idx, T* __restrict__ dst)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[idx[i]];
+}
+// heads of runs of equal (x,y,z) in a sorted dup list emit (x,y,z,-count) into the active list (:2434-2476)
+__global__ void k_merge_dups(int n, const int4* __restrict__ sorted, int4* __restrict__ act, int* __restrict__ nAct, int cap, int* __restrict__ overflow)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int4 v = sorted[i];
+    if (i > 0) {
+        const int4 u = sorted[i - 1];
+        if (u.x == v.x && u.y == v.y && u.z == v.z) return;
+    }
+    int cnt = 1;
+    while (i + cnt < n) {
+        const int4 w = sorted[i + cnt];
+        if (w.x != v.x || w.y != v.y || w.z != v.z) break;
+        ++cnt;
+    }
+    push4(act, nAct, cap, overflow, make_int4(v.x, v.y, v.z, -cnt));
+}
+
+} // namespace ipcgpu
+
+using namespace ipcgpu;
+
+#define CKC(call)                                                      \
+    do {                                                               \
+        cudaError_t e_ = (call);                                       \
+        if (e_ != cudaSuccess) {                                       \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); \
+            return IPCGPU_ERR_CUDA;                                    \
+        }                                                              \
+    } while (0)
+
+static inline int nblk(int n, int b) { return (n + b - 1) / b; }
+
+// stable radix sort of (keys, idx) pairs, result back in (keys, idx)
+static int sort_pass(ipcgpu_ctx* ctx, int n)
+{
+    ContactWork& w = ctx->cw;
+    size_t bytes = w.cub_tmp.n;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(w.cub_tmp.p, bytes, w.skey.p, w.skey2.p, w.sidx.p, w.sidx2.p, n, 0, 64, ctx->stream);
+    if (e != cudaSuccess) {
+        ctx->err = std::string("cub sort: ") + cudaGetErrorString(e);
+        return IPCGPU_ERR_CUDA;
+    }
+    std::swap(w.skey.p, w.skey2.p);
+    std::swap(w.sidx.p, w.sidx2.p);
+    ++ctx->launches;
+    return 0;
+}
+
+// sort int4 list lexicographically (optionally with an int2 companion as the least significant key)
+static int sort_lex(ipcgpu_ctx* ctx, int4* data, int2* comp, int n, int4* tmp4, int2* tmp2)
+{
+    if (n <= 1) return 0;
+    ContactWork& w = ctx->cw;
+    cudaStream_t st = ctx->stream;
+    k_iota<<<nblk(n, 256), 256, 0, st>>>(n, w.sidx.p);
+    int rc;
+    if (comp) {
+        k_key_from2<<<nblk(n, 256), 256, 0, st>>>(n, comp, w.sidx.p, w.skey.p);
+        if ((rc = sort_pass(ctx, n))) return rc;
+    }
+    k_key_from4<<<nblk(n, 256), 256, 0, st>>>(n, data, w.sidx.p, 0, w.skey.p);
+    if ((rc = sort_pass(ctx, n))) return rc;
+    k_key_from4<<<nblk(n, 256), 256, 0, st>>>(n, data, w.sidx.p, 1, w.skey.p);
+    if ((rc = sort_pass(ctx, n))) return rc;
+    k_gather<int4><<<nblk(n, 256), 256, 0, st>>>(n, data, w.sidx.p, tmp4);
+    CKC(cudaMemcpyAsync(data, tmp4, (size_t)n * sizeof(int4), cudaMemcpyDeviceToDevice, st));
+    if (comp) {
+        k_gather<int2><<<nblk(n, 256), 256, 0, st>>>(n, comp, w.sidx.p, tmp2);
+        CKC(cudaMemcpyAsync(comp, tmp2, (size_t)n * sizeof(int2), cudaMemcpyDeviceToDevice, st));
+    }
+    ctx->launches += 6;
+    return 0;
+}
+
+static int sort_int2(ipcgpu_ctx* ctx, int2* data, int n, int2* tmp2)
+{
+    if (n <= 1) return 0;
+    ContactWork& w = ctx->cw;
+    cudaStream_t st = ctx->stream;
+    k_iota<<<nblk(n, 256), 256, 0, st>>>(n, w.sidx.p);
+    k_key_from2<<<nblk(n, 256), 256, 0, st>>>(n, data, w.sidx.p, w.skey.p);
+    int rc;
+    if ((rc = sort_pass(ctx, n))) return rc;
+    k_gather<int2><<<nblk(n, 256), 256, 0, st>>>(n, data, w.sidx.p, tmp2);
+    CKC(cudaMemcpyAsync(data, tmp2, (size_t)n * sizeof(int2), cudaMemcpyDeviceToDevice, st));
+    ctx->launches += 3;
+    return 0;
+}
+
+int contact_alloc(ipcgpu_ctx* ctx)
+{
+    ContactWork& w = ctx->cw;
+    const int nSE = ctx->nSE, nSF = ctx->nSF, nSV = ctx->nSV;
+    const size_t nEnt = (size_t)8 * std::max(std::max(nSE, nSF), 1);
+    const int cap = std::max(ctx->pair_capacity, 1024);
+    bool ok = w.vbox.reserve(std::max(nSV, 1)) && w.ebox.reserve(std::max(nSE, 1)) && w.tbox.reserve(std::max(nSF, 1)) && w.bounds.reserve(8) && w.grid.reserve(2)
+        && w.tkeys.reserve(nEnt) && w.tvals.reserve(nEnt) && w.ekeys.reserve(nEnt) && w.evals.reserve(nEnt) && w.key_tmp.reserve(nEnt) && w.val_tmp.reserve(nEnt)
+        && w.act.reserve(cap) && w.dup.reserve(cap) && w.para.reserve(cap) && w.para_e.reserve(cap) && w.cand.reserve((size_t)4 * cap) && w.tmp4.reserve(cap)
+        && w.tmp2.reserve((size_t)4 * cap) && w.counters.reserve(16) && w.skey.reserve((size_t)4 * cap) && w.skey2.reserve((size_t)4 * cap) && w.sidx.reserve((size_t)4 * cap)
+        && w.sidx2.reserve((size_t)4 * cap);
+    if (!ok) {
+        ctx->err = "contact workspace allocation failed";
+        return IPCGPU_ERR_CUDA;
+    }
+    size_t b1 = 0, b2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, b1, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int*)nullptr, (int*)nullptr, (int)nEnt);
+    cub::DeviceRadixSort::SortPairs(nullptr, b2, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int*)nullptr, (int*)nullptr, 4 * cap);
+    if (!w.cub_tmp.reserve(std::max(b1, b2) + 256)) {
+        ctx->err = "cub temp allocation failed";
+        return IPCGPU_ERR_CUDA;
+    }
+    w.cap = cap;
+    return 0;
+}
+
+// build one sorted grid over `boxes` (n prims); result in (keys, vals) with *nValid entries
+static int build_grid(ipcgpu_ctx* ctx, int n, const Box* boxes, DevBuf<unsigned long long>& keys, DevBuf<int>& vals)
+{
+    ContactWork& w = ctx->cw;
+    cudaStream_t st = ctx->stream;
+    if (n <= 0) return 0;
+    k_emit<<<nblk(n, 256), 256, 0, st>>>(n, boxes, w.grid.p, w.key_tmp.p, w.val_tmp.p);
+    size_t bytes = w.cub_tmp.n;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(w.cub_tmp.p, bytes, w.key_tmp.p, keys.p, w.val_tmp.p, vals.p, 8 * n, 0, 64, st);
+    if (e != cudaSuccess) {
+        ctx->err = std::string("cub grid sort: ") + cudaGetErrorString(e);
+        return IPCGPU_ERR_CUDA;
+    }
+    ctx->launches += 2;
+    return 0;
+}
+
+SurfArgs surf_args(const ipcgpu_ctx* ctx)
+{
+    SurfArgs s;
+    s.nV = ctx->nV; s.V = ctx->V.p; s.Vrest = ctx->Vrest.p; s.dbc = ctx->has_dbc ? ctx->dbc.p : nullptr;
+    s.vCoDim = ctx->has_codim ? ctx->vCoDim.p : nullptr;
+    s.nSV = ctx->nSV; s.SVI = ctx->SVI.p; s.nSE = ctx->nSE; s.SE = ctx->SE.p; s.nSF = ctx->nSF; s.SF = ctx->SF.p;
+    return s;
+}
+
+// SelfCollisionHandler::computeConstraintSet on the device; counts come back through the pinned scalar buffer
+int contact_constraint_set(ipcgpu_ctx* ctx, double dHat, int wantCand, int* nC, int* nPara, int* nCand)
+{
+    ContactWork& w = ctx->cw;
+    cudaStream_t st = ctx->stream;
+    const SurfArgs s = surf_args(ctx);
+    const double radius = sqrt(dHat);
+    cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_HASH);
+    k_bounds_init<<<1, 32, 0, st>>>(w.bounds.p);
+    if (s.nSE > 0) k_boxes<<<nblk(s.nSE, 256), 256, 0, st>>>(s, 1, nullptr, 0.0, w.ebox.p, w.bounds.p);
+    if (s.nSF > 0) k_boxes<<<nblk(s.nSF, 256), 256, 0, st>>>(s, 2, nullptr, 0.0, w.tbox.p, w.bounds.p);
+    k_grid_params<<<1, 32, 0, st>>>(w.bounds.p, radius, w.grid.p);
+    ctx->launches += 4;
+    int rc;
+    if ((rc = build_grid(ctx, s.nSF, w.tbox.p, w.tkeys, w.tvals))) return rc;
+    if ((rc = build_grid(ctx, s.nSE, w.ebox.p, w.ekeys, w.evals))) return rc;
+    ctx->prof_end(pe);
+
+    pe = ctx->prof_begin(IPCGPU_STAGE_CONSTRAINT_SET);
+    CKC(cudaMemsetAsync(w.counters.p, 0, 16 * sizeof(int), st));
+    CsOut out;
+    out.act = w.act.p; out.nAct = w.counters.p + 0; out.capAct = w.cap;
+    out.dup = w.dup.p; out.nDup = w.counters.p + 1; out.capDup = w.cap;
+    out.para = w.para.p; out.para_e = w.para_e.p; out.nPara = w.counters.p + 2; out.capPara = w.cap;
+    out.cand = w.cand.p; out.nCand = w.counters.p + 3; out.capCand = 4 * w.cap;
+    out.overflow = w.counters.p + 4;
+    if (s.nSV > 0 && s.nSF > 0) k_query_pt<<<nblk(s.nSV, 128), 128, 0, st>>>(s, w.grid.p, w.tbox.p, w.tkeys.p, w.tvals.p, 8 * s.nSF, dHat, radius, wantCand, out);
+    if (s.nSE > 1) k_query_ee<<<nblk(s.nSE, 128), 128, 0, st>>>(s, w.grid.p, w.ebox.p, w.ekeys.p, w.evals.p, 8 * s.nSE, dHat, radius, wantCand, out);
+    ctx->launches += 2;
+    int* h = reinterpret_cast<int*>(ctx->h_scalar);
+    CKC(cudaMemcpyAsync(h, w.counters.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CKC(cudaStreamSynchronize(st));
+    if (h[4]) {
+        ctx->err = "constraint-set capacity exceeded (raise it with ipcgpu_set_pair_capacity)";
+        return IPCGPU_ERR_CAPACITY;
+    }
+    const int nAct = h[0], nDup = h[1], nP = h[2], nK = h[3];
+    // merge PP/PE duplicates into the active list with negative multiplicities
+    if (nDup > 0) {
+        if ((rc = sort_lex(ctx, w.dup.p, nullptr, nDup, w.tmp4.p, nullptr))) return rc;
+        k_merge_dups<<<nblk(nDup, 256), 256, 0, st>>>(nDup, w.dup.p, w.act.p, w.counters.p + 0, w.cap, w.counters.p + 4);
+        ++ctx->launches;
+        CKC(cudaMemcpyAsync(h, w.counters.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CKC(cudaStreamSynchronize(st));
+        if (h[4]) {
+            ctx->err = "constraint-set capacity exceeded (raise it with ipcgpu_set_pair_capacity)";
+            return IPCGPU_ERR_CAPACITY;
+        }
+    }
+    const int nTot = (nDup > 0) ? h[0] : nAct;
+    if ((rc = sort_lex(ctx, w.act.p, nullptr, nTot, w.tmp4.p, nullptr))) return rc;
+    if ((rc = sort_lex(ctx, w.para.p, w.para_e.p, nP, w.tmp4.p, w.tmp2.p))) return rc;
+    if (wantCand && (rc = sort_int2(ctx, w.cand.p, nK, w.tmp2.p))) return rc;
+    ctx->prof_end(pe);
+    w.nC = nTot;
+    w.nP = nP;
+    w.nK = wantCand ? nK : 0;
+    if (nC) *nC = w.nC;
+    if (nPara) *nPara = w.nP;
+    if (nCand) *nCand = w.nK;
+    return 0;
+}

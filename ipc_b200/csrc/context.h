@@ -1,6 +1,7 @@
 // context.h -- the ipcgpu_ctx object behind the C ABI: device buffers, scatter maps, streams, NCCL.
 #pragma once
 #include "kernels.h"
+#include "broadphase_types.h"
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <string>
@@ -38,7 +39,18 @@ struct DevBuf {
     }
 };
 
-struct NcclApi; // dlopen'ed subset of NCCL (comm.cu)
+// device workspace of the contact stages (constraint.cu / ccd.cu)
+struct ContactWork {
+    DevBuf<Box> vbox, ebox, tbox;
+    DevBuf<unsigned long long> bounds, tkeys, ekeys, key_tmp, skey, skey2;
+    DevBuf<Grid> grid;
+    DevBuf<int> tvals, evals, val_tmp, counters, sidx, sidx2;
+    DevBuf<int4> act, dup, para, tmp4;
+    DevBuf<int2> para_e, cand, tmp2;
+    DevBuf<unsigned char> cub_tmp;
+    int cap = 0;
+    int nC = 0, nP = 0, nK = 0; // current active / mollified / candidate counts
+};
 
 } // namespace ipcgpu
 
@@ -60,6 +72,14 @@ struct ipcgpu_ctx {
     ipcgpu::DevBuf<uint8_t> dbc;
     bool has_mass = false, has_dbc = false;
     std::vector<int> h_T; // host copy of tets (maps are rebuilt when the partition changes)
+
+    // surface (Mesh::SVI / SFEdges / SF) and contact workspace
+    int nSV = 0, nSE = 0, nSF = 0;
+    ipcgpu::DevBuf<int> SVI, SE, SF, vCoDim;
+    bool has_codim = false, surface_ready = false;
+    int pair_capacity = 1 << 20;
+    ipcgpu::ContactWork cw;
+    ipcgpu::DevBuf<double> bpartials;
 
     // gradient gather map (local tets)
     ipcgpu::DevBuf<int> inc_ptr, inc;

@@ -536,6 +536,7 @@ void elastic_energy(const ElasticArgs& p, double* e_per_tet, double* partials, d
     else launch_energy<1>(p, e_per_tet, partials, coef, out, st);
 }
 int elastic_energy_blocks(int nTets) { return (nTets + 255) / 256; }
+void reduce_sum(const double* partials, int n, double scale, double* out, cudaStream_t st) { k_reduce_sum<<<1, 1024, 0, st>>>(partials, n, scale, out); }
 
 template <int ENERGY, bool G, bool H>
 static void launch_gh(const ElasticArgs& p, double coef, int projectSPD, double* gcont, double* hblk, cudaStream_t st)

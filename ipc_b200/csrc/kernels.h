@@ -28,6 +28,39 @@ void slot_offsets(int nSlots, const int* slot_v, const int* slot_u, const int* i
 void inversion_step(const ElasticArgs& p, const double* dir, double slack, double* per_tet, unsigned long long* min_ord, cudaStream_t st);
 
 
+// ---- contact ------------------------------------------------------------------------------------------
+struct SurfArgs {
+    int nV;
+    const double* V;      // SoA current positions
+    const double* Vrest;  // SoA rest positions
+    const uint8_t* dbc;   // nullable
+    const int* vCoDim;    // nullable (=> 3)
+    int nSV; const int* SVI;
+    int nSE; const int* SE;   // interleaved (first, second)   [Mesh::SFEdges]
+    int nSF; const int* SF;   // SoA [v0|v1|v2]                [Mesh::SF column-major]
+};
+
+struct BarrierArgs {
+    int nV;
+    const double* V;
+    const double* Vrest;
+    const uint8_t* dbc;
+    const int* SE;
+    const int4* cs; int nC;          // active set (MMCVID encoding)
+    const int4* para; const int2* para_e; int nP; // mollified (nearly parallel EE) set + (eI,eJ)
+    double dHat, kappa;
+    int projectDBC;
+    const int* ia; const int* ja; int base;
+};
+
+// barrier.cu
+void barrier_energy(const BarrierArgs& p, double* partials, int* bad, cudaStream_t st);
+int barrier_energy_blocks(int n);
+void barrier_gradient(const BarrierArgs& p, double* g, cudaStream_t st);
+void barrier_hessian(const BarrierArgs& p, double* a, int* err, cudaStream_t st);
+// elastic.cu (shared fixed-order reduction)
+void reduce_sum(const double* partials, int n, double scale, double* out, cudaStream_t st);
+
 // misc.cu
 void step_forward(int nV, const double* x0_soa, const double* p_interleaved, double alpha, double* x_soa, cudaStream_t st);
 

@@ -41,6 +41,14 @@ SIGNATURES = {
     "ipcgpu_elastic_hessian": (C.c_int, [_ctxp, C.c_double, C.c_int, C.c_int, C.c_int, _dp]),
     "ipcgpu_elastic_grad_hess": (C.c_int, [_ctxp, C.c_double, C.c_int, C.c_int, C.c_int, _dp, _dp]),
     "ipcgpu_inversion_step": (C.c_int, [_ctxp, _dp, C.c_double, _dp]),
+    "ipcgpu_set_surface": (C.c_int, [_ctxp, C.c_int, _ip, C.c_int, _ip, C.c_int, _ip, _ip]),
+    "ipcgpu_set_pair_capacity": (C.c_int, [_ctxp, C.c_int]),
+    "ipcgpu_constraint_set": (C.c_int, [_ctxp, C.c_double, C.c_int, _ip, _ip, _ip]),
+    "ipcgpu_get_constraint_set": (C.c_int, [_ctxp, _ip, _ip, _ip, _ip]),
+    "ipcgpu_set_constraint_set": (C.c_int, [_ctxp, C.c_int, _ip, C.c_int, _ip, _ip, C.c_int, _ip]),
+    "ipcgpu_barrier_energy": (C.c_int, [_ctxp, C.c_double, C.c_double, _dp]),
+    "ipcgpu_barrier_gradient": (C.c_int, [_ctxp, C.c_double, C.c_double, _dp]),
+    "ipcgpu_barrier_hessian": (C.c_int, [_ctxp, C.c_double, C.c_double, C.c_int, _dp]),
     "ipcgpu_csr_set_zero": (C.c_int, [_ctxp]),
     "ipcgpu_allreduce_grad_hess": (C.c_int, [_ctxp, C.c_int, C.c_int]),
     "ipcgpu_download": (C.c_int, [_ctxp, C.c_int, _dp, C.c_uint64]),
@@ -204,6 +212,43 @@ class Context:
         a = C.c_double(alpha)
         self._ck(self.lib.ipcgpu_inversion_step(self.h, _d(f64(p)) if p is not None else None, slack, C.byref(a)))
         return a.value
+
+    # ---- contact ------------------------------------------------------------------------------
+    def set_surface(self, SVI, SFEdges, SF_soa, vCoDim=None):
+        SVI, SE, SF = i32(SVI).ravel(), i32(SFEdges).ravel(), i32(SF_soa).ravel()
+        self._ck(self.lib.ipcgpu_set_surface(self.h, SVI.size, _i(SVI), SE.size // 2, _i(SE), SF.size // 3, _i(SF), _i(i32(vCoDim))))
+
+    def set_pair_capacity(self, cap):
+        self._ck(self.lib.ipcgpu_set_pair_capacity(self.h, int(cap)))
+
+    def constraint_set(self, dHat, getPTEE=1, fetch=True):
+        nC, nP, nK = C.c_int(), C.c_int(), C.c_int()
+        self._ck(self.lib.ipcgpu_constraint_set(self.h, dHat, getPTEE, C.byref(nC), C.byref(nP), C.byref(nK)))
+        self.nC, self.nP, self.nK = nC.value, nP.value, nK.value
+        if not fetch:
+            return self.nC, self.nP, self.nK
+        mm = np.empty((self.nC, 4), dtype=np.int32); pa = np.empty((self.nP, 4), dtype=np.int32)
+        pe = np.empty((self.nP, 2), dtype=np.int32); cand = np.empty((self.nK, 2), dtype=np.int32)
+        self._ck(self.lib.ipcgpu_get_constraint_set(self.h, _i(mm), _i(pa), _i(pe), _i(cand)))
+        return mm, pa, pe, cand
+
+    def set_constraint_set(self, mm, pa, pe, cand=None):
+        mm, pa, pe = i32(mm), i32(pa), i32(pe)
+        cand = i32(cand) if cand is not None else np.empty((0, 2), dtype=np.int32)
+        self._ck(self.lib.ipcgpu_set_constraint_set(self.h, len(mm), _i(mm), len(pa), _i(pa), _i(pe), len(cand), _i(cand)))
+
+    def barrier_energy(self, dHat, kappa):
+        E = C.c_double()
+        self._ck(self.lib.ipcgpu_barrier_energy(self.h, dHat, kappa, C.byref(E)))
+        return E.value
+
+    def barrier_gradient(self, dHat, kappa, g_inout=None):
+        self._ck(self.lib.ipcgpu_barrier_gradient(self.h, dHat, kappa, _d(g_inout)))
+        return g_inout
+
+    def barrier_hessian(self, dHat, kappa, projectDBC=1, a_inout=None):
+        self._ck(self.lib.ipcgpu_barrier_hessian(self.h, dHat, kappa, projectDBC, _d(a_inout)))
+        return a_inout
 
     def profile(self, enable):
         self._ck(self.lib.ipcgpu_profile(self.h, int(enable)))

@@ -59,6 +59,17 @@ def ball_tets(n, radius=1.0, center=(0.0, 0.0, 0.0)):
     return V, T
 
 
+def superball_tets(n, radius=1.0, q=6.0, center=(0.0, 0.0, 0.0)):
+    """A rounded-cube "ball" (unit ball of the L_q norm): p -> p*|p|_inf/|p|_q.  q=2 is the round ball; q=6 has nearly
+    flat poles, so that stacked balls touch over a patch of surface primitives instead of a single point."""
+    V, T = grid_tets(n, n, n, h=2.0 / n, origin=(-1.0, -1.0, -1.0))
+    linf = np.abs(V).max(axis=1)
+    lq = (np.abs(V) ** q).sum(axis=1) ** (1.0 / q)
+    scale = np.where(lq > 0, linf / np.maximum(lq, 1e-300), 0.0)
+    V = V * scale[:, None] * radius + np.asarray(center)
+    return V, T
+
+
 def boundary_faces(T):
     """Outward-oriented boundary triangles of a positively oriented tet mesh."""
     a, b, c, d = T[:, 0], T[:, 1], T[:, 2], T[:, 3]

@@ -9,53 +9,55 @@ import numpy as np
 from . import mesh as M
 
 
-def ball_pile(n_balls, res=10, radius=0.5, seed=5, energy=0, dhat_rel=1e-3, gap_lo=0.3, gap_hi=1.2, deform_amp=0.01):
-    """Balls on a jittered cubic lattice.  Returns (mesh, info) with info = dict(dHat, p, centers).
+def ball_pile(n_balls, res=10, radius=0.5, seed=5, energy=0, dhat_rel=1e-3, gap_lo=0.3, gap_hi=1.2, q=6.0, height=5):
+    """Columns of stacked L_q "balls" (rounded, nearly flat poles).  Returns (mesh, info).
 
-    Neighbouring balls are separated by gaps g ~ U(gap_lo, gap_hi) * sqrt(dHat) along the lattice axes, so a
-    band of surface primitives of every ball is inside the barrier activation distance of its neighbours.
+    Balls of one column are separated along z by gaps g ~ U(gap_lo, gap_hi) * sqrt(dHat) (pole to pole), rotated about z
+    by a random angle (so facing edges are generically not parallel) and shifted laterally by a small jitter; columns
+    are far enough apart not to interact.  info = dict(dHat, p, ...): dHat = (dhat_rel)^2 * bboxDiag^2
+    (Optimizer.cpp:274-281) and p is a search direction that squeezes every column toward its middle with
+    |p| ~ 2-4 sqrt(dHat), i.e. alpha_CFL < 1: the full-CCD branch of Optimizer.cpp:1961 is taken.
     """
     rng = np.random.default_rng(seed)
-    side = int(np.ceil(n_balls ** (1.0 / 3.0)))
-    # scene bbox diag decides dHat (Optimizer.cpp:274-281): dHat = (dhat_rel)^2 * bboxDiag^2
-    pitch0 = 2.0 * radius
-    diag2 = 3.0 * (side * pitch0) ** 2
-    dHat = dhat_rel ** 2 * diag2
+    n_cols = int(np.ceil(n_balls / height))
+    side = int(np.ceil(np.sqrt(n_cols)))
+    col_pitch = 2.0 * radius + 0.5
+    ext = np.array([side * col_pitch, side * col_pitch, height * 2.0 * radius])
+    dHat = dhat_rel ** 2 * float((ext ** 2).sum())
     sq = np.sqrt(dHat)
-    Vb, Tb = M.ball_tets(res, radius)
-    parts, centers = [], []
+    Vb, Tb = M.superball_tets(res, radius, q)
+    parts, centers, col_mid = [], [], []
     k = 0
-    # cumulative positions with random gaps per axis-layer keep every axis-neighbour gap inside [gap_lo, gap_hi]*sqrt(dHat)
-    offs = [np.concatenate([[0.0], np.cumsum(pitch0 + rng.uniform(gap_lo, gap_hi, side - 1) * sq)]) for _ in range(3)]
-    for i in range(side):
-        for j in range(side):
-            for l in range(side):
-                if k >= n_balls:
-                    break
-                c = np.array([offs[0][i], offs[1][j], offs[2][l]])
-                # random rotation so that contacts are not axis aligned vertex-vertex only
-                q = rng.standard_normal(4)
-                q /= np.linalg.norm(q)
-                w, x, y, z = q
-                R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
-                              [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
-                              [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
-                parts.append((Vb @ R.T + c, Tb))
-                centers.append(c)
-                k += 1
+    for ci in range(n_cols):
+        cx, cy = (ci % side) * col_pitch, (ci // side) * col_pitch
+        z = 0.0
+        zs = []
+        for l in range(height):
+            if k >= n_balls:
+                break
+            th = rng.uniform(0, 2 * np.pi)
+            R = np.array([[np.cos(th), -np.sin(th), 0.0], [np.sin(th), np.cos(th), 0.0], [0.0, 0.0, 1.0]])
+            c = np.array([cx + rng.normal(0, 0.02), cy + rng.normal(0, 0.02), z])
+            parts.append((Vb @ R.T + c, Tb))
+            centers.append(c)
+            zs.append(z)
+            z += 2.0 * radius + rng.uniform(gap_lo, gap_hi) * sq
+            k += 1
+        col_mid += [0.5 * (zs[0] + zs[-1])] * len(zs)
     m = M.merge_meshes(parts, energy=energy)
     centers = np.array(centers)
-    # mild smooth deformation of every ball (keeps all tets positive), so that F != I everywhere
+    col_mid = np.array(col_mid)
+    # mild smooth volumetric deformation (keeps every tet positive and leaves the poles' gaps almost untouched)
     X = m.V_rest
-    m.V = X + deform_amp * radius * np.sin(2.0 * np.pi * X[:, [1, 2, 0]] / (2.0 * radius)) * 0.2
-    # search direction: toward the pile centre, scaled so that alpha_CFL < 1 (forces the full-CCD branch)
-    pile_c = centers.mean(0)
     nVb = Vb.shape[0]
     ball_of = np.repeat(np.arange(len(centers)), nVb)
-    dirn = pile_c - centers[ball_of]
-    nrm = np.linalg.norm(dirn, axis=1, keepdims=True)
-    dirn = np.where(nrm > 0, dirn / np.maximum(nrm, 1e-300), 0.0)
-    p = dirn * (4.0 * sq) * rng.uniform(0.5, 1.0, (m.nV, 1)) + rng.normal(0, 0.2 * sq, (m.nV, 3))
+    local = X - centers[ball_of]
+    m.V = X + 0.01 * radius * np.stack([np.sin(2 * np.pi * local[:, 1]), np.sin(2 * np.pi * local[:, 0]), 0 * local[:, 2]], axis=1)
+    # search direction: every ball moves toward its column's middle
+    dz = col_mid[ball_of] - centers[ball_of, 2]
+    p = np.zeros((m.nV, 3))
+    p[:, 2] = np.sign(dz) * 3.0 * sq * rng.uniform(0.6, 1.0, m.nV)
+    p += rng.normal(0, 0.1 * sq, (m.nV, 3))
     info = dict(dHat=dHat, p=np.ascontiguousarray(p).ravel(), centers=centers, radius=radius, n_balls=len(centers))
     return m, info
 
