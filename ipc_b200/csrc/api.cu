@@ -150,6 +150,10 @@ static int ensure_offsets(ipcgpu_ctx* ctx)
     return IPCGPU_OK;
 }
 
+// C++ linkage helpers implemented in constraint.cu / ccd.cu
+int contact_alloc(ipcgpu_ctx* ctx);
+int contact_constraint_set(ipcgpu_ctx* ctx, double dHat, int wantCand, int* nC, int* nPara, int* nCand);
+
 extern "C" {
 
 int ipcgpu_create(int device, ipcgpu_ctx** out)
@@ -428,9 +432,6 @@ int ipcgpu_inversion_step(ipcgpu_ctx* ctx, const double* p, double slack, double
 }
 
 // ---- contact ---------------------------------------------------------------------------------------------
-int contact_alloc(ipcgpu_ctx* ctx);                                                                 // constraint.cu
-int contact_constraint_set(ipcgpu_ctx* ctx, double dHat, int wantCand, int* nC, int* nPara, int* nCand); // constraint.cu
-
 int ipcgpu_set_surface(ipcgpu_ctx* ctx, int nSV, const int* SVI, int nSE, const int* SE, int nSF, const int* SF, const int* vCoDim)
 {
     REQUIRE(ctx->nV > 0, IPCGPU_ERR_STATE, "ipcgpu_set_mesh first");
