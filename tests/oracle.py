@@ -273,3 +273,48 @@ class Surf:
         mm4 = np.ascontiguousarray(mm4, dtype=np.int32)
         lib().orc_barrier_pair_hessian(C.byref(self.s), i(mm4), C.c_double(dHat), C.c_double(kappa), d(H), C.byref(nv))
         return H.reshape(12, 12), nv.value
+
+
+# ---- CCD (Tight-Inclusion restatement) -----------------------------------------------------------------------------
+class OrcGrid(C.Structure):
+    _fields_ = [("lo", C.c_double * 3), ("inv_h", C.c_double), ("count", C.c_int * 3)]
+
+
+def ti(kind, x0, x1, err, ms, tol=1e-6, max_t=1.0, max_itr=1000000, no_zero_toi=1):
+    x0 = np.ascontiguousarray(x0, dtype=np.float64).ravel(); x1 = np.ascontiguousarray(x1, dtype=np.float64).ravel()
+    err = np.ascontiguousarray(err, dtype=np.float64)
+    toi, ot = C.c_double(), C.c_double()
+    fn = lib().orc_ti_vf if kind == "vf" else lib().orc_ti_ee
+    hit = fn(d(x0), d(x1), d(err), C.c_double(ms), C.c_double(tol), C.c_double(max_t), int(max_itr), int(no_zero_toi), C.byref(toi), C.byref(ot))
+    return bool(hit), toi.value, ot.value
+
+
+def ti_error(V_soa, nV, p=None):
+    V_soa = np.ascontiguousarray(V_soa, dtype=np.float64)
+    evf, eee = np.empty(3), np.empty(3)
+    lib().orc_ti_error(d(V_soa), nV, d(np.ascontiguousarray(p, dtype=np.float64)) if p is not None else None, d(evf), d(eee))
+    return evf, eee
+
+
+def grid_swept(surf, p, alpha, h):
+    g = OrcGrid()
+    a = C.c_double(alpha)
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    lib().orc_grid_swept(C.byref(surf.s), d(p), C.byref(a), C.c_double(h), C.byref(g))
+    return g, a.value
+
+
+def ccd_partial(surf, p, cand, tol, evf, eee, alpha, nthreads=1):
+    p = np.ascontiguousarray(p, dtype=np.float64); cand = np.ascontiguousarray(cand, dtype=np.int32)
+    a = C.c_double(alpha)
+    z = lib().orc_ccd_partial(C.byref(surf.s), d(p), i(cand), len(cand), C.c_double(tol), d(np.ascontiguousarray(evf)), d(np.ascontiguousarray(eee)), C.byref(a), nthreads)
+    return a.value, z
+
+
+def ccd_full(surf, p, grid, alpha_grid, tol, evf, eee, alpha, nthreads=1):
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    a = C.c_double(alpha)
+    n = C.c_longlong()
+    z = lib().orc_ccd_full(C.byref(surf.s), d(p), C.byref(grid), C.c_double(alpha_grid), C.c_double(tol), d(np.ascontiguousarray(evf)), d(np.ascontiguousarray(eee)),
+                           C.byref(a), C.byref(n), nthreads)
+    return a.value, z, n.value

@@ -1,0 +1,112 @@
+"""CPU tests of the oracle's CCD restatement (Tight-Inclusion is "parity unpinned": no reference vectors exist; the
+checks below are the reference's own unit-test geometries with their analytic hit criteria, conservativeness and
+consistency properties)."""
+import numpy as np
+import pytest
+
+import oracle as orc
+from ipc_b200 import mesh as M
+from ipc_b200 import scenes
+
+ERR = np.full(3, 1e-13)
+
+
+@pytest.mark.parametrize("u0y", [-1.1, 0.0, 1.1])
+@pytest.mark.parametrize("u1y", [-1.1, 0.0, 1.1])
+def test_reference_pt_geometry(u0y, u1y):  # tests/Collisions/CollisionConstraintTests.cpp:18-35
+    v0 = np.array([0, 1, -0.5]); v1 = np.array([-1, 0, 1.0]); v2 = np.array([1, 0, 1.0]); v3 = np.array([0, 0, -1.0])
+    u0 = np.array([0, u0y, 0]); u1 = np.array([0, u1y, 0])
+    x0 = np.array([v0, v1, v3, v2]); x1 = np.array([v0 + u0, v1 + u1, v3 + u1, v2 + u1])
+    hit, toi, _ = orc.ti("vf", x0, x1, ERR, 0.0)
+    assert hit == (-u0y + u1y >= 1)
+    if hit:
+        exact = 1.0 / (u1y - u0y)
+        assert exact - 1e-4 <= toi <= exact  # conservative: never later than the true time of impact
+
+
+@pytest.mark.parametrize("ydisp", [-2.0, 0.0, 2.0])
+def test_reference_ee_geometry(ydisp):  # CollisionConstraintTests.cpp:83-99
+    v0 = np.array([-1, -1, 0.0]); v1 = np.array([1, -1, 0.0]); v2 = np.array([0, 1, -1.0]); v3 = np.array([0, 1, 1.0])
+    u0 = np.array([0, ydisp, 0]); u1 = np.array([0, -ydisp, 0])
+    x0 = np.array([v0, v1, v2, v3]); x1 = np.array([v0 + u0, v1 + u0, v2 + u1, v3 + u1])
+    hit, toi, _ = orc.ti("ee", x0, x1, ERR, 0.0)
+    assert hit == (ydisp >= 1.0)
+    if hit:
+        assert 0.5 - 1e-4 <= toi <= 0.5
+
+
+def test_minimum_separation_and_max_t():
+    v0 = np.array([0.2, 0.2, 1.0]); tri = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0.0]])
+    x0 = np.vstack([v0, tri]); x1 = x0.copy(); x1[0, 2] = -1.0  # point falls through the triangle at t = 0.5
+    hit, toi, _ = orc.ti("vf", x0, x1, ERR, 0.0)
+    assert hit and 0.5 - 5e-4 <= toi <= 0.5
+    hit, toi_ms, _ = orc.ti("vf", x0, x1, ERR, 0.1)  # stop 0.1 before contact: toi ~ (1-0.1)/2
+    assert hit and 0.45 - 5e-4 <= toi_ms <= 0.45
+    hit, _, _ = orc.ti("vf", x0, x1, ERR, 0.0, max_t=0.4)  # impact lies beyond max_t
+    assert not hit
+    hit, toi2, _ = orc.ti("vf", x0, x1, ERR, 0.0, max_t=0.6)
+    assert hit and abs(toi2 - toi) < 1e-4
+    x1m = x0.copy(); x1m[0, 0] += 5.0  # tangential motion: never hits
+    assert not orc.ti("vf", x0, x1m, ERR, 0.0)[0]
+    xs = x0.copy(); xs[0, 2] = 1e-9  # starts (almost) in contact while approaching: no_zero_toi must return a positive time
+    x1s = xs.copy(); x1s[0, 2] = -1.0
+    hit, toi0, _ = orc.ti("vf", xs, x1s, ERR, 0.0)
+    assert hit and 0.0 < toi0 <= 1e-9 * 1.0000001
+
+
+def test_conservative_on_random_pairs():
+    """toi returned by TI is never later than the first time the exact distance drops below ms (sampled)."""
+    rng = np.random.default_rng(3)
+    hits = 0
+    for _ in range(200):
+        x0 = rng.standard_normal((4, 3)); x1 = x0 + 0.8 * rng.standard_normal((4, 3))
+        for kind in ("vf", "ee"):
+            hit, toi, _ = orc.ti(kind, x0, x1, ERR, 1e-3)
+            ts = np.linspace(0, 1, 4001)
+            f = orc.point_tri_d if kind == "vf" else orc.edge_edge_d
+            dmin = np.array([f(x0 + t * (x1 - x0)) for t in ts[::20]])
+            if hit:
+                hits += 1
+                before = ts[::20] < toi - 1e-3
+                assert np.all(dmin[before] > 0.0)
+            else:
+                assert dmin.min() > 1e-8  # no contact anywhere on the sampled trajectory
+    assert hits > 20
+
+
+def test_ti_error_filter():
+    V = np.array([[0, 0, 0], [2, 1, 0.5]], dtype=float)
+    evf, eee = orc.ti_error(np.ascontiguousarray(V.T).ravel(), 2)
+    r = 0.5 * np.sqrt(4 + 1 + 0.25)
+    c = np.array([1, 0.5, 0.25])
+    mx = np.maximum(np.abs(c + 10 * r / np.sqrt(3)), 1.0)
+    assert np.allclose(eee, mx ** 3 * 7.105427357601002e-15, rtol=1e-14) and np.allclose(evf, mx ** 3 * 7.549516567451064e-15, rtol=1e-14)
+
+
+def test_partial_and_full_ccd_on_stacked_balls():
+    m, info = scenes.ball_pile(2, res=6, seed=11, height=2)
+    s = orc.Surf(m)
+    p = info["p"]
+    evf, eee = orc.ti_error(s.V, m.nV, p)
+    mm, pa, pe, cand = s.constraint_set(info["dHat"])
+    assert len(cand) > 0
+    a_part, z = orc.ccd_partial(s, p, cand, 1e-6, evf, eee, 1.0)
+    assert z == 0 and 0 < a_part < 1.0
+    g, a_grid = orc.grid_swept(s, p, 1.0, m.avgEdgeLen / 3)
+    assert a_grid <= 1.0
+    a_full, z, npairs = orc.ccd_full(s, p, g, a_grid, 1e-6, evf, eee, a_grid)
+    assert z == 0 and npairs > len(cand)
+    assert a_full <= min(a_part, a_grid) + 1e-15  # the full sweep sees at least the active candidates
+    # moving by 0.999*alpha keeps every active distance positive (intersection free)
+    V2 = m.V + 0.999 * a_full * p.reshape(-1, 3)
+    s2 = orc.Surf(m, V=V2)
+    for c in cand:
+        if c[0] < 0:
+            v = [m.SVI[-c[0] - 1]] + list(m.SF[c[1]])
+            assert orc.point_tri_d(V2[v]) > 0
+        else:
+            v = list(m.SFEdges[c[0]]) + list(m.SFEdges[c[1]])
+            assert orc.edge_edge_d(V2[v]) > 0
+    # separating motion: no bound
+    a_sep, _ = orc.ccd_partial(s, -p, cand, 1e-6, evf, eee, 1.0)
+    assert a_sep == 1.0
