@@ -128,6 +128,25 @@ int ipcgpu_barrier_gradient(ipcgpu_ctx* ctx, double dHat, double kappa, double* 
 /* CSR += makePD(kappa*mult*(b'' grad d grad d^T + b' hess d))  (augmentIPHessian :418-561, augmentParaEEHessian :3049-3201) */
 int ipcgpu_barrier_hessian(ipcgpu_ctx* ctx, double dHat, double kappa, int projectDBC, double* a_inout);
 
+/* ---- CCD step bound (Tight-Inclusion), Optimizer.cpp:1884-2040 ----------------------------------------------------- */
+/* capacity (pairs) of the device CCD candidate list; default 2^23 */
+int ipcgpu_set_ccd_capacity(ipcgpu_ctx* ctx, uint64_t capacity);
+/* scene-wide Tight-Inclusion numerical error (computeTightInclusionError, CCDUtils.cpp:55-87): world bbox of V (and V+p when p is
+ * given) inflated to centre +- 10*radius*(1,1,1)/sqrt(3), then inclusion_ccd::get_numerical_error(..., use_ms = true). Host-only. */
+int ipcgpu_ti_error(const double* V_soa, int nV, const double* p_interleaved /* may be NULL */, double err_vf[3], double err_ee[3]);
+/* largestFeasibleStepSize_TightInclusion (SelfCollisionHandler.cpp:690-866) over the candidate list cs_PTEE of the last
+ * ipcgpu_constraint_set(getPTEE=1).  alpha_inout: step on entry (max_t of every pair) -> min(alpha, earliest time of impact). */
+int ipcgpu_ccd_partial_ti(ipcgpu_ctx* ctx, const double* p_interleaved /* NULL = last uploaded */, double tolerance,
+    const double err_vf[3], const double err_ee[3], double* alpha_inout);
+/* SpatialHash::build(mesh, searchDir, curMaxStepSize, voxelSize) (SpatialHash.hpp:589-750): alpha_inout is scaled down when
+ * spanSize = alpha*mean|p|/h > 1 exactly like the reference (:603-618). */
+int ipcgpu_hash_build_swept(ipcgpu_ctx* ctx, const double* p_interleaved /* NULL = last uploaded */, double* alpha_inout, double voxel_size);
+/* largestFeasibleStepSize_CCD_TightInclusion (SelfCollisionHandler.cpp:1370-1630) over the candidates of the swept hash.
+ * n_candidates (may be NULL) receives the number of PT+EE pairs sent to the narrow phase. */
+int ipcgpu_ccd_full_ti(ipcgpu_ctx* ctx, double tolerance, const double err_vf[3], const double err_ee[3], double* alpha_inout, uint64_t* n_candidates);
+/* diagnostics of the last narrow phase: candidates tested, pairs surviving the root box, conservative early-outs (should be 0) */
+int ipcgpu_ccd_stats(ipcgpu_ctx* ctx, uint64_t* candidates, uint64_t* survivors, uint64_t* warnings);
+
 /* LinSysSolver::setZero (LinSysSolver.hpp:348) on the device-resident value array */
 int ipcgpu_csr_set_zero(ipcgpu_ctx* ctx);
 /* cross-rank reductions over NVLink (no-ops on a single rank): sum of [gradient, CSR values], min of step */

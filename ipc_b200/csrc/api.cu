@@ -2,6 +2,7 @@
 #include "../../include/ipcgpu.h"
 #include "context.h"
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <dlfcn.h>
 #include <numeric>
@@ -153,6 +154,10 @@ static int ensure_offsets(ipcgpu_ctx* ctx)
 // C++ linkage helpers implemented in constraint.cu / ccd.cu
 int contact_alloc(ipcgpu_ctx* ctx);
 int contact_constraint_set(ipcgpu_ctx* ctx, double dHat, int wantCand, int* nC, int* nPara, int* nCand);
+int ccd_alloc(ipcgpu_ctx* ctx);
+int ccd_narrow(ipcgpu_ctx* ctx, const int2* cand, unsigned long long nCand, double tol, const double* err_vf, const double* err_ee, double* alpha_inout);
+int ccd_build_swept(ipcgpu_ctx* ctx, const double* p_host, double* alpha_inout, double h);
+int ccd_full(ipcgpu_ctx* ctx, double tol, const double* err_vf, const double* err_ee, double* alpha_inout, unsigned long long* nCandOut);
 
 extern "C" {
 
@@ -298,7 +303,10 @@ int ipcgpu_step_forward(ipcgpu_ctx* ctx, const double* p, double alpha)
 {
     REQUIRE(ctx->nV > 0, IPCGPU_ERR_STATE, "ipcgpu_set_mesh first");
     CK(cudaSetDevice(ctx->device));
-    if (p) CK(cudaMemcpyAsync(ctx->dir.p, p, (size_t)3 * ctx->nV * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (p) {
+        ctx->h_dir.assign(p, p + (size_t)3 * ctx->nV);
+        CK(cudaMemcpyAsync(ctx->dir.p, p, (size_t)3 * ctx->nV * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
     step_forward(ctx->nV, ctx->Vsaved.p, ctx->dir.p, alpha, ctx->V.p, ctx->stream);
     ++ctx->launches;
     CK(cudaGetLastError());
@@ -411,7 +419,10 @@ int ipcgpu_inversion_step(ipcgpu_ctx* ctx, const double* p, double slack, double
     REQUIRE(ctx->maps_ready, IPCGPU_ERR_STATE, "ipcgpu_set_mesh first");
     REQUIRE(alpha_inout != nullptr, IPCGPU_ERR_ARG, "alpha_inout is null");
     CK(cudaSetDevice(ctx->device));
-    if (p) CK(cudaMemcpyAsync(ctx->dir.p, p, (size_t)3 * ctx->nV * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (p) {
+        ctx->h_dir.assign(p, p + (size_t)3 * ctx->nV);
+        CK(cudaMemcpyAsync(ctx->dir.p, p, (size_t)3 * ctx->nV * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
     const unsigned long long init = 0x7ff0000000000000ull; // +inf
     CK(cudaMemcpyAsync(ctx->min_ord.p, &init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
     cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_INVERSION);
@@ -446,9 +457,114 @@ int ipcgpu_set_surface(ipcgpu_ctx* ctx, int nSV, const int* SVI, int nSE, const 
     ctx->has_codim = vCoDim != nullptr;
     if (vCoDim) REQUIRE(ctx->vCoDim.upload(vCoDim, ctx->nV, ctx->stream), IPCGPU_ERR_CUDA, "codim upload failed");
     CK(cudaStreamSynchronize(ctx->stream));
+    ctx->h_SVI.assign(SVI, SVI + nSV);
     int rc = contact_alloc(ctx);
     if (rc) return rc;
+    if ((rc = ccd_alloc(ctx))) return rc;
     ctx->surface_ready = true;
+    return IPCGPU_OK;
+}
+
+int ipcgpu_set_ccd_capacity(ipcgpu_ctx* ctx, uint64_t capacity)
+{
+    REQUIRE(capacity > 0 && capacity < 0xffffffffull, IPCGPU_ERR_ARG, "capacity out of range");
+    ctx->ccd_capacity = (size_t)capacity;
+    if (ctx->surface_ready) return ccd_alloc(ctx);
+    return IPCGPU_OK;
+}
+
+int ipcgpu_ti_error(const double* V, int nV, const double* p, double err_vf[3], double err_ee[3])
+{
+    if (!V || nV <= 0 || !err_vf || !err_ee) return IPCGPU_ERR_ARG;
+    double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
+    for (int v = 0; v < nV; ++v)
+        for (int c = 0; c < 3; ++c) {
+            const double x = V[(size_t)c * nV + v];
+            lo[c] = std::min(lo[c], x);
+            hi[c] = std::max(hi[c], x);
+            if (p) {
+                const double y = x + p[3 * (size_t)v + c];
+                lo[c] = std::min(lo[c], y);
+                hi[c] = std::max(hi[c], y);
+            }
+        }
+    double diag2 = 0.0;
+    for (int c = 0; c < 3; ++c) diag2 += (hi[c] - lo[c]) * (hi[c] - lo[c]);
+    const double radius = 0.5 * std::sqrt(diag2);
+    // Tight-Inclusion get_numerical_error with minimum separation: filter * max(1, |x|max)^3
+    const double ee_filter = 7.105427357601002e-15, vf_filter = 7.549516567451064e-15;
+    for (int c = 0; c < 3; ++c) {
+        const double center = 0.5 * (lo[c] + hi[c]);
+        const double a = center - 10.0 * radius / std::sqrt(3.0), b = center + 10.0 * radius / std::sqrt(3.0);
+        double m = std::max(std::fabs(a), std::fabs(b));
+        m = std::max(m, 1.0);
+        err_ee[c] = m * m * m * ee_filter;
+        err_vf[c] = m * m * m * vf_filter;
+    }
+    return IPCGPU_OK;
+}
+
+static int upload_dir(ipcgpu_ctx* ctx, const double* p)
+{
+    if (p) {
+        ctx->h_dir.assign(p, p + (size_t)3 * ctx->nV);
+        CK(cudaMemcpyAsync(ctx->dir.p, p, (size_t)3 * ctx->nV * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    REQUIRE(ctx->h_dir.size() == (size_t)3 * ctx->nV, IPCGPU_ERR_STATE, "no search direction uploaded yet");
+    return IPCGPU_OK;
+}
+
+static int allreduce_min_step(ipcgpu_ctx* ctx, double* alpha)
+{
+    if (ctx->nranks <= 1) return IPCGPU_OK;
+    // ranks hold disjoint candidate ranges: min of the non-negative steps via their order-preserving integer image
+    CK(cudaMemcpyAsync(ctx->min_ord.p, alpha, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    int r = g_nccl.AllReduce(ctx->min_ord.p, ctx->min_ord.p, 1, kNcclUint64, kNcclMin, ctx->nccl_comm, ctx->stream);
+    REQUIRE(r == 0, IPCGPU_ERR_NCCL, "ncclAllReduce(min step) failed");
+    CK(cudaMemcpyAsync(alpha, ctx->min_ord.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return IPCGPU_OK;
+}
+
+int ipcgpu_ccd_partial_ti(ipcgpu_ctx* ctx, const double* p, double tol, const double err_vf[3], const double err_ee[3], double* alpha_inout)
+{
+    REQUIRE(ctx->surface_ready, IPCGPU_ERR_STATE, "ipcgpu_set_surface first");
+    REQUIRE(alpha_inout && err_vf && err_ee, IPCGPU_ERR_ARG, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    int rc = upload_dir(ctx, p);
+    if (rc) return rc;
+    // CFL_FOR_CCD != 0: empty candidate list returns immediately (:700)
+    const unsigned long long n = (unsigned long long)ctx->cw.nK;
+    const unsigned long long b = n * ctx->rank / ctx->nranks, e = n * (ctx->rank + 1) / ctx->nranks;
+    if ((rc = ccd_narrow(ctx, ctx->cw.cand.p + b, e - b, tol, err_vf, err_ee, alpha_inout))) return rc;
+    return allreduce_min_step(ctx, alpha_inout);
+}
+
+int ipcgpu_hash_build_swept(ipcgpu_ctx* ctx, const double* p, double* alpha_inout, double h)
+{
+    REQUIRE(ctx->surface_ready, IPCGPU_ERR_STATE, "ipcgpu_set_surface first");
+    REQUIRE(alpha_inout && h > 0.0, IPCGPU_ERR_ARG, "bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    return ccd_build_swept(ctx, p, alpha_inout, h);
+}
+
+int ipcgpu_ccd_full_ti(ipcgpu_ctx* ctx, double tol, const double err_vf[3], const double err_ee[3], double* alpha_inout, uint64_t* n_candidates)
+{
+    REQUIRE(ctx->surface_ready && ctx->ccd.swept_ready, IPCGPU_ERR_STATE, "ipcgpu_hash_build_swept first");
+    REQUIRE(alpha_inout && err_vf && err_ee, IPCGPU_ERR_ARG, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    unsigned long long nc = 0;
+    int rc = ccd_full(ctx, tol, err_vf, err_ee, alpha_inout, &nc);
+    if (n_candidates) *n_candidates = nc;
+    if (rc) return rc;
+    return allreduce_min_step(ctx, alpha_inout);
+}
+
+int ipcgpu_ccd_stats(ipcgpu_ctx* ctx, uint64_t* candidates, uint64_t* survivors, uint64_t* warnings)
+{
+    if (candidates) *candidates = ctx->ccd.last_candidates;
+    if (survivors) *survivors = ctx->ccd.last_survivors;
+    if (warnings) *warnings = (uint64_t)ctx->ccd.last_warnings;
     return IPCGPU_OK;
 }
 

@@ -1,0 +1,824 @@
+// ccd.cu -- CCD line-search step bound: swept broad phase + Tight-Inclusion narrow phase + device-wide min (sm_100a).
+//   *** this translation unit is compiled with --fmad=false ***  (bit-exact step bound: every product/sum is rounded
+//   exactly like the CPU oracle built with -ffp-contract=off; see __graft_entry__.py NOFMA_FILES)
+//
+// Reference being replaced:
+//   SpatialHash<3>::build(mesh, searchDir, curMaxStepSize, voxelSize)          src/Utils/SpatialHash.hpp:589-750
+//   SpatialHash queries  queryPointForPrimitives / queryEdgeForEdgesWithBBoxCheck  :752-773, :803-832
+//   SelfCollisionHandler::largestFeasibleStepSize_TightInclusion (partial)      src/CollisionObject/SelfCollisionHandler.cpp:690-866
+//   SelfCollisionHandler::largestFeasibleStepSize_CCD_TightInclusion (full)     :1370-1630
+//   inclusion_ccd::vertexFaceCCD_double / edgeEdgeCCD_double (un-vendored Tight-Inclusion; restated from the published algorithm)
+//
+// Structure
+//   broad phase : the same sort-based coarse grid as the constraint set, over SWEPT boxes; a pair becomes a candidate iff
+//                 the reference's own voxel ranges (cell = avgEdgeLen/3, origin = swept bbox corner) overlap -- i.e. exactly
+//                 the pairs the reference's hash query returns -- plus its swept-AABB test for edge pairs.
+//   narrow, stage 1 (thread per candidate, HBM-bound: 8 B pair + 4 x 48 B gather): current distance, ms, and the ROOT box
+//                 of the interval search; a candidate whose root box excludes the origin cannot collide and dies here.
+//   narrow, stage 2 (warp per surviving pair, persistent CTAs + atomic work counter): level-synchronous breadth-first
+//                 interval bisection.  The library's (level, t_lo) priority order is realised without sorting: per level,
+//                 two warp min-reductions over the lexicographic key (t_lo,u_lo,v_lo) give the first box containing the
+//                 origin and the first "terminal" box, which is all the sequential semantics depend on.
+//   reduction   : atomicMin on the order-preserving uint64 image of the (non-negative) time of impact.
+#include "broadphase.cuh"
+#include "context.h"
+#include "../../include/ipcgpu.h"
+#include <cub/cub.cuh>
+
+namespace ipcgpu {
+
+// ------------------------------------------------------------------------------------------------------------------
+// reference voxel ranges of every surface vertex on the swept grid (SpatialHash.hpp:642-662, :841-845)
+// ------------------------------------------------------------------------------------------------------------------
+struct RefGrid {
+    double lo[3];
+    double inv_h;
+};
+
+__global__ void __launch_bounds__(256) k_ref_ranges(SurfArgs s, const double* __restrict__ dir, double alpha, RefGrid g, int* __restrict__ vmin, int* __restrict__ vmax)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= s.nSV) return;
+    const int v = s.SVI[i];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const double x = s.V[(size_t)c * s.nV + v];
+        const double xt = x + alpha * dir[3 * (size_t)v + c];
+        const int a = (int)floor((x - g.lo[c]) * g.inv_h), b = (int)floor((xt - g.lo[c]) * g.inv_h);
+        vmin[3 * (size_t)v + c] = min(a, b);
+        vmax[3 * (size_t)v + c] = max(a, b);
+    }
+}
+
+// bbox of all vertices (V) and of the displaced surface vertices: bounds[0..2] min, [3..5] max (flipped-order uint64)
+__global__ void __launch_bounds__(256) k_swept_bounds(SurfArgs s, const double* __restrict__ dir, double alpha, unsigned long long* __restrict__ bounds)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
+    if (i < s.nV) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) lo[c] = hi[c] = s.V[(size_t)c * s.nV + i];
+    }
+    if (i < s.nSV) {
+        const int v = s.SVI[i];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double xt = s.V[(size_t)c * s.nV + v] + alpha * dir[3 * (size_t)v + c];
+            lo[c] = fmin(lo[c], xt);
+            hi[c] = fmax(hi[c], xt);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        double a = lo[c], b = hi[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a = fmin(a, __shfl_xor_sync(0xffffffffu, a, o));
+            b = fmax(b, __shfl_xor_sync(0xffffffffu, b, o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(bounds + c, flip_ord(a));
+            atomicMax(bounds + 3 + c, flip_ord(b));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// broad-phase queries on the coarse grid with the reference's exact candidate filter
+// ------------------------------------------------------------------------------------------------------------------
+DEV bool ranges_overlap(const int* alo, const int* ahi, const int* blo, const int* bhi)
+{
+    return !(blo[0] > ahi[0] || bhi[0] < alo[0] || blo[1] > ahi[1] || bhi[1] < alo[1] || blo[2] > ahi[2] || bhi[2] < alo[2]);
+}
+DEV void prim_range(const int* __restrict__ vmin, const int* __restrict__ vmax, const int* vs, int n, int* lo, int* hi)
+{
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        lo[c] = vmin[3 * (size_t)vs[0] + c];
+        hi[c] = vmax[3 * (size_t)vs[0] + c];
+        for (int k = 1; k < n; ++k) {
+            lo[c] = min(lo[c], vmin[3 * (size_t)vs[k] + c]);
+            hi[c] = max(hi[c], vmax[3 * (size_t)vs[k] + c]);
+        }
+    }
+}
+DEV bool dbc_v(const SurfArgs& s, int v) { return s.dbc && s.dbc[v] != 0; }
+DEV int cod_v(const SurfArgs& s, int v) { return s.vCoDim ? s.vCoDim[v] : 3; }
+
+struct CandOut {
+    int2* cand;
+    unsigned long long* n;
+    unsigned long long cap;
+    int* overflow;
+};
+DEV void push_cand(const CandOut& o, int2 c)
+{
+    unsigned long long i = atomicAdd(o.n, 1ull);
+    if (i < o.cap) o.cand[i] = c;
+    else atomicExch(o.overflow, 1);
+}
+
+__global__ void __launch_bounds__(128) k_ccd_query_pt(SurfArgs s, const Grid* __restrict__ gp, const Box* __restrict__ vboxes, const Box* __restrict__ tboxes,
+    const unsigned long long* __restrict__ keys, const int* __restrict__ vals, int nEntries, const int* __restrict__ vmin, const int* __restrict__ vmax, double radius,
+    CandOut out)
+{
+    const int svI = blockIdx.x * blockDim.x + threadIdx.x;
+    if (svI >= s.nSV) return;
+    const Grid g = *gp;
+    const int vI = s.SVI[svI];
+    Box qb = vboxes[svI];
+    for (int k = 0; k < 3; ++k) { qb.lo[k] -= radius; qb.hi[k] += radius; }
+    int c0[3], c1[3];
+    cell_range(g, qb, c0, c1);
+    const int* plo = vmin + 3 * (size_t)vI;
+    const int* phi = vmax + 3 * (size_t)vI;
+    const int vcod = cod_v(s, vI);
+    const bool vdbc = dbc_v(s, vI);
+    for (int iz = c0[2]; iz <= c1[2]; ++iz)
+        for (int iy = c0[1]; iy <= c1[1]; ++iy)
+            for (int ix = c0[0]; ix <= c1[0]; ++ix) {
+                const unsigned long long key = cell_key(g, ix, iy, iz);
+                for (int e = lower_bound_u64(keys, nEntries, key); e < nEntries && keys[e] == key; ++e) {
+                    const int sfI = vals[e];
+                    int t0[3], t1[3];
+                    cell_range(g, tboxes[sfI], t0, t1);
+                    if (max(t0[0], c0[0]) != ix || max(t0[1], c0[1]) != iy || max(t0[2], c0[2]) != iz) continue;
+                    int tv[3] = { s.SF[sfI], s.SF[(size_t)s.nSF + sfI], s.SF[(size_t)2 * s.nSF + sfI] };
+                    int lo[3], hi[3];
+                    prim_range(vmin, vmax, tv, 3, lo, hi);
+                    if (!ranges_overlap(plo, phi, lo, hi)) continue; // the reference's hash would not pair them
+                    if (vI == tv[0] || vI == tv[1] || vI == tv[2]) continue;
+                    if ((vcod < 3 && cod_v(s, tv[0]) < 3) || (vdbc && dbc_v(s, tv[0]) && dbc_v(s, tv[1]) && dbc_v(s, tv[2]))) continue;
+                    push_cand(out, make_int2(-svI - 1, sfI));
+                }
+            }
+}
+
+__global__ void __launch_bounds__(128) k_ccd_query_ee(SurfArgs s, const Grid* __restrict__ gp, const Box* __restrict__ eboxes,
+    const unsigned long long* __restrict__ keys, const int* __restrict__ vals, int nEntries, const int* __restrict__ vmin, const int* __restrict__ vmax, double radius,
+    CandOut out)
+{
+    const int eI = blockIdx.x * blockDim.x + threadIdx.x;
+    if (eI >= s.nSE) return;
+    const Grid g = *gp;
+    const int a[2] = { s.SE[2 * eI], s.SE[2 * eI + 1] };
+    const Box eb = eboxes[eI];
+    Box qb = eb;
+    for (int k = 0; k < 3; ++k) { qb.lo[k] -= radius; qb.hi[k] += radius; }
+    int c0[3], c1[3];
+    cell_range(g, qb, c0, c1);
+    int qlo[3], qhi[3];
+    prim_range(vmin, vmax, a, 2, qlo, qhi);
+    const int ecod = cod_v(s, a[0]);
+    const bool edbc = dbc_v(s, a[0]) && dbc_v(s, a[1]);
+    for (int iz = c0[2]; iz <= c1[2]; ++iz)
+        for (int iy = c0[1]; iy <= c1[1]; ++iy)
+            for (int ix = c0[0]; ix <= c1[0]; ++ix) {
+                const unsigned long long key = cell_key(g, ix, iy, iz);
+                for (int e = lower_bound_u64(keys, nEntries, key); e < nEntries && keys[e] == key; ++e) {
+                    const int eJ = vals[e];
+                    if (eJ <= eI) continue;
+                    const Box jb = eboxes[eJ];
+                    int t0[3], t1[3];
+                    cell_range(g, jb, t0, t1);
+                    if (max(t0[0], c0[0]) != ix || max(t0[1], c0[1]) != iy || max(t0[2], c0[2]) != iz) continue;
+                    const int b[2] = { s.SE[2 * eJ], s.SE[2 * eJ + 1] };
+                    int lo[3], hi[3];
+                    prim_range(vmin, vmax, b, 2, lo, hi);
+                    if (!ranges_overlap(qlo, qhi, lo, hi)) continue;
+                    // swept-AABB test of queryEdgeForEdgesWithBBoxCheck (SpatialHash.hpp:819-828); the boxes hold {x, x+alpha p}
+                    bool sep = false;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) sep = sep || (jb.lo[c] - eb.hi[c] > 0.0) || (eb.lo[c] - jb.hi[c] > 0.0);
+                    if (sep) continue;
+                    if (a[0] == b[0] || a[0] == b[1] || a[1] == b[0] || a[1] == b[1]) continue;
+                    if ((ecod < 3 && cod_v(s, b[0]) < 3) || (edbc && dbc_v(s, b[0]) && dbc_v(s, b[1]))) continue;
+                    push_cand(out, make_int2(eI, eJ));
+                }
+            }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Tight-Inclusion pieces shared by both narrow-phase stages
+// ------------------------------------------------------------------------------------------------------------------
+struct TiPair {
+    double x0[12], x1[12]; // 4 vertices at t=0 / t=1 ; VF: (p,t0,t1,t2)  EE: (a0,a1,b0,b1)
+};
+struct DBox { // parameter box: [n/2^k, (n+1)/2^k] per axis; kk = tk | uk<<8 | vk<<16 | flags<<24
+    unsigned long long tn, un, vn;
+    unsigned kk;
+    unsigned pad;
+};
+DEV double pow2neg(int k) { return __longlong_as_double((long long)(1023 - k) << 52); }
+DEV double dy_lo(unsigned long long n, int k) { return (double)n * pow2neg(k); }
+DEV double dy_hi(unsigned long long n, int k) { return (double)(n + 1) * pow2neg(k); }
+
+// co-domain test of one box: returns zero_in; sets box_in and max/each true_tol   (oracle: origin_in_box)
+template <bool VF>
+DEV bool origin_in_box(const TiPair& P, const DBox& b, const double* err, double ms, bool& box_in, double* true_tol)
+{
+    const int tk = b.kk & 0xff, uk = (b.kk >> 8) & 0xff, vk = (b.kk >> 16) & 0xff;
+    const double tv[2] = { dy_lo(b.tn, tk), dy_hi(b.tn, tk) }, uv[2] = { dy_lo(b.un, uk), dy_hi(b.un, uk) }, vv[2] = { dy_lo(b.vn, vk), dy_hi(b.vn, vk) };
+    box_in = true;
+    bool zero_in = true;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        double mn = 1e300, mx = -1e300;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            double p[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) p[k] = (P.x1[3 * k + c] - P.x0[3 * k + c]) * tv[i] + P.x0[3 * k + c];
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int l = 0; l < 2; ++l) {
+                    double f;
+                    if (VF) {
+                        const double pt = ((p[2] - p[1]) * uv[j] + (p[3] - p[1]) * vv[l]) + p[1];
+                        f = p[0] - pt;
+                    }
+                    else {
+                        const double pa = (p[1] - p[0]) * uv[j] + p[0];
+                        const double pb = (p[3] - p[2]) * vv[l] + p[2];
+                        f = pa - pb;
+                    }
+                    mn = fmin(mn, f);
+                    mx = fmax(mx, f);
+                }
+        }
+        true_tol[c] = mx - mn;
+        const double eps = err[c] + ms;
+        if (mn > eps || mx < -eps) zero_in = false;
+        if (!(mn >= -eps && mx <= eps)) box_in = false;
+    }
+    return zero_in;
+}
+
+DEV double linf3(const double* a, const double* b) { return fmax(fmax(fabs(a[0] - b[0]), fabs(a[1] - b[1])), fabs(a[2] - b[2])); }
+
+template <bool VF>
+DEV void width_tolerances(const TiPair& P, double tolerance, double* tol)
+{
+    double ps[4][3], pe[4][3];
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+        const double* x = side ? P.x1 : P.x0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            double q0, q1, q2, q3;
+            if (VF) {
+                q0 = x[c] - x[3 + c];
+                q1 = x[c] - x[9 + c];
+                q2 = x[c] - (x[6 + c] + x[9 + c] - x[3 + c]);
+                q3 = x[c] - x[6 + c];
+            }
+            else {
+                q0 = x[c] - x[6 + c];
+                q1 = x[c] - x[9 + c];
+                q2 = x[3 + c] - x[9 + c];
+                q3 = x[3 + c] - x[6 + c];
+            }
+            if (side) { pe[0][c] = q0; pe[1][c] = q1; pe[2][c] = q2; pe[3][c] = q3; }
+            else { ps[0][c] = q0; ps[1][c] = q1; ps[2][c] = q2; ps[3][c] = q3; }
+        }
+    }
+    double dl = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dl = fmax(dl, linf3(pe[q], ps[q]));
+    const double e0 = fmax(fmax(linf3(ps[3], ps[0]), linf3(pe[3], pe[0])), fmax(linf3(pe[2], pe[1]), linf3(ps[2], ps[1])));
+    const double e1 = fmax(fmax(linf3(ps[1], ps[0]), linf3(pe[1], pe[0])), fmax(linf3(pe[2], pe[3]), linf3(ps[2], ps[3])));
+    tol[0] = tolerance / (3.0 * dl);
+    tol[1] = tolerance / (3.0 * e0);
+    tol[2] = tolerance / (3.0 * e1);
+}
+
+DEV void load_pair(const SurfArgs& s, const double* __restrict__ dir, int2 c, bool& vf, int* v, TiPair& P)
+{
+    vf = c.x < 0;
+    if (vf) {
+        const int svI = -c.x - 1, sfI = c.y;
+        v[0] = s.SVI[svI]; v[1] = s.SF[sfI]; v[2] = s.SF[(size_t)s.nSF + sfI]; v[3] = s.SF[(size_t)2 * s.nSF + sfI];
+    }
+    else {
+        v[0] = s.SE[2 * c.x]; v[1] = s.SE[2 * c.x + 1]; v[2] = s.SE[2 * c.y]; v[3] = s.SE[2 * c.y + 1];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const double x = __ldg(s.V + (size_t)q * s.nV + v[k]);
+            P.x0[3 * k + q] = x;
+            P.x1[3 * k + q] = x + __ldg(dir + 3 * (size_t)v[k] + q);
+        }
+}
+
+DEV double pair_distance_sqrt(bool vf, const TiPair& P)
+{
+    const V3 a = { P.x0[0], P.x0[1], P.x0[2] }, b = { P.x0[3], P.x0[4], P.x0[5] }, c = { P.x0[6], P.x0[7], P.x0[8] }, d = { P.x0[9], P.x0[10], P.x0[11] };
+    return sqrt(vf ? point_tri_d(a, b, c, d) : edge_edge_d(a, b, c, d));
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// stage 1: one thread per candidate
+// ------------------------------------------------------------------------------------------------------------------
+struct NarrowArgs {
+    SurfArgs s;
+    const double* dir;
+    const int2* cand;
+    unsigned long long nCand;
+    double err_vf[3], err_ee[3];
+    double tol, max_t;
+    int max_itr;
+};
+
+__global__ void __launch_bounds__(128) k_ti_stage1(NarrowArgs a, unsigned* __restrict__ survivors, unsigned* __restrict__ nSurv, int* __restrict__ zero_flag)
+{
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool alive = false;
+    if (i < a.nCand) {
+        bool vf;
+        int v[4];
+        TiPair P;
+        load_pair(a.s, a.dir, a.cand[i], vf, v, P);
+        const double d = pair_distance_sqrt(vf, P);
+        if (d == 0.0) atomicExch(zero_flag, 1); // "Initial CCD distance is zero! Returning 0 stepSize." (:730-737)
+        else {
+            const double ms = fmin(0.2 * d, 1e-6);
+            DBox root = { 0ull, 0ull, 0ull, 0u, 0u };
+            bool box_in;
+            double tt[3];
+            alive = vf ? origin_in_box<true>(P, root, a.err_vf, ms, box_in, tt) : origin_in_box<false>(P, root, a.err_ee, ms, box_in, tt);
+        }
+    }
+    // warp-aggregated append of the survivors
+    const unsigned m = __ballot_sync(0xffffffffu, alive);
+    if (m) {
+        const int lane = threadIdx.x & 31;
+        unsigned base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(nSurv, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (alive) survivors[base + __popc(m & ((1u << lane) - 1))] = (unsigned)i;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// stage 2: warp per surviving pair
+// ------------------------------------------------------------------------------------------------------------------
+struct Key3 {
+    double t, u, v;
+};
+DEV bool key_less(const Key3& a, const Key3& b)
+{
+    if (a.t != b.t) return a.t < b.t;
+    if (a.u != b.u) return a.u < b.u;
+    return a.v < b.v;
+}
+// warp min of (key, payload)
+DEV void warp_min_key(Key3& k, unsigned& pay, double& aux)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        Key3 r;
+        r.t = __shfl_xor_sync(0xffffffffu, k.t, o);
+        r.u = __shfl_xor_sync(0xffffffffu, k.u, o);
+        r.v = __shfl_xor_sync(0xffffffffu, k.v, o);
+        const unsigned rp = __shfl_xor_sync(0xffffffffu, pay, o);
+        const double ra = __shfl_xor_sync(0xffffffffu, aux, o);
+        if (key_less(r, k)) {
+            k = r;
+            pay = rp;
+            aux = ra;
+        }
+    }
+}
+DEV bool sum_le_1(unsigned long long an, int ak, unsigned long long bn, int bk)
+{
+    // lo(a) + lo(b) <= 1 exactly; k <= 60 so the aligned sum fits in 64 bits when the larger exponent is used carefully
+    const int k = max(ak, bk);
+    // n < 2^ak: n << (k-ak) < 2^k <= 2^60 -> the sum is < 2^61
+    const unsigned long long s = (an << (k - ak)) + (bn << (k - bk));
+    return s <= (1ull << k);
+}
+
+constexpr unsigned F_ZERO = 1u << 24; // zero_in flag stored in DBox::kk
+
+// result codes of the root finder
+template <bool VF>
+__device__ bool ti_root_finder(const TiPair& P, const double* tol, double co_tol, double max_t, const double* err, double ms, int max_itr, DBox* bufA,
+    DBox* bufB, int cap, int lane, double& toi, double& out_tol, int* __restrict__ warn)
+{
+    const bool check_t = (max_t != 1.0);
+    const double INF = __longlong_as_double(0x7ff0000000000000ll);
+    DBox* cur = bufA;
+    DBox* nxt = bufB;
+    if (lane == 0) cur[0] = DBox{ 0ull, 0ull, 0ull, 0u, 0u };
+    __syncwarp();
+    int n = 1;
+    double toi_skip = INF;
+    bool use_skip = false;
+    long long refine = 0;
+    double temp_toi = INF, temp_out_tol = co_tol;
+    out_tol = co_tol;
+    toi = INF;
+    while (n > 0) {
+        // ---- pass 1: evaluate, find K1 (first box containing the origin) and K2 (first terminal box) ----------
+        Key3 k1 = { INF, INF, INF }, k2 = { INF, INF, INF };
+        unsigned p1 = 0, p2 = 0; // payload bit0: flagged (K1) / cond1 (K2)
+        double a1 = 0.0, a2 = 0.0;
+        int visited = 0;
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + lane;
+            Key3 mk1 = { INF, INF, INF }, mk2 = { INF, INF, INF };
+            unsigned mp1 = 0, mp2 = 0;
+            double ma1 = 0.0, ma2 = 0.0;
+            bool vis = false;
+            if (i < n) {
+                DBox b = cur[i];
+                const int tk = b.kk & 0xff, uk = (b.kk >> 8) & 0xff, vk = (b.kk >> 16) & 0xff;
+                const double tlo = dy_lo(b.tn, tk);
+                unsigned flags = 0;
+                if (tlo < toi_skip) {
+                    vis = true;
+                    bool box_in;
+                    double tt[3];
+                    if (origin_in_box<VF>(P, b, err, ms, box_in, tt)) {
+                        flags = F_ZERO;
+                        const bool tol_cond = tt[0] <= co_tol && tt[1] <= co_tol && tt[2] <= co_tol;
+                        const bool cond1 = pow2neg(tk) <= tol[0] && pow2neg(uk) <= tol[1] && pow2neg(vk) <= tol[2];
+                        const Key3 key = { tlo, dy_lo(b.un, uk), dy_lo(b.vn, vk) };
+                        mk1 = key;
+                        mp1 = (tol_cond || box_in || cond1) ? 1u : 0u;
+                        ma1 = fmax(fmax(tt[0], tt[1]), tt[2]);
+                        if (mp1) {
+                            mk2 = key;
+                            mp2 = cond1 ? 1u : 0u;
+                        }
+                    }
+                }
+                cur[i].kk = (b.kk & 0x00ffffffu) | flags;
+            }
+            visited += __popc(__ballot_sync(0xffffffffu, vis));
+            warp_min_key(mk1, mp1, ma1);
+            warp_min_key(mk2, mp2, ma2);
+            if (key_less(mk1, k1)) { k1 = mk1; p1 = mp1; a1 = ma1; }
+            if (key_less(mk2, k2)) { k2 = mk2; p2 = mp2; a2 = ma2; }
+        }
+        __syncwarp();
+        const bool any_zero = k1.t != INF;
+        if (!any_zero) { // nothing at this level contains the origin: the search space is exhausted
+            n = 0;
+            break;
+        }
+        if (p1 & 1u) { // the first box containing the origin is terminal: conditions 1/2/3 of the library
+            toi = k1.t;
+            return true;
+        }
+        const bool has_k2 = k2.t != INF;
+        if (has_k2 && (p2 & 1u)) { // a later box already below the width tolerances (condition 1)
+            // boxes between K1 and K2 do not matter: the library returns here
+            toi = k2.t;
+            return true;
+        }
+        if (max_itr > 0) {
+            temp_toi = k1.t;
+            temp_out_tol = fmax(a1, co_tol);
+            refine += visited;
+            if (refine > max_itr) { // conservative early-out (the library returns its per-level estimate here as well)
+                if (lane == 0) atomicAdd(warn, 1);
+                toi = temp_toi;
+                out_tol = temp_out_tol;
+                return true;
+            }
+        }
+        if (has_k2) {
+            if (k2.t < toi_skip) toi_skip = k2.t;
+            use_skip = true;
+        }
+        // ---- pass 2: split every box that contains the origin and precedes K2 ------------------------------------------
+        int nn = 0;
+        bool over = false;
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + lane;
+            int nchild = 0;
+            DBox c0, c1;
+            if (i < n) {
+                const DBox b = cur[i];
+                if (b.kk & F_ZERO) {
+                    const int tk = b.kk & 0xff, uk = (b.kk >> 8) & 0xff, vk = (b.kk >> 16) & 0xff;
+                    const Key3 key = { dy_lo(b.tn, tk), dy_lo(b.un, uk), dy_lo(b.vn, vk) };
+                    if (!has_k2 || key_less(key, k2)) {
+                        const double w[3] = { pow2neg(tk), pow2neg(uk), pow2neg(vk) };
+                        int split = -1;
+                        double best = -1.0;
+#pragma unroll
+                        for (int d = 0; d < 3; ++d)
+                            if (w[d] > tol[d]) {
+                                const double r = w[d] / tol[d];
+                                if (r > best) { best = r; split = d; }
+                            }
+                        const int pk = split == 0 ? tk : (split == 1 ? uk : vk);
+                        if (split < 0 || pk >= 60) over = true; // bisection overflow: handled like the iteration overflow
+                        else {
+                            const unsigned long long pn = split == 0 ? b.tn : (split == 1 ? b.un : b.vn);
+#pragma unroll
+                            for (int half = 0; half < 2; ++half) {
+                                const unsigned long long hn = 2 * pn + half;
+                                const int hk = pk + 1;
+                                bool keep = true;
+                                if (split == 0) { if (check_t) keep = !(dy_hi(hn, hk) < 0.0 || dy_lo(hn, hk) > max_t); }
+                                else if (VF) keep = (split == 1) ? sum_le_1(hn, hk, b.vn, vk) : sum_le_1(hn, hk, b.un, uk);
+                                if (keep) {
+                                    DBox c = b;
+                                    c.kk &= 0x00ffffffu;
+                                    if (split == 0) { c.tn = hn; c.kk = (c.kk & ~0xffu) | (unsigned)hk; }
+                                    else if (split == 1) { c.un = hn; c.kk = (c.kk & ~0xff00u) | ((unsigned)hk << 8); }
+                                    else { c.vn = hn; c.kk = (c.kk & ~0xff0000u) | ((unsigned)hk << 16); }
+                                    if (nchild == 0) c0 = c;
+                                    else c1 = c;
+                                    ++nchild;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            // warp exclusive scan of nchild
+            int incl = nchild;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += y;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            const int off = nn + incl - nchild;
+            if (nn + total > cap) over = true;
+            else {
+                if (nchild > 0) nxt[off] = c0;
+                if (nchild > 1) nxt[off + 1] = c1;
+            }
+            nn += total;
+            if (__any_sync(0xffffffffu, over)) { over = true; break; }
+        }
+        if (__any_sync(0xffffffffu, over)) {
+            // level buffer / bisection depth exhausted: return the conservative per-level estimate (earliest box containing the origin)
+            if (lane == 0) atomicAdd(warn, 1);
+            toi = temp_toi;
+            out_tol = temp_out_tol;
+            return true;
+        }
+        __syncwarp();
+        DBox* t = cur; cur = nxt; nxt = t;
+        n = nn;
+    }
+    if (use_skip) {
+        toi = toi_skip;
+        return true;
+    }
+    return false;
+}
+
+// vertexFaceCCD_double / edgeEdgeCCD_double including the no_zero_toi refinement loop
+template <bool VF>
+__device__ bool ti_ccd(const TiPair& P, const double* err, double ms, double tolerance, double t_max, int max_itr, DBox* bufA, DBox* bufB, int cap, int lane,
+    double& toi, int* __restrict__ warn)
+{
+    double tolerance_in = tolerance, ms_in = ms, out_tol = tolerance;
+    bool is_impacting = false, tmp = false;
+    unsigned iter = 0;
+    do {
+        double tol[3];
+        width_tolerances<VF>(P, tolerance_in, tol);
+        tmp = ti_root_finder<VF>(P, tol, tolerance_in, t_max, err, ms_in, max_itr, bufA, bufB, cap, lane, toi, out_tol, warn);
+        if (iter == 0) is_impacting = tmp;
+        else toi = tmp ? toi : t_max;
+        if (tmp && toi == 0.0) {
+            if (out_tol > tolerance_in) t_max *= 0.9;
+            else if (10 * tolerance_in < ms_in) ms_in *= 0.5;
+            else tolerance_in *= 0.1;
+        }
+        ++iter;
+    } while (iter < 0x7fffffffu && tmp && toi == 0.0);
+    return is_impacting;
+}
+
+__global__ void __launch_bounds__(128) k_ti_stage2(NarrowArgs a, const unsigned* __restrict__ survivors, const unsigned* __restrict__ nSurvPtr, unsigned* __restrict__ work,
+    DBox* __restrict__ scratch, int cap, unsigned long long* __restrict__ min_ord, int* __restrict__ warn)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    DBox* bufA = scratch + (size_t)warp_global * 2 * cap;
+    DBox* bufB = bufA + cap;
+    const unsigned nSurv = *nSurvPtr;
+    for (;;) {
+        unsigned w = 0;
+        if (lane == 0) w = atomicAdd(work, 1u);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= nSurv) break;
+        bool vf;
+        int v[4];
+        TiPair P;
+        load_pair(a.s, a.dir, a.cand[survivors[w]], vf, v, P);
+        const double d = pair_distance_sqrt(vf, P);
+        const double ms = fmin(0.2 * d, 1e-6);
+        double toi;
+        bool hit = vf ? ti_ccd<true>(P, a.err_vf, ms, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn)
+                      : ti_ccd<false>(P, a.err_ee, ms, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn);
+        if (hit && toi < 1e-6) { // :759-781
+            hit = vf ? ti_ccd<true>(P, a.err_vf, 0.0, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn)
+                     : ti_ccd<false>(P, a.err_ee, 0.0, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn);
+            if (hit) toi *= 0.8;
+        }
+        if (hit && lane == 0) atomicMin(min_ord, dbl_to_ord(toi));
+        __syncwarp();
+    }
+}
+
+__global__ void k_ccd_init(unsigned long long* min_ord, double alpha, unsigned* nSurv, unsigned* work, int* flags)
+{
+    if (threadIdx.x == 0) {
+        *min_ord = dbl_to_ord(alpha);
+        *nSurv = 0;
+        *work = 0;
+        flags[0] = flags[1] = flags[2] = 0;
+    }
+}
+
+} // namespace ipcgpu
+
+using namespace ipcgpu;
+
+#define CKD(call)                                                      \
+    do {                                                               \
+        cudaError_t e_ = (call);                                       \
+        if (e_ != cudaSuccess) {                                       \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); \
+            return IPCGPU_ERR_CUDA;                                    \
+        }                                                              \
+    } while (0)
+
+static inline int nblk(long long n, int b) { return (int)((n + b - 1) / b); }
+SurfArgs surf_args(const ipcgpu_ctx* ctx); // constraint.cu
+int boxes_and_grid(ipcgpu_ctx* ctx, const double* dir, double alpha, double radius, bool with_vertex_boxes); // constraint.cu
+
+constexpr int kStage2WarpsPerCta = 4;
+constexpr int kStage2Ctas = 148 * 6; // persistent: 6 CTAs x 4 warps per SM
+constexpr int kLevelCap = 4096;      // boxes per BFS level buffer (2 buffers per warp)
+
+int ccd_alloc(ipcgpu_ctx* ctx)
+{
+    CcdWork& w = ctx->ccd;
+    const size_t warps = (size_t)kStage2Ctas * kStage2WarpsPerCta;
+    bool ok = w.vmin.reserve((size_t)3 * ctx->nV) && w.vmax.reserve((size_t)3 * ctx->nV) && w.cand.reserve(ctx->ccd_capacity) && w.surv.reserve(ctx->ccd_capacity)
+        && w.scratch.reserve(warps * 2 * kLevelCap * sizeof(DBox)) && w.counters.reserve(16) && w.ncand.reserve(2) && w.bounds.reserve(8);
+    if (!ok) {
+        ctx->err = "CCD workspace allocation failed";
+        return IPCGPU_ERR_CUDA;
+    }
+    return 0;
+}
+
+// narrow phase over a device candidate list; alpha_inout is the step bound
+int ccd_narrow(ipcgpu_ctx* ctx, const int2* cand, unsigned long long nCand, double tol, const double* err_vf, const double* err_ee, double* alpha_inout)
+{
+    CcdWork& w = ctx->ccd;
+    cudaStream_t st = ctx->stream;
+    NarrowArgs a;
+    a.s = surf_args(ctx);
+    a.dir = ctx->dir.p;
+    a.cand = cand;
+    a.nCand = nCand;
+    for (int c = 0; c < 3; ++c) { a.err_vf[c] = err_vf[c]; a.err_ee[c] = err_ee[c]; }
+    a.tol = tol;
+    a.max_t = *alpha_inout; // canonical semantics: every pair sees the step on entry
+    a.max_itr = 1000000;    // TIGHT_INCLUSION_MAX_ITER (CCDUtils.hpp:14)
+    unsigned* nSurv = reinterpret_cast<unsigned*>(w.counters.p);
+    unsigned* work = nSurv + 1;
+    int* flags = w.counters.p + 2; // [0] zero distance, [1] warnings, [2] spare
+    cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_CCD_NARROW);
+    k_ccd_init<<<1, 32, 0, st>>>(ctx->min_ord.p, *alpha_inout, nSurv, work, flags);
+    if (nCand > 0) {
+        k_ti_stage1<<<nblk((long long)nCand, 128), 128, 0, st>>>(a, w.surv.p, nSurv, flags);
+        k_ti_stage2<<<kStage2Ctas, 32 * kStage2WarpsPerCta, 0, st>>>(a, w.surv.p, nSurv, work, reinterpret_cast<DBox*>(w.scratch.p), kLevelCap, ctx->min_ord.p, flags + 1);
+    }
+    ctx->prof_end(pe);
+    ctx->launches += 3;
+    CKD(cudaGetLastError());
+    if (ctx->nranks > 1) {
+        // min over ranks of the step (and max of the zero-distance flag) is done by the caller through NCCL (api.cu)
+    }
+    unsigned long long* h = reinterpret_cast<unsigned long long*>(ctx->h_scalar);
+    int* hi = reinterpret_cast<int*>(ctx->h_scalar + 2);
+    CKD(cudaMemcpyAsync(h, ctx->min_ord.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CKD(cudaMemcpyAsync(hi, w.counters.p, 6 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CKD(cudaStreamSynchronize(st));
+    double m;
+    std::memcpy(&m, h, sizeof(double));
+    w.last_survivors = (unsigned)hi[0];
+    w.last_warnings = hi[3];
+    w.last_candidates = nCand;
+    if (hi[2]) *alpha_inout = 0.0; // zero initial distance
+    else *alpha_inout = m;
+    return 0;
+}
+
+// ---- swept hash build: SpatialHash::build(mesh, searchDir, curMaxStepSize, voxelSize) ------------------------------------
+int ccd_build_swept(ipcgpu_ctx* ctx, const double* p_host, double* alpha_inout, double h)
+{
+    CcdWork& w = ctx->ccd;
+    cudaStream_t st = ctx->stream;
+    const SurfArgs s = surf_args(ctx);
+    if (p_host) {
+        ctx->h_dir.assign(p_host, p_host + (size_t)3 * ctx->nV);
+        CKD(cudaMemcpyAsync(ctx->dir.p, p_host, (size_t)3 * ctx->nV * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    if (ctx->h_dir.size() != (size_t)3 * ctx->nV) {
+        ctx->err = "no search direction: pass p (or call ipcgpu_step_forward with p first)";
+        return IPCGPU_ERR_STATE;
+    }
+    // :603-618 -- serial sum in the reference; kept on the host in the same order so that alpha is bit-identical
+    double pSize = 0;
+    const double* p = ctx->h_dir.data();
+    for (int i = 0; i < ctx->nSV; ++i) {
+        const int v = ctx->h_SVI[i];
+        pSize += std::abs(p[3 * (size_t)v]);
+        pSize += std::abs(p[3 * (size_t)v + 1]);
+        pSize += std::abs(p[3 * (size_t)v + 2]);
+    }
+    pSize /= (double)((long long)ctx->nSV * 3);
+    const double span = *alpha_inout * pSize / h;
+    if (span > 1) *alpha_inout /= span;
+    const double alpha = *alpha_inout;
+    cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_CCD_BROAD);
+    // bbox of V and of the displaced surface vertices (:627-628)
+    const unsigned long long init[6] = { ~0ull, ~0ull, ~0ull, 0ull, 0ull, 0ull };
+    CKD(cudaMemcpyAsync(w.bounds.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    k_swept_bounds<<<nblk(std::max(s.nV, s.nSV), 256), 256, 0, st>>>(s, ctx->dir.p, alpha, w.bounds.p);
+    unsigned long long* hb = reinterpret_cast<unsigned long long*>(ctx->h_scalar);
+    CKD(cudaMemcpyAsync(hb, w.bounds.p, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CKD(cudaStreamSynchronize(st));
+    double lo[3], hi[3];
+    for (int c = 0; c < 3; ++c) {
+        unsigned long long a = hb[c], b = hb[3 + c];
+        a = (a >> 63) ? (a & 0x7fffffffffffffffull) : ~a;
+        b = (b >> 63) ? (b & 0x7fffffffffffffffull) : ~b;
+        std::memcpy(&lo[c], &a, 8);
+        std::memcpy(&hi[c], &b, 8);
+    }
+    w.ref_inv_h = 1.0 / h;
+    double rmax = 0;
+    bool bad = false;
+    for (int c = 0; c < 3; ++c) {
+        w.ref_lo[c] = lo[c];
+        w.ref_count[c] = (int)std::ceil((hi[c] - lo[c]) * w.ref_inv_h);
+        rmax = std::max(rmax, hi[c] - lo[c]);
+        if (w.ref_count[c] <= 0) bad = true;
+    }
+    if (bad) { // cast overflow due to a huge search direction (:632-636)
+        w.ref_inv_h = 1.0 / (rmax * 1.01);
+        w.ref_count[0] = w.ref_count[1] = w.ref_count[2] = 1;
+    }
+    w.alpha_grid = alpha;
+    RefGrid g;
+    for (int c = 0; c < 3; ++c) g.lo[c] = w.ref_lo[c];
+    g.inv_h = w.ref_inv_h;
+    if (s.nSV > 0) k_ref_ranges<<<nblk(s.nSV, 256), 256, 0, st>>>(s, ctx->dir.p, alpha, g, w.vmin.p, w.vmax.p);
+    ctx->launches += 2;
+    // coarse accelerator grid over the swept boxes; pairs sharing a reference voxel are at most one voxel apart per axis
+    int rc = boxes_and_grid(ctx, ctx->dir.p, alpha, 1.0 / w.ref_inv_h, true);
+    ctx->prof_end(pe);
+    if (rc) return rc;
+    CKD(cudaGetLastError());
+    w.swept_ready = true;
+    return 0;
+}
+
+int ccd_full(ipcgpu_ctx* ctx, double tol, const double* err_vf, const double* err_ee, double* alpha_inout, unsigned long long* nCandOut)
+{
+    CcdWork& w = ctx->ccd;
+    ContactWork& cw = ctx->cw;
+    cudaStream_t st = ctx->stream;
+    const SurfArgs s = surf_args(ctx);
+    cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_CCD_BROAD);
+    CKD(cudaMemsetAsync(w.ncand.p, 0, 2 * sizeof(unsigned long long), st));
+    CKD(cudaMemsetAsync(w.counters.p + 8, 0, sizeof(int), st));
+    CandOut out{ w.cand.p, w.ncand.p, (unsigned long long)ctx->ccd_capacity, w.counters.p + 8 };
+    const double radius = 1.0 / w.ref_inv_h;
+    if (s.nSV > 0 && s.nSF > 0)
+        k_ccd_query_pt<<<nblk(s.nSV, 128), 128, 0, st>>>(s, cw.grid.p, cw.vbox.p, cw.tbox.p, cw.tkeys.p, cw.tvals.p, 8 * s.nSF, w.vmin.p, w.vmax.p, radius, out);
+    if (s.nSE > 1) k_ccd_query_ee<<<nblk(s.nSE, 128), 128, 0, st>>>(s, cw.grid.p, cw.ebox.p, cw.ekeys.p, cw.evals.p, 8 * s.nSE, w.vmin.p, w.vmax.p, radius, out);
+    ctx->launches += 2;
+    unsigned long long* hn = reinterpret_cast<unsigned long long*>(ctx->h_scalar);
+    int* ho = reinterpret_cast<int*>(ctx->h_scalar + 2);
+    CKD(cudaMemcpyAsync(hn, w.ncand.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CKD(cudaMemcpyAsync(ho, w.counters.p + 8, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CKD(cudaStreamSynchronize(st));
+    ctx->prof_end(pe);
+    if (*ho) {
+        ctx->err = "CCD candidate capacity exceeded (raise it with ipcgpu_set_ccd_capacity)";
+        return IPCGPU_ERR_CAPACITY;
+    }
+    const unsigned long long nCand = *hn;
+    if (nCandOut) *nCandOut = nCand;
+    return ccd_narrow(ctx, w.cand.p, nCand, tol, err_vf, err_ee, alpha_inout);
+}

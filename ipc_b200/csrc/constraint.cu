@@ -465,6 +465,24 @@ SurfArgs surf_args(const ipcgpu_ctx* ctx)
     return s;
 }
 
+// boxes of vertices/edges/triangles (optionally swept by alpha*dir), grid parameters, and the two sorted grids
+int boxes_and_grid(ipcgpu_ctx* ctx, const double* dir, double alpha, double radius, bool with_vertex_boxes)
+{
+    ContactWork& w = ctx->cw;
+    cudaStream_t st = ctx->stream;
+    const SurfArgs s = surf_args(ctx);
+    k_bounds_init<<<1, 32, 0, st>>>(w.bounds.p);
+    if (with_vertex_boxes && s.nSV > 0) k_boxes<<<nblk(s.nSV, 256), 256, 0, st>>>(s, 0, dir, alpha, w.vbox.p, w.bounds.p);
+    if (s.nSE > 0) k_boxes<<<nblk(s.nSE, 256), 256, 0, st>>>(s, 1, dir, alpha, w.ebox.p, w.bounds.p);
+    if (s.nSF > 0) k_boxes<<<nblk(s.nSF, 256), 256, 0, st>>>(s, 2, dir, alpha, w.tbox.p, w.bounds.p);
+    k_grid_params<<<1, 32, 0, st>>>(w.bounds.p, radius, w.grid.p);
+    ctx->launches += 5;
+    int rc;
+    if ((rc = build_grid(ctx, s.nSF, w.tbox.p, w.tkeys, w.tvals))) return rc;
+    if ((rc = build_grid(ctx, s.nSE, w.ebox.p, w.ekeys, w.evals))) return rc;
+    return 0;
+}
+
 // SelfCollisionHandler::computeConstraintSet on the device; counts come back through the pinned scalar buffer
 int contact_constraint_set(ipcgpu_ctx* ctx, double dHat, int wantCand, int* nC, int* nPara, int* nCand)
 {
@@ -473,14 +491,8 @@ int contact_constraint_set(ipcgpu_ctx* ctx, double dHat, int wantCand, int* nC, 
     const SurfArgs s = surf_args(ctx);
     const double radius = sqrt(dHat);
     cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_HASH);
-    k_bounds_init<<<1, 32, 0, st>>>(w.bounds.p);
-    if (s.nSE > 0) k_boxes<<<nblk(s.nSE, 256), 256, 0, st>>>(s, 1, nullptr, 0.0, w.ebox.p, w.bounds.p);
-    if (s.nSF > 0) k_boxes<<<nblk(s.nSF, 256), 256, 0, st>>>(s, 2, nullptr, 0.0, w.tbox.p, w.bounds.p);
-    k_grid_params<<<1, 32, 0, st>>>(w.bounds.p, radius, w.grid.p);
-    ctx->launches += 4;
     int rc;
-    if ((rc = build_grid(ctx, s.nSF, w.tbox.p, w.tkeys, w.tvals))) return rc;
-    if ((rc = build_grid(ctx, s.nSE, w.ebox.p, w.ekeys, w.evals))) return rc;
+    if ((rc = boxes_and_grid(ctx, nullptr, 0.0, radius, false))) return rc;
     ctx->prof_end(pe);
 
     pe = ctx->prof_begin(IPCGPU_STAGE_CONSTRAINT_SET);

@@ -4,6 +4,7 @@
 #include "broadphase_types.h"
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -52,6 +53,22 @@ struct ContactWork {
     int nC = 0, nP = 0, nK = 0; // current active / mollified / candidate counts
 };
 
+// device workspace of the CCD stage (ccd.cu)
+struct CcdWork {
+    DevBuf<int> vmin, vmax, counters;
+    DevBuf<int2> cand;
+    DevBuf<unsigned> surv;
+    DevBuf<unsigned char> scratch;
+    DevBuf<unsigned long long> ncand, bounds;
+    // reference swept-grid geometry (SpatialHash.hpp:589-640) of the last ipcgpu_hash_build_swept
+    double ref_lo[3] = { 0, 0, 0 }, ref_inv_h = 0.0, alpha_grid = 0.0;
+    int ref_count[3] = { 0, 0, 0 };
+    bool swept_ready = false;
+    unsigned last_survivors = 0;
+    int last_warnings = 0;
+    unsigned long long last_candidates = 0;
+};
+
 } // namespace ipcgpu
 
 struct ipcgpu_ctx {
@@ -79,6 +96,10 @@ struct ipcgpu_ctx {
     bool has_codim = false, surface_ready = false;
     int pair_capacity = 1 << 20;
     ipcgpu::ContactWork cw;
+    ipcgpu::CcdWork ccd;
+    size_t ccd_capacity = (size_t)1 << 23; // candidate pairs
+    std::vector<int> h_SVI;                // host copy (pSize of the swept build is a serial host sum, SpatialHash.hpp:603-612)
+    std::vector<double> h_dir;             // host shadow of the last uploaded search direction
     ipcgpu::DevBuf<double> bpartials;
 
     // gradient gather map (local tets)

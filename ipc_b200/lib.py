@@ -49,6 +49,12 @@ SIGNATURES = {
     "ipcgpu_barrier_energy": (C.c_int, [_ctxp, C.c_double, C.c_double, _dp]),
     "ipcgpu_barrier_gradient": (C.c_int, [_ctxp, C.c_double, C.c_double, _dp]),
     "ipcgpu_barrier_hessian": (C.c_int, [_ctxp, C.c_double, C.c_double, C.c_int, _dp]),
+    "ipcgpu_set_ccd_capacity": (C.c_int, [_ctxp, C.c_uint64]),
+    "ipcgpu_ti_error": (C.c_int, [_dp, C.c_int, _dp, _dp, _dp]),
+    "ipcgpu_ccd_partial_ti": (C.c_int, [_ctxp, _dp, C.c_double, _dp, _dp, _dp]),
+    "ipcgpu_hash_build_swept": (C.c_int, [_ctxp, _dp, _dp, C.c_double]),
+    "ipcgpu_ccd_full_ti": (C.c_int, [_ctxp, C.c_double, _dp, _dp, _dp, C.POINTER(C.c_uint64)]),
+    "ipcgpu_ccd_stats": (C.c_int, [_ctxp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "ipcgpu_csr_set_zero": (C.c_int, [_ctxp]),
     "ipcgpu_allreduce_grad_hess": (C.c_int, [_ctxp, C.c_int, C.c_int]),
     "ipcgpu_download": (C.c_int, [_ctxp, C.c_int, _dp, C.c_uint64]),
@@ -249,6 +255,39 @@ class Context:
     def barrier_hessian(self, dHat, kappa, projectDBC=1, a_inout=None):
         self._ck(self.lib.ipcgpu_barrier_hessian(self.h, dHat, kappa, projectDBC, _d(a_inout)))
         return a_inout
+
+    # ---- CCD ----------------------------------------------------------------------------------
+    @staticmethod
+    def ti_error(V_soa, nV, p=None):
+        evf, eee = np.empty(3), np.empty(3)
+        rc = load().ipcgpu_ti_error(_d(f64(V_soa).ravel()), int(nV), _d(f64(p)) if p is not None else None, _d(evf), _d(eee))
+        if rc:
+            raise IpcGpuError("ipcgpu_ti_error failed")
+        return evf, eee
+
+    def set_ccd_capacity(self, cap):
+        self._ck(self.lib.ipcgpu_set_ccd_capacity(self.h, int(cap)))
+
+    def ccd_partial(self, p, tol, err_vf, err_ee, alpha):
+        a = C.c_double(alpha)
+        self._ck(self.lib.ipcgpu_ccd_partial_ti(self.h, _d(f64(p)) if p is not None else None, tol, _d(f64(err_vf)), _d(f64(err_ee)), C.byref(a)))
+        return a.value
+
+    def hash_build_swept(self, p, alpha, h):
+        a = C.c_double(alpha)
+        self._ck(self.lib.ipcgpu_hash_build_swept(self.h, _d(f64(p)) if p is not None else None, C.byref(a), h))
+        return a.value
+
+    def ccd_full(self, tol, err_vf, err_ee, alpha):
+        a = C.c_double(alpha)
+        n = C.c_uint64()
+        self._ck(self.lib.ipcgpu_ccd_full_ti(self.h, tol, _d(f64(err_vf)), _d(f64(err_ee)), C.byref(a), C.byref(n)))
+        return a.value, n.value
+
+    def ccd_stats(self):
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._ck(self.lib.ipcgpu_ccd_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
 
     def profile(self, enable):
         self._ck(self.lib.ipcgpu_profile(self.h, int(enable)))
