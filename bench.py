@@ -73,17 +73,54 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def contact_pattern_pairs(m, mm, pa, pe):
+    """vertex pairs that the contact stencils add to the sparsity pattern (augmentConnectivity, SelfCollisionHandler.cpp:330-415)"""
+    out = []
+    for arr in (mm, pa):
+        if len(arr) == 0:
+            continue
+        a = np.asarray(arr, dtype=np.int64).copy()
+        a[:, 0] = np.where(a[:, 0] < 0, -a[:, 0] - 1, a[:, 0])
+        for i in range(4):
+            for j in range(i + 1, 4):
+                ok = (a[:, i] >= 0) & (a[:, j] >= 0)
+                out.append(np.stack([a[ok, i], a[ok, j]], axis=1))
+    if len(pe):
+        e = np.asarray(pe, dtype=np.int64)
+        e = e[e[:, 0] >= 0]
+        if len(e):
+            vs = np.concatenate([m.SFEdges[e[:, 0]], m.SFEdges[e[:, 1]]], axis=1)
+            for i in range(4):
+                for j in range(i + 1, 4):
+                    out.append(np.stack([vs[:, i], vs[:, j]], axis=1))
+    return np.concatenate(out) if out else None
+
+
 def oracle_step(m, info, nthreads):
-    """One Newton-iteration hot path on the CPU oracle (same stages as the GPU step)."""
+    """One Newton-iteration hot path on the CPU oracle: the same stages, in the reference's own algorithmic form
+    (spatial hash with serial inserts, parallel per-primitive loops, serial merges/scatters -- oracle/hash.cpp)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle as orc
     o = orc.Elastic(m)
-    ia, ja = m.csr_pattern(1)
+    s = orc.Surf(m)
+    dHat, p = info["dHat"], info["p"]
+    hvox = m.avgEdgeLen / 3.0
+    evf, eee = orc.ti_error(s.V, m.nV, p)
+    if "csr" not in info:  # untimed: sparsity pattern incl. the contact stencil (the solver's set_pattern)
+        mm, pa, pe, _ = s.constraint_set_hashed(dHat, hvox, nthreads)
+        info["csr"] = m.csr_pattern(1, extra_pairs=contact_pattern_pairs(m, mm, pa, pe))
+    ia, ja = info["csr"]
     t0 = time.perf_counter()
+    mm, pa, pe, cand = s.constraint_set_hashed(dHat, hvox, nthreads)
     o.energy(DT2, nthreads)
-    o.gradient(DT2, 1, nthreads)
-    o.hessian_csr(DT2, ia, ja, 1, 1, 1, nthreads=nthreads)
-    o.inversion_step(info["p"], 0.2, 1.0)
+    s.barrier_energy(mm, pa, pe, dHat, KAPPA)
+    g = o.gradient(DT2, 1, nthreads)
+    s.barrier_gradient(mm, pa, pe, dHat, KAPPA, g=g)
+    a = o.hessian_csr(DT2, ia, ja, 1, 1, 1, nthreads=nthreads)
+    s.barrier_hessian_csr(mm, pa, pe, dHat, KAPPA, ia, ja, 1, 1, a=a, nthreads=nthreads)
+    alpha, _ = o.inversion_step(p, 0.2, 1.0)
+    alpha, _ = orc.ccd_partial(s, p, cand, TI_TOL, evf, eee, alpha, nthreads)
+    alpha, _, _ = orc.ccd_full_hashed(s, p, alpha, hvox, TI_TOL, evf, eee, nthreads)
     return (time.perf_counter() - t0) * 1e3
 
 
@@ -124,7 +161,10 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-STAGES_RUN = ["elastic_energy", "elastic_gradient", "elastic_hessian+mass->CSR", "inversion_step_bound"]
+STAGES_RUN = ["constraint_set(hash+classify)", "elastic_energy", "barrier_energy", "elastic_gradient", "barrier_gradient",
+              "elastic_hessian+mass->CSR", "barrier_hessian->CSR", "inversion_step_bound", "partial_CCD(TI)", "swept_hash", "full_CCD(TI)"]
+KAPPA = 1e8
+TI_TOL = 1e-6
 
 
 def main():
@@ -162,9 +202,17 @@ def main():
         dist.broadcast_object_list(ids, src=0)
         ctx.comm_init(rank, world, ids[0])
     ctx.set_mesh(m.V_rest_soa, m.T_soa, m.restTriInv, m.vol, m.mu, m.lam, m.mass, m.dbc, m.energy)
-    ia, ja = m.csr_pattern(1)
+    ctx.set_surface(m.SVI, m.SFEdges, m.SF_soa, m.vCoDim)
+    ctx.set_state(m.V_soa)
+    dHat = info["dHat"]
+    hvox = m.avgEdgeLen / 3.0  # Optimizer.cpp:259,1965
+    err_vf, err_ee = L.Context.ti_error(m.V_soa, m.nV, info["p"])
+    # sparsity pattern incl. the contact stencil (augmentConnectivity + set_pattern are the solver's job: done once, untimed)
+    mm, pa, pe, cand = ctx.constraint_set(dHat, 1)
+    ia, ja = m.csr_pattern(1, extra_pairs=contact_pattern_pairs(m, mm, pa, pe))
     ctx.set_csr(ia, ja, 1)
     nnz = ja.size
+    n_active, n_para, n_cand = len(mm), len(pa), len(cand)
 
     # pinned host buffers for the e2e path
     hV = L.PinnedArray(3 * m.nV); hV.array[:] = m.V_soa
@@ -182,16 +230,37 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    stats = {}
+
     def step_device():
+        ctx.constraint_set(dHat, 1, fetch=False)
         ctx.elastic_energy(DT2, 1, want=False)
+        ctx.barrier_energy(dHat, KAPPA)
+        ctx.csr_set_zero()
         ctx.elastic_grad_hess(DT2, 1, 1, 1, None, None)
-        ctx.inversion_step(None, 0.2, 1.0)
+        ctx.barrier_gradient(dHat, KAPPA, None)
+        ctx.barrier_hessian(dHat, KAPPA, 1, None)
+        a = ctx.inversion_step(None, 0.2, 1.0)
+        a = ctx.ccd_partial(None, TI_TOL, err_vf, err_ee, a)
+        a = ctx.hash_build_swept(None, a, hvox)
+        a, nc = ctx.ccd_full(TI_TOL, err_vf, err_ee, a)
+        stats["alpha"], stats["ccd_candidates"] = a, nc
 
     def step_e2e():
         ctx.set_state(hV.array)
+        ctx.constraint_set(dHat, 1, fetch=False)
         ctx.elastic_energy(DT2, 1, want=True)
-        ctx.elastic_grad_hess(DT2, 1, 1, 1, hg.array, ha.array)
-        ctx.inversion_step(hp.array, 0.2, 1.0)
+        ctx.barrier_energy(dHat, KAPPA)
+        ctx.csr_set_zero()
+        ctx.elastic_grad_hess(DT2, 1, 1, 1, None, None)
+        ctx.barrier_gradient(dHat, KAPPA, None)
+        ctx.barrier_hessian(dHat, KAPPA, 1, None)
+        ctx.download_into(L.BUF_GRADIENT, hg.array)
+        ctx.download_into(L.BUF_CSR_VALUES, ha.array)
+        a = ctx.inversion_step(hp.array, 0.2, 1.0)
+        a = ctx.ccd_partial(None, TI_TOL, err_vf, err_ee, a)
+        a = ctx.hash_build_swept(None, a, hvox)
+        a, nc = ctx.ccd_full(TI_TOL, err_vf, err_ee, a)
 
     # ---- device-resident timing --------------------------------------------------------------------
     for _ in range(args.warmup):
@@ -248,7 +317,9 @@ def main():
             "metric": "newton_iteration_ms_assembly_ccd", "value": ms_step, "unit": "ms", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"synthetic 1M-tet ball pile ({m.nT} tets, {m.nV} verts, {info['n_balls']} balls), NeoHookean, dt=0.025",
+            "config": {"workload": f"synthetic 1M-tet ball pile ({m.nT} tets, {m.nV} verts, {info['n_balls']} stacked balls, {len(m.SVI)} surface verts), NeoHookean, dt=0.025, "
+                                   f"dHat=(1e-3 bboxDiag)^2, {n_active} active pairs + {n_para} mollified, {n_cand} partial-CCD candidates, "
+                                   f"{stats.get('ccd_candidates', 0)} full-CCD candidates, TI tol 1e-6",
                        "stages": STAGES_RUN, "csr_nnz": int(nnz), "l2": "working set (78 doubles/tet = %.0f MB + CSR %.0f MB) exceeds the 126 MB L2" % (m.nT * 624 / 1e6, nnz * 8 / 1e6),
                        "partition": f"tets block-partitioned over {world} rank(s); NCCL sum-allreduce of [gradient, CSR values], min-allreduce of the step"},
             "stage_ms": {k: v[0] / args.steps for k, v in prof.items()},

@@ -312,6 +312,9 @@ class Context:
     def csr_set_zero(self):
         self._ck(self.lib.ipcgpu_csr_set_zero(self.h))
 
+    def download_into(self, which, out):
+        self._ck(self.lib.ipcgpu_download(self.h, which, _d(out), int(out.size)))
+
     def download(self, which, count):
         out = np.empty(int(count))
         self._ck(self.lib.ipcgpu_download(self.h, which, _d(out), int(count)))

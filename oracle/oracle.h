@@ -148,6 +148,12 @@ int orc_ccd_partial(const orc_surf* s, const double* p, const int* cand, int nCa
 int orc_ccd_full(const orc_surf* s, const double* p, const orc_grid* g, double alpha_grid, double tol,
     const double err_vf[3], const double err_ee[3], double* alpha_inout, long long* nPairs, int nthreads);
 
+/* ---- reference-style hashed drivers (oracle/hash.cpp): the faithful CPU baselines ----------------------------- */
+int orc_constraint_set_hashed(const orc_surf* s, double dHat, double voxel_size,
+    int cap, int* mmcvid, int* nC, int capP, int* para, int* para_eIeJ, int* nPara, int capK, int* cand, int* nCand, int nthreads);
+int orc_ccd_full_hashed(const orc_surf* s, const double* p, double* alpha_inout, double voxel_size, double tol,
+    const double err_vf[3], const double err_ee[3], long long* nPairs, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -246,6 +246,15 @@ class Surf:
         assert rc == 0, "oracle constraint-set capacity exceeded"
         return mm[:nC.value].copy(), pa[:nP.value].copy(), pe[:nP.value].copy(), cand[:nK.value].copy()
 
+    def constraint_set_hashed(self, dHat, voxel_size, nthreads=1, cap=1 << 20):
+        mm = np.empty((cap, 4), dtype=np.int32); pa = np.empty((cap, 4), dtype=np.int32); pe = np.empty((cap, 2), dtype=np.int32)
+        cand = np.empty((4 * cap, 2), dtype=np.int32)
+        nC, nP, nK = C.c_int(), C.c_int(), C.c_int()
+        rc = lib().orc_constraint_set_hashed(C.byref(self.s), C.c_double(dHat), C.c_double(voxel_size), cap, i(mm), C.byref(nC), cap, i(pa), i(pe), C.byref(nP),
+                                             4 * cap, i(cand), C.byref(nK), nthreads)
+        assert rc == 0
+        return mm[:nC.value].copy(), pa[:nP.value].copy(), pe[:nP.value].copy(), cand[:nK.value].copy()
+
     def barrier_energy(self, mm, pa, pe, dHat, kappa):
         E = C.c_double()
         mm, pa, pe = (np.ascontiguousarray(x, dtype=np.int32) for x in (mm, pa, pe))
@@ -317,4 +326,13 @@ def ccd_full(surf, p, grid, alpha_grid, tol, evf, eee, alpha, nthreads=1):
     n = C.c_longlong()
     z = lib().orc_ccd_full(C.byref(surf.s), d(p), C.byref(grid), C.c_double(alpha_grid), C.c_double(tol), d(np.ascontiguousarray(evf)), d(np.ascontiguousarray(eee)),
                            C.byref(a), C.byref(n), nthreads)
+    return a.value, z, n.value
+
+
+def ccd_full_hashed(surf, p, alpha, voxel_size, tol, evf, eee, nthreads=1):
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    a = C.c_double(alpha)
+    n = C.c_longlong()
+    z = lib().orc_ccd_full_hashed(C.byref(surf.s), d(p), C.byref(a), C.c_double(voxel_size), C.c_double(tol), d(np.ascontiguousarray(evf)), d(np.ascontiguousarray(eee)),
+                                  C.byref(n), nthreads)
     return a.value, z, n.value

@@ -110,3 +110,21 @@ def test_partial_and_full_ccd_on_stacked_balls():
     # separating motion: no bound
     a_sep, _ = orc.ccd_partial(s, -p, cand, 1e-6, evf, eee, 1.0)
     assert a_sep == 1.0
+
+
+def test_hashed_drivers_equal_brute_force():
+    """The reference-style hash (oracle/hash.cpp) must not change any result: same sets, same step bound."""
+    m, info = scenes.ball_pile(3, res=6, seed=12, height=3)
+    s = orc.Surf(m)
+    p = info["p"]
+    h = m.avgEdgeLen / 3
+    mm, pa, pe, cand = s.constraint_set(info["dHat"])
+    mm2, pa2, pe2, cand2 = s.constraint_set_hashed(info["dHat"], h, nthreads=4)
+    assert len(mm) > 0
+    assert np.array_equal(mm, mm2) and np.array_equal(pa, pa2) and np.array_equal(pe, pe2) and np.array_equal(cand, cand2)
+    evf, eee = orc.ti_error(s.V, m.nV, p)
+    g, a_grid = orc.grid_swept(s, p, 1.0, h)
+    a_bf, z, n_bf = orc.ccd_full(s, p, g, a_grid, 1e-6, evf, eee, a_grid, nthreads=4)
+    a_h, z2, n_h = orc.ccd_full_hashed(s, p, 1.0, h, 1e-6, evf, eee, nthreads=4)
+    assert z == z2 == 0 and a_bf == a_h
+    assert n_h >= n_bf  # voxel-id aliasing in the hash can only add (harmless) candidates
