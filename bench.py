@@ -220,7 +220,7 @@ def main():
     hg = L.PinnedArray(3 * m.nV)
     ha = L.PinnedArray(nnz)
     ctx.set_state(hV.array)
-    ctx.step_forward(hp.array, 0.0)  # uploads the search direction once (device-resident for the HBM mode)
+    ctx.set_search_dir(hp.array)  # uploaded once: device-resident for the HBM mode
 
     def barrier():
         ctx.sync()

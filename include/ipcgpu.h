@@ -87,6 +87,8 @@ int ipcgpu_set_state(ipcgpu_ctx* ctx, const double* V_soa);
 /* x = x0 + alpha*p on the device (Optimizer::stepForward, Optimizer.cpp:2919-2938); x0 = state at the
  * time of ipcgpu_save_state */
 int ipcgpu_save_state(ipcgpu_ctx* ctx);
+/* upload the search direction p (interleaved 3nV) once; later calls may pass p = NULL to reuse it */
+int ipcgpu_set_search_dir(ipcgpu_ctx* ctx, const double* p_interleaved);
 int ipcgpu_step_forward(ipcgpu_ctx* ctx, const double* p_interleaved /* NULL = last search dir */, double alpha);
 
 /* ---- elastic plug-in: Energy<3> virtuals (Energy.hpp:42-131) ---------------------------------------- */

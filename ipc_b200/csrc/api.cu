@@ -296,12 +296,24 @@ int ipcgpu_save_state(ipcgpu_ctx* ctx)
 {
     REQUIRE(ctx->nV > 0, IPCGPU_ERR_STATE, "ipcgpu_set_mesh first");
     CK(cudaMemcpyAsync(ctx->Vsaved.p, ctx->V.p, (size_t)3 * ctx->nV * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->state_saved = true;
+    return IPCGPU_OK;
+}
+
+int ipcgpu_set_search_dir(ipcgpu_ctx* ctx, const double* p)
+{
+    REQUIRE(ctx->nV > 0 && p, IPCGPU_ERR_ARG, "ipcgpu_set_search_dir: mesh and p required");
+    CK(cudaSetDevice(ctx->device));
+    ctx->h_dir.assign(p, p + (size_t)3 * ctx->nV);
+    CK(cudaMemcpyAsync(ctx->dir.p, p, (size_t)3 * ctx->nV * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return IPCGPU_OK;
 }
 
 int ipcgpu_step_forward(ipcgpu_ctx* ctx, const double* p, double alpha)
 {
     REQUIRE(ctx->nV > 0, IPCGPU_ERR_STATE, "ipcgpu_set_mesh first");
+    REQUIRE(ctx->state_saved, IPCGPU_ERR_STATE, "ipcgpu_save_state must precede ipcgpu_step_forward");
     CK(cudaSetDevice(ctx->device));
     if (p) {
         ctx->h_dir.assign(p, p + (size_t)3 * ctx->nV);

@@ -142,7 +142,7 @@ struct CsOut {
 DEV void push4(int4* arr, int* cnt, int cap, int* overflow, int4 v)
 {
     int i = atomicAdd(cnt, 1);
-    if (i < cap) arr[i] = v;
+    if ((unsigned)i < (unsigned)cap) arr[i] = v; // unsigned: a wrapped counter must not index backwards
     else atomicExch(overflow, 1);
 }
 
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(128) k_query_pt(SurfArgs s, const Grid* __rest
                         else push4(out.dup, out.nDup, out.capDup, out.overflow, q);
                         if (wantCand) {
                             int i = atomicAdd(out.nCand, 1);
-                            if (i < out.capCand) out.cand[i] = make_int2(-svI - 1, sfI);
+                            if ((unsigned)i < (unsigned)out.capCand) out.cand[i] = make_int2(-svI - 1, sfI);
                             else atomicExch(out.overflow, 1);
                         }
                     }
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(128) k_query_ee(SurfArgs s, const Grid* __rest
                         if (ty == 8) {
                             if (add_e <= -2) { // nearly parallel EE: mollified set, keeps its own stencil (:2464-2467)
                                 int i = atomicAdd(out.nPara, 1);
-                                if (i < out.capPara) { out.para[i] = q; out.para_e[i] = make_int2(-1, -1); }
+                                if ((unsigned)i < (unsigned)out.capPara) { out.para[i] = q; out.para_e[i] = make_int2(-1, -1); }
                                 else atomicExch(out.overflow, 1);
                             }
                             else push4(out.act, out.nAct, out.capAct, out.overflow, q);
@@ -279,12 +279,12 @@ __global__ void __launch_bounds__(128) k_query_ee(SurfArgs s, const Grid* __rest
                         else if (add_e == -1) push4(out.dup, out.nDup, out.capDup, out.overflow, q);
                         else { // PP / PE that came from a nearly parallel edge pair (:2459-2462)
                             int i = atomicAdd(out.nPara, 1);
-                            if (i < out.capPara) { out.para[i] = make_int4(q.x, q.y, q.z, -1); out.para_e[i] = make_int2(eI, eJ); }
+                            if ((unsigned)i < (unsigned)out.capPara) { out.para[i] = make_int4(q.x, q.y, q.z, -1); out.para_e[i] = make_int2(eI, eJ); }
                             else atomicExch(out.overflow, 1);
                         }
                         if (wantCand) {
                             int i = atomicAdd(out.nCand, 1);
-                            if (i < out.capCand) out.cand[i] = make_int2(eI, eJ);
+                            if ((unsigned)i < (unsigned)out.capCand) out.cand[i] = make_int2(eI, eJ);
                             else atomicExch(out.overflow, 1);
                         }
                     }

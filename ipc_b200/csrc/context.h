@@ -87,7 +87,7 @@ struct ipcgpu_ctx {
     ipcgpu::DevBuf<double> V, Vsaved, Vrest, Ainv, vol, mu, lam, mass;
     ipcgpu::DevBuf<int> T;
     ipcgpu::DevBuf<uint8_t> dbc;
-    bool has_mass = false, has_dbc = false;
+    bool has_mass = false, has_dbc = false, state_saved = false;
     std::vector<int> h_T; // host copy of tets (maps are rebuilt when the partition changes)
 
     // surface (Mesh::SVI / SFEdges / SF) and contact workspace

@@ -35,6 +35,7 @@ SIGNATURES = {
     "ipcgpu_set_csr": (C.c_int, [_ctxp, C.c_int, _ip, _ip, C.c_int]),
     "ipcgpu_set_state": (C.c_int, [_ctxp, _dp]),
     "ipcgpu_save_state": (C.c_int, [_ctxp]),
+    "ipcgpu_set_search_dir": (C.c_int, [_ctxp, _dp]),
     "ipcgpu_step_forward": (C.c_int, [_ctxp, _dp, C.c_double]),
     "ipcgpu_elastic_energy": (C.c_int, [_ctxp, C.c_double, C.c_int, _dp]),
     "ipcgpu_elastic_gradient": (C.c_int, [_ctxp, C.c_double, C.c_int, C.c_int, _dp]),
@@ -185,6 +186,9 @@ class Context:
 
     def save_state(self):
         self._ck(self.lib.ipcgpu_save_state(self.h))
+
+    def set_search_dir(self, p):
+        self._ck(self.lib.ipcgpu_set_search_dir(self.h, _d(f64(p))))
 
     def step_forward(self, p, alpha):
         self._ck(self.lib.ipcgpu_step_forward(self.h, _d(f64(p)) if p is not None else None, float(alpha)))
