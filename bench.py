@@ -240,11 +240,13 @@ def main():
         ctx.elastic_grad_hess(DT2, 1, 1, 1, None, None)
         ctx.barrier_gradient(dHat, KAPPA, None)
         ctx.barrier_hessian(dHat, KAPPA, 1, None)
+        ctx.allreduce_grad_hess(1, 1)  # one NCCL sum over [gradient, CSR values] (no-op on a single rank)
         a = ctx.inversion_step(None, 0.2, 1.0)
         a = ctx.ccd_partial(None, TI_TOL, err_vf, err_ee, a)
         a = ctx.hash_build_swept(None, a, hvox)
         a, nc = ctx.ccd_full(TI_TOL, err_vf, err_ee, a)
         stats["alpha"], stats["ccd_candidates"] = a, nc
+        stats["ccd_full_stats"] = ctx.ccd_stats()
 
     def step_e2e():
         ctx.set_state(hV.array)
@@ -255,6 +257,7 @@ def main():
         ctx.elastic_grad_hess(DT2, 1, 1, 1, None, None)
         ctx.barrier_gradient(dHat, KAPPA, None)
         ctx.barrier_hessian(dHat, KAPPA, 1, None)
+        ctx.allreduce_grad_hess(1, 1)
         ctx.download_into(L.BUF_GRADIENT, hg.array)
         ctx.download_into(L.BUF_CSR_VALUES, ha.array)
         a = ctx.inversion_step(hp.array, 0.2, 1.0)
@@ -269,7 +272,7 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-        time.sleep(0.3)
+        time.sleep(0.5)
     n0 = ctx.launch_count()
     ctx.profile(1)
     barrier()
@@ -281,7 +284,6 @@ def main():
     launches = ctx.launch_count() - n0
     prof = ctx.profile_read()
     ctx.profile(0)
-    clocks = sampler.finish() if sampler else None
     ms_step = ms_total / args.steps
 
     # ---- end-to-end timing (host buffers through the C ABI) -----------------------------------------
@@ -294,6 +296,7 @@ def main():
         step_e2e()
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    clocks = sampler.finish() if sampler else None
 
     if dist is not None:
         import torch
@@ -320,7 +323,8 @@ def main():
             "config": {"workload": f"synthetic 1M-tet ball pile ({m.nT} tets, {m.nV} verts, {info['n_balls']} stacked balls, {len(m.SVI)} surface verts), NeoHookean, dt=0.025, "
                                    f"dHat=(1e-3 bboxDiag)^2, {n_active} active pairs + {n_para} mollified, {n_cand} partial-CCD candidates, "
                                    f"{stats.get('ccd_candidates', 0)} full-CCD candidates, TI tol 1e-6",
-                       "stages": STAGES_RUN, "csr_nnz": int(nnz), "l2": "working set (78 doubles/tet = %.0f MB + CSR %.0f MB) exceeds the 126 MB L2" % (m.nT * 624 / 1e6, nnz * 8 / 1e6),
+                       "stages": STAGES_RUN, "csr_nnz": int(nnz), "step_bound_alpha": stats.get("alpha"),
+                       "full_ccd_candidates_survivors_warnings": stats.get("ccd_full_stats"), "l2": "working set (78 doubles/tet = %.0f MB + CSR %.0f MB) exceeds the 126 MB L2" % (m.nT * 624 / 1e6, nnz * 8 / 1e6),
                        "partition": f"tets block-partitioned over {world} rank(s); NCCL sum-allreduce of [gradient, CSR values], min-allreduce of the step"},
             "stage_ms": {k: v[0] / args.steps for k, v in prof.items()},
             "roofline": {"bound": "hbm", "kernel": "k_elastic_grad_hess<NH,g,H>", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",

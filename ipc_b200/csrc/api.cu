@@ -381,7 +381,7 @@ int ipcgpu_elastic_gradient(ipcgpu_ctx* ctx, double coef, int /*redoSVD*/, int p
     CK(cudaSetDevice(ctx->device));
     int rc = run_grad_hess(ctx, coef, 1, projectDBC, true, false, 0, false);
     if (rc) return rc;
-    if (ctx->nranks > 1) {
+    if (ctx->nranks > 1 && g) { // host result requested: complete it across ranks; NULL = deferred (ipcgpu_allreduce_grad_hess)
         rc = ipcgpu_allreduce_grad_hess(ctx, 1, 0);
         if (rc) return rc;
     }
@@ -396,10 +396,13 @@ int ipcgpu_elastic_hessian(ipcgpu_ctx* ctx, double coef, int /*redoSVD*/, int pr
 {
     CK(cudaSetDevice(ctx->device));
     REQUIRE(ctx->nnz > 0, IPCGPU_ERR_STATE, "ipcgpu_set_csr first");
-    if (a_inout) CK(cudaMemcpyAsync(ctx->a.p, a_inout, (size_t)ctx->nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (a_inout) {
+        if (ctx->rank == 0) CK(cudaMemcpyAsync(ctx->a.p, a_inout, (size_t)ctx->nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        else CK(cudaMemsetAsync(ctx->a.p, 0, (size_t)ctx->nnz * sizeof(double), ctx->stream));
+    }
     int rc = run_grad_hess(ctx, coef, projectSPD, projectDBC, false, true, 0, true);
     if (rc) return rc;
-    if (ctx->nranks > 1) {
+    if (ctx->nranks > 1 && a_inout) {
         rc = ipcgpu_allreduce_grad_hess(ctx, 0, 1);
         if (rc) return rc;
     }
@@ -416,8 +419,8 @@ int ipcgpu_elastic_grad_hess(ipcgpu_ctx* ctx, double coef, int projectSPD, int p
     REQUIRE(ctx->nnz > 0, IPCGPU_ERR_STATE, "ipcgpu_set_csr first");
     int rc = run_grad_hess(ctx, coef, projectSPD, projectDBC, true, true, add_mass, false);
     if (rc) return rc;
-    if (ctx->nranks > 1) {
-        rc = ipcgpu_allreduce_grad_hess(ctx, 1, 1);
+    if (ctx->nranks > 1 && (g || a)) {
+        rc = ipcgpu_allreduce_grad_hess(ctx, g ? 1 : 0, a ? 1 : 0);
         if (rc) return rc;
     }
     if (g) CK(cudaMemcpyAsync(g, ctx->g.p, (size_t)3 * ctx->nV * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -626,7 +629,11 @@ static BarrierArgs barrier_args(ipcgpu_ctx* ctx, double dHat, double kappa, int 
 {
     BarrierArgs p;
     p.nV = ctx->nV; p.V = ctx->V.p; p.Vrest = ctx->Vrest.p; p.dbc = ctx->has_dbc ? ctx->dbc.p : nullptr; p.SE = ctx->SE.p;
-    p.cs = ctx->cw.act.p; p.nC = ctx->cw.nC; p.para = ctx->cw.para.p; p.para_e = ctx->cw.para_e.p; p.nP = ctx->cw.nP;
+    // every rank owns a contiguous share of the (replicated, canonically sorted) pair lists
+    const long long nC = ctx->cw.nC, nP = ctx->cw.nP;
+    const int cb = (int)(nC * ctx->rank / ctx->nranks), ce = (int)(nC * (ctx->rank + 1) / ctx->nranks);
+    const int pb = (int)(nP * ctx->rank / ctx->nranks), pe = (int)(nP * (ctx->rank + 1) / ctx->nranks);
+    p.cs = ctx->cw.act.p + cb; p.nC = ce - cb; p.para = ctx->cw.para.p + pb; p.para_e = ctx->cw.para_e.p + pb; p.nP = pe - pb;
     p.dHat = dHat; p.kappa = kappa; p.projectDBC = projectDBC;
     p.ia = ctx->ia.p; p.ja = ctx->ja.p; p.base = ctx->index_base;
     return p;
@@ -646,6 +653,11 @@ int ipcgpu_barrier_energy(ipcgpu_ctx* ctx, double dHat, double kappa, double* E)
     reduce_sum(ctx->bpartials.p, nb, kappa, ctx->scalar_out.p + 1, ctx->stream);
     ctx->prof_end(pe);
     ctx->launches += 2;
+    if (ctx->nranks > 1) {
+        int r = g_nccl.AllReduce(ctx->scalar_out.p + 1, ctx->scalar_out.p + 1, 1, kNcclFloat64, kNcclSum, ctx->nccl_comm, ctx->stream);
+        REQUIRE(r == 0, IPCGPU_ERR_NCCL, "ncclAllReduce(barrier energy) failed");
+        // the d<=0 flag is local; a max-reduce would need a second collective: every rank checks its own share
+    }
     CK(cudaGetLastError());
     int* hf = reinterpret_cast<int*>(ctx->h_scalar + 4);
     CK(cudaMemcpyAsync(ctx->h_scalar, ctx->scalar_out.p + 1, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -660,12 +672,19 @@ int ipcgpu_barrier_gradient(ipcgpu_ctx* ctx, double dHat, double kappa, double* 
 {
     REQUIRE(ctx->surface_ready, IPCGPU_ERR_STATE, "ipcgpu_set_surface first");
     CK(cudaSetDevice(ctx->device));
-    if (g_inout) CK(cudaMemcpyAsync(ctx->g.p, g_inout, (size_t)3 * ctx->nV * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (g_inout) {
+        if (ctx->rank == 0) CK(cudaMemcpyAsync(ctx->g.p, g_inout, (size_t)3 * ctx->nV * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        else CK(cudaMemsetAsync(ctx->g.p, 0, (size_t)3 * ctx->nV * sizeof(double), ctx->stream));
+    }
     cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_BARRIER);
     barrier_gradient(barrier_args(ctx, dHat, kappa, 0), ctx->g.p, ctx->stream);
     ctx->prof_end(pe);
     ++ctx->launches;
     CK(cudaGetLastError());
+    if (g_inout && ctx->nranks > 1) {
+        int rc = ipcgpu_allreduce_grad_hess(ctx, 1, 0);
+        if (rc) return rc;
+    }
     if (g_inout) {
         CK(cudaMemcpyAsync(g_inout, ctx->g.p, (size_t)3 * ctx->nV * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
@@ -678,13 +697,20 @@ int ipcgpu_barrier_hessian(ipcgpu_ctx* ctx, double dHat, double kappa, int proje
     REQUIRE(ctx->surface_ready, IPCGPU_ERR_STATE, "ipcgpu_set_surface first");
     REQUIRE(ctx->nnz > 0, IPCGPU_ERR_STATE, "ipcgpu_set_csr first");
     CK(cudaSetDevice(ctx->device));
-    if (a_inout) CK(cudaMemcpyAsync(ctx->a.p, a_inout, (size_t)ctx->nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (a_inout) {
+        if (ctx->rank == 0) CK(cudaMemcpyAsync(ctx->a.p, a_inout, (size_t)ctx->nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        else CK(cudaMemsetAsync(ctx->a.p, 0, (size_t)ctx->nnz * sizeof(double), ctx->stream));
+    }
     CK(cudaMemsetAsync(ctx->flag.p, 0, sizeof(int), ctx->stream));
     cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_BARRIER);
     barrier_hessian(barrier_args(ctx, dHat, kappa, projectDBC), ctx->a.p, ctx->flag.p, ctx->stream);
     ctx->prof_end(pe);
     ++ctx->launches;
     CK(cudaGetLastError());
+    if (a_inout && ctx->nranks > 1) {
+        int rc = ipcgpu_allreduce_grad_hess(ctx, 0, 1);
+        if (rc) return rc;
+    }
     int* hf = reinterpret_cast<int*>(ctx->h_scalar + 4);
     CK(cudaMemcpyAsync(hf, ctx->flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     if (a_inout) CK(cudaMemcpyAsync(a_inout, ctx->a.p, (size_t)ctx->nnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

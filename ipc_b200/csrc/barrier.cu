@@ -215,7 +215,7 @@ __device__ inline void jacobi_psd(int n, double* __restrict__ A, double* __restr
                 off += u * u;
             }
         }
-        if (off <= 1e-34 * dg || off <= 1e-300) break;
+        if (off <= 1e-26 * dg || off <= 1e-300) break; // off-diagonal mass at rounding level (eigenvalue error is second order in it)
         for (int pI = 0; pI < n; ++pI)
             for (int q = pI + 1; q < n; ++q) {
                 const double apq = EL(A, pI, q);

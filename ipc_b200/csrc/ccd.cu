@@ -120,10 +120,10 @@ DEV void push_cand(const CandOut& o, int2 c)
 
 __global__ void __launch_bounds__(128) k_ccd_query_pt(SurfArgs s, const Grid* __restrict__ gp, const Box* __restrict__ vboxes, const Box* __restrict__ tboxes,
     const unsigned long long* __restrict__ keys, const int* __restrict__ vals, int nEntries, const int* __restrict__ vmin, const int* __restrict__ vmax, double radius,
-    CandOut out)
+    int first, int last, CandOut out)
 {
-    const int svI = blockIdx.x * blockDim.x + threadIdx.x;
-    if (svI >= s.nSV) return;
+    const int svI = first + blockIdx.x * blockDim.x + threadIdx.x;
+    if (svI >= last) return;
     const Grid g = *gp;
     const int vI = s.SVI[svI];
     Box qb = vboxes[svI];
@@ -156,10 +156,10 @@ __global__ void __launch_bounds__(128) k_ccd_query_pt(SurfArgs s, const Grid* __
 
 __global__ void __launch_bounds__(128) k_ccd_query_ee(SurfArgs s, const Grid* __restrict__ gp, const Box* __restrict__ eboxes,
     const unsigned long long* __restrict__ keys, const int* __restrict__ vals, int nEntries, const int* __restrict__ vmin, const int* __restrict__ vmax, double radius,
-    CandOut out)
+    int first, int last, CandOut out)
 {
-    const int eI = blockIdx.x * blockDim.x + threadIdx.x;
-    if (eI >= s.nSE) return;
+    const int eI = first + blockIdx.x * blockDim.x + threadIdx.x;
+    if (eI >= last) return;
     const Grid g = *gp;
     const int a[2] = { s.SE[2 * eI], s.SE[2 * eI + 1] };
     const Box eb = eboxes[eI];
@@ -804,9 +804,13 @@ int ccd_full(ipcgpu_ctx* ctx, double tol, const double* err_vf, const double* er
     CKD(cudaMemsetAsync(w.counters.p + 8, 0, sizeof(int), st));
     CandOut out{ w.cand.p, w.ncand.p, (unsigned long long)ctx->ccd_capacity, w.counters.p + 8 };
     const double radius = 1.0 / w.ref_inv_h;
-    if (s.nSV > 0 && s.nSF > 0)
-        k_ccd_query_pt<<<nblk(s.nSV, 128), 128, 0, st>>>(s, cw.grid.p, cw.vbox.p, cw.tbox.p, cw.tkeys.p, cw.tvals.p, 8 * s.nSF, w.vmin.p, w.vmax.p, radius, out);
-    if (s.nSE > 1) k_ccd_query_ee<<<nblk(s.nSE, 128), 128, 0, st>>>(s, cw.grid.p, cw.ebox.p, cw.ekeys.p, cw.evals.p, 8 * s.nSE, w.vmin.p, w.vmax.p, radius, out);
+    // multi-GPU: every rank sweeps a contiguous share of the query primitives (the reference's own loop decomposition, :1385, :1498)
+    const int v0 = (int)((long long)s.nSV * ctx->rank / ctx->nranks), v1 = (int)((long long)s.nSV * (ctx->rank + 1) / ctx->nranks);
+    const int e0 = (int)((long long)s.nSE * ctx->rank / ctx->nranks), e1 = (int)((long long)s.nSE * (ctx->rank + 1) / ctx->nranks);
+    if (v1 > v0 && s.nSF > 0)
+        k_ccd_query_pt<<<nblk(v1 - v0, 128), 128, 0, st>>>(s, cw.grid.p, cw.vbox.p, cw.tbox.p, cw.tkeys.p, cw.tvals.p, 8 * s.nSF, w.vmin.p, w.vmax.p, radius, v0, v1, out);
+    if (e1 > e0 && s.nSE > 1)
+        k_ccd_query_ee<<<nblk(e1 - e0, 128), 128, 0, st>>>(s, cw.grid.p, cw.ebox.p, cw.ekeys.p, cw.evals.p, 8 * s.nSE, w.vmin.p, w.vmax.p, radius, e0, e1, out);
     ctx->launches += 2;
     unsigned long long* hn = reinterpret_cast<unsigned long long*>(ctx->h_scalar);
     int* ho = reinterpret_cast<int*>(ctx->h_scalar + 2);

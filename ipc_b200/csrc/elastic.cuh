@@ -165,7 +165,7 @@ DEV void make_pd3(double* A /* a00 a01 a02 a11 a12 a22 */)
     for (int sweep = 0; sweep < 12; ++sweep) {
         double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
         double dg = a[0][0] * a[0][0] + a[1][1] * a[1][1] + a[2][2] * a[2][2];
-        if (off <= 1e-34 * dg || off <= 1e-300) break;
+        if (off <= 1e-26 * dg || off <= 1e-300) break;
         jacobi_rot3<0, 1>(a, v);
         jacobi_rot3<0, 2>(a, v);
         jacobi_rot3<1, 2>(a, v);

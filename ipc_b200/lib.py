@@ -313,6 +313,9 @@ class Context:
         self._ck(self.lib.ipcgpu_timer_stop(self.h, C.byref(ms)))
         return ms.value
 
+    def allreduce_grad_hess(self, with_gradient=1, with_hessian=1):
+        self._ck(self.lib.ipcgpu_allreduce_grad_hess(self.h, with_gradient, with_hessian))
+
     def csr_set_zero(self):
         self._ck(self.lib.ipcgpu_csr_set_zero(self.h))
 

@@ -328,7 +328,7 @@ void jacobi_eig(int n, const double* Min, double* evals, double* evecs /* column
             diag += A[i * n + i] * A[i * n + i];
             for (int j = i + 1; j < n; ++j) off += A[i * n + j] * A[i * n + j];
         }
-        if (off <= 1e-60 || off <= 1e-34 * diag) break;
+        if (off <= 1e-300 || off <= 1e-28 * diag) break; /* rounding floor of the off-diagonal mass is ~1e-30*diag */
         for (int p = 0; p < n; ++p)
             for (int q = p + 1; q < n; ++q) {
                 double apq = A[p * n + q];
