@@ -1,0 +1,79 @@
+"""Launched by torchrun (one rank per GPU): the N-rank hot path must reproduce the single-process oracle.
+   torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tests/mp/multi_gpu_check.py"""
+import os
+import struct
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch
+import torch.distributed as dist
+
+import oracle as orc
+from bench import contact_pattern_pairs
+from ipc_b200 import lib as L
+from ipc_b200 import scenes
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    m, info = scenes.ball_pile(4, res=8, seed=5, height=4)
+    dHat, p, kappa, coef = info["dHat"], info["p"], 1e8, 0.025 ** 2
+    ctx = L.Context(local)
+    ids = [L.Context.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    ctx.comm_init(rank, world, ids[0])
+    ctx.set_mesh(m.V_rest_soa, m.T_soa, m.restTriInv, m.vol, m.mu, m.lam, m.mass, m.dbc, m.energy)
+    ctx.set_surface(m.SVI, m.SFEdges, m.SF_soa, m.vCoDim)
+    ctx.set_state(m.V_soa)
+    ctx.set_search_dir(p)
+    mm, pa, pe, cand = ctx.constraint_set(dHat, 1)
+    ia, ja = m.csr_pattern(1, extra_pairs=contact_pattern_pairs(m, mm, pa, pe))
+    ctx.set_csr(ia, ja, 1)
+    E = ctx.elastic_energy(coef) + ctx.barrier_energy(dHat, kappa)
+    ctx.csr_set_zero()
+    ctx.elastic_grad_hess(coef, 1, 1, 1, None, None)
+    ctx.barrier_gradient(dHat, kappa, None)
+    ctx.barrier_hessian(dHat, kappa, 1, None)
+    ctx.allreduce_grad_hess(1, 1)
+    g = ctx.download(L.BUF_GRADIENT, 3 * m.nV)
+    a = ctx.download(L.BUF_CSR_VALUES, ja.size)
+    evf, eee = L.Context.ti_error(m.V_soa, m.nV, p)
+    al = ctx.inversion_step(None, 0.2, 1.0)
+    al = ctx.ccd_partial(None, 1e-6, evf, eee, al)
+    al = ctx.hash_build_swept(None, al, m.avgEdgeLen / 3)
+    al, _ = ctx.ccd_full(1e-6, evf, eee, al)
+    ok = True
+    if rank == 0:
+        o, s = orc.Elastic(m), orc.Surf(m)
+        mm_r, pa_r, pe_r, cand_r = s.constraint_set(dHat, nthreads=8)
+        assert np.array_equal(mm, mm_r) and np.array_equal(cand, cand_r)
+        E_ref = o.energy(coef)[0] + s.barrier_energy(mm_r, pa_r, pe_r, dHat, kappa)[0]
+        g_ref = s.barrier_gradient(mm_r, pa_r, pe_r, dHat, kappa, g=o.gradient(coef, 1))
+        a_ref = o.hessian_csr(coef, ia, ja, 1, 1, 1)
+        for v in range(m.nV):
+            for r in range(3):
+                a_ref[ia[3 * v + r] - 1] += m.mass[v]
+        a_ref = s.barrier_hessian_csr(mm_r, pa_r, pe_r, dHat, kappa, ia, ja, 1, 1, a=a_ref)
+        al_ref, _ = o.inversion_step(p, 0.2, 1.0)
+        al_ref, _ = orc.ccd_partial(s, p, cand_r, 1e-6, evf, eee, al_ref, 8)
+        gr, ag = orc.grid_swept(s, p, al_ref, m.avgEdgeLen / 3)
+        al_ref, _, _ = orc.ccd_full(s, p, gr, ag, 1e-6, evf, eee, ag, 8)
+        rel = lambda x, y: np.linalg.norm(x - y) / np.linalg.norm(y)
+        res = dict(E=abs(E - E_ref) / abs(E_ref), g=rel(g, g_ref), a=rel(a, a_ref), alpha_bits=struct.pack("<d", al) == struct.pack("<d", al_ref))
+        ok = res["E"] <= 1e-10 and res["g"] <= 1e-10 and res["a"] <= 1e-9 and res["alpha_bits"]
+        print(f"MULTI_GPU_CHECK world={world} {'OK' if ok else 'FAIL'} {res} alpha={al}")
+    ctx.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
