@@ -1,0 +1,172 @@
+// IpcGpuAdapters.hpp -- reference-side binding of libipcgpu.so (include/ipcgpu.h).
+//
+// This header is compiled INSIDE an ipc-sim/IPC checkout (it includes the reference's own headers: Eigen, Mesh.hpp,
+// Energy.hpp, LinSysSolver.hpp ...), next to the files it replaces; it is NOT built in this repository, where Eigen /
+// TBB / libigl are absent.  It shows exactly how the reference's plug-in interfaces map onto the
+// C ABI, so that `Optimizer` drives the GPU path unchanged:
+//
+//   main.cpp:1383-1392   energyTerms.emplace_back(new IPC::GpuElasticEnergy<DIM>(gpu, /*NeoHookean*/0));
+//   SelfCollisionHandler.cpp  -> the static functions below replace the bodies of the same names
+//   Optimizer.cpp:1965        sh.build(result, searchDir, alpha, h)  -> IpcGpuScene::hashBuildSwept
+//
+// Everything is a thin marshalling layer: Eigen objects already have the memory layout the ABI expects
+// (column-major MatrixXd/MatrixXi == SoA, VectorXd gradient == interleaved), so no copies are made on the host side.
+#pragma once
+#include "../include/ipcgpu.h"
+
+#include "Energy.hpp"          // IPC::Energy<dim>                      (src/Energy/Energy.hpp:38-131)
+#include "LinSysSolver.hpp"    // IPC::LinSysSolver                     (src/LinSysSolver/LinSysSolver.hpp:34-37)
+#include "Mesh.hpp"            // IPC::Mesh<dim>                        (src/Mesh.hpp:61-144)
+#include "MeshCollisionUtils.hpp" // IPC::MMCVID                        (src/CollisionObject/MeshCollisionUtils.hpp:24-110)
+
+#include <spdlog/spdlog.h>
+#include <stdexcept>
+#include <vector>
+
+namespace IPC {
+
+// One per simulation: owns the device context and mirrors the scene arrays once (Mesh::computeFeatures output).
+class IpcGpuScene {
+public:
+    ipcgpu_ctx* ctx = nullptr;
+
+    explicit IpcGpuScene(int device = 0)
+    {
+        if (ipcgpu_create(device, &ctx) != IPCGPU_OK) throw std::runtime_error("ipcgpu_create failed: no CUDA device (there is no CPU fallback)");
+    }
+    ~IpcGpuScene() { ipcgpu_destroy(ctx); }
+
+    static void check(ipcgpu_ctx* c, int rc, const char* what)
+    {
+        if (rc == IPCGPU_OK) return;
+        // the reference's own convention on invariant violations is spdlog::error + exit (Optimizer.cpp:2031-2033, 3296-3306);
+        // the ABI never exits, the adapter decides
+        spdlog::error("{}: {}", what, ipcgpu_last_error(c));
+        if (rc == IPCGPU_ERR_NONPOSITIVE_DISTANCE) exit(0);
+        exit(-1);
+    }
+
+    // after Mesh::computeFeatures / setLameParam and AnimScripter::initAnimScript (Optimizer.cpp:170)
+    void setMesh(const Mesh<3>& mesh, int energyType)
+    {
+        std::vector<double> A(9 * mesh.F.rows());
+        for (int t = 0; t < mesh.F.rows(); ++t) std::copy(mesh.restTriInv[t].data(), mesh.restTriInv[t].data() + 9, A.data() + 9 * t);
+        std::vector<uint8_t> dbc(mesh.V.rows());
+        for (int v = 0; v < mesh.V.rows(); ++v) dbc[v] = static_cast<uint8_t>(mesh.vertexDBCType[v]); // NOT_DBC=0, ZERO=1, NONZERO=2 (Mesh.hpp:135-144)
+        Eigen::VectorXd mass = mesh.massMatrix.diagonal();
+        check(ctx, ipcgpu_set_mesh(ctx, (int)mesh.V.rows(), (int)mesh.F.rows(), mesh.V_rest.data(), mesh.F.data(), A.data(), mesh.triArea.data(),
+                       mesh.u.data(), mesh.lambda.data(), mass.data(), dbc.data(), energyType), "ipcgpu_set_mesh");
+        std::vector<int> se(2 * mesh.SFEdges.size()), codim(mesh.V.rows());
+        for (size_t e = 0; e < mesh.SFEdges.size(); ++e) { se[2 * e] = mesh.SFEdges[e].first; se[2 * e + 1] = mesh.SFEdges[e].second; }
+        for (int v = 0; v < mesh.V.rows(); ++v) codim[v] = mesh.vICoDim(v);
+        check(ctx, ipcgpu_set_surface(ctx, (int)mesh.SVI.size(), mesh.SVI.data(), (int)mesh.SFEdges.size(), se.data(), (int)mesh.SF.rows(), mesh.SF.data(), codim.data()),
+            "ipcgpu_set_surface");
+    }
+    // after every LinSysSolver::set_pattern (Optimizer.cpp:457-507, 3556-3595)
+    void setPattern(LinSysSolver<Eigen::VectorXi, Eigen::VectorXd>* solver, int indexBase /* 1, or 0 after CHOLMODSolver::set_pattern */)
+    {
+        check(ctx, ipcgpu_set_csr(ctx, solver->getNumRows(), solver->get_ia().data(), solver->get_ja().data(), indexBase), "ipcgpu_set_csr");
+    }
+    // whenever mesh.V changes (stepForward, Optimizer.cpp:2919-2938)
+    void setState(const Mesh<3>& mesh) { check(ctx, ipcgpu_set_state(ctx, mesh.V.data()), "ipcgpu_set_state"); }
+};
+
+// Energy<3> plug-in (replaces NeoHookeanEnergy / FixedCoRotEnergy objects created at main.cpp:1383-1392)
+template <int dim>
+class GpuElasticEnergy : public Energy<dim> {
+    IpcGpuScene& gpu;
+
+public:
+    GpuElasticEnergy(IpcGpuScene& scene, int energyType)
+        : Energy<dim>(/*needElemInvSafeGuard=*/energyType == IPCGPU_NEOHOOKEAN)
+        , gpu(scene)
+    {
+    }
+    // Energy.hpp:42-47.  redoSVD is accepted for interface fidelity; F/SVD are recomputed on the device (DESIGN.md "SVD cache")
+    void computeEnergyVal(const Mesh<dim>& data, int redoSVD, std::vector<AutoFlipSVD<Eigen::Matrix<double, dim, dim>>>&,
+        std::vector<Eigen::Matrix<double, dim, dim>>&, double coef, double& energyVal) const override
+    {
+        IpcGpuScene::check(gpu.ctx, ipcgpu_elastic_energy(gpu.ctx, coef, redoSVD, &energyVal), "ipcgpu_elastic_energy");
+    }
+    // Energy.hpp:56-62
+    void computeGradient(const Mesh<dim>& data, bool redoSVD, std::vector<AutoFlipSVD<Eigen::Matrix<double, dim, dim>>>&,
+        std::vector<Eigen::Matrix<double, dim, dim>>&, double coef, Eigen::VectorXd& gradient, bool projectDBC = true) const override
+    {
+        gradient.conservativeResize(data.V.rows() * dim); // Energy.cpp:267
+        IpcGpuScene::check(gpu.ctx, ipcgpu_elastic_gradient(gpu.ctx, coef, redoSVD, projectDBC, gradient.data()), "ipcgpu_elastic_gradient");
+    }
+    // Energy.hpp:64-71: the sink's value array is written wholesale (LinSysSolver::get_a() is mutable, LinSysSolver.hpp:463-466)
+    void computeHessian(const Mesh<dim>& data, bool redoSVD, std::vector<AutoFlipSVD<Eigen::Matrix<double, dim, dim>>>&,
+        std::vector<Eigen::Matrix<double, dim, dim>>&, double coef, LinSysSolver<Eigen::VectorXi, Eigen::VectorXd>* sink, bool projectSPD = true,
+        bool projectDBC = true) const override
+    {
+        IpcGpuScene::check(gpu.ctx, ipcgpu_elastic_hessian(gpu.ctx, coef, redoSVD, projectSPD, projectDBC, sink->get_a().data()), "ipcgpu_elastic_hessian");
+    }
+    // Energy.hpp:118-120
+    void filterStepSize(const Mesh<dim>& data, const Eigen::VectorXd& searchDir, double& stepSize) const override
+    {
+        if (this->needElemInvSafeGuard) IpcGpuScene::check(gpu.ctx, ipcgpu_inversion_step(gpu.ctx, searchDir.data(), 0.2, &stepSize), "ipcgpu_inversion_step");
+    }
+};
+
+// SelfCollisionHandler<3> statics (SelfCollisionHandler.hpp:23-232): same names, same argument meaning.
+struct GpuSelfCollisionHandler {
+    static IpcGpuScene* gpu; // set once by main()
+
+    // :2149-2478. `sh` is unused: the broad phase lives on the device.
+    static void computeConstraintSet(const Mesh<3>& mesh, const SpatialHash<3>& /*sh*/, double dHat, std::vector<MMCVID>& constraintSet,
+        std::vector<MMCVID>& paraEEMMCVIDSet, std::vector<std::pair<int, int>>& paraEEeIeJSet, bool getPTEE, std::vector<std::pair<int, int>>& cs_PTEE)
+    {
+        int nC = 0, nP = 0, nK = 0;
+        IpcGpuScene::check(gpu->ctx, ipcgpu_constraint_set(gpu->ctx, dHat, getPTEE, &nC, &nP, &nK), "ipcgpu_constraint_set");
+        constraintSet.assign(nC, MMCVID());
+        paraEEMMCVIDSet.assign(nP, MMCVID());
+        paraEEeIeJSet.assign(nP, {});
+        if (getPTEE) cs_PTEE.assign(nK, {});
+        static_assert(sizeof(MMCVID) == 4 * sizeof(int), "MMCVID is std::array<int,4>");
+        static_assert(sizeof(std::pair<int, int>) == 2 * sizeof(int), "pair<int,int> is two ints");
+        IpcGpuScene::check(gpu->ctx, ipcgpu_get_constraint_set(gpu->ctx, reinterpret_cast<int*>(constraintSet.data()), reinterpret_cast<int*>(paraEEMMCVIDSet.data()),
+                                         reinterpret_cast<int*>(paraEEeIeJSet.data()), getPTEE ? reinterpret_cast<int*>(cs_PTEE.data()) : nullptr),
+            "ipcgpu_get_constraint_set");
+    }
+    // energy of the sets just built: Optimizer.cpp:3290-3353 collapses to one call
+    static double barrierEnergy(double dHat, double kappa)
+    {
+        double E = 0.0;
+        IpcGpuScene::check(gpu->ctx, ipcgpu_barrier_energy(gpu->ctx, dHat, kappa, &E), "ipcgpu_barrier_energy");
+        return E;
+    }
+    // :84-148 + :2990-3045 (input = b'(d) is recomputed on the device)
+    static void leftMultiplyConstraintJacobianT(const Mesh<3>&, const std::vector<MMCVID>&, const Eigen::VectorXd&, Eigen::VectorXd& output_incremental, double dHat,
+        double kappa)
+    {
+        IpcGpuScene::check(gpu->ctx, ipcgpu_barrier_gradient(gpu->ctx, dHat, kappa, output_incremental.data()), "ipcgpu_barrier_gradient");
+    }
+    // :418-561 + :3049-3201
+    static void augmentIPHessian(const Mesh<3>&, const std::vector<MMCVID>&, LinSysSolver<Eigen::VectorXi, Eigen::VectorXd>* mtr, double dHat, double kappa,
+        bool projectDBC)
+    {
+        IpcGpuScene::check(gpu->ctx, ipcgpu_barrier_hessian(gpu->ctx, dHat, kappa, projectDBC, mtr->get_a().data()), "ipcgpu_barrier_hessian");
+    }
+    // :690-866
+    static void largestFeasibleStepSize_TightInclusion(const Mesh<3>&, const SpatialHash<3>&, const Eigen::VectorXd& searchDir, double tolerance,
+        const std::vector<std::pair<int, int>>&, std::vector<std::pair<int, int>>&, double& stepSize)
+    {
+        IpcGpuScene::check(gpu->ctx, ipcgpu_ccd_partial_ti(gpu->ctx, searchDir.data(), tolerance, tight_inclusion_vf_err.data(), tight_inclusion_ee_err.data(), &stepSize),
+            "ipcgpu_ccd_partial_ti");
+    }
+    // SpatialHash::build(mesh, searchDir, curMaxStepSize, voxelSize) at Optimizer.cpp:1965 (alpha is mutated, SpatialHash.hpp:603-618)
+    static void hashBuildSwept(const Eigen::VectorXd& searchDir, double& alpha, double voxelSize)
+    {
+        IpcGpuScene::check(gpu->ctx, ipcgpu_hash_build_swept(gpu->ctx, searchDir.data(), &alpha, voxelSize), "ipcgpu_hash_build_swept");
+    }
+    // :1370-1630
+    static void largestFeasibleStepSize_CCD_TightInclusion(const Mesh<3>&, const SpatialHash<3>&, const Eigen::VectorXd&, double tolerance,
+        std::vector<std::pair<int, int>>&, double& stepSize)
+    {
+        IpcGpuScene::check(gpu->ctx, ipcgpu_ccd_full_ti(gpu->ctx, tolerance, tight_inclusion_vf_err.data(), tight_inclusion_ee_err.data(), &stepSize, nullptr),
+            "ipcgpu_ccd_full_ti");
+    }
+};
+
+} // namespace IPC
