@@ -364,11 +364,15 @@ static int run_grad_hess(ipcgpu_ctx* ctx, double coef, int projectSPD, int proje
         ++ctx->launches;
     }
     if (need_h) {
-        // the mass term is added by rank 0 only so that the cross-rank sum counts it once
-        const double* m = (add_mass && ctx->has_mass && ctx->rank == 0) ? ctx->mass.p : nullptr;
         pe = ctx->prof_begin(IPCGPU_STAGE_ASSEMBLE_CSR);
         assemble_csr(ctx->nSlots, ctx->slot_v.p, ctx->slot_u.p, ctx->slot_off.p, ctx->con_ptr.p, ctx->con_src.p, ctx->hblk.p,
-            ctx->has_dbc ? ctx->dbc.p : nullptr, projectDBC, m, accumulate_a ? 1 : 0, ctx->a.p, ctx->stream);
+            ctx->has_dbc ? ctx->dbc.p : nullptr, projectDBC, nullptr, accumulate_a ? 1 : 0, ctx->a.p, ctx->stream);
+        // per-vertex diagonal terms (mass, Dirichlet identity) over ALL vertices, by rank 0 only so that the cross-rank sum counts them once
+        if (ctx->rank == 0) {
+            const double* m = (add_mass && ctx->has_mass) ? ctx->mass.p : nullptr;
+            diag_mass_dbc(ctx->nV, ctx->ia.p, ctx->index_base, ctx->has_dbc ? ctx->dbc.p : nullptr, projectDBC, m, ctx->a.p, ctx->stream);
+            ++ctx->launches;
+        }
         ctx->prof_end(pe);
         ++ctx->launches;
     }
@@ -703,9 +707,15 @@ int ipcgpu_barrier_hessian(ipcgpu_ctx* ctx, double dHat, double kappa, int proje
     }
     CK(cudaMemsetAsync(ctx->flag.p, 0, sizeof(int), ctx->stream));
     cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_BARRIER);
-    barrier_hessian(barrier_args(ctx, dHat, kappa, projectDBC), ctx->a.p, ctx->flag.p, ctx->stream);
+    {
+        const BarrierArgs ba = barrier_args(ctx, dHat, kappa, projectDBC);
+        const size_t np = (size_t)std::max(ba.nC + ba.nP, 1);
+        ALLOC(ctx->bHraw, np * 144);
+        ALLOC(ctx->brows, np * 4);
+        barrier_hessian(ba, ctx->a.p, ctx->flag.p, ctx->bHraw.p, ctx->brows.p, ctx->stream);
+    }
     ctx->prof_end(pe);
-    ++ctx->launches;
+    ctx->launches += 2;
     CK(cudaGetLastError());
     if (a_inout && ctx->nranks > 1) {
         int rc = ipcgpu_allreduce_grad_hess(ctx, 0, 1);

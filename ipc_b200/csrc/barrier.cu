@@ -12,6 +12,7 @@
 //    tet count; the elastic path stays deterministic, the barrier scatter is order-free to ~1 ulp of the sum).
 #include "contact.cuh"
 #include "kernels.h"
+#include <algorithm>
 
 namespace ipcgpu {
 
@@ -193,87 +194,25 @@ __global__ void __launch_bounds__(128) k_barrier_gradient(BarrierArgs p, double*
 
 // -----------------------------------------------------------------------------------------------------------
 // Hessian: makePD( kappa*mult*(b'' g g^T + b' H_d) ) scattered into the CSR (upper triangle)
+//   pass 1 (thread per pair)  : unprojected block, zero-padded to 12x12, to global memory (144 contiguous doubles per pair)
+//   pass 2 (warp per pair)    : parallel-order Jacobi eigen-solver on the 12x12 (6 disjoint rotations per round, 11 rounds
+//                               per sweep, the round-robin tournament schedule), clamp, rebuild, red.add into the CSR
 // -----------------------------------------------------------------------------------------------------------
-constexpr int kHW = 32; // pairs per CTA (one warp); 3 matrices x 144 x 32 lanes x 8 B = 110,592 B of shared memory
-
-__device__ inline void jacobi_psd(int n, double* __restrict__ A, double* __restrict__ Vv, const double* __restrict__ H0, double* __restrict__ out, int lane)
+__global__ void __launch_bounds__(64) k_barrier_hessian_build(BarrierArgs p, double* __restrict__ Hraw, int* __restrict__ rows_out)
 {
-    // A: work copy (destroyed), Vv: eigenvectors, H0: original, out: result (may alias H0). element (i,j) at (i*12+j)*32+lane
-#define EL(M, i, j) M[((i) * 12 + (j)) * kHW + lane]
-    for (int i = 0; i < n; ++i)
-        for (int j = 0; j < n; ++j) {
-            EL(A, i, j) = EL(H0, i, j);
-            EL(Vv, i, j) = (i == j) ? 1.0 : 0.0;
-        }
-    for (int sweep = 0; sweep < 40; ++sweep) {
-        double off = 0.0, dg = 0.0;
-        for (int i = 0; i < n; ++i) {
-            double t = EL(A, i, i);
-            dg += t * t;
-            for (int j = i + 1; j < n; ++j) {
-                double u = EL(A, i, j);
-                off += u * u;
-            }
-        }
-        if (off <= 1e-26 * dg || off <= 1e-300) break; // off-diagonal mass at rounding level (eigenvalue error is second order in it)
-        for (int pI = 0; pI < n; ++pI)
-            for (int q = pI + 1; q < n; ++q) {
-                const double apq = EL(A, pI, q);
-                if (apq == 0.0) continue;
-                const double theta = (EL(A, q, q) - EL(A, pI, pI)) / (2.0 * apq);
-                const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-                for (int k = 0; k < n; ++k) {
-                    const double akp = EL(A, k, pI), akq = EL(A, k, q);
-                    EL(A, k, pI) = c * akp - s * akq;
-                    EL(A, k, q) = s * akp + c * akq;
-                }
-                for (int k = 0; k < n; ++k) {
-                    const double apk = EL(A, pI, k), aqk = EL(A, q, k);
-                    EL(A, pI, k) = c * apk - s * aqk;
-                    EL(A, q, k) = s * apk + c * aqk;
-                }
-                for (int k = 0; k < n; ++k) {
-                    const double vkp = EL(Vv, k, pI), vkq = EL(Vv, k, q);
-                    EL(Vv, k, pI) = c * vkp - s * vkq;
-                    EL(Vv, k, q) = s * vkp + c * vkq;
-                }
-            }
-    }
-    bool neg = false;
-    for (int i = 0; i < n; ++i) neg = neg || (EL(A, i, i) < 0.0);
-    if (!neg) return; // lambda_min >= 0: the reference returns the matrix unchanged
-    for (int i = 0; i < n; ++i)
-        for (int j = i; j < n; ++j) {
-            double sacc = 0.0;
-            for (int k = 0; k < n; ++k) {
-                const double lam = EL(A, k, k);
-                if (lam > 0.0) sacc += EL(Vv, i, k) * lam * EL(Vv, j, k);
-            }
-            EL(out, i, j) = sacc;
-            EL(out, j, i) = sacc;
-        }
-#undef EL
-}
-
-__global__ void __launch_bounds__(kHW) k_barrier_hessian(BarrierArgs p, double* __restrict__ a, int* __restrict__ err)
-{
-    extern __shared__ double sm[];
-    double* H = sm;
-    double* A = sm + 144 * kHW;
-    double* Vv = sm + 288 * kHW;
-    const int lane = threadIdx.x;
-    const int c = blockIdx.x * kHW + lane;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= p.nC + p.nP) return;
-#define HE(i, j) H[((i) * 12 + (j)) * kHW + lane]
+    double* H = Hraw + (size_t)c * 144;
+#define HE(i, j) H[(i) * 12 + (j)]
+    for (int i = 0; i < 144; ++i) H[i] = 0.0;
     const bool is_para = c >= p.nC;
     const int4 mm = is_para ? p.para[c - p.nC] : p.cs[c];
     PairStencil s = decode(mm);
     V3 x[4];
     for (int k = 0; k < s.nv; ++k) x[k] = load_vertex(p.V, p.nV, s.v[k]);
-    int n, rows[4];
+    int rows[4];
     if (!is_para) {
-        n = 3 * s.nv;
+        const int n = 3 * s.nv;
         double gd[12];
         const double d = pair_derivs(s, x, gd, true, [&](int i, int j, double v) { HE(i, j) = v; });
         double b, db, d2b;
@@ -285,33 +224,28 @@ __global__ void __launch_bounds__(kHW) k_barrier_hessian(BarrierArgs p, double* 
     }
     else {
         // mollified pair on the two-edge stencil (:3049-3173)
-        n = 12;
         int ev[4];
         para_edge_stencil(mm, p.para_e[c - p.nC], p.SE, ev);
         V3 ex[4];
         for (int k = 0; k < 4; ++k) ex[k] = load_vertex(p.V, p.nV, ev[k]);
         double gd0[12], gd[12], eg[12];
-        // distance derivatives first into A (scratch), then embedded into the edge stencil in Vv (scratch)
-#define AE(i, j) A[((i) * 12 + (j)) * kHW + lane]
-#define VE(i, j) Vv[((i) * 12 + (j)) * kHW + lane]
-        const double d = pair_derivs(s, x, gd0, true, [&](int i, int j, double v) { AE(i, j) = v; });
+        double AE[144], VE[144]; // distance Hessian on its own stencil / embedded in the edge stencil
+        const double d = pair_derivs(s, x, gd0, true, [&](int i, int j, double v) { AE[i * 12 + j] = v; });
         int map[4];
         for (int k = 0; k < s.nv; ++k) {
             map[k] = -1;
             for (int i = 0; i < 4; ++i)
                 if (ev[i] == s.v[k]) map[k] = i;
         }
-        for (int i = 0; i < 12; ++i) {
-            gd[i] = 0.0;
-            for (int j = 0; j < 12; ++j) VE(i, j) = 0.0;
-        }
+        for (int i = 0; i < 12; ++i) gd[i] = 0.0;
+        for (int i = 0; i < 144; ++i) VE[i] = 0.0;
         for (int k = 0; k < s.nv; ++k) {
             if (map[k] < 0) continue;
             for (int i = 0; i < 3; ++i) gd[3 * map[k] + i] = gd0[3 * k + i];
             for (int l = 0; l < s.nv; ++l) {
                 if (map[l] < 0) continue;
                 for (int i = 0; i < 3; ++i)
-                    for (int j = 0; j < 3; ++j) VE(3 * map[k] + i, 3 * map[l] + j) = AE(3 * k + i, 3 * l + j);
+                    for (int j = 0; j < 3; ++j) VE[(3 * map[k] + i) * 12 + 3 * map[l] + j] = AE[(3 * k + i) * 12 + 3 * l + j];
             }
         }
         double b, db, d2b;
@@ -320,32 +254,156 @@ __global__ void __launch_bounds__(kHW) k_barrier_hessian(BarrierArgs p, double* 
         const double k = p.kappa;
         for (int i = 0; i < 12; ++i)
             for (int j = 0; j < 12; ++j)
-                HE(i, j) = ((k * db) * gd[i]) * eg[j] + ((k * db) * gd[j]) * eg[i] + (k * b) * HE(i, j) + ((k * e * d2b) * gd[i]) * gd[j] + (k * e * db) * VE(i, j);
+                HE(i, j) = ((k * db) * gd[i]) * eg[j] + ((k * db) * gd[j]) * eg[i] + (k * b) * HE(i, j) + ((k * e * d2b) * gd[i]) * gd[j] + (k * e * db) * VE[i * 12 + j];
         for (int q = 0; q < 4; ++q) rows[q] = ev[q];
-#undef AE
-#undef VE
     }
-    jacobi_psd(n, A, Vv, H, H, lane);
-    // scatter (upper triangle only; projected Dirichlet rows/cols dropped)   [:533-556]
-    const int nvb = n / 3;
-    for (int i = 0; i < nvb; ++i) {
-        if (proj_dbc(p.dbc, rows[i], p.projectDBC)) continue;
-        for (int j = 0; j < nvb; ++j) {
-            if (proj_dbc(p.dbc, rows[j], p.projectDBC)) continue;
-            if (rows[i] > rows[j]) continue; // lower-triangular block: its transpose is added by (j,i)
-            for (int r = 0; r < 3; ++r) {
-                const int row = 3 * rows[i] + r;
-                const int c0 = (rows[i] == rows[j]) ? r : 0;
-                const int pos = csr_find(p.ia, p.ja, p.base, row, 3 * rows[j] + c0);
-                if (pos < 0) {
-                    atomicExch(err, 1);
-                    continue;
+    for (int q = 0; q < 4; ++q) rows_out[4 * (size_t)c + q] = rows[q];
+#undef HE
+}
+
+// round-robin tournament: 11 rounds of 6 disjoint (p,q) pairs over 12 indices; kPartner[r][i] = index paired with i in round r
+__constant__ signed char kPartner[11][12];
+__constant__ signed char kPairP[11][6], kPairQ[11][6];
+
+constexpr int kProjWarps = 8; // warps (pairs) per CTA in the projection kernel
+
+__global__ void __launch_bounds__(32 * kProjWarps) k_barrier_hessian_project(BarrierArgs p, const double* __restrict__ Hraw, const int* __restrict__ rows_in,
+    double* __restrict__ a, int* __restrict__ err)
+{
+    __shared__ double sA[kProjWarps][144];
+    __shared__ double sV[kProjWarps][144];
+    __shared__ double sCS[kProjWarps][12]; // c (0..5) and s (6..11) of the round's rotations
+    __shared__ int sOff[kProjWarps][48];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int c = blockIdx.x * kProjWarps + wib;
+    if (c >= p.nC + p.nP) return;
+    double* A = sA[wib];
+    double* Vv = sV[wib];
+    double* cs = sCS[wib];
+    const double* H0 = Hraw + (size_t)c * 144;
+    for (int e = lane; e < 144; e += 32) {
+        A[e] = H0[e];
+        Vv[e] = ((e / 12) == (e % 12)) ? 1.0 : 0.0;
+    }
+    __syncwarp();
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        // convergence: off-diagonal mass vs diagonal mass
+        double off = 0.0, dg = 0.0;
+        for (int e = lane; e < 144; e += 32) {
+            const double v = A[e];
+            if ((e / 12) == (e % 12)) dg += v * v;
+            else off += v * v;
+        }
+        off = warp_sum(off);
+        dg = warp_sum(dg);
+        if (off <= 2e-26 * dg || off <= 1e-300) break;
+        for (int r = 0; r < 11; ++r) {
+            if (lane < 6) {
+                const int pI = kPairP[r][lane], q = kPairQ[r][lane];
+                const double apq = A[pI * 12 + q];
+                double cc = 1.0, ss = 0.0;
+                if (apq != 0.0) {
+                    const double theta = (A[q * 12 + q] - A[pI * 12 + pI]) / (2.0 * apq);
+                    const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                    cc = 1.0 / sqrt(t * t + 1.0);
+                    ss = t * cc;
                 }
-                for (int q = c0; q < 3; ++q) atomicAdd(a + pos + (q - c0), HE(3 * i + r, 3 * j + q));
+                cs[lane] = cc;
+                cs[6 + lane] = ss;
+            }
+            __syncwarp();
+            // A <- J^T A J with J = product of the 6 disjoint rotations; element (i,j) mixes rows {i,i'} and columns {j,j'}
+            double newA[5], newV[5];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const int e = lane + 32 * k;
+                if (e < 144) {
+                    const int i = e / 12, j = e % 12;
+                    const int ip = kPartner[r][i], jp = kPartner[r][j];
+                    // rotation acting on index i: if i is the "p" of its pair, x_i' = c x_i - s x_ip ; if "q": x_i' = s x_ip + c x_i
+                    const int pi = min(i, ip), pj = min(j, jp);
+                    int ri = 0, rj = 0;
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) {
+                        if (kPairP[r][q] == pi) ri = q;
+                        if (kPairP[r][q] == pj) rj = q;
+                    }
+                    const double ci = cs[ri], si = (i < ip) ? -cs[6 + ri] : cs[6 + ri];
+                    const double cj = cs[rj], sj = (j < jp) ? -cs[6 + rj] : cs[6 + rj];
+                    // y = c*x_self + sgn*s*x_partner  (p: c x_p - s x_q ; q: s x_p + c x_q)
+                    const double a_ij = A[i * 12 + j], a_ipj = A[ip * 12 + j], a_ijp = A[i * 12 + jp], a_ipjp = A[ip * 12 + jp];
+                    const double row_j = ci * a_ij + si * a_ipj;    // (J^T A)[i][j]
+                    const double row_jp = ci * a_ijp + si * a_ipjp; // (J^T A)[i][jp]
+                    newA[k] = cj * row_j + sj * row_jp;
+                    newV[k] = cj * Vv[i * 12 + j] + sj * Vv[i * 12 + jp]; // V <- V J
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const int e = lane + 32 * k;
+                if (e < 144) {
+                    A[e] = newA[k];
+                    Vv[e] = newV[k];
+                }
+            }
+            __syncwarp();
+        }
+    }
+    // clamp: lambda_min >= 0 -> unchanged (IglUtils.hpp:123-125)
+    bool neg = false;
+    if (lane < 12) neg = A[lane * 12 + lane] < 0.0;
+    neg = __any_sync(0xffffffffu, neg);
+    double out[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const int e = lane + 32 * k;
+        out[k] = 0.0;
+        if (e < 144) {
+            if (!neg) out[k] = H0[e];
+            else {
+                const int i = e / 12, j = e % 12;
+                double sacc = 0.0;
+#pragma unroll
+                for (int q = 0; q < 12; ++q) {
+                    const double lam = A[q * 12 + q];
+                    if (lam > 0.0) sacc += Vv[i * 12 + q] * lam * Vv[j * 12 + q];
+                }
+                out[k] = sacc;
             }
         }
     }
-#undef HE
+    // CSR offsets of the 16 vertex blocks x 3 rows (upper-triangular blocks only); -1 = skip, -2 = missing in the pattern
+    int rows[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) rows[q] = rows_in[4 * (size_t)c + q];
+    for (int t = lane; t < 48; t += 32) {
+        const int bi = t / 12, bj = (t / 3) % 4, r = t % 3;
+        int o = -1;
+        const int vi = rows[bi], vj = rows[bj];
+        if (vi >= 0 && vj >= 0 && vi <= vj && !(vi == vj && bi != bj) && !proj_dbc(p.dbc, vi, p.projectDBC) && !proj_dbc(p.dbc, vj, p.projectDBC)) {
+            const int c0 = (vi == vj) ? r : 0;
+            o = csr_find(p.ia, p.ja, p.base, 3 * vi + r, 3 * vj + c0);
+            if (o < 0) o = -2;
+            else o -= c0; // so that column q of the block lands at o + q
+        }
+        sOff[wib][t] = o;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const int e = lane + 32 * k;
+        if (e < 144) {
+            const int i = e / 12, j = e % 12;
+            const int bi = i / 3, r = i % 3, bj = j / 3, q = j % 3;
+            const int o = sOff[wib][(bi * 4 + bj) * 3 + r];
+            if (o == -2) atomicExch(err, 1);
+            else if (o != -1) {
+                if (rows[bi] == rows[bj] && q < r) continue; // strictly lower part of a diagonal block
+                atomicAdd(a + o + q, out[k]);
+            }
+        }
+    }
 }
 
 // -----------------------------------------------------------------------------------------------------------
@@ -360,17 +418,37 @@ void barrier_gradient(const BarrierArgs& p, double* g, cudaStream_t st)
     const int n = p.nC + p.nP;
     if (n > 0) k_barrier_gradient<<<(n + 127) / 128, 128, 0, st>>>(p, g);
 }
-void barrier_hessian(const BarrierArgs& p, double* a, int* err, cudaStream_t st)
+static void init_tournament()
+{
+    // circle method: index 11 fixed, the others rotate
+    signed char partner[11][12], P[11][6], Q[11][6];
+    for (int r = 0; r < 11; ++r) {
+        int ring[11];
+        for (int k = 0; k < 11; ++k) ring[k] = (r + k) % 11;
+        int a0 = ring[0], b0 = 11, cnt = 0;
+        P[r][cnt] = (signed char)std::min(a0, b0); Q[r][cnt] = (signed char)std::max(a0, b0); ++cnt;
+        for (int k = 1; k <= 5; ++k) {
+            int x = ring[k], y = ring[11 - k];
+            P[r][cnt] = (signed char)std::min(x, y); Q[r][cnt] = (signed char)std::max(x, y); ++cnt;
+        }
+        for (int q = 0; q < 6; ++q) { partner[r][P[r][q]] = Q[r][q]; partner[r][Q[r][q]] = P[r][q]; }
+    }
+    cudaMemcpyToSymbol(kPartner, partner, sizeof(partner));
+    cudaMemcpyToSymbol(kPairP, P, sizeof(P));
+    cudaMemcpyToSymbol(kPairQ, Q, sizeof(Q));
+}
+
+void barrier_hessian(const BarrierArgs& p, double* a, int* err, double* Hraw, int* rows, cudaStream_t st)
 {
     const int n = p.nC + p.nP;
     if (n <= 0) return;
-    const size_t smem = (size_t)3 * 144 * kHW * sizeof(double);
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(k_barrier_hessian, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = true;
+    static bool init = false;
+    if (!init) {
+        init_tournament();
+        init = true;
     }
-    k_barrier_hessian<<<(n + kHW - 1) / kHW, kHW, smem, st>>>(p, a, err);
+    k_barrier_hessian_build<<<(n + 63) / 64, 64, 0, st>>>(p, Hraw, rows);
+    k_barrier_hessian_project<<<(n + kProjWarps - 1) / kProjWarps, 32 * kProjWarps, 0, st>>>(p, Hraw, rows, a, err);
 }
 
 } // namespace ipcgpu

@@ -100,7 +100,8 @@ struct ipcgpu_ctx {
     size_t ccd_capacity = (size_t)1 << 23; // candidate pairs
     std::vector<int> h_SVI;                // host copy (pSize of the swept build is a serial host sum, SpatialHash.hpp:603-612)
     std::vector<double> h_dir;             // host shadow of the last uploaded search direction
-    ipcgpu::DevBuf<double> bpartials;
+    ipcgpu::DevBuf<double> bpartials, bHraw;
+    ipcgpu::DevBuf<int> brows;
 
     // gradient gather map (local tets)
     ipcgpu::DevBuf<int> inc_ptr, inc;

@@ -307,19 +307,13 @@ __global__ void __launch_bounds__(256) k_assemble_csr(int nSlots, const int* __r
     const int b = con_ptr[sIdx], e = con_ptr[sIdx + 1];
     if (v == u) {
         double h[6] = { 0, 0, 0, 0, 0, 0 };
-        if (pv) { // identity rows for projected Dirichlet vertices (IglUtils.hpp:44-53)
-            h[0] = h[3] = h[5] = 1.0;
+        if (pv) { // projected Dirichlet vertex: block dropped here, identity written by k_diag_mass_dbc (IglUtils.hpp:44-53)
         }
         else {
             for (int q = b; q < e; ++q) {
                 const double* s = hblk + __ldg(con_src + q);
 #pragma unroll
                 for (int k = 0; k < 6; ++k) h[k] += s[k];
-            }
-            if (mass) {
-                h[0] += mass[v];
-                h[3] += mass[v];
-                h[5] += mass[v];
             }
         }
         if (accumulate && !pv) {
@@ -360,6 +354,22 @@ __global__ void __launch_bounds__(256) k_assemble_csr(int nSlots, const int* __r
                 a[o2 + c] = h[6 + c];
             }
         }
+    }
+}
+
+// per-vertex diagonal terms of computePrecondMtr (Optimizer.cpp:3638-3668): mass on free vertices, identity on projected
+// Dirichlet vertices (setCoeff, also IglUtils.hpp:44-53).  The diagonal is the first stored entry of an upper-triangular row.
+__global__ void __launch_bounds__(256) k_diag_mass_dbc(int nV, const int* __restrict__ ia, int base, const uint8_t* __restrict__ dbc, int projectDBC,
+    const double* __restrict__ mass, double* __restrict__ a)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nV) return;
+    const bool pv = dbc && (dbc[v] == 1 || (dbc[v] == 2 && projectDBC));
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int o = ia[3 * v + r] - base;
+        if (pv) a[o] = 1.0;
+        else if (mass) a[o] += mass[v];
     }
 }
 
@@ -576,6 +586,10 @@ void assemble_csr(int nSlots, const int* slot_v, const int* slot_u, const int* s
 {
     if (nSlots <= 0) return;
     k_assemble_csr<<<(nSlots + 255) / 256, 256, 0, st>>>(nSlots, slot_v, slot_u, slot_off, con_ptr, con_src, hblk, dbc, projectDBC, mass, accumulate, a);
+}
+void diag_mass_dbc(int nV, const int* ia, int base, const uint8_t* dbc, int projectDBC, const double* mass, double* a, cudaStream_t st)
+{
+    if (nV > 0 && (dbc || mass)) k_diag_mass_dbc<<<(nV + 255) / 256, 256, 0, st>>>(nV, ia, base, dbc, projectDBC, mass, a);
 }
 void slot_offsets(int nSlots, const int* slot_v, const int* slot_u, const int* ia, const int* ja, int base, int* slot_off, int* err, cudaStream_t st)
 {

@@ -24,6 +24,7 @@ void elastic_grad_hess(const ElasticArgs& p, double coef, int projectSPD, bool n
 void gather_gradient(int nV, const int* inc_ptr, const int* inc, const double* gcont, const uint8_t* dbc, int projectDBC, int accumulate, double* g, cudaStream_t st);
 void assemble_csr(int nSlots, const int* slot_v, const int* slot_u, const int* slot_off, const int* con_ptr, const unsigned* con_src,
     const double* hblk, const uint8_t* dbc, int projectDBC, const double* mass, int accumulate, double* a, cudaStream_t st);
+void diag_mass_dbc(int nV, const int* ia, int base, const uint8_t* dbc, int projectDBC, const double* mass, double* a, cudaStream_t st);
 void slot_offsets(int nSlots, const int* slot_v, const int* slot_u, const int* ia, const int* ja, int base, int* slot_off, int* err, cudaStream_t st);
 void inversion_step(const ElasticArgs& p, const double* dir, double slack, double* per_tet, unsigned long long* min_ord, cudaStream_t st);
 
@@ -57,7 +58,7 @@ struct BarrierArgs {
 void barrier_energy(const BarrierArgs& p, double* partials, int* bad, cudaStream_t st);
 int barrier_energy_blocks(int n);
 void barrier_gradient(const BarrierArgs& p, double* g, cudaStream_t st);
-void barrier_hessian(const BarrierArgs& p, double* a, int* err, cudaStream_t st);
+void barrier_hessian(const BarrierArgs& p, double* a, int* err, double* Hraw /* 144 per pair */, int* rows /* 4 per pair */, cudaStream_t st);
 // elastic.cu (shared fixed-order reduction)
 void reduce_sum(const double* partials, int n, double scale, double* out, cudaStream_t st);
 
