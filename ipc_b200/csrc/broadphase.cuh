@@ -52,4 +52,49 @@ DEV int lower_bound_u64(const unsigned long long* __restrict__ keys, int n, unsi
     return lo;
 }
 
+DEV int upper_bound_u64(const unsigned long long* __restrict__ keys, int n, unsigned long long k)
+{
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (keys[mid] <= k) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// Grid v2: every primitive is registered ONCE, in the cell of its box's lower corner.  With cell edge >= (largest box extent +
+// 2*radius), a box starting in cell c ends in c or c+1, and a query box inflated by `radius` covers cells q0..q1 (q1 <= q0+1), so
+// every partner starts in [q0-1, q1] per axis: at most 3x3 rows of <= 3 consecutive cells = 9 contiguous key ranges.
+struct SortedGrid {
+    const unsigned long long* keys; // sorted cell keys
+    const int* ids;                 // primitive id per entry
+    const Box* boxes;               // primitive boxes gathered in sorted order (coalesced candidate scan)
+    int n;
+};
+
+DEV bool boxes_overlap(const Box& a, const Box& b)
+{
+    return !(a.lo[0] > b.hi[0] || b.lo[0] > a.hi[0] || a.lo[1] > b.hi[1] || b.lo[1] > a.hi[1] || a.lo[2] > b.hi[2] || b.lo[2] > a.hi[2]);
+}
+
+// warp-cooperative scan: calls f(id, box) on every registered primitive whose box overlaps the (already inflated) query box.
+// All 32 lanes must call this together; f runs on the lane that found the candidate.
+template <typename F>
+DEV void warp_scan_candidates(const Grid& g, const SortedGrid& sg, const Box& qb, int lane, F f)
+{
+    int c0[3], c1[3];
+    cell_range(g, qb, c0, c1);
+    const int x0 = max(c0[0] - 1, 0), x1 = c1[0];
+    for (int iz = max(c0[2] - 1, 0); iz <= c1[2]; ++iz)
+        for (int iy = max(c0[1] - 1, 0); iy <= c1[1]; ++iy) {
+            const int start = lower_bound_u64(sg.keys, sg.n, cell_key(g, x0, iy, iz));
+            const int end = upper_bound_u64(sg.keys, sg.n, cell_key(g, x1, iy, iz));
+            for (int k = start + lane; k < end; k += 32) {
+                const Box b = sg.boxes[k];
+                if (boxes_overlap(qb, b)) f(sg.ids[k], b);
+            }
+        }
+}
+
 } // namespace ipcgpu

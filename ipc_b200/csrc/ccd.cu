@@ -118,84 +118,63 @@ DEV void push_cand(const CandOut& o, int2 c)
     else atomicExch(o.overflow, 1);
 }
 
-__global__ void __launch_bounds__(128) k_ccd_query_pt(SurfArgs s, const Grid* __restrict__ gp, const Box* __restrict__ vboxes, const Box* __restrict__ tboxes,
-    const unsigned long long* __restrict__ keys, const int* __restrict__ vals, int nEntries, const int* __restrict__ vmin, const int* __restrict__ vmax, double radius,
-    int first, int last, CandOut out)
+// one WARP per surface vertex (queryPointForPrimitives, triangle part)
+__global__ void __launch_bounds__(128) k_ccd_query_pt(SurfArgs s, const Grid* __restrict__ gp, const Box* __restrict__ vboxes, SortedGrid tg, const int* __restrict__ vmin,
+    const int* __restrict__ vmax, double radius, int first, int last, CandOut out)
 {
-    const int svI = first + blockIdx.x * blockDim.x + threadIdx.x;
+    const int svI = first + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
     if (svI >= last) return;
     const Grid g = *gp;
     const int vI = s.SVI[svI];
     Box qb = vboxes[svI];
     for (int k = 0; k < 3; ++k) { qb.lo[k] -= radius; qb.hi[k] += radius; }
-    int c0[3], c1[3];
-    cell_range(g, qb, c0, c1);
     const int* plo = vmin + 3 * (size_t)vI;
     const int* phi = vmax + 3 * (size_t)vI;
     const int vcod = cod_v(s, vI);
     const bool vdbc = dbc_v(s, vI);
-    for (int iz = c0[2]; iz <= c1[2]; ++iz)
-        for (int iy = c0[1]; iy <= c1[1]; ++iy)
-            for (int ix = c0[0]; ix <= c1[0]; ++ix) {
-                const unsigned long long key = cell_key(g, ix, iy, iz);
-                for (int e = lower_bound_u64(keys, nEntries, key); e < nEntries && keys[e] == key; ++e) {
-                    const int sfI = vals[e];
-                    int t0[3], t1[3];
-                    cell_range(g, tboxes[sfI], t0, t1);
-                    if (max(t0[0], c0[0]) != ix || max(t0[1], c0[1]) != iy || max(t0[2], c0[2]) != iz) continue;
-                    int tv[3] = { s.SF[sfI], s.SF[(size_t)s.nSF + sfI], s.SF[(size_t)2 * s.nSF + sfI] };
-                    int lo[3], hi[3];
-                    prim_range(vmin, vmax, tv, 3, lo, hi);
-                    if (!ranges_overlap(plo, phi, lo, hi)) continue; // the reference's hash would not pair them
-                    if (vI == tv[0] || vI == tv[1] || vI == tv[2]) continue;
-                    if ((vcod < 3 && cod_v(s, tv[0]) < 3) || (vdbc && dbc_v(s, tv[0]) && dbc_v(s, tv[1]) && dbc_v(s, tv[2]))) continue;
-                    push_cand(out, make_int2(-svI - 1, sfI));
-                }
-            }
+    warp_scan_candidates(g, tg, qb, lane, [&](int sfI, const Box&) {
+        int tv[3] = { s.SF[sfI], s.SF[(size_t)s.nSF + sfI], s.SF[(size_t)2 * s.nSF + sfI] };
+        int lo[3], hi[3];
+        prim_range(vmin, vmax, tv, 3, lo, hi);
+        if (!ranges_overlap(plo, phi, lo, hi)) return; // the reference's hash would not pair them
+        if (vI == tv[0] || vI == tv[1] || vI == tv[2]) return;
+        if ((vcod < 3 && cod_v(s, tv[0]) < 3) || (vdbc && dbc_v(s, tv[0]) && dbc_v(s, tv[1]) && dbc_v(s, tv[2]))) return;
+        push_cand(out, make_int2(-svI - 1, sfI));
+    });
 }
 
-__global__ void __launch_bounds__(128) k_ccd_query_ee(SurfArgs s, const Grid* __restrict__ gp, const Box* __restrict__ eboxes,
-    const unsigned long long* __restrict__ keys, const int* __restrict__ vals, int nEntries, const int* __restrict__ vmin, const int* __restrict__ vmax, double radius,
-    int first, int last, CandOut out)
+// one WARP per surface edge (queryEdgeForEdgesWithBBoxCheck, SpatialHash.hpp:803-832)
+__global__ void __launch_bounds__(128) k_ccd_query_ee(SurfArgs s, const Grid* __restrict__ gp, const Box* __restrict__ eboxes, SortedGrid eg, const int* __restrict__ vmin,
+    const int* __restrict__ vmax, double radius, int first, int last, CandOut out)
 {
-    const int eI = first + blockIdx.x * blockDim.x + threadIdx.x;
+    const int eI = first + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
     if (eI >= last) return;
     const Grid g = *gp;
     const int a[2] = { s.SE[2 * eI], s.SE[2 * eI + 1] };
     const Box eb = eboxes[eI];
     Box qb = eb;
     for (int k = 0; k < 3; ++k) { qb.lo[k] -= radius; qb.hi[k] += radius; }
-    int c0[3], c1[3];
-    cell_range(g, qb, c0, c1);
     int qlo[3], qhi[3];
     prim_range(vmin, vmax, a, 2, qlo, qhi);
     const int ecod = cod_v(s, a[0]);
     const bool edbc = dbc_v(s, a[0]) && dbc_v(s, a[1]);
-    for (int iz = c0[2]; iz <= c1[2]; ++iz)
-        for (int iy = c0[1]; iy <= c1[1]; ++iy)
-            for (int ix = c0[0]; ix <= c1[0]; ++ix) {
-                const unsigned long long key = cell_key(g, ix, iy, iz);
-                for (int e = lower_bound_u64(keys, nEntries, key); e < nEntries && keys[e] == key; ++e) {
-                    const int eJ = vals[e];
-                    if (eJ <= eI) continue;
-                    const Box jb = eboxes[eJ];
-                    int t0[3], t1[3];
-                    cell_range(g, jb, t0, t1);
-                    if (max(t0[0], c0[0]) != ix || max(t0[1], c0[1]) != iy || max(t0[2], c0[2]) != iz) continue;
-                    const int b[2] = { s.SE[2 * eJ], s.SE[2 * eJ + 1] };
-                    int lo[3], hi[3];
-                    prim_range(vmin, vmax, b, 2, lo, hi);
-                    if (!ranges_overlap(qlo, qhi, lo, hi)) continue;
-                    // swept-AABB test of queryEdgeForEdgesWithBBoxCheck (SpatialHash.hpp:819-828); the boxes hold {x, x+alpha p}
-                    bool sep = false;
+    warp_scan_candidates(g, eg, qb, lane, [&](int eJ, const Box& jb) {
+        if (eJ <= eI) return;
+        const int b[2] = { s.SE[2 * eJ], s.SE[2 * eJ + 1] };
+        int lo[3], hi[3];
+        prim_range(vmin, vmax, b, 2, lo, hi);
+        if (!ranges_overlap(qlo, qhi, lo, hi)) return;
+        // swept-AABB test of queryEdgeForEdgesWithBBoxCheck (SpatialHash.hpp:819-828); the boxes hold {x, x+alpha p}
+        bool sep = false;
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) sep = sep || (jb.lo[c] - eb.hi[c] > 0.0) || (eb.lo[c] - jb.hi[c] > 0.0);
-                    if (sep) continue;
-                    if (a[0] == b[0] || a[0] == b[1] || a[1] == b[0] || a[1] == b[1]) continue;
-                    if ((ecod < 3 && cod_v(s, b[0]) < 3) || (edbc && dbc_v(s, b[0]) && dbc_v(s, b[1]))) continue;
-                    push_cand(out, make_int2(eI, eJ));
-                }
-            }
+        for (int c = 0; c < 3; ++c) sep = sep || (jb.lo[c] - eb.hi[c] > 0.0) || (eb.lo[c] - jb.hi[c] > 0.0);
+        if (sep) return;
+        if (a[0] == b[0] || a[0] == b[1] || a[1] == b[0] || a[1] == b[1]) return;
+        if ((ecod < 3 && cod_v(s, b[0]) < 3) || (edbc && dbc_v(s, b[0]) && dbc_v(s, b[1]))) return;
+        push_cand(out, make_int2(eI, eJ));
+    });
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -403,9 +382,28 @@ DEV bool sum_le_1(unsigned long long an, int ak, unsigned long long bn, int bk)
 
 constexpr unsigned F_ZERO = 1u << 24; // zero_in flag stored in DBox::kk
 
-// result codes of the root finder
-template <bool VF>
-__device__ bool ti_root_finder(const TiPair& P, const double* tol, double co_tol, double max_t, const double* err, double ms, int max_itr, DBox* bufA,
+// group helpers: W = 32 (one warp per pair) or W = 1 (one thread per pair, no cross-lane traffic)
+template <int W> DEV void group_min_key(Key3& k, unsigned& pay, double& aux) { if (W == 32) warp_min_key(k, pay, aux); }
+template <int W> DEV int group_count(bool b) { return (W == 32) ? __popc(__ballot_sync(0xffffffffu, b)) : (b ? 1 : 0); }
+template <int W> DEV bool group_any(bool b) { return (W == 32) ? (__any_sync(0xffffffffu, b) != 0) : b; }
+template <int W> DEV void group_sync() { if (W == 32) __syncwarp(); }
+template <int W> DEV void group_scan(int v, int lane, int& incl, int& total)
+{
+    incl = v;
+    total = v;
+    if (W == 32) {
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        total = __shfl_sync(0xffffffffu, incl, 31);
+    }
+}
+
+// result codes of the root finder: 0 no collision, 1 collision (toi set), 2 deferred (W = 1 only: level buffer too small)
+template <bool VF, int W>
+__device__ int ti_root_finder(const TiPair& P, const double* tol, double co_tol, double max_t, const double* err, double ms, int max_itr, DBox* bufA,
     DBox* bufB, int cap, int lane, double& toi, double& out_tol, int* __restrict__ warn)
 {
     const bool check_t = (max_t != 1.0);
@@ -413,7 +411,7 @@ __device__ bool ti_root_finder(const TiPair& P, const double* tol, double co_tol
     DBox* cur = bufA;
     DBox* nxt = bufB;
     if (lane == 0) cur[0] = DBox{ 0ull, 0ull, 0ull, 0u, 0u };
-    __syncwarp();
+    group_sync<W>();
     int n = 1;
     double toi_skip = INF;
     bool use_skip = false;
@@ -427,7 +425,7 @@ __device__ bool ti_root_finder(const TiPair& P, const double* tol, double co_tol
         unsigned p1 = 0, p2 = 0; // payload bit0: flagged (K1) / cond1 (K2)
         double a1 = 0.0, a2 = 0.0;
         int visited = 0;
-        for (int base = 0; base < n; base += 32) {
+        for (int base = 0; base < n; base += W) {
             const int i = base + lane;
             Key3 mk1 = { INF, INF, INF }, mk2 = { INF, INF, INF };
             unsigned mp1 = 0, mp2 = 0;
@@ -458,13 +456,13 @@ __device__ bool ti_root_finder(const TiPair& P, const double* tol, double co_tol
                 }
                 cur[i].kk = (b.kk & 0x00ffffffu) | flags;
             }
-            visited += __popc(__ballot_sync(0xffffffffu, vis));
-            warp_min_key(mk1, mp1, ma1);
-            warp_min_key(mk2, mp2, ma2);
+            visited += group_count<W>(vis);
+            group_min_key<W>(mk1, mp1, ma1);
+            group_min_key<W>(mk2, mp2, ma2);
             if (key_less(mk1, k1)) { k1 = mk1; p1 = mp1; a1 = ma1; }
             if (key_less(mk2, k2)) { k2 = mk2; p2 = mp2; a2 = ma2; }
         }
-        __syncwarp();
+        group_sync<W>();
         const bool any_zero = k1.t != INF;
         if (!any_zero) { // nothing at this level contains the origin: the search space is exhausted
             n = 0;
@@ -472,13 +470,13 @@ __device__ bool ti_root_finder(const TiPair& P, const double* tol, double co_tol
         }
         if (p1 & 1u) { // the first box containing the origin is terminal: conditions 1/2/3 of the library
             toi = k1.t;
-            return true;
+            return 1;
         }
         const bool has_k2 = k2.t != INF;
         if (has_k2 && (p2 & 1u)) { // a later box already below the width tolerances (condition 1)
             // boxes between K1 and K2 do not matter: the library returns here
             toi = k2.t;
-            return true;
+            return 1;
         }
         if (max_itr > 0) {
             temp_toi = k1.t;
@@ -488,7 +486,7 @@ __device__ bool ti_root_finder(const TiPair& P, const double* tol, double co_tol
                 if (lane == 0) atomicAdd(warn, 1);
                 toi = temp_toi;
                 out_tol = temp_out_tol;
-                return true;
+                return 1;
             }
         }
         if (has_k2) {
@@ -498,7 +496,7 @@ __device__ bool ti_root_finder(const TiPair& P, const double* tol, double co_tol
         // ---- pass 2: split every box that contains the origin and precedes K2 ------------------------------------------
         int nn = 0;
         bool over = false;
-        for (int base = 0; base < n; base += 32) {
+        for (int base = 0; base < n; base += W) {
             const int i = base + lane;
             int nchild = 0;
             DBox c0, c1;
@@ -543,14 +541,9 @@ __device__ bool ti_root_finder(const TiPair& P, const double* tol, double co_tol
                     }
                 }
             }
-            // warp exclusive scan of nchild
-            int incl = nchild;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int y = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += y;
-            }
-            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            // group exclusive scan of nchild
+            int incl, total;
+            group_scan<W>(nchild, lane, incl, total);
             const int off = nn + incl - nchild;
             if (nn + total > cap) over = true;
             else {
@@ -558,29 +551,30 @@ __device__ bool ti_root_finder(const TiPair& P, const double* tol, double co_tol
                 if (nchild > 1) nxt[off + 1] = c1;
             }
             nn += total;
-            if (__any_sync(0xffffffffu, over)) { over = true; break; }
+            if (group_any<W>(over)) { over = true; break; }
         }
-        if (__any_sync(0xffffffffu, over)) {
+        if (group_any<W>(over)) {
+            if (W == 1) return 2; // the thread-level pass hands the pair to the warp-level pass
             // level buffer / bisection depth exhausted: return the conservative per-level estimate (earliest box containing the origin)
             if (lane == 0) atomicAdd(warn, 1);
             toi = temp_toi;
             out_tol = temp_out_tol;
-            return true;
+            return 1;
         }
-        __syncwarp();
+        group_sync<W>();
         DBox* t = cur; cur = nxt; nxt = t;
         n = nn;
     }
     if (use_skip) {
         toi = toi_skip;
-        return true;
+        return 1;
     }
-    return false;
+    return 0;
 }
 
-// vertexFaceCCD_double / edgeEdgeCCD_double including the no_zero_toi refinement loop
-template <bool VF>
-__device__ bool ti_ccd(const TiPair& P, const double* err, double ms, double tolerance, double t_max, int max_itr, DBox* bufA, DBox* bufB, int cap, int lane,
+// vertexFaceCCD_double / edgeEdgeCCD_double including the no_zero_toi refinement loop; returns 0 / 1 / 2 (deferred)
+template <bool VF, int W>
+__device__ int ti_ccd(const TiPair& P, const double* err, double ms, double tolerance, double t_max, int max_itr, DBox* bufA, DBox* bufB, int cap, int lane,
     double& toi, int* __restrict__ warn)
 {
     double tolerance_in = tolerance, ms_in = ms, out_tol = tolerance;
@@ -589,7 +583,9 @@ __device__ bool ti_ccd(const TiPair& P, const double* err, double ms, double tol
     do {
         double tol[3];
         width_tolerances<VF>(P, tolerance_in, tol);
-        tmp = ti_root_finder<VF>(P, tol, tolerance_in, t_max, err, ms_in, max_itr, bufA, bufB, cap, lane, toi, out_tol, warn);
+        const int rc = ti_root_finder<VF, W>(P, tol, tolerance_in, t_max, err, ms_in, max_itr, bufA, bufB, cap, lane, toi, out_tol, warn);
+        if (rc == 2) return 2;
+        tmp = rc == 1;
         if (iter == 0) is_impacting = tmp;
         else toi = tmp ? toi : t_max;
         if (tmp && toi == 0.0) {
@@ -599,7 +595,56 @@ __device__ bool ti_ccd(const TiPair& P, const double* err, double ms, double tol
         }
         ++iter;
     } while (iter < 0x7fffffffu && tmp && toi == 0.0);
-    return is_impacting;
+    return is_impacting ? 1 : 0;
+}
+
+// one candidate end to end (SelfCollisionHandler.cpp:740-790): 0 / 1 (toi set) / 2 deferred
+template <int W>
+__device__ int pair_ccd(bool vf, const TiPair& P, const NarrowArgs& a, DBox* bufA, DBox* bufB, int cap, int lane, double& toi, int* __restrict__ warn)
+{
+    const double d = pair_distance_sqrt(vf, P);
+    const double ms = fmin(0.2 * d, 1e-6);
+    int hit = vf ? ti_ccd<true, W>(P, a.err_vf, ms, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn)
+                 : ti_ccd<false, W>(P, a.err_ee, ms, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn);
+    if (hit == 2) return 2;
+    if (hit && toi < 1e-6) { // :759-781
+        hit = vf ? ti_ccd<true, W>(P, a.err_vf, 0.0, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn)
+                 : ti_ccd<false, W>(P, a.err_ee, 0.0, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn);
+        if (hit == 2) return 2;
+        if (hit) toi *= 0.8;
+    }
+    return hit;
+}
+
+// stage 1.5: one THREAD per surviving pair with a small private level buffer; pairs whose search outgrows it are deferred
+constexpr int kThreadCap = 24;
+__global__ void __launch_bounds__(128) k_ti_stage15(NarrowArgs a, const unsigned* __restrict__ survivors, const unsigned* __restrict__ nSurvPtr,
+    unsigned* __restrict__ deferred, unsigned* __restrict__ nDeferred, unsigned long long* __restrict__ min_ord, int* __restrict__ warn)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned nSurv = *nSurvPtr;
+    bool defer = false;
+    unsigned idx = 0;
+    if (i < nSurv) {
+        idx = survivors[i];
+        bool vf;
+        int v[4];
+        TiPair P;
+        load_pair(a.s, a.dir, a.cand[idx], vf, v, P);
+        DBox bufA[kThreadCap], bufB[kThreadCap];
+        double toi;
+        const int hit = pair_ccd<1>(vf, P, a, bufA, bufB, kThreadCap, 0, toi, warn);
+        if (hit == 2) defer = true;
+        else if (hit == 1) atomicMin(min_ord, dbl_to_ord(toi));
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, defer);
+    if (m) {
+        const int lane = threadIdx.x & 31;
+        unsigned base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(nDeferred, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (defer) deferred[base + __popc(m & ((1u << lane) - 1))] = idx;
+    }
 }
 
 __global__ void __launch_bounds__(128) k_ti_stage2(NarrowArgs a, const unsigned* __restrict__ survivors, const unsigned* __restrict__ nSurvPtr, unsigned* __restrict__ work,
@@ -619,16 +664,8 @@ __global__ void __launch_bounds__(128) k_ti_stage2(NarrowArgs a, const unsigned*
         int v[4];
         TiPair P;
         load_pair(a.s, a.dir, a.cand[survivors[w]], vf, v, P);
-        const double d = pair_distance_sqrt(vf, P);
-        const double ms = fmin(0.2 * d, 1e-6);
         double toi;
-        bool hit = vf ? ti_ccd<true>(P, a.err_vf, ms, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn)
-                      : ti_ccd<false>(P, a.err_ee, ms, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn);
-        if (hit && toi < 1e-6) { // :759-781
-            hit = vf ? ti_ccd<true>(P, a.err_vf, 0.0, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn)
-                     : ti_ccd<false>(P, a.err_ee, 0.0, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn);
-            if (hit) toi *= 0.8;
-        }
+        const int hit = pair_ccd<32>(vf, P, a, bufA, bufB, cap, lane, toi, warn);
         if (hit && lane == 0) atomicMin(min_ord, dbl_to_ord(toi));
         __syncwarp();
     }
@@ -640,7 +677,7 @@ __global__ void k_ccd_init(unsigned long long* min_ord, double alpha, unsigned* 
         *min_ord = dbl_to_ord(alpha);
         *nSurv = 0;
         *work = 0;
-        flags[0] = flags[1] = flags[2] = 0;
+        flags[0] = flags[1] = flags[2] = 0; // zero distance, warnings, deferred count
     }
 }
 
@@ -669,7 +706,7 @@ int ccd_alloc(ipcgpu_ctx* ctx)
 {
     CcdWork& w = ctx->ccd;
     const size_t warps = (size_t)kStage2Ctas * kStage2WarpsPerCta;
-    bool ok = w.vmin.reserve((size_t)3 * ctx->nV) && w.vmax.reserve((size_t)3 * ctx->nV) && w.cand.reserve(ctx->ccd_capacity) && w.surv.reserve(ctx->ccd_capacity)
+    bool ok = w.vmin.reserve((size_t)3 * ctx->nV) && w.vmax.reserve((size_t)3 * ctx->nV) && w.cand.reserve(ctx->ccd_capacity) && w.surv.reserve(ctx->ccd_capacity) && w.surv2.reserve(ctx->ccd_capacity)
         && w.scratch.reserve(warps * 2 * kLevelCap * sizeof(DBox)) && w.counters.reserve(16) && w.ncand.reserve(2) && w.bounds.reserve(8);
     if (!ok) {
         ctx->err = "CCD workspace allocation failed";
@@ -699,10 +736,13 @@ int ccd_narrow(ipcgpu_ctx* ctx, const int2* cand, unsigned long long nCand, doub
     k_ccd_init<<<1, 32, 0, st>>>(ctx->min_ord.p, *alpha_inout, nSurv, work, flags);
     if (nCand > 0) {
         k_ti_stage1<<<nblk((long long)nCand, 128), 128, 0, st>>>(a, w.surv.p, nSurv, flags);
-        k_ti_stage2<<<kStage2Ctas, 32 * kStage2WarpsPerCta, 0, st>>>(a, w.surv.p, nSurv, work, reinterpret_cast<DBox*>(w.scratch.p), kLevelCap, ctx->min_ord.p, flags + 1);
+        // the survivor count lives on the device; the thread-level pass is launched over the candidate count (extra threads exit)
+        unsigned* nDef = reinterpret_cast<unsigned*>(flags + 2);
+        k_ti_stage15<<<nblk((long long)nCand, 128), 128, 0, st>>>(a, w.surv.p, nSurv, w.surv2.p, nDef, ctx->min_ord.p, flags + 1);
+        k_ti_stage2<<<kStage2Ctas, 32 * kStage2WarpsPerCta, 0, st>>>(a, w.surv2.p, nDef, work, reinterpret_cast<DBox*>(w.scratch.p), kLevelCap, ctx->min_ord.p, flags + 1);
     }
     ctx->prof_end(pe);
-    ctx->launches += 3;
+    ctx->launches += 4;
     CKD(cudaGetLastError());
     if (ctx->nranks > 1) {
         // min over ranks of the step (and max of the zero-distance flag) is done by the caller through NCCL (api.cu)
@@ -716,6 +756,7 @@ int ccd_narrow(ipcgpu_ctx* ctx, const int2* cand, unsigned long long nCand, doub
     std::memcpy(&m, h, sizeof(double));
     w.last_survivors = (unsigned)hi[0];
     w.last_warnings = hi[3];
+    w.last_deferred = (unsigned)hi[4];
     w.last_candidates = nCand;
     if (hi[2]) *alpha_inout = 0.0; // zero initial distance
     else *alpha_inout = m;
@@ -807,10 +848,11 @@ int ccd_full(ipcgpu_ctx* ctx, double tol, const double* err_vf, const double* er
     // multi-GPU: every rank sweeps a contiguous share of the query primitives (the reference's own loop decomposition, :1385, :1498)
     const int v0 = (int)((long long)s.nSV * ctx->rank / ctx->nranks), v1 = (int)((long long)s.nSV * (ctx->rank + 1) / ctx->nranks);
     const int e0 = (int)((long long)s.nSE * ctx->rank / ctx->nranks), e1 = (int)((long long)s.nSE * (ctx->rank + 1) / ctx->nranks);
+    const SortedGrid tg{ cw.tkeys.p, cw.tvals.p, cw.tsbox.p, s.nSF }, eg{ cw.ekeys.p, cw.evals.p, cw.esbox.p, s.nSE };
     if (v1 > v0 && s.nSF > 0)
-        k_ccd_query_pt<<<nblk(v1 - v0, 128), 128, 0, st>>>(s, cw.grid.p, cw.vbox.p, cw.tbox.p, cw.tkeys.p, cw.tvals.p, 8 * s.nSF, w.vmin.p, w.vmax.p, radius, v0, v1, out);
+        k_ccd_query_pt<<<nblk((long long)(v1 - v0) * 32, 128), 128, 0, st>>>(s, cw.grid.p, cw.vbox.p, tg, w.vmin.p, w.vmax.p, radius, v0, v1, out);
     if (e1 > e0 && s.nSE > 1)
-        k_ccd_query_ee<<<nblk(e1 - e0, 128), 128, 0, st>>>(s, cw.grid.p, cw.ebox.p, cw.ekeys.p, cw.evals.p, 8 * s.nSE, w.vmin.p, w.vmax.p, radius, e0, e1, out);
+        k_ccd_query_ee<<<nblk((long long)(e1 - e0) * 32, 128), 128, 0, st>>>(s, cw.grid.p, cw.ebox.p, eg, w.vmin.p, w.vmax.p, radius, e0, e1, out);
     ctx->launches += 2;
     unsigned long long* hn = reinterpret_cast<unsigned long long*>(ctx->h_scalar);
     int* ho = reinterpret_cast<int*>(ctx->h_scalar + 2);

@@ -105,7 +105,7 @@ __global__ void k_grid_params(const unsigned long long* __restrict__ bounds, dou
     g->nz = max(1, (int)floor((hi[2] - lo[2]) * g->inv_h) + 1);
 }
 
-// 8 slots per primitive; unused slots get the all-ones key so that they sort to the end
+// one entry per primitive: the cell of the box's lower corner
 __global__ void __launch_bounds__(256) k_emit(int n, const Box* __restrict__ boxes, const Grid* __restrict__ gp, unsigned long long* __restrict__ keys,
     int* __restrict__ vals)
 {
@@ -114,18 +114,13 @@ __global__ void __launch_bounds__(256) k_emit(int n, const Box* __restrict__ box
     const Grid g = *gp;
     int c0[3], c1[3];
     cell_range(g, boxes[i], c0, c1);
-    int k = 0;
-    for (int iz = c0[2]; iz <= c1[2] && iz <= c0[2] + 1; ++iz)
-        for (int iy = c0[1]; iy <= c1[1] && iy <= c0[1] + 1; ++iy)
-            for (int ix = c0[0]; ix <= c1[0] && ix <= c0[0] + 1; ++ix) {
-                keys[(size_t)8 * i + k] = cell_key(g, ix, iy, iz);
-                vals[(size_t)8 * i + k] = i;
-                ++k;
-            }
-    for (; k < 8; ++k) {
-        keys[(size_t)8 * i + k] = ~0ull;
-        vals[(size_t)8 * i + k] = -1;
-    }
+    keys[i] = cell_key(g, c0[0], c0[1], c0[2]);
+    vals[i] = i;
+}
+__global__ void __launch_bounds__(256) k_gather_boxes(int n, const Box* __restrict__ boxes, const int* __restrict__ ids, Box* __restrict__ sorted)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) sorted[i] = boxes[ids[i]];
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -159,11 +154,11 @@ DEV double box_gap2(const Box& a, const Box& b)
 DEV bool is_dbc_v(const SurfArgs& s, int v) { return s.dbc && s.dbc[v] != 0; }
 DEV int codim_v(const SurfArgs& s, int v) { return s.vCoDim ? s.vCoDim[v] : 3; }
 
-// one thread per surface vertex  (:2168-2260)
-__global__ void __launch_bounds__(128) k_query_pt(SurfArgs s, const Grid* __restrict__ gp, const Box* __restrict__ tri_boxes,
-    const unsigned long long* __restrict__ keys, const int* __restrict__ vals, int nEntries, double dHat, double radius, int wantCand, CsOut out)
+// one WARP per surface vertex  (:2168-2260)
+__global__ void __launch_bounds__(128) k_query_pt(SurfArgs s, const Grid* __restrict__ gp, SortedGrid tg, double dHat, double radius, int wantCand, CsOut out)
 {
-    const int svI = blockIdx.x * blockDim.x + threadIdx.x;
+    const int svI = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (svI >= s.nSV) return;
     const Grid g = *gp;
     const int vI = s.SVI[svI];
@@ -171,125 +166,102 @@ __global__ void __launch_bounds__(128) k_query_pt(SurfArgs s, const Grid* __rest
     Box qb;
     qb.lo[0] = p.x - radius; qb.lo[1] = p.y - radius; qb.lo[2] = p.z - radius;
     qb.hi[0] = p.x + radius; qb.hi[1] = p.y + radius; qb.hi[2] = p.z + radius;
-    int c0[3], c1[3];
-    cell_range(g, qb, c0, c1);
     const int vcod = codim_v(s, vI);
     const bool vdbc = is_dbc_v(s, vI);
     const double cull = dHat * (1.0 + 1e-9) + 1e-300;
-    for (int iz = c0[2]; iz <= c1[2]; ++iz)
-        for (int iy = c0[1]; iy <= c1[1]; ++iy)
-            for (int ix = c0[0]; ix <= c1[0]; ++ix) {
-                const unsigned long long key = cell_key(g, ix, iy, iz);
-                for (int e = lower_bound_u64(keys, nEntries, key); e < nEntries && keys[e] == key; ++e) {
-                    const int sfI = vals[e];
-                    const Box tb = tri_boxes[sfI];
-                    int t0[3], t1[3];
-                    cell_range(g, tb, t0, t1);
-                    if (max(t0[0], c0[0]) != ix || max(t0[1], c0[1]) != iy || max(t0[2], c0[2]) != iz) continue; // not the canonical cell
-                    Box pb;
-                    pb.lo[0] = pb.hi[0] = p.x; pb.lo[1] = pb.hi[1] = p.y; pb.lo[2] = pb.hi[2] = p.z;
-                    if (box_gap2(pb, tb) > cull) continue;
-                    const int a = s.SF[sfI], b = s.SF[(size_t)s.nSF + sfI], c = s.SF[(size_t)2 * s.nSF + sfI];
-                    if (vI == a || vI == b || vI == c) continue;
-                    if ((vcod < 3 && codim_v(s, a) < 3) || (vdbc && is_dbc_v(s, a) && is_dbc_v(s, b) && is_dbc_v(s, c))) continue;
-                    const V3 ta = load_vertex(s.V, s.nV, a), tb_ = load_vertex(s.V, s.nV, b), tc = load_vertex(s.V, s.nV, c);
-                    const int ty = dType_PT(p, ta, tb_, tc);
-                    double d;
-                    int4 q;
-                    switch (ty) {
-                    case 0: d = d_PP(p, ta); q = make_int4(-vI - 1, a, -1, -1); break;
-                    case 1: d = d_PP(p, tb_); q = make_int4(-vI - 1, b, -1, -1); break;
-                    case 2: d = d_PP(p, tc); q = make_int4(-vI - 1, c, -1, -1); break;
-                    case 3: d = d_PE(p, ta, tb_); q = make_int4(-vI - 1, a, b, -1); break;
-                    case 4: d = d_PE(p, tb_, tc); q = make_int4(-vI - 1, b, c, -1); break;
-                    case 5: d = d_PE(p, tc, ta); q = make_int4(-vI - 1, c, a, -1); break;
-                    default: d = d_PT(p, ta, tb_, tc); q = make_int4(-vI - 1, a, b, c);
-                    }
-                    if (d < dHat) {
-                        if (q.w >= 0) push4(out.act, out.nAct, out.capAct, out.overflow, q);
-                        else push4(out.dup, out.nDup, out.capDup, out.overflow, q);
-                        if (wantCand) {
-                            int i = atomicAdd(out.nCand, 1);
-                            if ((unsigned)i < (unsigned)out.capCand) out.cand[i] = make_int2(-svI - 1, sfI);
-                            else atomicExch(out.overflow, 1);
-                        }
-                    }
-                }
+    warp_scan_candidates(g, tg, qb, lane, [&](int sfI, const Box& tb) {
+        Box pb;
+        pb.lo[0] = pb.hi[0] = p.x; pb.lo[1] = pb.hi[1] = p.y; pb.lo[2] = pb.hi[2] = p.z;
+        if (box_gap2(pb, tb) > cull) return;
+        const int a = s.SF[sfI], b = s.SF[(size_t)s.nSF + sfI], c = s.SF[(size_t)2 * s.nSF + sfI];
+        if (vI == a || vI == b || vI == c) return;
+        if ((vcod < 3 && codim_v(s, a) < 3) || (vdbc && is_dbc_v(s, a) && is_dbc_v(s, b) && is_dbc_v(s, c))) return;
+        const V3 ta = load_vertex(s.V, s.nV, a), tb_ = load_vertex(s.V, s.nV, b), tc = load_vertex(s.V, s.nV, c);
+        const int ty = dType_PT(p, ta, tb_, tc);
+        double d;
+        int4 q;
+        switch (ty) {
+        case 0: d = d_PP(p, ta); q = make_int4(-vI - 1, a, -1, -1); break;
+        case 1: d = d_PP(p, tb_); q = make_int4(-vI - 1, b, -1, -1); break;
+        case 2: d = d_PP(p, tc); q = make_int4(-vI - 1, c, -1, -1); break;
+        case 3: d = d_PE(p, ta, tb_); q = make_int4(-vI - 1, a, b, -1); break;
+        case 4: d = d_PE(p, tb_, tc); q = make_int4(-vI - 1, b, c, -1); break;
+        case 5: d = d_PE(p, tc, ta); q = make_int4(-vI - 1, c, a, -1); break;
+        default: d = d_PT(p, ta, tb_, tc); q = make_int4(-vI - 1, a, b, c);
+        }
+        if (d < dHat) {
+            if (q.w >= 0) push4(out.act, out.nAct, out.capAct, out.overflow, q);
+            else push4(out.dup, out.nDup, out.capDup, out.overflow, q);
+            if (wantCand) {
+                int i = atomicAdd(out.nCand, 1);
+                if ((unsigned)i < (unsigned)out.capCand) out.cand[i] = make_int2(-svI - 1, sfI);
+                else atomicExch(out.overflow, 1);
             }
+        }
+    });
 }
 
-// one thread per surface edge eI; partners eJ > eI  (:2271-2407)
-__global__ void __launch_bounds__(128) k_query_ee(SurfArgs s, const Grid* __restrict__ gp, const Box* __restrict__ edge_boxes,
-    const unsigned long long* __restrict__ keys, const int* __restrict__ vals, int nEntries, double dHat, double radius, int wantCand, CsOut out)
+// one WARP per surface edge eI; partners eJ > eI  (:2271-2407)
+__global__ void __launch_bounds__(128) k_query_ee(SurfArgs s, const Grid* __restrict__ gp, const Box* __restrict__ edge_boxes, SortedGrid eg, double dHat, double radius,
+    int wantCand, CsOut out)
 {
-    const int eI = blockIdx.x * blockDim.x + threadIdx.x;
+    const int eI = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (eI >= s.nSE) return;
     const Grid g = *gp;
     const int a0 = s.SE[2 * eI], a1 = s.SE[2 * eI + 1];
     const Box eb = edge_boxes[eI];
     Box qb = eb;
     for (int k = 0; k < 3; ++k) { qb.lo[k] -= radius; qb.hi[k] += radius; }
-    int c0[3], c1[3];
-    cell_range(g, qb, c0, c1);
     const V3 xa0 = load_vertex(s.V, s.nV, a0), xa1 = load_vertex(s.V, s.nV, a1);
     const int ecod = codim_v(s, a0);
     const bool edbc = is_dbc_v(s, a0) && is_dbc_v(s, a1);
     const double cull = dHat * (1.0 + 1e-9) + 1e-300;
-    for (int iz = c0[2]; iz <= c1[2]; ++iz)
-        for (int iy = c0[1]; iy <= c1[1]; ++iy)
-            for (int ix = c0[0]; ix <= c1[0]; ++ix) {
-                const unsigned long long key = cell_key(g, ix, iy, iz);
-                for (int e = lower_bound_u64(keys, nEntries, key); e < nEntries && keys[e] == key; ++e) {
-                    const int eJ = vals[e];
-                    if (eJ <= eI) continue;
-                    const Box jb = edge_boxes[eJ];
-                    int t0[3], t1[3];
-                    cell_range(g, jb, t0, t1);
-                    if (max(t0[0], c0[0]) != ix || max(t0[1], c0[1]) != iy || max(t0[2], c0[2]) != iz) continue;
-                    if (box_gap2(eb, jb) > cull) continue;
-                    const int b0 = s.SE[2 * eJ], b1 = s.SE[2 * eJ + 1];
-                    if (a0 == b0 || a0 == b1 || a1 == b0 || a1 == b1) continue;
-                    if ((ecod < 3 && codim_v(s, b0) < 3) || (edbc && is_dbc_v(s, b0) && is_dbc_v(s, b1))) continue;
-                    const V3 xb0 = load_vertex(s.V, s.nV, b0), xb1 = load_vertex(s.V, s.nV, b1);
-                    const int ty = dType_EE(xa0, xa1, xb0, xb1);
-                    const double cr = norm2(cross(xa1 - xa0, xb1 - xb0));
-                    const int add_e = (cr < eps_x_rest(s.Vrest, s.nV, a0, a1, b0, b1)) ? (-eJ - 2) : -1;
-                    double d;
-                    int4 q;
-                    switch (ty) {
-                    case 0: d = d_PP(xa0, xb0); q = make_int4(-a0 - 1, b0, -1, add_e); break;
-                    case 1: d = d_PP(xa0, xb1); q = make_int4(-a0 - 1, b1, -1, add_e); break;
-                    case 2: d = d_PE(xa0, xb0, xb1); q = make_int4(-a0 - 1, b0, b1, add_e); break;
-                    case 3: d = d_PP(xa1, xb0); q = make_int4(-a1 - 1, b0, -1, add_e); break;
-                    case 4: d = d_PP(xa1, xb1); q = make_int4(-a1 - 1, b1, -1, add_e); break;
-                    case 5: d = d_PE(xa1, xb0, xb1); q = make_int4(-a1 - 1, b0, b1, add_e); break;
-                    case 6: d = d_PE(xb0, xa0, xa1); q = make_int4(-b0 - 1, a0, a1, add_e); break;
-                    case 7: d = d_PE(xb1, xa0, xa1); q = make_int4(-b1 - 1, a0, a1, add_e); break;
-                    default: d = d_EE(xa0, xa1, xb0, xb1); q = make_int4(a0, a1, b0, b1);
-                    }
-                    if (d < dHat) {
-                        if (ty == 8) {
-                            if (add_e <= -2) { // nearly parallel EE: mollified set, keeps its own stencil (:2464-2467)
-                                int i = atomicAdd(out.nPara, 1);
-                                if ((unsigned)i < (unsigned)out.capPara) { out.para[i] = q; out.para_e[i] = make_int2(-1, -1); }
-                                else atomicExch(out.overflow, 1);
-                            }
-                            else push4(out.act, out.nAct, out.capAct, out.overflow, q);
-                        }
-                        else if (add_e == -1) push4(out.dup, out.nDup, out.capDup, out.overflow, q);
-                        else { // PP / PE that came from a nearly parallel edge pair (:2459-2462)
-                            int i = atomicAdd(out.nPara, 1);
-                            if ((unsigned)i < (unsigned)out.capPara) { out.para[i] = make_int4(q.x, q.y, q.z, -1); out.para_e[i] = make_int2(eI, eJ); }
-                            else atomicExch(out.overflow, 1);
-                        }
-                        if (wantCand) {
-                            int i = atomicAdd(out.nCand, 1);
-                            if ((unsigned)i < (unsigned)out.capCand) out.cand[i] = make_int2(eI, eJ);
-                            else atomicExch(out.overflow, 1);
-                        }
-                    }
+    warp_scan_candidates(g, eg, qb, lane, [&](int eJ, const Box& jb) {
+        if (eJ <= eI) return;
+        if (box_gap2(eb, jb) > cull) return;
+        const int b0 = s.SE[2 * eJ], b1 = s.SE[2 * eJ + 1];
+        if (a0 == b0 || a0 == b1 || a1 == b0 || a1 == b1) return;
+        if ((ecod < 3 && codim_v(s, b0) < 3) || (edbc && is_dbc_v(s, b0) && is_dbc_v(s, b1))) return;
+        const V3 xb0 = load_vertex(s.V, s.nV, b0), xb1 = load_vertex(s.V, s.nV, b1);
+        const int ty = dType_EE(xa0, xa1, xb0, xb1);
+        const double cr = norm2(cross(xa1 - xa0, xb1 - xb0));
+        const int add_e = (cr < eps_x_rest(s.Vrest, s.nV, a0, a1, b0, b1)) ? (-eJ - 2) : -1;
+        double d;
+        int4 q;
+        switch (ty) {
+        case 0: d = d_PP(xa0, xb0); q = make_int4(-a0 - 1, b0, -1, add_e); break;
+        case 1: d = d_PP(xa0, xb1); q = make_int4(-a0 - 1, b1, -1, add_e); break;
+        case 2: d = d_PE(xa0, xb0, xb1); q = make_int4(-a0 - 1, b0, b1, add_e); break;
+        case 3: d = d_PP(xa1, xb0); q = make_int4(-a1 - 1, b0, -1, add_e); break;
+        case 4: d = d_PP(xa1, xb1); q = make_int4(-a1 - 1, b1, -1, add_e); break;
+        case 5: d = d_PE(xa1, xb0, xb1); q = make_int4(-a1 - 1, b0, b1, add_e); break;
+        case 6: d = d_PE(xb0, xa0, xa1); q = make_int4(-b0 - 1, a0, a1, add_e); break;
+        case 7: d = d_PE(xb1, xa0, xa1); q = make_int4(-b1 - 1, a0, a1, add_e); break;
+        default: d = d_EE(xa0, xa1, xb0, xb1); q = make_int4(a0, a1, b0, b1);
+        }
+        if (d < dHat) {
+            if (ty == 8) {
+                if (add_e <= -2) { // nearly parallel EE: mollified set, keeps its own stencil (:2464-2467)
+                    int i = atomicAdd(out.nPara, 1);
+                    if ((unsigned)i < (unsigned)out.capPara) { out.para[i] = q; out.para_e[i] = make_int2(-1, -1); }
+                    else atomicExch(out.overflow, 1);
                 }
+                else push4(out.act, out.nAct, out.capAct, out.overflow, q);
             }
+            else if (add_e == -1) push4(out.dup, out.nDup, out.capDup, out.overflow, q);
+            else { // PP / PE that came from a nearly parallel edge pair (:2459-2462)
+                int i = atomicAdd(out.nPara, 1);
+                if ((unsigned)i < (unsigned)out.capPara) { out.para[i] = make_int4(q.x, q.y, q.z, -1); out.para_e[i] = make_int2(eI, eJ); }
+                else atomicExch(out.overflow, 1);
+            }
+            if (wantCand) {
+                int i = atomicAdd(out.nCand, 1);
+                if ((unsigned)i < (unsigned)out.capCand) out.cand[i] = make_int2(eI, eJ);
+                else atomicExch(out.overflow, 1);
+            }
+        }
+    });
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -354,7 +326,7 @@ using namespace ipcgpu;
         }                                                              \
     } while (0)
 
-static inline int nblk(int n, int b) { return (n + b - 1) / b; }
+static inline int nblk(long long n, int b) { return (int)((n + b - 1) / b); }
 
 // stable radix sort of (keys, idx) pairs, result back in (keys, idx)
 static int sort_pass(ipcgpu_ctx* ctx, int n)
@@ -417,10 +389,10 @@ int contact_alloc(ipcgpu_ctx* ctx)
 {
     ContactWork& w = ctx->cw;
     const int nSE = ctx->nSE, nSF = ctx->nSF, nSV = ctx->nSV;
-    const size_t nEnt = (size_t)8 * std::max(std::max(nSE, nSF), 1);
+    const size_t nEnt = (size_t)std::max(std::max(nSE, nSF), 1);
     const int cap = std::max(ctx->pair_capacity, 1024);
     bool ok = w.vbox.reserve(std::max(nSV, 1)) && w.ebox.reserve(std::max(nSE, 1)) && w.tbox.reserve(std::max(nSF, 1)) && w.bounds.reserve(8) && w.grid.reserve(2)
-        && w.tkeys.reserve(nEnt) && w.tvals.reserve(nEnt) && w.ekeys.reserve(nEnt) && w.evals.reserve(nEnt) && w.key_tmp.reserve(nEnt) && w.val_tmp.reserve(nEnt)
+        && w.tsbox.reserve(std::max(nSF, 1)) && w.esbox.reserve(std::max(nSE, 1)) && w.tkeys.reserve(nEnt) && w.tvals.reserve(nEnt) && w.ekeys.reserve(nEnt) && w.evals.reserve(nEnt) && w.key_tmp.reserve(nEnt) && w.val_tmp.reserve(nEnt)
         && w.act.reserve(cap) && w.dup.reserve(cap) && w.para.reserve(cap) && w.para_e.reserve(cap) && w.cand.reserve((size_t)4 * cap) && w.tmp4.reserve(cap)
         && w.tmp2.reserve((size_t)4 * cap) && w.counters.reserve(16) && w.skey.reserve((size_t)4 * cap) && w.skey2.reserve((size_t)4 * cap) && w.sidx.reserve((size_t)4 * cap)
         && w.sidx2.reserve((size_t)4 * cap);
@@ -439,20 +411,21 @@ int contact_alloc(ipcgpu_ctx* ctx)
     return 0;
 }
 
-// build one sorted grid over `boxes` (n prims); result in (keys, vals) with *nValid entries
-static int build_grid(ipcgpu_ctx* ctx, int n, const Box* boxes, DevBuf<unsigned long long>& keys, DevBuf<int>& vals)
+// build one sorted grid over `boxes` (n prims): (keys, vals) sorted by cell, boxes gathered into `sorted_boxes`
+static int build_grid(ipcgpu_ctx* ctx, int n, const Box* boxes, DevBuf<unsigned long long>& keys, DevBuf<int>& vals, Box* sorted_boxes)
 {
     ContactWork& w = ctx->cw;
     cudaStream_t st = ctx->stream;
     if (n <= 0) return 0;
     k_emit<<<nblk(n, 256), 256, 0, st>>>(n, boxes, w.grid.p, w.key_tmp.p, w.val_tmp.p);
     size_t bytes = w.cub_tmp.n;
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(w.cub_tmp.p, bytes, w.key_tmp.p, keys.p, w.val_tmp.p, vals.p, 8 * n, 0, 64, st);
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(w.cub_tmp.p, bytes, w.key_tmp.p, keys.p, w.val_tmp.p, vals.p, n, 0, 32, st); // <= 1025^3 cells: 31 bits
     if (e != cudaSuccess) {
         ctx->err = std::string("cub grid sort: ") + cudaGetErrorString(e);
         return IPCGPU_ERR_CUDA;
     }
-    ctx->launches += 2;
+    k_gather_boxes<<<nblk(n, 256), 256, 0, st>>>(n, boxes, vals.p, sorted_boxes);
+    ctx->launches += 3;
     return 0;
 }
 
@@ -478,8 +451,8 @@ int boxes_and_grid(ipcgpu_ctx* ctx, const double* dir, double alpha, double radi
     k_grid_params<<<1, 32, 0, st>>>(w.bounds.p, radius, w.grid.p);
     ctx->launches += 5;
     int rc;
-    if ((rc = build_grid(ctx, s.nSF, w.tbox.p, w.tkeys, w.tvals))) return rc;
-    if ((rc = build_grid(ctx, s.nSE, w.ebox.p, w.ekeys, w.evals))) return rc;
+    if ((rc = build_grid(ctx, s.nSF, w.tbox.p, w.tkeys, w.tvals, w.tsbox.p))) return rc;
+    if ((rc = build_grid(ctx, s.nSE, w.ebox.p, w.ekeys, w.evals, w.esbox.p))) return rc;
     return 0;
 }
 
@@ -503,8 +476,9 @@ int contact_constraint_set(ipcgpu_ctx* ctx, double dHat, int wantCand, int* nC, 
     out.para = w.para.p; out.para_e = w.para_e.p; out.nPara = w.counters.p + 2; out.capPara = w.cap;
     out.cand = w.cand.p; out.nCand = w.counters.p + 3; out.capCand = 4 * w.cap;
     out.overflow = w.counters.p + 4;
-    if (s.nSV > 0 && s.nSF > 0) k_query_pt<<<nblk(s.nSV, 128), 128, 0, st>>>(s, w.grid.p, w.tbox.p, w.tkeys.p, w.tvals.p, 8 * s.nSF, dHat, radius, wantCand, out);
-    if (s.nSE > 1) k_query_ee<<<nblk(s.nSE, 128), 128, 0, st>>>(s, w.grid.p, w.ebox.p, w.ekeys.p, w.evals.p, 8 * s.nSE, dHat, radius, wantCand, out);
+    const SortedGrid tg{ w.tkeys.p, w.tvals.p, w.tsbox.p, s.nSF }, eg{ w.ekeys.p, w.evals.p, w.esbox.p, s.nSE };
+    if (s.nSV > 0 && s.nSF > 0) k_query_pt<<<nblk((long long)s.nSV * 32, 128), 128, 0, st>>>(s, w.grid.p, tg, dHat, radius, wantCand, out);
+    if (s.nSE > 1) k_query_ee<<<nblk((long long)s.nSE * 32, 128), 128, 0, st>>>(s, w.grid.p, w.ebox.p, eg, dHat, radius, wantCand, out);
     ctx->launches += 2;
     int* h = reinterpret_cast<int*>(ctx->h_scalar);
     CKC(cudaMemcpyAsync(h, w.counters.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -42,7 +42,7 @@ struct DevBuf {
 
 // device workspace of the contact stages (constraint.cu / ccd.cu)
 struct ContactWork {
-    DevBuf<Box> vbox, ebox, tbox;
+    DevBuf<Box> vbox, ebox, tbox, tsbox, esbox; // per-primitive boxes; t/e boxes again in grid-sorted order
     DevBuf<unsigned long long> bounds, tkeys, ekeys, key_tmp, skey, skey2;
     DevBuf<Grid> grid;
     DevBuf<int> tvals, evals, val_tmp, counters, sidx, sidx2;
@@ -57,14 +57,14 @@ struct ContactWork {
 struct CcdWork {
     DevBuf<int> vmin, vmax, counters;
     DevBuf<int2> cand;
-    DevBuf<unsigned> surv;
+    DevBuf<unsigned> surv, surv2;
     DevBuf<unsigned char> scratch;
     DevBuf<unsigned long long> ncand, bounds;
     // reference swept-grid geometry (SpatialHash.hpp:589-640) of the last ipcgpu_hash_build_swept
     double ref_lo[3] = { 0, 0, 0 }, ref_inv_h = 0.0, alpha_grid = 0.0;
     int ref_count[3] = { 0, 0, 0 };
     bool swept_ready = false;
-    unsigned last_survivors = 0;
+    unsigned last_survivors = 0, last_deferred = 0;
     int last_warnings = 0;
     unsigned long long last_candidates = 0;
 };
