@@ -171,7 +171,7 @@ int ipcgpu_create(int device, ipcgpu_ctx** out)
     if (cudaSetDevice(device) != cudaSuccess) return IPCGPU_ERR_CUDA;
     ipcgpu_ctx* ctx = new ipcgpu_ctx();
     ctx->device = device;
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess || cudaMallocHost(&ctx->h_scalar, 64) != cudaSuccess
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess || cudaMallocHost(&ctx->h_scalar, 512) != cudaSuccess
         || !ctx->flag.reserve(4) || !ctx->scalar_out.reserve(8) || !ctx->min_ord.reserve(4)) {
         delete ctx;
         return IPCGPU_ERR_CUDA;
@@ -584,6 +584,14 @@ int ipcgpu_ccd_stats(ipcgpu_ctx* ctx, uint64_t* candidates, uint64_t* survivors,
     if (candidates) *candidates = ctx->ccd.last_candidates;
     if (survivors) *survivors = ctx->ccd.last_survivors;
     if (warnings) *warnings = (uint64_t)ctx->ccd.last_warnings;
+    return IPCGPU_OK;
+}
+
+int ipcgpu_ccd_stats_ex(ipcgpu_ctx* ctx, uint64_t* deferred, uint64_t* boxes_thread_pass, uint64_t* boxes_warp_pass)
+{
+    if (deferred) *deferred = ctx->ccd.last_deferred;
+    if (boxes_thread_pass) *boxes_thread_pass = ctx->ccd.last_boxes_thread;
+    if (boxes_warp_pass) *boxes_warp_pass = ctx->ccd.last_boxes_warp;
     return IPCGPU_OK;
 }
 

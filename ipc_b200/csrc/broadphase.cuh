@@ -86,15 +86,25 @@ DEV void warp_scan_candidates(const Grid& g, const SortedGrid& sg, const Box& qb
     int c0[3], c1[3];
     cell_range(g, qb, c0, c1);
     const int x0 = max(c0[0] - 1, 0), x1 = c1[0];
-    for (int iz = max(c0[2] - 1, 0); iz <= c1[2]; ++iz)
-        for (int iy = max(c0[1] - 1, 0); iy <= c1[1]; ++iy) {
-            const int start = lower_bound_u64(sg.keys, sg.n, cell_key(g, x0, iy, iz));
-            const int end = upper_bound_u64(sg.keys, sg.n, cell_key(g, x1, iy, iz));
-            for (int k = start + lane; k < end; k += 32) {
-                const Box b = sg.boxes[k];
-                if (boxes_overlap(qb, b)) f(sg.ids[k], b);
-            }
+    const int y0 = max(c0[1] - 1, 0), z0 = max(c0[2] - 1, 0);
+    const int ny = c1[1] - y0 + 1, nz = c1[2] - z0 + 1; // <= 3 each
+    const int nrows = ny * nz;
+    // the (<= 9) row ranges are located by 18 binary searches running on 18 different lanes at once
+    int mine = 0;
+    {
+        const int r = lane & 15;
+        if (r < nrows) {
+            const int iy = y0 + r % ny, iz = z0 + r / ny;
+            mine = (lane < 16) ? lower_bound_u64(sg.keys, sg.n, cell_key(g, x0, iy, iz)) : upper_bound_u64(sg.keys, sg.n, cell_key(g, x1, iy, iz));
         }
+    }
+    for (int r = 0; r < nrows; ++r) {
+        const int start = __shfl_sync(0xffffffffu, mine, r), end = __shfl_sync(0xffffffffu, mine, 16 + r);
+        for (int k = start + lane; k < end; k += 32) {
+            const Box b = sg.boxes[k];
+            if (boxes_overlap(qb, b)) f(sg.ids[k], b);
+        }
+    }
 }
 
 } // namespace ipcgpu

@@ -478,6 +478,7 @@ __device__ int ti_root_finder(const TiPair& P, const double* tol, double co_tol,
             toi = k2.t;
             return 1;
         }
+        if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(warn + (W == 1 ? 5 : 7)), (unsigned long long)visited); // diagnostics: boxes evaluated
         if (max_itr > 0) {
             temp_toi = k1.t;
             temp_out_tol = fmax(a1, co_tol);
@@ -677,7 +678,7 @@ __global__ void k_ccd_init(unsigned long long* min_ord, double alpha, unsigned* 
         *min_ord = dbl_to_ord(alpha);
         *nSurv = 0;
         *work = 0;
-        flags[0] = flags[1] = flags[2] = 0; // zero distance, warnings, deferred count
+        for (int q = 0; q < 12; ++q) flags[q] = 0; // zero distance, warnings, deferred count, pad, boxes(thread pass) x2, boxes(warp pass) x2
     }
 }
 
@@ -750,13 +751,15 @@ int ccd_narrow(ipcgpu_ctx* ctx, const int2* cand, unsigned long long nCand, doub
     unsigned long long* h = reinterpret_cast<unsigned long long*>(ctx->h_scalar);
     int* hi = reinterpret_cast<int*>(ctx->h_scalar + 2);
     CKD(cudaMemcpyAsync(h, ctx->min_ord.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    CKD(cudaMemcpyAsync(hi, w.counters.p, 6 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CKD(cudaMemcpyAsync(hi, w.counters.p, 12 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CKD(cudaStreamSynchronize(st));
     double m;
     std::memcpy(&m, h, sizeof(double));
     w.last_survivors = (unsigned)hi[0];
     w.last_warnings = hi[3];
     w.last_deferred = (unsigned)hi[4];
+    std::memcpy(&w.last_boxes_thread, hi + 8, 8);
+    std::memcpy(&w.last_boxes_warp, hi + 10, 8);
     w.last_candidates = nCand;
     if (hi[2]) *alpha_inout = 0.0; // zero initial distance
     else *alpha_inout = m;
@@ -842,8 +845,8 @@ int ccd_full(ipcgpu_ctx* ctx, double tol, const double* err_vf, const double* er
     const SurfArgs s = surf_args(ctx);
     cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_CCD_BROAD);
     CKD(cudaMemsetAsync(w.ncand.p, 0, 2 * sizeof(unsigned long long), st));
-    CKD(cudaMemsetAsync(w.counters.p + 8, 0, sizeof(int), st));
-    CandOut out{ w.cand.p, w.ncand.p, (unsigned long long)ctx->ccd_capacity, w.counters.p + 8 };
+    CKD(cudaMemsetAsync(w.counters.p + 14, 0, sizeof(int), st));
+    CandOut out{ w.cand.p, w.ncand.p, (unsigned long long)ctx->ccd_capacity, w.counters.p + 14 };
     const double radius = 1.0 / w.ref_inv_h;
     // multi-GPU: every rank sweeps a contiguous share of the query primitives (the reference's own loop decomposition, :1385, :1498)
     const int v0 = (int)((long long)s.nSV * ctx->rank / ctx->nranks), v1 = (int)((long long)s.nSV * (ctx->rank + 1) / ctx->nranks);
@@ -857,7 +860,7 @@ int ccd_full(ipcgpu_ctx* ctx, double tol, const double* err_vf, const double* er
     unsigned long long* hn = reinterpret_cast<unsigned long long*>(ctx->h_scalar);
     int* ho = reinterpret_cast<int*>(ctx->h_scalar + 2);
     CKD(cudaMemcpyAsync(hn, w.ncand.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    CKD(cudaMemcpyAsync(ho, w.counters.p + 8, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CKD(cudaMemcpyAsync(ho, w.counters.p + 14, sizeof(int), cudaMemcpyDeviceToHost, st));
     CKD(cudaStreamSynchronize(st));
     ctx->prof_end(pe);
     if (*ho) {

@@ -66,7 +66,7 @@ struct CcdWork {
     bool swept_ready = false;
     unsigned last_survivors = 0, last_deferred = 0;
     int last_warnings = 0;
-    unsigned long long last_candidates = 0;
+    unsigned long long last_candidates = 0, last_boxes_thread = 0, last_boxes_warp = 0;
 };
 
 } // namespace ipcgpu

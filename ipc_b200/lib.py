@@ -56,6 +56,7 @@ SIGNATURES = {
     "ipcgpu_hash_build_swept": (C.c_int, [_ctxp, _dp, _dp, C.c_double]),
     "ipcgpu_ccd_full_ti": (C.c_int, [_ctxp, C.c_double, _dp, _dp, _dp, C.POINTER(C.c_uint64)]),
     "ipcgpu_ccd_stats": (C.c_int, [_ctxp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "ipcgpu_ccd_stats_ex": (C.c_int, [_ctxp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "ipcgpu_csr_set_zero": (C.c_int, [_ctxp]),
     "ipcgpu_allreduce_grad_hess": (C.c_int, [_ctxp, C.c_int, C.c_int]),
     "ipcgpu_download": (C.c_int, [_ctxp, C.c_int, _dp, C.c_uint64]),
@@ -291,6 +292,11 @@ class Context:
     def ccd_stats(self):
         a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
         self._ck(self.lib.ipcgpu_ccd_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def ccd_stats_ex(self):
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._ck(self.lib.ipcgpu_ccd_stats_ex(self.h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
 
     def profile(self, enable):
