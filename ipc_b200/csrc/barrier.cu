@@ -261,9 +261,21 @@ __global__ void __launch_bounds__(64) k_barrier_hessian_build(BarrierArgs p, dou
 #undef HE
 }
 
-// round-robin tournament: 11 rounds of 6 disjoint (p,q) pairs over 12 indices; kPartner[r][i] = index paired with i in round r
-__constant__ signed char kPartner[11][12];
-__constant__ signed char kPairP[11][6], kPairQ[11][6];
+// round-robin tournament (circle method): 11 rounds of 6 disjoint pairs over 12 indices.  Index 11 is fixed, the others sit on a
+// ring: ring position k of round r holds index (r+k)%11; position 0 plays index 11, position k plays position 11-k.
+// Everything is computed arithmetically -- a lookup table indexed per lane would serialise in the constant cache.
+DEV int rr_partner(int r, int i)
+{
+    if (i == 11) return r % 11;
+    const int k = (i - r + 11) % 11;
+    return k == 0 ? 11 : (r + 11 - k) % 11;
+}
+DEV int rr_rot(int r, int i) // which of the round's 6 rotations acts on index i
+{
+    if (i == 11) return 0;
+    const int k = (i - r + 11) % 11;
+    return min(k, 11 - k);
+}
 
 constexpr int kProjWarps = 8; // warps (pairs) per CTA in the projection kernel
 
@@ -299,7 +311,8 @@ __global__ void __launch_bounds__(32 * kProjWarps) k_barrier_hessian_project(Bar
         if (off <= 2e-26 * dg || off <= 1e-300) break;
         for (int r = 0; r < 11; ++r) {
             if (lane < 6) {
-                const int pI = kPairP[r][lane], q = kPairQ[r][lane];
+                const int x = (lane == 0) ? (r % 11) : (r + lane) % 11, y = (lane == 0) ? 11 : (r + 11 - lane) % 11;
+                const int pI = min(x, y), q = max(x, y);
                 const double apq = A[pI * 12 + q];
                 double cc = 1.0, ss = 0.0;
                 if (apq != 0.0) {
@@ -319,15 +332,9 @@ __global__ void __launch_bounds__(32 * kProjWarps) k_barrier_hessian_project(Bar
                 const int e = lane + 32 * k;
                 if (e < 144) {
                     const int i = e / 12, j = e % 12;
-                    const int ip = kPartner[r][i], jp = kPartner[r][j];
+                    const int ip = rr_partner(r, i), jp = rr_partner(r, j);
                     // rotation acting on index i: if i is the "p" of its pair, x_i' = c x_i - s x_ip ; if "q": x_i' = s x_ip + c x_i
-                    const int pi = min(i, ip), pj = min(j, jp);
-                    int ri = 0, rj = 0;
-#pragma unroll
-                    for (int q = 0; q < 6; ++q) {
-                        if (kPairP[r][q] == pi) ri = q;
-                        if (kPairP[r][q] == pj) rj = q;
-                    }
+                    const int ri = rr_rot(r, i), rj = rr_rot(r, j);
                     const double ci = cs[ri], si = (i < ip) ? -cs[6 + ri] : cs[6 + ri];
                     const double cj = cs[rj], sj = (j < jp) ? -cs[6 + rj] : cs[6 + rj];
                     // y = c*x_self + sgn*s*x_partner  (p: c x_p - s x_q ; q: s x_p + c x_q)
@@ -418,35 +425,10 @@ void barrier_gradient(const BarrierArgs& p, double* g, cudaStream_t st)
     const int n = p.nC + p.nP;
     if (n > 0) k_barrier_gradient<<<(n + 127) / 128, 128, 0, st>>>(p, g);
 }
-static void init_tournament()
-{
-    // circle method: index 11 fixed, the others rotate
-    signed char partner[11][12], P[11][6], Q[11][6];
-    for (int r = 0; r < 11; ++r) {
-        int ring[11];
-        for (int k = 0; k < 11; ++k) ring[k] = (r + k) % 11;
-        int a0 = ring[0], b0 = 11, cnt = 0;
-        P[r][cnt] = (signed char)std::min(a0, b0); Q[r][cnt] = (signed char)std::max(a0, b0); ++cnt;
-        for (int k = 1; k <= 5; ++k) {
-            int x = ring[k], y = ring[11 - k];
-            P[r][cnt] = (signed char)std::min(x, y); Q[r][cnt] = (signed char)std::max(x, y); ++cnt;
-        }
-        for (int q = 0; q < 6; ++q) { partner[r][P[r][q]] = Q[r][q]; partner[r][Q[r][q]] = P[r][q]; }
-    }
-    cudaMemcpyToSymbol(kPartner, partner, sizeof(partner));
-    cudaMemcpyToSymbol(kPairP, P, sizeof(P));
-    cudaMemcpyToSymbol(kPairQ, Q, sizeof(Q));
-}
-
 void barrier_hessian(const BarrierArgs& p, double* a, int* err, double* Hraw, int* rows, cudaStream_t st)
 {
     const int n = p.nC + p.nP;
     if (n <= 0) return;
-    static bool init = false;
-    if (!init) {
-        init_tournament();
-        init = true;
-    }
     k_barrier_hessian_build<<<(n + 63) / 64, 64, 0, st>>>(p, Hraw, rows);
     k_barrier_hessian_project<<<(n + kProjWarps - 1) / kProjWarps, 32 * kProjWarps, 0, st>>>(p, Hraw, rows, a, err);
 }

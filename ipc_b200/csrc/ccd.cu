@@ -382,6 +382,10 @@ DEV bool sum_le_1(unsigned long long an, int ak, unsigned long long bn, int bk)
 
 constexpr unsigned F_ZERO = 1u << 24; // zero_in flag stored in DBox::kk
 
+constexpr int kStage2WarpsPerCtaDev = 4;
+constexpr int kThreadBudget = 10; // boxes a single thread may evaluate for one pair before handing it to the warp-level pass
+constexpr int kSmemLevel = 64;    // boxes per level buffer kept in shared memory by the warp-level pass
+
 // group helpers: W = 32 (one warp per pair) or W = 1 (one thread per pair, no cross-lane traffic)
 template <int W> DEV void group_min_key(Key3& k, unsigned& pay, double& aux) { if (W == 32) warp_min_key(k, pay, aux); }
 template <int W> DEV int group_count(bool b) { return (W == 32) ? __popc(__ballot_sync(0xffffffffu, b)) : (b ? 1 : 0); }
@@ -404,12 +408,15 @@ template <int W> DEV void group_scan(int v, int lane, int& incl, int& total)
 // result codes of the root finder: 0 no collision, 1 collision (toi set), 2 deferred (W = 1 only: level buffer too small)
 template <bool VF, int W>
 __device__ int ti_root_finder(const TiPair& P, const double* tol, double co_tol, double max_t, const double* err, double ms, int max_itr, DBox* bufA,
-    DBox* bufB, int cap, int lane, double& toi, double& out_tol, int* __restrict__ warn)
+    DBox* bufB, int gcap, int lane, double& toi, double& out_tol, int* __restrict__ warn, DBox* sA = nullptr, DBox* sB = nullptr)
 {
     const bool check_t = (max_t != 1.0);
     const double INF = __longlong_as_double(0x7ff0000000000000ll);
-    DBox* cur = bufA;
-    DBox* nxt = bufB;
+    // levels start in shared memory (when provided) and migrate to the global buffers if they outgrow it
+    bool in_smem = (sA != nullptr);
+    DBox* cur = in_smem ? sA : bufA;
+    DBox* nxt = in_smem ? sB : bufB;
+    int cap = in_smem ? kSmemLevel : gcap;
     if (lane == 0) cur[0] = DBox{ 0ull, 0ull, 0ull, 0u, 0u };
     group_sync<W>();
     int n = 1;
@@ -417,6 +424,8 @@ __device__ int ti_root_finder(const TiPair& P, const double* tol, double co_tol,
     bool use_skip = false;
     long long refine = 0;
     double temp_toi = INF, temp_out_tol = co_tol;
+    DBox* gA = bufA; // global (or local) backing store used when a level outgrows the shared-memory buffers
+    DBox* gB = bufB;
     out_tol = co_tol;
     toi = INF;
     while (n > 0) {
@@ -479,6 +488,7 @@ __device__ int ti_root_finder(const TiPair& P, const double* tol, double co_tol,
             return 1;
         }
         if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(warn + (W == 1 ? 5 : 7)), (unsigned long long)visited); // diagnostics: boxes evaluated
+        if (W == 1 && refine + visited > kThreadBudget) return 2; // deep search: a job for a whole warp
         if (max_itr > 0) {
             temp_toi = k1.t;
             temp_out_tol = fmax(a1, co_tol);
@@ -546,6 +556,13 @@ __device__ int ti_root_finder(const TiPair& P, const double* tol, double co_tol,
             int incl, total;
             group_scan<W>(nchild, lane, incl, total);
             const int off = nn + incl - nchild;
+            if (W == 32 && in_smem && nn + total > cap) { // this level no longer fits in shared memory: continue it in global memory
+                for (int q = lane; q < nn; q += 32) gB[q] = nxt[q];
+                group_sync<W>();
+                nxt = gB;
+                cap = gcap;
+                in_smem = false;
+            }
             if (nn + total > cap) over = true;
             else {
                 if (nchild > 0) nxt[off] = c0;
@@ -563,7 +580,13 @@ __device__ int ti_root_finder(const TiPair& P, const double* tol, double co_tol,
             return 1;
         }
         group_sync<W>();
-        DBox* t = cur; cur = nxt; nxt = t;
+        if (W == 32 && !in_smem && nxt == gB && cur != gA) { // first level after the migration: from now on ping-pong between the global buffers
+            cur = gB;
+            nxt = gA;
+        }
+        else {
+            DBox* t = cur; cur = nxt; nxt = t;
+        }
         n = nn;
     }
     if (use_skip) {
@@ -576,7 +599,7 @@ __device__ int ti_root_finder(const TiPair& P, const double* tol, double co_tol,
 // vertexFaceCCD_double / edgeEdgeCCD_double including the no_zero_toi refinement loop; returns 0 / 1 / 2 (deferred)
 template <bool VF, int W>
 __device__ int ti_ccd(const TiPair& P, const double* err, double ms, double tolerance, double t_max, int max_itr, DBox* bufA, DBox* bufB, int cap, int lane,
-    double& toi, int* __restrict__ warn)
+    double& toi, int* __restrict__ warn, DBox* sA = nullptr, DBox* sB = nullptr)
 {
     double tolerance_in = tolerance, ms_in = ms, out_tol = tolerance;
     bool is_impacting = false, tmp = false;
@@ -584,7 +607,7 @@ __device__ int ti_ccd(const TiPair& P, const double* err, double ms, double tole
     do {
         double tol[3];
         width_tolerances<VF>(P, tolerance_in, tol);
-        const int rc = ti_root_finder<VF, W>(P, tol, tolerance_in, t_max, err, ms_in, max_itr, bufA, bufB, cap, lane, toi, out_tol, warn);
+        const int rc = ti_root_finder<VF, W>(P, tol, tolerance_in, t_max, err, ms_in, max_itr, bufA, bufB, cap, lane, toi, out_tol, warn, sA, sB);
         if (rc == 2) return 2;
         tmp = rc == 1;
         if (iter == 0) is_impacting = tmp;
@@ -601,16 +624,17 @@ __device__ int ti_ccd(const TiPair& P, const double* err, double ms, double tole
 
 // one candidate end to end (SelfCollisionHandler.cpp:740-790): 0 / 1 (toi set) / 2 deferred
 template <int W>
-__device__ int pair_ccd(bool vf, const TiPair& P, const NarrowArgs& a, DBox* bufA, DBox* bufB, int cap, int lane, double& toi, int* __restrict__ warn)
+__device__ int pair_ccd(bool vf, const TiPair& P, const NarrowArgs& a, DBox* bufA, DBox* bufB, int cap, int lane, double& toi, int* __restrict__ warn,
+    DBox* sA = nullptr, DBox* sB = nullptr)
 {
     const double d = pair_distance_sqrt(vf, P);
     const double ms = fmin(0.2 * d, 1e-6);
-    int hit = vf ? ti_ccd<true, W>(P, a.err_vf, ms, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn)
-                 : ti_ccd<false, W>(P, a.err_ee, ms, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn);
+    int hit = vf ? ti_ccd<true, W>(P, a.err_vf, ms, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn, sA, sB)
+                 : ti_ccd<false, W>(P, a.err_ee, ms, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn, sA, sB);
     if (hit == 2) return 2;
     if (hit && toi < 1e-6) { // :759-781
-        hit = vf ? ti_ccd<true, W>(P, a.err_vf, 0.0, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn)
-                 : ti_ccd<false, W>(P, a.err_ee, 0.0, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn);
+        hit = vf ? ti_ccd<true, W>(P, a.err_vf, 0.0, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn, sA, sB)
+                 : ti_ccd<false, W>(P, a.err_ee, 0.0, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn, sA, sB);
         if (hit == 2) return 2;
         if (hit) toi *= 0.8;
     }
@@ -618,7 +642,7 @@ __device__ int pair_ccd(bool vf, const TiPair& P, const NarrowArgs& a, DBox* buf
 }
 
 // stage 1.5: one THREAD per surviving pair with a small private level buffer; pairs whose search outgrows it are deferred
-constexpr int kThreadCap = 24;
+constexpr int kThreadCap = 12;
 __global__ void __launch_bounds__(128) k_ti_stage15(NarrowArgs a, const unsigned* __restrict__ survivors, const unsigned* __restrict__ nSurvPtr,
     unsigned* __restrict__ deferred, unsigned* __restrict__ nDeferred, unsigned long long* __restrict__ min_ord, int* __restrict__ warn)
 {
@@ -651,8 +675,11 @@ __global__ void __launch_bounds__(128) k_ti_stage15(NarrowArgs a, const unsigned
 __global__ void __launch_bounds__(128) k_ti_stage2(NarrowArgs a, const unsigned* __restrict__ survivors, const unsigned* __restrict__ nSurvPtr, unsigned* __restrict__ work,
     DBox* __restrict__ scratch, int cap, unsigned long long* __restrict__ min_ord, int* __restrict__ warn)
 {
+    __shared__ DBox sLevels[kStage2WarpsPerCtaDev][2][kSmemLevel];
     const int lane = threadIdx.x & 31;
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    DBox* sA = sLevels[threadIdx.x >> 5][0];
+    DBox* sB = sLevels[threadIdx.x >> 5][1];
     DBox* bufA = scratch + (size_t)warp_global * 2 * cap;
     DBox* bufB = bufA + cap;
     const unsigned nSurv = *nSurvPtr;
@@ -666,7 +693,7 @@ __global__ void __launch_bounds__(128) k_ti_stage2(NarrowArgs a, const unsigned*
         TiPair P;
         load_pair(a.s, a.dir, a.cand[survivors[w]], vf, v, P);
         double toi;
-        const int hit = pair_ccd<32>(vf, P, a, bufA, bufB, cap, lane, toi, warn);
+        const int hit = pair_ccd<32>(vf, P, a, bufA, bufB, cap, lane, toi, warn, sA, sB);
         if (hit && lane == 0) atomicMin(min_ord, dbl_to_ord(toi));
         __syncwarp();
     }
