@@ -286,6 +286,13 @@ __global__ void __launch_bounds__(32 * kProjWarps) k_barrier_hessian_project(Bar
     __shared__ double sV[kProjWarps][144];
     __shared__ double sCS[kProjWarps][12]; // c (0..5) and s (6..11) of the round's rotations
     __shared__ int sOff[kProjWarps][48];
+    __shared__ unsigned short sTab[11][144]; // per (round, element): partner row/col, rotation ids, sign bits
+    for (int t = threadIdx.x; t < 11 * 144; t += blockDim.x) {
+        const int r = t / 144, e = t % 144, i = e / 12, j = e % 12;
+        const int ip = rr_partner(r, i), jp = rr_partner(r, j);
+        sTab[r][e] = (unsigned short)(ip | (jp << 4) | (rr_rot(r, i) << 8) | (rr_rot(r, j) << 11) | ((i < ip ? 1 : 0) << 14) | ((j < jp ? 1 : 0) << 15));
+    }
+    __syncthreads();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int c = blockIdx.x * kProjWarps + wib;
     if (c >= p.nC + p.nP) return;
@@ -331,12 +338,12 @@ __global__ void __launch_bounds__(32 * kProjWarps) k_barrier_hessian_project(Bar
             for (int k = 0; k < 5; ++k) {
                 const int e = lane + 32 * k;
                 if (e < 144) {
-                    const int i = e / 12, j = e % 12;
-                    const int ip = rr_partner(r, i), jp = rr_partner(r, j);
+                    const int i = e / 12, j = e - 12 * i;
+                    const unsigned tb = sTab[r][e];
+                    const int ip = tb & 15, jp = (tb >> 4) & 15, ri = (tb >> 8) & 7, rj = (tb >> 11) & 7;
                     // rotation acting on index i: if i is the "p" of its pair, x_i' = c x_i - s x_ip ; if "q": x_i' = s x_ip + c x_i
-                    const int ri = rr_rot(r, i), rj = rr_rot(r, j);
-                    const double ci = cs[ri], si = (i < ip) ? -cs[6 + ri] : cs[6 + ri];
-                    const double cj = cs[rj], sj = (j < jp) ? -cs[6 + rj] : cs[6 + rj];
+                    const double ci = cs[ri], si = (tb & 0x4000u) ? -cs[6 + ri] : cs[6 + ri];
+                    const double cj = cs[rj], sj = (tb & 0x8000u) ? -cs[6 + rj] : cs[6 + rj];
                     // y = c*x_self + sgn*s*x_partner  (p: c x_p - s x_q ; q: s x_p + c x_q)
                     const double a_ij = A[i * 12 + j], a_ipj = A[ip * 12 + j], a_ijp = A[i * 12 + jp], a_ipjp = A[ip * 12 + jp];
                     const double row_j = ci * a_ij + si * a_ipj;    // (J^T A)[i][j]

@@ -383,7 +383,6 @@ DEV bool sum_le_1(unsigned long long an, int ak, unsigned long long bn, int bk)
 constexpr unsigned F_ZERO = 1u << 24; // zero_in flag stored in DBox::kk
 
 constexpr int kStage2WarpsPerCtaDev = 4;
-constexpr int kThreadBudget = 10; // boxes a single thread may evaluate for one pair before handing it to the warp-level pass
 constexpr int kSmemLevel = 64;    // boxes per level buffer kept in shared memory by the warp-level pass
 
 // group helpers: W = 32 (one warp per pair) or W = 1 (one thread per pair, no cross-lane traffic)
@@ -408,7 +407,7 @@ template <int W> DEV void group_scan(int v, int lane, int& incl, int& total)
 // result codes of the root finder: 0 no collision, 1 collision (toi set), 2 deferred (W = 1 only: level buffer too small)
 template <bool VF, int W>
 __device__ int ti_root_finder(const TiPair& P, const double* tol, double co_tol, double max_t, const double* err, double ms, int max_itr, DBox* bufA,
-    DBox* bufB, int gcap, int lane, double& toi, double& out_tol, int* __restrict__ warn, DBox* sA = nullptr, DBox* sB = nullptr)
+    DBox* bufB, int gcap, int lane, double& toi, double& out_tol, int* __restrict__ warn, DBox* sA = nullptr, DBox* sB = nullptr, long long thread_budget = 0)
 {
     const bool check_t = (max_t != 1.0);
     const double INF = __longlong_as_double(0x7ff0000000000000ll);
@@ -488,7 +487,7 @@ __device__ int ti_root_finder(const TiPair& P, const double* tol, double co_tol,
             return 1;
         }
         if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(warn + (W == 1 ? 5 : 7)), (unsigned long long)visited); // diagnostics: boxes evaluated
-        if (W == 1 && refine + visited > kThreadBudget) return 2; // deep search: a job for a whole warp
+        if (W == 1 && refine + visited > thread_budget) return 2; // over budget: handed to the next pass
         if (max_itr > 0) {
             temp_toi = k1.t;
             temp_out_tol = fmax(a1, co_tol);
@@ -599,7 +598,7 @@ __device__ int ti_root_finder(const TiPair& P, const double* tol, double co_tol,
 // vertexFaceCCD_double / edgeEdgeCCD_double including the no_zero_toi refinement loop; returns 0 / 1 / 2 (deferred)
 template <bool VF, int W>
 __device__ int ti_ccd(const TiPair& P, const double* err, double ms, double tolerance, double t_max, int max_itr, DBox* bufA, DBox* bufB, int cap, int lane,
-    double& toi, int* __restrict__ warn, DBox* sA = nullptr, DBox* sB = nullptr)
+    double& toi, int* __restrict__ warn, DBox* sA = nullptr, DBox* sB = nullptr, long long thread_budget = 0)
 {
     double tolerance_in = tolerance, ms_in = ms, out_tol = tolerance;
     bool is_impacting = false, tmp = false;
@@ -607,7 +606,7 @@ __device__ int ti_ccd(const TiPair& P, const double* err, double ms, double tole
     do {
         double tol[3];
         width_tolerances<VF>(P, tolerance_in, tol);
-        const int rc = ti_root_finder<VF, W>(P, tol, tolerance_in, t_max, err, ms_in, max_itr, bufA, bufB, cap, lane, toi, out_tol, warn, sA, sB);
+        const int rc = ti_root_finder<VF, W>(P, tol, tolerance_in, t_max, err, ms_in, max_itr, bufA, bufB, cap, lane, toi, out_tol, warn, sA, sB, thread_budget);
         if (rc == 2) return 2;
         tmp = rc == 1;
         if (iter == 0) is_impacting = tmp;
@@ -625,16 +624,16 @@ __device__ int ti_ccd(const TiPair& P, const double* err, double ms, double tole
 // one candidate end to end (SelfCollisionHandler.cpp:740-790): 0 / 1 (toi set) / 2 deferred
 template <int W>
 __device__ int pair_ccd(bool vf, const TiPair& P, const NarrowArgs& a, DBox* bufA, DBox* bufB, int cap, int lane, double& toi, int* __restrict__ warn,
-    DBox* sA = nullptr, DBox* sB = nullptr)
+    DBox* sA = nullptr, DBox* sB = nullptr, long long thread_budget = 0)
 {
     const double d = pair_distance_sqrt(vf, P);
     const double ms = fmin(0.2 * d, 1e-6);
-    int hit = vf ? ti_ccd<true, W>(P, a.err_vf, ms, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn, sA, sB)
-                 : ti_ccd<false, W>(P, a.err_ee, ms, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn, sA, sB);
+    int hit = vf ? ti_ccd<true, W>(P, a.err_vf, ms, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn, sA, sB, thread_budget)
+                 : ti_ccd<false, W>(P, a.err_ee, ms, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn, sA, sB, thread_budget);
     if (hit == 2) return 2;
     if (hit && toi < 1e-6) { // :759-781
-        hit = vf ? ti_ccd<true, W>(P, a.err_vf, 0.0, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn, sA, sB)
-                 : ti_ccd<false, W>(P, a.err_ee, 0.0, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn, sA, sB);
+        hit = vf ? ti_ccd<true, W>(P, a.err_vf, 0.0, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn, sA, sB, thread_budget)
+                 : ti_ccd<false, W>(P, a.err_ee, 0.0, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn, sA, sB, thread_budget);
         if (hit == 2) return 2;
         if (hit) toi *= 0.8;
     }
@@ -644,31 +643,35 @@ __device__ int pair_ccd(bool vf, const TiPair& P, const NarrowArgs& a, DBox* buf
 // stage 1.5: one THREAD per surviving pair with a small private level buffer; pairs whose search outgrows it are deferred
 constexpr int kThreadCap = 12;
 __global__ void __launch_bounds__(128) k_ti_stage15(NarrowArgs a, const unsigned* __restrict__ survivors, const unsigned* __restrict__ nSurvPtr,
-    unsigned* __restrict__ deferred, unsigned* __restrict__ nDeferred, unsigned long long* __restrict__ min_ord, int* __restrict__ warn)
+    unsigned* __restrict__ deferred, unsigned* __restrict__ nDeferred, long long budget, unsigned long long* __restrict__ min_ord, int* __restrict__ warn)
 {
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned nSurv = *nSurvPtr;
-    bool defer = false;
-    unsigned idx = 0;
-    if (i < nSurv) {
-        idx = survivors[i];
-        bool vf;
-        int v[4];
-        TiPair P;
-        load_pair(a.s, a.dir, a.cand[idx], vf, v, P);
-        DBox bufA[kThreadCap], bufB[kThreadCap];
-        double toi;
-        const int hit = pair_ccd<1>(vf, P, a, bufA, bufB, kThreadCap, 0, toi, warn);
-        if (hit == 2) defer = true;
-        else if (hit == 1) atomicMin(min_ord, dbl_to_ord(toi));
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, defer);
-    if (m) {
-        const int lane = threadIdx.x & 31;
-        unsigned base = 0;
-        if (lane == __ffs(m) - 1) base = atomicAdd(nDeferred, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-        if (defer) deferred[base + __popc(m & ((1u << lane) - 1))] = idx;
+    const unsigned stride = gridDim.x * blockDim.x;
+    // grid-stride over whole warps so that the warp-aggregated append below always has all 32 lanes present
+    for (unsigned base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < nSurv; base += stride) {
+        const unsigned i = base + (threadIdx.x & 31);
+        bool defer = false;
+        unsigned idx = 0;
+        if (i < nSurv) {
+            idx = survivors[i];
+            bool vf;
+            int v[4];
+            TiPair P;
+            load_pair(a.s, a.dir, a.cand[idx], vf, v, P);
+            DBox bufA[kThreadCap], bufB[kThreadCap];
+            double toi;
+            const int hit = pair_ccd<1>(vf, P, a, bufA, bufB, kThreadCap, 0, toi, warn, nullptr, nullptr, budget);
+            if (hit == 2) defer = true;
+            else if (hit == 1) atomicMin(min_ord, dbl_to_ord(toi));
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, defer);
+        if (m) {
+            const int lane = threadIdx.x & 31;
+            unsigned b0 = 0;
+            if (lane == __ffs(m) - 1) b0 = atomicAdd(nDeferred, __popc(m));
+            b0 = __shfl_sync(0xffffffffu, b0, __ffs(m) - 1);
+            if (defer) deferred[b0 + __popc(m & ((1u << lane) - 1))] = idx;
+        }
     }
 }
 
@@ -765,12 +768,18 @@ int ccd_narrow(ipcgpu_ctx* ctx, const int2* cand, unsigned long long nCand, doub
     if (nCand > 0) {
         k_ti_stage1<<<nblk((long long)nCand, 128), 128, 0, st>>>(a, w.surv.p, nSurv, flags);
         // the survivor count lives on the device; the thread-level pass is launched over the candidate count (extra threads exit)
-        unsigned* nDef = reinterpret_cast<unsigned*>(flags + 2);
-        k_ti_stage15<<<nblk((long long)nCand, 128), 128, 0, st>>>(a, w.surv.p, nSurv, w.surv2.p, nDef, ctx->min_ord.p, flags + 1);
-        k_ti_stage2<<<kStage2Ctas, 32 * kStage2WarpsPerCta, 0, st>>>(a, w.surv2.p, nDef, work, reinterpret_cast<DBox*>(w.scratch.p), kLevelCap, ctx->min_ord.p, flags + 1);
+        // pass A: every survivor, tiny budget (the shallow majority dies here without holding its warp hostage);
+        // pass B: the deferred pairs, compacted, with a large budget (deep but narrow searches: all lanes of a warp are busy);
+        // pass C: what is left (levels wider than a thread's buffer) goes to the warp-per-pair kernel.
+        unsigned* nDefA = reinterpret_cast<unsigned*>(flags + 2);
+        unsigned* nDefB = reinterpret_cast<unsigned*>(flags + 3);
+        const int gridA = std::min(nblk((long long)nCand, 128), 148 * 16);
+        k_ti_stage15<<<gridA, 128, 0, st>>>(a, w.surv.p, nSurv, w.surv2.p, nDefA, 10, ctx->min_ord.p, flags + 1);
+        k_ti_stage15<<<148 * 4, 128, 0, st>>>(a, w.surv2.p, nDefA, w.surv.p, nDefB, 1000000, ctx->min_ord.p, flags + 1);
+        k_ti_stage2<<<kStage2Ctas, 32 * kStage2WarpsPerCta, 0, st>>>(a, w.surv.p, nDefB, work, reinterpret_cast<DBox*>(w.scratch.p), kLevelCap, ctx->min_ord.p, flags + 1);
     }
     ctx->prof_end(pe);
-    ctx->launches += 4;
+    ctx->launches += 5;
     CKD(cudaGetLastError());
     if (ctx->nranks > 1) {
         // min over ranks of the step (and max of the zero-distance flag) is done by the caller through NCCL (api.cu)
@@ -784,7 +793,7 @@ int ccd_narrow(ipcgpu_ctx* ctx, const int2* cand, unsigned long long nCand, doub
     std::memcpy(&m, h, sizeof(double));
     w.last_survivors = (unsigned)hi[0];
     w.last_warnings = hi[3];
-    w.last_deferred = (unsigned)hi[4];
+    w.last_deferred = (unsigned)hi[4] * 1000000ull + (unsigned)hi[5]; // passA deferred * 1e6 + passB deferred
     std::memcpy(&w.last_boxes_thread, hi + 8, 8);
     std::memcpy(&w.last_boxes_warp, hi + 10, 8);
     w.last_candidates = nCand;

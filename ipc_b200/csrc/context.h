@@ -64,7 +64,8 @@ struct CcdWork {
     double ref_lo[3] = { 0, 0, 0 }, ref_inv_h = 0.0, alpha_grid = 0.0;
     int ref_count[3] = { 0, 0, 0 };
     bool swept_ready = false;
-    unsigned last_survivors = 0, last_deferred = 0;
+    unsigned last_survivors = 0;
+    unsigned long long last_deferred = 0;
     int last_warnings = 0;
     unsigned long long last_candidates = 0, last_boxes_thread = 0, last_boxes_warp = 0;
 };
