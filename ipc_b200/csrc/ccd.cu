@@ -595,6 +595,161 @@ __device__ int ti_root_finder(const TiPair& P, const double* tol, double co_tol,
     return 0;
 }
 
+// ---- corner-parallel variant of the root finder for the warp-level pass ------------------------------------------------------
+// Deep searches are narrow (1-2 boxes per level), so parallelism over boxes does not exist; what can be parallelised is ONE box:
+// its 3 coordinates x 8 corners = 24 values of F are evaluated by 24 lanes, the co-domain interval of each coordinate is a 3-step
+// shuffle min/max inside its 8-lane group, and the inclusion flags are warp ballots.  All bookkeeping (K1/K2 tracking, bisection) is
+// warp-uniform scalar code over level buffers in shared memory.  Same arithmetic per corner, same decisions => same result as the
+// box-parallel variant.  Returns -1 when a level outgrows the shared-memory buffer (the caller restarts with the box-parallel variant).
+template <bool VF>
+__device__ int ti_root_finder_cp(const TiPair& P, const double* tol, double co_tol, double max_t, const double* err, double ms, int max_itr, DBox* sA, DBox* sB,
+    int lane, double& toi, double& out_tol, int* __restrict__ warn)
+{
+    const bool check_t = (max_t != 1.0);
+    const double INF = __longlong_as_double(0x7ff0000000000000ll);
+    const int c = lane >> 3, corner = lane & 7;
+    const int ci = corner >> 2, cj = (corner >> 1) & 1, cl = corner & 1;
+    double a0[4], a1[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        a0[k] = (c == 0) ? P.x0[3 * k] : ((c == 1) ? P.x0[3 * k + 1] : P.x0[3 * k + 2]);
+        a1[k] = (c == 0) ? P.x1[3 * k] : ((c == 1) ? P.x1[3 * k + 1] : P.x1[3 * k + 2]);
+    }
+    const double eps = ((c == 0) ? err[0] : ((c == 1) ? err[1] : err[2])) + ms;
+    const unsigned live = 0x00ffffffu; // lanes 24..31 idle
+    DBox* cur = sA;
+    DBox* nxt = sB;
+    if (lane == 0) cur[0] = DBox{ 0ull, 0ull, 0ull, 0u, 0u };
+    __syncwarp();
+    int n = 1;
+    double toi_skip = INF;
+    bool use_skip = false;
+    long long refine = 0;
+    double temp_toi = INF, temp_out_tol = co_tol;
+    out_tol = co_tol;
+    toi = INF;
+    while (n > 0) {
+        Key3 k1 = { INF, INF, INF }, k2 = { INF, INF, INF };
+        unsigned p1 = 0, p2 = 0;
+        double a1max = 0.0;
+        int visited = 0;
+        for (int bI = 0; bI < n; ++bI) {
+            const DBox b = cur[bI];
+            const int tk = b.kk & 0xff, uk = (b.kk >> 8) & 0xff, vk = (b.kk >> 16) & 0xff;
+            const double tlo = dy_lo(b.tn, tk);
+            unsigned flags = 0;
+            if (tlo < toi_skip) {
+                ++visited;
+                const double tv = ci ? dy_hi(b.tn, tk) : tlo;
+                const double uv = cj ? dy_hi(b.un, uk) : dy_lo(b.un, uk);
+                const double vv = cl ? dy_hi(b.vn, vk) : dy_lo(b.vn, vk);
+                double pp[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) pp[k] = (a1[k] - a0[k]) * tv + a0[k];
+                double f;
+                if (VF) {
+                    const double pt = ((pp[2] - pp[1]) * uv + (pp[3] - pp[1]) * vv) + pp[1];
+                    f = pp[0] - pt;
+                }
+                else {
+                    const double pa = (pp[1] - pp[0]) * uv + pp[0];
+                    const double pb = (pp[3] - pp[2]) * vv + pp[2];
+                    f = pa - pb;
+                }
+                double mn = f, mx = f;
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) {
+                    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                }
+                const double tt = mx - mn;
+                const bool excl = (mn > eps || mx < -eps);
+                if (!(__ballot_sync(0xffffffffu, excl) & live)) { // the co-domain box contains the origin
+                    flags = F_ZERO;
+                    const bool box_in = !(__ballot_sync(0xffffffffu, !(mn >= -eps && mx <= eps)) & live);
+                    const bool tol_cond = !(__ballot_sync(0xffffffffu, tt > co_tol) & live);
+                    const double tmax = fmax(fmax(__shfl_sync(0xffffffffu, tt, 0), __shfl_sync(0xffffffffu, tt, 8)), __shfl_sync(0xffffffffu, tt, 16));
+                    const bool cond1 = pow2neg(tk) <= tol[0] && pow2neg(uk) <= tol[1] && pow2neg(vk) <= tol[2];
+                    const Key3 key = { tlo, dy_lo(b.un, uk), dy_lo(b.vn, vk) };
+                    const bool flagged = tol_cond || box_in || cond1;
+                    if (key_less(key, k1)) { k1 = key; p1 = flagged ? 1u : 0u; a1max = tmax; }
+                    if (flagged && key_less(key, k2)) { k2 = key; p2 = cond1 ? 1u : 0u; }
+                }
+            }
+            if (lane == 0) cur[bI].kk = (b.kk & 0x00ffffffu) | flags;
+        }
+        __syncwarp();
+        if (k1.t == INF) break; // search space exhausted
+        if (p1 & 1u) { toi = k1.t; return 1; }
+        const bool has_k2 = k2.t != INF;
+        if (has_k2 && (p2 & 1u)) { toi = k2.t; return 1; }
+        if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(warn + 7), (unsigned long long)visited);
+        if (max_itr > 0) {
+            temp_toi = k1.t;
+            temp_out_tol = fmax(a1max, co_tol);
+            refine += visited;
+            if (refine > max_itr) {
+                if (lane == 0) atomicAdd(warn, 1);
+                toi = temp_toi;
+                out_tol = temp_out_tol;
+                return 1;
+            }
+        }
+        if (has_k2) {
+            if (k2.t < toi_skip) toi_skip = k2.t;
+            use_skip = true;
+        }
+        int nn = 0;
+        for (int bI = 0; bI < n; ++bI) {
+            const DBox b = cur[bI];
+            if (!(b.kk & F_ZERO)) continue;
+            const int tk = b.kk & 0xff, uk = (b.kk >> 8) & 0xff, vk = (b.kk >> 16) & 0xff;
+            const Key3 key = { dy_lo(b.tn, tk), dy_lo(b.un, uk), dy_lo(b.vn, vk) };
+            if (has_k2 && !key_less(key, k2)) continue;
+            const double w[3] = { pow2neg(tk), pow2neg(uk), pow2neg(vk) };
+            int split = -1;
+            double best = -1.0;
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+                if (w[d] > tol[d]) {
+                    const double r = w[d] / tol[d];
+                    if (r > best) { best = r; split = d; }
+                }
+            const int pk = split == 0 ? tk : (split == 1 ? uk : vk);
+            if (split < 0 || pk >= 60) { // bisection overflow: conservative per-level estimate, as in the box-parallel variant
+                if (lane == 0) atomicAdd(warn, 1);
+                toi = temp_toi;
+                out_tol = temp_out_tol;
+                return 1;
+            }
+            const unsigned long long pn = split == 0 ? b.tn : (split == 1 ? b.un : b.vn);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const unsigned long long hn = 2 * pn + half;
+                const int hk = pk + 1;
+                bool keep = true;
+                if (split == 0) { if (check_t) keep = !(dy_hi(hn, hk) < 0.0 || dy_lo(hn, hk) > max_t); }
+                else if (VF) keep = (split == 1) ? sum_le_1(hn, hk, b.vn, vk) : sum_le_1(hn, hk, b.un, uk);
+                if (keep) {
+                    if (nn >= kSmemLevel) return -1; // level too wide for shared memory
+                    DBox ch = b;
+                    ch.kk &= 0x00ffffffu;
+                    if (split == 0) { ch.tn = hn; ch.kk = (ch.kk & ~0xffu) | (unsigned)hk; }
+                    else if (split == 1) { ch.un = hn; ch.kk = (ch.kk & ~0xff00u) | ((unsigned)hk << 8); }
+                    else { ch.vn = hn; ch.kk = (ch.kk & ~0xff0000u) | ((unsigned)hk << 16); }
+                    if (lane == 0) nxt[nn] = ch;
+                    ++nn;
+                }
+            }
+        }
+        __syncwarp();
+        DBox* t = cur; cur = nxt; nxt = t;
+        n = nn;
+    }
+    if (use_skip) { toi = toi_skip; return 1; }
+    return 0;
+}
+
 // vertexFaceCCD_double / edgeEdgeCCD_double including the no_zero_toi refinement loop; returns 0 / 1 / 2 (deferred)
 template <bool VF, int W>
 __device__ int ti_ccd(const TiPair& P, const double* err, double ms, double tolerance, double t_max, int max_itr, DBox* bufA, DBox* bufB, int cap, int lane,
@@ -606,7 +761,12 @@ __device__ int ti_ccd(const TiPair& P, const double* err, double ms, double tole
     do {
         double tol[3];
         width_tolerances<VF>(P, tolerance_in, tol);
-        const int rc = ti_root_finder<VF, W>(P, tol, tolerance_in, t_max, err, ms_in, max_itr, bufA, bufB, cap, lane, toi, out_tol, warn, sA, sB, thread_budget);
+        int rc;
+        if (W == 32 && sA) {
+            rc = ti_root_finder_cp<VF>(P, tol, tolerance_in, t_max, err, ms_in, max_itr, sA, sB, lane, toi, out_tol, warn);
+            if (rc == -1) rc = ti_root_finder<VF, W>(P, tol, tolerance_in, t_max, err, ms_in, max_itr, bufA, bufB, cap, lane, toi, out_tol, warn, nullptr, nullptr, 0);
+        }
+        else rc = ti_root_finder<VF, W>(P, tol, tolerance_in, t_max, err, ms_in, max_itr, bufA, bufB, cap, lane, toi, out_tol, warn, sA, sB, thread_budget);
         if (rc == 2) return 2;
         tmp = rc == 1;
         if (iter == 0) is_impacting = tmp;
@@ -768,18 +928,17 @@ int ccd_narrow(ipcgpu_ctx* ctx, const int2* cand, unsigned long long nCand, doub
     if (nCand > 0) {
         k_ti_stage1<<<nblk((long long)nCand, 128), 128, 0, st>>>(a, w.surv.p, nSurv, flags);
         // the survivor count lives on the device; the thread-level pass is launched over the candidate count (extra threads exit)
-        // pass A: every survivor, tiny budget (the shallow majority dies here without holding its warp hostage);
-        // pass B: the deferred pairs, compacted, with a large budget (deep but narrow searches: all lanes of a warp are busy);
-        // pass C: what is left (levels wider than a thread's buffer) goes to the warp-per-pair kernel.
+        // pass A (thread per pair, 10-box budget): the shallow majority dies here without holding its warp hostage;
+        // pass B (warp per pair, corner-parallel box evaluation): the deep searches, compacted.
         unsigned* nDefA = reinterpret_cast<unsigned*>(flags + 2);
         unsigned* nDefB = reinterpret_cast<unsigned*>(flags + 3);
         const int gridA = std::min(nblk((long long)nCand, 128), 148 * 16);
         k_ti_stage15<<<gridA, 128, 0, st>>>(a, w.surv.p, nSurv, w.surv2.p, nDefA, 10, ctx->min_ord.p, flags + 1);
-        k_ti_stage15<<<148 * 4, 128, 0, st>>>(a, w.surv2.p, nDefA, w.surv.p, nDefB, 1000000, ctx->min_ord.p, flags + 1);
-        k_ti_stage2<<<kStage2Ctas, 32 * kStage2WarpsPerCta, 0, st>>>(a, w.surv.p, nDefB, work, reinterpret_cast<DBox*>(w.scratch.p), kLevelCap, ctx->min_ord.p, flags + 1);
+        (void)nDefB;
+        k_ti_stage2<<<kStage2Ctas, 32 * kStage2WarpsPerCta, 0, st>>>(a, w.surv2.p, nDefA, work, reinterpret_cast<DBox*>(w.scratch.p), kLevelCap, ctx->min_ord.p, flags + 1);
     }
     ctx->prof_end(pe);
-    ctx->launches += 5;
+    ctx->launches += 4;
     CKD(cudaGetLastError());
     if (ctx->nranks > 1) {
         // min over ranks of the step (and max of the zero-distance flag) is done by the caller through NCCL (api.cu)
