@@ -383,7 +383,8 @@ DEV bool sum_le_1(unsigned long long an, int ak, unsigned long long bn, int bk)
 constexpr unsigned F_ZERO = 1u << 24; // zero_in flag stored in DBox::kk
 
 constexpr int kStage2WarpsPerCtaDev = 4;
-constexpr int kSmemLevel = 64;    // boxes per level buffer kept in shared memory by the warp-level pass
+constexpr int kSmemLevel = 192;
+constexpr int kWideLevel = 10; // levels with at least this many boxes are evaluated box-parallel, narrower ones corner-parallel    // boxes per level buffer kept in shared memory by the warp-level pass
 
 // group helpers: W = 32 (one warp per pair) or W = 1 (one thread per pair, no cross-lane traffic)
 template <int W> DEV void group_min_key(Key3& k, unsigned& pay, double& aux) { if (W == 32) warp_min_key(k, pay, aux); }
@@ -633,6 +634,44 @@ __device__ int ti_root_finder_cp(const TiPair& P, const double* tol, double co_t
         unsigned p1 = 0, p2 = 0;
         double a1max = 0.0;
         int visited = 0;
+        if (n >= kWideLevel) {
+            // wide level: one box per lane (box-parallel), K1/K2 by warp min-reduction over the keys
+            for (int base = 0; base < n; base += 32) {
+                const int i = base + lane;
+                Key3 mk1 = { INF, INF, INF }, mk2 = { INF, INF, INF };
+                unsigned mp1 = 0, mp2 = 0;
+                double ma1 = 0.0, ma2 = 0.0;
+                bool vis = false;
+                if (i < n) {
+                    const DBox b = cur[i];
+                    const int tk = b.kk & 0xff, uk = (b.kk >> 8) & 0xff, vk = (b.kk >> 16) & 0xff;
+                    const double tlo = dy_lo(b.tn, tk);
+                    unsigned flags = 0;
+                    if (tlo < toi_skip) {
+                        vis = true;
+                        bool box_in;
+                        double tt[3];
+                        if (origin_in_box<VF>(P, b, err, ms, box_in, tt)) {
+                            flags = F_ZERO;
+                            const bool tol_cond = tt[0] <= co_tol && tt[1] <= co_tol && tt[2] <= co_tol;
+                            const bool cond1 = pow2neg(tk) <= tol[0] && pow2neg(uk) <= tol[1] && pow2neg(vk) <= tol[2];
+                            const Key3 key = { tlo, dy_lo(b.un, uk), dy_lo(b.vn, vk) };
+                            mk1 = key;
+                            mp1 = (tol_cond || box_in || cond1) ? 1u : 0u;
+                            ma1 = fmax(fmax(tt[0], tt[1]), tt[2]);
+                            if (mp1) { mk2 = key; mp2 = cond1 ? 1u : 0u; }
+                        }
+                    }
+                    cur[i].kk = (b.kk & 0x00ffffffu) | flags;
+                }
+                visited += __popc(__ballot_sync(0xffffffffu, vis));
+                warp_min_key(mk1, mp1, ma1);
+                warp_min_key(mk2, mp2, ma2);
+                if (key_less(mk1, k1)) { k1 = mk1; p1 = mp1; a1max = ma1; }
+                if (key_less(mk2, k2)) { k2 = mk2; p2 = mp2; }
+            }
+        }
+        else
         for (int bI = 0; bI < n; ++bI) {
             const DBox b = cur[bI];
             const int tk = b.kk & 0xff, uk = (b.kk >> 8) & 0xff, vk = (b.kk >> 16) & 0xff;
@@ -700,6 +739,73 @@ __device__ int ti_root_finder_cp(const TiPair& P, const double* tol, double co_t
             use_skip = true;
         }
         int nn = 0;
+        if (n >= kWideLevel) {
+            bool over = false, deep = false;
+            for (int base = 0; base < n; base += 32) {
+                const int i = base + lane;
+                int nchild = 0;
+                DBox c0, c1;
+                if (i < n) {
+                    const DBox b = cur[i];
+                    if (b.kk & F_ZERO) {
+                        const int tk = b.kk & 0xff, uk = (b.kk >> 8) & 0xff, vk = (b.kk >> 16) & 0xff;
+                        const Key3 key = { dy_lo(b.tn, tk), dy_lo(b.un, uk), dy_lo(b.vn, vk) };
+                        if (!has_k2 || key_less(key, k2)) {
+                            const double w[3] = { pow2neg(tk), pow2neg(uk), pow2neg(vk) };
+                            int split = -1;
+                            double best = -1.0;
+#pragma unroll
+                            for (int d = 0; d < 3; ++d)
+                                if (w[d] > tol[d]) {
+                                    const double r = w[d] / tol[d];
+                                    if (r > best) { best = r; split = d; }
+                                }
+                            const int pk = split == 0 ? tk : (split == 1 ? uk : vk);
+                            if (split < 0 || pk >= 60) deep = true;
+                            else {
+                                const unsigned long long pn = split == 0 ? b.tn : (split == 1 ? b.un : b.vn);
+#pragma unroll
+                                for (int half = 0; half < 2; ++half) {
+                                    const unsigned long long hn = 2 * pn + half;
+                                    const int hk = pk + 1;
+                                    bool keep = true;
+                                    if (split == 0) { if (check_t) keep = !(dy_hi(hn, hk) < 0.0 || dy_lo(hn, hk) > max_t); }
+                                    else if (VF) keep = (split == 1) ? sum_le_1(hn, hk, b.vn, vk) : sum_le_1(hn, hk, b.un, uk);
+                                    if (keep) {
+                                        DBox ch = b;
+                                        ch.kk &= 0x00ffffffu;
+                                        if (split == 0) { ch.tn = hn; ch.kk = (ch.kk & ~0xffu) | (unsigned)hk; }
+                                        else if (split == 1) { ch.un = hn; ch.kk = (ch.kk & ~0xff00u) | ((unsigned)hk << 8); }
+                                        else { ch.vn = hn; ch.kk = (ch.kk & ~0xff0000u) | ((unsigned)hk << 16); }
+                                        if (nchild == 0) c0 = ch;
+                                        else c1 = ch;
+                                        ++nchild;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                int incl, total;
+                group_scan<32>(nchild, lane, incl, total);
+                const int off = nn + incl - nchild;
+                if (nn + total > kSmemLevel) over = true;
+                else {
+                    if (nchild > 0) nxt[off] = c0;
+                    if (nchild > 1) nxt[off + 1] = c1;
+                }
+                nn += total;
+                if (__any_sync(0xffffffffu, over || deep)) break;
+            }
+            if (__any_sync(0xffffffffu, deep)) {
+                if (lane == 0) atomicAdd(warn, 1);
+                toi = temp_toi;
+                out_tol = temp_out_tol;
+                return 1;
+            }
+            if (__any_sync(0xffffffffu, over)) return -1;
+        }
+        else
         for (int bI = 0; bI < n; ++bI) {
             const DBox b = cur[bI];
             if (!(b.kk & F_ZERO)) continue;
