@@ -309,6 +309,7 @@ struct NarrowArgs {
     double err_vf[3], err_ee[3];
     double tol, max_t;
     int max_itr;
+    const unsigned long long* best; // running device-wide minimum (ordered-uint image): boxes starting at or after it cannot lower the result
 };
 
 __global__ void __launch_bounds__(128) k_ti_stage1(NarrowArgs a, unsigned* __restrict__ survivors, unsigned* __restrict__ nSurv, int* __restrict__ zero_flag)
@@ -408,7 +409,8 @@ template <int W> DEV void group_scan(int v, int lane, int& incl, int& total)
 // result codes of the root finder: 0 no collision, 1 collision (toi set), 2 deferred (W = 1 only: level buffer too small)
 template <bool VF, int W>
 __device__ int ti_root_finder(const TiPair& P, const double* tol, double co_tol, double max_t, const double* err, double ms, int max_itr, DBox* bufA,
-    DBox* bufB, int gcap, int lane, double& toi, double& out_tol, int* __restrict__ warn, DBox* sA = nullptr, DBox* sB = nullptr, long long thread_budget = 0)
+    DBox* bufB, int gcap, int lane, double& toi, double& out_tol, int* __restrict__ warn, DBox* sA = nullptr, DBox* sB = nullptr, long long thread_budget = 0,
+    const unsigned long long* best = nullptr)
 {
     const bool check_t = (max_t != 1.0);
     const double INF = __longlong_as_double(0x7ff0000000000000ll);
@@ -429,6 +431,15 @@ __device__ int ti_root_finder(const TiPair& P, const double* tol, double co_tol,
     out_tol = co_tol;
     toi = INF;
     while (n > 0) {
+        // exact pruning against the running device-wide minimum: a box that starts at t_lo >= max(best, 1e-6) can only yield a time of
+        // impact >= best (and no 0.8-rescaled retry, which needs toi < 1e-6), so dropping it cannot change the final min over pairs
+        double t_prune = INF;
+        if (best) {
+            unsigned long long bo = 0;
+            if (W == 1 || lane == 0) bo = *reinterpret_cast<const volatile unsigned long long*>(best);
+            if (W == 32) bo = __shfl_sync(0xffffffffu, bo, 0);
+            t_prune = fmax(ord_to_dbl(bo), 1e-6);
+        }
         // ---- pass 1: evaluate, find K1 (first box containing the origin) and K2 (first terminal box) ----------
         Key3 k1 = { INF, INF, INF }, k2 = { INF, INF, INF };
         unsigned p1 = 0, p2 = 0; // payload bit0: flagged (K1) / cond1 (K2)
@@ -445,7 +456,7 @@ __device__ int ti_root_finder(const TiPair& P, const double* tol, double co_tol,
                 const int tk = b.kk & 0xff, uk = (b.kk >> 8) & 0xff, vk = (b.kk >> 16) & 0xff;
                 const double tlo = dy_lo(b.tn, tk);
                 unsigned flags = 0;
-                if (tlo < toi_skip) {
+                if (tlo < toi_skip && tlo < t_prune) {
                     vis = true;
                     bool box_in;
                     double tt[3];
@@ -604,7 +615,7 @@ __device__ int ti_root_finder(const TiPair& P, const double* tol, double co_tol,
 // box-parallel variant.  Returns -1 when a level outgrows the shared-memory buffer (the caller restarts with the box-parallel variant).
 template <bool VF>
 __device__ int ti_root_finder_cp(const TiPair& P, const double* tol, double co_tol, double max_t, const double* err, double ms, int max_itr, DBox* sA, DBox* sB,
-    int lane, double& toi, double& out_tol, int* __restrict__ warn)
+    int lane, double& toi, double& out_tol, int* __restrict__ warn, const unsigned long long* best)
 {
     const bool check_t = (max_t != 1.0);
     const double INF = __longlong_as_double(0x7ff0000000000000ll);
@@ -634,6 +645,13 @@ __device__ int ti_root_finder_cp(const TiPair& P, const double* tol, double co_t
         unsigned p1 = 0, p2 = 0;
         double a1max = 0.0;
         int visited = 0;
+        double t_prune = INF; // exact pruning against the running device-wide minimum (see ti_root_finder)
+        if (best) {
+            unsigned long long bo = 0;
+            if (lane == 0) bo = *reinterpret_cast<const volatile unsigned long long*>(best);
+            bo = __shfl_sync(0xffffffffu, bo, 0);
+            t_prune = fmax(ord_to_dbl(bo), 1e-6);
+        }
         if (n >= kWideLevel) {
             // wide level: one box per lane (box-parallel), K1/K2 by warp min-reduction over the keys
             for (int base = 0; base < n; base += 32) {
@@ -647,7 +665,7 @@ __device__ int ti_root_finder_cp(const TiPair& P, const double* tol, double co_t
                     const int tk = b.kk & 0xff, uk = (b.kk >> 8) & 0xff, vk = (b.kk >> 16) & 0xff;
                     const double tlo = dy_lo(b.tn, tk);
                     unsigned flags = 0;
-                    if (tlo < toi_skip) {
+                    if (tlo < toi_skip && tlo < t_prune) {
                         vis = true;
                         bool box_in;
                         double tt[3];
@@ -677,7 +695,7 @@ __device__ int ti_root_finder_cp(const TiPair& P, const double* tol, double co_t
             const int tk = b.kk & 0xff, uk = (b.kk >> 8) & 0xff, vk = (b.kk >> 16) & 0xff;
             const double tlo = dy_lo(b.tn, tk);
             unsigned flags = 0;
-            if (tlo < toi_skip) {
+            if (tlo < toi_skip && tlo < t_prune) {
                 ++visited;
                 const double tv = ci ? dy_hi(b.tn, tk) : tlo;
                 const double uv = cj ? dy_hi(b.un, uk) : dy_lo(b.un, uk);
@@ -859,7 +877,7 @@ __device__ int ti_root_finder_cp(const TiPair& P, const double* tol, double co_t
 // vertexFaceCCD_double / edgeEdgeCCD_double including the no_zero_toi refinement loop; returns 0 / 1 / 2 (deferred)
 template <bool VF, int W>
 __device__ int ti_ccd(const TiPair& P, const double* err, double ms, double tolerance, double t_max, int max_itr, DBox* bufA, DBox* bufB, int cap, int lane,
-    double& toi, int* __restrict__ warn, DBox* sA = nullptr, DBox* sB = nullptr, long long thread_budget = 0)
+    double& toi, int* __restrict__ warn, DBox* sA = nullptr, DBox* sB = nullptr, long long thread_budget = 0, const unsigned long long* best = nullptr)
 {
     double tolerance_in = tolerance, ms_in = ms, out_tol = tolerance;
     bool is_impacting = false, tmp = false;
@@ -869,10 +887,10 @@ __device__ int ti_ccd(const TiPair& P, const double* err, double ms, double tole
         width_tolerances<VF>(P, tolerance_in, tol);
         int rc;
         if (W == 32 && sA) {
-            rc = ti_root_finder_cp<VF>(P, tol, tolerance_in, t_max, err, ms_in, max_itr, sA, sB, lane, toi, out_tol, warn);
-            if (rc == -1) rc = ti_root_finder<VF, W>(P, tol, tolerance_in, t_max, err, ms_in, max_itr, bufA, bufB, cap, lane, toi, out_tol, warn, nullptr, nullptr, 0);
+            rc = ti_root_finder_cp<VF>(P, tol, tolerance_in, t_max, err, ms_in, max_itr, sA, sB, lane, toi, out_tol, warn, best);
+            if (rc == -1) rc = ti_root_finder<VF, W>(P, tol, tolerance_in, t_max, err, ms_in, max_itr, bufA, bufB, cap, lane, toi, out_tol, warn, nullptr, nullptr, 0, best);
         }
-        else rc = ti_root_finder<VF, W>(P, tol, tolerance_in, t_max, err, ms_in, max_itr, bufA, bufB, cap, lane, toi, out_tol, warn, sA, sB, thread_budget);
+        else rc = ti_root_finder<VF, W>(P, tol, tolerance_in, t_max, err, ms_in, max_itr, bufA, bufB, cap, lane, toi, out_tol, warn, sA, sB, thread_budget, best);
         if (rc == 2) return 2;
         tmp = rc == 1;
         if (iter == 0) is_impacting = tmp;
@@ -894,12 +912,12 @@ __device__ int pair_ccd(bool vf, const TiPair& P, const NarrowArgs& a, DBox* buf
 {
     const double d = pair_distance_sqrt(vf, P);
     const double ms = fmin(0.2 * d, 1e-6);
-    int hit = vf ? ti_ccd<true, W>(P, a.err_vf, ms, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn, sA, sB, thread_budget)
-                 : ti_ccd<false, W>(P, a.err_ee, ms, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn, sA, sB, thread_budget);
+    int hit = vf ? ti_ccd<true, W>(P, a.err_vf, ms, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn, sA, sB, thread_budget, a.best)
+                 : ti_ccd<false, W>(P, a.err_ee, ms, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn, sA, sB, thread_budget, a.best);
     if (hit == 2) return 2;
     if (hit && toi < 1e-6) { // :759-781
-        hit = vf ? ti_ccd<true, W>(P, a.err_vf, 0.0, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn, sA, sB, thread_budget)
-                 : ti_ccd<false, W>(P, a.err_ee, 0.0, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn, sA, sB, thread_budget);
+        hit = vf ? ti_ccd<true, W>(P, a.err_vf, 0.0, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn, sA, sB, thread_budget, a.best)
+                 : ti_ccd<false, W>(P, a.err_ee, 0.0, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn, sA, sB, thread_budget, a.best);
         if (hit == 2) return 2;
         if (hit) toi *= 0.8;
     }
@@ -1026,6 +1044,7 @@ int ccd_narrow(ipcgpu_ctx* ctx, const int2* cand, unsigned long long nCand, doub
     a.tol = tol;
     a.max_t = *alpha_inout; // canonical semantics: every pair sees the step on entry
     a.max_itr = 1000000;    // TIGHT_INCLUSION_MAX_ITER (CCDUtils.hpp:14)
+    a.best = ctx->min_ord.p;
     unsigned* nSurv = reinterpret_cast<unsigned*>(w.counters.p);
     unsigned* work = nSurv + 1;
     int* flags = w.counters.p + 2; // [0] zero distance, [1] warnings, [2] spare
