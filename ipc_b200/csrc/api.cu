@@ -90,26 +90,28 @@ static int build_maps(ipcgpu_ctx* ctx)
         ctx->err = "upload of incidence map failed";
         return IPCGPU_ERR_CUDA;
     }
-    // slots: (v<=u) pairs; contributions (key, src) sorted by key then tet (src ascending == tet ascending)
-    REQUIRE((uint64_t)nL * 78ull < 0xffffffffull, IPCGPU_ERR_CAPACITY, "local tet count too large for 32-bit block offsets");
+    // slots: (v<=u) pairs; contributions (key, src) sorted by key then tet
+    REQUIRE(((uint64_t)nL + 64ull) * 78ull < 0xffffffffull, IPCGPU_ERR_CAPACITY, "local tet count too large for 32-bit block offsets");
     struct KS {
         uint64_t key;
         unsigned src;
+        unsigned tet;
     };
     std::vector<KS> ks((size_t)10 * nL);
     static const int pa[6] = { 0, 0, 0, 1, 1, 2 }, pb[6] = { 1, 2, 3, 2, 3, 3 };
     for (int t = tb; t < te; ++t) {
         int v[4];
         for (int k = 0; k < 4; ++k) v[k] = T[(size_t)k * nT + t];
-        const unsigned base = (unsigned)(t - tb) * 78u;
+        // tile-major block addresses (elastic.cu): (t/64)*64*78 + o*64 + (t%64)*len
+        const unsigned tl = (unsigned)(t - tb), tile_base = (tl / 64u) * (64u * 78u), tin = tl % 64u;
         KS* o = &ks[(size_t)10 * (t - tb)];
-        for (int a = 0; a < 4; ++a) o[a] = { ((uint64_t)v[a] << 32) | (uint32_t)v[a], base + 6u * a };
+        for (int a = 0; a < 4; ++a) o[a] = { ((uint64_t)v[a] << 32) | (uint32_t)v[a], tile_base + 6u * a * 64u + tin * 6u, tl };
         for (int q = 0; q < 6; ++q) {
             int lo = std::min(v[pa[q]], v[pb[q]]), hi = std::max(v[pa[q]], v[pb[q]]);
-            o[4 + q] = { ((uint64_t)lo << 32) | (uint32_t)hi, base + 24u + 9u * q };
+            o[4 + q] = { ((uint64_t)lo << 32) | (uint32_t)hi, tile_base + (24u + 9u * q) * 64u + tin * 9u, tl };
         }
     }
-    std::sort(ks.begin(), ks.end(), [](const KS& a, const KS& b) { return a.key < b.key || (a.key == b.key && a.src < b.src); });
+    std::sort(ks.begin(), ks.end(), [](const KS& a, const KS& b) { return a.key < b.key || (a.key == b.key && (a.tet < b.tet || (a.tet == b.tet && a.src < b.src))); });
     std::vector<int> sv, su, cptr;
     std::vector<unsigned> csrc(ks.size());
     for (size_t i = 0; i < ks.size(); ++i) {
@@ -127,7 +129,7 @@ static int build_maps(ipcgpu_ctx* ctx)
         && ctx->slot_off.reserve((size_t)3 * std::max(1, ctx->nSlots));
     REQUIRE(ok, IPCGPU_ERR_CUDA, "upload of Hessian scatter map failed");
     ALLOC(ctx->gcont, (size_t)12 * std::max(1, nL));
-    ALLOC(ctx->hblk, (size_t)78 * std::max(1, nL));
+    ALLOC(ctx->hblk, (size_t)78 * 64 * ((size_t)(std::max(1, nL) + 63) / 64));
     ALLOC(ctx->partials, (size_t)std::max(1, elastic_energy_blocks(nL)) + 8);
     CK(cudaStreamSynchronize(ctx->stream)); // host vectors go out of scope
     ctx->maps_ready = true;
@@ -818,7 +820,7 @@ static int buf_info(ipcgpu_ctx* ctx, int which, double** p, uint64_t* n)
     case IPCGPU_BUF_GRADIENT: *p = ctx->g.p; *n = (uint64_t)3 * ctx->nV; return 0;
     case IPCGPU_BUF_CSR_VALUES: *p = ctx->a.p; *n = (uint64_t)ctx->nnz; return 0;
     case IPCGPU_BUF_ENERGY_PER_TET: *p = ctx->e_per_tet.p; *n = (uint64_t)ctx->nT; return 0;
-    case IPCGPU_BUF_TET_HESSIANS: *p = ctx->hblk.p; *n = 78 * nL; return 0;
+    case IPCGPU_BUF_TET_HESSIANS: *p = ctx->hblk.p; *n = 78 * 64 * ((nL + 63) / 64); return 0; /* tile-major, see elastic.cu */
     case IPCGPU_BUF_TET_GRADIENTS: *p = ctx->gcont.p; *n = 12 * nL; return 0;
     case IPCGPU_BUF_INVERSION_STEPS: *p = ctx->inv_steps.p; *n = (uint64_t)ctx->nT; return 0;
     default: return 1;

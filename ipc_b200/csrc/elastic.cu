@@ -118,21 +118,33 @@ DEV void tma_store_tile(void* gdst, const void* ssrc, unsigned bytes)
     asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
 }
 
+// Output layout of the per-tet Hessian blocks ("tile-major"): tets are grouped in tiles of kHessTile = 64; inside a tile the
+// 10 block slots follow each other (4 diagonal blocks of 6 upper scalars, then the 6 off-diagonal 3x3 blocks of the vertex pairs
+// (0,1)(0,2)(0,3)(1,2)(1,3)(2,3)), and inside a slot the 64 tets are contiguous:
+//     address(t, slot offset o, entry q) = (t/64)*64*78 + o*64 + (t%64)*len(o) + q,   o in {0,6,12,18,24,33,...,69}, len = 6 or 9.
+// Every (tile, slot) region is therefore one contiguous 3 KB / 4.5 KB run that a CTA ships with a single TMA bulk store as soon
+// as the slot is computed; only two such regions live in shared memory at a time (9 KB instead of 46 KB per CTA), which lifts the
+// shared-memory occupancy limit of the first version of this kernel.
 template <int ENERGY, bool NEED_G, bool NEED_H>
 __global__ void __launch_bounds__(kHessTile) k_elastic_grad_hess(ElasticArgs p, double coef, int projectSPD,
-    double* __restrict__ gcont /* 12 per LOCAL tet */, double* __restrict__ hblk /* 78 per LOCAL tet */)
+    double* __restrict__ gcont /* 12 per LOCAL tet */, double* __restrict__ hblk /* tile-major, 78 per LOCAL tet */)
 {
     extern __shared__ __align__(128) double smem[];
-    double* sH = smem;                                   // kHessTile * 78
-    double* sG = smem + (NEED_H ? kHessTile * 78 : 0);   // kHessTile * 12
+    double* sHb[2] = { smem, smem + kHessTile * 9 };          // two slot buffers (ping-pong)
+    double* sG = smem + (NEED_H ? 2 * kHessTile * 9 : 0);     // kHessTile * 12
     const int nLocal = p.t_end - p.t_begin;
     const int tile0 = blockIdx.x * kHessTile;
     const int t = tile0 + threadIdx.x;
-    if (t < nLocal) {
+    const bool active = t < nLocal;
+    const int ntile = min(kHessTile, nLocal - tile0);
+    TetIn in;
+    M3 U;
+    double W[4][3];
+    double a00 = 0, a01 = 0, a02 = 0, a11 = 0, a12 = 0, a22 = 0, d01 = 0, d10 = 0, o01 = 0, d12 = 0, d21 = 0, o12 = 0, d20 = 0, d02 = 0, o02 = 0;
+    if (active) {
         const int tt = p.t_begin + t;
-        TetIn in;
         load_tet(p, tt, in);
-        M3 F, U, V;
+        M3 F, V;
         double s[3];
         def_grad(in, F);
         svd3<true>(F, U, s, V);
@@ -181,12 +193,11 @@ __global__ void __launch_bounds__(kHessTile) k_elastic_grad_hess(ElasticArgs p, 
             }
             // weights in (k,l) index space   [Energy.cpp:497-528; note the transposed (2,0) block]
             //   d[k][l] = M(kl,kl), o[k][m] = M(km,mk)
-            const double a00 = w * sd.A[0], a01 = w * sd.A[1], a02 = w * sd.A[2], a11 = w * sd.A[3], a12 = w * sd.A[4], a22 = w * sd.A[5];
-            const double d01 = w * bd0[0], d10 = w * bd1[0], o01 = w * bo[0];
-            const double d12 = w * bd0[1], d21 = w * bd1[1], o12 = w * bo[1];
-            const double d20 = w * bd0[2], d02 = w * bd1[2], o02 = w * bo[2];
+            a00 = w * sd.A[0]; a01 = w * sd.A[1]; a02 = w * sd.A[2]; a11 = w * sd.A[3]; a12 = w * sd.A[4]; a22 = w * sd.A[5];
+            d01 = w * bd0[0]; d10 = w * bd1[0]; o01 = w * bo[0];
+            d12 = w * bd0[1]; d21 = w * bd1[1]; o12 = w * bo[1];
+            d20 = w * bd0[2]; d02 = w * bd1[2]; o02 = w * bo[2];
             // W = G V
-            double W[4][3];
 #pragma unroll
             for (int l = 0; l < 3; ++l) {
                 double s0 = 0.0;
@@ -198,12 +209,20 @@ __global__ void __launch_bounds__(kHessTile) k_elastic_grad_hess(ElasticArgs p, 
                 }
                 W[0][l] = s0;
             }
-            double* out = sH + threadIdx.x * 78;
-            int off = 24;
+        }
+    }
+    if (NEED_H) {
+        int slot = 0;
+        int offd = 24; // old-style offset of the next off-diagonal block
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
+        for (int a = 0; a < 4; ++a) {
 #pragma unroll
-                for (int b = a; b < 4; ++b) {
+            for (int b = a; b < 4; ++b) {
+                const int len = (a == b) ? 6 : 9;
+                const int o = (a == b) ? 6 * a : offd;
+                if (a != b) offd += 9;
+                double* buf = sHb[slot & 1];
+                if (active) {
                     const double wa0 = W[a][0], wa1 = W[a][1], wa2 = W[a][2];
                     const double wb0 = W[b][0], wb1 = W[b][1], wb2 = W[b][2];
                     // Ht (U-frame) 3x3
@@ -223,37 +242,41 @@ __global__ void __launch_bounds__(kHessTile) k_elastic_grad_hess(ElasticArgs p, 
                     for (int i = 0; i < 3; ++i)
 #pragma unroll
                         for (int m = 0; m < 3; ++m) Tm(i, m) = U(i, 0) * Ht(0, m) + U(i, 1) * Ht(1, m) + U(i, 2) * Ht(2, m);
+                    double* oo = buf + threadIdx.x * len;
                     if (a == b) {
-                        double* o = out + 6 * a;
                         int q = 0;
 #pragma unroll
                         for (int i = 0; i < 3; ++i)
 #pragma unroll
-                            for (int r = i; r < 3; ++r) o[q++] = Tm(i, 0) * U(r, 0) + Tm(i, 1) * U(r, 1) + Tm(i, 2) * U(r, 2);
+                            for (int r = i; r < 3; ++r) oo[q++] = Tm(i, 0) * U(r, 0) + Tm(i, 1) * U(r, 1) + Tm(i, 2) * U(r, 2);
                     }
                     else {
-                        double* o = out + off;
-                        off += 9;
                         const bool flip = in.v[a] > in.v[b]; // rows must belong to the smaller global vertex
 #pragma unroll
                         for (int i = 0; i < 3; ++i)
 #pragma unroll
                             for (int r = 0; r < 3; ++r) {
                                 double h = Tm(i, 0) * U(r, 0) + Tm(i, 1) * U(r, 1) + Tm(i, 2) * U(r, 2);
-                                o[flip ? (3 * r + i) : (3 * i + r)] = h;
+                                oo[flip ? (3 * r + i) : (3 * i + r)] = h;
                             }
                     }
                 }
+                // ship this slot: generic-proxy writes -> async-proxy fence -> CTA barrier -> one elected TMA store
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    tma_store_tile(hblk + (size_t)blockIdx.x * (kHessTile * 78) + (size_t)o * kHessTile, buf, (unsigned)ntile * (unsigned)len * 8u);
+                    asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory"); // the other buffer's store has been read out
+                }
+                __syncthreads();
+                ++slot;
             }
         }
     }
-    // ship the tile: generic-proxy writes -> async proxy fence -> CTA barrier -> one elected TMA store
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     __syncthreads();
     if (threadIdx.x == 0) {
-        const int n = min(kHessTile, nLocal - tile0);
-        if (NEED_H) tma_store_tile(hblk + (size_t)tile0 * 78, sH, (unsigned)n * 78u * 8u);
-        if (NEED_G) tma_store_tile(gcont + (size_t)tile0 * 12, sG, (unsigned)n * 12u * 8u);
+        if (NEED_G) tma_store_tile(gcont + (size_t)tile0 * 12, sG, (unsigned)ntile * 12u * 8u);
         asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
     }
 }
@@ -293,68 +316,37 @@ __global__ void __launch_bounds__(256) k_gather_gradient(int nV, const int* __re
 // one thread per block-slot (vertex pair v<=u of the mesh topology); contributions are summed in
 // ascending tet order (the reference's vFLoc order), then written to the three CSR rows.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_assemble_csr(int nSlots, const int* __restrict__ slot_v, const int* __restrict__ slot_u,
+__global__ void __launch_bounds__(288) k_assemble_csr(int nSlots, const int* __restrict__ slot_v, const int* __restrict__ slot_u,
     const int* __restrict__ slot_off /* 3 per slot */, const int* __restrict__ con_ptr, const unsigned* __restrict__ con_src,
     const double* __restrict__ hblk, const uint8_t* __restrict__ dbc, int projectDBC, const double* __restrict__ mass,
     int accumulate, double* __restrict__ a)
 {
-    const int sIdx = blockIdx.x * blockDim.x + threadIdx.x;
+    // 9 consecutive threads per slot: thread q sums entry q of every contributing block (ascending tet order: the reference's
+    // vFLoc order, so the sum is bitwise reproducible); the 9 loads of one block are one contiguous 72-byte run
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int sIdx = (int)(tid / 9), q = (int)(tid - 9ll * sIdx);
     if (sIdx >= nSlots) return;
     const int v = slot_v[sIdx], u = slot_u[sIdx];
-    const int o0 = slot_off[3 * sIdx], o1 = slot_off[3 * sIdx + 1], o2 = slot_off[3 * sIdx + 2];
+    const bool diag = (v == u);
+    if (diag && q >= 6) return;
     const bool pv = dbc && (dbc[v] == 1 || (dbc[v] == 2 && projectDBC));
     const bool pu = dbc && (dbc[u] == 1 || (dbc[u] == 2 && projectDBC));
-    const int b = con_ptr[sIdx], e = con_ptr[sIdx + 1];
-    if (v == u) {
-        double h[6] = { 0, 0, 0, 0, 0, 0 };
-        if (pv) { // projected Dirichlet vertex: block dropped here, identity written by k_diag_mass_dbc (IglUtils.hpp:44-53)
-        }
-        else {
-            for (int q = b; q < e; ++q) {
-                const double* s = hblk + __ldg(con_src + q);
-#pragma unroll
-                for (int k = 0; k < 6; ++k) h[k] += s[k];
-            }
-        }
-        if (accumulate && !pv) {
-            a[o0] += h[0]; a[o0 + 1] += h[1]; a[o0 + 2] += h[2];
-            a[o1] += h[3]; a[o1 + 1] += h[4];
-            a[o2] += h[5];
-        }
-        else {
-            a[o0] = h[0]; a[o0 + 1] = h[1]; a[o0 + 2] = h[2];
-            a[o1] = h[3]; a[o1 + 1] = h[4];
-            a[o2] = h[5];
-        }
+    const bool dropped = pv || pu; // projected Dirichlet vertex: block dropped; the identity is written by k_diag_mass_dbc
+    double h = 0.0;
+    if (!dropped) {
+        const int b = con_ptr[sIdx], e = con_ptr[sIdx + 1];
+        for (int k = b; k < e; ++k) h += hblk[__ldg(con_src + k) + q];
     }
-    else {
-        double h[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
-        if (!pv && !pu) {
-            for (int q = b; q < e; ++q) {
-                const double* s = hblk + __ldg(con_src + q);
-#pragma unroll
-                for (int k = 0; k < 9; ++k) h[k] += s[k];
-            }
-        }
-        if (accumulate) {
-            if (!pv && !pu) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    a[o0 + c] += h[c];
-                    a[o1 + c] += h[3 + c];
-                    a[o2 + c] += h[6 + c];
-                }
-            }
-        }
-        else {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                a[o0 + c] = h[c];
-                a[o1 + c] = h[3 + c];
-                a[o2 + c] = h[6 + c];
-            }
-        }
+    int r, c;
+    if (diag) { r = (q < 3) ? 0 : (q < 5 ? 1 : 2); c = (q < 3) ? q : (q < 5 ? q - 3 : 0); }
+    else { r = q / 3; c = q - 3 * r; }
+    const int o = slot_off[3 * sIdx + r] + c;
+    if (accumulate) {
+        if (!dropped) a[o] += h;
+        else if (diag) a[o] = 0.0;
     }
+    else a[o] = h;
+    (void)mass;
 }
 
 // per-vertex diagonal terms of computePrecondMtr (Optimizer.cpp:3638-3668): mass on free vertices, identity on projected
@@ -554,7 +546,7 @@ static void launch_gh(const ElasticArgs& p, double coef, int projectSPD, double*
     const int n = p.t_end - p.t_begin;
     if (n <= 0) return;
     const int nb = (n + kHessTile - 1) / kHessTile;
-    const size_t smem = (size_t)kHessTile * 8 * ((H ? 78 : 0) + (G ? 12 : 0));
+    const size_t smem = (size_t)kHessTile * 8 * ((H ? 18 : 0) + (G ? 12 : 0));
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(k_elastic_grad_hess<ENERGY, G, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -585,7 +577,7 @@ void assemble_csr(int nSlots, const int* slot_v, const int* slot_u, const int* s
     const double* hblk, const uint8_t* dbc, int projectDBC, const double* mass, int accumulate, double* a, cudaStream_t st)
 {
     if (nSlots <= 0) return;
-    k_assemble_csr<<<(nSlots + 255) / 256, 256, 0, st>>>(nSlots, slot_v, slot_u, slot_off, con_ptr, con_src, hblk, dbc, projectDBC, mass, accumulate, a);
+    k_assemble_csr<<<(int)(((long long)nSlots * 9 + 287) / 288), 288, 0, st>>>(nSlots, slot_v, slot_u, slot_off, con_ptr, con_src, hblk, dbc, projectDBC, mass, accumulate, a);
 }
 void diag_mass_dbc(int nV, const int* ia, int base, const uint8_t* dbc, int projectDBC, const double* mass, double* a, cudaStream_t st)
 {

@@ -332,3 +332,17 @@ class Context:
         out = np.empty(int(count))
         self._ck(self.lib.ipcgpu_download(self.h, which, _d(out), int(count)))
         return out
+
+
+def untile_hessians(raw, nT):
+    """BUF_TET_HESSIANS is tile-major (64-tet tiles, slot-major inside a tile; csrc/elastic.cu). Returns the (nT, 78) per-tet view:
+    4 diagonal blocks (6 upper scalars) then the 6 oriented off-diagonal 3x3 blocks."""
+    out = np.empty((nT, 78))
+    ntile = (nT + 63) // 64
+    r = np.asarray(raw).reshape(ntile, 64 * 78)
+    t = np.arange(nT)
+    tile, tin = t // 64, t % 64
+    for o, ln in [(0, 6), (6, 6), (12, 6), (18, 6)] + [(24 + 9 * q, 9) for q in range(6)]:
+        for q in range(ln):
+            out[:, o + q] = r[tile, o * 64 + tin * ln + q]
+    return out

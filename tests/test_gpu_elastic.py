@@ -60,7 +60,7 @@ def test_energy_gradient_hessian_parity(gpu_ctx, et, inverted):
         H_ref = o.hessian_blocks(coef, projectSPD)
         a = np.zeros(ja.size)
         gpu_ctx.elastic_hessian(coef, 1, projectSPD, 1, a)
-        h78 = gpu_ctx.download(L.BUF_TET_HESSIANS, 78 * m.nT).reshape(m.nT, 78)
+        h78 = L.untile_hessians(gpu_ctx.download(L.BUF_TET_HESSIANS, 78 * 64 * ((m.nT + 63) // 64)), m.nT)
         worst = 0.0
         for t in range(m.nT):
             worst = max(worst, np.abs(orc.blocks78_to_dense(h78[t], m.T[t]) - H_ref[t]).max() / np.abs(H_ref[t]).max())
@@ -152,7 +152,7 @@ def test_large_mesh_properties(gpu_ctx):
     gpu_ctx.set_state(m.V_soa)
     a = np.zeros(ja.size)
     gpu_ctx.elastic_hessian(coef, 1, 1, 0, a)
-    h78 = gpu_ctx.download(L.BUF_TET_HESSIANS, 78 * m.nT).reshape(m.nT, 78)
+    h78 = L.untile_hessians(gpu_ctx.download(L.BUF_TET_HESSIANS, 78 * 64 * ((m.nT + 63) // 64)), m.nT)
     rng = np.random.default_rng(0)
     for t in rng.integers(0, m.nT, 200):
         H = orc.blocks78_to_dense(h78[t], m.T[t])
