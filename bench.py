@@ -213,6 +213,7 @@ def main():
     ctx.set_csr(ia, ja, 1)
     nnz = ja.size
     n_active, n_para, n_cand = len(mm), len(pa), len(cand)
+    ctx.set_contact_partition(1)  # timed steps: every rank builds and processes only its share of the contact sets
 
     # pinned host buffers for the e2e path
     hV = L.PinnedArray(3 * m.nV); hV.array[:] = m.V_soa

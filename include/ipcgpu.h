@@ -117,6 +117,11 @@ int ipcgpu_set_pair_capacity(ipcgpu_ctx* ctx, int capacity);
  * SpatialHash::build/query* (SpatialHash.hpp:46-229, 375-421) done on the device. The sets stay on the device (they feed the
  * barrier_* calls and the partial CCD); sizes are returned.  Output order is canonical: every list sorted lexicographically. */
 int ipcgpu_constraint_set(ipcgpu_ctx* ctx, double dHat, int getPTEE, int* nC, int* nPara, int* nCand);
+/* Multi-rank only. enable=1: ipcgpu_constraint_set issues only this rank's share of the PT/EE queries, so every rank holds a disjoint
+ * part of the sets (PP/PE multiplicities may be split between ranks, which leaves the summed E/g/H unchanged because
+ * makePD(c*M) = c*makePD(M) for c > 0); the counts returned are local.  enable=0 (default): every rank builds the whole set
+ * (what the host needs to extend the sparsity pattern) and the per-pair work is split by list index. */
+int ipcgpu_set_contact_partition(ipcgpu_ctx* ctx, int enable);
 /* copies of constraintSet (4 ints each, MMCVID encoding), paraEEMMCVIDSet (4), paraEEeIeJSet (2), cs_PTEE (2); any may be NULL */
 int ipcgpu_get_constraint_set(ipcgpu_ctx* ctx, int* mmcvid4, int* para4, int* para_eIeJ2, int* cand2);
 /* upload host-built sets instead (drop-in use of only the per-pair kernels) */

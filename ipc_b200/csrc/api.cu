@@ -556,7 +556,7 @@ int ipcgpu_ccd_partial_ti(ipcgpu_ctx* ctx, const double* p, double tol, const do
     if (rc) return rc;
     // CFL_FOR_CCD != 0: empty candidate list returns immediately (:700)
     const unsigned long long n = (unsigned long long)ctx->cw.nK;
-    const unsigned long long b = n * ctx->rank / ctx->nranks, e = n * (ctx->rank + 1) / ctx->nranks;
+    const unsigned long long b = ctx->lists_local ? 0 : n * ctx->rank / ctx->nranks, e = ctx->lists_local ? n : n * (ctx->rank + 1) / ctx->nranks;
     if ((rc = ccd_narrow(ctx, ctx->cw.cand.p + b, e - b, tol, err_vf, err_ee, alpha_inout))) return rc;
     return allreduce_min_step(ctx, alpha_inout);
 }
@@ -610,7 +610,15 @@ int ipcgpu_constraint_set(ipcgpu_ctx* ctx, double dHat, int getPTEE, int* nC, in
     REQUIRE(ctx->surface_ready, IPCGPU_ERR_STATE, "ipcgpu_set_surface first");
     REQUIRE(dHat > 0.0, IPCGPU_ERR_ARG, "dHat must be positive");
     CK(cudaSetDevice(ctx->device));
-    return contact_constraint_set(ctx, dHat, getPTEE, nC, nPara, nCand);
+    int rc = contact_constraint_set(ctx, dHat, getPTEE, nC, nPara, nCand);
+    ctx->lists_local = (rc == 0) && ctx->partition_contact && ctx->nranks > 1;
+    return rc;
+}
+
+int ipcgpu_set_contact_partition(ipcgpu_ctx* ctx, int enable)
+{
+    ctx->partition_contact = enable != 0;
+    return IPCGPU_OK;
 }
 
 int ipcgpu_get_constraint_set(ipcgpu_ctx* ctx, int* mm, int* para, int* para_e, int* cand)
@@ -636,6 +644,7 @@ int ipcgpu_set_constraint_set(ipcgpu_ctx* ctx, int nC, const int* mm, int nP, co
     if (nK) CK(cudaMemcpyAsync(w.cand.p, cand, (size_t)nK * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     w.nC = nC; w.nP = nP; w.nK = nK;
+    ctx->lists_local = false; // uploaded sets are the global ones
     return IPCGPU_OK;
 }
 
@@ -643,10 +652,11 @@ static BarrierArgs barrier_args(ipcgpu_ctx* ctx, double dHat, double kappa, int 
 {
     BarrierArgs p;
     p.nV = ctx->nV; p.V = ctx->V.p; p.Vrest = ctx->Vrest.p; p.dbc = ctx->has_dbc ? ctx->dbc.p : nullptr; p.SE = ctx->SE.p;
-    // every rank owns a contiguous share of the (replicated, canonically sorted) pair lists
+    // replicated lists: every rank owns a contiguous share of them; partitioned lists (ipcgpu_set_contact_partition): all local
     const long long nC = ctx->cw.nC, nP = ctx->cw.nP;
-    const int cb = (int)(nC * ctx->rank / ctx->nranks), ce = (int)(nC * (ctx->rank + 1) / ctx->nranks);
-    const int pb = (int)(nP * ctx->rank / ctx->nranks), pe = (int)(nP * (ctx->rank + 1) / ctx->nranks);
+    const bool local = ctx->lists_local;
+    const int cb = local ? 0 : (int)(nC * ctx->rank / ctx->nranks), ce = local ? (int)nC : (int)(nC * (ctx->rank + 1) / ctx->nranks);
+    const int pb = local ? 0 : (int)(nP * ctx->rank / ctx->nranks), pe = local ? (int)nP : (int)(nP * (ctx->rank + 1) / ctx->nranks);
     p.cs = ctx->cw.act.p + cb; p.nC = ce - cb; p.para = ctx->cw.para.p + pb; p.para_e = ctx->cw.para_e.p + pb; p.nP = pe - pb;
     p.dHat = dHat; p.kappa = kappa; p.projectDBC = projectDBC;
     p.ia = ctx->ia.p; p.ja = ctx->ja.p; p.base = ctx->index_base;

@@ -155,11 +155,12 @@ DEV bool is_dbc_v(const SurfArgs& s, int v) { return s.dbc && s.dbc[v] != 0; }
 DEV int codim_v(const SurfArgs& s, int v) { return s.vCoDim ? s.vCoDim[v] : 3; }
 
 // one WARP per surface vertex  (:2168-2260)
-__global__ void __launch_bounds__(128) k_query_pt(SurfArgs s, const Grid* __restrict__ gp, SortedGrid tg, double dHat, double radius, int wantCand, CsOut out)
+__global__ void __launch_bounds__(128) k_query_pt(SurfArgs s, const Grid* __restrict__ gp, SortedGrid tg, double dHat, double radius, int wantCand, int first, int last,
+    CsOut out)
 {
-    const int svI = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int svI = first + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
-    if (svI >= s.nSV) return;
+    if (svI >= last) return;
     const Grid g = *gp;
     const int vI = s.SVI[svI];
     const V3 p = load_vertex(s.V, s.nV, vI);
@@ -203,11 +204,11 @@ __global__ void __launch_bounds__(128) k_query_pt(SurfArgs s, const Grid* __rest
 
 // one WARP per surface edge eI; partners eJ > eI  (:2271-2407)
 __global__ void __launch_bounds__(128) k_query_ee(SurfArgs s, const Grid* __restrict__ gp, const Box* __restrict__ edge_boxes, SortedGrid eg, double dHat, double radius,
-    int wantCand, CsOut out)
+    int wantCand, int first, int last, CsOut out)
 {
-    const int eI = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int eI = first + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
-    if (eI >= s.nSE) return;
+    if (eI >= last) return;
     const Grid g = *gp;
     const int a0 = s.SE[2 * eI], a1 = s.SE[2 * eI + 1];
     const Box eb = edge_boxes[eI];
@@ -477,8 +478,15 @@ int contact_constraint_set(ipcgpu_ctx* ctx, double dHat, int wantCand, int* nC, 
     out.cand = w.cand.p; out.nCand = w.counters.p + 3; out.capCand = 4 * w.cap;
     out.overflow = w.counters.p + 4;
     const SortedGrid tg{ w.tkeys.p, w.tvals.p, w.tsbox.p, s.nSF }, eg{ w.ekeys.p, w.evals.p, w.esbox.p, s.nSE };
-    if (s.nSV > 0 && s.nSF > 0) k_query_pt<<<nblk((long long)s.nSV * 32, 128), 128, 0, st>>>(s, w.grid.p, tg, dHat, radius, wantCand, out);
-    if (s.nSE > 1) k_query_ee<<<nblk((long long)s.nSE * 32, 128), 128, 0, st>>>(s, w.grid.p, w.ebox.p, eg, dHat, radius, wantCand, out);
+    // partitioned mode (ipcgpu_set_contact_partition): this rank only issues its share of the queries (the reference's own loop
+    // decomposition, :2168 / :2271), so its lists hold a disjoint part of the global sets
+    int v0 = 0, v1 = s.nSV, e0 = 0, e1 = s.nSE;
+    if (ctx->partition_contact && ctx->nranks > 1) {
+        v0 = (int)((long long)s.nSV * ctx->rank / ctx->nranks); v1 = (int)((long long)s.nSV * (ctx->rank + 1) / ctx->nranks);
+        e0 = (int)((long long)s.nSE * ctx->rank / ctx->nranks); e1 = (int)((long long)s.nSE * (ctx->rank + 1) / ctx->nranks);
+    }
+    if (v1 > v0 && s.nSF > 0) k_query_pt<<<nblk((long long)(v1 - v0) * 32, 128), 128, 0, st>>>(s, w.grid.p, tg, dHat, radius, wantCand, v0, v1, out);
+    if (e1 > e0 && s.nSE > 1) k_query_ee<<<nblk((long long)(e1 - e0) * 32, 128), 128, 0, st>>>(s, w.grid.p, w.ebox.p, eg, dHat, radius, wantCand, e0, e1, out);
     ctx->launches += 2;
     int* h = reinterpret_cast<int*>(ctx->h_scalar);
     CKC(cudaMemcpyAsync(h, w.counters.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -96,6 +96,7 @@ struct ipcgpu_ctx {
     ipcgpu::DevBuf<int> SVI, SE, SF, vCoDim;
     bool has_codim = false, surface_ready = false;
     int pair_capacity = 1 << 20;
+    bool partition_contact = false, lists_local = false; // multi-rank: build only this rank's share of the contact sets
     ipcgpu::ContactWork cw;
     ipcgpu::CcdWork ccd;
     size_t ccd_capacity = (size_t)1 << 23; // candidate pairs

@@ -36,6 +36,9 @@ def main():
     mm, pa, pe, cand = ctx.constraint_set(dHat, 1)
     ia, ja = m.csr_pattern(1, extra_pairs=contact_pattern_pairs(m, mm, pa, pe))
     ctx.set_csr(ia, ja, 1)
+    if os.environ.get("IPCGPU_PARTITION_CONTACT", "1") == "1":  # second build: partitioned sets (the pattern above came from the replicated one)
+        ctx.set_contact_partition(1)
+        ctx.constraint_set(dHat, 1, fetch=False)
     E = ctx.elastic_energy(coef) + ctx.barrier_energy(dHat, kappa)
     ctx.csr_set_zero()
     ctx.elastic_grad_hess(coef, 1, 1, 1, None, None)
