@@ -214,6 +214,7 @@ def main():
     nnz = ja.size
     n_active, n_para, n_cand = len(mm), len(pa), len(cand)
     ctx.set_contact_partition(1)  # timed steps: every rank builds and processes only its share of the contact sets
+    ctx.set_canonical_order(0)    # the sets are consumed on the device: no need for the canonical sort (the reference's order is arbitrary too)
 
     # pinned host buffers for the e2e path
     hV = L.PinnedArray(3 * m.nV); hV.array[:] = m.V_soa

@@ -117,6 +117,10 @@ int ipcgpu_set_pair_capacity(ipcgpu_ctx* ctx, int capacity);
  * SpatialHash::build/query* (SpatialHash.hpp:46-229, 375-421) done on the device. The sets stay on the device (they feed the
  * barrier_* calls and the partial CCD); sizes are returned.  Output order is canonical: every list sorted lexicographically. */
 int ipcgpu_constraint_set(ipcgpu_ctx* ctx, double dHat, int getPTEE, int* nC, int* nPara, int* nCand);
+/* enable=1 (default): the lists are returned in canonical (lexicographic) order, so two runs give bitwise identical sets and sums.
+ * enable=0: the order is whatever the atomic appends produced -- the same freedom the reference has (its order depends on
+ * unordered_set iteration and TBB scheduling); saves the sorting passes when the sets are only consumed on the device. */
+int ipcgpu_set_canonical_order(ipcgpu_ctx* ctx, int enable);
 /* Multi-rank only. enable=1: ipcgpu_constraint_set issues only this rank's share of the PT/EE queries, so every rank holds a disjoint
  * part of the sets (PP/PE multiplicities may be split between ranks, which leaves the summed E/g/H unchanged because
  * makePD(c*M) = c*makePD(M) for c > 0); the counts returned are local.  enable=0 (default): every rank builds the whole set

@@ -615,6 +615,12 @@ int ipcgpu_constraint_set(ipcgpu_ctx* ctx, double dHat, int getPTEE, int* nC, in
     return rc;
 }
 
+int ipcgpu_set_canonical_order(ipcgpu_ctx* ctx, int enable)
+{
+    ctx->canonical_order = enable != 0;
+    return IPCGPU_OK;
+}
+
 int ipcgpu_set_contact_partition(ipcgpu_ctx* ctx, int enable)
 {
     ctx->partition_contact = enable != 0;

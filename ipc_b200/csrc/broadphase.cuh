@@ -65,13 +65,30 @@ DEV int upper_bound_u64(const unsigned long long* __restrict__ keys, int n, unsi
 
 // Grid v2: every primitive is registered ONCE, in the cell of its box's lower corner.  With cell edge >= (largest box extent +
 // 2*radius), a box starting in cell c ends in c or c+1, and a query box inflated by `radius` covers cells q0..q1 (q1 <= q0+1), so
-// every partner starts in [q0-1, q1] per axis: at most 3x3 rows of <= 3 consecutive cells = 9 contiguous key ranges.
+// every partner starts in [q0-1, q1] per axis: at most 3x3 rows of <= 3 consecutive cells.  Entries are sorted by cell key; an
+// open-addressing table (cell key -> index of the first entry of that cell) replaces binary searches: the <= 27 cell lookups of a
+// query run on 27 lanes at once.
 struct SortedGrid {
     const unsigned long long* keys; // sorted cell keys
     const int* ids;                 // primitive id per entry
     const Box* boxes;               // primitive boxes gathered in sorted order (coalesced candidate scan)
     int n;
+    const unsigned* tab_key;        // hash table: cell key (0xffffffff = empty)
+    const int* tab_start;           //             first entry of that cell in the sorted arrays
+    unsigned tab_mask;              // table size - 1 (power of two)
 };
+
+DEV unsigned cell_hash(unsigned key) { return key * 2654435761u; }
+DEV int cell_lookup(const SortedGrid& sg, unsigned key)
+{
+    unsigned h = cell_hash(key) & sg.tab_mask;
+    for (;;) {
+        const unsigned k = sg.tab_key[h];
+        if (k == key) return sg.tab_start[h];
+        if (k == 0xffffffffu) return -1;
+        h = (h + 1) & sg.tab_mask;
+    }
+}
 
 DEV bool boxes_overlap(const Box& a, const Box& b)
 {
@@ -89,20 +106,24 @@ DEV void warp_scan_candidates(const Grid& g, const SortedGrid& sg, const Box& qb
     const int y0 = max(c0[1] - 1, 0), z0 = max(c0[2] - 1, 0);
     const int ny = c1[1] - y0 + 1, nz = c1[2] - z0 + 1; // <= 3 each
     const int nrows = ny * nz;
-    // the (<= 9) row ranges are located by 18 binary searches running on 18 different lanes at once
-    int mine = 0;
+    // lane 3r+dx looks up cell (x0+dx) of row r
+    int mine = -1;
     {
-        const int r = lane & 15;
-        if (r < nrows) {
-            const int iy = y0 + r % ny, iz = z0 + r / ny;
-            mine = (lane < 16) ? lower_bound_u64(sg.keys, sg.n, cell_key(g, x0, iy, iz)) : upper_bound_u64(sg.keys, sg.n, cell_key(g, x1, iy, iz));
-        }
+        const int r = lane / 3, dx = lane - 3 * r;
+        if (r < nrows && x0 + dx <= x1) mine = cell_lookup(sg, (unsigned)cell_key(g, x0 + dx, y0 + r % ny, z0 + r / ny));
     }
     for (int r = 0; r < nrows; ++r) {
-        const int start = __shfl_sync(0xffffffffu, mine, r), end = __shfl_sync(0xffffffffu, mine, 16 + r);
-        for (int k = start + lane; k < end; k += 32) {
-            const Box b = sg.boxes[k];
-            if (boxes_overlap(qb, b)) f(sg.ids[k], b);
+        const int s0 = __shfl_sync(0xffffffffu, mine, 3 * r), s1 = __shfl_sync(0xffffffffu, mine, 3 * r + 1), s2 = __shfl_sync(0xffffffffu, mine, 3 * r + 2);
+        const int start = s0 >= 0 ? s0 : (s1 >= 0 ? s1 : s2); // cells of one row are consecutive keys => consecutive runs
+        if (start < 0) continue;
+        const unsigned long long key_hi = cell_key(g, x1, y0 + r % ny, z0 + r / ny);
+        for (int k = start + lane;; k += 32) {
+            const bool in = k < sg.n && sg.keys[k] <= key_hi;
+            if (in) {
+                const Box b = sg.boxes[k];
+                if (boxes_overlap(qb, b)) f(sg.ids[k], b);
+            }
+            if (!__any_sync(0xffffffffu, in)) break;
         }
     }
 }

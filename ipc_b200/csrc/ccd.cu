@@ -1171,7 +1171,7 @@ int ccd_full(ipcgpu_ctx* ctx, double tol, const double* err_vf, const double* er
     // multi-GPU: every rank sweeps a contiguous share of the query primitives (the reference's own loop decomposition, :1385, :1498)
     const int v0 = (int)((long long)s.nSV * ctx->rank / ctx->nranks), v1 = (int)((long long)s.nSV * (ctx->rank + 1) / ctx->nranks);
     const int e0 = (int)((long long)s.nSE * ctx->rank / ctx->nranks), e1 = (int)((long long)s.nSE * (ctx->rank + 1) / ctx->nranks);
-    const SortedGrid tg{ cw.tkeys.p, cw.tvals.p, cw.tsbox.p, s.nSF }, eg{ cw.ekeys.p, cw.evals.p, cw.esbox.p, s.nSE };
+    const SortedGrid tg{ cw.tkeys.p, cw.tvals.p, cw.tsbox.p, s.nSF, cw.ttab_key.p, cw.ttab_start.p, cw.tab_mask }, eg{ cw.ekeys.p, cw.evals.p, cw.esbox.p, s.nSE, cw.etab_key.p, cw.etab_start.p, cw.tab_mask };
     if (v1 > v0 && s.nSF > 0)
         k_ccd_query_pt<<<nblk((long long)(v1 - v0) * 32, 128), 128, 0, st>>>(s, cw.grid.p, cw.vbox.p, tg, w.vmin.p, w.vmax.p, radius, v0, v1, out);
     if (e1 > e0 && s.nSE > 1)

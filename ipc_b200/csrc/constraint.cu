@@ -117,6 +117,24 @@ __global__ void __launch_bounds__(256) k_emit(int n, const Box* __restrict__ box
     keys[i] = cell_key(g, c0[0], c0[1], c0[2]);
     vals[i] = i;
 }
+// run heads of the sorted key array go into the open-addressing table (cell key -> first entry)
+__global__ void __launch_bounds__(256) k_build_cell_table(int n, const unsigned long long* __restrict__ keys, unsigned* __restrict__ tab_key, int* __restrict__ tab_start,
+    unsigned mask)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned key = (unsigned)keys[i];
+    if (i > 0 && (unsigned)keys[i - 1] == key) return;
+    unsigned h = cell_hash(key) & mask;
+    for (;;) {
+        const unsigned old = atomicCAS(tab_key + h, 0xffffffffu, key);
+        if (old == 0xffffffffu || old == key) {
+            tab_start[h] = i;
+            return;
+        }
+        h = (h + 1) & mask;
+    }
+}
 __global__ void __launch_bounds__(256) k_gather_boxes(int n, const Box* __restrict__ boxes, const int* __restrict__ ids, Box* __restrict__ sorted)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -397,6 +415,10 @@ int contact_alloc(ipcgpu_ctx* ctx)
         && w.act.reserve(cap) && w.dup.reserve(cap) && w.para.reserve(cap) && w.para_e.reserve(cap) && w.cand.reserve((size_t)4 * cap) && w.tmp4.reserve(cap)
         && w.tmp2.reserve((size_t)4 * cap) && w.counters.reserve(16) && w.skey.reserve((size_t)4 * cap) && w.skey2.reserve((size_t)4 * cap) && w.sidx.reserve((size_t)4 * cap)
         && w.sidx2.reserve((size_t)4 * cap);
+    unsigned tsz = 1024;
+    while (tsz < 2u * (unsigned)nEnt) tsz <<= 1;
+    w.tab_mask = tsz - 1;
+    ok = ok && w.ttab_key.reserve(tsz) && w.ttab_start.reserve(tsz) && w.etab_key.reserve(tsz) && w.etab_start.reserve(tsz);
     if (!ok) {
         ctx->err = "contact workspace allocation failed";
         return IPCGPU_ERR_CUDA;
@@ -413,7 +435,7 @@ int contact_alloc(ipcgpu_ctx* ctx)
 }
 
 // build one sorted grid over `boxes` (n prims): (keys, vals) sorted by cell, boxes gathered into `sorted_boxes`
-static int build_grid(ipcgpu_ctx* ctx, int n, const Box* boxes, DevBuf<unsigned long long>& keys, DevBuf<int>& vals, Box* sorted_boxes)
+static int build_grid(ipcgpu_ctx* ctx, int n, const Box* boxes, DevBuf<unsigned long long>& keys, DevBuf<int>& vals, Box* sorted_boxes, unsigned* tab_key, int* tab_start)
 {
     ContactWork& w = ctx->cw;
     cudaStream_t st = ctx->stream;
@@ -426,7 +448,9 @@ static int build_grid(ipcgpu_ctx* ctx, int n, const Box* boxes, DevBuf<unsigned 
         return IPCGPU_ERR_CUDA;
     }
     k_gather_boxes<<<nblk(n, 256), 256, 0, st>>>(n, boxes, vals.p, sorted_boxes);
-    ctx->launches += 3;
+    cudaMemsetAsync(tab_key, 0xff, (size_t)(w.tab_mask + 1) * sizeof(unsigned), st);
+    k_build_cell_table<<<nblk(n, 256), 256, 0, st>>>(n, keys.p, tab_key, tab_start, w.tab_mask);
+    ctx->launches += 4;
     return 0;
 }
 
@@ -452,8 +476,8 @@ int boxes_and_grid(ipcgpu_ctx* ctx, const double* dir, double alpha, double radi
     k_grid_params<<<1, 32, 0, st>>>(w.bounds.p, radius, w.grid.p);
     ctx->launches += 5;
     int rc;
-    if ((rc = build_grid(ctx, s.nSF, w.tbox.p, w.tkeys, w.tvals, w.tsbox.p))) return rc;
-    if ((rc = build_grid(ctx, s.nSE, w.ebox.p, w.ekeys, w.evals, w.esbox.p))) return rc;
+    if ((rc = build_grid(ctx, s.nSF, w.tbox.p, w.tkeys, w.tvals, w.tsbox.p, w.ttab_key.p, w.ttab_start.p))) return rc;
+    if ((rc = build_grid(ctx, s.nSE, w.ebox.p, w.ekeys, w.evals, w.esbox.p, w.etab_key.p, w.etab_start.p))) return rc;
     return 0;
 }
 
@@ -477,7 +501,7 @@ int contact_constraint_set(ipcgpu_ctx* ctx, double dHat, int wantCand, int* nC, 
     out.para = w.para.p; out.para_e = w.para_e.p; out.nPara = w.counters.p + 2; out.capPara = w.cap;
     out.cand = w.cand.p; out.nCand = w.counters.p + 3; out.capCand = 4 * w.cap;
     out.overflow = w.counters.p + 4;
-    const SortedGrid tg{ w.tkeys.p, w.tvals.p, w.tsbox.p, s.nSF }, eg{ w.ekeys.p, w.evals.p, w.esbox.p, s.nSE };
+    const SortedGrid tg{ w.tkeys.p, w.tvals.p, w.tsbox.p, s.nSF, w.ttab_key.p, w.ttab_start.p, w.tab_mask }, eg{ w.ekeys.p, w.evals.p, w.esbox.p, s.nSE, w.etab_key.p, w.etab_start.p, w.tab_mask };
     // partitioned mode (ipcgpu_set_contact_partition): this rank only issues its share of the queries (the reference's own loop
     // decomposition, :2168 / :2271), so its lists hold a disjoint part of the global sets
     int v0 = 0, v1 = s.nSV, e0 = 0, e1 = s.nSE;
@@ -509,9 +533,11 @@ int contact_constraint_set(ipcgpu_ctx* ctx, double dHat, int wantCand, int* nC, 
         }
     }
     const int nTot = (nDup > 0) ? h[0] : nAct;
-    if ((rc = sort_lex(ctx, w.act.p, nullptr, nTot, w.tmp4.p, nullptr))) return rc;
-    if ((rc = sort_lex(ctx, w.para.p, w.para_e.p, nP, w.tmp4.p, w.tmp2.p))) return rc;
-    if (wantCand && (rc = sort_int2(ctx, w.cand.p, nK, w.tmp2.p))) return rc;
+    if (ctx->canonical_order) { // deterministic output order (the reference's own order is scheduling dependent, :2176, :2282)
+        if ((rc = sort_lex(ctx, w.act.p, nullptr, nTot, w.tmp4.p, nullptr))) return rc;
+        if ((rc = sort_lex(ctx, w.para.p, w.para_e.p, nP, w.tmp4.p, w.tmp2.p))) return rc;
+        if (wantCand && (rc = sort_int2(ctx, w.cand.p, nK, w.tmp2.p))) return rc;
+    }
     ctx->prof_end(pe);
     w.nC = nTot;
     w.nP = nP;

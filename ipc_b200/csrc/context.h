@@ -49,6 +49,9 @@ struct ContactWork {
     DevBuf<int4> act, dup, para, tmp4;
     DevBuf<int2> para_e, cand, tmp2;
     DevBuf<unsigned char> cub_tmp;
+    DevBuf<unsigned> ttab_key, etab_key; // cell hash tables of the triangle / edge grids
+    DevBuf<int> ttab_start, etab_start;
+    unsigned tab_mask = 0;
     int cap = 0;
     int nC = 0, nP = 0, nK = 0; // current active / mollified / candidate counts
 };
@@ -96,6 +99,7 @@ struct ipcgpu_ctx {
     ipcgpu::DevBuf<int> SVI, SE, SF, vCoDim;
     bool has_codim = false, surface_ready = false;
     int pair_capacity = 1 << 20;
+    bool canonical_order = true; // sort the contact lists lexicographically after the build
     bool partition_contact = false, lists_local = false; // multi-rank: build only this rank's share of the contact sets
     ipcgpu::ContactWork cw;
     ipcgpu::CcdWork ccd;

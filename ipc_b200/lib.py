@@ -46,6 +46,7 @@ SIGNATURES = {
     "ipcgpu_set_pair_capacity": (C.c_int, [_ctxp, C.c_int]),
     "ipcgpu_constraint_set": (C.c_int, [_ctxp, C.c_double, C.c_int, _ip, _ip, _ip]),
     "ipcgpu_set_contact_partition": (C.c_int, [_ctxp, C.c_int]),
+    "ipcgpu_set_canonical_order": (C.c_int, [_ctxp, C.c_int]),
     "ipcgpu_get_constraint_set": (C.c_int, [_ctxp, _ip, _ip, _ip, _ip]),
     "ipcgpu_set_constraint_set": (C.c_int, [_ctxp, C.c_int, _ip, C.c_int, _ip, _ip, C.c_int, _ip]),
     "ipcgpu_barrier_energy": (C.c_int, [_ctxp, C.c_double, C.c_double, _dp]),
@@ -229,6 +230,9 @@ class Context:
     def set_surface(self, SVI, SFEdges, SF_soa, vCoDim=None):
         SVI, SE, SF = i32(SVI).ravel(), i32(SFEdges).ravel(), i32(SF_soa).ravel()
         self._ck(self.lib.ipcgpu_set_surface(self.h, SVI.size, _i(SVI), SE.size // 2, _i(SE), SF.size // 3, _i(SF), _i(i32(vCoDim))))
+
+    def set_canonical_order(self, enable):
+        self._ck(self.lib.ipcgpu_set_canonical_order(self.h, int(enable)))
 
     def set_contact_partition(self, enable):
         self._ck(self.lib.ipcgpu_set_contact_partition(self.h, int(enable)))
