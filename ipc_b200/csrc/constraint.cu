@@ -172,115 +172,137 @@ DEV double box_gap2(const Box& a, const Box& b)
 DEV bool is_dbc_v(const SurfArgs& s, int v) { return s.dbc && s.dbc[v] != 0; }
 DEV int codim_v(const SurfArgs& s, int v) { return s.vCoDim ? s.vCoDim[v] : 3; }
 
-// one WARP per surface vertex  (:2168-2260)
-__global__ void __launch_bounds__(128) k_query_pt(SurfArgs s, const Grid* __restrict__ gp, SortedGrid tg, double dHat, double radius, int wantCand, int first, int last,
-    CsOut out)
+// ---- phase 1: broad phase proper.  One WARP per query primitive scans the grid and appends (query, partner) pairs whose boxes are
+// closer than sqrt(dHat).  Only boxes are touched here, so the kernel needs few registers and runs at high occupancy.
+struct PairOut {
+    int2* pairs;
+    unsigned* n;
+    unsigned cap;
+    int* overflow;
+};
+DEV void push_pair(const PairOut& o, int a, int b)
+{
+    const unsigned i = atomicAdd(o.n, 1u);
+    if (i < o.cap) o.pairs[i] = make_int2(a, b);
+    else atomicExch(o.overflow, 1);
+}
+
+__global__ void __launch_bounds__(256) k_pairs_pt(SurfArgs s, const Grid* __restrict__ gp, SortedGrid tg, double dHat, double radius, int first, int last, PairOut out)
 {
     const int svI = first + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     if (svI >= last) return;
     const Grid g = *gp;
-    const int vI = s.SVI[svI];
-    const V3 p = load_vertex(s.V, s.nV, vI);
-    Box qb;
+    const V3 p = load_vertex(s.V, s.nV, s.SVI[svI]);
+    Box qb, pb;
     qb.lo[0] = p.x - radius; qb.lo[1] = p.y - radius; qb.lo[2] = p.z - radius;
     qb.hi[0] = p.x + radius; qb.hi[1] = p.y + radius; qb.hi[2] = p.z + radius;
-    const int vcod = codim_v(s, vI);
-    const bool vdbc = is_dbc_v(s, vI);
+    pb.lo[0] = pb.hi[0] = p.x; pb.lo[1] = pb.hi[1] = p.y; pb.lo[2] = pb.hi[2] = p.z;
     const double cull = dHat * (1.0 + 1e-9) + 1e-300;
     warp_scan_candidates(g, tg, qb, lane, [&](int sfI, const Box& tb) {
-        Box pb;
-        pb.lo[0] = pb.hi[0] = p.x; pb.lo[1] = pb.hi[1] = p.y; pb.lo[2] = pb.hi[2] = p.z;
-        if (box_gap2(pb, tb) > cull) return;
-        const int a = s.SF[sfI], b = s.SF[(size_t)s.nSF + sfI], c = s.SF[(size_t)2 * s.nSF + sfI];
-        if (vI == a || vI == b || vI == c) return;
-        if ((vcod < 3 && codim_v(s, a) < 3) || (vdbc && is_dbc_v(s, a) && is_dbc_v(s, b) && is_dbc_v(s, c))) return;
-        const V3 ta = load_vertex(s.V, s.nV, a), tb_ = load_vertex(s.V, s.nV, b), tc = load_vertex(s.V, s.nV, c);
-        const int ty = dType_PT(p, ta, tb_, tc);
-        double d;
-        int4 q;
-        switch (ty) {
-        case 0: d = d_PP(p, ta); q = make_int4(-vI - 1, a, -1, -1); break;
-        case 1: d = d_PP(p, tb_); q = make_int4(-vI - 1, b, -1, -1); break;
-        case 2: d = d_PP(p, tc); q = make_int4(-vI - 1, c, -1, -1); break;
-        case 3: d = d_PE(p, ta, tb_); q = make_int4(-vI - 1, a, b, -1); break;
-        case 4: d = d_PE(p, tb_, tc); q = make_int4(-vI - 1, b, c, -1); break;
-        case 5: d = d_PE(p, tc, ta); q = make_int4(-vI - 1, c, a, -1); break;
-        default: d = d_PT(p, ta, tb_, tc); q = make_int4(-vI - 1, a, b, c);
-        }
-        if (d < dHat) {
-            if (q.w >= 0) push4(out.act, out.nAct, out.capAct, out.overflow, q);
-            else push4(out.dup, out.nDup, out.capDup, out.overflow, q);
-            if (wantCand) {
-                int i = atomicAdd(out.nCand, 1);
-                if ((unsigned)i < (unsigned)out.capCand) out.cand[i] = make_int2(-svI - 1, sfI);
-                else atomicExch(out.overflow, 1);
-            }
-        }
+        if (box_gap2(pb, tb) <= cull) push_pair(out, svI, sfI);
     });
 }
 
-// one WARP per surface edge eI; partners eJ > eI  (:2271-2407)
-__global__ void __launch_bounds__(128) k_query_ee(SurfArgs s, const Grid* __restrict__ gp, const Box* __restrict__ edge_boxes, SortedGrid eg, double dHat, double radius,
-    int wantCand, int first, int last, CsOut out)
+__global__ void __launch_bounds__(256) k_pairs_ee(SurfArgs s, const Grid* __restrict__ gp, const Box* __restrict__ edge_boxes, SortedGrid eg, double dHat, double radius, int first,
+    int last, PairOut out)
 {
     const int eI = first + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     if (eI >= last) return;
     const Grid g = *gp;
-    const int a0 = s.SE[2 * eI], a1 = s.SE[2 * eI + 1];
     const Box eb = edge_boxes[eI];
     Box qb = eb;
     for (int k = 0; k < 3; ++k) { qb.lo[k] -= radius; qb.hi[k] += radius; }
-    const V3 xa0 = load_vertex(s.V, s.nV, a0), xa1 = load_vertex(s.V, s.nV, a1);
-    const int ecod = codim_v(s, a0);
-    const bool edbc = is_dbc_v(s, a0) && is_dbc_v(s, a1);
     const double cull = dHat * (1.0 + 1e-9) + 1e-300;
     warp_scan_candidates(g, eg, qb, lane, [&](int eJ, const Box& jb) {
-        if (eJ <= eI) return;
-        if (box_gap2(eb, jb) > cull) return;
-        const int b0 = s.SE[2 * eJ], b1 = s.SE[2 * eJ + 1];
-        if (a0 == b0 || a0 == b1 || a1 == b0 || a1 == b1) return;
-        if ((ecod < 3 && codim_v(s, b0) < 3) || (edbc && is_dbc_v(s, b0) && is_dbc_v(s, b1))) return;
-        const V3 xb0 = load_vertex(s.V, s.nV, b0), xb1 = load_vertex(s.V, s.nV, b1);
-        const int ty = dType_EE(xa0, xa1, xb0, xb1);
-        const double cr = norm2(cross(xa1 - xa0, xb1 - xb0));
-        const int add_e = (cr < eps_x_rest(s.Vrest, s.nV, a0, a1, b0, b1)) ? (-eJ - 2) : -1;
-        double d;
-        int4 q;
-        switch (ty) {
-        case 0: d = d_PP(xa0, xb0); q = make_int4(-a0 - 1, b0, -1, add_e); break;
-        case 1: d = d_PP(xa0, xb1); q = make_int4(-a0 - 1, b1, -1, add_e); break;
-        case 2: d = d_PE(xa0, xb0, xb1); q = make_int4(-a0 - 1, b0, b1, add_e); break;
-        case 3: d = d_PP(xa1, xb0); q = make_int4(-a1 - 1, b0, -1, add_e); break;
-        case 4: d = d_PP(xa1, xb1); q = make_int4(-a1 - 1, b1, -1, add_e); break;
-        case 5: d = d_PE(xa1, xb0, xb1); q = make_int4(-a1 - 1, b0, b1, add_e); break;
-        case 6: d = d_PE(xb0, xa0, xa1); q = make_int4(-b0 - 1, a0, a1, add_e); break;
-        case 7: d = d_PE(xb1, xa0, xa1); q = make_int4(-b1 - 1, a0, a1, add_e); break;
-        default: d = d_EE(xa0, xa1, xb0, xb1); q = make_int4(a0, a1, b0, b1);
-        }
-        if (d < dHat) {
-            if (ty == 8) {
-                if (add_e <= -2) { // nearly parallel EE: mollified set, keeps its own stencil (:2464-2467)
-                    int i = atomicAdd(out.nPara, 1);
-                    if ((unsigned)i < (unsigned)out.capPara) { out.para[i] = q; out.para_e[i] = make_int2(-1, -1); }
-                    else atomicExch(out.overflow, 1);
-                }
-                else push4(out.act, out.nAct, out.capAct, out.overflow, q);
-            }
-            else if (add_e == -1) push4(out.dup, out.nDup, out.capDup, out.overflow, q);
-            else { // PP / PE that came from a nearly parallel edge pair (:2459-2462)
-                int i = atomicAdd(out.nPara, 1);
-                if ((unsigned)i < (unsigned)out.capPara) { out.para[i] = make_int4(q.x, q.y, q.z, -1); out.para_e[i] = make_int2(eI, eJ); }
-                else atomicExch(out.overflow, 1);
-            }
-            if (wantCand) {
-                int i = atomicAdd(out.nCand, 1);
-                if ((unsigned)i < (unsigned)out.capCand) out.cand[i] = make_int2(eI, eJ);
-                else atomicExch(out.overflow, 1);
-            }
-        }
+        if (eJ > eI && box_gap2(eb, jb) <= cull) push_pair(out, eI, eJ);
     });
+}
+
+// ---- phase 2: exact closest-feature classification, one THREAD per surviving pair (dense, convergent)
+// (:2168-2260)
+__global__ void __launch_bounds__(128) k_classify_pt(SurfArgs s, const int2* __restrict__ pairs, const unsigned* __restrict__ nPairs, double dHat, int wantCand, CsOut out)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *nPairs) return;
+    const int svI = pairs[i].x, sfI = pairs[i].y;
+    const int vI = s.SVI[svI];
+    const int a = s.SF[sfI], b = s.SF[(size_t)s.nSF + sfI], c = s.SF[(size_t)2 * s.nSF + sfI];
+    if (vI == a || vI == b || vI == c) return;
+    if ((codim_v(s, vI) < 3 && codim_v(s, a) < 3) || (is_dbc_v(s, vI) && is_dbc_v(s, a) && is_dbc_v(s, b) && is_dbc_v(s, c))) return;
+    const V3 p = load_vertex(s.V, s.nV, vI);
+    const V3 ta = load_vertex(s.V, s.nV, a), tb_ = load_vertex(s.V, s.nV, b), tc = load_vertex(s.V, s.nV, c);
+    const int ty = dType_PT(p, ta, tb_, tc);
+    double d;
+    int4 q;
+    switch (ty) {
+    case 0: d = d_PP(p, ta); q = make_int4(-vI - 1, a, -1, -1); break;
+    case 1: d = d_PP(p, tb_); q = make_int4(-vI - 1, b, -1, -1); break;
+    case 2: d = d_PP(p, tc); q = make_int4(-vI - 1, c, -1, -1); break;
+    case 3: d = d_PE(p, ta, tb_); q = make_int4(-vI - 1, a, b, -1); break;
+    case 4: d = d_PE(p, tb_, tc); q = make_int4(-vI - 1, b, c, -1); break;
+    case 5: d = d_PE(p, tc, ta); q = make_int4(-vI - 1, c, a, -1); break;
+    default: d = d_PT(p, ta, tb_, tc); q = make_int4(-vI - 1, a, b, c);
+    }
+    if (d < dHat) {
+        if (q.w >= 0) push4(out.act, out.nAct, out.capAct, out.overflow, q);
+        else push4(out.dup, out.nDup, out.capDup, out.overflow, q);
+        if (wantCand) {
+            int k = atomicAdd(out.nCand, 1);
+            if ((unsigned)k < (unsigned)out.capCand) out.cand[k] = make_int2(-svI - 1, sfI);
+            else atomicExch(out.overflow, 1);
+        }
+    }
+}
+
+// (:2271-2407)
+__global__ void __launch_bounds__(128) k_classify_ee(SurfArgs s, const int2* __restrict__ pairs, const unsigned* __restrict__ nPairs, double dHat, int wantCand, CsOut out)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *nPairs) return;
+    const int eI = pairs[i].x, eJ = pairs[i].y;
+    const int a0 = s.SE[2 * eI], a1 = s.SE[2 * eI + 1], b0 = s.SE[2 * eJ], b1 = s.SE[2 * eJ + 1];
+    if (a0 == b0 || a0 == b1 || a1 == b0 || a1 == b1) return;
+    if ((codim_v(s, a0) < 3 && codim_v(s, b0) < 3) || (is_dbc_v(s, a0) && is_dbc_v(s, a1) && is_dbc_v(s, b0) && is_dbc_v(s, b1))) return;
+    const V3 xa0 = load_vertex(s.V, s.nV, a0), xa1 = load_vertex(s.V, s.nV, a1), xb0 = load_vertex(s.V, s.nV, b0), xb1 = load_vertex(s.V, s.nV, b1);
+    const int ty = dType_EE(xa0, xa1, xb0, xb1);
+    const double cr = norm2(cross(xa1 - xa0, xb1 - xb0));
+    const int add_e = (cr < eps_x_rest(s.Vrest, s.nV, a0, a1, b0, b1)) ? (-eJ - 2) : -1;
+    double d;
+    int4 q;
+    switch (ty) {
+    case 0: d = d_PP(xa0, xb0); q = make_int4(-a0 - 1, b0, -1, add_e); break;
+    case 1: d = d_PP(xa0, xb1); q = make_int4(-a0 - 1, b1, -1, add_e); break;
+    case 2: d = d_PE(xa0, xb0, xb1); q = make_int4(-a0 - 1, b0, b1, add_e); break;
+    case 3: d = d_PP(xa1, xb0); q = make_int4(-a1 - 1, b0, -1, add_e); break;
+    case 4: d = d_PP(xa1, xb1); q = make_int4(-a1 - 1, b1, -1, add_e); break;
+    case 5: d = d_PE(xa1, xb0, xb1); q = make_int4(-a1 - 1, b0, b1, add_e); break;
+    case 6: d = d_PE(xb0, xa0, xa1); q = make_int4(-b0 - 1, a0, a1, add_e); break;
+    case 7: d = d_PE(xb1, xa0, xa1); q = make_int4(-b1 - 1, a0, a1, add_e); break;
+    default: d = d_EE(xa0, xa1, xb0, xb1); q = make_int4(a0, a1, b0, b1);
+    }
+    if (d < dHat) {
+        if (ty == 8) {
+            if (add_e <= -2) { // nearly parallel EE: mollified set, keeps its own stencil (:2464-2467)
+                int k = atomicAdd(out.nPara, 1);
+                if ((unsigned)k < (unsigned)out.capPara) { out.para[k] = q; out.para_e[k] = make_int2(-1, -1); }
+                else atomicExch(out.overflow, 1);
+            }
+            else push4(out.act, out.nAct, out.capAct, out.overflow, q);
+        }
+        else if (add_e == -1) push4(out.dup, out.nDup, out.capDup, out.overflow, q);
+        else { // PP / PE that came from a nearly parallel edge pair (:2459-2462)
+            int k = atomicAdd(out.nPara, 1);
+            if ((unsigned)k < (unsigned)out.capPara) { out.para[k] = make_int4(q.x, q.y, q.z, -1); out.para_e[k] = make_int2(eI, eJ); }
+            else atomicExch(out.overflow, 1);
+        }
+        if (wantCand) {
+            int k = atomicAdd(out.nCand, 1);
+            if ((unsigned)k < (unsigned)out.capCand) out.cand[k] = make_int2(eI, eJ);
+            else atomicExch(out.overflow, 1);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -418,7 +440,8 @@ int contact_alloc(ipcgpu_ctx* ctx)
     unsigned tsz = 1024;
     while (tsz < 2u * (unsigned)nEnt) tsz <<= 1;
     w.tab_mask = tsz - 1;
-    ok = ok && w.ttab_key.reserve(tsz) && w.ttab_start.reserve(tsz) && w.etab_key.reserve(tsz) && w.etab_start.reserve(tsz);
+    w.bp_cap = (size_t)24 * std::max(std::max(nSE, nSV), 1024);
+    ok = ok && w.bp_pairs.reserve(2 * w.bp_cap) && w.ttab_key.reserve(tsz) && w.ttab_start.reserve(tsz) && w.etab_key.reserve(tsz) && w.etab_start.reserve(tsz);
     if (!ok) {
         ctx->err = "contact workspace allocation failed";
         return IPCGPU_ERR_CUDA;
@@ -509,8 +532,19 @@ int contact_constraint_set(ipcgpu_ctx* ctx, double dHat, int wantCand, int* nC, 
         v0 = (int)((long long)s.nSV * ctx->rank / ctx->nranks); v1 = (int)((long long)s.nSV * (ctx->rank + 1) / ctx->nranks);
         e0 = (int)((long long)s.nSE * ctx->rank / ctx->nranks); e1 = (int)((long long)s.nSE * (ctx->rank + 1) / ctx->nranks);
     }
-    if (v1 > v0 && s.nSF > 0) k_query_pt<<<nblk((long long)(v1 - v0) * 32, 128), 128, 0, st>>>(s, w.grid.p, tg, dHat, radius, wantCand, v0, v1, out);
-    if (e1 > e0 && s.nSE > 1) k_query_ee<<<nblk((long long)(e1 - e0) * 32, 128), 128, 0, st>>>(s, w.grid.p, w.ebox.p, eg, dHat, radius, wantCand, e0, e1, out);
+    // phase 1 (boxes only) -> pair lists ; phase 2 (exact classification) over the lists.  The list sizes stay on the device:
+    // phase 2 is launched over the list capacity and surplus threads exit.
+    unsigned* nPairs = reinterpret_cast<unsigned*>(w.counters.p + 8); // [8] PT pairs, [9] EE pairs
+    PairOut ppt{ w.bp_pairs.p, nPairs, (unsigned)w.bp_cap, w.counters.p + 4 }, pee{ w.bp_pairs.p + w.bp_cap, nPairs + 1, (unsigned)w.bp_cap, w.counters.p + 4 };
+    if (v1 > v0 && s.nSF > 0) {
+        k_pairs_pt<<<nblk((long long)(v1 - v0) * 32, 256), 256, 0, st>>>(s, w.grid.p, tg, dHat, radius, v0, v1, ppt);
+        k_classify_pt<<<nblk((long long)w.bp_cap, 128), 128, 0, st>>>(s, ppt.pairs, ppt.n, dHat, wantCand, out);
+    }
+    if (e1 > e0 && s.nSE > 1) {
+        k_pairs_ee<<<nblk((long long)(e1 - e0) * 32, 256), 256, 0, st>>>(s, w.grid.p, w.ebox.p, eg, dHat, radius, e0, e1, pee);
+        k_classify_ee<<<nblk((long long)w.bp_cap, 128), 128, 0, st>>>(s, pee.pairs, pee.n, dHat, wantCand, out);
+    }
+    ctx->launches += 2;
     ctx->launches += 2;
     int* h = reinterpret_cast<int*>(ctx->h_scalar);
     CKC(cudaMemcpyAsync(h, w.counters.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -52,6 +52,8 @@ struct ContactWork {
     DevBuf<unsigned> ttab_key, etab_key; // cell hash tables of the triangle / edge grids
     DevBuf<int> ttab_start, etab_start;
     unsigned tab_mask = 0;
+    DevBuf<int2> bp_pairs; // broad-phase pair lists (PT then EE), bp_cap each
+    size_t bp_cap = 0;
     int cap = 0;
     int nC = 0, nP = 0, nK = 0; // current active / mollified / candidate counts
 };
