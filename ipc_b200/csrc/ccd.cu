@@ -118,63 +118,77 @@ DEV void push_cand(const CandOut& o, int2 c)
     else atomicExch(o.overflow, 1);
 }
 
-// one WARP per surface vertex (queryPointForPrimitives, triangle part)
-__global__ void __launch_bounds__(128) k_ccd_query_pt(SurfArgs s, const Grid* __restrict__ gp, const Box* __restrict__ vboxes, SortedGrid tg, const int* __restrict__ vmin,
-    const int* __restrict__ vmax, double radius, int first, int last, CandOut out)
+// ---- phase 1: one WARP per query primitive, boxes only: (query, partner) pairs whose swept boxes are within one reference voxel
+struct PairOut {
+    int2* pairs;
+    unsigned* n;
+    unsigned cap;
+    int* overflow;
+};
+DEV void push_pair(const PairOut& o, int a, int b)
+{
+    const unsigned i = atomicAdd(o.n, 1u);
+    if (i < o.cap) o.pairs[i] = make_int2(a, b);
+    else atomicExch(o.overflow, 1);
+}
+__global__ void __launch_bounds__(256) k_ccd_pairs_pt(const Grid* __restrict__ gp, const Box* __restrict__ vboxes, SortedGrid tg, double radius, int first, int last, PairOut out)
 {
     const int svI = first + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     if (svI >= last) return;
     const Grid g = *gp;
-    const int vI = s.SVI[svI];
     Box qb = vboxes[svI];
     for (int k = 0; k < 3; ++k) { qb.lo[k] -= radius; qb.hi[k] += radius; }
-    const int* plo = vmin + 3 * (size_t)vI;
-    const int* phi = vmax + 3 * (size_t)vI;
-    const int vcod = cod_v(s, vI);
-    const bool vdbc = dbc_v(s, vI);
-    warp_scan_candidates(g, tg, qb, lane, [&](int sfI, const Box&) {
-        int tv[3] = { s.SF[sfI], s.SF[(size_t)s.nSF + sfI], s.SF[(size_t)2 * s.nSF + sfI] };
-        int lo[3], hi[3];
-        prim_range(vmin, vmax, tv, 3, lo, hi);
-        if (!ranges_overlap(plo, phi, lo, hi)) return; // the reference's hash would not pair them
-        if (vI == tv[0] || vI == tv[1] || vI == tv[2]) return;
-        if ((vcod < 3 && cod_v(s, tv[0]) < 3) || (vdbc && dbc_v(s, tv[0]) && dbc_v(s, tv[1]) && dbc_v(s, tv[2]))) return;
-        push_cand(out, make_int2(-svI - 1, sfI));
-    });
+    warp_scan_candidates(g, tg, qb, lane, [&](int sfI, const Box&) { push_pair(out, svI, sfI); });
 }
-
-// one WARP per surface edge (queryEdgeForEdgesWithBBoxCheck, SpatialHash.hpp:803-832)
-__global__ void __launch_bounds__(128) k_ccd_query_ee(SurfArgs s, const Grid* __restrict__ gp, const Box* __restrict__ eboxes, SortedGrid eg, const int* __restrict__ vmin,
-    const int* __restrict__ vmax, double radius, int first, int last, CandOut out)
+__global__ void __launch_bounds__(256) k_ccd_pairs_ee(const Grid* __restrict__ gp, const Box* __restrict__ eboxes, SortedGrid eg, double radius, int first, int last, PairOut out)
 {
     const int eI = first + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     if (eI >= last) return;
     const Grid g = *gp;
-    const int a[2] = { s.SE[2 * eI], s.SE[2 * eI + 1] };
     const Box eb = eboxes[eI];
     Box qb = eb;
     for (int k = 0; k < 3; ++k) { qb.lo[k] -= radius; qb.hi[k] += radius; }
-    int qlo[3], qhi[3];
-    prim_range(vmin, vmax, a, 2, qlo, qhi);
-    const int ecod = cod_v(s, a[0]);
-    const bool edbc = dbc_v(s, a[0]) && dbc_v(s, a[1]);
     warp_scan_candidates(g, eg, qb, lane, [&](int eJ, const Box& jb) {
         if (eJ <= eI) return;
-        const int b[2] = { s.SE[2 * eJ], s.SE[2 * eJ + 1] };
-        int lo[3], hi[3];
-        prim_range(vmin, vmax, b, 2, lo, hi);
-        if (!ranges_overlap(qlo, qhi, lo, hi)) return;
         // swept-AABB test of queryEdgeForEdgesWithBBoxCheck (SpatialHash.hpp:819-828); the boxes hold {x, x+alpha p}
         bool sep = false;
 #pragma unroll
         for (int c = 0; c < 3; ++c) sep = sep || (jb.lo[c] - eb.hi[c] > 0.0) || (eb.lo[c] - jb.hi[c] > 0.0);
-        if (sep) return;
-        if (a[0] == b[0] || a[0] == b[1] || a[1] == b[0] || a[1] == b[1]) return;
-        if ((ecod < 3 && cod_v(s, b[0]) < 3) || (edbc && dbc_v(s, b[0]) && dbc_v(s, b[1]))) return;
-        push_cand(out, make_int2(eI, eJ));
+        if (!sep) push_pair(out, eI, eJ);
     });
+}
+// ---- phase 2: one THREAD per pair: the reference's voxel-range overlap (its hash query) and the index filters
+__global__ void __launch_bounds__(256) k_ccd_filter_pt(SurfArgs s, const int2* __restrict__ pairs, const unsigned* __restrict__ nPairs, const int* __restrict__ vmin,
+    const int* __restrict__ vmax, CandOut out)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *nPairs) return;
+    const int svI = pairs[i].x, sfI = pairs[i].y;
+    const int vI = s.SVI[svI];
+    int tv[3] = { s.SF[sfI], s.SF[(size_t)s.nSF + sfI], s.SF[(size_t)2 * s.nSF + sfI] };
+    if (vI == tv[0] || vI == tv[1] || vI == tv[2]) return;
+    int lo[3], hi[3];
+    prim_range(vmin, vmax, tv, 3, lo, hi);
+    if (!ranges_overlap(vmin + 3 * (size_t)vI, vmax + 3 * (size_t)vI, lo, hi)) return; // the reference's hash would not pair them
+    if ((cod_v(s, vI) < 3 && cod_v(s, tv[0]) < 3) || (dbc_v(s, vI) && dbc_v(s, tv[0]) && dbc_v(s, tv[1]) && dbc_v(s, tv[2]))) return;
+    push_cand(out, make_int2(-svI - 1, sfI));
+}
+__global__ void __launch_bounds__(256) k_ccd_filter_ee(SurfArgs s, const int2* __restrict__ pairs, const unsigned* __restrict__ nPairs, const int* __restrict__ vmin,
+    const int* __restrict__ vmax, CandOut out)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *nPairs) return;
+    const int eI = pairs[i].x, eJ = pairs[i].y;
+    const int a[2] = { s.SE[2 * eI], s.SE[2 * eI + 1] }, b[2] = { s.SE[2 * eJ], s.SE[2 * eJ + 1] };
+    if (a[0] == b[0] || a[0] == b[1] || a[1] == b[0] || a[1] == b[1]) return;
+    int qlo[3], qhi[3], lo[3], hi[3];
+    prim_range(vmin, vmax, a, 2, qlo, qhi);
+    prim_range(vmin, vmax, b, 2, lo, hi);
+    if (!ranges_overlap(qlo, qhi, lo, hi)) return;
+    if ((cod_v(s, a[0]) < 3 && cod_v(s, b[0]) < 3) || (dbc_v(s, a[0]) && dbc_v(s, a[1]) && dbc_v(s, b[0]) && dbc_v(s, b[1]))) return;
+    push_cand(out, make_int2(eI, eJ));
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1172,10 +1186,18 @@ int ccd_full(ipcgpu_ctx* ctx, double tol, const double* err_vf, const double* er
     const int v0 = (int)((long long)s.nSV * ctx->rank / ctx->nranks), v1 = (int)((long long)s.nSV * (ctx->rank + 1) / ctx->nranks);
     const int e0 = (int)((long long)s.nSE * ctx->rank / ctx->nranks), e1 = (int)((long long)s.nSE * (ctx->rank + 1) / ctx->nranks);
     const SortedGrid tg{ cw.tkeys.p, cw.tvals.p, cw.tsbox.p, s.nSF, cw.ttab_key.p, cw.ttab_start.p, cw.tab_mask }, eg{ cw.ekeys.p, cw.evals.p, cw.esbox.p, s.nSE, cw.etab_key.p, cw.etab_start.p, cw.tab_mask };
-    if (v1 > v0 && s.nSF > 0)
-        k_ccd_query_pt<<<nblk((long long)(v1 - v0) * 32, 128), 128, 0, st>>>(s, cw.grid.p, cw.vbox.p, tg, w.vmin.p, w.vmax.p, radius, v0, v1, out);
-    if (e1 > e0 && s.nSE > 1)
-        k_ccd_query_ee<<<nblk((long long)(e1 - e0) * 32, 128), 128, 0, st>>>(s, cw.grid.p, cw.ebox.p, eg, w.vmin.p, w.vmax.p, radius, e0, e1, out);
+    CKD(cudaMemsetAsync(cw.counters.p + 8, 0, 2 * sizeof(int), st));
+    unsigned* nPairs = reinterpret_cast<unsigned*>(cw.counters.p + 8);
+    PairOut ppt{ cw.bp_pairs.p, nPairs, (unsigned)cw.bp_cap, w.counters.p + 14 }, pee{ cw.bp_pairs.p + cw.bp_cap, nPairs + 1, (unsigned)cw.bp_cap, w.counters.p + 14 };
+    if (v1 > v0 && s.nSF > 0) {
+        k_ccd_pairs_pt<<<nblk((long long)(v1 - v0) * 32, 256), 256, 0, st>>>(cw.grid.p, cw.vbox.p, tg, radius, v0, v1, ppt);
+        k_ccd_filter_pt<<<nblk((long long)cw.bp_cap, 256), 256, 0, st>>>(s, ppt.pairs, ppt.n, w.vmin.p, w.vmax.p, out);
+    }
+    if (e1 > e0 && s.nSE > 1) {
+        k_ccd_pairs_ee<<<nblk((long long)(e1 - e0) * 32, 256), 256, 0, st>>>(cw.grid.p, cw.ebox.p, eg, radius, e0, e1, pee);
+        k_ccd_filter_ee<<<nblk((long long)cw.bp_cap, 256), 256, 0, st>>>(s, pee.pairs, pee.n, w.vmin.p, w.vmax.p, out);
+    }
+    ctx->launches += 2;
     ctx->launches += 2;
     unsigned long long* hn = reinterpret_cast<unsigned long long*>(ctx->h_scalar);
     int* ho = reinterpret_cast<int*>(ctx->h_scalar + 2);
