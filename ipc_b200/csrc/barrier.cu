@@ -261,132 +261,155 @@ __global__ void __launch_bounds__(64) k_barrier_hessian_build(BarrierArgs p, dou
 #undef HE
 }
 
-// round-robin tournament (circle method): 11 rounds of 6 disjoint pairs over 12 indices.  Index 11 is fixed, the others sit on a
-// ring: ring position k of round r holds index (r+k)%11; position 0 plays index 11, position k plays position 11-k.
-// Everything is computed arithmetically -- a lookup table indexed per lane would serialise in the constant cache.
-DEV int rr_partner(int r, int i)
+// -----------------------------------------------------------------------------------------------------------
+// PSD projection of the 12x12 pair Hessians (IglUtils::makePD, IglUtils.hpp:112-133), parallel-order cyclic Jacobi held
+// entirely in registers.  Six lanes share one matrix: lane k owns the columns sitting at positions 2k ("top") and 2k+1
+// ("bottom") of A and of the accumulated eigenvector matrix V, so the column half of a rotation is lane-local and the row half
+// only needs the six (c, s) pairs of the round.  Between rounds the columns travel round a Brent-Luk ring (position 0 fixed,
+// tops move one lane up, bottoms one lane down) and the rows of A follow the same permutation, which costs nothing because
+// every moved value passes through a shuffle whose destination register is chosen at compile time.  After 11 rounds (one sweep)
+// the ring is back where it started.  Five matrices per warp (30 lanes).
+constexpr int kProjWarps = 4;      // warps per CTA
+constexpr int kProjPerWarp = 5;    // matrices per warp
+__host__ __device__ constexpr int ring_next(int i) // where the row/column at position i sits after one round
 {
-    if (i == 11) return r % 11;
-    const int k = (i - r + 11) % 11;
-    return k == 0 ? 11 : (r + 11 - k) % 11;
-}
-DEV int rr_rot(int r, int i) // which of the round's 6 rotations acts on index i
-{
-    if (i == 11) return 0;
-    const int k = (i - r + 11) % 11;
-    return min(k, 11 - k);
+    return i == 0 ? 0 : i == 1 ? 2 : i == 10 ? 11 : (i % 2 == 0) ? i + 2 : i - 2;
 }
 
-constexpr int kProjWarps = 8; // warps (pairs) per CTA in the projection kernel
-
-__global__ void __launch_bounds__(32 * kProjWarps) k_barrier_hessian_project(BarrierArgs p, const double* __restrict__ Hraw, const int* __restrict__ rows_in,
-    double* __restrict__ a, int* __restrict__ err)
+__global__ void __launch_bounds__(32 * kProjWarps) k_barrier_hessian_project(int n, double* __restrict__ H)
 {
-    __shared__ double sA[kProjWarps][144];
-    __shared__ double sV[kProjWarps][144];
-    __shared__ double sCS[kProjWarps][12]; // c (0..5) and s (6..11) of the round's rotations
-    __shared__ int sOff[kProjWarps][48];
-    __shared__ unsigned short sTab[11][144]; // per (round, element): partner row/col, rotation ids, sign bits
-    for (int t = threadIdx.x; t < 11 * 144; t += blockDim.x) {
-        const int r = t / 144, e = t % 144, i = e / 12, j = e % 12;
-        const int ip = rr_partner(r, i), jp = rr_partner(r, j);
-        sTab[r][e] = (unsigned short)(ip | (jp << 4) | (rr_rot(r, i) << 8) | (rr_rot(r, j) << 11) | ((i < ip ? 1 : 0) << 14) | ((j < jp ? 1 : 0) << 15));
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int grp = lane / 6, k = lane - 6 * grp, base = 6 * grp;
+    const int warp = blockIdx.x * kProjWarps + (threadIdx.x >> 5);
+    const int c = warp * kProjPerWarp + grp;
+    const bool live = grp < kProjPerWarp && c < n;
+    double AT[12], AB[12], VT[12], VB[12];
+    double* H0 = H + (size_t)(live ? c : 0) * 144;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        AT[i] = live ? H0[(2 * k) * 12 + i] : ((i == 2 * k) ? 1.0 : 0.0);
+        AB[i] = live ? H0[(2 * k + 1) * 12 + i] : ((i == 2 * k + 1) ? 1.0 : 0.0);
+        VT[i] = (i == 2 * k) ? 1.0 : 0.0;
+        VB[i] = (i == 2 * k + 1) ? 1.0 : 0.0;
     }
-    __syncthreads();
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int c = blockIdx.x * kProjWarps + wib;
-    if (c >= p.nC + p.nP) return;
-    double* A = sA[wib];
-    double* Vv = sV[wib];
-    double* cs = sCS[wib];
-    const double* H0 = Hraw + (size_t)c * 144;
-    for (int e = lane; e < 144; e += 32) {
-        A[e] = H0[e];
-        Vv[e] = ((e / 12) == (e % 12)) ? 1.0 : 0.0;
-    }
-    __syncwarp();
+    bool done = !live;
     for (int sweep = 0; sweep < 30; ++sweep) {
-        // convergence: off-diagonal mass vs diagonal mass
-        double off = 0.0, dg = 0.0;
-        for (int e = lane; e < 144; e += 32) {
-            const double v = A[e];
-            if ((e / 12) == (e % 12)) dg += v * v;
-            else off += v * v;
+        // convergence of each matrix: off-diagonal mass against diagonal mass
+        {
+            double off = 0.0, dg = 0.0;
+#pragma unroll
+            for (int i = 0; i < 12; ++i) {
+                const double t2 = AT[i] * AT[i], b2 = AB[i] * AB[i];
+                off += ((i == 2 * k) ? 0.0 : t2) + ((i == 2 * k + 1) ? 0.0 : b2);
+                dg += ((i == 2 * k) ? t2 : 0.0) + ((i == 2 * k + 1) ? b2 : 0.0);
+            }
+            const double o2 = off + __shfl_sync(full, off, base + (k + 3) % 6);
+            const double d2 = dg + __shfl_sync(full, dg, base + (k + 3) % 6);
+            const double o3 = o2 + __shfl_sync(full, o2, base + (k + 1) % 6) + __shfl_sync(full, o2, base + (k + 2) % 6);
+            const double d3 = d2 + __shfl_sync(full, d2, base + (k + 1) % 6) + __shfl_sync(full, d2, base + (k + 2) % 6);
+            // the sums are evaluated in a different order on each lane; take lane 0's so the whole group agrees
+            const double offg = __shfl_sync(full, o3, base), dgg = __shfl_sync(full, d3, base);
+            if (offg <= 2e-26 * dgg || offg <= 1e-300) done = true;
         }
-        off = warp_sum(off);
-        dg = warp_sum(dg);
-        if (off <= 2e-26 * dg || off <= 1e-300) break;
+        if (__all_sync(full, done)) break;
         for (int r = 0; r < 11; ++r) {
-            if (lane < 6) {
-                const int x = (lane == 0) ? (r % 11) : (r + lane) % 11, y = (lane == 0) ? 11 : (r + 11 - lane) % 11;
-                const int pI = min(x, y), q = max(x, y);
-                const double apq = A[pI * 12 + q];
-                double cc = 1.0, ss = 0.0;
-                if (apq != 0.0) {
-                    const double theta = (A[q * 12 + q] - A[pI * 12 + pI]) / (2.0 * apq);
-                    const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                    cc = 1.0 / sqrt(t * t + 1.0);
-                    ss = t * cc;
-                }
-                cs[lane] = cc;
-                cs[6 + lane] = ss;
-            }
-            __syncwarp();
-            // A <- J^T A J with J = product of the 6 disjoint rotations; element (i,j) mixes rows {i,i'} and columns {j,j'}
-            double newA[5], newV[5];
+            double app = 0.0, aqq = 0.0, apq = 0.0;
 #pragma unroll
-            for (int k = 0; k < 5; ++k) {
-                const int e = lane + 32 * k;
-                if (e < 144) {
-                    const int i = e / 12, j = e - 12 * i;
-                    const unsigned tb = sTab[r][e];
-                    const int ip = tb & 15, jp = (tb >> 4) & 15, ri = (tb >> 8) & 7, rj = (tb >> 11) & 7;
-                    // rotation acting on index i: if i is the "p" of its pair, x_i' = c x_i - s x_ip ; if "q": x_i' = s x_ip + c x_i
-                    const double ci = cs[ri], si = (tb & 0x4000u) ? -cs[6 + ri] : cs[6 + ri];
-                    const double cj = cs[rj], sj = (tb & 0x8000u) ? -cs[6 + rj] : cs[6 + rj];
-                    // y = c*x_self + sgn*s*x_partner  (p: c x_p - s x_q ; q: s x_p + c x_q)
-                    const double a_ij = A[i * 12 + j], a_ipj = A[ip * 12 + j], a_ijp = A[i * 12 + jp], a_ipjp = A[ip * 12 + jp];
-                    const double row_j = ci * a_ij + si * a_ipj;    // (J^T A)[i][j]
-                    const double row_jp = ci * a_ijp + si * a_ipjp; // (J^T A)[i][jp]
-                    newA[k] = cj * row_j + sj * row_jp;
-                    newV[k] = cj * Vv[i * 12 + j] + sj * Vv[i * 12 + jp]; // V <- V J
+            for (int m = 0; m < 6; ++m)
+                if (k == m) {
+                    app = AT[2 * m];
+                    aqq = AB[2 * m + 1];
+                    apq = AB[2 * m];
                 }
+            double cc = 1.0, ss = 0.0;
+            if (!done && apq != 0.0) {
+                const double theta = (aqq - app) / (2.0 * apq);
+                const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                cc = 1.0 / sqrt(t * t + 1.0);
+                ss = t * cc;
             }
-            __syncwarp();
+            // columns (own pair): col_p' = c col_p - s col_q, col_q' = s col_p + c col_q, for A and V
 #pragma unroll
-            for (int k = 0; k < 5; ++k) {
-                const int e = lane + 32 * k;
-                if (e < 144) {
-                    A[e] = newA[k];
-                    Vv[e] = newV[k];
-                }
+            for (int i = 0; i < 12; ++i) {
+                const double a0 = AT[i], a1 = AB[i], v0 = VT[i], v1 = VB[i];
+                AT[i] = cc * a0 - ss * a1;
+                AB[i] = ss * a0 + cc * a1;
+                VT[i] = cc * v0 - ss * v1;
+                VB[i] = ss * v0 + cc * v1;
             }
-            __syncwarp();
+            // rows (all six pairs of the round)
+#pragma unroll
+            for (int m = 0; m < 6; ++m) {
+                const double cm = __shfl_sync(full, cc, base + m), sm = __shfl_sync(full, ss, base + m);
+                const double t0 = AT[2 * m], t1 = AT[2 * m + 1], b0 = AB[2 * m], b1 = AB[2 * m + 1];
+                AT[2 * m] = cm * t0 - sm * t1;
+                AT[2 * m + 1] = sm * t0 + cm * t1;
+                AB[2 * m] = cm * b0 - sm * b1;
+                AB[2 * m + 1] = sm * b0 + cm * b1;
+            }
+            // ring move
+            double nAT[12], nAB[12];
+#pragma unroll
+            for (int i = 0; i < 12; ++i) {
+                const double upA = __shfl_up_sync(full, (k == 0) ? AB[i] : AT[i], 1);
+                const double dnA = __shfl_down_sync(full, AB[i], 1);
+                nAT[ring_next(i)] = (k == 0) ? AT[i] : upA;
+                nAB[ring_next(i)] = (k == 5) ? AT[i] : dnA;
+                const double upV = __shfl_up_sync(full, (k == 0) ? VB[i] : VT[i], 1);
+                const double dnV = __shfl_down_sync(full, VB[i], 1);
+                const double vt = VT[i];
+                VT[i] = (k == 0) ? vt : upV;
+                VB[i] = (k == 5) ? vt : dnV;
+            }
+#pragma unroll
+            for (int i = 0; i < 12; ++i) {
+                AT[i] = nAT[i];
+                AB[i] = nAB[i];
+            }
         }
     }
     // clamp: lambda_min >= 0 -> unchanged (IglUtils.hpp:123-125)
-    bool neg = false;
-    if (lane < 12) neg = A[lane * 12 + lane] < 0.0;
-    neg = __any_sync(0xffffffffu, neg);
-    double out[5];
+    double lt = 0.0, lb = 0.0;
 #pragma unroll
-    for (int k = 0; k < 5; ++k) {
-        const int e = lane + 32 * k;
-        out[k] = 0.0;
-        if (e < 144) {
-            if (!neg) out[k] = H0[e];
-            else {
-                const int i = e / 12, j = e % 12;
-                double sacc = 0.0;
+    for (int m = 0; m < 6; ++m)
+        if (k == m) {
+            lt = AT[2 * m];
+            lb = AB[2 * m + 1];
+        }
+    const bool neg_lane = live && (lt < 0.0 || lb < 0.0);
+    const unsigned negmask = __ballot_sync(full, neg_lane);
+    const bool neg = (negmask >> base) & 0x3fu;
+    if (!__any_sync(full, neg)) return;
+    lt = fmax(lt, 0.0);
+    lb = fmax(lb, 0.0);
 #pragma unroll
-                for (int q = 0; q < 12; ++q) {
-                    const double lam = A[q * 12 + q];
-                    if (lam > 0.0) sacc += Vv[i * 12 + q] * lam * Vv[j * 12 + q];
-                }
-                out[k] = sacc;
+    for (int i = 0; i < 12; ++i) {
+        const double wt = lt * VT[i], wb = lb * VB[i];
+#pragma unroll
+        for (int j = i; j < 12; ++j) {
+            const double part = wt * VT[j] + wb * VB[j];
+            const double x2 = part + __shfl_sync(full, part, base + (k + 3) % 6);
+            const double x3 = x2 + __shfl_sync(full, x2, base + (k + 1) % 6) + __shfl_sync(full, x2, base + (k + 2) % 6);
+            const double tot = __shfl_sync(full, x3, base); // one summation order for both triangles
+            if (neg && live && k == ((i * 12 + j) % 6)) {
+                H0[i * 12 + j] = tot;
+                H0[j * 12 + i] = tot;
             }
         }
     }
+}
+
+// scatter of the projected pair Hessians into the CSR values (upper-triangular 3x3 blocks, LinSysSolver.hpp:207-265)
+constexpr int kScatWarps = 8;
+__global__ void __launch_bounds__(32 * kScatWarps) k_barrier_hessian_scatter(BarrierArgs p, const double* __restrict__ H, const int* __restrict__ rows_in,
+    double* __restrict__ a, int* __restrict__ err)
+{
+    __shared__ int sOff[kScatWarps][48];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int c = blockIdx.x * kScatWarps + wib;
+    if (c >= p.nC + p.nP) return;
+    const double* H0 = H + (size_t)c * 144;
     // CSR offsets of the 16 vertex blocks x 3 rows (upper-triangular blocks only); -1 = skip, -2 = missing in the pattern
     int rows[4];
 #pragma unroll
@@ -405,8 +428,8 @@ __global__ void __launch_bounds__(32 * kProjWarps) k_barrier_hessian_project(Bar
     }
     __syncwarp();
 #pragma unroll
-    for (int k = 0; k < 5; ++k) {
-        const int e = lane + 32 * k;
+    for (int kk = 0; kk < 5; ++kk) {
+        const int e = lane + 32 * kk;
         if (e < 144) {
             const int i = e / 12, j = e % 12;
             const int bi = i / 3, r = i % 3, bj = j / 3, q = j % 3;
@@ -414,7 +437,7 @@ __global__ void __launch_bounds__(32 * kProjWarps) k_barrier_hessian_project(Bar
             if (o == -2) atomicExch(err, 1);
             else if (o != -1) {
                 if (rows[bi] == rows[bj] && q < r) continue; // strictly lower part of a diagonal block
-                atomicAdd(a + o + q, out[k]);
+                atomicAdd(a + o + q, H0[e]);
             }
         }
     }
@@ -437,7 +460,9 @@ void barrier_hessian(const BarrierArgs& p, double* a, int* err, double* Hraw, in
     const int n = p.nC + p.nP;
     if (n <= 0) return;
     k_barrier_hessian_build<<<(n + 63) / 64, 64, 0, st>>>(p, Hraw, rows);
-    k_barrier_hessian_project<<<(n + kProjWarps - 1) / kProjWarps, 32 * kProjWarps, 0, st>>>(p, Hraw, rows, a, err);
+    const int per_cta = kProjWarps * kProjPerWarp;
+    k_barrier_hessian_project<<<(n + per_cta - 1) / per_cta, 32 * kProjWarps, 0, st>>>(n, Hraw);
+    k_barrier_hessian_scatter<<<(n + kScatWarps - 1) / kScatWarps, 32 * kScatWarps, 0, st>>>(p, Hraw, rows, a, err);
 }
 
 } // namespace ipcgpu

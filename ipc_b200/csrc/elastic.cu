@@ -126,7 +126,7 @@ DEV void tma_store_tile(void* gdst, const void* ssrc, unsigned bytes)
 // as the slot is computed; only two such regions live in shared memory at a time (9 KB instead of 46 KB per CTA), which lifts the
 // shared-memory occupancy limit of the first version of this kernel.
 template <int ENERGY, bool NEED_G, bool NEED_H>
-__global__ void __launch_bounds__(kHessTile) k_elastic_grad_hess(ElasticArgs p, double coef, int projectSPD,
+__global__ void __launch_bounds__(kHessTile, 8) k_elastic_grad_hess(ElasticArgs p, double coef, int projectSPD,
     double* __restrict__ gcont /* 12 per LOCAL tet */, double* __restrict__ hblk /* tile-major, 78 per LOCAL tet */)
 {
     extern __shared__ __align__(128) double smem[];
