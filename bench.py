@@ -249,6 +249,7 @@ def main():
         a, nc = ctx.ccd_full(TI_TOL, err_vf, err_ee, a)
         stats["alpha"], stats["ccd_candidates"] = a, nc
         stats["ccd_full_stats"] = ctx.ccd_stats() + ctx.ccd_stats_ex()
+        stats["ccd_warp_pass_cycles_longest_total"] = ctx.ccd_stats_timing()
 
     def step_e2e():
         ctx.set_state(hV.array)
@@ -326,7 +327,7 @@ def main():
                                    f"dHat=(1e-3 bboxDiag)^2, {n_active} active pairs + {n_para} mollified, {n_cand} partial-CCD candidates, "
                                    f"{stats.get('ccd_candidates', 0)} full-CCD candidates, TI tol 1e-6",
                        "stages": STAGES_RUN, "csr_nnz": int(nnz), "step_bound_alpha": stats.get("alpha"),
-                       "full_ccd_candidates_survivors_warnings_deferred_boxesThreadPass_boxesWarpPass": stats.get("ccd_full_stats"), "l2": "working set (78 doubles/tet = %.0f MB + CSR %.0f MB) exceeds the 126 MB L2" % (m.nT * 624 / 1e6, nnz * 8 / 1e6),
+                       "full_ccd_candidates_survivors_warnings_deferred_boxesThreadPass_boxesWarpPass": stats.get("ccd_full_stats"), "full_ccd_warp_pass_sm_cycles_longest_pair_and_total": stats.get("ccd_warp_pass_cycles_longest_total"), "l2": "working set (78 doubles/tet = %.0f MB + CSR %.0f MB) exceeds the 126 MB L2" % (m.nT * 624 / 1e6, nnz * 8 / 1e6),
                        "partition": f"tets block-partitioned over {world} rank(s); NCCL sum-allreduce of [gradient, CSR values], min-allreduce of the step"},
             "stage_ms": {k: v[0] / args.steps for k, v in prof.items()},
             "roofline": {"bound": "hbm", "kernel": "k_elastic_grad_hess<NH,g,H>", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",

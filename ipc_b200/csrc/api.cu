@@ -597,6 +597,13 @@ int ipcgpu_ccd_stats_ex(ipcgpu_ctx* ctx, uint64_t* deferred, uint64_t* boxes_thr
     return IPCGPU_OK;
 }
 
+int ipcgpu_ccd_stats_timing(ipcgpu_ctx* ctx, uint64_t* longest_pair_cycles, uint64_t* total_pair_cycles)
+{
+    if (longest_pair_cycles) *longest_pair_cycles = ctx->ccd.last_longest_cycles;
+    if (total_pair_cycles) *total_pair_cycles = ctx->ccd.last_total_cycles;
+    return IPCGPU_OK;
+}
+
 int ipcgpu_set_pair_capacity(ipcgpu_ctx* ctx, int capacity)
 {
     REQUIRE(capacity > 0, IPCGPU_ERR_ARG, "capacity must be positive");

@@ -74,18 +74,19 @@ struct SortedGrid {
     const Box* boxes;               // primitive boxes gathered in sorted order (coalesced candidate scan)
     int n;
     const unsigned* tab_key;        // hash table: cell key (0xffffffff = empty)
-    const int* tab_start;           //             first entry of that cell in the sorted arrays
+    const int2* tab_range;          //             [first, last+1) entries of that cell in the sorted arrays
     unsigned tab_mask;              // table size - 1 (power of two)
 };
 
 DEV unsigned cell_hash(unsigned key) { return key * 2654435761u; }
-DEV int cell_lookup(const SortedGrid& sg, unsigned key)
+DEV int2 cell_lookup(const SortedGrid& sg, unsigned key)
 {
     unsigned h = cell_hash(key) & sg.tab_mask;
     for (;;) {
         const unsigned k = sg.tab_key[h];
-        if (k == key) return sg.tab_start[h];
-        if (k == 0xffffffffu) return -1;
+        const int2 r = sg.tab_range[h]; // issued together with the key: one memory latency per probe
+        if (k == key) return r;
+        if (k == 0xffffffffu) return make_int2(0x7fffffff, -1);
         h = (h + 1) & sg.tab_mask;
     }
 }
@@ -95,11 +96,15 @@ DEV bool boxes_overlap(const Box& a, const Box& b)
     return !(a.lo[0] > b.hi[0] || b.lo[0] > a.hi[0] || a.lo[1] > b.hi[1] || b.lo[1] > a.hi[1] || a.lo[2] > b.hi[2] || b.lo[2] > a.hi[2]);
 }
 
-// warp-cooperative scan: calls f(id, box) on every registered primitive whose box overlaps the (already inflated) query box.
-// All 32 lanes must call this together; f runs on the lane that found the candidate.
+// warp-cooperative scan: calls f(hit, id, box) with hit = true on every registered primitive whose box overlaps the (already
+// inflated) query box.  All 32 lanes must call this together and f is called by all 32 lanes together (hit = false on the lanes
+// that have nothing), so that f can aggregate its output over the warp.
+// The <= 27 cells are looked up by 27 lanes at once; the <= 9 rows (runs of consecutive entries) are then walked as ONE flattened
+// index range, so that a query costs ceil(total/32) independent, coalesced loads instead of a dependent chain per row.
 template <typename F>
 DEV void warp_scan_candidates(const Grid& g, const SortedGrid& sg, const Box& qb, int lane, F f)
 {
+    const unsigned full = 0xffffffffu;
     int c0[3], c1[3];
     cell_range(g, qb, c0, c1);
     const int x0 = max(c0[0] - 1, 0), x1 = c1[0];
@@ -107,24 +112,78 @@ DEV void warp_scan_candidates(const Grid& g, const SortedGrid& sg, const Box& qb
     const int ny = c1[1] - y0 + 1, nz = c1[2] - z0 + 1; // <= 3 each
     const int nrows = ny * nz;
     // lane 3r+dx looks up cell (x0+dx) of row r
-    int mine = -1;
+    int2 mine = make_int2(0x7fffffff, -1);
     {
         const int r = lane / 3, dx = lane - 3 * r;
         if (r < nrows && x0 + dx <= x1) mine = cell_lookup(sg, (unsigned)cell_key(g, x0 + dx, y0 + r % ny, z0 + r / ny));
     }
-    for (int r = 0; r < nrows; ++r) {
-        const int s0 = __shfl_sync(0xffffffffu, mine, 3 * r), s1 = __shfl_sync(0xffffffffu, mine, 3 * r + 1), s2 = __shfl_sync(0xffffffffu, mine, 3 * r + 2);
-        const int start = s0 >= 0 ? s0 : (s1 >= 0 ? s1 : s2); // cells of one row are consecutive keys => consecutive runs
-        if (start < 0) continue;
-        const unsigned long long key_hi = cell_key(g, x1, y0 + r % ny, z0 + r / ny);
-        for (int k = start + lane;; k += 32) {
-            const bool in = k < sg.n && sg.keys[k] <= key_hi;
-            if (in) {
-                const Box b = sg.boxes[k];
-                if (boxes_overlap(qb, b)) f(sg.ids[k], b);
-            }
-            if (!__any_sync(0xffffffffu, in)) break;
+    // lane L (and L+9, L+18, ...) gets the run of row L % 9: cells of one row are consecutive keys => consecutive entries
+    const int rr = lane % 9;
+    const int s0 = __shfl_sync(full, mine.x, 3 * rr), s1 = __shfl_sync(full, mine.x, 3 * rr + 1), s2 = __shfl_sync(full, mine.x, 3 * rr + 2);
+    const int e0 = __shfl_sync(full, mine.y, 3 * rr), e1 = __shfl_sync(full, mine.y, 3 * rr + 1), e2 = __shfl_sync(full, mine.y, 3 * rr + 2);
+    const int rend = max(e0, max(e1, e2));
+    const int rstart = (rend > 0) ? min(s0, min(s1, s2)) : 0; // empty row: harmless start
+    const int rlen = (lane < 9 && rend > rstart) ? rend - rstart : 0;
+    int incl = rlen; // inclusive prefix over lanes 0..8
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        const int t = __shfl_up_sync(full, incl, o);
+        if (lane >= o) incl += t;
+    }
+    int inc[9], st[9];
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+        inc[r] = __shfl_sync(full, incl, r);
+        st[r] = __shfl_sync(full, rstart, r);
+    }
+    const int total = inc[8];
+    auto locate = [&](int j) { // flattened index -> entry
+        int k = st[0] + j;
+#pragma unroll
+        for (int r = 1; r < 9; ++r)
+            if (j >= inc[r - 1]) k = st[r] + (j - inc[r - 1]);
+        return k;
+    };
+    // software pipeline: the loads of iteration i+1 are in flight while f handles iteration i
+    Box bn = qb;
+    int idn = -1;
+    if (lane < total) {
+        const int k = locate(lane);
+        bn = sg.boxes[k];
+        idn = sg.ids[k];
+    }
+    for (int j = lane; j - lane < total; j += 32) {
+        const Box b = bn;
+        const int id = idn;
+        const bool in = j < total;
+        if (j + 32 < total) {
+            const int k = locate(j + 32);
+            bn = sg.boxes[k];
+            idn = sg.ids[k];
         }
+        f(in && boxes_overlap(qb, b), id, b); // convergent: every lane calls f
+    }
+}
+
+// warp-aggregated append: one atomicAdd per warp for all lanes with want = true.  Must be called by all 32 lanes.
+struct PairOut {
+    int2* pairs;
+    unsigned* n;
+    unsigned cap;
+    int* overflow;
+};
+DEV void warp_push_pair(const PairOut& o, bool want, int a, int b, int lane)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, want);
+    if (m == 0) return;
+    const int leader = __ffs(m) - 1;
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(o.n, (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (want) {
+        const unsigned i = base + __popc(m & ((1u << lane) - 1u));
+        if (i < o.cap) o.pairs[i] = make_int2(a, b);
+        else atomicExch(o.overflow, 1);
     }
 }
 

@@ -113,24 +113,18 @@ struct CandOut {
 };
 DEV void push_cand(const CandOut& o, int2 c)
 {
-    unsigned long long i = atomicAdd(o.n, 1ull);
+    // aggregated over the lanes that are active here: one atomic per warp
+    const unsigned m = __activemask();
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(o.n, (unsigned long long)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    const unsigned long long i = base + __popc(m & ((1u << lane) - 1u));
     if (i < o.cap) o.cand[i] = c;
     else atomicExch(o.overflow, 1);
 }
 
 // ---- phase 1: one WARP per query primitive, boxes only: (query, partner) pairs whose swept boxes are within one reference voxel
-struct PairOut {
-    int2* pairs;
-    unsigned* n;
-    unsigned cap;
-    int* overflow;
-};
-DEV void push_pair(const PairOut& o, int a, int b)
-{
-    const unsigned i = atomicAdd(o.n, 1u);
-    if (i < o.cap) o.pairs[i] = make_int2(a, b);
-    else atomicExch(o.overflow, 1);
-}
 __global__ void __launch_bounds__(256) k_ccd_pairs_pt(const Grid* __restrict__ gp, const Box* __restrict__ vboxes, SortedGrid tg, double radius, int first, int last, PairOut out)
 {
     const int svI = first + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -139,7 +133,7 @@ __global__ void __launch_bounds__(256) k_ccd_pairs_pt(const Grid* __restrict__ g
     const Grid g = *gp;
     Box qb = vboxes[svI];
     for (int k = 0; k < 3; ++k) { qb.lo[k] -= radius; qb.hi[k] += radius; }
-    warp_scan_candidates(g, tg, qb, lane, [&](int sfI, const Box&) { push_pair(out, svI, sfI); });
+    warp_scan_candidates(g, tg, qb, lane, [&](bool hit, int sfI, const Box&) { warp_push_pair(out, hit, svI, sfI, lane); });
 }
 __global__ void __launch_bounds__(256) k_ccd_pairs_ee(const Grid* __restrict__ gp, const Box* __restrict__ eboxes, SortedGrid eg, double radius, int first, int last, PairOut out)
 {
@@ -150,13 +144,12 @@ __global__ void __launch_bounds__(256) k_ccd_pairs_ee(const Grid* __restrict__ g
     const Box eb = eboxes[eI];
     Box qb = eb;
     for (int k = 0; k < 3; ++k) { qb.lo[k] -= radius; qb.hi[k] += radius; }
-    warp_scan_candidates(g, eg, qb, lane, [&](int eJ, const Box& jb) {
-        if (eJ <= eI) return;
+    warp_scan_candidates(g, eg, qb, lane, [&](bool hit, int eJ, const Box& jb) {
         // swept-AABB test of queryEdgeForEdgesWithBBoxCheck (SpatialHash.hpp:819-828); the boxes hold {x, x+alpha p}
-        bool sep = false;
+        bool sep = !hit || eJ <= eI;
 #pragma unroll
         for (int c = 0; c < 3; ++c) sep = sep || (jb.lo[c] - eb.hi[c] > 0.0) || (eb.lo[c] - jb.hi[c] > 0.0);
-        if (!sep) push_pair(out, eI, eJ);
+        warp_push_pair(out, !sep, eI, eJ, lane);
     });
 }
 // ---- phase 2: one THREAD per pair: the reference's voxel-range overlap (its hash query) and the index filters
@@ -398,7 +391,7 @@ DEV bool sum_le_1(unsigned long long an, int ak, unsigned long long bn, int bk)
 constexpr unsigned F_ZERO = 1u << 24; // zero_in flag stored in DBox::kk
 
 constexpr int kStage2WarpsPerCtaDev = 4;
-constexpr int kSmemLevel = 192;
+constexpr int kSmemLevel = 184;
 constexpr int kWideLevel = 10; // levels with at least this many boxes are evaluated box-parallel, narrower ones corner-parallel    // boxes per level buffer kept in shared memory by the warp-level pass
 
 // group helpers: W = 32 (one warp per pair) or W = 1 (one thread per pair, no cross-lane traffic)
@@ -888,6 +881,21 @@ __device__ int ti_root_finder_cp(const TiPair& P, const double* tol, double co_t
     return 0;
 }
 
+// out-of-line instances for the warp-level pass: four inlined copies (VF/EE x the two calls of pair_ccd) of both root finders cost
+// 255 registers plus spills and an instruction footprint that starves the fetch unit
+template <bool VF>
+__device__ __noinline__ int ti_root_finder_cp_call(const TiPair& P, const double* tol, double co_tol, double max_t, const double* err, double ms, int max_itr, DBox* sA,
+    DBox* sB, int lane, double& toi, double& out_tol, int* __restrict__ warn, const unsigned long long* best)
+{
+    return ti_root_finder_cp<VF>(P, tol, co_tol, max_t, err, ms, max_itr, sA, sB, lane, toi, out_tol, warn, best);
+}
+template <bool VF>
+__device__ __noinline__ int ti_root_finder_warp_call(const TiPair& P, const double* tol, double co_tol, double max_t, const double* err, double ms, int max_itr, DBox* bufA,
+    DBox* bufB, int cap, int lane, double& toi, double& out_tol, int* __restrict__ warn, const unsigned long long* best)
+{
+    return ti_root_finder<VF, 32>(P, tol, co_tol, max_t, err, ms, max_itr, bufA, bufB, cap, lane, toi, out_tol, warn, nullptr, nullptr, 0, best);
+}
+
 // vertexFaceCCD_double / edgeEdgeCCD_double including the no_zero_toi refinement loop; returns 0 / 1 / 2 (deferred)
 template <bool VF, int W>
 __device__ int ti_ccd(const TiPair& P, const double* err, double ms, double tolerance, double t_max, int max_itr, DBox* bufA, DBox* bufB, int cap, int lane,
@@ -901,8 +909,8 @@ __device__ int ti_ccd(const TiPair& P, const double* err, double ms, double tole
         width_tolerances<VF>(P, tolerance_in, tol);
         int rc;
         if (W == 32 && sA) {
-            rc = ti_root_finder_cp<VF>(P, tol, tolerance_in, t_max, err, ms_in, max_itr, sA, sB, lane, toi, out_tol, warn, best);
-            if (rc == -1) rc = ti_root_finder<VF, W>(P, tol, tolerance_in, t_max, err, ms_in, max_itr, bufA, bufB, cap, lane, toi, out_tol, warn, nullptr, nullptr, 0, best);
+            rc = ti_root_finder_cp_call<VF>(P, tol, tolerance_in, t_max, err, ms_in, max_itr, sA, sB, lane, toi, out_tol, warn, best);
+            if (rc == -1) rc = ti_root_finder_warp_call<VF>(P, tol, tolerance_in, t_max, err, ms_in, max_itr, bufA, bufB, cap, lane, toi, out_tol, warn, best);
         }
         else rc = ti_root_finder<VF, W>(P, tol, tolerance_in, t_max, err, ms_in, max_itr, bufA, bufB, cap, lane, toi, out_tol, warn, sA, sB, thread_budget, best);
         if (rc == 2) return 2;
@@ -973,10 +981,11 @@ __global__ void __launch_bounds__(128) k_ti_stage15(NarrowArgs a, const unsigned
     }
 }
 
-__global__ void __launch_bounds__(128) k_ti_stage2(NarrowArgs a, const unsigned* __restrict__ survivors, const unsigned* __restrict__ nSurvPtr, unsigned* __restrict__ work,
+__global__ void __launch_bounds__(128, 3) k_ti_stage2(NarrowArgs a, const unsigned* __restrict__ survivors, const unsigned* __restrict__ nSurvPtr, unsigned* __restrict__ work,
     DBox* __restrict__ scratch, int cap, unsigned long long* __restrict__ min_ord, int* __restrict__ warn)
 {
     __shared__ DBox sLevels[kStage2WarpsPerCtaDev][2][kSmemLevel];
+    __shared__ TiPair sPair[kStage2WarpsPerCtaDev];
     const int lane = threadIdx.x & 31;
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     DBox* sA = sLevels[threadIdx.x >> 5][0];
@@ -990,12 +999,24 @@ __global__ void __launch_bounds__(128) k_ti_stage2(NarrowArgs a, const unsigned*
         w = __shfl_sync(0xffffffffu, w, 0);
         if (w >= nSurv) break;
         bool vf;
-        int v[4];
-        TiPair P;
-        load_pair(a.s, a.dir, a.cand[survivors[w]], vf, v, P);
+        {
+            // the pair's 24 coordinates live in shared memory: the warp-level search only needs them 8 at a time per lane
+            int v[4];
+            TiPair Pl;
+            load_pair(a.s, a.dir, a.cand[survivors[w]], vf, v, Pl);
+            if (lane == 0) sPair[threadIdx.x >> 5] = Pl;
+            __syncwarp();
+        }
+        const TiPair& P = sPair[threadIdx.x >> 5];
         double toi;
+        const long long t0 = clock64();
         const int hit = pair_ccd<32>(vf, P, a, bufA, bufB, cap, lane, toi, warn, sA, sB);
         if (hit && lane == 0) atomicMin(min_ord, dbl_to_ord(toi));
+        if (lane == 0) { // diagnostics: the longest pair bounds this pass from below
+            const unsigned dt = (unsigned)((clock64() - t0) >> 6);
+            atomicMax(reinterpret_cast<unsigned*>(warn + 2), dt);
+            atomicAdd(reinterpret_cast<unsigned*>(warn + 3), dt);
+        }
         __syncwarp();
     }
 }
@@ -1091,7 +1112,9 @@ int ccd_narrow(ipcgpu_ctx* ctx, const int2* cand, unsigned long long nCand, doub
     std::memcpy(&m, h, sizeof(double));
     w.last_survivors = (unsigned)hi[0];
     w.last_warnings = hi[3];
-    w.last_deferred = (unsigned)hi[4] * 1000000ull + (unsigned)hi[5]; // passA deferred * 1e6 + passB deferred
+    w.last_deferred = (unsigned)hi[4];
+    w.last_longest_cycles = (unsigned long long)(unsigned)hi[5] << 6;
+    w.last_total_cycles = (unsigned long long)(unsigned)hi[6] << 6;
     std::memcpy(&w.last_boxes_thread, hi + 8, 8);
     std::memcpy(&w.last_boxes_warp, hi + 10, 8);
     w.last_candidates = nCand;

@@ -117,19 +117,22 @@ __global__ void __launch_bounds__(256) k_emit(int n, const Box* __restrict__ box
     keys[i] = cell_key(g, c0[0], c0[1], c0[2]);
     vals[i] = i;
 }
-// run heads of the sorted key array go into the open-addressing table (cell key -> first entry)
-__global__ void __launch_bounds__(256) k_build_cell_table(int n, const unsigned long long* __restrict__ keys, unsigned* __restrict__ tab_key, int* __restrict__ tab_start,
+// heads and tails of the runs of the sorted key array go into the open-addressing table (cell key -> [first, last+1))
+__global__ void __launch_bounds__(256) k_build_cell_table(int n, const unsigned long long* __restrict__ keys, unsigned* __restrict__ tab_key, int2* __restrict__ tab_range,
     unsigned mask)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned key = (unsigned)keys[i];
-    if (i > 0 && (unsigned)keys[i - 1] == key) return;
+    const bool head = (i == 0) || (unsigned)keys[i - 1] != key;
+    const bool tail = (i == n - 1) || (unsigned)keys[i + 1] != key;
+    if (!head && !tail) return;
     unsigned h = cell_hash(key) & mask;
     for (;;) {
         const unsigned old = atomicCAS(tab_key + h, 0xffffffffu, key);
         if (old == 0xffffffffu || old == key) {
-            tab_start[h] = i;
+            if (head) tab_range[h].x = i;
+            if (tail) tab_range[h].y = i + 1;
             return;
         }
         h = (h + 1) & mask;
@@ -174,18 +177,6 @@ DEV int codim_v(const SurfArgs& s, int v) { return s.vCoDim ? s.vCoDim[v] : 3; }
 
 // ---- phase 1: broad phase proper.  One WARP per query primitive scans the grid and appends (query, partner) pairs whose boxes are
 // closer than sqrt(dHat).  Only boxes are touched here, so the kernel needs few registers and runs at high occupancy.
-struct PairOut {
-    int2* pairs;
-    unsigned* n;
-    unsigned cap;
-    int* overflow;
-};
-DEV void push_pair(const PairOut& o, int a, int b)
-{
-    const unsigned i = atomicAdd(o.n, 1u);
-    if (i < o.cap) o.pairs[i] = make_int2(a, b);
-    else atomicExch(o.overflow, 1);
-}
 
 __global__ void __launch_bounds__(256) k_pairs_pt(SurfArgs s, const Grid* __restrict__ gp, SortedGrid tg, double dHat, double radius, int first, int last, PairOut out)
 {
@@ -199,8 +190,8 @@ __global__ void __launch_bounds__(256) k_pairs_pt(SurfArgs s, const Grid* __rest
     qb.hi[0] = p.x + radius; qb.hi[1] = p.y + radius; qb.hi[2] = p.z + radius;
     pb.lo[0] = pb.hi[0] = p.x; pb.lo[1] = pb.hi[1] = p.y; pb.lo[2] = pb.hi[2] = p.z;
     const double cull = dHat * (1.0 + 1e-9) + 1e-300;
-    warp_scan_candidates(g, tg, qb, lane, [&](int sfI, const Box& tb) {
-        if (box_gap2(pb, tb) <= cull) push_pair(out, svI, sfI);
+    warp_scan_candidates(g, tg, qb, lane, [&](bool hit, int sfI, const Box& tb) {
+        warp_push_pair(out, hit && box_gap2(pb, tb) <= cull, svI, sfI, lane);
     });
 }
 
@@ -215,8 +206,8 @@ __global__ void __launch_bounds__(256) k_pairs_ee(SurfArgs s, const Grid* __rest
     Box qb = eb;
     for (int k = 0; k < 3; ++k) { qb.lo[k] -= radius; qb.hi[k] += radius; }
     const double cull = dHat * (1.0 + 1e-9) + 1e-300;
-    warp_scan_candidates(g, eg, qb, lane, [&](int eJ, const Box& jb) {
-        if (eJ > eI && box_gap2(eb, jb) <= cull) push_pair(out, eI, eJ);
+    warp_scan_candidates(g, eg, qb, lane, [&](bool hit, int eJ, const Box& jb) {
+        warp_push_pair(out, hit && eJ > eI && box_gap2(eb, jb) <= cull, eI, eJ, lane);
     });
 }
 
@@ -458,7 +449,7 @@ int contact_alloc(ipcgpu_ctx* ctx)
 }
 
 // build one sorted grid over `boxes` (n prims): (keys, vals) sorted by cell, boxes gathered into `sorted_boxes`
-static int build_grid(ipcgpu_ctx* ctx, int n, const Box* boxes, DevBuf<unsigned long long>& keys, DevBuf<int>& vals, Box* sorted_boxes, unsigned* tab_key, int* tab_start)
+static int build_grid(ipcgpu_ctx* ctx, int n, const Box* boxes, DevBuf<unsigned long long>& keys, DevBuf<int>& vals, Box* sorted_boxes, unsigned* tab_key, int2* tab_range)
 {
     ContactWork& w = ctx->cw;
     cudaStream_t st = ctx->stream;
@@ -472,7 +463,7 @@ static int build_grid(ipcgpu_ctx* ctx, int n, const Box* boxes, DevBuf<unsigned 
     }
     k_gather_boxes<<<nblk(n, 256), 256, 0, st>>>(n, boxes, vals.p, sorted_boxes);
     cudaMemsetAsync(tab_key, 0xff, (size_t)(w.tab_mask + 1) * sizeof(unsigned), st);
-    k_build_cell_table<<<nblk(n, 256), 256, 0, st>>>(n, keys.p, tab_key, tab_start, w.tab_mask);
+    k_build_cell_table<<<nblk(n, 256), 256, 0, st>>>(n, keys.p, tab_key, tab_range, w.tab_mask);
     ctx->launches += 4;
     return 0;
 }

@@ -50,7 +50,7 @@ struct ContactWork {
     DevBuf<int2> para_e, cand, tmp2;
     DevBuf<unsigned char> cub_tmp;
     DevBuf<unsigned> ttab_key, etab_key; // cell hash tables of the triangle / edge grids
-    DevBuf<int> ttab_start, etab_start;
+    DevBuf<int2> ttab_start, etab_start; // [first, last+1) entry range per table slot
     unsigned tab_mask = 0;
     DevBuf<int2> bp_pairs; // broad-phase pair lists (PT then EE), bp_cap each
     size_t bp_cap = 0;
@@ -70,7 +70,7 @@ struct CcdWork {
     int ref_count[3] = { 0, 0, 0 };
     bool swept_ready = false;
     unsigned last_survivors = 0;
-    unsigned long long last_deferred = 0;
+    unsigned long long last_deferred = 0, last_longest_cycles = 0, last_total_cycles = 0;
     int last_warnings = 0;
     unsigned long long last_candidates = 0, last_boxes_thread = 0, last_boxes_warp = 0;
 };

@@ -59,6 +59,7 @@ SIGNATURES = {
     "ipcgpu_ccd_full_ti": (C.c_int, [_ctxp, C.c_double, _dp, _dp, _dp, C.POINTER(C.c_uint64)]),
     "ipcgpu_ccd_stats": (C.c_int, [_ctxp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "ipcgpu_ccd_stats_ex": (C.c_int, [_ctxp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "ipcgpu_ccd_stats_timing": (C.c_int, [_ctxp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "ipcgpu_csr_set_zero": (C.c_int, [_ctxp]),
     "ipcgpu_allreduce_grad_hess": (C.c_int, [_ctxp, C.c_int, C.c_int]),
     "ipcgpu_download": (C.c_int, [_ctxp, C.c_int, _dp, C.c_uint64]),
@@ -306,6 +307,11 @@ class Context:
         a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
         self._ck(self.lib.ipcgpu_ccd_stats_ex(self.h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
+
+    def ccd_stats_timing(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        self._ck(self.lib.ipcgpu_ccd_stats_timing(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def profile(self, enable):
         self._ck(self.lib.ipcgpu_profile(self.h, int(enable)))
