@@ -127,30 +127,38 @@ DEV void push_cand(const CandOut& o, int2 c)
 // ---- phase 1: one WARP per query primitive, boxes only: (query, partner) pairs whose swept boxes are within one reference voxel
 __global__ void __launch_bounds__(256) k_ccd_pairs_pt(const Grid* __restrict__ gp, const Box* __restrict__ vboxes, SortedGrid tg, double radius, int first, int last, PairOut out)
 {
-    const int svI = first + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    __shared__ PairStage stage;
+    pair_stage_init(stage);
     const int lane = threadIdx.x & 31;
-    if (svI >= last) return;
     const Grid g = *gp;
-    Box qb = vboxes[svI];
-    for (int k = 0; k < 3; ++k) { qb.lo[k] -= radius; qb.hi[k] += radius; }
-    warp_scan_candidates(g, tg, qb, lane, [&](bool hit, int sfI, const Box&) { warp_push_pair(out, hit, svI, sfI, lane); });
+    const int q0 = first + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kPairQueriesPerWarp;
+    for (int svI = q0; svI < min(q0 + kPairQueriesPerWarp, last); ++svI) {
+        Box qb = vboxes[svI];
+        for (int k = 0; k < 3; ++k) { qb.lo[k] -= radius; qb.hi[k] += radius; }
+        warp_scan_candidates(g, tg, qb, lane, [&](bool hit, int sfI, const Box&) { warp_push_pair(stage, out, hit, svI, sfI, lane); });
+    }
+    pair_stage_flush(stage, out);
 }
 __global__ void __launch_bounds__(256) k_ccd_pairs_ee(const Grid* __restrict__ gp, const Box* __restrict__ eboxes, SortedGrid eg, double radius, int first, int last, PairOut out)
 {
-    const int eI = first + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    __shared__ PairStage stage;
+    pair_stage_init(stage);
     const int lane = threadIdx.x & 31;
-    if (eI >= last) return;
     const Grid g = *gp;
-    const Box eb = eboxes[eI];
-    Box qb = eb;
-    for (int k = 0; k < 3; ++k) { qb.lo[k] -= radius; qb.hi[k] += radius; }
-    warp_scan_candidates(g, eg, qb, lane, [&](bool hit, int eJ, const Box& jb) {
-        // swept-AABB test of queryEdgeForEdgesWithBBoxCheck (SpatialHash.hpp:819-828); the boxes hold {x, x+alpha p}
-        bool sep = !hit || eJ <= eI;
+    const int q0 = first + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kPairQueriesPerWarp;
+    for (int eI = q0; eI < min(q0 + kPairQueriesPerWarp, last); ++eI) {
+        const Box eb = eboxes[eI];
+        Box qb = eb;
+        for (int k = 0; k < 3; ++k) { qb.lo[k] -= radius; qb.hi[k] += radius; }
+        warp_scan_candidates(g, eg, qb, lane, [&](bool hit, int eJ, const Box& jb) {
+            // swept-AABB test of queryEdgeForEdgesWithBBoxCheck (SpatialHash.hpp:819-828); the boxes hold {x, x+alpha p}
+            bool sep = !hit || eJ <= eI;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) sep = sep || (jb.lo[c] - eb.hi[c] > 0.0) || (eb.lo[c] - jb.hi[c] > 0.0);
-        warp_push_pair(out, !sep, eI, eJ, lane);
-    });
+            for (int c = 0; c < 3; ++c) sep = sep || (jb.lo[c] - eb.hi[c] > 0.0) || (eb.lo[c] - jb.hi[c] > 0.0);
+            warp_push_pair(stage, out, !sep, eI, eJ, lane);
+        });
+    }
+    pair_stage_flush(stage, out);
 }
 // ---- phase 2: one THREAD per pair: the reference's voxel-range overlap (its hash query) and the index filters
 __global__ void __launch_bounds__(256) k_ccd_filter_pt(SurfArgs s, const int2* __restrict__ pairs, const unsigned* __restrict__ nPairs, const int* __restrict__ vmin,
@@ -1213,11 +1221,11 @@ int ccd_full(ipcgpu_ctx* ctx, double tol, const double* err_vf, const double* er
     unsigned* nPairs = reinterpret_cast<unsigned*>(cw.counters.p + 8);
     PairOut ppt{ cw.bp_pairs.p, nPairs, (unsigned)cw.bp_cap, w.counters.p + 14 }, pee{ cw.bp_pairs.p + cw.bp_cap, nPairs + 1, (unsigned)cw.bp_cap, w.counters.p + 14 };
     if (v1 > v0 && s.nSF > 0) {
-        k_ccd_pairs_pt<<<nblk((long long)(v1 - v0) * 32, 256), 256, 0, st>>>(cw.grid.p, cw.vbox.p, tg, radius, v0, v1, ppt);
+        k_ccd_pairs_pt<<<nblk(v1 - v0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(cw.grid.p, cw.vbox.p, tg, radius, v0, v1, ppt);
         k_ccd_filter_pt<<<nblk((long long)cw.bp_cap, 256), 256, 0, st>>>(s, ppt.pairs, ppt.n, w.vmin.p, w.vmax.p, out);
     }
     if (e1 > e0 && s.nSE > 1) {
-        k_ccd_pairs_ee<<<nblk((long long)(e1 - e0) * 32, 256), 256, 0, st>>>(cw.grid.p, cw.ebox.p, eg, radius, e0, e1, pee);
+        k_ccd_pairs_ee<<<nblk(e1 - e0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(cw.grid.p, cw.ebox.p, eg, radius, e0, e1, pee);
         k_ccd_filter_ee<<<nblk((long long)cw.bp_cap, 256), 256, 0, st>>>(s, pee.pairs, pee.n, w.vmin.p, w.vmax.p, out);
     }
     ctx->launches += 2;

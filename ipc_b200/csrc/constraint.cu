@@ -180,35 +180,43 @@ DEV int codim_v(const SurfArgs& s, int v) { return s.vCoDim ? s.vCoDim[v] : 3; }
 
 __global__ void __launch_bounds__(256) k_pairs_pt(SurfArgs s, const Grid* __restrict__ gp, SortedGrid tg, double dHat, double radius, int first, int last, PairOut out)
 {
-    const int svI = first + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    __shared__ PairStage stage;
+    pair_stage_init(stage);
     const int lane = threadIdx.x & 31;
-    if (svI >= last) return;
     const Grid g = *gp;
-    const V3 p = load_vertex(s.V, s.nV, s.SVI[svI]);
-    Box qb, pb;
-    qb.lo[0] = p.x - radius; qb.lo[1] = p.y - radius; qb.lo[2] = p.z - radius;
-    qb.hi[0] = p.x + radius; qb.hi[1] = p.y + radius; qb.hi[2] = p.z + radius;
-    pb.lo[0] = pb.hi[0] = p.x; pb.lo[1] = pb.hi[1] = p.y; pb.lo[2] = pb.hi[2] = p.z;
     const double cull = dHat * (1.0 + 1e-9) + 1e-300;
-    warp_scan_candidates(g, tg, qb, lane, [&](bool hit, int sfI, const Box& tb) {
-        warp_push_pair(out, hit && box_gap2(pb, tb) <= cull, svI, sfI, lane);
-    });
+    const int q0 = first + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kPairQueriesPerWarp;
+    for (int svI = q0; svI < min(q0 + kPairQueriesPerWarp, last); ++svI) {
+        const V3 p = load_vertex(s.V, s.nV, s.SVI[svI]);
+        Box qb, pb;
+        qb.lo[0] = p.x - radius; qb.lo[1] = p.y - radius; qb.lo[2] = p.z - radius;
+        qb.hi[0] = p.x + radius; qb.hi[1] = p.y + radius; qb.hi[2] = p.z + radius;
+        pb.lo[0] = pb.hi[0] = p.x; pb.lo[1] = pb.hi[1] = p.y; pb.lo[2] = pb.hi[2] = p.z;
+        warp_scan_candidates(g, tg, qb, lane, [&](bool hit, int sfI, const Box& tb) {
+            warp_push_pair(stage, out, hit && box_gap2(pb, tb) <= cull, svI, sfI, lane);
+        });
+    }
+    pair_stage_flush(stage, out);
 }
 
 __global__ void __launch_bounds__(256) k_pairs_ee(SurfArgs s, const Grid* __restrict__ gp, const Box* __restrict__ edge_boxes, SortedGrid eg, double dHat, double radius, int first,
     int last, PairOut out)
 {
-    const int eI = first + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    __shared__ PairStage stage;
+    pair_stage_init(stage);
     const int lane = threadIdx.x & 31;
-    if (eI >= last) return;
     const Grid g = *gp;
-    const Box eb = edge_boxes[eI];
-    Box qb = eb;
-    for (int k = 0; k < 3; ++k) { qb.lo[k] -= radius; qb.hi[k] += radius; }
     const double cull = dHat * (1.0 + 1e-9) + 1e-300;
-    warp_scan_candidates(g, eg, qb, lane, [&](bool hit, int eJ, const Box& jb) {
-        warp_push_pair(out, hit && eJ > eI && box_gap2(eb, jb) <= cull, eI, eJ, lane);
-    });
+    const int q0 = first + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kPairQueriesPerWarp;
+    for (int eI = q0; eI < min(q0 + kPairQueriesPerWarp, last); ++eI) {
+        const Box eb = edge_boxes[eI];
+        Box qb = eb;
+        for (int k = 0; k < 3; ++k) { qb.lo[k] -= radius; qb.hi[k] += radius; }
+        warp_scan_candidates(g, eg, qb, lane, [&](bool hit, int eJ, const Box& jb) {
+            warp_push_pair(stage, out, hit && eJ > eI && box_gap2(eb, jb) <= cull, eI, eJ, lane);
+        });
+    }
+    pair_stage_flush(stage, out);
 }
 
 // ---- phase 2: exact closest-feature classification, one THREAD per surviving pair (dense, convergent)
@@ -528,11 +536,11 @@ int contact_constraint_set(ipcgpu_ctx* ctx, double dHat, int wantCand, int* nC, 
     unsigned* nPairs = reinterpret_cast<unsigned*>(w.counters.p + 8); // [8] PT pairs, [9] EE pairs
     PairOut ppt{ w.bp_pairs.p, nPairs, (unsigned)w.bp_cap, w.counters.p + 4 }, pee{ w.bp_pairs.p + w.bp_cap, nPairs + 1, (unsigned)w.bp_cap, w.counters.p + 4 };
     if (v1 > v0 && s.nSF > 0) {
-        k_pairs_pt<<<nblk((long long)(v1 - v0) * 32, 256), 256, 0, st>>>(s, w.grid.p, tg, dHat, radius, v0, v1, ppt);
+        k_pairs_pt<<<nblk(v1 - v0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(s, w.grid.p, tg, dHat, radius, v0, v1, ppt);
         k_classify_pt<<<nblk((long long)w.bp_cap, 128), 128, 0, st>>>(s, ppt.pairs, ppt.n, dHat, wantCand, out);
     }
     if (e1 > e0 && s.nSE > 1) {
-        k_pairs_ee<<<nblk((long long)(e1 - e0) * 32, 256), 256, 0, st>>>(s, w.grid.p, w.ebox.p, eg, dHat, radius, e0, e1, pee);
+        k_pairs_ee<<<nblk(e1 - e0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(s, w.grid.p, w.ebox.p, eg, dHat, radius, e0, e1, pee);
         k_classify_ee<<<nblk((long long)w.bp_cap, 128), 128, 0, st>>>(s, pee.pairs, pee.n, dHat, wantCand, out);
     }
     ctx->launches += 2;
