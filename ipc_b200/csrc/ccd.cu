@@ -1022,8 +1022,8 @@ __global__ void __launch_bounds__(128, 3) k_ti_stage2(NarrowArgs a, const unsign
         if (hit && lane == 0) atomicMin(min_ord, dbl_to_ord(toi));
         if (lane == 0) { // diagnostics: the longest pair bounds this pass from below
             const unsigned dt = (unsigned)((clock64() - t0) >> 6);
-            atomicMax(reinterpret_cast<unsigned*>(warn + 2), dt);
-            atomicAdd(reinterpret_cast<unsigned*>(warn + 3), dt);
+            atomicMax(reinterpret_cast<unsigned*>(warn + 3), dt);
+            atomicAdd(reinterpret_cast<unsigned*>(warn + 4), dt);
         }
         __syncwarp();
     }
@@ -1098,11 +1098,10 @@ int ccd_narrow(ipcgpu_ctx* ctx, const int2* cand, unsigned long long nCand, doub
         // the survivor count lives on the device; the thread-level pass is launched over the candidate count (extra threads exit)
         // pass A (thread per pair, 10-box budget): the shallow majority dies here without holding its warp hostage;
         // pass B (warp per pair, corner-parallel box evaluation): the deep searches, compacted.
+        // (a three-tier split -- 3-box, then 12-box thread passes -- was measured slower: the per-pair set-up dominates pass A)
         unsigned* nDefA = reinterpret_cast<unsigned*>(flags + 2);
-        unsigned* nDefB = reinterpret_cast<unsigned*>(flags + 3);
         const int gridA = std::min(nblk((long long)nCand, 128), 148 * 16);
         k_ti_stage15<<<gridA, 128, 0, st>>>(a, w.surv.p, nSurv, w.surv2.p, nDefA, 10, ctx->min_ord.p, flags + 1);
-        (void)nDefB;
         k_ti_stage2<<<kStage2Ctas, 32 * kStage2WarpsPerCta, 0, st>>>(a, w.surv2.p, nDefA, work, reinterpret_cast<DBox*>(w.scratch.p), kLevelCap, ctx->min_ord.p, flags + 1);
     }
     ctx->prof_end(pe);
@@ -1121,8 +1120,8 @@ int ccd_narrow(ipcgpu_ctx* ctx, const int2* cand, unsigned long long nCand, doub
     w.last_survivors = (unsigned)hi[0];
     w.last_warnings = hi[3];
     w.last_deferred = (unsigned)hi[4];
-    w.last_longest_cycles = (unsigned long long)(unsigned)hi[5] << 6;
-    w.last_total_cycles = (unsigned long long)(unsigned)hi[6] << 6;
+    w.last_longest_cycles = (unsigned long long)(unsigned)hi[6] << 6;
+    w.last_total_cycles = (unsigned long long)(unsigned)hi[7] << 6;
     std::memcpy(&w.last_boxes_thread, hi + 8, 8);
     std::memcpy(&w.last_boxes_warp, hi + 10, 8);
     w.last_candidates = nCand;
