@@ -26,6 +26,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ALG_BYTES_PER_TET = 208 + 624 + 96  # read stencil+material, write 78 upper-triangular scalars + 12 gradient scalars
+# dram__bytes_read.sum + dram__bytes_write.sum of k_elastic_grad_hess<NH,g,H> from the `ncu --set full` capture of this same
+# command (profiles/r01b_prof_k_elastic_grad_hess.summary.csv: 117.7 MB + 727.7 MB over 1,002,000 tets)
+NCU_DRAM_BYTES_PER_TET = (117.712128e6 + 727.696128e6) / 1002000
+ALG_BYTES_PER_CCD_CANDIDATE = 200  # k_ti_stage1: 8 B candidate + 4 vertices x (x, p) x 24 B
 DT2 = 0.025 ** 2
 
 
@@ -319,6 +323,16 @@ def main():
         local_tets = m.nT // world
         per_launch_s = tet_ms / max(tet_n, 1) * 1e-3
         achieved = ALG_BYTES_PER_TET * local_tets / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
+        rf_ms, rf_n = prof.get("ccd_root_filter", (0.0, 0))
+        ccd_roof = None
+        if rf_n:
+            # two launches per step (partial + full CCD); bytes = candidates both launches looked at
+            cand_per_step = float(n_cand) / world + float(stats.get("ccd_candidates", 0)) / world
+            ach = ALG_BYTES_PER_CCD_CANDIDATE * cand_per_step / (rf_ms / args.steps * 1e-3) / 1e9
+            ccd_roof = {"bound": "hbm", "kernel": "k_ti_stage1 (root-box inclusion over every CCD candidate)", "achieved": ach, "peak": peak_gbs,
+                        "unit": "GB/s", "frac": ach / peak_gbs, "traffic": None, "algorithmic_bytes_per_candidate": ALG_BYTES_PER_CCD_CANDIDATE,
+                        "kernel_ms_per_step": rf_ms / args.steps,
+                        "note": "vertex data is L2-resident (ncu: 4.6 MB DRAM for 42.8k candidates), so DRAM is not what bounds this kernel"}
         line = {
             "metric": "newton_iteration_ms_assembly_ccd", "value": ms_step, "unit": "ms", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
@@ -331,8 +345,11 @@ def main():
                        "partition": f"tets block-partitioned over {world} rank(s); NCCL sum-allreduce of [gradient, CSR values], min-allreduce of the step"},
             "stage_ms": {k: v[0] / args.steps for k, v in prof.items()},
             "roofline": {"bound": "hbm", "kernel": "k_elastic_grad_hess<NH,g,H>", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                         "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_tet": ALG_BYTES_PER_TET, "kernel_ms": tet_ms / max(tet_n, 1)},
+                         "frac": achieved / peak_gbs, "traffic": NCU_DRAM_BYTES_PER_TET * local_tets, "peak_source": peak_src,
+                         "algorithmic_bytes_per_tet": ALG_BYTES_PER_TET, "algorithmic_bytes_per_launch": ALG_BYTES_PER_TET * local_tets,
+                         "traffic_source": "ncu --set full, profiles/r01b_prof_k_elastic_grad_hess.summary.csv (bytes per tet x tets of this rank)",
+                         "kernel_ms": tet_ms / max(tet_n, 1)},
+            "roofline_ccd": ccd_roof,
             "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(2 * 3 * m.nV * 8), "d2h_bytes_per_step": int((3 * m.nV + nnz) * 8 + 16)},
             "gpu_launches": int(launches), "clocks": clocks,
         }

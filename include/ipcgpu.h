@@ -183,7 +183,8 @@ enum {
     IPCGPU_STAGE_CCD_BROAD = 8,
     IPCGPU_STAGE_CCD_NARROW = 9,
     IPCGPU_STAGE_ALLREDUCE = 10,
-    IPCGPU_STAGE_COUNT = 11
+    IPCGPU_STAGE_CCD_ROOT_FILTER = 11, /* first narrow-phase kernel (root-box inclusion test), nested inside CCD_NARROW */
+    IPCGPU_STAGE_COUNT = 12
 };
 /* enable=1 starts recording an event pair around every stage launch (and clears old records) */
 int ipcgpu_profile(ipcgpu_ctx* ctx, int enable);

@@ -748,7 +748,7 @@ int ipcgpu_barrier_hessian(ipcgpu_ctx* ctx, double dHat, double kappa, int proje
         barrier_hessian(ba, ctx->a.p, ctx->flag.p, ctx->bHraw.p, ctx->brows.p, ctx->stream);
     }
     ctx->prof_end(pe);
-    ctx->launches += 2;
+    ctx->launches += 3;
     CK(cudaGetLastError());
     if (a_inout && ctx->nranks > 1) {
         int rc = ipcgpu_allreduce_grad_hess(ctx, 0, 1);

@@ -1094,7 +1094,9 @@ int ccd_narrow(ipcgpu_ctx* ctx, const int2* cand, unsigned long long nCand, doub
     cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_CCD_NARROW);
     k_ccd_init<<<1, 32, 0, st>>>(ctx->min_ord.p, *alpha_inout, nSurv, work, flags);
     if (nCand > 0) {
+        cudaEvent_t pe1 = ctx->prof_begin(IPCGPU_STAGE_CCD_ROOT_FILTER);
         k_ti_stage1<<<nblk((long long)nCand, 128), 128, 0, st>>>(a, w.surv.p, nSurv, flags);
+        ctx->prof_end(pe1);
         // the survivor count lives on the device; the thread-level pass is launched over the candidate count (extra threads exit)
         // pass A (thread per pair, 10-box budget): the shallow majority dies here without holding its warp hostage;
         // pass B (warp per pair, corner-parallel box evaluation): the deep searches, compacted.

@@ -71,7 +71,7 @@ SIGNATURES = {
 }
 
 STAGES = ["elastic_energy", "elastic_tet", "gather_gradient", "assemble_csr", "inversion", "hash", "constraint_set", "barrier",
-          "ccd_broad", "ccd_narrow", "allreduce"]
+          "ccd_broad", "ccd_narrow", "allreduce", "ccd_root_filter"]
 
 _lib = None
 
