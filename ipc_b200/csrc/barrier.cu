@@ -202,7 +202,10 @@ __global__ void __launch_bounds__(64) k_barrier_hessian_build(BarrierArgs p, dou
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= p.nC + p.nP) return;
-    double* H = Hraw + (size_t)c * 144;
+    // the matrix is assembled in thread-local memory (interleaved across the warp by the hardware: every access is one coalesced
+    // transaction) and shipped to its pair-major slot once at the end; read-modify-write straight on the 1152-byte-strided slots
+    // cost 32 sectors per warp access
+    double H[144];
 #define HE(i, j) H[(i) * 12 + (j)]
     for (int i = 0; i < 144; ++i) H[i] = 0.0;
     const bool is_para = c >= p.nC;
@@ -258,65 +261,123 @@ __global__ void __launch_bounds__(64) k_barrier_hessian_build(BarrierArgs p, dou
         for (int q = 0; q < 4; ++q) rows[q] = ev[q];
     }
     for (int q = 0; q < 4; ++q) rows_out[4 * (size_t)c + q] = rows[q];
+    double2* out = reinterpret_cast<double2*>(Hraw + (size_t)c * 144);
+    for (int i = 0; i < 72; ++i) out[i] = make_double2(H[2 * i], H[2 * i + 1]);
 #undef HE
 }
 
 // -----------------------------------------------------------------------------------------------------------
-// PSD projection of the 12x12 pair Hessians (IglUtils::makePD, IglUtils.hpp:112-133), parallel-order cyclic Jacobi held
-// entirely in registers.  Six lanes share one matrix: lane k owns the columns sitting at positions 2k ("top") and 2k+1
-// ("bottom") of A and of the accumulated eigenvector matrix V, so the column half of a rotation is lane-local and the row half
-// only needs the six (c, s) pairs of the round.  Between rounds the columns travel round a Brent-Luk ring (position 0 fixed,
-// tops move one lane up, bottoms one lane down) and the rows of A follow the same permutation, which costs nothing because
-// every moved value passes through a shuffle whose destination register is chosen at compile time.  After 11 rounds (one sweep)
-// the ring is back where it started.  Five matrices per warp (30 lanes).
-constexpr int kProjWarps = 4;      // warps per CTA
-constexpr int kProjPerWarp = 5;    // matrices per warp
+// PSD projection of the 12x12 pair Hessians (IglUtils::makePD, IglUtils.hpp:112-133).
+//
+// (1) Reduction 12 -> 9.  Every pair energy depends on vertex differences only, so H (1,1,1,1)^T (x) e_k = 0 for k = 1..3 (unused
+// vertex blocks are zero, which keeps this true for the 2- and 3-vertex stencils).  With Q = Q4 (x) I3, Q4 the 3x4 Helmert matrix
+// (orthonormal rows orthogonal to (1,1,1,1)), range(H) lies in range(Q^T), hence H = Q^T M Q with M = Q H Q^T (9x9) and, Q^T having
+// orthonormal columns, makePD(H) = Q^T makePD(M) Q exactly.  A 9x9 (padded to 10x10) eigenproblem costs half a 12x12 one.
+//
+// (2) Parallel-order cyclic Jacobi held entirely in registers.  Five lanes share one matrix: lane k owns the columns sitting at
+// ring positions 2k ("top") and 2k+1 ("bottom") of A and of the eigenvector accumulator V, so the column half of a rotation is
+// lane-local and the row half only needs the five (c, s) pairs of the round.  Between rounds the columns travel round a Brent-Luk
+// tournament ring (position 0 fixed, tops move one lane up, bottoms one lane down) and the rows of A follow the same permutation,
+// which costs nothing because every moved value passes through a shuffle whose destination register is chosen at compile time.
+// After 9 rounds (one sweep) the ring is back where it started.  Six matrices per warp (30 lanes).  A matrix that has converged
+// freezes (c = 1, s = 0), so its result does not depend on its neighbours in the warp.
+//
+// Output: makePD(M) (81 doubles, row-major 9x9) over the first 81 entries of the pair's 144-double slot; the scatter kernel applies
+// Q^T . Q on the fly.
+constexpr int kProjWarps = 4;   // warps per CTA
+constexpr int kProjN = 10;      // padded matrix order
+constexpr int kProjG = 5;       // lanes per matrix
+constexpr int kProjPerWarp = 6; // matrices per warp
 __host__ __device__ constexpr int ring_next(int i) // where the row/column at position i sits after one round
 {
-    return i == 0 ? 0 : i == 1 ? 2 : i == 10 ? 11 : (i % 2 == 0) ? i + 2 : i - 2;
+    return i == 0 ? 0 : i == 1 ? 2 : i == kProjN - 2 ? kProjN - 1 : (i % 2 == 0) ? i + 2 : i - 2;
+}
+// Helmert rows: q0 = (1,-1,0,0)/sqrt2, q1 = (1,1,-2,0)/sqrt6, q2 = (1,1,1,-3)/sqrt12
+DEV double helmert(int a, int c)
+{
+    const double r2 = 0.70710678118654752440, r6 = 0.40824829046386301637, r12 = 0.28867513459481288225;
+    if (a == 0) return c == 0 ? r2 : (c == 1 ? -r2 : 0.0);
+    if (a == 1) return c <= 1 ? r6 : (c == 2 ? -2.0 * r6 : 0.0);
+    return c <= 2 ? r12 : -3.0 * r12;
+}
+// column j (< 9) of M = Q H Q^T, rows 0..8 (row 9 of the padded matrix is zero)
+DEV void reduced_column(const double* __restrict__ H0, int j, double* col /* 10 */)
+{
+    const int b = j / 3, s = j - 3 * b;
+    double w[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) w[i] = 0.0;
+#pragma unroll
+    for (int dd = 0; dd < 4; ++dd) {
+        const double q = helmert(b, dd);
+        const double* row = H0 + (3 * dd + s) * 12; // H is symmetric: row 3d+s stands for column 3d+s
+#pragma unroll
+        for (int i = 0; i < 12; ++i) w[i] += q * row[i];
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            double v = 0.0;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) v += helmert(a, cc) * w[3 * cc + r];
+            col[3 * a + r] = v;
+        }
+    col[9] = 0.0;
 }
 
 __global__ void __launch_bounds__(32 * kProjWarps) k_barrier_hessian_project(int n, double* __restrict__ H)
 {
+    constexpr int N = kProjN, G = kProjG;
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const int grp = lane / 6, k = lane - 6 * grp, base = 6 * grp;
+    const int grp = lane / G, k = lane - G * grp, base = G * grp;
     const int warp = blockIdx.x * kProjWarps + (threadIdx.x >> 5);
     const int c = warp * kProjPerWarp + grp;
     const bool live = grp < kProjPerWarp && c < n;
-    double AT[12], AB[12], VT[12], VB[12];
+    double AT[N], AB[N], VT[N], VB[N];
     double* H0 = H + (size_t)(live ? c : 0) * 144;
 #pragma unroll
-    for (int i = 0; i < 12; ++i) {
-        AT[i] = live ? H0[(2 * k) * 12 + i] : ((i == 2 * k) ? 1.0 : 0.0);
-        AB[i] = live ? H0[(2 * k + 1) * 12 + i] : ((i == 2 * k + 1) ? 1.0 : 0.0);
+    for (int i = 0; i < N; ++i) {
+        AT[i] = (i == 2 * k) ? 1.0 : 0.0;
+        AB[i] = (i == 2 * k + 1) ? 1.0 : 0.0;
         VT[i] = (i == 2 * k) ? 1.0 : 0.0;
         VB[i] = (i == 2 * k + 1) ? 1.0 : 0.0;
     }
+    if (live) {
+        reduced_column(H0, 2 * k, AT);
+        if (2 * k + 1 < 9) reduced_column(H0, 2 * k + 1, AB);
+        else {
+#pragma unroll
+            for (int i = 0; i < N; ++i) AB[i] = 0.0; // the padding column
+        }
+    }
+    __syncwarp(); // every lane has read H before anything is written back
+    auto group_sum = [&](double v) {
+        double t = 0.0;
+#pragma unroll
+        for (int m = 0; m < G; ++m) t += __shfl_sync(full, v, base + m);
+        return t; // same order on every lane of the group
+    };
     bool done = !live;
     for (int sweep = 0; sweep < 30; ++sweep) {
         // convergence of each matrix: off-diagonal mass against diagonal mass
         {
             double off = 0.0, dg = 0.0;
 #pragma unroll
-            for (int i = 0; i < 12; ++i) {
+            for (int i = 0; i < N; ++i) {
                 const double t2 = AT[i] * AT[i], b2 = AB[i] * AB[i];
                 off += ((i == 2 * k) ? 0.0 : t2) + ((i == 2 * k + 1) ? 0.0 : b2);
                 dg += ((i == 2 * k) ? t2 : 0.0) + ((i == 2 * k + 1) ? b2 : 0.0);
             }
-            const double o2 = off + __shfl_sync(full, off, base + (k + 3) % 6);
-            const double d2 = dg + __shfl_sync(full, dg, base + (k + 3) % 6);
-            const double o3 = o2 + __shfl_sync(full, o2, base + (k + 1) % 6) + __shfl_sync(full, o2, base + (k + 2) % 6);
-            const double d3 = d2 + __shfl_sync(full, d2, base + (k + 1) % 6) + __shfl_sync(full, d2, base + (k + 2) % 6);
-            // the sums are evaluated in a different order on each lane; take lane 0's so the whole group agrees
-            const double offg = __shfl_sync(full, o3, base), dgg = __shfl_sync(full, d3, base);
+            const double offg = group_sum(off), dgg = group_sum(dg);
             if (offg <= 2e-26 * dgg || offg <= 1e-300) done = true;
         }
         if (__all_sync(full, done)) break;
-        for (int r = 0; r < 11; ++r) {
+        for (int r = 0; r < N - 1; ++r) {
             double app = 0.0, aqq = 0.0, apq = 0.0;
 #pragma unroll
-            for (int m = 0; m < 6; ++m)
+            for (int m = 0; m < G; ++m)
                 if (k == m) {
                     app = AT[2 * m];
                     aqq = AB[2 * m + 1];
@@ -331,16 +392,16 @@ __global__ void __launch_bounds__(32 * kProjWarps) k_barrier_hessian_project(int
             }
             // columns (own pair): col_p' = c col_p - s col_q, col_q' = s col_p + c col_q, for A and V
 #pragma unroll
-            for (int i = 0; i < 12; ++i) {
+            for (int i = 0; i < N; ++i) {
                 const double a0 = AT[i], a1 = AB[i], v0 = VT[i], v1 = VB[i];
                 AT[i] = cc * a0 - ss * a1;
                 AB[i] = ss * a0 + cc * a1;
                 VT[i] = cc * v0 - ss * v1;
                 VB[i] = ss * v0 + cc * v1;
             }
-            // rows (all six pairs of the round)
+            // rows (all pairs of the round)
 #pragma unroll
-            for (int m = 0; m < 6; ++m) {
+            for (int m = 0; m < G; ++m) {
                 const double cm = __shfl_sync(full, cc, base + m), sm = __shfl_sync(full, ss, base + m);
                 const double t0 = AT[2 * m], t1 = AT[2 * m + 1], b0 = AB[2 * m], b1 = AB[2 * m + 1];
                 AT[2 * m] = cm * t0 - sm * t1;
@@ -349,52 +410,45 @@ __global__ void __launch_bounds__(32 * kProjWarps) k_barrier_hessian_project(int
                 AB[2 * m + 1] = sm * b0 + cm * b1;
             }
             // ring move
-            double nAT[12], nAB[12];
+            double nAT[N], nAB[N];
 #pragma unroll
-            for (int i = 0; i < 12; ++i) {
+            for (int i = 0; i < N; ++i) {
                 const double upA = __shfl_up_sync(full, (k == 0) ? AB[i] : AT[i], 1);
                 const double dnA = __shfl_down_sync(full, AB[i], 1);
                 nAT[ring_next(i)] = (k == 0) ? AT[i] : upA;
-                nAB[ring_next(i)] = (k == 5) ? AT[i] : dnA;
+                nAB[ring_next(i)] = (k == G - 1) ? AT[i] : dnA;
                 const double upV = __shfl_up_sync(full, (k == 0) ? VB[i] : VT[i], 1);
                 const double dnV = __shfl_down_sync(full, VB[i], 1);
                 const double vt = VT[i];
                 VT[i] = (k == 0) ? vt : upV;
-                VB[i] = (k == 5) ? vt : dnV;
+                VB[i] = (k == G - 1) ? vt : dnV;
             }
 #pragma unroll
-            for (int i = 0; i < 12; ++i) {
+            for (int i = 0; i < N; ++i) {
                 AT[i] = nAT[i];
                 AB[i] = nAB[i];
             }
         }
     }
-    // clamp: lambda_min >= 0 -> unchanged (IglUtils.hpp:123-125)
+    // clamp the negative eigenvalues and rebuild: makePD(M) = sum_{lambda > 0} lambda v v^T  (IglUtils.hpp:123-131)
     double lt = 0.0, lb = 0.0;
 #pragma unroll
-    for (int m = 0; m < 6; ++m)
+    for (int m = 0; m < G; ++m)
         if (k == m) {
             lt = AT[2 * m];
             lb = AB[2 * m + 1];
         }
-    const bool neg_lane = live && (lt < 0.0 || lb < 0.0);
-    const unsigned negmask = __ballot_sync(full, neg_lane);
-    const bool neg = (negmask >> base) & 0x3fu;
-    if (!__any_sync(full, neg)) return;
     lt = fmax(lt, 0.0);
     lb = fmax(lb, 0.0);
 #pragma unroll
-    for (int i = 0; i < 12; ++i) {
+    for (int i = 0; i < 9; ++i) {
         const double wt = lt * VT[i], wb = lb * VB[i];
 #pragma unroll
-        for (int j = i; j < 12; ++j) {
-            const double part = wt * VT[j] + wb * VB[j];
-            const double x2 = part + __shfl_sync(full, part, base + (k + 3) % 6);
-            const double x3 = x2 + __shfl_sync(full, x2, base + (k + 1) % 6) + __shfl_sync(full, x2, base + (k + 2) % 6);
-            const double tot = __shfl_sync(full, x3, base); // one summation order for both triangles
-            if (neg && live && k == ((i * 12 + j) % 6)) {
-                H0[i * 12 + j] = tot;
-                H0[j * 12 + i] = tot;
+        for (int j = i; j < 9; ++j) {
+            const double tot = group_sum(wt * VT[j] + wb * VB[j]);
+            if (live && k == ((i * 9 + j) % G)) {
+                H0[i * 9 + j] = tot;
+                H0[j * 9 + i] = tot;
             }
         }
     }
@@ -437,7 +491,15 @@ __global__ void __launch_bounds__(32 * kScatWarps) k_barrier_hessian_scatter(Bar
             if (o == -2) atomicExch(err, 1);
             else if (o != -1) {
                 if (rows[bi] == rows[bj] && q < r) continue; // strictly lower part of a diagonal block
-                atomicAdd(a + o + q, H0[e]);
+                // (Q^T M Q)[i][j] = sum_{a,b} Q4[a][bi] Q4[b][bj] M[3a+r][3b+q]
+                double v = 0.0;
+#pragma unroll
+                for (int ka = 0; ka < 3; ++ka) {
+                    const double qa = helmert(ka, bi);
+#pragma unroll
+                    for (int kb = 0; kb < 3; ++kb) v += (qa * helmert(kb, bj)) * H0[(3 * ka + r) * 9 + 3 * kb + q];
+                }
+                atomicAdd(a + o + q, v);
             }
         }
     }
