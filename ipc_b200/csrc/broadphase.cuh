@@ -101,8 +101,10 @@ DEV bool boxes_overlap(const Box& a, const Box& b)
 // that have nothing), so that f can aggregate its output over the warp.
 // The <= 27 cells are looked up by 27 lanes at once; the <= 9 rows (runs of consecutive entries) are then walked as ONE flattened
 // index range, so that a query costs ceil(total/32) independent, coalesced loads instead of a dependent chain per row.
+// `after` >= 0 restricts the walk to entries at sorted positions > after: a query that is itself entry `after` of the same grid
+// then sees each of its partners from exactly one side (half the work of testing every pair twice and dropping one).
 template <typename F>
-DEV void warp_scan_candidates(const Grid& g, const SortedGrid& sg, const Box& qb, int lane, F f)
+DEV void warp_scan_candidates(const Grid& g, const SortedGrid& sg, const Box& qb, int lane, F f, int after = -1)
 {
     const unsigned full = 0xffffffffu;
     int c0[3], c1[3];
@@ -122,7 +124,7 @@ DEV void warp_scan_candidates(const Grid& g, const SortedGrid& sg, const Box& qb
     const int s0 = __shfl_sync(full, mine.x, 3 * rr), s1 = __shfl_sync(full, mine.x, 3 * rr + 1), s2 = __shfl_sync(full, mine.x, 3 * rr + 2);
     const int e0 = __shfl_sync(full, mine.y, 3 * rr), e1 = __shfl_sync(full, mine.y, 3 * rr + 1), e2 = __shfl_sync(full, mine.y, 3 * rr + 2);
     const int rend = max(e0, max(e1, e2));
-    const int rstart = (rend > 0) ? min(s0, min(s1, s2)) : 0; // empty row: harmless start
+    const int rstart = (rend > 0) ? max(min(s0, min(s1, s2)), after + 1) : 0; // empty row: harmless start
     const int rlen = (lane < 9 && rend > rstart) ? rend - rstart : 0;
     int incl = rlen; // inclusive prefix over lanes 0..8
 #pragma unroll

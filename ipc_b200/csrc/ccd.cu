@@ -139,24 +139,26 @@ __global__ void __launch_bounds__(256) k_ccd_pairs_pt(const Grid* __restrict__ g
     }
     pair_stage_flush(stage, out);
 }
-__global__ void __launch_bounds__(256) k_ccd_pairs_ee(const Grid* __restrict__ gp, const Box* __restrict__ eboxes, SortedGrid eg, double radius, int first, int last, PairOut out)
+// queries are the entries of the sorted swept-edge grid itself ([first, last) = sorted positions); each walks only the entries behind it
+__global__ void __launch_bounds__(256) k_ccd_pairs_ee(const Grid* __restrict__ gp, SortedGrid eg, double radius, int first, int last, PairOut out)
 {
     __shared__ PairStage stage;
     pair_stage_init(stage);
     const int lane = threadIdx.x & 31;
     const Grid g = *gp;
     const int q0 = first + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kPairQueriesPerWarp;
-    for (int eI = q0; eI < min(q0 + kPairQueriesPerWarp, last); ++eI) {
-        const Box eb = eboxes[eI];
+    for (int i = q0; i < min(q0 + kPairQueriesPerWarp, last); ++i) {
+        const int eI = eg.ids[i];
+        const Box eb = eg.boxes[i];
         Box qb = eb;
         for (int k = 0; k < 3; ++k) { qb.lo[k] -= radius; qb.hi[k] += radius; }
         warp_scan_candidates(g, eg, qb, lane, [&](bool hit, int eJ, const Box& jb) {
             // swept-AABB test of queryEdgeForEdgesWithBBoxCheck (SpatialHash.hpp:819-828); the boxes hold {x, x+alpha p}
-            bool sep = !hit || eJ <= eI;
+            bool sep = !hit;
 #pragma unroll
             for (int c = 0; c < 3; ++c) sep = sep || (jb.lo[c] - eb.hi[c] > 0.0) || (eb.lo[c] - jb.hi[c] > 0.0);
-            warp_push_pair(stage, out, !sep, eI, eJ, lane);
-        });
+            warp_push_pair(stage, out, !sep, min(eI, eJ), max(eI, eJ), lane);
+        }, i);
     }
     pair_stage_flush(stage, out);
 }
@@ -400,7 +402,8 @@ constexpr unsigned F_ZERO = 1u << 24; // zero_in flag stored in DBox::kk
 
 constexpr int kStage2WarpsPerCtaDev = 4;
 constexpr int kSmemLevel = 184;
-constexpr int kWideLevel = 10; // levels with at least this many boxes are evaluated box-parallel, narrower ones corner-parallel    // boxes per level buffer kept in shared memory by the warp-level pass
+constexpr int kWideLevel = 10; // levels with at least this many boxes are evaluated box-parallel, narrower ones corner-parallel
+__constant__ int c_wide_level = kWideLevel; // (IPCGPU_TI_WIDE_LEVEL overrides it for tuning runs)    // boxes per level buffer kept in shared memory by the warp-level pass
 
 // group helpers: W = 32 (one warp per pair) or W = 1 (one thread per pair, no cross-lane traffic)
 template <int W> DEV void group_min_key(Key3& k, unsigned& pay, double& aux) { if (W == 32) warp_min_key(k, pay, aux); }
@@ -445,15 +448,15 @@ __device__ int ti_root_finder(const TiPair& P, const double* tol, double co_tol,
     DBox* gB = bufB;
     out_tol = co_tol;
     toi = INF;
+    unsigned long long bo_cur = best ? *reinterpret_cast<const volatile unsigned long long*>(best) : 0ull;
     while (n > 0) {
         // exact pruning against the running device-wide minimum: a box that starts at t_lo >= max(best, 1e-6) can only yield a time of
         // impact >= best (and no 0.8-rescaled retry, which needs toi < 1e-6), so dropping it cannot change the final min over pairs
+        // The bound used here was requested one level ago (stale = prunes less, never wrong): its L2 round trip overlaps the level.
         double t_prune = INF;
         if (best) {
-            unsigned long long bo = 0;
-            if (W == 1 || lane == 0) bo = *reinterpret_cast<const volatile unsigned long long*>(best);
-            if (W == 32) bo = __shfl_sync(0xffffffffu, bo, 0);
-            t_prune = fmax(ord_to_dbl(bo), 1e-6);
+            t_prune = fmax(ord_to_dbl(bo_cur), 1e-6);
+            bo_cur = *reinterpret_cast<const volatile unsigned long long*>(best); // W == 32: same address on all lanes, one value
         }
         // ---- pass 1: evaluate, find K1 (first box containing the origin) and K2 (first terminal box) ----------
         Key3 k1 = { INF, INF, INF }, k2 = { INF, INF, INF };
@@ -655,19 +658,20 @@ __device__ int ti_root_finder_cp(const TiPair& P, const double* tol, double co_t
     double temp_toi = INF, temp_out_tol = co_tol;
     out_tol = co_tol;
     toi = INF;
+    unsigned long long bo_cur = best ? *reinterpret_cast<const volatile unsigned long long*>(best) : 0ull;
     while (n > 0) {
         Key3 k1 = { INF, INF, INF }, k2 = { INF, INF, INF };
         unsigned p1 = 0, p2 = 0;
         double a1max = 0.0;
         int visited = 0;
-        double t_prune = INF; // exact pruning against the running device-wide minimum (see ti_root_finder)
+        // exact pruning against the running device-wide minimum (see ti_root_finder).  The value used at this level was requested
+        // one level ago (a stale bound only prunes less), so its L2 round trip is off the per-level critical path.
+        double t_prune = INF;
         if (best) {
-            unsigned long long bo = 0;
-            if (lane == 0) bo = *reinterpret_cast<const volatile unsigned long long*>(best);
-            bo = __shfl_sync(0xffffffffu, bo, 0);
-            t_prune = fmax(ord_to_dbl(bo), 1e-6);
+            t_prune = fmax(ord_to_dbl(bo_cur), 1e-6);
+            bo_cur = *reinterpret_cast<const volatile unsigned long long*>(best); // same address on all lanes: one broadcast request
         }
-        if (n >= kWideLevel) {
+        if (n >= c_wide_level) {
             // wide level: one box per lane (box-parallel), K1/K2 by warp min-reduction over the keys
             for (int base = 0; base < n; base += 32) {
                 const int i = base + lane;
@@ -772,7 +776,7 @@ __device__ int ti_root_finder_cp(const TiPair& P, const double* tol, double co_t
             use_skip = true;
         }
         int nn = 0;
-        if (n >= kWideLevel) {
+        if (n >= c_wide_level) {
             bool over = false, deep = false;
             for (int base = 0; base < n; base += 32) {
                 const int i = base + lane;
@@ -1091,6 +1095,11 @@ int ccd_narrow(ipcgpu_ctx* ctx, const int2* cand, unsigned long long nCand, doub
     unsigned* nSurv = reinterpret_cast<unsigned*>(w.counters.p);
     unsigned* work = nSurv + 1;
     int* flags = w.counters.p + 2; // [0] zero distance, [1] warnings, [2] spare
+    static const int wide_env = [] { const char* e = std::getenv("IPCGPU_TI_WIDE_LEVEL"); return e ? std::atoi(e) : 0; }();
+    if (wide_env > 0 && !w.wide_level_set) {
+        CKD(cudaMemcpyToSymbolAsync(c_wide_level, &wide_env, sizeof(int), 0, cudaMemcpyHostToDevice, st));
+        w.wide_level_set = true;
+    }
     cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_CCD_NARROW);
     k_ccd_init<<<1, 32, 0, st>>>(ctx->min_ord.p, *alpha_inout, nSurv, work, flags);
     if (nCand > 0) {
@@ -1226,7 +1235,7 @@ int ccd_full(ipcgpu_ctx* ctx, double tol, const double* err_vf, const double* er
         k_ccd_filter_pt<<<nblk((long long)cw.bp_cap, 256), 256, 0, st>>>(s, ppt.pairs, ppt.n, w.vmin.p, w.vmax.p, out);
     }
     if (e1 > e0 && s.nSE > 1) {
-        k_ccd_pairs_ee<<<nblk(e1 - e0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(cw.grid.p, cw.ebox.p, eg, radius, e0, e1, pee);
+        k_ccd_pairs_ee<<<nblk(e1 - e0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(cw.grid.p, eg, radius, e0, e1, pee);
         k_ccd_filter_ee<<<nblk((long long)cw.bp_cap, 256), 256, 0, st>>>(s, pee.pairs, pee.n, w.vmin.p, w.vmax.p, out);
     }
     ctx->launches += 2;

@@ -199,8 +199,8 @@ __global__ void __launch_bounds__(256) k_pairs_pt(SurfArgs s, const Grid* __rest
     pair_stage_flush(stage, out);
 }
 
-__global__ void __launch_bounds__(256) k_pairs_ee(SurfArgs s, const Grid* __restrict__ gp, const Box* __restrict__ edge_boxes, SortedGrid eg, double dHat, double radius, int first,
-    int last, PairOut out)
+// queries are the entries of the sorted edge grid itself ([first, last) = sorted positions); each walks only the entries behind it
+__global__ void __launch_bounds__(256) k_pairs_ee(const Grid* __restrict__ gp, SortedGrid eg, double dHat, double radius, int first, int last, PairOut out)
 {
     __shared__ PairStage stage;
     pair_stage_init(stage);
@@ -208,13 +208,14 @@ __global__ void __launch_bounds__(256) k_pairs_ee(SurfArgs s, const Grid* __rest
     const Grid g = *gp;
     const double cull = dHat * (1.0 + 1e-9) + 1e-300;
     const int q0 = first + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kPairQueriesPerWarp;
-    for (int eI = q0; eI < min(q0 + kPairQueriesPerWarp, last); ++eI) {
-        const Box eb = edge_boxes[eI];
+    for (int i = q0; i < min(q0 + kPairQueriesPerWarp, last); ++i) {
+        const int eI = eg.ids[i];
+        const Box eb = eg.boxes[i];
         Box qb = eb;
         for (int k = 0; k < 3; ++k) { qb.lo[k] -= radius; qb.hi[k] += radius; }
         warp_scan_candidates(g, eg, qb, lane, [&](bool hit, int eJ, const Box& jb) {
-            warp_push_pair(stage, out, hit && eJ > eI && box_gap2(eb, jb) <= cull, eI, eJ, lane);
-        });
+            warp_push_pair(stage, out, hit && box_gap2(eb, jb) <= cull, min(eI, eJ), max(eI, eJ), lane);
+        }, i);
     }
     pair_stage_flush(stage, out);
 }
@@ -540,7 +541,7 @@ int contact_constraint_set(ipcgpu_ctx* ctx, double dHat, int wantCand, int* nC, 
         k_classify_pt<<<nblk((long long)w.bp_cap, 128), 128, 0, st>>>(s, ppt.pairs, ppt.n, dHat, wantCand, out);
     }
     if (e1 > e0 && s.nSE > 1) {
-        k_pairs_ee<<<nblk(e1 - e0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(s, w.grid.p, w.ebox.p, eg, dHat, radius, e0, e1, pee);
+        k_pairs_ee<<<nblk(e1 - e0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(w.grid.p, eg, dHat, radius, e0, e1, pee);
         k_classify_ee<<<nblk((long long)w.bp_cap, 128), 128, 0, st>>>(s, pee.pairs, pee.n, dHat, wantCand, out);
     }
     ctx->launches += 2;

@@ -63,6 +63,7 @@ struct CcdWork {
     DevBuf<int> vmin, vmax, counters;
     DevBuf<int2> cand;
     DevBuf<unsigned> surv, surv2;
+    bool wide_level_set = false;
     DevBuf<unsigned char> scratch;
     DevBuf<unsigned long long> ncand, bounds;
     // reference swept-grid geometry (SpatialHash.hpp:589-640) of the last ipcgpu_hash_build_swept

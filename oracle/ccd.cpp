@@ -25,6 +25,7 @@
 #include <cstdint>
 #include <cstring>
 #include <limits>
+#include <atomic>
 #include <vector>
 
 namespace {
@@ -123,6 +124,28 @@ void width_tolerances(bool vf, const double* x0, const double* x1, double tolera
     tol[2] = tolerance / (3.0 * e1);
 }
 
+/* diagnostics for sizing the GPU passes (not part of the algorithm): histograms over root-finder calls of the boxes evaluated,
+ * the widest level and the number of levels, in powers of two */
+static std::atomic<long long> g_ti_hist[3][24];
+struct TiStat {
+    long long boxes = 0, width = 0, levels = 0;
+    static int bin(long long v) { int b = 0; while (v > 1 && b < 23) { v >>= 1; ++b; } return b; }
+    ~TiStat()
+    {
+        g_ti_hist[0][bin(boxes)].fetch_add(1, std::memory_order_relaxed);
+        g_ti_hist[1][bin(width)].fetch_add(1, std::memory_order_relaxed);
+        g_ti_hist[2][bin(levels)].fetch_add(1, std::memory_order_relaxed);
+    }
+};
+extern "C" void orc_ti_stats(long long* out72, int reset)
+{
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 24; ++b) {
+            out72[a * 24 + b] = g_ti_hist[a][b].load();
+            if (reset) g_ti_hist[a][b].store(0);
+        }
+}
+
 /* interval_root_finder_double_horizontal_tree with the canonical in-level order */
 bool root_finder(bool vf, const double* x0, const double* x1, const double tol[3], double co_tol, double max_t, const double err[3], double ms,
     int max_itr, double& toi, double& out_tol)
@@ -137,7 +160,10 @@ bool root_finder(bool vf, const double* x0, const double* x1, const double tol[3
     out_tol = co_tol;
     toi = std::numeric_limits<double>::infinity();
     bool overflow = false;
+    TiStat stat;
     while (!level.empty() && !overflow) {
+        ++stat.levels;
+        stat.width = std::max<long long>(stat.width, (long long)level.size());
         std::sort(level.begin(), level.end(), [](const Box3& a, const Box3& b) {
             double ta = lo_of(a.t), tb = lo_of(b.t);
             if (ta != tb) return ta < tb;
@@ -151,6 +177,7 @@ bool root_finder(bool vf, const double* x0, const double* x1, const double tol[3
             const double t_lo = lo_of(cur.t);
             if (!(t_lo < toi_skip)) continue;
             ++refine;
+            ++stat.boxes;
             bool box_in;
             double true_tol[3];
             if (!origin_in_box(vf, x0, x1, cur, err, ms, box_in, true_tol)) continue;
