@@ -354,6 +354,35 @@ __global__ void k_merge_dups(int n, const int4* __restrict__ sorted, int4* __res
     push4(act, nAct, cap, overflow, make_int4(v.x, v.y, v.z, -cnt));
 }
 
+// sort-free variant of the same merge for meshes below 2^21 vertices: (x,y,z) packs into one 64-bit key, an open-addressing table
+// counts the multiplicities (2 short kernels instead of 16 radix passes over a list of a few thousand entries)
+DEV unsigned long long dup_key(int4 v) { return ((unsigned long long)(unsigned)(-v.x - 1) << 42) | ((unsigned long long)(unsigned)v.y << 21) | (unsigned long long)(unsigned)(v.z + 1); }
+__global__ void k_dup_insert(int n, const int4* __restrict__ dup, unsigned long long* __restrict__ tab_key, int* __restrict__ tab_cnt, unsigned mask)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long key = dup_key(dup[i]);
+    unsigned h = (unsigned)((key * 0x9E3779B97F4A7C15ull) >> 40) & mask;
+    for (;;) {
+        const unsigned long long old = atomicCAS(tab_key + h, ~0ull, key);
+        if (old == ~0ull || old == key) {
+            atomicAdd(tab_cnt + h, 1);
+            return;
+        }
+        h = (h + 1) & mask;
+    }
+}
+__global__ void k_dup_emit(unsigned size, const unsigned long long* __restrict__ tab_key, const int* __restrict__ tab_cnt, int4* __restrict__ act, int* __restrict__ nAct, int cap,
+    int* __restrict__ overflow)
+{
+    const unsigned h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= size) return;
+    const unsigned long long key = tab_key[h];
+    if (key == ~0ull) return;
+    const int x = -(int)(key >> 42) - 1, y = (int)((key >> 21) & 0x1fffffu), z = (int)(key & 0x1fffffu) - 1;
+    push4(act, nAct, cap, overflow, make_int4(x, y, z, -tab_cnt[h]));
+}
+
 } // namespace ipcgpu
 
 using namespace ipcgpu;
@@ -556,9 +585,20 @@ int contact_constraint_set(ipcgpu_ctx* ctx, double dHat, int wantCand, int* nC, 
     const int nAct = h[0], nDup = h[1], nP = h[2], nK = h[3];
     // merge PP/PE duplicates into the active list with negative multiplicities
     if (nDup > 0) {
-        if ((rc = sort_lex(ctx, w.dup.p, nullptr, nDup, w.tmp4.p, nullptr))) return rc;
-        k_merge_dups<<<nblk(nDup, 256), 256, 0, st>>>(nDup, w.dup.p, w.act.p, w.counters.p + 0, w.cap, w.counters.p + 4);
-        ++ctx->launches;
+        if (ctx->nV < (1 << 21) - 2) {
+            unsigned size = 1024;
+            while (size < 2u * (unsigned)nDup) size <<= 1; // <= 4 * cap entries: fits the sort scratch
+            CKC(cudaMemsetAsync(w.skey.p, 0xff, (size_t)size * sizeof(unsigned long long), st));
+            CKC(cudaMemsetAsync(w.sidx.p, 0, (size_t)size * sizeof(int), st));
+            k_dup_insert<<<nblk(nDup, 256), 256, 0, st>>>(nDup, w.dup.p, w.skey.p, w.sidx.p, size - 1);
+            k_dup_emit<<<nblk(size, 256), 256, 0, st>>>(size, w.skey.p, w.sidx.p, w.act.p, w.counters.p + 0, w.cap, w.counters.p + 4);
+            ctx->launches += 2;
+        }
+        else {
+            if ((rc = sort_lex(ctx, w.dup.p, nullptr, nDup, w.tmp4.p, nullptr))) return rc;
+            k_merge_dups<<<nblk(nDup, 256), 256, 0, st>>>(nDup, w.dup.p, w.act.p, w.counters.p + 0, w.cap, w.counters.p + 4);
+            ++ctx->launches;
+        }
         CKC(cudaMemcpyAsync(h, w.counters.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
         CKC(cudaStreamSynchronize(st));
         if (h[4]) {
