@@ -626,10 +626,12 @@ __device__ int ti_root_finder(const TiPair& P, const double* tol, double co_tol,
 }
 
 // ---- corner-parallel variant of the root finder for the warp-level pass ------------------------------------------------------
-// Deep searches are narrow (1-2 boxes per level), so parallelism over boxes does not exist; what can be parallelised is ONE box:
-// its 3 coordinates x 8 corners = 24 values of F are evaluated by 24 lanes, the co-domain interval of each coordinate is a 3-step
-// shuffle min/max inside its 8-lane group, and the inclusion flags are warp ballots.  All bookkeeping (K1/K2 tracking, bisection) is
-// warp-uniform scalar code over level buffers in shared memory.  Same arithmetic per corner, same decisions => same result as the
+// Deep searches are narrow (a handful of boxes per level), so there is little parallelism over boxes; what can be parallelised is
+// the box itself.  A narrow level is evaluated four boxes at a time: each 8-lane group takes one box, a lane is one of its 8 corners
+// and evaluates the 3 coordinates of F in turn; the co-domain interval of a coordinate is a 3-step shuffle min/max inside the group,
+// after which all 8 lanes know every inclusion flag of their box (no ballots).  Each group keeps its own K1/K2 candidates, merged by
+// one 2-step exchange per level.  Levels of >= kWideLevel boxes switch to one box per lane.  The split pass is always one box per
+// lane with a warp scan.  Level buffers live in shared memory.  Same arithmetic per corner, same decisions => same result as the
 // box-parallel variant.  Returns -1 when a level outgrows the shared-memory buffer (the caller restarts with the box-parallel variant).
 template <bool VF>
 __device__ int ti_root_finder_cp(const TiPair& P, const double* tol, double co_tol, double max_t, const double* err, double ms, int max_itr, DBox* sA, DBox* sB,
@@ -637,16 +639,8 @@ __device__ int ti_root_finder_cp(const TiPair& P, const double* tol, double co_t
 {
     const bool check_t = (max_t != 1.0);
     const double INF = __longlong_as_double(0x7ff0000000000000ll);
-    const int c = lane >> 3, corner = lane & 7;
+    const int corner = lane & 7;
     const int ci = corner >> 2, cj = (corner >> 1) & 1, cl = corner & 1;
-    double a0[4], a1[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        a0[k] = (c == 0) ? P.x0[3 * k] : ((c == 1) ? P.x0[3 * k + 1] : P.x0[3 * k + 2]);
-        a1[k] = (c == 0) ? P.x1[3 * k] : ((c == 1) ? P.x1[3 * k + 1] : P.x1[3 * k + 2]);
-    }
-    const double eps = ((c == 0) ? err[0] : ((c == 1) ? err[1] : err[2])) + ms;
-    const unsigned live = 0x00ffffffu; // lanes 24..31 idle
     DBox* cur = sA;
     DBox* nxt = sB;
     if (lane == 0) cur[0] = DBox{ 0ull, 0ull, 0ull, 0u, 0u };
@@ -708,51 +702,79 @@ __device__ int ti_root_finder_cp(const TiPair& P, const double* tol, double co_t
                 if (key_less(mk2, k2)) { k2 = mk2; p2 = mp2; }
             }
         }
-        else
-        for (int bI = 0; bI < n; ++bI) {
-            const DBox b = cur[bI];
-            const int tk = b.kk & 0xff, uk = (b.kk >> 8) & 0xff, vk = (b.kk >> 16) & 0xff;
-            const double tlo = dy_lo(b.tn, tk);
-            unsigned flags = 0;
-            if (tlo < toi_skip && tlo < t_prune) {
-                ++visited;
+        else {
+            // narrow level: FOUR boxes at a time, one per 8-lane group; a lane is one corner and evaluates the three coordinates in
+            // turn, so the co-domain interval of a coordinate is a 3-step shuffle min/max inside the group and every inclusion flag
+            // is known to all 8 lanes without a ballot.  Each group tracks its own K1/K2; one 2-step exchange merges them.
+            Key3 gk1 = { INF, INF, INF }, gk2 = { INF, INF, INF };
+            unsigned gp1 = 0, gp2 = 0;
+            double ga1 = 0.0, ga2 = 0.0;
+            const int grp = lane >> 3;
+            for (int base = 0; base < n; base += 4) {
+                const int bI = base + grp;
+                DBox b = DBox{ 0ull, 0ull, 0ull, 0u, 0u };
+                if (bI < n) b = cur[bI];
+                const int tk = b.kk & 0xff, uk = (b.kk >> 8) & 0xff, vk = (b.kk >> 16) & 0xff;
+                const double tlo = dy_lo(b.tn, tk);
+                const bool act = bI < n && tlo < toi_skip && tlo < t_prune;
                 const double tv = ci ? dy_hi(b.tn, tk) : tlo;
                 const double uv = cj ? dy_hi(b.un, uk) : dy_lo(b.un, uk);
                 const double vv = cl ? dy_hi(b.vn, vk) : dy_lo(b.vn, vk);
-                double pp[4];
+                bool excl = false, inside = true, tolc = true;
+                double tmax = 0.0;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) pp[k] = (a1[k] - a0[k]) * tv + a0[k];
-                double f;
-                if (VF) {
-                    const double pt = ((pp[2] - pp[1]) * uv + (pp[3] - pp[1]) * vv) + pp[1];
-                    f = pp[0] - pt;
-                }
-                else {
-                    const double pa = (pp[1] - pp[0]) * uv + pp[0];
-                    const double pb = (pp[3] - pp[2]) * vv + pp[2];
-                    f = pa - pb;
-                }
-                double mn = f, mx = f;
+                for (int cc = 0; cc < 3; ++cc) {
+                    double pp[4];
 #pragma unroll
-                for (int o = 1; o < 8; o <<= 1) {
-                    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-                    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                    for (int k = 0; k < 4; ++k) pp[k] = (P.x1[3 * k + cc] - P.x0[3 * k + cc]) * tv + P.x0[3 * k + cc];
+                    double f;
+                    if (VF) {
+                        const double pt = ((pp[2] - pp[1]) * uv + (pp[3] - pp[1]) * vv) + pp[1];
+                        f = pp[0] - pt;
+                    }
+                    else {
+                        const double pa = (pp[1] - pp[0]) * uv + pp[0];
+                        const double pb = (pp[3] - pp[2]) * vv + pp[2];
+                        f = pa - pb;
+                    }
+                    double mn = f, mx = f;
+#pragma unroll
+                    for (int o = 1; o < 8; o <<= 1) {
+                        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                    }
+                    const double e = err[cc] + ms;
+                    const double tt = mx - mn;
+                    excl = excl || (mn > e || mx < -e);
+                    inside = inside && (mn >= -e && mx <= e);
+                    tolc = tolc && !(tt > co_tol);
+                    tmax = (cc == 0) ? tt : fmax(tmax, tt);
                 }
-                const double tt = mx - mn;
-                const bool excl = (mn > eps || mx < -eps);
-                if (!(__ballot_sync(0xffffffffu, excl) & live)) { // the co-domain box contains the origin
+                unsigned flags = 0;
+                if (act && !excl) { // the co-domain box contains the origin
                     flags = F_ZERO;
-                    const bool box_in = !(__ballot_sync(0xffffffffu, !(mn >= -eps && mx <= eps)) & live);
-                    const bool tol_cond = !(__ballot_sync(0xffffffffu, tt > co_tol) & live);
-                    const double tmax = fmax(fmax(__shfl_sync(0xffffffffu, tt, 0), __shfl_sync(0xffffffffu, tt, 8)), __shfl_sync(0xffffffffu, tt, 16));
                     const bool cond1 = pow2neg(tk) <= tol[0] && pow2neg(uk) <= tol[1] && pow2neg(vk) <= tol[2];
                     const Key3 key = { tlo, dy_lo(b.un, uk), dy_lo(b.vn, vk) };
-                    const bool flagged = tol_cond || box_in || cond1;
-                    if (key_less(key, k1)) { k1 = key; p1 = flagged ? 1u : 0u; a1max = tmax; }
-                    if (flagged && key_less(key, k2)) { k2 = key; p2 = cond1 ? 1u : 0u; }
+                    const bool flagged = tolc || inside || cond1;
+                    if (key_less(key, gk1)) { gk1 = key; gp1 = flagged ? 1u : 0u; ga1 = tmax; }
+                    if (flagged && key_less(key, gk2)) { gk2 = key; gp2 = cond1 ? 1u : 0u; }
                 }
+                visited += __popc(__ballot_sync(0xffffffffu, act && corner == 0));
+                if (bI < n && corner == 0) cur[bI].kk = (b.kk & 0x00ffffffu) | flags;
             }
-            if (lane == 0) cur[bI].kk = (b.kk & 0x00ffffffu) | flags;
+#pragma unroll
+            for (int o = 8; o <= 16; o <<= 1) { // merge the four groups (all lanes of a group hold the same candidates)
+                Key3 r1, r2;
+                r1.t = __shfl_xor_sync(0xffffffffu, gk1.t, o); r1.u = __shfl_xor_sync(0xffffffffu, gk1.u, o); r1.v = __shfl_xor_sync(0xffffffffu, gk1.v, o);
+                r2.t = __shfl_xor_sync(0xffffffffu, gk2.t, o); r2.u = __shfl_xor_sync(0xffffffffu, gk2.u, o); r2.v = __shfl_xor_sync(0xffffffffu, gk2.v, o);
+                const unsigned rp1 = __shfl_xor_sync(0xffffffffu, gp1, o), rp2 = __shfl_xor_sync(0xffffffffu, gp2, o);
+                const double ra1 = __shfl_xor_sync(0xffffffffu, ga1, o);
+                if (key_less(r1, gk1)) { gk1 = r1; gp1 = rp1; ga1 = ra1; }
+                if (key_less(r2, gk2)) { gk2 = r2; gp2 = rp2; }
+            }
+            (void)ga2;
+            k1 = gk1; p1 = gp1; a1max = ga1;
+            k2 = gk2; p2 = gp2;
         }
         __syncwarp();
         if (k1.t == INF) break; // search space exhausted
@@ -776,7 +798,7 @@ __device__ int ti_root_finder_cp(const TiPair& P, const double* tol, double co_t
             use_skip = true;
         }
         int nn = 0;
-        if (n >= c_wide_level) {
+        { // split pass, one box per lane (levels of the warp-level pass never exceed a few dozen boxes before the box-parallel switch)
             bool over = false, deep = false;
             for (int base = 0; base < n; base += 32) {
                 const int i = base + lane;
@@ -841,49 +863,6 @@ __device__ int ti_root_finder_cp(const TiPair& P, const double* tol, double co_t
                 return 1;
             }
             if (__any_sync(0xffffffffu, over)) return -1;
-        }
-        else
-        for (int bI = 0; bI < n; ++bI) {
-            const DBox b = cur[bI];
-            if (!(b.kk & F_ZERO)) continue;
-            const int tk = b.kk & 0xff, uk = (b.kk >> 8) & 0xff, vk = (b.kk >> 16) & 0xff;
-            const Key3 key = { dy_lo(b.tn, tk), dy_lo(b.un, uk), dy_lo(b.vn, vk) };
-            if (has_k2 && !key_less(key, k2)) continue;
-            const double w[3] = { pow2neg(tk), pow2neg(uk), pow2neg(vk) };
-            int split = -1;
-            double best = -1.0;
-#pragma unroll
-            for (int d = 0; d < 3; ++d)
-                if (w[d] > tol[d]) {
-                    const double r = w[d] / tol[d];
-                    if (r > best) { best = r; split = d; }
-                }
-            const int pk = split == 0 ? tk : (split == 1 ? uk : vk);
-            if (split < 0 || pk >= 60) { // bisection overflow: conservative per-level estimate, as in the box-parallel variant
-                if (lane == 0) atomicAdd(warn, 1);
-                toi = temp_toi;
-                out_tol = temp_out_tol;
-                return 1;
-            }
-            const unsigned long long pn = split == 0 ? b.tn : (split == 1 ? b.un : b.vn);
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const unsigned long long hn = 2 * pn + half;
-                const int hk = pk + 1;
-                bool keep = true;
-                if (split == 0) { if (check_t) keep = !(dy_hi(hn, hk) < 0.0 || dy_lo(hn, hk) > max_t); }
-                else if (VF) keep = (split == 1) ? sum_le_1(hn, hk, b.vn, vk) : sum_le_1(hn, hk, b.un, uk);
-                if (keep) {
-                    if (nn >= kSmemLevel) return -1; // level too wide for shared memory
-                    DBox ch = b;
-                    ch.kk &= 0x00ffffffu;
-                    if (split == 0) { ch.tn = hn; ch.kk = (ch.kk & ~0xffu) | (unsigned)hk; }
-                    else if (split == 1) { ch.un = hn; ch.kk = (ch.kk & ~0xff00u) | ((unsigned)hk << 8); }
-                    else { ch.vn = hn; ch.kk = (ch.kk & ~0xff0000u) | ((unsigned)hk << 16); }
-                    if (lane == 0) nxt[nn] = ch;
-                    ++nn;
-                }
-            }
         }
         __syncwarp();
         DBox* t = cur; cur = nxt; nxt = t;
