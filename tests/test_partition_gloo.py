@@ -50,3 +50,52 @@ def test_tet_partition_allreduce_gloo():
     for p in procs:
         p.join(120)
     assert q.get(timeout=5) is True
+
+
+def _contact_worker(rank, world, port, q):
+    """Contact stage under the context's partition rules (api.cu / constraint.cu / ccd.cu): every rank keeps a contiguous share of the
+    pair lists and of the CCD candidates; SUM of the barrier energy / gradient / CSR values and MIN of the step reproduce one rank."""
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle as orc
+    from ipc_b200 import scenes
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    m, info = scenes.ball_pile(2, res=5, seed=5, height=2)
+    s = orc.Surf(m)
+    dHat, p, kappa = info["dHat"], info["p"], 1e8
+    mm, pa, pe, cand = s.constraint_set(dHat, nthreads=2)
+    ia, ja = m.csr_pattern(1, extra_pairs=[(a, b) for r in list(mm) + list(pa) for a in ([(-r[0] - 1) if r[0] < 0 else r[0]] + [x for x in r[1:] if x >= 0])
+                                            for b in ([(-r[0] - 1) if r[0] < 0 else r[0]] + [x for x in r[1:] if x >= 0]) if a < b]
+                       + [(a, b) for e in pe if e[0] >= 0 for a in list(m.SFEdges[e[0]]) + list(m.SFEdges[e[1]]) for b in list(m.SFEdges[e[0]]) + list(m.SFEdges[e[1]]) if a != b])
+
+    def share(n):  # [n*rank/world, n*(rank+1)/world)
+        return slice(n * rank // world, n * (rank + 1) // world)
+
+    mm_l, pa_l, pe_l, cand_l = mm[share(len(mm))], pa[share(len(pa))], pe[share(len(pa))], cand[share(len(cand))]
+    E = torch.tensor([s.barrier_energy(mm_l, pa_l, pe_l, dHat, kappa)[0]], dtype=torch.float64)
+    g = torch.from_numpy(s.barrier_gradient(mm_l, pa_l, pe_l, dHat, kappa))
+    a = torch.from_numpy(s.barrier_hessian_csr(mm_l, pa_l, pe_l, dHat, kappa, ia, ja, 1, 1, nthreads=2))
+    evf, eee = orc.ti_error(s.V, m.nV, p)
+    step = torch.tensor([orc.ccd_partial(s, p, cand_l, 1e-6, evf, eee, 1.0, 2)[0]], dtype=torch.float64)
+    for t, op in ((E, dist.ReduceOp.SUM), (g, dist.ReduceOp.SUM), (a, dist.ReduceOp.SUM), (step, dist.ReduceOp.MIN)):
+        dist.all_reduce(t, op=op)
+    if rank == 0:
+        E1 = s.barrier_energy(mm, pa, pe, dHat, kappa)[0]
+        g1 = s.barrier_gradient(mm, pa, pe, dHat, kappa)
+        a1 = s.barrier_hessian_csr(mm, pa, pe, dHat, kappa, ia, ja, 1, 1, nthreads=2)
+        st1 = orc.ccd_partial(s, p, cand, 1e-6, evf, eee, 1.0, 2)[0]
+        ok = (len(mm) > 10 and abs(float(E) - E1) <= 1e-12 * abs(E1) and np.abs(g.numpy() - g1).max() <= 1e-12 * np.abs(g1).max()
+              and np.abs(a.numpy() - a1).max() <= 1e-12 * np.abs(a1).max() and float(step) == st1)  # the step is bit-exact: min is exact
+        q.put(ok)
+    dist.destroy_process_group()
+
+
+def test_contact_partition_allreduce_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_contact_worker, args=(r, 2, 29643, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+    assert q.get(timeout=5) is True
