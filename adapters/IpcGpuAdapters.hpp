@@ -18,8 +18,13 @@
 #include "LinSysSolver.hpp"    // IPC::LinSysSolver                     (src/LinSysSolver/LinSysSolver.hpp:34-37)
 #include "Mesh.hpp"            // IPC::Mesh<dim>                        (src/Mesh.hpp:61-144)
 #include "MeshCollisionUtils.hpp" // IPC::MMCVID                        (src/CollisionObject/MeshCollisionUtils.hpp:24-110)
+#include "SpatialHash.hpp"     // IPC::SpatialHash<dim>                 (src/Utils/SpatialHash.hpp:21-22)
+#include "CCDUtils.hpp"        // tight_inclusion_{vf,ee}_err           (src/Utils/CCDUtils.hpp:24)
 
 #include <spdlog/spdlog.h>
+#include <algorithm>
+#include <cstdint>
+#include <cstdlib>
 #include <stdexcept>
 #include <vector>
 

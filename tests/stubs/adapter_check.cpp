@@ -1,0 +1,21 @@
+// Instantiates every adapter against the restated reference interface (syntax/semantic check only: g++ -fsyntax-only).
+#include "IpcGpuAdapters.hpp"
+template class IPC::GpuElasticEnergy<3>;
+void touch(IPC::IpcGpuScene& s, const IPC::Mesh<3>& m, IPC::LinSysSolver<Eigen::VectorXi, Eigen::VectorXd>* sol, const IPC::SpatialHash<3>& sh)
+{
+    s.setMesh(m, IPCGPU_NEOHOOKEAN);
+    s.setPattern(sol, 1);
+    s.setState(m);
+    std::vector<IPC::MMCVID> a, b;
+    std::vector<std::pair<int, int>> c, d;
+    Eigen::VectorXd v;
+    double x = 1.0;
+    using H = IPC::GpuSelfCollisionHandler;
+    H::computeConstraintSet(m, sh, 1e-6, a, b, c, true, d);
+    (void)H::barrierEnergy(1e-6, 1e8);
+    H::leftMultiplyConstraintJacobianT(m, a, v, v, 1e-6, 1e8);
+    H::augmentIPHessian(m, a, sol, 1e-6, 1e8, true);
+    H::largestFeasibleStepSize_TightInclusion(m, sh, v, 1e-6, d, d, x);
+    H::hashBuildSwept(v, x, 0.1);
+    H::largestFeasibleStepSize_CCD_TightInclusion(m, sh, v, 1e-6, d, x);
+}
