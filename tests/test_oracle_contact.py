@@ -255,3 +255,32 @@ def test_barrier_gradient_hessian_fd():
         for r in range(3 * m.nV):
             cols = ja[ia[r] - 1:ia[r + 1] - 1] - 1
             assert np.allclose(a[ia[r] - 1:ia[r + 1] - 1], dense[r, cols], atol=1e-10 * abs(dense).max())
+
+
+def test_pair_hessians_are_translation_invariant():
+    """Assumption behind the GPU's 12 -> 9 reduction of makePD: every pair Hessian annihilates rigid translations of its
+    stencil, for all closest-feature types incl. PP/PE multiplicities; and makePD(H) = Q^T makePD(Q H Q^T) Q for the Helmert Q."""
+    from ipc_b200 import scenes
+    m, info = scenes.ball_pile(3, res=6, seed=5, height=3)
+    s = orc.Surf(m)
+    mm, pa, pe, _ = s.constraint_set(info["dHat"], nthreads=4)
+    assert len(mm) > 50
+    kinds = set()
+    r2, r6, r12 = 2 ** -0.5, 6 ** -0.5, 12 ** -0.5
+    Q = np.kron(np.array([[r2, -r2, 0, 0], [r6, r6, -2 * r6, 0], [r12, r12, r12, -3 * r12]]), np.eye(3))
+
+    def make_pd(M):
+        w, v = np.linalg.eigh(M)
+        return (v * np.maximum(w, 0)) @ v.T
+
+    for row in mm:
+        H, nv = s.pair_hessian(row, info["dHat"], 1e8)
+        kinds.add((int(row[0] < 0), nv))
+        scale = np.abs(H).max()
+        for k in range(3):
+            t = np.zeros(12)
+            t[k:3 * nv:3] = 1.0
+            assert np.abs(H @ t).max() <= 1e-9 * scale
+        # the projected matrix is a fixed point of the reduced projection
+        assert np.abs(Q.T @ make_pd(Q @ H @ Q.T) @ Q - H).max() <= 1e-9 * scale
+    assert len(kinds) >= 3  # several stencil types were exercised
