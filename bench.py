@@ -29,7 +29,7 @@ ALG_BYTES_PER_TET = 208 + 624 + 96  # read stencil+material, write 78 upper-tria
 # dram__bytes_read.sum + dram__bytes_write.sum of k_elastic_grad_hess<NH,g,H> from the `ncu --set full` capture of this same
 # command (profiles/r01b_prof_k_elastic_grad_hess.summary.csv: 117.7 MB + 727.7 MB over 1,002,000 tets)
 NCU_DRAM_BYTES_PER_TET = (117.712128e6 + 727.696128e6) / 1002000
-ALG_BYTES_PER_CCD_CANDIDATE = 200  # k_ti_stage1: 8 B candidate + 4 vertices x (x, p) x 24 B
+ALG_BYTES_PER_CCD_CANDIDATE = 208  # 8 B candidate + 4 vertices x (x, p) x 24 B + 8 B result
 DT2 = 0.025 ** 2
 
 
