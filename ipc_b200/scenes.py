@@ -71,3 +71,29 @@ def twisted_mat(nx=26, ny=26, nz=25, seed=2, energy=1, invert_frac=0.001):
         k = max(1, int(invert_frac * m.nV))
         m.V[rng.integers(0, m.nV, k)] += 0.8 * m.avgEdgeLen * rng.standard_normal((k, 3))
     return m
+
+
+def ball_on_mat(nx=40, res=6, seed=3, energy=0, dhat_rel=1e-3, gap_lo=0.2, gap_hi=1.5):
+    """BASELINE config C3 ("ball-on-mat, barrier contact + CCD line search"): a one-cell-thick mat of nx x nx x 1 cells (all surface, as
+    the reference's thin mats are) and a ball hovering over its middle at a gap of U(gap_lo, gap_hi)*sqrt(dHat); the search direction
+    pushes the ball down by up to 2 sqrt(dHat) (nx=200 -> 240,000 mat tets).  Returns (mesh, info) like ball_pile."""
+    rng = np.random.default_rng(seed)
+    h = 1.0 / nx
+    Vm, Tm = M.grid_tets(nx, nx, 1, h=h)
+    radius = 0.15
+    Vb, Tb = M.superball_tets(res, radius, 2.0)
+    ext = np.array([1.0, 1.0, h + 2 * radius])
+    dHat = dhat_rel ** 2 * float((ext ** 2).sum())
+    sq = np.sqrt(dHat)
+    gap = rng.uniform(gap_lo, gap_hi) * sq
+    nVm = Vm.shape[0]
+    Vm_def = Vm + 0.02 * h * rng.standard_normal((nVm, 3)) * np.array([1.0, 1.0, 0.2])
+    # the ball's lowest vertex sits `gap` above the highest mat vertex; off the lattice so that no feature pair is exactly degenerate
+    c = np.array([0.5 + 0.31 * h, 0.5 - 0.17 * h, Vm_def[:, 2].max() + gap - Vb[:, 2].min()])
+    m = M.merge_meshes([(Vm, Tm), (Vb + c, Tb)], energy=energy)
+    m.V = m.V_rest.copy()
+    m.V[:nVm] = Vm_def
+    p = np.zeros((m.nV, 3))
+    p[nVm:, 2] = -rng.uniform(0.0, 2.0, m.nV - nVm) * sq
+    p += rng.normal(0, 0.05 * sq, (m.nV, 3))
+    return m, dict(dHat=dHat, p=np.ascontiguousarray(p).ravel(), n_mat_verts=nVm, gap=gap)

@@ -128,3 +128,31 @@ def test_hashed_drivers_equal_brute_force():
     a_h, z2, n_h = orc.ccd_full_hashed(s, p, 1.0, h, 1e-6, evf, eee, nthreads=4)
     assert z == z2 == 0 and a_bf == a_h
     assert n_h >= n_bf  # voxel-id aliasing in the hash can only add (harmless) candidates
+
+
+def test_ball_on_mat_config_c3():
+    """BASELINE config C3 (ball on a one-cell-thick mat, barrier contact + CCD) at a size the brute-force enumeration sweeps: the
+    reference-style hashed drivers equal brute force, the barrier is finite, and the TI step bound is conservative."""
+    from ipc_b200 import scenes
+    m, info = scenes.ball_on_mat(24, res=5)
+    s = orc.Surf(m)
+    dHat, p = info["dHat"], info["p"]
+    hv = m.avgEdgeLen / 3.0
+    mm, pa, pe, cand = s.constraint_set(dHat, nthreads=4)
+    mm2, pa2, pe2, cand2 = s.constraint_set_hashed(dHat, hv, 4)
+    assert len(mm) >= 10 and len(cand) >= len(mm)
+    assert np.array_equal(mm, mm2) and np.array_equal(pa, pa2) and np.array_equal(pe, pe2) and np.array_equal(cand, cand2)
+    E, bad = s.barrier_energy(mm, pa, pe, dHat, 1e8)
+    assert bad == 0 and np.isfinite(E) and E > 0
+    evf, eee = orc.ti_error(s.V, m.nV, p)
+    a_part, _ = orc.ccd_partial(s, p, cand, 1e-6, evf, eee, 1.0, 4)
+    g, ag = orc.grid_swept(s, p, a_part, hv)
+    a_bf, z, npairs = orc.ccd_full(s, p, g, ag, 1e-6, evf, eee, ag, nthreads=4)
+    a_h, z2, npairs2 = orc.ccd_full_hashed(s, p, a_part, hv, 1e-6, evf, eee, 4)
+    assert z == 0 and z2 == 0 and npairs == npairs2 and a_bf == a_h and 0.0 < a_h <= a_part < 1.0  # the ball does reach the mat within the step
+    V2 = m.V + a_h * p.reshape(-1, 3)
+    for c in cand:
+        if c[0] < 0:
+            assert orc.point_tri_d(V2[[m.SVI[-c[0] - 1]] + list(m.SF[c[1]])]) > 0
+        else:
+            assert orc.edge_edge_d(V2[list(m.SFEdges[c[0]]) + list(m.SFEdges[c[1]])]) > 0
