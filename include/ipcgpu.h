@@ -100,8 +100,10 @@ int ipcgpu_elastic_gradient(ipcgpu_ctx* ctx, double coef, int redoSVD, int proje
  * a_inout != NULL: host array is uploaded, accumulated into and downloaded (addCoeff semantics);
  * a_inout == NULL: device-resident values are accumulated (zero them with ipcgpu_csr_set_zero). */
 int ipcgpu_elastic_hessian(ipcgpu_ctx* ctx, double coef, int redoSVD, int projectSPD, int projectDBC, double* a_inout);
-/* fused variant for the Newton loop: computeGradient + computePrecondMtr's elastic and mass terms in one
- * pass over the tets (Optimizer.cpp:3416, 3439-3450, 3619-3668). Results stay on the device when NULL. */
+/* fused variant for the Newton loop: computeGradient + computePrecondMtr's setZero, elastic and mass terms in one
+ * pass over the tets (Optimizer.cpp:3416, 3439-3450, 3616-3668). The device-resident gradient and CSR values are
+ * OVERWRITTEN (the value array is zeroed first, like LinSysSolver::setZero at :3616); the barrier_* calls then accumulate
+ * on top.  Results stay on the device when the pointers are NULL. */
 int ipcgpu_elastic_grad_hess(ipcgpu_ctx* ctx, double coef, int projectSPD, int projectDBC, int add_mass,
     double* g, double* a);
 /* Energy::filterStepSize (Energy.cpp:565-581) */

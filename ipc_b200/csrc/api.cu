@@ -186,6 +186,13 @@ void ipcgpu_destroy(ipcgpu_ctx* ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    for (auto& v : ctx->prof)
+        for (auto& pr : v) {
+            cudaEventDestroy(pr.first);
+            cudaEventDestroy(pr.second);
+        }
+    if (ctx->timer_a) cudaEventDestroy(ctx->timer_a);
+    if (ctx->timer_b) cudaEventDestroy(ctx->timer_b);
     if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->nccl_comm);
     if (ctx->stream) {
         cudaStreamSynchronize(ctx->stream);
@@ -423,7 +430,10 @@ int ipcgpu_elastic_grad_hess(ipcgpu_ctx* ctx, double coef, int projectSPD, int p
 {
     CK(cudaSetDevice(ctx->device));
     REQUIRE(ctx->nnz > 0, IPCGPU_ERR_STATE, "ipcgpu_set_csr first");
-    int rc = run_grad_hess(ctx, coef, projectSPD, projectDBC, true, true, add_mass, false);
+    // the value array is rebuilt from scratch (LinSysSolver::setZero, then addCoeff of every term): slots that no local tet touches
+    // -- contact-only blocks of the augmented pattern, other ranks' blocks -- must not keep last iteration's values
+    CK(cudaMemsetAsync(ctx->a.p, 0, (size_t)ctx->nnz * sizeof(double), ctx->stream));
+    int rc = run_grad_hess(ctx, coef, projectSPD, projectDBC, true, true, add_mass, true);
     if (rc) return rc;
     if (ctx->nranks > 1 && (g || a)) {
         rc = ipcgpu_allreduce_grad_hess(ctx, g ? 1 : 0, a ? 1 : 0);
@@ -744,7 +754,7 @@ int ipcgpu_barrier_hessian(ipcgpu_ctx* ctx, double dHat, double kappa, int proje
         const BarrierArgs ba = barrier_args(ctx, dHat, kappa, projectDBC);
         const size_t np = (size_t)std::max(ba.nC + ba.nP, 1);
         ALLOC(ctx->bHraw, np * 144);
-        ALLOC(ctx->brows, np * 4);
+        ALLOC(ctx->brows, np * 5); // 4 row ids + the makePD "unchanged" flag per pair
         barrier_hessian(ba, ctx->a.p, ctx->flag.p, ctx->bHraw.p, ctx->brows.p, ctx->stream);
     }
     ctx->prof_end(pe);

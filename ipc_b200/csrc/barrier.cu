@@ -326,7 +326,7 @@ DEV void reduced_column(const double* __restrict__ H0, int j, double* col /* 10 
     col[9] = 0.0;
 }
 
-__global__ void __launch_bounds__(32 * kProjWarps) k_barrier_hessian_project(int n, double* __restrict__ H)
+__global__ void __launch_bounds__(32 * kProjWarps) k_barrier_hessian_project(int n, double* __restrict__ H, int* __restrict__ psd)
 {
     constexpr int N = kProjN, G = kProjG;
     const unsigned full = 0xffffffffu;
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(32 * kProjWarps) k_barrier_hessian_project(int
     const int grp = lane / G, k = lane - G * grp, base = G * grp;
     const int warp = blockIdx.x * kProjWarps + (threadIdx.x >> 5);
     const int c = warp * kProjPerWarp + grp;
-    const bool live = grp < kProjPerWarp && c < n;
+    bool live = grp < kProjPerWarp && c < n;
     double AT[N], AB[N], VT[N], VB[N];
     double* H0 = H + (size_t)(live ? c : 0) * 144;
 #pragma unroll
@@ -438,6 +438,16 @@ __global__ void __launch_bounds__(32 * kProjWarps) k_barrier_hessian_project(int
             lt = AT[2 * m];
             lb = AB[2 * m + 1];
         }
+    // IglUtils.hpp:123-125: "if (eigenvalues()[0] >= 0.0) return;" -- a block without a negative eigenvalue is handed back untouched.
+    // The raw 12x12 input then stays in its slot (nothing is written below) and the scatter kernel reads it directly.
+    {
+        double lmin = fmin(lt, lb);
+#pragma unroll
+        for (int m = 0; m < G; ++m) lmin = fmin(lmin, __shfl_sync(full, fmin(lt, lb), base + m));
+        const bool unchanged = lmin >= 0.0;
+        if (live && k == 0) psd[c] = unchanged ? 1 : 0;
+        if (unchanged) live = false; // (group-uniform) keep the shuffles below convergent, skip the stores
+    }
     lt = fmax(lt, 0.0);
     lb = fmax(lb, 0.0);
 #pragma unroll
@@ -457,13 +467,14 @@ __global__ void __launch_bounds__(32 * kProjWarps) k_barrier_hessian_project(int
 // scatter of the projected pair Hessians into the CSR values (upper-triangular 3x3 blocks, LinSysSolver.hpp:207-265)
 constexpr int kScatWarps = 8;
 __global__ void __launch_bounds__(32 * kScatWarps) k_barrier_hessian_scatter(BarrierArgs p, const double* __restrict__ H, const int* __restrict__ rows_in,
-    double* __restrict__ a, int* __restrict__ err)
+    const int* __restrict__ psd, double* __restrict__ a, int* __restrict__ err)
 {
     __shared__ int sOff[kScatWarps][48];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int c = blockIdx.x * kScatWarps + wib;
     if (c >= p.nC + p.nP) return;
     const double* H0 = H + (size_t)c * 144;
+    const bool raw = psd[c] != 0; // makePD returned its input: the slot still holds the unprojected 12x12
     // CSR offsets of the 16 vertex blocks x 3 rows (upper-triangular blocks only); -1 = skip, -2 = missing in the pattern
     int rows[4];
 #pragma unroll
@@ -493,11 +504,14 @@ __global__ void __launch_bounds__(32 * kScatWarps) k_barrier_hessian_scatter(Bar
                 if (rows[bi] == rows[bj] && q < r) continue; // strictly lower part of a diagonal block
                 // (Q^T M Q)[i][j] = sum_{a,b} Q4[a][bi] Q4[b][bj] M[3a+r][3b+q]
                 double v = 0.0;
+                if (raw) v = H0[i * 12 + j];
+                else {
 #pragma unroll
-                for (int ka = 0; ka < 3; ++ka) {
-                    const double qa = helmert(ka, bi);
+                    for (int ka = 0; ka < 3; ++ka) {
+                        const double qa = helmert(ka, bi);
 #pragma unroll
-                    for (int kb = 0; kb < 3; ++kb) v += (qa * helmert(kb, bj)) * H0[(3 * ka + r) * 9 + 3 * kb + q];
+                        for (int kb = 0; kb < 3; ++kb) v += (qa * helmert(kb, bj)) * H0[(3 * ka + r) * 9 + 3 * kb + q];
+                    }
                 }
                 atomicAdd(a + o + q, v);
             }
@@ -523,8 +537,9 @@ void barrier_hessian(const BarrierArgs& p, double* a, int* err, double* Hraw, in
     if (n <= 0) return;
     k_barrier_hessian_build<<<(n + 63) / 64, 64, 0, st>>>(p, Hraw, rows);
     const int per_cta = kProjWarps * kProjPerWarp;
-    k_barrier_hessian_project<<<(n + per_cta - 1) / per_cta, 32 * kProjWarps, 0, st>>>(n, Hraw);
-    k_barrier_hessian_scatter<<<(n + kScatWarps - 1) / kScatWarps, 32 * kScatWarps, 0, st>>>(p, Hraw, rows, a, err);
+    int* psd = rows + (size_t)4 * n; // one flag per pair behind the row ids
+    k_barrier_hessian_project<<<(n + per_cta - 1) / per_cta, 32 * kProjWarps, 0, st>>>(n, Hraw, psd);
+    k_barrier_hessian_scatter<<<(n + kScatWarps - 1) / kScatWarps, 32 * kScatWarps, 0, st>>>(p, Hraw, rows, psd, a, err);
 }
 
 } // namespace ipcgpu

@@ -929,8 +929,10 @@ __device__ int pair_ccd(bool vf, const TiPair& P, const NarrowArgs& a, DBox* buf
                  : ti_ccd<false, W>(P, a.err_ee, ms, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn, sA, sB, thread_budget, a.best);
     if (hit == 2) return 2;
     if (hit && toi < 1e-6) { // :759-781
-        hit = vf ? ti_ccd<true, W>(P, a.err_vf, 0.0, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn, sA, sB, thread_budget, a.best)
-                 : ti_ccd<false, W>(P, a.err_ee, 0.0, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn, sA, sB, thread_budget, a.best);
+        // no pruning against the running minimum here: this result is rescaled by 0.8 afterwards, so a box starting in
+        // [best, 1.25 best) can still lower the global step (the exactness argument of ti_root_finder only covers unscaled results)
+        hit = vf ? ti_ccd<true, W>(P, a.err_vf, 0.0, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn, sA, sB, thread_budget, nullptr)
+                 : ti_ccd<false, W>(P, a.err_ee, 0.0, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn, sA, sB, thread_budget, nullptr);
         if (hit == 2) return 2;
         if (hit) toi *= 0.8;
     }

@@ -58,7 +58,7 @@ struct BarrierArgs {
 void barrier_energy(const BarrierArgs& p, double* partials, int* bad, cudaStream_t st);
 int barrier_energy_blocks(int n);
 void barrier_gradient(const BarrierArgs& p, double* g, cudaStream_t st);
-void barrier_hessian(const BarrierArgs& p, double* a, int* err, double* Hraw /* 144 per pair */, int* rows /* 4 per pair */, cudaStream_t st);
+void barrier_hessian(const BarrierArgs& p, double* a, int* err, double* Hraw /* 144 per pair */, int* rows /* 5 per pair: 4 vertex ids, then n flags */, cudaStream_t st);
 // elastic.cu (shared fixed-order reduction)
 void reduce_sum(const double* partials, int n, double scale, double* out, cudaStream_t st);
 

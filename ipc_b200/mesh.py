@@ -103,7 +103,7 @@ def surface_edges(SF):
 class Mesh:
     """Arrays the reference's Mesh<3> owns, in the layouts its Eigen members expose through .data()."""
 
-    def __init__(self, V_rest, T, YM=1e5, PR=0.4, density=1000.0, energy=0):
+    def __init__(self, V_rest, T, YM=1e5, PR=0.4, density=1000.0, energy=0, SF=None):
         self.V_rest = np.ascontiguousarray(V_rest, dtype=np.float64)  # (nV,3)
         self.V = self.V_rest.copy()
         self.T = np.ascontiguousarray(T, dtype=np.int32)  # (nT,4)
@@ -122,7 +122,9 @@ class Mesh:
         # igl::avg_edge_length over the cyclic tet edges (0,1)(1,2)(2,3)(3,0), used for the hash cell size
         cyc = [(0, 1), (1, 2), (2, 3), (3, 0)]
         self.avgEdgeLen = float(np.mean([np.linalg.norm(x[:, i] - x[:, j], axis=1).mean() for i, j in cyc]))
-        self.SF = boundary_faces(self.T)
+        # surface triangles: the file's own $Surface block when the mesh came from a reference .msh (IglUtils.cpp:548-560),
+        # otherwise the boundary faces of the tets (what the reference's findSurfaceTris does for files without one)
+        self.SF = boundary_faces(self.T) if SF is None or len(SF) == 0 else np.ascontiguousarray(SF, dtype=np.int32)
         self.SVI = np.unique(self.SF).astype(np.int32)  # Mesh::computeBoundaryVert (sorted surface vertices)
         self.SFEdges = surface_edges(self.SF)
         self.bbox_diag2 = float(((self.V_rest.max(0) - self.V_rest.min(0)) ** 2).sum())
@@ -186,13 +188,20 @@ class Mesh:
 
 
 def merge_meshes(parts, **kw):
-    """Concatenate (V,T) pairs into one Mesh (multiple bodies = one reference Mesh with several components)."""
-    Vs, Ts, off = [], [], 0
-    for V, T in parts:
+    """Concatenate (V,T[,SF]) parts into one Mesh (multiple bodies = one reference Mesh with several components).  When every part
+    brings its surface triangles they are concatenated too (the reference appends each shape's $Surface block, Config/main load
+    loop); otherwise the surface is recomputed from the tets."""
+    Vs, Ts, Fs, off = [], [], [], 0
+    all_sf = all(len(pt) > 2 and pt[2] is not None and len(pt[2]) for pt in parts)
+    for pt in parts:
+        V, T = pt[0], pt[1]
         Vs.append(V)
         Ts.append(T + off)
+        if all_sf:
+            Fs.append(np.asarray(pt[2]) + off)
         off += V.shape[0]
-    return Mesh(np.concatenate(Vs), np.concatenate(Ts).astype(np.int32), **kw)
+    SF = np.concatenate(Fs).astype(np.int32) if all_sf else None
+    return Mesh(np.concatenate(Vs), np.concatenate(Ts).astype(np.int32), SF=SF, **kw)
 
 
 def deform(mesh, seed, twist=0.5, amp=0.02, noise=0.02, require_positive=True):
