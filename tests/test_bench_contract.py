@@ -10,8 +10,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def run(env_extra):
     env = dict(os.environ, **env_extra)
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--res", "5",
-                          "--cpu-sample-tets", "3000", "--tets", "30000"], capture_output=True, text=True, env=env, timeout=600)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--res", "5", "--scene", "pile",
+                          "--tets", "30000"], capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     return out.stdout.strip()
 
