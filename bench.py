@@ -30,6 +30,10 @@ ALG_BYTES_PER_TET = 208 + 624 + 96  # read stencil+material, write 78 upper-tria
 # command (profiles/r01b_prof_k_elastic_grad_hess.summary.csv: 117.7 MB + 727.7 MB over 1,002,000 tets)
 NCU_DRAM_BYTES_PER_TET = (117.712128e6 + 727.696128e6) / 1002000
 ALG_BYTES_PER_CCD_CANDIDATE = 208  # 8 B candidate + 4 vertices x (x, p) x 24 B + 8 B result
+NCU_TRAFFIC_SOURCE = "ncu --set full, profiles/r01b_prof_k_elastic_grad_hess.summary.csv (bytes per tet x tets this rank assembles)"
+# figures of the committed ncu captures that go with the roofline objects (see profiles/)
+NCU_TET = {"fp64_pipe_pct": 50.5, "issue_slots_pct": 38.0, "warps_active_pct": 23.7, "source": "profiles/r01b_prof_k_elastic_grad_hess.summary.csv"}
+NCU_TI = {"kernel": "k_ti_stage2", "fp64_pipe_pct": 10.7, "issue_slots_pct": 22.5, "warps_active_pct": 12.0, "source": "profiles/r01b_prof_k_ti_stage2.summary.csv"}
 DT2 = 0.025 ** 2
 
 
@@ -194,6 +198,7 @@ def main():
     ap.add_argument("--res", type=int, default=10, help="ball resolution of --scene pile: 6*res^3 tets per ball")
     ap.add_argument("--scene", default="c5", choices=["c5", "pile"], help="c5 = 146 x sphere1K.msh FCC pile (BASELINE C5 as specified), pile = round-1 synthetic column pile")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity check against the oracle (rank 0, before the warm-up)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -250,40 +255,72 @@ def main():
             torch.cuda.synchronize()
 
     stats = {}
+    part = ctx.partition_info()
+    own0, own1 = part["value_begin"], part["value_end"]  # CSR values of the rows this rank owns (everything on one rank)
+
+    def enqueue_iteration():
+        """one Newton iteration's hot path, NULL outputs everywhere: one uninterrupted stream, nothing read back"""
+        ctx.constraint_set(dHat, 1, fetch=False, sizes=False)
+        ctx.elastic_energy(DT2, 1, want=False)
+        ctx.barrier_energy(dHat, KAPPA, want=False)
+        ctx.elastic_grad_hess(DT2, 1, 1, 1, None, None)   # zeroes the value array first (LinSysSolver::setZero)
+        ctx.barrier_gradient(dHat, KAPPA, None)
+        ctx.barrier_hessian(dHat, KAPPA, 1, None)
+        ctx.allreduce_grad_hess(1, 0)  # one NCCL sum of the gradient; the Hessian is complete per row owner (no-op on a single rank)
+        ctx.step_bound_set(1.0)
+        ctx.inversion_step(None, 0.2, None)
+        ctx.ccd_partial(None, TI_TOL, err_vf, err_ee, None)
+        ctx.hash_build_swept(None, None, hvox)
+        ctx.ccd_full(TI_TOL, err_vf, err_ee, None)
 
     def step_device():
-        ctx.constraint_set(dHat, 1, fetch=False)
-        ctx.elastic_energy(DT2, 1, want=False)
-        ctx.barrier_energy(dHat, KAPPA)
-        ctx.csr_set_zero()
-        ctx.elastic_grad_hess(DT2, 1, 1, 1, None, None)
-        ctx.barrier_gradient(dHat, KAPPA, None)
-        ctx.barrier_hessian(dHat, KAPPA, 1, None)
-        ctx.allreduce_grad_hess(1, 1)  # one NCCL sum over [gradient, CSR values] (no-op on a single rank)
-        a = ctx.inversion_step(None, 0.2, 1.0)
-        a = ctx.ccd_partial(None, TI_TOL, err_vf, err_ee, a)
-        a = ctx.hash_build_swept(None, a, hvox)
-        a, nc = ctx.ccd_full(TI_TOL, err_vf, err_ee, a)
-        stats["alpha"], stats["ccd_candidates"] = a, nc
-        stats["ccd_full_stats"] = ctx.ccd_stats() + ctx.ccd_stats_ex()
-        stats["ccd_warp_pass_cycles_longest_total"] = ctx.ccd_stats_timing()
+        enqueue_iteration()
+        it = ctx.fetch_iteration()  # the single synchronisation of the iteration (+ the deferred cross-rank scalars)
+        stats["it"] = it
 
     def step_e2e():
-        ctx.set_state(hV.array)
-        ctx.constraint_set(dHat, 1, fetch=False)
-        ctx.elastic_energy(DT2, 1, want=True)
-        ctx.barrier_energy(dHat, KAPPA)
-        ctx.csr_set_zero()
-        ctx.elastic_grad_hess(DT2, 1, 1, 1, None, None)
-        ctx.barrier_gradient(dHat, KAPPA, None)
-        ctx.barrier_hessian(dHat, KAPPA, 1, None)
-        ctx.allreduce_grad_hess(1, 1)
-        ctx.download_into(L.BUF_GRADIENT, hg.array)
-        ctx.download_into(L.BUF_CSR_VALUES, ha.array)
-        a = ctx.inversion_step(hp.array, 0.2, 1.0)
-        a = ctx.ccd_partial(None, TI_TOL, err_vf, err_ee, a)
-        a = ctx.hash_build_swept(None, a, hvox)
-        a, nc = ctx.ccd_full(TI_TOL, err_vf, err_ee, a)
+        ctx.set_state(hV.array)        # H2D: positions
+        ctx.set_search_dir(hp.array)   # H2D: search direction
+        enqueue_iteration()
+        it = ctx.fetch_iteration()
+        ctx.download_into(L.BUF_GRADIENT, hg.array)                      # D2H: gradient
+        ctx.download_range_into(L.BUF_CSR_VALUES, own0, ha.array[own0:own1])  # D2H: the CSR values of the rows this rank owns
+        stats["it_e2e"] = it
+
+    # ---- parity of exactly this mode at exactly this size, inside the run (rank 0 asserts; every rank takes part in the collectives)
+    parity = None
+    if not args.no_parity:
+        step_device()
+        it = stats["it"]
+        g_dev = ctx.download(L.BUF_GRADIENT, 3 * m.nV)
+        ctx.allreduce_grad_hess(0, 1)  # parity only: complete the matrix on every rank so that rank 0 can compare all of it
+        a_dev = ctx.download(L.BUF_CSR_VALUES, nnz)
+        if rank == 0:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle as orc
+            import struct
+            nth = os.cpu_count() or 1
+            o, s_ = orc.Elastic(m), orc.Surf(m)
+            mm_r, pa_r, pe_r, cand_r = s_.constraint_set_hashed(dHat, hvox, nth)
+            E_ref = o.energy(DT2, nth)[0] + s_.barrier_energy(mm_r, pa_r, pe_r, dHat, KAPPA)[0]
+            g_ref = s_.barrier_gradient(mm_r, pa_r, pe_r, dHat, KAPPA, g=o.gradient(DT2, 1, nth))
+            a_ref = o.hessian_csr(DT2, ia, ja, 1, 1, 1, nthreads=nth)
+            diag = np.asarray(ia[:-1:1], dtype=np.int64)[: 3 * m.nV] - 1
+            a_ref[diag] += np.repeat(m.mass, 3)
+            a_ref = s_.barrier_hessian_csr(mm_r, pa_r, pe_r, dHat, KAPPA, ia, ja, 1, 1, a=a_ref, nthreads=nth)
+            al_r, _ = o.inversion_step(info["p"], 0.2, 1.0)
+            al_p, _ = orc.ccd_partial(s_, info["p"], cand_r, TI_TOL, err_vf, err_ee, al_r, nth)
+            al_f, _, npairs = orc.ccd_full_hashed(s_, info["p"], al_p, hvox, TI_TOL, err_vf, err_ee, nth)
+            rel = lambda x, y: float(np.linalg.norm(x - y) / np.linalg.norm(y))
+            bits = lambda x: struct.pack("<d", float(x))
+            parity = {"energy_rel": abs(it.energy_elastic + it.energy_barrier - E_ref) / abs(E_ref), "gradient_rel": rel(g_dev, g_ref), "csr_rel": rel(a_dev, a_ref),
+                      "alpha_partial_bits_equal": bits(it.alpha_partial_ccd) == bits(al_p), "alpha_bits_equal": bits(it.alpha) == bits(al_f),
+                      "alpha": it.alpha, "alpha_oracle": al_f, "ti_warnings": int(it.ti_warnings), "ranks": world}
+            ok = (parity["energy_rel"] <= 1e-10 and parity["gradient_rel"] <= 1e-10 and parity["csr_rel"] <= 1e-9 and parity["alpha_partial_bits_equal"]
+                  and parity["alpha_bits_equal"] and parity["ti_warnings"] == 0)
+            parity["ok"] = bool(ok)
+            print("PARITY", json.dumps(parity), file=sys.stderr)
+            assert ok, parity
 
     # ---- device-resident timing --------------------------------------------------------------------
     for _ in range(args.warmup):
@@ -305,6 +342,8 @@ def main():
     prof = ctx.profile_read()
     ctx.profile(0)
     ms_step = ms_total / args.steps
+    it = stats["it"]
+    ccd_stats = ctx.ccd_stats() + ctx.ccd_stats_ex() + ctx.ccd_stats_timing()
 
     # ---- end-to-end timing (host buffers through the C ABI) -----------------------------------------
     for _ in range(2):
@@ -333,37 +372,53 @@ def main():
         peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         tet_ms, tet_n = prof.get("elastic_tet", (0.0, 1))
-        local_tets = m.nT // world
+        local_tets = part["n_assembled_tets"]  # tets this rank assembles (its share plus the boundary tets of its rows)
         per_launch_s = tet_ms / max(tet_n, 1) * 1e-3
         achieved = ALG_BYTES_PER_TET * local_tets / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
-        rf_ms, rf_n = prof.get("ccd_root_filter", (0.0, 0))
-        ccd_roof = None
-        if rf_n:
-            # two launches per step (partial + full CCD); bytes = candidates both launches looked at
-            cand_per_step = float(n_cand) / world + float(stats.get("ccd_candidates", 0)) / world
-            ach = ALG_BYTES_PER_CCD_CANDIDATE * cand_per_step / (rf_ms / args.steps * 1e-3) / 1e9
-            ccd_roof = {"bound": "hbm", "kernel": "k_ti_stage1 (root-box inclusion over every CCD candidate)", "achieved": ach, "peak": peak_gbs,
-                        "unit": "GB/s", "frac": ach / peak_gbs, "traffic": None, "algorithmic_bytes_per_candidate": ALG_BYTES_PER_CCD_CANDIDATE,
-                        "kernel_ms_per_step": rf_ms / args.steps,
-                        "note": "vertex data is L2-resident (ncu: 4.6 MB DRAM for 42.8k candidates), so DRAM is not what bounds this kernel"}
+        per_step = lambda k: prof.get(k, (0.0, 0))[0] / args.steps
+        # Hessian-to-sink path as the CSR sees it: per-tet kernel + gradient gather + CSR assembly (incl. mass/DBC diagonal)
+        h2s_ms = per_step("elastic_tet") + per_step("gather_gradient") + per_step("assemble_csr")
+        h2s = ALG_BYTES_PER_TET * local_tets / (h2s_ms * 1e-3) / 1e9 if h2s_ms > 0 else 0.0
+        # whole CCD narrow phase (root filter + thread pass + warp pass, both the partial and the full CCD of the step)
+        n_full = int(it.n_full_ccd_candidates)
+        cand_per_step = float(n_cand) / world + float(n_full)
+        nar_ms = per_step("ccd_narrow")
+        nar = ALG_BYTES_PER_CCD_CANDIDATE * cand_per_step / (nar_ms * 1e-3) / 1e9 if nar_ms > 0 else 0.0
         line = {
             "metric": "newton_iteration_ms_assembly_ccd", "value": ms_step, "unit": "ms", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"synthetic 1M-tet ball pile [{info['workload']}] ({m.nT} tets, {m.nV} verts, {len(m.SVI)} surface verts), NeoHookean, dt=0.025, "
                                    f"dHat=(1e-3 bboxDiag)^2, {n_active} active pairs + {n_para} mollified, {n_cand} partial-CCD candidates, "
-                                   f"{stats.get('ccd_candidates', 0)} full-CCD candidates, TI tol 1e-6",
-                       "stages": STAGES_RUN, "csr_nnz": int(nnz), "step_bound_alpha": stats.get("alpha"),
-                       "full_ccd_candidates_survivors_warnings_deferred_boxesThreadPass_boxesWarpPass": stats.get("ccd_full_stats"), "full_ccd_warp_pass_sm_cycles_longest_pair_and_total": stats.get("ccd_warp_pass_cycles_longest_total"), "l2": "working set (78 doubles/tet = %.0f MB + CSR %.0f MB) exceeds the 126 MB L2" % (m.nT * 624 / 1e6, nnz * 8 / 1e6),
-                       "partition": f"tets block-partitioned over {world} rank(s); NCCL sum-allreduce of [gradient, CSR values], min-allreduce of the step"},
+                                   f"{n_full} full-CCD candidates on rank 0, TI tol 1e-6",
+                       "stages": STAGES_RUN, "csr_nnz": int(nnz), "step_bound_alpha": it.alpha,
+                       "alpha_after_inversion_partial_swept_full": [it.alpha_inversion, it.alpha_partial_ccd, it.alpha_swept_grid, it.alpha_full_ccd],
+                       "energy_elastic_barrier": [it.energy_elastic, it.energy_barrier],
+                       "full_ccd_candidates_survivors_warnings_deferred_boxesThreadPass_boxesWarpPass_longestPairCycles_totalCycles": list(ccd_stats),
+                       "l2": "working set (78 doubles/tet = %.0f MB + CSR %.0f MB) exceeds the 126 MB L2" % (m.nT * 624 / 1e6, nnz * 8 / 1e6),
+                       "mode": "device-resident iteration: every stage enqueued with NULL outputs, one ipcgpu_fetch_iteration per step; "
+                               "canonical_order=0, contact_partition=1",
+                       "partition": (f"{world} rank(s): tets block-partitioned (energy, inversion); gradient/Hessian by row owner (rank 0 assembles {local_tets} tets, "
+                                     f"CSR values [{own0},{own1}) of {nnz}); queries of both broad phases partitioned; NCCL: allgather of the pair lists, "
+                                     "sum-allreduce of the gradient, min-allreduce of each step bound; no Hessian reduction")},
             "stage_ms": {k: v[0] / args.steps for k, v in prof.items()},
+            "sum_stage_ms": sum(v[0] for k, v in prof.items() if k != "ccd_root_filter") / args.steps,
             "roofline": {"bound": "hbm", "kernel": "k_elastic_grad_hess<NH,g,H>", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                          "frac": achieved / peak_gbs, "traffic": NCU_DRAM_BYTES_PER_TET * local_tets, "peak_source": peak_src,
                          "algorithmic_bytes_per_tet": ALG_BYTES_PER_TET, "algorithmic_bytes_per_launch": ALG_BYTES_PER_TET * local_tets,
-                         "traffic_source": "ncu --set full, profiles/r01b_prof_k_elastic_grad_hess.summary.csv (bytes per tet x tets of this rank)",
-                         "kernel_ms": tet_ms / max(tet_n, 1)},
-            "roofline_ccd": ccd_roof,
-            "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(2 * 3 * m.nV * 8), "d2h_bytes_per_step": int((3 * m.nV + nnz) * 8 + 16)},
+                         "traffic_source": NCU_TRAFFIC_SOURCE, "kernel_ms": tet_ms / max(tet_n, 1), "ncu": NCU_TET},
+            "roofline_hessian_to_csr": {"bound": "hbm", "kernel": "k_elastic_grad_hess + k_gather_gradient + k_assemble_csr + k_diag_mass_dbc (what the CSR sink sees)",
+                                        "achieved": h2s, "peak": peak_gbs, "unit": "GB/s", "frac": h2s / peak_gbs, "traffic": None,
+                                        "algorithmic_bytes_per_tet": ALG_BYTES_PER_TET, "path_ms_per_step": h2s_ms},
+            "roofline_ccd_narrow": {"bound": "hbm", "kernel": "k_ti_stage1 + k_ti_stage15 + k_ti_stage2 (whole Tight-Inclusion narrow phase, partial + full CCD)",
+                                    "achieved": nar, "peak": peak_gbs, "unit": "GB/s", "frac": nar / peak_gbs, "traffic": None,
+                                    "algorithmic_bytes_per_candidate": ALG_BYTES_PER_CCD_CANDIDATE, "candidates_per_step": cand_per_step, "path_ms_per_step": nar_ms,
+                                    "root_filter_ms_per_step": per_step("ccd_root_filter"), "ncu": NCU_TI,
+                                    "note": "latency/ALU-bound interval search on the surviving pairs (SURVEY 8d): the vertex data is L2-resident and the "
+                                            "critical path is the deepest pair, so the HBM fraction only says how far from a pure streaming pass the stage is"},
+            "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(2 * 3 * m.nV * 8), "d2h_bytes_per_step": int((3 * m.nV + (own1 - own0)) * 8 + 120),
+                    "note": "host clock around: H2D of x and p, the whole iteration, D2H of the gradient and of the CSR values of the rows this rank owns (rank 0's byte counts)"},
+            "parity": parity,
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -18,9 +18,16 @@
  *       CSR        : upper-triangular ia/ja/a of LinSysSolver                    (LinSysSolver.hpp:34-37)
  *  - Every function returns 0 on success, otherwise an IPCGPU_ERR_* code; nothing here calls exit().
  *    ipcgpu_last_error() gives a human-readable message for the last failure on that context.
- *  - Host output pointers may be NULL: the result then stays device-resident (no D2H copy) and can be
- *    consumed by a later call or fetched with ipcgpu_download().  This is how a device-side solver
- *    (cuDSS) or the benchmark's HBM-resident mode avoids PCIe traffic.
+ *  - Host output pointers may be NULL: the result then stays device-resident (no D2H copy, NO host synchronisation) and
+ *    is consumed by the later calls on the device.  With every output NULL a whole Newton iteration -- constraint set, E, g, H,
+ *    inversion filter, partial CCD, swept grid, full CCD, and with several ranks the NCCL reductions between them -- is ONE
+ *    uninterrupted stream; ipcgpu_fetch_iteration() then reads all scalars back with a single synchronisation.  In particular
+ *    the step bound travels on the device: alpha_inout == NULL means "the device-resident step" (start it with
+ *    ipcgpu_step_bound_set).  Host INPUT arrays handed to such calls must stay untouched until the next fetch / sync.
+ *  - Several ranks: tets are block-partitioned for the energy and the inversion filter; the gradient/Hessian assembly is by ROW
+ *    OWNER -- a rank owns a contiguous vertex range, assembles every tet and every contact pair that touches it and holds the
+ *    complete CSR rows of that range (ipcgpu_partition_info), so the Hessian needs no cross-rank reduction; the gradient is one
+ *    sum-allreduce of 3 nV doubles, every step bound one min-allreduce of a uint64.
  */
 #ifndef IPCGPU_H
 #define IPCGPU_H
@@ -70,6 +77,27 @@ uint64_t ipcgpu_launch_count(const ipcgpu_ctx* ctx);
 /* 128-byte ncclUniqueId created on rank 0 and broadcast by the host (torch.distributed / MPI / file). */
 int ipcgpu_comm_unique_id(void* id128);
 int ipcgpu_comm_init(ipcgpu_ctx* ctx, int rank, int nranks, const void* id128);
+/* what this rank owns: tets [tet_begin, tet_end) (energy, inversion filter), the rows of vertices [row_vertex_begin,
+ * row_vertex_end) = CSR values [value_begin, value_end) (0-based offsets into `a`; valid after ipcgpu_set_csr), and how many
+ * tets it assembles for them (boundary tets are assembled by both neighbours).  Any pointer may be NULL. */
+int ipcgpu_partition_info(ipcgpu_ctx* ctx, int* rank, int* nranks, int* tet_begin, int* tet_end, int* row_vertex_begin, int* row_vertex_end,
+    int64_t* value_begin, int64_t* value_end, int* n_assembled_tets);
+
+/* ---- one read-back per Newton iteration -------------------------------------------------------------------- */
+typedef struct ipcgpu_iteration {
+    double energy_elastic, energy_barrier;   /* last ipcgpu_elastic_energy / ipcgpu_barrier_energy (summed over ranks) */
+    double alpha_inversion, alpha_partial_ccd, alpha_swept_grid, alpha_full_ccd; /* the step after each bound of Optimizer.cpp:1884-2040 */
+    double alpha;                            /* the device-resident step now */
+    int n_active, n_mollified, n_candidates; /* sizes of the last constraint set (this rank's lists) */
+    int status;                              /* IPCGPU_OK or the first deferred error (d <= 0, capacity, pattern) -- same on every rank */
+    uint64_t n_full_ccd_candidates;          /* candidates of the last full CCD (this rank) */
+    uint64_t ti_warnings;                    /* conservative early-outs of the Tight-Inclusion searches since the last fetch (should be 0) */
+} ipcgpu_iteration;
+/* Synchronises once, completes the deferred cross-rank scalars (collective: every rank must call it), fills `out`, clears the
+ * deferred error flags and returns out->status. */
+int ipcgpu_fetch_iteration(ipcgpu_ctx* ctx, ipcgpu_iteration* out);
+/* start value of the device-resident step bound (Optimizer.cpp:1884: alpha = 1) */
+int ipcgpu_step_bound_set(ipcgpu_ctx* ctx, double alpha);
 
 /* ---- scene (once per scene; replaces what Mesh<3> precomputes, Mesh.cpp:415-527, :661-671) ------- */
 int ipcgpu_set_mesh(ipcgpu_ctx* ctx, int nV, int nT,
@@ -106,7 +134,7 @@ int ipcgpu_elastic_hessian(ipcgpu_ctx* ctx, double coef, int redoSVD, int projec
  * on top.  Results stay on the device when the pointers are NULL. */
 int ipcgpu_elastic_grad_hess(ipcgpu_ctx* ctx, double coef, int projectSPD, int projectDBC, int add_mass,
     double* g, double* a);
-/* Energy::filterStepSize (Energy.cpp:565-581) */
+/* Energy::filterStepSize (Energy.cpp:565-581); alpha_inout == NULL: the device-resident step */
 int ipcgpu_inversion_step(ipcgpu_ctx* ctx, const double* p_interleaved, double slack, double* alpha_inout);
 
 /* ---- contact plug-in: SelfCollisionHandler<3> statics (SelfCollisionHandler.hpp:23-232) ------------------- */
@@ -119,6 +147,8 @@ int ipcgpu_set_pair_capacity(ipcgpu_ctx* ctx, int capacity);
  * SpatialHash::build/query* (SpatialHash.hpp:46-229, 375-421) done on the device. The sets stay on the device (they feed the
  * barrier_* calls and the partial CCD); sizes are returned.  Output order is canonical: every list sorted lexicographically. */
 int ipcgpu_constraint_set(ipcgpu_ctx* ctx, double dHat, int getPTEE, int* nC, int* nPara, int* nCand);
+/* sizes of the last set (synchronises if it was built with NULL size pointers) */
+int ipcgpu_constraint_set_sizes(ipcgpu_ctx* ctx, int* nC, int* nPara, int* nCand);
 /* enable=1 (default): the lists are returned in canonical (lexicographic) order, so two runs give bitwise identical sets and sums.
  * enable=0: the order is whatever the atomic appends produced -- the same freedom the reference has (its order depends on
  * unordered_set iteration and TBB scheduling); saves the sorting passes when the sets are only consumed on the device. */
@@ -144,11 +174,13 @@ int ipcgpu_barrier_hessian(ipcgpu_ctx* ctx, double dHat, double kappa, int proje
 /* ---- CCD step bound (Tight-Inclusion), Optimizer.cpp:1884-2040 ----------------------------------------------------- */
 /* capacity (pairs) of the device CCD candidate list; default 2^23 */
 int ipcgpu_set_ccd_capacity(ipcgpu_ctx* ctx, uint64_t capacity);
-/* scene-wide Tight-Inclusion numerical error (computeTightInclusionError, CCDUtils.cpp:55-87): world bbox of V (and V+p when p is
- * given) inflated to centre +- 10*radius*(1,1,1)/sqrt(3), then inclusion_ccd::get_numerical_error(..., use_ms = true). Host-only. */
+/* scene-wide Tight-Inclusion numerical error (computeTightInclusionError, CCDUtils.cpp:55-87): world bbox of V inflated to centre +-
+ * 10*radius*(1,1,1)/sqrt(3) (computeConservativeWorldBBox, :21-52, uses mesh.V only: pass p = NULL for the reference's value; a non-NULL
+ * p widens the box by V+p, an extension), then inclusion_ccd::get_numerical_error(..., use_ms = true). Host-only. */
 int ipcgpu_ti_error(const double* V_soa, int nV, const double* p_interleaved /* may be NULL */, double err_vf[3], double err_ee[3]);
 /* largestFeasibleStepSize_TightInclusion (SelfCollisionHandler.cpp:690-866) over the candidate list cs_PTEE of the last
- * ipcgpu_constraint_set(getPTEE=1).  alpha_inout: step on entry (max_t of every pair) -> min(alpha, earliest time of impact). */
+ * ipcgpu_constraint_set(getPTEE=1).  alpha_inout: step on entry (max_t of every pair) -> min(alpha, earliest time of impact);
+ * NULL = the device-resident step (no synchronisation). */
 int ipcgpu_ccd_partial_ti(ipcgpu_ctx* ctx, const double* p_interleaved /* NULL = last uploaded */, double tolerance,
     const double err_vf[3], const double err_ee[3], double* alpha_inout);
 /* SpatialHash::build(mesh, searchDir, curMaxStepSize, voxelSize) (SpatialHash.hpp:589-750): alpha_inout is scaled down when
@@ -163,12 +195,20 @@ int ipcgpu_ccd_stats(ipcgpu_ctx* ctx, uint64_t* candidates, uint64_t* survivors,
 int ipcgpu_ccd_stats_ex(ipcgpu_ctx* ctx, uint64_t* deferred, uint64_t* boxes_thread_pass, uint64_t* boxes_warp_pass);
 /* critical path of the warp-level pass: SM cycles spent on its longest single pair, and summed over all its pairs */
 int ipcgpu_ccd_stats_timing(ipcgpu_ctx* ctx, uint64_t* longest_pair_cycles, uint64_t* total_pair_cycles);
+/* TEST HOOK.  Pairs prune their interval search against the earliest impact any pair has reported so far -- which pair reports first
+ * depends on scheduling.  toi >= 0 makes every later narrow phase start as if some pair had already reported `toi` (the step on entry,
+ * i.e. max_t of every pair, is unchanged; the result is min(toi, the pairs' impacts)); toi < 0 switches the hook off. */
+int ipcgpu_ccd_debug_seed_bound(ipcgpu_ctx* ctx, double toi);
 
 /* LinSysSolver::setZero (LinSysSolver.hpp:348) on the device-resident value array */
 int ipcgpu_csr_set_zero(ipcgpu_ctx* ctx);
-/* cross-rank reductions over NVLink (no-ops on a single rank): sum of [gradient, CSR values], min of step */
+/* cross-rank completion over NVLink (no-op on a single rank).  with_gradient: sum-allreduce of the gradient (needed every iteration).
+ * with_hessian: only for a caller that wants the WHOLE matrix on every rank -- each rank's own rows are complete without it (row-owner
+ * assembly); it ships the other ranks' rows (a sum over arrays that are zero outside the owned rows). */
 int ipcgpu_allreduce_grad_hess(ipcgpu_ctx* ctx, int with_gradient, int with_hessian);
 int ipcgpu_download(ipcgpu_ctx* ctx, int which, double* dst, uint64_t count);
+/* count entries starting at `offset` (e.g. the CSR values of the rows this rank owns: ipcgpu_partition_info) */
+int ipcgpu_download_range(ipcgpu_ctx* ctx, int which, uint64_t offset, uint64_t count, double* dst);
 /* raw device pointer of a result buffer (for a device-side linear solver) */
 void* ipcgpu_device_ptr(ipcgpu_ctx* ctx, int which);
 

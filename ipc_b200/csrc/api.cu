@@ -1,4 +1,9 @@
 // api.cu -- extern "C" entry points declared in include/ipcgpu.h
+//
+// Execution model.  Every stage enqueues its kernels (and, with several ranks, its NCCL reductions) on the context's stream and leaves
+// its scalar results in the device-resident iteration state (kernels.h: IterState).  An entry point synchronises with the host only if
+// the caller hands it a host output pointer; with NULL outputs a whole Newton iteration is one uninterrupted stream, read back once by
+// ipcgpu_fetch_iteration.  The synchronous forms are the same code followed by that read-back.
 #include "../../include/ipcgpu.h"
 #include "context.h"
 #include <algorithm>
@@ -38,6 +43,7 @@ struct Nccl {
     int (*GetUniqueId)(void*) = nullptr;
     int (*CommInitRank)(void**, int, /* ncclUniqueId by value: 128 bytes */ Id128, int) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
     int (*CommDestroy)(void*) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
@@ -57,63 +63,135 @@ bool nccl_load(std::string& err)
     g_nccl.GetUniqueId = (int (*)(void*))dlsym(g_nccl.h, "ncclGetUniqueId");
     g_nccl.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(g_nccl.h, "ncclCommInitRank");
     g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.h, "ncclAllReduce");
+    g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(g_nccl.h, "ncclAllGather");
     g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.h, "ncclCommDestroy");
     g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.h, "ncclGetErrorString");
-    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce) {
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.AllGather) {
         err = "NCCL symbols missing";
         return false;
     }
     return true;
 }
+constexpr int kNcclInt32 = 2;   // ncclInt32
 constexpr int kNcclFloat64 = 8; // ncclDouble
 constexpr int kNcclUint64 = 5;  // ncclUint64
-constexpr int kNcclSum = 0, kNcclMin = 3;
+constexpr int kNcclSum = 0, kNcclMax = 2, kNcclMin = 3;
 } // namespace
 
+// min over ranks of a device-resident uint64 (the order-preserving image of a step), in stream; no-op on one rank
+int nccl_min_u64(ipcgpu_ctx* ctx, unsigned long long* word)
+{
+    if (ctx->nranks <= 1) return IPCGPU_OK;
+    cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_ALLREDUCE);
+    int r = g_nccl.AllReduce(word, word, 1, kNcclUint64, kNcclMin, ctx->nccl_comm, ctx->stream);
+    ctx->prof_end(pe);
+    REQUIRE(r == 0, IPCGPU_ERR_NCCL, "ncclAllReduce(min step) failed");
+    return IPCGPU_OK;
+}
+
+// one D2H copy of the iteration state + stream synchronisation
+int fetch_iter_state(ipcgpu_ctx* ctx)
+{
+    CK(cudaMemcpyAsync(ctx->h_iter, ctx->iter.p, sizeof(IterState), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return IPCGPU_OK;
+}
+static int clear_flag(ipcgpu_ctx* ctx, int idx)
+{
+    CK(cudaMemsetAsync(&ctx->iter.p->flags[idx], 0, sizeof(int), ctx->stream));
+    return IPCGPU_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------
-// map building (host, once per mesh/partition): vertex->incident (tet,local) lists and Hessian slots
+// map building (host, once per mesh/partition): vertex->incident (tet,local) lists and Hessian slots.
+// Partition (nranks > 1): rank r owns the rows of the vertex range [v_begin, v_end) -- chosen so that the incident-tet counts
+// balance -- and assembles EVERY tet that touches one of them (tets on a range boundary are computed by both neighbours), so that
+// each rank's part of the CSR is complete and the Hessian needs no cross-rank reduction.
 // ---------------------------------------------------------------------------------------------------
 static int build_maps(ipcgpu_ctx* ctx)
 {
     const int nT = ctx->nT, nV = ctx->nV;
-    const int tb = ctx->t_begin, te = ctx->t_end, nL = te - tb;
     const std::vector<int>& T = ctx->h_T;
-    // incidence: counting sort by vertex; entries 4*localTet+loc ascending
+    ctx->t_begin = (int)((int64_t)nT * ctx->rank / ctx->nranks);
+    ctx->t_end = (int)((int64_t)nT * (ctx->rank + 1) / ctx->nranks);
+    // vertex ranges balanced by incident-tet count
+    std::vector<int64_t> cum(nV + 1, 0);
+    for (size_t i = 0; i < (size_t)4 * nT; ++i) ++cum[T[i] + 1];
+    for (int v = 0; v < nV; ++v) cum[v + 1] += cum[v];
+    auto boundary = [&](int r) -> int {
+        if (r <= 0) return 0;
+        if (r >= ctx->nranks) return nV;
+        const int64_t target = cum[nV] * r / ctx->nranks;
+        return (int)(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin());
+    };
+    const int vb = std::min(boundary(ctx->rank), nV), ve = std::max(vb, std::min(boundary(ctx->rank + 1), nV));
+    ctx->v_begin = vb;
+    ctx->v_end = ve;
+    // tets touching the owned rows, ascending
+    std::vector<int> list;
+    if (ctx->nranks == 1) {
+        list.resize(nT);
+        std::iota(list.begin(), list.end(), 0);
+    }
+    else {
+        list.reserve((size_t)(nT / ctx->nranks) + 1024);
+        for (int t = 0; t < nT; ++t) {
+            bool touch = false;
+            for (int k = 0; k < 4; ++k) {
+                const int v = T[(size_t)k * nT + t];
+                touch = touch || (v >= vb && v < ve);
+            }
+            if (touch) list.push_back(t);
+        }
+    }
+    const int nL = (int)list.size();
+    ctx->n_list = nL;
+    if (list.empty()) list.push_back(0); // keep the upload non-empty
+    REQUIRE(ctx->tet_list.upload(list.data(), list.size(), ctx->stream), IPCGPU_ERR_CUDA, "upload of the tet list failed");
+    // incidence of the OWNED vertices: counting sort by vertex; entries 4*localTet+loc ascending
     std::vector<int> ptr(nV + 1, 0);
-    for (int k = 0; k < 4; ++k)
-        for (int t = tb; t < te; ++t) ++ptr[T[(size_t)k * nT + t] + 1];
+    for (int l = 0; l < nL; ++l)
+        for (int k = 0; k < 4; ++k) {
+            const int v = T[(size_t)k * nT + list[l]];
+            if (v >= vb && v < ve) ++ptr[v + 1];
+        }
     for (int v = 0; v < nV; ++v) ptr[v + 1] += ptr[v];
-    std::vector<int> inc((size_t)4 * nL), cur(ptr.begin(), ptr.end() - 1);
-    for (int t = tb; t < te; ++t)
-        for (int k = 0; k < 4; ++k) inc[cur[T[(size_t)k * nT + t]]++] = 4 * (t - tb) + k;
+    std::vector<int> inc((size_t)std::max(ptr[nV], 1)), cur(ptr.begin(), ptr.end() - 1);
+    for (int l = 0; l < nL; ++l)
+        for (int k = 0; k < 4; ++k) {
+            const int v = T[(size_t)k * nT + list[l]];
+            if (v >= vb && v < ve) inc[cur[v]++] = 4 * l + k;
+        }
     if (!ctx->inc_ptr.upload(ptr.data(), ptr.size(), ctx->stream) || !ctx->inc.upload(inc.data(), inc.size(), ctx->stream)) {
         ctx->err = "upload of incidence map failed";
         return IPCGPU_ERR_CUDA;
     }
-    // slots: (v<=u) pairs; contributions (key, src) sorted by key then tet
+    // slots: (v<=u) pairs whose ROW vertex v is owned; contributions (key, src) sorted by key then tet
     REQUIRE(((uint64_t)nL + 64ull) * 78ull < 0xffffffffull, IPCGPU_ERR_CAPACITY, "local tet count too large for 32-bit block offsets");
     struct KS {
         uint64_t key;
         unsigned src;
         unsigned tet;
     };
-    std::vector<KS> ks((size_t)10 * nL);
+    std::vector<KS> ks;
+    ks.reserve((size_t)10 * nL);
     static const int pa[6] = { 0, 0, 0, 1, 1, 2 }, pb[6] = { 1, 2, 3, 2, 3, 3 };
-    for (int t = tb; t < te; ++t) {
+    for (int l = 0; l < nL; ++l) {
+        const int t = list[l];
         int v[4];
         for (int k = 0; k < 4; ++k) v[k] = T[(size_t)k * nT + t];
-        // tile-major block addresses (elastic.cu): (t/64)*64*78 + o*64 + (t%64)*len
-        const unsigned tl = (unsigned)(t - tb), tile_base = (tl / 64u) * (64u * 78u), tin = tl % 64u;
-        KS* o = &ks[(size_t)10 * (t - tb)];
-        for (int a = 0; a < 4; ++a) o[a] = { ((uint64_t)v[a] << 32) | (uint32_t)v[a], tile_base + 6u * a * 64u + tin * 6u, tl };
+        // tile-major block addresses (elastic.cu): (l/64)*64*78 + o*64 + (l%64)*len
+        const unsigned tl = (unsigned)l, tile_base = (tl / 64u) * (64u * 78u), tin = tl % 64u;
+        for (int a = 0; a < 4; ++a)
+            if (v[a] >= vb && v[a] < ve) ks.push_back({ ((uint64_t)v[a] << 32) | (uint32_t)v[a], tile_base + 6u * a * 64u + tin * 6u, tl });
         for (int q = 0; q < 6; ++q) {
-            int lo = std::min(v[pa[q]], v[pb[q]]), hi = std::max(v[pa[q]], v[pb[q]]);
-            o[4 + q] = { ((uint64_t)lo << 32) | (uint32_t)hi, tile_base + (24u + 9u * q) * 64u + tin * 9u, tl };
+            const int lo = std::min(v[pa[q]], v[pb[q]]), hi = std::max(v[pa[q]], v[pb[q]]);
+            if (lo >= vb && lo < ve) ks.push_back({ ((uint64_t)lo << 32) | (uint32_t)hi, tile_base + (24u + 9u * q) * 64u + tin * 9u, tl });
         }
     }
     std::sort(ks.begin(), ks.end(), [](const KS& a, const KS& b) { return a.key < b.key || (a.key == b.key && (a.tet < b.tet || (a.tet == b.tet && a.src < b.src))); });
     std::vector<int> sv, su, cptr;
-    std::vector<unsigned> csrc(ks.size());
+    std::vector<unsigned> csrc(std::max<size_t>(ks.size(), 1));
     for (size_t i = 0; i < ks.size(); ++i) {
         if (i == 0 || ks[i].key != ks[i - 1].key) {
             sv.push_back((int)(ks[i].key >> 32));
@@ -124,17 +202,26 @@ static int build_maps(ipcgpu_ctx* ctx)
     }
     cptr.push_back((int)ks.size());
     ctx->nSlots = (int)sv.size();
+    if (sv.empty()) { sv.push_back(0); su.push_back(0); } // keep the uploads non-empty
     bool ok = ctx->slot_v.upload(sv.data(), sv.size(), ctx->stream) && ctx->slot_u.upload(su.data(), su.size(), ctx->stream)
         && ctx->con_ptr.upload(cptr.data(), cptr.size(), ctx->stream) && ctx->con_src.upload(csrc.data(), csrc.size(), ctx->stream)
         && ctx->slot_off.reserve((size_t)3 * std::max(1, ctx->nSlots));
     REQUIRE(ok, IPCGPU_ERR_CUDA, "upload of Hessian scatter map failed");
     ALLOC(ctx->gcont, (size_t)12 * std::max(1, nL));
     ALLOC(ctx->hblk, (size_t)78 * 64 * ((size_t)(std::max(1, nL) + 63) / 64));
-    ALLOC(ctx->partials, (size_t)std::max(1, elastic_energy_blocks(nL)) + 8);
+    ALLOC(ctx->partials, (size_t)std::max(1, elastic_energy_blocks(ctx->t_end - ctx->t_begin)) + 8);
     CK(cudaStreamSynchronize(ctx->stream)); // host vectors go out of scope
     ctx->maps_ready = true;
     ctx->offsets_ready = false;
     return IPCGPU_OK;
+}
+
+static void owned_value_range(ipcgpu_ctx* ctx)
+{
+    // CSR value range of the owned rows [3 v_begin, 3 v_end)
+    if (ctx->h_ia.empty()) return;
+    ctx->a_begin = (long long)ctx->h_ia[(size_t)3 * ctx->v_begin] - ctx->index_base;
+    ctx->a_end = (long long)ctx->h_ia[(size_t)3 * ctx->v_end] - ctx->index_base;
 }
 
 static int ensure_offsets(ipcgpu_ctx* ctx)
@@ -156,10 +243,41 @@ static int ensure_offsets(ipcgpu_ctx* ctx)
 // C++ linkage helpers implemented in constraint.cu / ccd.cu
 int contact_alloc(ipcgpu_ctx* ctx);
 int contact_constraint_set(ipcgpu_ctx* ctx, double dHat, int wantCand, int* nC, int* nPara, int* nCand);
+int contact_sync_counts(ipcgpu_ctx* ctx);
+void contact_pack_lists(ipcgpu_ctx* ctx);
+void contact_unpack_lists(ipcgpu_ctx* ctx);
 int ccd_alloc(ipcgpu_ctx* ctx);
-int ccd_narrow(ipcgpu_ctx* ctx, const int2* cand, unsigned long long nCand, double tol, const double* err_vf, const double* err_ee, double* alpha_inout);
-int ccd_build_swept(ipcgpu_ctx* ctx, const double* p_host, double* alpha_inout, double h);
-int ccd_full(ipcgpu_ctx* ctx, double tol, const double* err_vf, const double* err_ee, double* alpha_inout, unsigned long long* nCandOut);
+int ccd_narrow(ipcgpu_ctx* ctx, const int2* cand, const int* n32, const unsigned long long* n64, unsigned long long cap, int share, double tol, const double* err_vf,
+    const double* err_ee, int stage, const int* overflow);
+int ccd_build_swept(ipcgpu_ctx* ctx, double h);
+int ccd_full(ipcgpu_ctx* ctx, double tol, const double* err_vf, const double* err_ee);
+int ccd_read_back(ipcgpu_ctx* ctx, double* alpha_out);
+
+// deferred error flags of the iteration state -> status code (first raised flag wins) and message
+static int status_from_flags(ipcgpu_ctx* ctx, const int* f)
+{
+    if (f[FLAG_NONPOSITIVE_DISTANCE]) {
+        ctx->err = "a constraint has d <= 0 (the reference exits here, Optimizer.cpp:3296-3306)";
+        return IPCGPU_ERR_NONPOSITIVE_DISTANCE;
+    }
+    if (f[FLAG_SET_CAPACITY]) {
+        ctx->err = "constraint-set capacity exceeded (raise it with ipcgpu_set_pair_capacity)";
+        return IPCGPU_ERR_CAPACITY;
+    }
+    if (f[FLAG_EXCHANGE_CAPACITY]) {
+        ctx->err = "pair-list exchange capacity exceeded (65536 pairs per rank and list)";
+        return IPCGPU_ERR_CAPACITY;
+    }
+    if (f[FLAG_CCD_CAPACITY]) {
+        ctx->err = "CCD candidate capacity exceeded (raise it with ipcgpu_set_ccd_capacity)";
+        return IPCGPU_ERR_CAPACITY;
+    }
+    if (f[FLAG_PATTERN]) {
+        ctx->err = "CSR pattern misses a contact block: call ipcgpu_set_csr with the augmented pattern (augmentConnectivity, SelfCollisionHandler.cpp:330-415)";
+        return IPCGPU_ERR_PATTERN;
+    }
+    return IPCGPU_OK;
+}
 
 extern "C" {
 
@@ -173,11 +291,16 @@ int ipcgpu_create(int device, ipcgpu_ctx** out)
     if (cudaSetDevice(device) != cudaSuccess) return IPCGPU_ERR_CUDA;
     ipcgpu_ctx* ctx = new ipcgpu_ctx();
     ctx->device = device;
+    void* hi = nullptr;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess || cudaMallocHost(&ctx->h_scalar, 512) != cudaSuccess
-        || !ctx->flag.reserve(4) || !ctx->scalar_out.reserve(8) || !ctx->min_ord.reserve(4)) {
+        || cudaMallocHost(&hi, sizeof(IterState)) != cudaSuccess || !ctx->flag.reserve(4) || !ctx->scalar_out.reserve(8) || !ctx->iter.reserve(1)
+        || cudaMemsetAsync(ctx->iter.p, 0, sizeof(IterState), ctx->stream) != cudaSuccess) {
         delete ctx;
         return IPCGPU_ERR_CUDA;
     }
+    ctx->h_iter = static_cast<IterState*>(hi);
+    std::memset(ctx->h_iter, 0, sizeof(IterState));
+    step_set(ctx->iter.p, 1.0, ctx->stream);
     *out = ctx;
     return IPCGPU_OK;
 }
@@ -186,6 +309,7 @@ void ipcgpu_destroy(ipcgpu_ctx* ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto& v : ctx->prof)
         for (auto& pr : v) {
             cudaEventDestroy(pr.first);
@@ -194,11 +318,9 @@ void ipcgpu_destroy(ipcgpu_ctx* ctx)
     if (ctx->timer_a) cudaEventDestroy(ctx->timer_a);
     if (ctx->timer_b) cudaEventDestroy(ctx->timer_b);
     if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->nccl_comm);
-    if (ctx->stream) {
-        cudaStreamSynchronize(ctx->stream);
-        cudaStreamDestroy(ctx->stream);
-    }
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->h_scalar) cudaFreeHost(ctx->h_scalar);
+    if (ctx->h_iter) cudaFreeHost(ctx->h_iter);
     delete ctx;
 }
 
@@ -234,10 +356,26 @@ int ipcgpu_comm_init(ipcgpu_ctx* ctx, int rank, int nranks, const void* id128)
         REQUIRE(r == 0, IPCGPU_ERR_NCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
     }
     if (ctx->nT > 0) { // re-partition an already loaded mesh
-        ctx->t_begin = (int)((int64_t)ctx->nT * rank / nranks);
-        ctx->t_end = (int)((int64_t)ctx->nT * (rank + 1) / nranks);
-        return build_maps(ctx);
+        int rc = build_maps(ctx);
+        if (rc) return rc;
+        owned_value_range(ctx);
+        if (ctx->surface_ready && (rc = contact_alloc(ctx))) return rc;
     }
+    return IPCGPU_OK;
+}
+
+int ipcgpu_partition_info(ipcgpu_ctx* ctx, int* rank, int* nranks, int* tet_begin, int* tet_end, int* row_vertex_begin, int* row_vertex_end, int64_t* value_begin,
+    int64_t* value_end, int* n_assembled_tets)
+{
+    if (rank) *rank = ctx->rank;
+    if (nranks) *nranks = ctx->nranks;
+    if (tet_begin) *tet_begin = ctx->t_begin;
+    if (tet_end) *tet_end = ctx->t_end;
+    if (row_vertex_begin) *row_vertex_begin = ctx->v_begin;
+    if (row_vertex_end) *row_vertex_end = ctx->v_end;
+    if (value_begin) *value_begin = ctx->a_begin;
+    if (value_end) *value_end = ctx->a_end;
+    if (n_assembled_tets) *n_assembled_tets = ctx->n_list;
     return IPCGPU_OK;
 }
 
@@ -252,6 +390,10 @@ int ipcgpu_set_mesh(ipcgpu_ctx* ctx, int nV, int nT, const double* Vrest, const 
     ctx->nT = nT;
     ctx->energy = energy;
     ctx->h_T.assign(tets, tets + (size_t)4 * nT);
+    ctx->h_ia.clear();
+    ctx->nnz = 0;
+    ctx->surface_ready = false;
+    ctx->dir_valid = false;
     // Dm^-1: reference layout is per-tet column-major; device layout is SoA over the row-major index q=3i+j
     std::vector<double> A((size_t)9 * std::max(nT, 1));
     for (int t = 0; t < nT; ++t)
@@ -271,25 +413,27 @@ int ipcgpu_set_mesh(ipcgpu_ctx* ctx, int nV, int nT, const double* Vrest, const 
     ALLOC(ctx->e_per_tet, (size_t)std::max(nT, 1));
     ALLOC(ctx->inv_steps, (size_t)std::max(nT, 1));
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->t_begin = (int)((int64_t)nT * ctx->rank / ctx->nranks);
-    ctx->t_end = (int)((int64_t)nT * (ctx->rank + 1) / ctx->nranks);
     return build_maps(ctx);
 }
 
 int ipcgpu_set_csr(ipcgpu_ctx* ctx, int n_rows, const int* ia, const int* ja, int index_base)
 {
     REQUIRE(n_rows > 0 && ia && ja && (index_base == 0 || index_base == 1), IPCGPU_ERR_ARG, "ipcgpu_set_csr: bad arguments");
+    REQUIRE(ctx->nV > 0 && n_rows == 3 * ctx->nV, IPCGPU_ERR_ARG, "ipcgpu_set_csr: n_rows must be 3*nV of the mesh set before");
     CK(cudaSetDevice(ctx->device));
     const int nnz = ia[n_rows] - index_base;
     REQUIRE(nnz >= 0, IPCGPU_ERR_ARG, "ipcgpu_set_csr: negative nnz");
     ctx->n_rows = n_rows;
     ctx->nnz = nnz;
     ctx->index_base = index_base;
+    ctx->h_ia.assign(ia, ia + (size_t)n_rows + 1);
     bool ok = ctx->ia.upload(ia, (size_t)n_rows + 1, ctx->stream) && ctx->ja.upload(ja, (size_t)nnz, ctx->stream) && ctx->a.reserve((size_t)std::max(nnz, 1));
     REQUIRE(ok, IPCGPU_ERR_CUDA, "CSR upload failed");
     CK(cudaMemsetAsync(ctx->a.p, 0, (size_t)nnz * sizeof(double), ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    ctx->a_all_dirty = false;
     ctx->offsets_ready = false;
+    owned_value_range(ctx);
     return IPCGPU_OK;
 }
 
@@ -309,14 +453,32 @@ int ipcgpu_save_state(ipcgpu_ctx* ctx)
     return IPCGPU_OK;
 }
 
+// upload the search direction; pSize = mean |p| over the surface vertices in the reference's serial order (SpatialHash.hpp:603-612),
+// taken straight from the caller's array (it is only needed by the swept build and costs one pass over the surface)
+static int upload_dir(ipcgpu_ctx* ctx, const double* p)
+{
+    if (p) {
+        CK(cudaMemcpyAsync(ctx->dir.p, p, (size_t)3 * ctx->nV * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        double pSize = 0;
+        for (int i = 0; i < ctx->nSV; ++i) {
+            const int v = ctx->h_SVI[i];
+            pSize += std::abs(p[3 * (size_t)v]);
+            pSize += std::abs(p[3 * (size_t)v + 1]);
+            pSize += std::abs(p[3 * (size_t)v + 2]);
+        }
+        ctx->pSize = ctx->nSV > 0 ? pSize / (double)((long long)ctx->nSV * 3) : 0.0;
+        ctx->pSize_surface = ctx->surface_ready;
+        ctx->dir_valid = true; // (no synchronisation: like every host input of the deferred mode, p must stay untouched until the next fetch)
+    }
+    REQUIRE(ctx->dir_valid, IPCGPU_ERR_STATE, "no search direction uploaded yet");
+    return IPCGPU_OK;
+}
+
 int ipcgpu_set_search_dir(ipcgpu_ctx* ctx, const double* p)
 {
     REQUIRE(ctx->nV > 0 && p, IPCGPU_ERR_ARG, "ipcgpu_set_search_dir: mesh and p required");
     CK(cudaSetDevice(ctx->device));
-    ctx->h_dir.assign(p, p + (size_t)3 * ctx->nV);
-    CK(cudaMemcpyAsync(ctx->dir.p, p, (size_t)3 * ctx->nV * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    return IPCGPU_OK;
+    return upload_dir(ctx, p);
 }
 
 int ipcgpu_step_forward(ipcgpu_ctx* ctx, const double* p, double alpha)
@@ -324,10 +486,8 @@ int ipcgpu_step_forward(ipcgpu_ctx* ctx, const double* p, double alpha)
     REQUIRE(ctx->nV > 0, IPCGPU_ERR_STATE, "ipcgpu_set_mesh first");
     REQUIRE(ctx->state_saved, IPCGPU_ERR_STATE, "ipcgpu_save_state must precede ipcgpu_step_forward");
     CK(cudaSetDevice(ctx->device));
-    if (p) {
-        ctx->h_dir.assign(p, p + (size_t)3 * ctx->nV);
-        CK(cudaMemcpyAsync(ctx->dir.p, p, (size_t)3 * ctx->nV * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    }
+    int rc = upload_dir(ctx, p);
+    if (rc) return rc;
     step_forward(ctx->nV, ctx->Vsaved.p, ctx->dir.p, alpha, ctx->V.p, ctx->stream);
     ++ctx->launches;
     CK(cudaGetLastError());
@@ -342,10 +502,13 @@ int ipcgpu_elastic_energy(ipcgpu_ctx* ctx, double coef, int /*redoSVD*/, double*
     elastic_energy(ctx->eargs(), ctx->e_per_tet.p, ctx->partials.p, coef, ctx->scalar_out.p, ctx->stream);
     ctx->prof_end(pe);
     ctx->launches += 2;
-    if (ctx->nranks > 1) {
+    if (ctx->nranks > 1 && E) { // host result requested: complete it now; NULL = local sum, reduced by ipcgpu_fetch_iteration
         int r = g_nccl.AllReduce(ctx->scalar_out.p, ctx->scalar_out.p, 1, kNcclFloat64, kNcclSum, ctx->nccl_comm, ctx->stream);
         REQUIRE(r == 0, IPCGPU_ERR_NCCL, "ncclAllReduce(energy) failed");
     }
+    energy_store(ctx->iter.p, 0, ctx->scalar_out.p, ctx->stream);
+    ++ctx->launches;
+    ctx->energy_local[0] = (ctx->nranks > 1 && !E);
     CK(cudaGetLastError());
     if (E) {
         CK(cudaMemcpyAsync(ctx->h_scalar, ctx->scalar_out.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -355,7 +518,18 @@ int ipcgpu_elastic_energy(ipcgpu_ctx* ctx, double coef, int /*redoSVD*/, double*
     return IPCGPU_OK;
 }
 
-static int run_grad_hess(ipcgpu_ctx* ctx, double coef, int projectSPD, int projectDBC, bool need_g, bool need_h, int add_mass, bool accumulate_a)
+// zero the part of the value array this rank writes (everything after a cross-rank completion has filled the other rows)
+static int zero_values(ipcgpu_ctx* ctx)
+{
+    if (ctx->nranks > 1 && !ctx->a_all_dirty) {
+        if (ctx->a_end > ctx->a_begin) CK(cudaMemsetAsync(ctx->a.p + ctx->a_begin, 0, (size_t)(ctx->a_end - ctx->a_begin) * sizeof(double), ctx->stream));
+    }
+    else CK(cudaMemsetAsync(ctx->a.p, 0, (size_t)ctx->nnz * sizeof(double), ctx->stream));
+    ctx->a_all_dirty = false;
+    return IPCGPU_OK;
+}
+
+static int run_grad_hess(ipcgpu_ctx* ctx, double coef, int projectSPD, int projectDBC, bool need_g, bool need_h, int add_mass)
 {
     REQUIRE(ctx->maps_ready, IPCGPU_ERR_STATE, "ipcgpu_set_mesh first");
     if (need_h) {
@@ -367,6 +541,7 @@ static int run_grad_hess(ipcgpu_ctx* ctx, double coef, int projectSPD, int proje
     ctx->prof_end(pe);
     ++ctx->launches;
     if (need_g) {
+        // owned vertices gather their complete sums (every incident tet is in this rank's list); the other rows are written as zeros
         pe = ctx->prof_begin(IPCGPU_STAGE_GATHER_GRADIENT);
         gather_gradient(ctx->nV, ctx->inc_ptr.p, ctx->inc.p, ctx->gcont.p, ctx->has_dbc ? ctx->dbc.p : nullptr, projectDBC, 0, ctx->g.p, ctx->stream);
         ctx->prof_end(pe);
@@ -375,15 +550,12 @@ static int run_grad_hess(ipcgpu_ctx* ctx, double coef, int projectSPD, int proje
     if (need_h) {
         pe = ctx->prof_begin(IPCGPU_STAGE_ASSEMBLE_CSR);
         assemble_csr(ctx->nSlots, ctx->slot_v.p, ctx->slot_u.p, ctx->slot_off.p, ctx->con_ptr.p, ctx->con_src.p, ctx->hblk.p,
-            ctx->has_dbc ? ctx->dbc.p : nullptr, projectDBC, nullptr, accumulate_a ? 1 : 0, ctx->a.p, ctx->stream);
-        // per-vertex diagonal terms (mass, Dirichlet identity) over ALL vertices, by rank 0 only so that the cross-rank sum counts them once
-        if (ctx->rank == 0) {
-            const double* m = (add_mass && ctx->has_mass) ? ctx->mass.p : nullptr;
-            diag_mass_dbc(ctx->nV, ctx->ia.p, ctx->index_base, ctx->has_dbc ? ctx->dbc.p : nullptr, projectDBC, m, ctx->a.p, ctx->stream);
-            ++ctx->launches;
-        }
+            ctx->has_dbc ? ctx->dbc.p : nullptr, projectDBC, nullptr, 1, ctx->a.p, ctx->stream);
+        // per-vertex diagonal terms (mass, Dirichlet identity) of the owned rows
+        const double* m = (add_mass && ctx->has_mass) ? ctx->mass.p : nullptr;
+        diag_mass_dbc_range(ctx->v_begin, ctx->v_end, ctx->ia.p, ctx->index_base, ctx->has_dbc ? ctx->dbc.p : nullptr, projectDBC, m, ctx->a.p, ctx->stream);
         ctx->prof_end(pe);
-        ++ctx->launches;
+        ctx->launches += 2;
     }
     CK(cudaGetLastError());
     return IPCGPU_OK;
@@ -392,7 +564,7 @@ static int run_grad_hess(ipcgpu_ctx* ctx, double coef, int projectSPD, int proje
 int ipcgpu_elastic_gradient(ipcgpu_ctx* ctx, double coef, int /*redoSVD*/, int projectDBC, double* g)
 {
     CK(cudaSetDevice(ctx->device));
-    int rc = run_grad_hess(ctx, coef, 1, projectDBC, true, false, 0, false);
+    int rc = run_grad_hess(ctx, coef, 1, projectDBC, true, false, 0);
     if (rc) return rc;
     if (ctx->nranks > 1 && g) { // host result requested: complete it across ranks; NULL = deferred (ipcgpu_allreduce_grad_hess)
         rc = ipcgpu_allreduce_grad_hess(ctx, 1, 0);
@@ -405,24 +577,32 @@ int ipcgpu_elastic_gradient(ipcgpu_ctx* ctx, double coef, int /*redoSVD*/, int p
     return IPCGPU_OK;
 }
 
+// host value array in (addCoeff semantics): rank 0 contributes it, everybody else starts from zero
+static int upload_values(ipcgpu_ctx* ctx, const double* a_host)
+{
+    if (ctx->rank == 0) CK(cudaMemcpyAsync(ctx->a.p, a_host, (size_t)ctx->nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    else CK(cudaMemsetAsync(ctx->a.p, 0, (size_t)ctx->nnz * sizeof(double), ctx->stream));
+    return IPCGPU_OK;
+}
+static int download_values(ipcgpu_ctx* ctx, double* a_host)
+{
+    if (ctx->nranks > 1) {
+        int rc = ipcgpu_allreduce_grad_hess(ctx, 0, 1);
+        if (rc) return rc;
+    }
+    CK(cudaMemcpyAsync(a_host, ctx->a.p, (size_t)ctx->nnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return IPCGPU_OK;
+}
+
 int ipcgpu_elastic_hessian(ipcgpu_ctx* ctx, double coef, int /*redoSVD*/, int projectSPD, int projectDBC, double* a_inout)
 {
     CK(cudaSetDevice(ctx->device));
     REQUIRE(ctx->nnz > 0, IPCGPU_ERR_STATE, "ipcgpu_set_csr first");
-    if (a_inout) {
-        if (ctx->rank == 0) CK(cudaMemcpyAsync(ctx->a.p, a_inout, (size_t)ctx->nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        else CK(cudaMemsetAsync(ctx->a.p, 0, (size_t)ctx->nnz * sizeof(double), ctx->stream));
-    }
-    int rc = run_grad_hess(ctx, coef, projectSPD, projectDBC, false, true, 0, true);
-    if (rc) return rc;
-    if (ctx->nranks > 1 && a_inout) {
-        rc = ipcgpu_allreduce_grad_hess(ctx, 0, 1);
-        if (rc) return rc;
-    }
-    if (a_inout) {
-        CK(cudaMemcpyAsync(a_inout, ctx->a.p, (size_t)ctx->nnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-    }
+    int rc;
+    if (a_inout && (rc = upload_values(ctx, a_inout))) return rc;
+    if ((rc = run_grad_hess(ctx, coef, projectSPD, projectDBC, false, true, 0))) return rc;
+    if (a_inout) return download_values(ctx, a_inout);
     return IPCGPU_OK;
 }
 
@@ -431,10 +611,10 @@ int ipcgpu_elastic_grad_hess(ipcgpu_ctx* ctx, double coef, int projectSPD, int p
     CK(cudaSetDevice(ctx->device));
     REQUIRE(ctx->nnz > 0, IPCGPU_ERR_STATE, "ipcgpu_set_csr first");
     // the value array is rebuilt from scratch (LinSysSolver::setZero, then addCoeff of every term): slots that no local tet touches
-    // -- contact-only blocks of the augmented pattern, other ranks' blocks -- must not keep last iteration's values
-    CK(cudaMemsetAsync(ctx->a.p, 0, (size_t)ctx->nnz * sizeof(double), ctx->stream));
-    int rc = run_grad_hess(ctx, coef, projectSPD, projectDBC, true, true, add_mass, true);
+    // -- contact-only blocks of the augmented pattern -- must not keep last iteration's values
+    int rc = zero_values(ctx);
     if (rc) return rc;
+    if ((rc = run_grad_hess(ctx, coef, projectSPD, projectDBC, true, true, add_mass))) return rc;
     if (ctx->nranks > 1 && (g || a)) {
         rc = ipcgpu_allreduce_grad_hess(ctx, g ? 1 : 0, a ? 1 : 0);
         if (rc) return rc;
@@ -445,31 +625,33 @@ int ipcgpu_elastic_grad_hess(ipcgpu_ctx* ctx, double coef, int projectSPD, int p
     return IPCGPU_OK;
 }
 
+// ---- step bound: device-resident chain ---------------------------------------------------------------------
+int ipcgpu_step_bound_set(ipcgpu_ctx* ctx, double alpha)
+{
+    REQUIRE(alpha >= 0.0, IPCGPU_ERR_ARG, "the step must be non-negative");
+    CK(cudaSetDevice(ctx->device));
+    step_set(ctx->iter.p, alpha, ctx->stream);
+    ++ctx->launches;
+    CK(cudaGetLastError());
+    return IPCGPU_OK;
+}
+
 int ipcgpu_inversion_step(ipcgpu_ctx* ctx, const double* p, double slack, double* alpha_inout)
 {
     REQUIRE(ctx->maps_ready, IPCGPU_ERR_STATE, "ipcgpu_set_mesh first");
-    REQUIRE(alpha_inout != nullptr, IPCGPU_ERR_ARG, "alpha_inout is null");
     CK(cudaSetDevice(ctx->device));
-    if (p) {
-        ctx->h_dir.assign(p, p + (size_t)3 * ctx->nV);
-        CK(cudaMemcpyAsync(ctx->dir.p, p, (size_t)3 * ctx->nV * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    }
-    const unsigned long long init = 0x7ff0000000000000ull; // +inf
-    CK(cudaMemcpyAsync(ctx->min_ord.p, &init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = upload_dir(ctx, p);
+    if (rc) return rc;
+    if (alpha_inout && (rc = ipcgpu_step_bound_set(ctx, *alpha_inout))) return rc;
     cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_INVERSION);
-    inversion_step(ctx->eargs(), ctx->dir.p, slack, ctx->inv_steps.p, ctx->min_ord.p, ctx->stream);
+    inversion_step(ctx->eargs(), ctx->dir.p, slack, ctx->inv_steps.p, ctx->iter.p, ctx->stream);
     ctx->prof_end(pe);
+    ctx->launches += 2;
+    if ((rc = nccl_min_u64(ctx, &ctx->iter.p->inv_ord))) return rc;
+    inversion_apply(ctx->iter.p, ctx->nT, ctx->stream); // Energy.cpp:576-579
     ++ctx->launches;
-    if (ctx->nranks > 1) {
-        int r = g_nccl.AllReduce(ctx->min_ord.p, ctx->min_ord.p, 1, kNcclUint64, kNcclMin, ctx->nccl_comm, ctx->stream);
-        REQUIRE(r == 0, IPCGPU_ERR_NCCL, "ncclAllReduce(min step) failed");
-    }
-    unsigned long long* h = reinterpret_cast<unsigned long long*>(ctx->h_scalar);
-    CK(cudaMemcpyAsync(h, ctx->min_ord.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    double m;
-    std::memcpy(&m, h, sizeof(double));
-    if (ctx->nT > 0 && m > 0.0 && m < *alpha_inout) *alpha_inout = m; // Energy.cpp:576-579
+    CK(cudaGetLastError());
+    if (alpha_inout) return ccd_read_back(ctx, alpha_inout);
     return IPCGPU_OK;
 }
 
@@ -489,6 +671,7 @@ int ipcgpu_set_surface(ipcgpu_ctx* ctx, int nSV, const int* SVI, int nSE, const 
     if (vCoDim) REQUIRE(ctx->vCoDim.upload(vCoDim, ctx->nV, ctx->stream), IPCGPU_ERR_CUDA, "codim upload failed");
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->h_SVI.assign(SVI, SVI + nSV);
+    ctx->pSize_surface = false; // pSize belongs to the surface
     int rc = contact_alloc(ctx);
     if (rc) return rc;
     if ((rc = ccd_alloc(ctx))) return rc;
@@ -535,60 +718,63 @@ int ipcgpu_ti_error(const double* V, int nV, const double* p, double err_vf[3], 
     return IPCGPU_OK;
 }
 
-static int upload_dir(ipcgpu_ctx* ctx, const double* p)
+int ipcgpu_ccd_debug_seed_bound(ipcgpu_ctx* ctx, double toi)
 {
-    if (p) {
-        ctx->h_dir.assign(p, p + (size_t)3 * ctx->nV);
-        CK(cudaMemcpyAsync(ctx->dir.p, p, (size_t)3 * ctx->nV * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    }
-    REQUIRE(ctx->h_dir.size() == (size_t)3 * ctx->nV, IPCGPU_ERR_STATE, "no search direction uploaded yet");
-    return IPCGPU_OK;
-}
-
-static int allreduce_min_step(ipcgpu_ctx* ctx, double* alpha)
-{
-    if (ctx->nranks <= 1) return IPCGPU_OK;
-    // ranks hold disjoint candidate ranges: min of the non-negative steps via their order-preserving integer image
-    CK(cudaMemcpyAsync(ctx->min_ord.p, alpha, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    int r = g_nccl.AllReduce(ctx->min_ord.p, ctx->min_ord.p, 1, kNcclUint64, kNcclMin, ctx->nccl_comm, ctx->stream);
-    REQUIRE(r == 0, IPCGPU_ERR_NCCL, "ncclAllReduce(min step) failed");
-    CK(cudaMemcpyAsync(alpha, ctx->min_ord.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->debug_prune_seed = toi;
     return IPCGPU_OK;
 }
 
 int ipcgpu_ccd_partial_ti(ipcgpu_ctx* ctx, const double* p, double tol, const double err_vf[3], const double err_ee[3], double* alpha_inout)
 {
     REQUIRE(ctx->surface_ready, IPCGPU_ERR_STATE, "ipcgpu_set_surface first");
-    REQUIRE(alpha_inout && err_vf && err_ee, IPCGPU_ERR_ARG, "null argument");
+    REQUIRE(err_vf && err_ee, IPCGPU_ERR_ARG, "null argument");
     CK(cudaSetDevice(ctx->device));
     int rc = upload_dir(ctx, p);
     if (rc) return rc;
-    // CFL_FOR_CCD != 0: empty candidate list returns immediately (:700)
-    const unsigned long long n = (unsigned long long)ctx->cw.nK;
-    const unsigned long long b = ctx->lists_local ? 0 : n * ctx->rank / ctx->nranks, e = ctx->lists_local ? n : n * (ctx->rank + 1) / ctx->nranks;
-    if ((rc = ccd_narrow(ctx, ctx->cw.cand.p + b, e - b, tol, err_vf, err_ee, alpha_inout))) return rc;
-    return allreduce_min_step(ctx, alpha_inout);
+    if (alpha_inout && (rc = ipcgpu_step_bound_set(ctx, *alpha_inout))) return rc;
+    // CFL_FOR_CCD != 0: an empty candidate list leaves the step unchanged (:700).  Replicated lists: every rank walks a contiguous
+    // slice; partitioned lists (ipcgpu_set_contact_partition) are already this rank's own.
+    ContactWork& w = ctx->cw;
+    const int share = (ctx->nranks > 1 && !ctx->lists_local) ? 1 : 0;
+    if ((rc = ccd_narrow(ctx, w.cand.p, w.counters.p + 3, nullptr, (unsigned long long)4 * w.cap, share, tol, err_vf, err_ee, 1, nullptr))) return rc;
+    if (alpha_inout) return ccd_read_back(ctx, alpha_inout);
+    return IPCGPU_OK;
 }
 
 int ipcgpu_hash_build_swept(ipcgpu_ctx* ctx, const double* p, double* alpha_inout, double h)
 {
     REQUIRE(ctx->surface_ready, IPCGPU_ERR_STATE, "ipcgpu_set_surface first");
-    REQUIRE(alpha_inout && h > 0.0, IPCGPU_ERR_ARG, "bad arguments");
+    REQUIRE(h > 0.0, IPCGPU_ERR_ARG, "bad arguments");
     CK(cudaSetDevice(ctx->device));
-    return ccd_build_swept(ctx, p, alpha_inout, h);
+    int rc = upload_dir(ctx, p);
+    if (rc) return rc;
+    REQUIRE(ctx->pSize_surface, IPCGPU_ERR_STATE, "the search direction was uploaded before ipcgpu_set_surface: upload it again");
+    if (alpha_inout && (rc = ipcgpu_step_bound_set(ctx, *alpha_inout))) return rc;
+    if ((rc = ccd_build_swept(ctx, h))) return rc;
+    if (alpha_inout) return ccd_read_back(ctx, alpha_inout);
+    return IPCGPU_OK;
 }
 
 int ipcgpu_ccd_full_ti(ipcgpu_ctx* ctx, double tol, const double err_vf[3], const double err_ee[3], double* alpha_inout, uint64_t* n_candidates)
 {
     REQUIRE(ctx->surface_ready && ctx->ccd.swept_ready, IPCGPU_ERR_STATE, "ipcgpu_hash_build_swept first");
-    REQUIRE(alpha_inout && err_vf && err_ee, IPCGPU_ERR_ARG, "null argument");
+    REQUIRE(err_vf && err_ee, IPCGPU_ERR_ARG, "null argument");
     CK(cudaSetDevice(ctx->device));
-    unsigned long long nc = 0;
-    int rc = ccd_full(ctx, tol, err_vf, err_ee, alpha_inout, &nc);
-    if (n_candidates) *n_candidates = nc;
-    if (rc) return rc;
-    return allreduce_min_step(ctx, alpha_inout);
+    int rc;
+    // (the swept grid was built for the step the chain held then; a host step that differs from it only lowers max_t)
+    if (alpha_inout && (rc = ipcgpu_step_bound_set(ctx, *alpha_inout))) return rc;
+    if ((rc = ccd_full(ctx, tol, err_vf, err_ee))) return rc;
+    if (alpha_inout || n_candidates) {
+        if ((rc = ccd_read_back(ctx, alpha_inout))) return rc;
+        if (n_candidates) *n_candidates = ctx->h_iter->n_full_cand;
+        if (ctx->h_iter->flags[FLAG_CCD_CAPACITY]) {
+            clear_flag(ctx, FLAG_CCD_CAPACITY);
+            int only[8] = { 0 };
+            only[FLAG_CCD_CAPACITY] = 1;
+            return status_from_flags(ctx, only);
+        }
+    }
+    return IPCGPU_OK;
 }
 
 int ipcgpu_ccd_stats(ipcgpu_ctx* ctx, uint64_t* candidates, uint64_t* survivors, uint64_t* warnings)
@@ -629,6 +815,20 @@ int ipcgpu_constraint_set(ipcgpu_ctx* ctx, double dHat, int getPTEE, int* nC, in
     CK(cudaSetDevice(ctx->device));
     int rc = contact_constraint_set(ctx, dHat, getPTEE, nC, nPara, nCand);
     ctx->lists_local = (rc == 0) && ctx->partition_contact && ctx->nranks > 1;
+    ctx->cw.lists_global = false;
+    if (rc == 0 && ctx->lists_local) {
+        // every rank holds a disjoint part of the sets: exchange them (one fixed-size message per rank) so that each rank can assemble
+        // the Hessian rows it owns from ALL pairs that touch them
+        ContactWork& w = ctx->cw;
+        contact_pack_lists(ctx);
+        cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_ALLREDUCE);
+        int r = g_nccl.AllGather(w.xsend.p, w.xrecv.p, w.xstride * 4, kNcclInt32, ctx->nccl_comm, ctx->stream);
+        ctx->prof_end(pe);
+        REQUIRE(r == 0, IPCGPU_ERR_NCCL, "ncclAllGather(pair lists) failed");
+        contact_unpack_lists(ctx);
+        w.lists_global = true;
+        CK(cudaGetLastError());
+    }
     return rc;
 }
 
@@ -648,11 +848,29 @@ int ipcgpu_get_constraint_set(ipcgpu_ctx* ctx, int* mm, int* para, int* para_e, 
 {
     REQUIRE(ctx->surface_ready, IPCGPU_ERR_STATE, "ipcgpu_set_surface first");
     ContactWork& w = ctx->cw;
+    if (w.nC < 0) { // built without a read-back: fetch the sizes now
+        int rc = contact_sync_counts(ctx);
+        if (rc) return rc;
+    }
     if (mm && w.nC) CK(cudaMemcpyAsync(mm, w.act.p, (size_t)w.nC * sizeof(int4), cudaMemcpyDeviceToHost, ctx->stream));
     if (para && w.nP) CK(cudaMemcpyAsync(para, w.para.p, (size_t)w.nP * sizeof(int4), cudaMemcpyDeviceToHost, ctx->stream));
     if (para_e && w.nP) CK(cudaMemcpyAsync(para_e, w.para_e.p, (size_t)w.nP * sizeof(int2), cudaMemcpyDeviceToHost, ctx->stream));
     if (cand && w.nK) CK(cudaMemcpyAsync(cand, w.cand.p, (size_t)w.nK * sizeof(int2), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return IPCGPU_OK;
+}
+
+int ipcgpu_constraint_set_sizes(ipcgpu_ctx* ctx, int* nC, int* nPara, int* nCand)
+{
+    REQUIRE(ctx->surface_ready, IPCGPU_ERR_STATE, "ipcgpu_set_surface first");
+    ContactWork& w = ctx->cw;
+    if (w.nC < 0) {
+        int rc = contact_sync_counts(ctx);
+        if (rc) return rc;
+    }
+    if (nC) *nC = w.nC;
+    if (nPara) *nPara = w.nP;
+    if (nCand) *nCand = w.nK;
     return IPCGPU_OK;
 }
 
@@ -665,22 +883,34 @@ int ipcgpu_set_constraint_set(ipcgpu_ctx* ctx, int nC, const int* mm, int nP, co
     if (nP) CK(cudaMemcpyAsync(w.para.p, para, (size_t)nP * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
     if (nP) CK(cudaMemcpyAsync(w.para_e.p, para_e, (size_t)nP * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
     if (nK) CK(cudaMemcpyAsync(w.cand.p, cand, (size_t)nK * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+    int* h = reinterpret_cast<int*>(ctx->h_scalar);
+    for (int i = 0; i < 16; ++i) h[i] = 0;
+    h[0] = nC; h[2] = nP; h[3] = nK;
+    CK(cudaMemcpyAsync(w.counters.p, h, 16 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream)); // the consumers read the sizes on the device
     CK(cudaStreamSynchronize(ctx->stream));
     w.nC = nC; w.nP = nP; w.nK = nK;
+    w.want_cand = nK > 0;
     ctx->lists_local = false; // uploaded sets are the global ones
+    w.lists_global = false;
     return IPCGPU_OK;
 }
 
 static BarrierArgs barrier_args(ipcgpu_ctx* ctx, double dHat, double kappa, int projectDBC)
 {
     BarrierArgs p;
+    ContactWork& w = ctx->cw;
     p.nV = ctx->nV; p.V = ctx->V.p; p.Vrest = ctx->Vrest.p; p.dbc = ctx->has_dbc ? ctx->dbc.p : nullptr; p.SE = ctx->SE.p;
-    // replicated lists: every rank owns a contiguous share of them; partitioned lists (ipcgpu_set_contact_partition): all local
-    const long long nC = ctx->cw.nC, nP = ctx->cw.nP;
-    const bool local = ctx->lists_local;
-    const int cb = local ? 0 : (int)(nC * ctx->rank / ctx->nranks), ce = local ? (int)nC : (int)(nC * (ctx->rank + 1) / ctx->nranks);
-    const int pb = local ? 0 : (int)(nP * ctx->rank / ctx->nranks), pe = local ? (int)nP : (int)(nP * (ctx->rank + 1) / ctx->nranks);
-    p.cs = ctx->cw.act.p + cb; p.nC = ce - cb; p.para = ctx->cw.para.p + pb; p.para_e = ctx->cw.para_e.p + pb; p.nP = pe - pb;
+    // one rank: the lists as built.  Several ranks: the GLOBAL lists (replicated build, or partitioned build + exchange); energy and
+    // gradient take a contiguous share of them, the Hessian goes by row owner.
+    if (ctx->nranks > 1 && w.lists_global) {
+        p.cs = w.gact.p; p.nC = w.counters.p + 10; p.para = w.gpara.p; p.para_e = w.gpara_e.p; p.nP = w.counters.p + 11;
+    }
+    else {
+        p.cs = w.act.p; p.nC = w.counters.p + 0; p.para = w.para.p; p.para_e = w.para_e.p; p.nP = w.counters.p + 2;
+    }
+    p.rank = ctx->rank; p.nranks = ctx->nranks; p.share = ctx->nranks > 1 ? 1 : 0;
+    p.row_lo = ctx->nranks > 1 ? ctx->v_begin : 0;
+    p.row_hi = ctx->nranks > 1 ? ctx->v_end : ctx->nV;
     p.dHat = dHat; p.kappa = kappa; p.projectDBC = projectDBC;
     p.ia = ctx->ia.p; p.ja = ctx->ja.p; p.base = ctx->index_base;
     return p;
@@ -691,27 +921,30 @@ int ipcgpu_barrier_energy(ipcgpu_ctx* ctx, double dHat, double kappa, double* E)
     REQUIRE(ctx->surface_ready, IPCGPU_ERR_STATE, "ipcgpu_set_surface first");
     CK(cudaSetDevice(ctx->device));
     BarrierArgs p = barrier_args(ctx, dHat, kappa, 0);
-    const int n = p.nC + p.nP;
-    const int nb = barrier_energy_blocks(n);
-    ALLOC(ctx->bpartials, (size_t)std::max(nb, 1));
-    CK(cudaMemsetAsync(ctx->flag.p, 0, sizeof(int), ctx->stream));
     cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_BARRIER);
-    barrier_energy(p, ctx->bpartials.p, ctx->flag.p, ctx->stream);
-    reduce_sum(ctx->bpartials.p, nb, kappa, ctx->scalar_out.p + 1, ctx->stream);
+    barrier_energy(p, ctx->cw.bpartials.p, &ctx->iter.p->flags[FLAG_NONPOSITIVE_DISTANCE], ctx->stream);
+    reduce_sum(ctx->cw.bpartials.p, barrier_energy_blocks(), kappa, ctx->scalar_out.p + 1, ctx->stream);
     ctx->prof_end(pe);
     ctx->launches += 2;
-    if (ctx->nranks > 1) {
+    if (ctx->nranks > 1 && E) {
         int r = g_nccl.AllReduce(ctx->scalar_out.p + 1, ctx->scalar_out.p + 1, 1, kNcclFloat64, kNcclSum, ctx->nccl_comm, ctx->stream);
         REQUIRE(r == 0, IPCGPU_ERR_NCCL, "ncclAllReduce(barrier energy) failed");
-        // the d<=0 flag is local; a max-reduce would need a second collective: every rank checks its own share
     }
+    energy_store(ctx->iter.p, 1, ctx->scalar_out.p + 1, ctx->stream);
+    ++ctx->launches;
+    ctx->energy_local[1] = (ctx->nranks > 1 && !E);
     CK(cudaGetLastError());
-    int* hf = reinterpret_cast<int*>(ctx->h_scalar + 4);
-    CK(cudaMemcpyAsync(ctx->h_scalar, ctx->scalar_out.p + 1, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(hf, ctx->flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    if (E) *E = ctx->h_scalar[0];
-    REQUIRE(*hf == 0, IPCGPU_ERR_NONPOSITIVE_DISTANCE, "a constraint has d <= 0 (the reference exits here, Optimizer.cpp:3296-3306)");
+    if (E) { // synchronous form: the d <= 0 flag is checked right here (every rank checks its own share of the pairs)
+        int rc = fetch_iter_state(ctx);
+        if (rc) return rc;
+        *E = ctx->h_iter->energy[1];
+        if (ctx->h_iter->flags[FLAG_NONPOSITIVE_DISTANCE]) {
+            clear_flag(ctx, FLAG_NONPOSITIVE_DISTANCE);
+            int only[8] = { 0 };
+            only[FLAG_NONPOSITIVE_DISTANCE] = 1;
+            return status_from_flags(ctx, only);
+        }
+    }
     return IPCGPU_OK;
 }
 
@@ -744,39 +977,33 @@ int ipcgpu_barrier_hessian(ipcgpu_ctx* ctx, double dHat, double kappa, int proje
     REQUIRE(ctx->surface_ready, IPCGPU_ERR_STATE, "ipcgpu_set_surface first");
     REQUIRE(ctx->nnz > 0, IPCGPU_ERR_STATE, "ipcgpu_set_csr first");
     CK(cudaSetDevice(ctx->device));
-    if (a_inout) {
-        if (ctx->rank == 0) CK(cudaMemcpyAsync(ctx->a.p, a_inout, (size_t)ctx->nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        else CK(cudaMemsetAsync(ctx->a.p, 0, (size_t)ctx->nnz * sizeof(double), ctx->stream));
-    }
-    CK(cudaMemsetAsync(ctx->flag.p, 0, sizeof(int), ctx->stream));
+    int rc;
+    if (a_inout && (rc = upload_values(ctx, a_inout))) return rc;
+    ContactWork& w = ctx->cw;
     cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_BARRIER);
-    {
-        const BarrierArgs ba = barrier_args(ctx, dHat, kappa, projectDBC);
-        const size_t np = (size_t)std::max(ba.nC + ba.nP, 1);
-        ALLOC(ctx->bHraw, np * 144);
-        ALLOC(ctx->brows, np * 5); // 4 row ids + the makePD "unchanged" flag per pair
-        barrier_hessian(ba, ctx->a.p, ctx->flag.p, ctx->bHraw.p, ctx->brows.p, ctx->stream);
-    }
+    barrier_hessian(barrier_args(ctx, dHat, kappa, projectDBC), ctx->a.p, ctx->iter.p->flags, w.bHraw.p, w.brows.p, w.bpsd.p, w.counters.p + 12, w.cap, ctx->stream);
     ctx->prof_end(pe);
     ctx->launches += 3;
     CK(cudaGetLastError());
-    if (a_inout && ctx->nranks > 1) {
-        int rc = ipcgpu_allreduce_grad_hess(ctx, 0, 1);
-        if (rc) return rc;
+    if (a_inout) { // synchronous form: complete across ranks, download, check the pattern flag now
+        if ((rc = download_values(ctx, a_inout))) return rc;
+        if ((rc = fetch_iter_state(ctx))) return rc;
+        if (ctx->h_iter->flags[FLAG_PATTERN] || ctx->h_iter->flags[FLAG_SET_CAPACITY]) {
+            int only[8] = { 0 };
+            only[FLAG_PATTERN] = ctx->h_iter->flags[FLAG_PATTERN];
+            only[FLAG_SET_CAPACITY] = ctx->h_iter->flags[FLAG_SET_CAPACITY];
+            clear_flag(ctx, FLAG_PATTERN);
+            clear_flag(ctx, FLAG_SET_CAPACITY);
+            return status_from_flags(ctx, only);
+        }
     }
-    int* hf = reinterpret_cast<int*>(ctx->h_scalar + 4);
-    CK(cudaMemcpyAsync(hf, ctx->flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    if (a_inout) CK(cudaMemcpyAsync(a_inout, ctx->a.p, (size_t)ctx->nnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    REQUIRE(*hf == 0, IPCGPU_ERR_PATTERN, "CSR pattern misses a contact block: call ipcgpu_set_csr with the augmented pattern (augmentConnectivity, SelfCollisionHandler.cpp:330-415)");
     return IPCGPU_OK;
 }
 
 int ipcgpu_csr_set_zero(ipcgpu_ctx* ctx)
 {
     REQUIRE(ctx->nnz > 0, IPCGPU_ERR_STATE, "ipcgpu_set_csr first");
-    CK(cudaMemsetAsync(ctx->a.p, 0, (size_t)ctx->nnz * sizeof(double), ctx->stream));
-    return IPCGPU_OK;
+    return zero_values(ctx);
 }
 
 int ipcgpu_allreduce_grad_hess(ipcgpu_ctx* ctx, int with_gradient, int with_hessian)
@@ -784,16 +1011,60 @@ int ipcgpu_allreduce_grad_hess(ipcgpu_ctx* ctx, int with_gradient, int with_hess
     if (ctx->nranks <= 1) return IPCGPU_OK;
     REQUIRE(ctx->nccl_comm != nullptr, IPCGPU_ERR_STATE, "ipcgpu_comm_init first");
     cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_ALLREDUCE);
-    if (with_gradient) {
+    if (with_gradient) { // elastic part: every rank holds the complete rows it owns (zeros elsewhere); barrier part: partial sums
         int r = g_nccl.AllReduce(ctx->g.p, ctx->g.p, (size_t)3 * ctx->nV, kNcclFloat64, kNcclSum, ctx->nccl_comm, ctx->stream);
         REQUIRE(r == 0, IPCGPU_ERR_NCCL, "ncclAllReduce(gradient) failed");
     }
     if (with_hessian) {
+        // The rows a rank owns are already complete (row-owner assembly): this only matters to a caller that wants the WHOLE matrix on
+        // every rank.  Non-owned rows are zero, so a sum completes it.
         int r = g_nccl.AllReduce(ctx->a.p, ctx->a.p, (size_t)ctx->nnz, kNcclFloat64, kNcclSum, ctx->nccl_comm, ctx->stream);
         REQUIRE(r == 0, IPCGPU_ERR_NCCL, "ncclAllReduce(csr values) failed");
+        ctx->a_all_dirty = true; // the next rebuild must clear every row, not only the owned ones
     }
     ctx->prof_end(pe);
     return IPCGPU_OK;
+}
+
+int ipcgpu_fetch_iteration(ipcgpu_ctx* ctx, ipcgpu_iteration* out)
+{
+    REQUIRE(out != nullptr, IPCGPU_ERR_ARG, "null output");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->nranks > 1) {
+        // complete the deferred scalars across ranks: locally summed energies, and the error flags (max) so that every rank returns
+        // the same status
+        cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_ALLREDUCE);
+        for (int s = 0; s < 2; ++s)
+            if (ctx->energy_local[s]) {
+                int r = g_nccl.AllReduce(&ctx->iter.p->energy[s], &ctx->iter.p->energy[s], 1, kNcclFloat64, kNcclSum, ctx->nccl_comm, ctx->stream);
+                REQUIRE(r == 0, IPCGPU_ERR_NCCL, "ncclAllReduce(energy) failed");
+                ctx->energy_local[s] = false;
+            }
+        int r = g_nccl.AllReduce(ctx->iter.p->flags, ctx->iter.p->flags, 8, kNcclInt32, kNcclMax, ctx->nccl_comm, ctx->stream);
+        ctx->prof_end(pe);
+        REQUIRE(r == 0, IPCGPU_ERR_NCCL, "ncclAllReduce(status flags) failed");
+    }
+    int rc = ccd_read_back(ctx, nullptr);
+    if (rc) return rc;
+    const IterState& h = *ctx->h_iter;
+    out->energy_elastic = h.energy[0];
+    out->energy_barrier = h.energy[1];
+    out->alpha_inversion = h.alpha_stage[0];
+    out->alpha_partial_ccd = h.alpha_stage[1];
+    out->alpha_swept_grid = h.alpha_stage[2];
+    out->alpha_full_ccd = h.alpha_stage[3];
+    std::memcpy(&out->alpha, &h.step_ord, sizeof(double));
+    out->n_active = h.n_set[0];
+    out->n_mollified = h.n_set[1];
+    out->n_candidates = h.n_set[2];
+    out->n_full_ccd_candidates = h.n_full_cand;
+    out->ti_warnings = (uint64_t)h.flags[FLAG_TI_WARNINGS];
+    ContactWork& w = ctx->cw;
+    w.nC = h.n_set[0]; w.nP = h.n_set[1]; w.nK = h.n_set[2];
+    const int status = status_from_flags(ctx, h.flags);
+    out->status = status;
+    CK(cudaMemsetAsync(ctx->iter.p->flags, 0, 8 * sizeof(int), ctx->stream)); // flags are per fetch
+    return status;
 }
 
 int ipcgpu_profile(ipcgpu_ctx* ctx, int enable)
@@ -848,7 +1119,7 @@ int ipcgpu_timer_stop(ipcgpu_ctx* ctx, double* ms)
 
 static int buf_info(ipcgpu_ctx* ctx, int which, double** p, uint64_t* n)
 {
-    const uint64_t nL = (uint64_t)(ctx->t_end - ctx->t_begin);
+    const uint64_t nL = (uint64_t)ctx->n_list;
     switch (which) {
     case IPCGPU_BUF_GRADIENT: *p = ctx->g.p; *n = (uint64_t)3 * ctx->nV; return 0;
     case IPCGPU_BUF_CSR_VALUES: *p = ctx->a.p; *n = (uint64_t)ctx->nnz; return 0;
@@ -860,13 +1131,15 @@ static int buf_info(ipcgpu_ctx* ctx, int which, double** p, uint64_t* n)
     }
 }
 
-int ipcgpu_download(ipcgpu_ctx* ctx, int which, double* dst, uint64_t count)
+int ipcgpu_download(ipcgpu_ctx* ctx, int which, double* dst, uint64_t count) { return ipcgpu_download_range(ctx, which, 0, count, dst); }
+
+int ipcgpu_download_range(ipcgpu_ctx* ctx, int which, uint64_t offset, uint64_t count, double* dst)
 {
     double* p;
     uint64_t n;
     REQUIRE(buf_info(ctx, which, &p, &n) == 0, IPCGPU_ERR_ARG, "unknown buffer id");
-    REQUIRE(dst && count <= n, IPCGPU_ERR_ARG, "download: bad destination or count");
-    CK(cudaMemcpyAsync(dst, p, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    REQUIRE((dst || count == 0) && offset + count <= n, IPCGPU_ERR_ARG, "download: bad destination or range");
+    if (count) CK(cudaMemcpyAsync(dst, p + offset, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return IPCGPU_OK;
 }

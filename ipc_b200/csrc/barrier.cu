@@ -118,16 +118,37 @@ DEV void para_edge_stencil(int4 mm, int2 e, const int* __restrict__ SE, int* ev)
     }
 }
 
+// The list sizes live on the device (the constraint set is built there and nothing is read back inside an iteration), so every
+// kernel below is a grid-stride loop over [0, n) with n taken from device memory.  Item i of a rank's share: the first (ce - cb)
+// items are entries [cb, ce) of the active list, the rest entries [pb, pe) of the mollified list.
+struct ListRange {
+    int cb, ce, pb, pe;
+};
+DEV ListRange list_range(const BarrierArgs& p, bool whole)
+{
+    const long long nC = *p.nC, nP = *p.nP;
+    ListRange r;
+    if (p.share && !whole) {
+        r.cb = (int)(nC * p.rank / p.nranks); r.ce = (int)(nC * (p.rank + 1) / p.nranks);
+        r.pb = (int)(nP * p.rank / p.nranks); r.pe = (int)(nP * (p.rank + 1) / p.nranks);
+    }
+    else { r.cb = 0; r.ce = (int)nC; r.pb = 0; r.pe = (int)nP; }
+    return r;
+}
+
 // -----------------------------------------------------------------------------------------------------------
 // energy: kappa * sum( mult*b(d) ) + kappa * sum( e*b(d) )      (Optimizer.cpp:3290-3353)
 // -----------------------------------------------------------------------------------------------------------
+constexpr int kBarrierEnergyBlocks = 148 * 2;
 __global__ void __launch_bounds__(256) k_barrier_energy(BarrierArgs p, double* __restrict__ partials, int* __restrict__ bad)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const ListRange lr = list_range(p, false);
+    const int nA = lr.ce - lr.cb, n = nA + (lr.pe - lr.pb);
     double val = 0.0;
-    if (c < p.nC + p.nP) {
-        const bool is_para = c >= p.nC;
-        const int4 mm = is_para ? p.para[c - p.nC] : p.cs[c];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const bool is_para = i >= nA;
+        const int c = is_para ? lr.pb + (i - nA) : lr.cb + i;
+        const int4 mm = is_para ? p.para[c] : p.cs[c];
         PairStencil s = decode(mm);
         V3 x[4];
         for (int k = 0; k < s.nv; ++k) x[k] = load_vertex(p.V, p.nV, s.v[k]);
@@ -136,15 +157,15 @@ __global__ void __launch_bounds__(256) k_barrier_energy(BarrierArgs p, double* _
         else {
             double b, db, d2b;
             barrier_all(d, p.dHat, b, db, d2b);
-            if (!is_para) val = (mm.x < 0 && mm.w < -1) ? b * (double)(-mm.w) : b;
+            if (!is_para) val += (mm.x < 0 && mm.w < -1) ? b * (double)(-mm.w) : b;
             else {
                 int ev[4];
-                para_edge_stencil(mm, p.para_e[c - p.nC], p.SE, ev);
+                para_edge_stencil(mm, p.para_e[c], p.SE, ev);
                 V3 ex[4];
                 for (int k = 0; k < 4; ++k) ex[k] = load_vertex(p.V, p.nV, ev[k]);
                 double eg[12];
                 const double e = mollifier(ex, eps_x_rest(p.Vrest, p.nV, ev[0], ev[1], ev[2], ev[3]), eg, false, [](int, int, double) {});
-                val = b * e;
+                val += b * e;
             }
         }
     }
@@ -164,10 +185,12 @@ __global__ void __launch_bounds__(256) k_barrier_energy(BarrierArgs p, double* _
 // -----------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_barrier_gradient(BarrierArgs p, double* __restrict__ g)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= p.nC + p.nP) return;
-    const bool is_para = c >= p.nC;
-    const int4 mm = is_para ? p.para[c - p.nC] : p.cs[c];
+    const ListRange lr = list_range(p, false);
+    const int nA = lr.ce - lr.cb, n = nA + (lr.pe - lr.pb);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const bool is_para = i >= nA;
+    const int c = is_para ? lr.pb + (i - nA) : lr.cb + i;
+    const int4 mm = is_para ? p.para[c] : p.cs[c];
     PairStencil s = decode(mm);
     V3 x[4];
     for (int k = 0; k < s.nv; ++k) x[k] = load_vertex(p.V, p.nV, s.v[k]);
@@ -179,17 +202,18 @@ __global__ void __launch_bounds__(128) k_barrier_gradient(BarrierArgs p, double*
     if (!is_para) w = p.kappa * s.mult * db;
     else {
         int ev[4];
-        para_edge_stencil(mm, p.para_e[c - p.nC], p.SE, ev);
+        para_edge_stencil(mm, p.para_e[c], p.SE, ev);
         V3 ex[4];
         for (int k = 0; k < 4; ++k) ex[k] = load_vertex(p.V, p.nV, ev[k]);
         double eg[12];
         const double e = mollifier(ex, eps_x_rest(p.Vrest, p.nV, ev[0], ev[1], ev[2], ev[3]), eg, false, [](int, int, double) {});
         for (int k = 0; k < 4; ++k)
-            for (int i = 0; i < 3; ++i) atomicAdd(g + 3 * (size_t)ev[k] + i, p.kappa * b * eg[3 * k + i]);
+            for (int q = 0; q < 3; ++q) atomicAdd(g + 3 * (size_t)ev[k] + q, p.kappa * b * eg[3 * k + q]);
         w = p.kappa * e * db; // slot 3 is -1 (or a vertex id): multiplicity 1
     }
     for (int k = 0; k < s.nv; ++k)
-        for (int i = 0; i < 3; ++i) atomicAdd(g + 3 * (size_t)s.v[k] + i, w * gd[3 * k + i]);
+        for (int q = 0; q < 3; ++q) atomicAdd(g + 3 * (size_t)s.v[k] + q, w * gd[3 * k + q]);
+    }
 }
 
 // -----------------------------------------------------------------------------------------------------------
@@ -198,22 +222,34 @@ __global__ void __launch_bounds__(128) k_barrier_gradient(BarrierArgs p, double*
 //   pass 2 (warp per pair)    : parallel-order Jacobi eigen-solver on the 12x12 (6 disjoint rotations per round, 11 rounds
 //                               per sweep, the round-robin tournament schedule), clamp, rebuild, red.add into the CSR
 // -----------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64) k_barrier_hessian_build(BarrierArgs p, double* __restrict__ Hraw, int* __restrict__ rows_out)
+DEV bool owns_row(const BarrierArgs& p, int v) { return v >= p.row_lo && v < p.row_hi; }
+
+__global__ void __launch_bounds__(64) k_barrier_hessian_build(BarrierArgs p, double* __restrict__ Hraw, int* __restrict__ rows_out, int* __restrict__ n_owned,
+    int capacity, int* __restrict__ flags)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= p.nC + p.nP) return;
+    const int nC = *p.nC, nTot = nC + *p.nP;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nTot; c += gridDim.x * blockDim.x) {
     // the matrix is assembled in thread-local memory (interleaved across the warp by the hardware: every access is one coalesced
     // transaction) and shipped to its pair-major slot once at the end; read-modify-write straight on the 1152-byte-strided slots
     // cost 32 sectors per warp access
+    const bool is_para = c >= nC;
+    const int4 mm = is_para ? p.para[c - nC] : p.cs[c];
+    PairStencil s = decode(mm);
+    int rows[4];
+    {   // row ownership (multi-rank): this rank assembles the pair only if it owns a row of its stencil
+        bool mine = false;
+        if (!is_para) {
+            for (int k = 0; k < 4; ++k) rows[k] = (k < s.nv) ? s.v[k] : -1;
+        }
+        else para_edge_stencil(mm, p.para_e[c - nC], p.SE, rows);
+        for (int k = 0; k < 4; ++k) mine = mine || (rows[k] >= 0 && owns_row(p, rows[k]));
+        if (!mine) continue;
+    }
     double H[144];
 #define HE(i, j) H[(i) * 12 + (j)]
     for (int i = 0; i < 144; ++i) H[i] = 0.0;
-    const bool is_para = c >= p.nC;
-    const int4 mm = is_para ? p.para[c - p.nC] : p.cs[c];
-    PairStencil s = decode(mm);
     V3 x[4];
     for (int k = 0; k < s.nv; ++k) x[k] = load_vertex(p.V, p.nV, s.v[k]);
-    int rows[4];
     if (!is_para) {
         const int n = 3 * s.nv;
         double gd[12];
@@ -223,12 +259,11 @@ __global__ void __launch_bounds__(64) k_barrier_hessian_build(BarrierArgs p, dou
         const double coef = p.kappa * s.mult;
         for (int i = 0; i < n; ++i)
             for (int j = 0; j < n; ++j) HE(i, j) = ((coef * d2b) * gd[i]) * gd[j] + (coef * db) * HE(i, j);
-        for (int k = 0; k < 4; ++k) rows[k] = (k < s.nv) ? s.v[k] : -1;
     }
     else {
         // mollified pair on the two-edge stencil (:3049-3173)
         int ev[4];
-        para_edge_stencil(mm, p.para_e[c - p.nC], p.SE, ev);
+        para_edge_stencil(mm, p.para_e[c - nC], p.SE, ev);
         V3 ex[4];
         for (int k = 0; k < 4; ++k) ex[k] = load_vertex(p.V, p.nV, ev[k]);
         double gd0[12], gd[12], eg[12];
@@ -258,11 +293,25 @@ __global__ void __launch_bounds__(64) k_barrier_hessian_build(BarrierArgs p, dou
         for (int i = 0; i < 12; ++i)
             for (int j = 0; j < 12; ++j)
                 HE(i, j) = ((k * db) * gd[i]) * eg[j] + ((k * db) * gd[j]) * eg[i] + (k * b) * HE(i, j) + ((k * e * d2b) * gd[i]) * gd[j] + (k * e * db) * VE[i * 12 + j];
-        for (int q = 0; q < 4; ++q) rows[q] = ev[q];
     }
-    for (int q = 0; q < 4; ++q) rows_out[4 * (size_t)c + q] = rows[q];
-    double2* out = reinterpret_cast<double2*>(Hraw + (size_t)c * 144);
+    // compacted output slot (one atomic per warp iteration)
+    int slot;
+    {
+        const unsigned m = __activemask();
+        const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(n_owned, __popc(m));
+        base = __shfl_sync(m, base, leader);
+        slot = base + __popc(m & ((1u << lane) - 1u));
+    }
+    if (slot >= capacity) {
+        atomicExch(flags + FLAG_SET_CAPACITY, 1);
+        continue;
+    }
+    for (int q = 0; q < 4; ++q) rows_out[4 * (size_t)slot + q] = rows[q];
+    double2* out = reinterpret_cast<double2*>(Hraw + (size_t)slot * 144);
     for (int i = 0; i < 72; ++i) out[i] = make_double2(H[2 * i], H[2 * i + 1]);
+    }
 #undef HE
 }
 
@@ -326,13 +375,15 @@ DEV void reduced_column(const double* __restrict__ H0, int j, double* col /* 10 
     col[9] = 0.0;
 }
 
-__global__ void __launch_bounds__(32 * kProjWarps) k_barrier_hessian_project(int n, double* __restrict__ H, int* __restrict__ psd)
+__global__ void __launch_bounds__(32 * kProjWarps) k_barrier_hessian_project(const int* __restrict__ n_ptr, int capacity, double* __restrict__ H, int* __restrict__ psd)
 {
     constexpr int N = kProjN, G = kProjG;
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int grp = lane / G, k = lane - G * grp, base = G * grp;
-    const int warp = blockIdx.x * kProjWarps + (threadIdx.x >> 5);
+    const int n = min(*n_ptr, capacity);
+    const int nwarps = gridDim.x * kProjWarps;
+    for (int warp = blockIdx.x * kProjWarps + (threadIdx.x >> 5); warp * kProjPerWarp < n; warp += nwarps) { // warp-uniform trip count
     const int c = warp * kProjPerWarp + grp;
     bool live = grp < kProjPerWarp && c < n;
     double AT[N], AB[N], VT[N], VB[N];
@@ -462,17 +513,19 @@ __global__ void __launch_bounds__(32 * kProjWarps) k_barrier_hessian_project(int
             }
         }
     }
+    __syncwarp();
+    }
 }
 
 // scatter of the projected pair Hessians into the CSR values (upper-triangular 3x3 blocks, LinSysSolver.hpp:207-265)
 constexpr int kScatWarps = 8;
-__global__ void __launch_bounds__(32 * kScatWarps) k_barrier_hessian_scatter(BarrierArgs p, const double* __restrict__ H, const int* __restrict__ rows_in,
-    const int* __restrict__ psd, double* __restrict__ a, int* __restrict__ err)
+__global__ void __launch_bounds__(32 * kScatWarps) k_barrier_hessian_scatter(BarrierArgs p, const int* __restrict__ n_ptr, int capacity, const double* __restrict__ H,
+    const int* __restrict__ rows_in, const int* __restrict__ psd, double* __restrict__ a, int* __restrict__ err)
 {
     __shared__ int sOff[kScatWarps][48];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int c = blockIdx.x * kScatWarps + wib;
-    if (c >= p.nC + p.nP) return;
+    const int n = min(*n_ptr, capacity);
+    for (int c = blockIdx.x * kScatWarps + wib; c < n; c += gridDim.x * kScatWarps) {
     const double* H0 = H + (size_t)c * 144;
     const bool raw = psd[c] != 0; // makePD returned its input: the slot still holds the unprojected 12x12
     // CSR offsets of the 16 vertex blocks x 3 rows (upper-triangular blocks only); -1 = skip, -2 = missing in the pattern
@@ -483,7 +536,7 @@ __global__ void __launch_bounds__(32 * kScatWarps) k_barrier_hessian_scatter(Bar
         const int bi = t / 12, bj = (t / 3) % 4, r = t % 3;
         int o = -1;
         const int vi = rows[bi], vj = rows[bj];
-        if (vi >= 0 && vj >= 0 && vi <= vj && !(vi == vj && bi != bj) && !proj_dbc(p.dbc, vi, p.projectDBC) && !proj_dbc(p.dbc, vj, p.projectDBC)) {
+        if (vi >= 0 && vj >= 0 && vi <= vj && !(vi == vj && bi != bj) && owns_row(p, vi) && !proj_dbc(p.dbc, vi, p.projectDBC) && !proj_dbc(p.dbc, vj, p.projectDBC)) {
             const int c0 = (vi == vj) ? r : 0;
             o = csr_find(p.ia, p.ja, p.base, 3 * vi + r, 3 * vj + c0);
             if (o < 0) o = -2;
@@ -517,29 +570,26 @@ __global__ void __launch_bounds__(32 * kScatWarps) k_barrier_hessian_scatter(Bar
             }
         }
     }
+    __syncwarp(); // sOff is reused by the next slot of this warp
+    }
 }
 
 // -----------------------------------------------------------------------------------------------------------
 void barrier_energy(const BarrierArgs& p, double* partials, int* bad, cudaStream_t st)
 {
-    const int n = p.nC + p.nP;
-    if (n > 0) k_barrier_energy<<<(n + 255) / 256, 256, 0, st>>>(p, partials, bad);
+    k_barrier_energy<<<kBarrierEnergyBlocks, 256, 0, st>>>(p, partials, bad);
 }
-int barrier_energy_blocks(int n) { return (n + 255) / 256; }
+int barrier_energy_blocks() { return kBarrierEnergyBlocks; }
 void barrier_gradient(const BarrierArgs& p, double* g, cudaStream_t st)
 {
-    const int n = p.nC + p.nP;
-    if (n > 0) k_barrier_gradient<<<(n + 127) / 128, 128, 0, st>>>(p, g);
+    k_barrier_gradient<<<kSMs * 4, 128, 0, st>>>(p, g);
 }
-void barrier_hessian(const BarrierArgs& p, double* a, int* err, double* Hraw, int* rows, cudaStream_t st)
+void barrier_hessian(const BarrierArgs& p, double* a, int* flags, double* Hraw, int* rows, int* psd, int* n_owned, int capacity, cudaStream_t st)
 {
-    const int n = p.nC + p.nP;
-    if (n <= 0) return;
-    k_barrier_hessian_build<<<(n + 63) / 64, 64, 0, st>>>(p, Hraw, rows);
-    const int per_cta = kProjWarps * kProjPerWarp;
-    int* psd = rows + (size_t)4 * n; // one flag per pair behind the row ids
-    k_barrier_hessian_project<<<(n + per_cta - 1) / per_cta, 32 * kProjWarps, 0, st>>>(n, Hraw, psd);
-    k_barrier_hessian_scatter<<<(n + kScatWarps - 1) / kScatWarps, 32 * kScatWarps, 0, st>>>(p, Hraw, rows, psd, a, err);
+    cudaMemsetAsync(n_owned, 0, sizeof(int), st);
+    k_barrier_hessian_build<<<kSMs * 8, 64, 0, st>>>(p, Hraw, rows, n_owned, capacity, flags);
+    k_barrier_hessian_project<<<kSMs * 4, 32 * kProjWarps, 0, st>>>(n_owned, capacity, Hraw, psd);
+    k_barrier_hessian_scatter<<<kSMs * 4, 32 * kScatWarps, 0, st>>>(p, n_owned, capacity, Hraw, rows, psd, a, flags + FLAG_PATTERN);
 }
 
 } // namespace ipcgpu

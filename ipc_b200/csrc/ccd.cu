@@ -30,30 +30,27 @@ namespace ipcgpu {
 // ------------------------------------------------------------------------------------------------------------------
 // reference voxel ranges of every surface vertex on the swept grid (SpatialHash.hpp:642-662, :841-845)
 // ------------------------------------------------------------------------------------------------------------------
-struct RefGrid {
-    double lo[3];
-    double inv_h;
-};
-
-__global__ void __launch_bounds__(256) k_ref_ranges(SurfArgs s, const double* __restrict__ dir, double alpha, RefGrid g, int* __restrict__ vmin, int* __restrict__ vmax)
+__global__ void __launch_bounds__(256) k_ref_ranges(SurfArgs s, const double* __restrict__ dir, const IterState* __restrict__ st, int* __restrict__ vmin, int* __restrict__ vmax)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= s.nSV) return;
+    const double alpha = st->alpha_grid, inv_h = st->ref_inv_h;
     const int v = s.SVI[i];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         const double x = s.V[(size_t)c * s.nV + v];
         const double xt = x + alpha * dir[3 * (size_t)v + c];
-        const int a = (int)floor((x - g.lo[c]) * g.inv_h), b = (int)floor((xt - g.lo[c]) * g.inv_h);
+        const int a = (int)floor((x - st->ref_lo[c]) * inv_h), b = (int)floor((xt - st->ref_lo[c]) * inv_h);
         vmin[3 * (size_t)v + c] = min(a, b);
         vmax[3 * (size_t)v + c] = max(a, b);
     }
 }
 
 // bbox of all vertices (V) and of the displaced surface vertices: bounds[0..2] min, [3..5] max (flipped-order uint64)
-__global__ void __launch_bounds__(256) k_swept_bounds(SurfArgs s, const double* __restrict__ dir, double alpha, unsigned long long* __restrict__ bounds)
+__global__ void __launch_bounds__(256) k_swept_bounds(SurfArgs s, const double* __restrict__ dir, const IterState* __restrict__ st, unsigned long long* __restrict__ bounds)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const double alpha = st->alpha_grid;
     double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
     if (i < s.nV) {
 #pragma unroll
@@ -81,6 +78,42 @@ __global__ void __launch_bounds__(256) k_swept_bounds(SurfArgs s, const double* 
             atomicMax(bounds + 3 + c, flip_ord(b));
         }
     }
+}
+
+// SpatialHash.hpp:603-618 on the device-resident step: spanSize = alpha * mean|p| / h ; if (spanSize > 1) alpha /= spanSize.
+// (pSize is the reference's serial host sum over the surface vertices, computed when the search direction is uploaded.)
+__global__ void k_swept_alpha(IterState* st, double pSize, double h, unsigned long long* __restrict__ bounds)
+{
+    if (threadIdx.x != 0) return;
+    double alpha = ord_to_dbl(st->step_ord);
+    const double span = alpha * pSize / h;
+    if (span > 1) alpha /= span;
+    st->step_ord = dbl_to_ord(alpha);
+    st->alpha_grid = alpha;
+    st->alpha_stage[2] = alpha;
+    for (int c = 0; c < 3; ++c) { bounds[c] = ~0ull; bounds[3 + c] = 0ull; }
+}
+// reference grid geometry from the swept bbox (SpatialHash.hpp:627-640), incl. the cast-overflow fallback (:632-636)
+__global__ void k_refgrid_params(IterState* st, const unsigned long long* __restrict__ bounds, double h)
+{
+    if (threadIdx.x != 0) return;
+    double lo[3], hi[3], rmax = 0.0;
+    double inv_h = 1.0 / h;
+    bool bad = false;
+    for (int c = 0; c < 3; ++c) {
+        lo[c] = unflip_ord(bounds[c]);
+        hi[c] = unflip_ord(bounds[3 + c]);
+        st->ref_lo[c] = lo[c];
+        st->ref_count[c] = (int)ceil((hi[c] - lo[c]) * inv_h);
+        rmax = fmax(rmax, hi[c] - lo[c]);
+        if (st->ref_count[c] <= 0) bad = true;
+    }
+    if (bad) { // cast overflow due to a huge search direction
+        inv_h = 1.0 / (rmax * 1.01);
+        st->ref_count[0] = st->ref_count[1] = st->ref_count[2] = 1;
+    }
+    st->ref_inv_h = inv_h;
+    st->radius = 1.0 / inv_h; // pairs sharing a reference voxel are at most one voxel apart per axis
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -125,10 +158,11 @@ DEV void push_cand(const CandOut& o, int2 c)
 }
 
 // ---- phase 1: one WARP per query primitive, boxes only: (query, partner) pairs whose swept boxes are within one reference voxel
-__global__ void __launch_bounds__(256) k_ccd_pairs_pt(const Grid* __restrict__ gp, const Box* __restrict__ vboxes, SortedGrid tg, double radius, int first, int last, PairOut out)
+__global__ void __launch_bounds__(256) k_ccd_pairs_pt(const Grid* __restrict__ gp, const Box* __restrict__ vboxes, SortedGrid tg, const IterState* __restrict__ st, int first, int last, PairOut out)
 {
     __shared__ PairStage stage;
     pair_stage_init(stage);
+    const double radius = st->radius;
     const int lane = threadIdx.x & 31;
     const Grid g = *gp;
     const int q0 = first + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kPairQueriesPerWarp;
@@ -140,10 +174,11 @@ __global__ void __launch_bounds__(256) k_ccd_pairs_pt(const Grid* __restrict__ g
     pair_stage_flush(stage, out);
 }
 // queries are the entries of the sorted swept-edge grid itself ([first, last) = sorted positions); each walks only the entries behind it
-__global__ void __launch_bounds__(256) k_ccd_pairs_ee(const Grid* __restrict__ gp, SortedGrid eg, double radius, int first, int last, PairOut out)
+__global__ void __launch_bounds__(256) k_ccd_pairs_ee(const Grid* __restrict__ gp, SortedGrid eg, const IterState* __restrict__ st, int first, int last, PairOut out)
 {
     __shared__ PairStage stage;
     pair_stage_init(stage);
+    const double radius = st->radius;
     const int lane = threadIdx.x & 31;
     const Grid g = *gp;
     const int q0 = first + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kPairQueriesPerWarp;
@@ -322,18 +357,22 @@ struct NarrowArgs {
     SurfArgs s;
     const double* dir;
     const int2* cand;
-    unsigned long long nCand;
     double err_vf[3], err_ee[3];
-    double tol, max_t;
+    double tol;
     int max_itr;
-    const unsigned long long* best; // running device-wide minimum (ordered-uint image): boxes starting at or after it cannot lower the result
+    // device-resident: cand_range = the slice of `cand` this rank walks, max_t = the step on entry (every pair's max_t), ccd_ord = the
+    // running device-wide minimum (ordered-uint image): boxes starting at or after it cannot lower the result
+    const IterState* st;
 };
 
 __global__ void __launch_bounds__(128) k_ti_stage1(NarrowArgs a, unsigned* __restrict__ survivors, unsigned* __restrict__ nSurv, int* __restrict__ zero_flag)
 {
-    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long begin = a.st->cand_range[0], end = a.st->cand_range[1];
+    // grid-stride over whole warps (the warp-aggregated append below needs all 32 lanes)
+    for (unsigned long long base = begin + (unsigned long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < end; base += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long i = base + (threadIdx.x & 31);
     bool alive = false;
-    if (i < a.nCand) {
+    if (i < end) {
         bool vf;
         int v[4];
         TiPair P;
@@ -356,6 +395,7 @@ __global__ void __launch_bounds__(128) k_ti_stage1(NarrowArgs a, unsigned* __res
         if (lane == __ffs(m) - 1) base = atomicAdd(nSurv, __popc(m));
         base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
         if (alive) survivors[base + __popc(m & ((1u << lane) - 1))] = (unsigned)i;
+    }
     }
 }
 
@@ -925,14 +965,16 @@ __device__ int pair_ccd(bool vf, const TiPair& P, const NarrowArgs& a, DBox* buf
 {
     const double d = pair_distance_sqrt(vf, P);
     const double ms = fmin(0.2 * d, 1e-6);
-    int hit = vf ? ti_ccd<true, W>(P, a.err_vf, ms, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn, sA, sB, thread_budget, a.best)
-                 : ti_ccd<false, W>(P, a.err_ee, ms, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn, sA, sB, thread_budget, a.best);
+    const double max_t = a.st->max_t;                 // canonical semantics: every pair sees the step on entry
+    const unsigned long long* best = &a.st->ccd_ord;  // running device-wide minimum
+    int hit = vf ? ti_ccd<true, W>(P, a.err_vf, ms, a.tol, max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn, sA, sB, thread_budget, best)
+                 : ti_ccd<false, W>(P, a.err_ee, ms, a.tol, max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn, sA, sB, thread_budget, best);
     if (hit == 2) return 2;
     if (hit && toi < 1e-6) { // :759-781
         // no pruning against the running minimum here: this result is rescaled by 0.8 afterwards, so a box starting in
         // [best, 1.25 best) can still lower the global step (the exactness argument of ti_root_finder only covers unscaled results)
-        hit = vf ? ti_ccd<true, W>(P, a.err_vf, 0.0, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn, sA, sB, thread_budget, nullptr)
-                 : ti_ccd<false, W>(P, a.err_ee, 0.0, a.tol, a.max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn, sA, sB, thread_budget, nullptr);
+        hit = vf ? ti_ccd<true, W>(P, a.err_vf, 0.0, a.tol, max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn, sA, sB, thread_budget, nullptr)
+                 : ti_ccd<false, W>(P, a.err_ee, 0.0, a.tol, max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn, sA, sB, thread_budget, nullptr);
         if (hit == 2) return 2;
         if (hit) toi *= 0.8;
     }
@@ -1014,14 +1056,49 @@ __global__ void __launch_bounds__(128, 3) k_ti_stage2(NarrowArgs a, const unsign
     }
 }
 
-__global__ void k_ccd_init(unsigned long long* min_ord, double alpha, unsigned* nSurv, unsigned* work, int* flags)
+// start of a narrow phase: snapshot the device-resident step as max_t and as the initial running minimum, fix this rank's slice of the
+// candidate list (n32 / n64: the list size, wherever the producing stage left it), clear the per-phase counters
+__global__ void k_ccd_init(IterState* st, const int* __restrict__ n32, const unsigned long long* __restrict__ n64, unsigned long long cap, int rank, int nranks, int share,
+    double seed, unsigned* nSurv, unsigned* work, int* flags)
 {
-    if (threadIdx.x == 0) {
-        *min_ord = dbl_to_ord(alpha);
-        *nSurv = 0;
-        *work = 0;
-        for (int q = 0; q < 12; ++q) flags[q] = 0; // zero distance, warnings, deferred count, pad, boxes(thread pass) x2, boxes(warp pass) x2
+    if (threadIdx.x != 0) return;
+    const double alpha = ord_to_dbl(st->step_ord);
+    st->max_t = alpha;
+    st->ccd_ord = (seed >= 0.0 && seed < alpha) ? dbl_to_ord(seed) : st->step_ord; // (seed: test hook, ipcgpu_ccd_debug_seed_bound)
+    unsigned long long n = n32 ? (unsigned long long)max(*n32, 0) : *n64;
+    if (n > cap) n = cap; // an overflowing producer raised its capacity flag; stay inside the list
+    st->cand_range[0] = share ? n * rank / nranks : 0ull;
+    st->cand_range[1] = share ? n * (rank + 1) / nranks : n;
+    *nSurv = 0;
+    *work = 0;
+    for (int q = 0; q < 12; ++q) flags[q] = 0; // zero distance, warnings, deferred count, pad, boxes(thread pass) x2, boxes(warp pass) x2
+}
+// end of a narrow phase (this rank): a zero initial distance forces the step to 0 (:730-737); diagnostics go to the iteration state
+__global__ void k_ccd_finish(IterState* st, const unsigned* __restrict__ nSurv, const int* __restrict__ flags, const int* __restrict__ overflow, int is_full)
+{
+    if (threadIdx.x != 0) return;
+    if (flags[0]) {
+        st->ccd_ord = 0ull;
+        st->flags[FLAG_ZERO_CCD_DISTANCE] = 1;
     }
+    if (overflow && *overflow) st->flags[FLAG_CCD_CAPACITY] = 1;
+    st->flags[FLAG_TI_WARNINGS] += flags[1];
+    st->ccd_stats[0] = *nSurv;
+    st->ccd_stats[1] = (unsigned long long)flags[1];
+    st->ccd_stats[2] = (unsigned)flags[2];
+    st->ccd_stats[3] = (unsigned long long)(unsigned)flags[4] << 6;
+    st->ccd_stats[4] = (unsigned long long)(unsigned)flags[5] << 6;
+    st->ccd_stats[5] = *reinterpret_cast<const unsigned long long*>(flags + 6);
+    st->ccd_stats[6] = *reinterpret_cast<const unsigned long long*>(flags + 8);
+    st->ccd_stats[7] = st->cand_range[1] - st->cand_range[0];
+    if (is_full) st->n_full_cand = st->ccd_stats[7];
+}
+// after the cross-rank min: the narrow phase's minimum becomes the step
+__global__ void k_ccd_commit(IterState* st, int stage)
+{
+    if (threadIdx.x != 0) return;
+    st->step_ord = st->ccd_ord;
+    st->alpha_stage[stage] = ord_to_dbl(st->ccd_ord);
 }
 
 } // namespace ipcgpu
@@ -1039,7 +1116,7 @@ using namespace ipcgpu;
 
 static inline int nblk(long long n, int b) { return (int)((n + b - 1) / b); }
 SurfArgs surf_args(const ipcgpu_ctx* ctx); // constraint.cu
-int boxes_and_grid(ipcgpu_ctx* ctx, const double* dir, double alpha, double radius, bool with_vertex_boxes); // constraint.cu
+int boxes_and_grid(ipcgpu_ctx* ctx, const double* dir, const double* alpha_ptr, double radius, const double* radius_ptr, bool with_vertex_boxes); // constraint.cu
 
 constexpr int kStage2WarpsPerCta = 4;
 constexpr int kStage2Ctas = 148 * 6; // persistent: 6 CTAs x 4 warps per SM
@@ -1058,8 +1135,15 @@ int ccd_alloc(ipcgpu_ctx* ctx)
     return 0;
 }
 
-// narrow phase over a device candidate list; alpha_inout is the step bound
-int ccd_narrow(ipcgpu_ctx* ctx, const int2* cand, unsigned long long nCand, double tol, const double* err_vf, const double* err_ee, double* alpha_inout)
+// cross-rank min of the running minimum (api.cu; no-op on one rank)
+int nccl_min_u64(ipcgpu_ctx* ctx, unsigned long long* word);
+int fetch_iter_state(ipcgpu_ctx* ctx); // api.cu: one D2H copy of the iteration state + stream synchronisation
+
+// Narrow phase over a device-resident candidate list.  The step is read from and written back to the device-resident iteration state
+// (IterState::step_ord): nothing is read back here.  n32 / n64: device-resident list size; share: walk only this rank's contiguous
+// slice of the list (replicated lists) or all of it (lists that are already this rank's own); stage: 1 = partial, 3 = full CCD.
+int ccd_narrow(ipcgpu_ctx* ctx, const int2* cand, const int* n32, const unsigned long long* n64, unsigned long long cap, int share, double tol, const double* err_vf,
+    const double* err_ee, int stage, const int* overflow)
 {
     CcdWork& w = ctx->ccd;
     cudaStream_t st = ctx->stream;
@@ -1067,125 +1151,86 @@ int ccd_narrow(ipcgpu_ctx* ctx, const int2* cand, unsigned long long nCand, doub
     a.s = surf_args(ctx);
     a.dir = ctx->dir.p;
     a.cand = cand;
-    a.nCand = nCand;
     for (int c = 0; c < 3; ++c) { a.err_vf[c] = err_vf[c]; a.err_ee[c] = err_ee[c]; }
     a.tol = tol;
-    a.max_t = *alpha_inout; // canonical semantics: every pair sees the step on entry
     a.max_itr = 1000000;    // TIGHT_INCLUSION_MAX_ITER (CCDUtils.hpp:14)
-    a.best = ctx->min_ord.p;
+    a.st = ctx->iter.p;
+    IterState* ist = ctx->iter.p;
     unsigned* nSurv = reinterpret_cast<unsigned*>(w.counters.p);
     unsigned* work = nSurv + 1;
-    int* flags = w.counters.p + 2; // [0] zero distance, [1] warnings, [2] spare
+    int* flags = w.counters.p + 2; // [0] zero distance, [1] warnings, [2] deferred, [4] longest, [5] total cycles, [6..7] / [8..9] boxes
     static const int wide_env = [] { const char* e = std::getenv("IPCGPU_TI_WIDE_LEVEL"); return e ? std::atoi(e) : 0; }();
     if (wide_env > 0 && !w.wide_level_set) {
         CKD(cudaMemcpyToSymbolAsync(c_wide_level, &wide_env, sizeof(int), 0, cudaMemcpyHostToDevice, st));
         w.wide_level_set = true;
     }
     cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_CCD_NARROW);
-    k_ccd_init<<<1, 32, 0, st>>>(ctx->min_ord.p, *alpha_inout, nSurv, work, flags);
-    if (nCand > 0) {
-        cudaEvent_t pe1 = ctx->prof_begin(IPCGPU_STAGE_CCD_ROOT_FILTER);
-        k_ti_stage1<<<nblk((long long)nCand, 128), 128, 0, st>>>(a, w.surv.p, nSurv, flags);
-        ctx->prof_end(pe1);
-        // the survivor count lives on the device; the thread-level pass is launched over the candidate count (extra threads exit)
-        // pass A (thread per pair, 10-box budget): the shallow majority dies here without holding its warp hostage;
+    k_ccd_init<<<1, 32, 0, st>>>(ist, n32, n64, cap, ctx->rank, ctx->nranks, share, ctx->debug_prune_seed, nSurv, work, flags);
+    {
+        // the candidate count lives on the device: every pass is a grid-stride / persistent kernel that reads it there
+        // pass 1 (thread per candidate): the root box only;
+        // pass A (thread per survivor, 10-box budget): the shallow majority dies here without holding its warp hostage;
         // pass B (warp per pair, corner-parallel box evaluation): the deep searches, compacted.
         // (a three-tier split -- 3-box, then 12-box thread passes -- was measured slower: the per-pair set-up dominates pass A)
+        cudaEvent_t pe1 = ctx->prof_begin(IPCGPU_STAGE_CCD_ROOT_FILTER);
+        k_ti_stage1<<<kSMs * 16, 128, 0, st>>>(a, w.surv.p, nSurv, flags);
+        ctx->prof_end(pe1);
         unsigned* nDefA = reinterpret_cast<unsigned*>(flags + 2);
-        const int gridA = std::min(nblk((long long)nCand, 128), 148 * 16);
-        k_ti_stage15<<<gridA, 128, 0, st>>>(a, w.surv.p, nSurv, w.surv2.p, nDefA, 10, ctx->min_ord.p, flags + 1);
-        k_ti_stage2<<<kStage2Ctas, 32 * kStage2WarpsPerCta, 0, st>>>(a, w.surv2.p, nDefA, work, reinterpret_cast<DBox*>(w.scratch.p), kLevelCap, ctx->min_ord.p, flags + 1);
+        k_ti_stage15<<<kSMs * 16, 128, 0, st>>>(a, w.surv.p, nSurv, w.surv2.p, nDefA, 10, &ist->ccd_ord, flags + 1);
+        k_ti_stage2<<<kStage2Ctas, 32 * kStage2WarpsPerCta, 0, st>>>(a, w.surv2.p, nDefA, work, reinterpret_cast<DBox*>(w.scratch.p), kLevelCap, &ist->ccd_ord, flags + 1);
     }
+    k_ccd_finish<<<1, 32, 0, st>>>(ist, nSurv, flags, overflow, stage == 3);
     ctx->prof_end(pe);
-    ctx->launches += 4;
+    ctx->launches += 5;
     CKD(cudaGetLastError());
-    if (ctx->nranks > 1) {
-        // min over ranks of the step (and max of the zero-distance flag) is done by the caller through NCCL (api.cu)
-    }
-    unsigned long long* h = reinterpret_cast<unsigned long long*>(ctx->h_scalar);
-    int* hi = reinterpret_cast<int*>(ctx->h_scalar + 2);
-    CKD(cudaMemcpyAsync(h, ctx->min_ord.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    CKD(cudaMemcpyAsync(hi, w.counters.p, 12 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CKD(cudaStreamSynchronize(st));
-    double m;
-    std::memcpy(&m, h, sizeof(double));
-    w.last_survivors = (unsigned)hi[0];
-    w.last_warnings = hi[3];
-    w.last_deferred = (unsigned)hi[4];
-    w.last_longest_cycles = (unsigned long long)(unsigned)hi[6] << 6;
-    w.last_total_cycles = (unsigned long long)(unsigned)hi[7] << 6;
-    std::memcpy(&w.last_boxes_thread, hi + 8, 8);
-    std::memcpy(&w.last_boxes_warp, hi + 10, 8);
-    w.last_candidates = nCand;
-    if (hi[2]) *alpha_inout = 0.0; // zero initial distance
-    else *alpha_inout = m;
+    int rc = nccl_min_u64(ctx, &ist->ccd_ord); // min over ranks of the step; a zero-distance flag travels as step 0
+    if (rc) return rc;
+    k_ccd_commit<<<1, 32, 0, st>>>(ist, stage);
+    ++ctx->launches;
+    return 0;
+}
+
+// sync-mode helper shared by the three step-bound entry points: copy the iteration state back and refresh the host-side diagnostics
+int ccd_read_back(ipcgpu_ctx* ctx, double* alpha_out)
+{
+    int rc = fetch_iter_state(ctx);
+    if (rc) return rc;
+    CcdWork& w = ctx->ccd;
+    const IterState& h = *ctx->h_iter;
+    w.last_survivors = (unsigned)h.ccd_stats[0];
+    w.last_warnings = (int)h.ccd_stats[1];
+    w.last_deferred = h.ccd_stats[2];
+    w.last_longest_cycles = h.ccd_stats[3];
+    w.last_total_cycles = h.ccd_stats[4];
+    w.last_boxes_thread = h.ccd_stats[5];
+    w.last_boxes_warp = h.ccd_stats[6];
+    w.last_candidates = h.ccd_stats[7];
+    if (alpha_out) std::memcpy(alpha_out, &h.step_ord, sizeof(double));
     return 0;
 }
 
 // ---- swept hash build: SpatialHash::build(mesh, searchDir, curMaxStepSize, voxelSize) ------------------------------------
-int ccd_build_swept(ipcgpu_ctx* ctx, const double* p_host, double* alpha_inout, double h)
+// Entirely on the stream: the span rescale of the step (:603-618), the swept bbox, the reference grid geometry and the coarse
+// accelerator grid all take their inputs from the device-resident iteration state.
+int ccd_build_swept(ipcgpu_ctx* ctx, double h)
 {
     CcdWork& w = ctx->ccd;
     cudaStream_t st = ctx->stream;
     const SurfArgs s = surf_args(ctx);
-    if (p_host) {
-        ctx->h_dir.assign(p_host, p_host + (size_t)3 * ctx->nV);
-        CKD(cudaMemcpyAsync(ctx->dir.p, p_host, (size_t)3 * ctx->nV * sizeof(double), cudaMemcpyHostToDevice, st));
-    }
-    if (ctx->h_dir.size() != (size_t)3 * ctx->nV) {
-        ctx->err = "no search direction: pass p (or call ipcgpu_step_forward with p first)";
+    IterState* ist = ctx->iter.p;
+    if (!ctx->dir_valid) {
+        ctx->err = "no search direction: pass p (or call ipcgpu_set_search_dir first)";
         return IPCGPU_ERR_STATE;
     }
-    // :603-618 -- serial sum in the reference; kept on the host in the same order so that alpha is bit-identical
-    double pSize = 0;
-    const double* p = ctx->h_dir.data();
-    for (int i = 0; i < ctx->nSV; ++i) {
-        const int v = ctx->h_SVI[i];
-        pSize += std::abs(p[3 * (size_t)v]);
-        pSize += std::abs(p[3 * (size_t)v + 1]);
-        pSize += std::abs(p[3 * (size_t)v + 2]);
-    }
-    pSize /= (double)((long long)ctx->nSV * 3);
-    const double span = *alpha_inout * pSize / h;
-    if (span > 1) *alpha_inout /= span;
-    const double alpha = *alpha_inout;
     cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_CCD_BROAD);
+    k_swept_alpha<<<1, 32, 0, st>>>(ist, ctx->pSize, h, w.bounds.p);
     // bbox of V and of the displaced surface vertices (:627-628)
-    const unsigned long long init[6] = { ~0ull, ~0ull, ~0ull, 0ull, 0ull, 0ull };
-    CKD(cudaMemcpyAsync(w.bounds.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
-    k_swept_bounds<<<nblk(std::max(s.nV, s.nSV), 256), 256, 0, st>>>(s, ctx->dir.p, alpha, w.bounds.p);
-    unsigned long long* hb = reinterpret_cast<unsigned long long*>(ctx->h_scalar);
-    CKD(cudaMemcpyAsync(hb, w.bounds.p, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    CKD(cudaStreamSynchronize(st));
-    double lo[3], hi[3];
-    for (int c = 0; c < 3; ++c) {
-        unsigned long long a = hb[c], b = hb[3 + c];
-        a = (a >> 63) ? (a & 0x7fffffffffffffffull) : ~a;
-        b = (b >> 63) ? (b & 0x7fffffffffffffffull) : ~b;
-        std::memcpy(&lo[c], &a, 8);
-        std::memcpy(&hi[c], &b, 8);
-    }
-    w.ref_inv_h = 1.0 / h;
-    double rmax = 0;
-    bool bad = false;
-    for (int c = 0; c < 3; ++c) {
-        w.ref_lo[c] = lo[c];
-        w.ref_count[c] = (int)std::ceil((hi[c] - lo[c]) * w.ref_inv_h);
-        rmax = std::max(rmax, hi[c] - lo[c]);
-        if (w.ref_count[c] <= 0) bad = true;
-    }
-    if (bad) { // cast overflow due to a huge search direction (:632-636)
-        w.ref_inv_h = 1.0 / (rmax * 1.01);
-        w.ref_count[0] = w.ref_count[1] = w.ref_count[2] = 1;
-    }
-    w.alpha_grid = alpha;
-    RefGrid g;
-    for (int c = 0; c < 3; ++c) g.lo[c] = w.ref_lo[c];
-    g.inv_h = w.ref_inv_h;
-    if (s.nSV > 0) k_ref_ranges<<<nblk(s.nSV, 256), 256, 0, st>>>(s, ctx->dir.p, alpha, g, w.vmin.p, w.vmax.p);
-    ctx->launches += 2;
+    k_swept_bounds<<<nblk(std::max(s.nV, s.nSV), 256), 256, 0, st>>>(s, ctx->dir.p, ist, w.bounds.p);
+    k_refgrid_params<<<1, 32, 0, st>>>(ist, w.bounds.p, h);
+    if (s.nSV > 0) k_ref_ranges<<<nblk(s.nSV, 256), 256, 0, st>>>(s, ctx->dir.p, ist, w.vmin.p, w.vmax.p);
+    ctx->launches += 4;
     // coarse accelerator grid over the swept boxes; pairs sharing a reference voxel are at most one voxel apart per axis
-    int rc = boxes_and_grid(ctx, ctx->dir.p, alpha, 1.0 / w.ref_inv_h, true);
+    int rc = boxes_and_grid(ctx, ctx->dir.p, &ist->alpha_grid, 0.0, &ist->radius, true);
     ctx->prof_end(pe);
     if (rc) return rc;
     CKD(cudaGetLastError());
@@ -1193,17 +1238,17 @@ int ccd_build_swept(ipcgpu_ctx* ctx, const double* p_host, double* alpha_inout, 
     return 0;
 }
 
-int ccd_full(ipcgpu_ctx* ctx, double tol, const double* err_vf, const double* err_ee, double* alpha_inout, unsigned long long* nCandOut)
+int ccd_full(ipcgpu_ctx* ctx, double tol, const double* err_vf, const double* err_ee)
 {
     CcdWork& w = ctx->ccd;
     ContactWork& cw = ctx->cw;
     cudaStream_t st = ctx->stream;
     const SurfArgs s = surf_args(ctx);
+    IterState* ist = ctx->iter.p;
     cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_CCD_BROAD);
     CKD(cudaMemsetAsync(w.ncand.p, 0, 2 * sizeof(unsigned long long), st));
     CKD(cudaMemsetAsync(w.counters.p + 14, 0, sizeof(int), st));
     CandOut out{ w.cand.p, w.ncand.p, (unsigned long long)ctx->ccd_capacity, w.counters.p + 14 };
-    const double radius = 1.0 / w.ref_inv_h;
     // multi-GPU: every rank sweeps a contiguous share of the query primitives (the reference's own loop decomposition, :1385, :1498)
     const int v0 = (int)((long long)s.nSV * ctx->rank / ctx->nranks), v1 = (int)((long long)s.nSV * (ctx->rank + 1) / ctx->nranks);
     const int e0 = (int)((long long)s.nSE * ctx->rank / ctx->nranks), e1 = (int)((long long)s.nSE * (ctx->rank + 1) / ctx->nranks);
@@ -1212,26 +1257,17 @@ int ccd_full(ipcgpu_ctx* ctx, double tol, const double* err_vf, const double* er
     unsigned* nPairs = reinterpret_cast<unsigned*>(cw.counters.p + 8);
     PairOut ppt{ cw.bp_pairs.p, nPairs, (unsigned)cw.bp_cap, w.counters.p + 14 }, pee{ cw.bp_pairs.p + cw.bp_cap, nPairs + 1, (unsigned)cw.bp_cap, w.counters.p + 14 };
     if (v1 > v0 && s.nSF > 0) {
-        k_ccd_pairs_pt<<<nblk(v1 - v0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(cw.grid.p, cw.vbox.p, tg, radius, v0, v1, ppt);
+        k_ccd_pairs_pt<<<nblk(v1 - v0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(cw.grid.p, cw.vbox.p, tg, ist, v0, v1, ppt);
         k_ccd_filter_pt<<<nblk((long long)cw.bp_cap, 256), 256, 0, st>>>(s, ppt.pairs, ppt.n, w.vmin.p, w.vmax.p, out);
+        ctx->launches += 2;
     }
     if (e1 > e0 && s.nSE > 1) {
-        k_ccd_pairs_ee<<<nblk(e1 - e0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(cw.grid.p, eg, radius, e0, e1, pee);
+        k_ccd_pairs_ee<<<nblk(e1 - e0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(cw.grid.p, eg, ist, e0, e1, pee);
         k_ccd_filter_ee<<<nblk((long long)cw.bp_cap, 256), 256, 0, st>>>(s, pee.pairs, pee.n, w.vmin.p, w.vmax.p, out);
+        ctx->launches += 2;
     }
-    ctx->launches += 2;
-    ctx->launches += 2;
-    unsigned long long* hn = reinterpret_cast<unsigned long long*>(ctx->h_scalar);
-    int* ho = reinterpret_cast<int*>(ctx->h_scalar + 2);
-    CKD(cudaMemcpyAsync(hn, w.ncand.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    CKD(cudaMemcpyAsync(ho, w.counters.p + 14, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CKD(cudaStreamSynchronize(st));
     ctx->prof_end(pe);
-    if (*ho) {
-        ctx->err = "CCD candidate capacity exceeded (raise it with ipcgpu_set_ccd_capacity)";
-        return IPCGPU_ERR_CAPACITY;
-    }
-    const unsigned long long nCand = *hn;
-    if (nCandOut) *nCandOut = nCand;
-    return ccd_narrow(ctx, w.cand.p, nCand, tol, err_vf, err_ee, alpha_inout);
+    // the candidate list is this rank's own (its share of the queries produced it): no further slicing; the list size and the
+    // capacity flag stay on the device (checked at ipcgpu_fetch_iteration / by the synchronous wrapper)
+    return ccd_narrow(ctx, w.cand.p, nullptr, w.ncand.p, (unsigned long long)ctx->ccd_capacity, 0, tol, err_vf, err_ee, 3, w.counters.p + 14);
 }

@@ -40,9 +40,10 @@ DEV Box empty_box()
 }
 
 // prim: 0 = surface vertices, 1 = edges, 2 = triangles.  swept: include x + alpha*dir
-__global__ void __launch_bounds__(256) k_boxes(SurfArgs s, int prim, const double* __restrict__ dir, double alpha, Box* __restrict__ boxes,
+__global__ void __launch_bounds__(256) k_boxes(SurfArgs s, int prim, const double* __restrict__ dir, const double* __restrict__ alpha_ptr, Box* __restrict__ boxes,
     unsigned long long* __restrict__ bounds)
 {
+    const double alpha = alpha_ptr ? *alpha_ptr : 0.0; // sweep length: device resident (IterState::alpha_grid)
     const int n = prim == 0 ? s.nSV : (prim == 1 ? s.nSE : s.nSF);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     Box b = empty_box();
@@ -88,9 +89,10 @@ __global__ void k_bounds_init(unsigned long long* bounds)
     else if (threadIdx.x < 7) bounds[threadIdx.x] = 0ull;
 }
 
-__global__ void k_grid_params(const unsigned long long* __restrict__ bounds, double radius, Grid* __restrict__ g)
+__global__ void k_grid_params(const unsigned long long* __restrict__ bounds, double radius_val, const double* __restrict__ radius_ptr, Grid* __restrict__ g)
 {
     if (threadIdx.x != 0) return;
+    const double radius = radius_ptr ? *radius_ptr : radius_val;
     double lo[3], hi[3];
     for (int a = 0; a < 3; ++a) { lo[a] = unflip_ord(bounds[a]) - radius; hi[a] = unflip_ord(bounds[3 + a]) + radius; }
     double ext = unflip_ord(bounds[6]);
@@ -357,19 +359,89 @@ __global__ void k_merge_dups(int n, const int4* __restrict__ sorted, int4* __res
 // sort-free variant of the same merge for meshes below 2^21 vertices: (x,y,z) packs into one 64-bit key, an open-addressing table
 // counts the multiplicities (2 short kernels instead of 16 radix passes over a list of a few thousand entries)
 DEV unsigned long long dup_key(int4 v) { return ((unsigned long long)(unsigned)(-v.x - 1) << 42) | ((unsigned long long)(unsigned)v.y << 21) | (unsigned long long)(unsigned)(v.z + 1); }
-__global__ void k_dup_insert(int n, const int4* __restrict__ dup, unsigned long long* __restrict__ tab_key, int* __restrict__ tab_cnt, unsigned mask)
+__global__ void k_dup_insert(const int* __restrict__ n_ptr, int cap, const int4* __restrict__ dup, unsigned long long* __restrict__ tab_key, int* __restrict__ tab_cnt,
+    unsigned mask, int* __restrict__ overflow)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const unsigned long long key = dup_key(dup[i]);
-    unsigned h = (unsigned)((key * 0x9E3779B97F4A7C15ull) >> 40) & mask;
-    for (;;) {
-        const unsigned long long old = atomicCAS(tab_key + h, ~0ull, key);
-        if (old == ~0ull || old == key) {
-            atomicAdd(tab_cnt + h, 1);
+    const int n = min(*n_ptr, cap); // the list size stays on the device
+    if (2ll * n > (long long)mask + 1) { // the table must stay at most half full
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicExch(overflow, 1);
+        return;
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned long long key = dup_key(dup[i]);
+        unsigned h = (unsigned)((key * 0x9E3779B97F4A7C15ull) >> 40) & mask;
+        for (;;) {
+            const unsigned long long old = atomicCAS(tab_key + h, ~0ull, key);
+            if (old == ~0ull || old == key) {
+                atomicAdd(tab_cnt + h, 1);
+                break;
+            }
+            h = (h + 1) & mask;
+        }
+    }
+}
+// sizes of the finished lists -> the iteration state (read back once per iteration by ipcgpu_fetch_iteration)
+__global__ void k_publish_counts(const int* __restrict__ counters, int wantCand, IterState* __restrict__ st)
+{
+    if (threadIdx.x != 0) return;
+    st->n_set[0] = counters[0];
+    st->n_set[1] = counters[2];
+    st->n_set[2] = wantCand ? counters[3] : 0;
+    if (counters[4]) st->flags[FLAG_SET_CAPACITY] = 1;
+}
+
+// ---- multi-rank exchange of the (small) pair lists: every rank packs [header | active | mollified | (eI,eJ)] into one fixed-size
+// message, one ncclAllGather moves all of them, and every rank rebuilds the GLOBAL lists (rank-major order) from the N messages.
+// Message layout in int4 units: [0] = (nAct, nPara, 0, 0); [1, 1+xcap) active; [1+xcap, 1+2 xcap) mollified; then xcap int2.
+__global__ void __launch_bounds__(256) k_pack_lists(const int4* __restrict__ act, const int4* __restrict__ para, const int2* __restrict__ para_e, const int* __restrict__ counters,
+    int xcap, int4* __restrict__ msg, int* __restrict__ overflow)
+{
+    const int nA = counters[0], nP = counters[2];
+    if (nA > xcap || nP > xcap) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            atomicExch(overflow, 1);
+            msg[0] = make_int4(0, 0, 0, 0);
+        }
+        return;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) msg[0] = make_int4(nA, nP, 0, 0);
+    int2* pe = reinterpret_cast<int2*>(msg + 1 + 2 * (size_t)xcap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < max(nA, nP); i += gridDim.x * blockDim.x) {
+        if (i < nA) msg[1 + i] = act[i];
+        if (i < nP) {
+            msg[1 + xcap + i] = para[i];
+            pe[i] = para_e[i];
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_unpack_lists(const int4* __restrict__ all, int nranks, int xcap, size_t stride /* int4 per message */, int4* __restrict__ gact,
+    int4* __restrict__ gpara, int2* __restrict__ gpara_e, int cap, int* __restrict__ counts_out /* [0] active, [1] mollified */, int* __restrict__ overflow)
+{
+    for (int q = 0; q < nranks; ++q) {
+        int offA = 0, offP = 0;
+        for (int r = 0; r < q; ++r) {
+            const int4 h = all[(size_t)r * stride];
+            offA += h.x;
+            offP += h.y;
+        }
+        const int4 * m = all + (size_t)q * stride;
+        const int nA = m[0].x, nP = m[0].y;
+        if (offA + nA > cap || offP + nP > cap) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) atomicExch(overflow, 1);
             return;
         }
-        h = (h + 1) & mask;
+        const int2* pe = reinterpret_cast<const int2*>(m + 1 + 2 * (size_t)xcap);
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < max(nA, nP); i += gridDim.x * blockDim.x) {
+            if (i < nA) gact[offA + i] = m[1 + i];
+            if (i < nP) {
+                gpara[offP + i] = m[1 + xcap + i];
+                gpara_e[offP + i] = pe[i];
+            }
+        }
+        if (q == nranks - 1 && blockIdx.x == 0 && threadIdx.x == 0) {
+            counts_out[0] = offA + nA;
+            counts_out[1] = offP + nP;
+        }
     }
 }
 __global__ void k_dup_emit(unsigned size, const unsigned long long* __restrict__ tab_key, const int* __restrict__ tab_cnt, int4* __restrict__ act, int* __restrict__ nAct, int cap,
@@ -466,6 +538,17 @@ int contact_alloc(ipcgpu_ctx* ctx)
         && w.act.reserve(cap) && w.dup.reserve(cap) && w.para.reserve(cap) && w.para_e.reserve(cap) && w.cand.reserve((size_t)4 * cap) && w.tmp4.reserve(cap)
         && w.tmp2.reserve((size_t)4 * cap) && w.counters.reserve(16) && w.skey.reserve((size_t)4 * cap) && w.skey2.reserve((size_t)4 * cap) && w.sidx.reserve((size_t)4 * cap)
         && w.sidx2.reserve((size_t)4 * cap);
+    // PP/PE duplicate-merge table: the largest power of two that fits the sort scratch, at most 2^20 slots (cleared every build)
+    w.dup_tab = 1024;
+    while (w.dup_tab * 2 <= (unsigned)std::min<size_t>((size_t)4 * cap, (size_t)1 << 20)) w.dup_tab *= 2;
+    // pair Hessians of the barrier stage (144 doubles per pair) + stencil rows + makePD flags, sized by the pair capacity so that the
+    // barrier stage needs no host-side size
+    ok = ok && w.bHraw.reserve((size_t)cap * 144) && w.brows.reserve((size_t)cap * 4) && w.bpsd.reserve(cap) && w.bpartials.reserve(1024);
+    if (ctx->nranks > 1) { // exchange of the pair lists between ranks (ipcgpu_set_contact_partition)
+        w.xcap = std::min(cap, 1 << 16);
+        w.xstride = 1 + 2 * (size_t)w.xcap + (size_t)(w.xcap + 1) / 2;
+        ok = ok && w.xsend.reserve(w.xstride) && w.xrecv.reserve(w.xstride * ctx->nranks) && w.gact.reserve(cap) && w.gpara.reserve(cap) && w.gpara_e.reserve(cap);
+    }
     unsigned tsz = 1024;
     while (tsz < 2u * (unsigned)nEnt) tsz <<= 1;
     w.tab_mask = tsz - 1;
@@ -516,16 +599,18 @@ SurfArgs surf_args(const ipcgpu_ctx* ctx)
 }
 
 // boxes of vertices/edges/triangles (optionally swept by alpha*dir), grid parameters, and the two sorted grids
-int boxes_and_grid(ipcgpu_ctx* ctx, const double* dir, double alpha, double radius, bool with_vertex_boxes)
+// dir == nullptr: static boxes.  alpha_ptr / radius_ptr (device) override the by-value radius: the swept build takes both from the
+// device-resident iteration state
+int boxes_and_grid(ipcgpu_ctx* ctx, const double* dir, const double* alpha_ptr, double radius, const double* radius_ptr, bool with_vertex_boxes)
 {
     ContactWork& w = ctx->cw;
     cudaStream_t st = ctx->stream;
     const SurfArgs s = surf_args(ctx);
     k_bounds_init<<<1, 32, 0, st>>>(w.bounds.p);
-    if (with_vertex_boxes && s.nSV > 0) k_boxes<<<nblk(s.nSV, 256), 256, 0, st>>>(s, 0, dir, alpha, w.vbox.p, w.bounds.p);
-    if (s.nSE > 0) k_boxes<<<nblk(s.nSE, 256), 256, 0, st>>>(s, 1, dir, alpha, w.ebox.p, w.bounds.p);
-    if (s.nSF > 0) k_boxes<<<nblk(s.nSF, 256), 256, 0, st>>>(s, 2, dir, alpha, w.tbox.p, w.bounds.p);
-    k_grid_params<<<1, 32, 0, st>>>(w.bounds.p, radius, w.grid.p);
+    if (with_vertex_boxes && s.nSV > 0) k_boxes<<<nblk(s.nSV, 256), 256, 0, st>>>(s, 0, dir, alpha_ptr, w.vbox.p, w.bounds.p);
+    if (s.nSE > 0) k_boxes<<<nblk(s.nSE, 256), 256, 0, st>>>(s, 1, dir, alpha_ptr, w.ebox.p, w.bounds.p);
+    if (s.nSF > 0) k_boxes<<<nblk(s.nSF, 256), 256, 0, st>>>(s, 2, dir, alpha_ptr, w.tbox.p, w.bounds.p);
+    k_grid_params<<<1, 32, 0, st>>>(w.bounds.p, radius, radius_ptr, w.grid.p);
     ctx->launches += 5;
     int rc;
     if ((rc = build_grid(ctx, s.nSF, w.tbox.p, w.tkeys, w.tvals, w.tsbox.p, w.ttab_key.p, w.ttab_start.p))) return rc;
@@ -533,7 +618,41 @@ int boxes_and_grid(ipcgpu_ctx* ctx, const double* dir, double alpha, double radi
     return 0;
 }
 
-// SelfCollisionHandler::computeConstraintSet on the device; counts come back through the pinned scalar buffer
+// pack this rank's lists, allgather, rebuild the global lists (called by api.cu around its ncclAllGather)
+void contact_pack_lists(ipcgpu_ctx* ctx)
+{
+    ContactWork& w = ctx->cw;
+    k_pack_lists<<<kSMs, 256, 0, ctx->stream>>>(w.act.p, w.para.p, w.para_e.p, w.counters.p, w.xcap, w.xsend.p, &ctx->iter.p->flags[FLAG_EXCHANGE_CAPACITY]);
+    ++ctx->launches;
+}
+void contact_unpack_lists(ipcgpu_ctx* ctx)
+{
+    ContactWork& w = ctx->cw;
+    k_unpack_lists<<<kSMs, 256, 0, ctx->stream>>>(w.xrecv.p, ctx->nranks, w.xcap, w.xstride, w.gact.p, w.gpara.p, w.gpara_e.p, w.cap, w.counters.p + 10,
+        &ctx->iter.p->flags[FLAG_EXCHANGE_CAPACITY]);
+    ++ctx->launches;
+}
+
+// read the list sizes back (one synchronisation); only the host-facing calls need them
+int contact_sync_counts(ipcgpu_ctx* ctx)
+{
+    ContactWork& w = ctx->cw;
+    int* h = reinterpret_cast<int*>(ctx->h_scalar);
+    CKC(cudaMemcpyAsync(h, w.counters.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CKC(cudaStreamSynchronize(ctx->stream));
+    if (h[4]) {
+        ctx->err = "constraint-set capacity exceeded (raise it with ipcgpu_set_pair_capacity)";
+        return IPCGPU_ERR_CAPACITY;
+    }
+    w.nC = h[0];
+    w.nP = h[2];
+    w.nK = w.want_cand ? h[3] : 0;
+    return 0;
+}
+
+// SelfCollisionHandler::computeConstraintSet on the device.  Nothing is read back unless the caller asks for the sizes (nC / nPara /
+// nCand non-NULL) or for the canonical order (whose sorts are sized on the host): the lists and their counts stay on the device and
+// every consumer (barrier_*, partial CCD) takes the counts from there.
 int contact_constraint_set(ipcgpu_ctx* ctx, double dHat, int wantCand, int* nC, int* nPara, int* nCand)
 {
     ContactWork& w = ctx->cw;
@@ -542,7 +661,7 @@ int contact_constraint_set(ipcgpu_ctx* ctx, double dHat, int wantCand, int* nC, 
     const double radius = sqrt(dHat);
     cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_HASH);
     int rc;
-    if ((rc = boxes_and_grid(ctx, nullptr, 0.0, radius, false))) return rc;
+    if ((rc = boxes_and_grid(ctx, nullptr, nullptr, radius, nullptr, false))) return rc;
     ctx->prof_end(pe);
 
     pe = ctx->prof_begin(IPCGPU_STAGE_CONSTRAINT_SET);
@@ -568,54 +687,47 @@ int contact_constraint_set(ipcgpu_ctx* ctx, double dHat, int wantCand, int* nC, 
     if (v1 > v0 && s.nSF > 0) {
         k_pairs_pt<<<nblk(v1 - v0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(s, w.grid.p, tg, dHat, radius, v0, v1, ppt);
         k_classify_pt<<<nblk((long long)w.bp_cap, 128), 128, 0, st>>>(s, ppt.pairs, ppt.n, dHat, wantCand, out);
+        ctx->launches += 2;
     }
     if (e1 > e0 && s.nSE > 1) {
         k_pairs_ee<<<nblk(e1 - e0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(w.grid.p, eg, dHat, radius, e0, e1, pee);
         k_classify_ee<<<nblk((long long)w.bp_cap, 128), 128, 0, st>>>(s, pee.pairs, pee.n, dHat, wantCand, out);
+        ctx->launches += 2;
     }
-    ctx->launches += 2;
-    ctx->launches += 2;
-    int* h = reinterpret_cast<int*>(ctx->h_scalar);
-    CKC(cudaMemcpyAsync(h, w.counters.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CKC(cudaStreamSynchronize(st));
-    if (h[4]) {
-        ctx->err = "constraint-set capacity exceeded (raise it with ipcgpu_set_pair_capacity)";
-        return IPCGPU_ERR_CAPACITY;
+    // merge PP/PE duplicates into the active list with negative multiplicities (:2434-2476)
+    const bool hashed_merge = ctx->nV < (1 << 21) - 2;
+    if (hashed_merge) { // (x,y,z) packs into one 64-bit key: fixed-size table, no host-side size needed
+        CKC(cudaMemsetAsync(w.skey.p, 0xff, (size_t)w.dup_tab * sizeof(unsigned long long), st));
+        CKC(cudaMemsetAsync(w.sidx.p, 0, (size_t)w.dup_tab * sizeof(int), st));
+        k_dup_insert<<<kSMs * 2, 256, 0, st>>>(w.counters.p + 1, w.cap, w.dup.p, w.skey.p, w.sidx.p, w.dup_tab - 1, w.counters.p + 4);
+        k_dup_emit<<<nblk(w.dup_tab, 256), 256, 0, st>>>(w.dup_tab, w.skey.p, w.sidx.p, w.act.p, w.counters.p + 0, w.cap, w.counters.p + 4);
+        ctx->launches += 2;
     }
-    const int nAct = h[0], nDup = h[1], nP = h[2], nK = h[3];
-    // merge PP/PE duplicates into the active list with negative multiplicities
-    if (nDup > 0) {
-        if (ctx->nV < (1 << 21) - 2) {
-            unsigned size = 1024;
-            while (size < 2u * (unsigned)nDup) size <<= 1; // <= 4 * cap entries: fits the sort scratch
-            CKC(cudaMemsetAsync(w.skey.p, 0xff, (size_t)size * sizeof(unsigned long long), st));
-            CKC(cudaMemsetAsync(w.sidx.p, 0, (size_t)size * sizeof(int), st));
-            k_dup_insert<<<nblk(nDup, 256), 256, 0, st>>>(nDup, w.dup.p, w.skey.p, w.sidx.p, size - 1);
-            k_dup_emit<<<nblk(size, 256), 256, 0, st>>>(size, w.skey.p, w.sidx.p, w.act.p, w.counters.p + 0, w.cap, w.counters.p + 4);
-            ctx->launches += 2;
+    w.want_cand = wantCand != 0;
+    w.nC = w.nP = w.nK = -1; // unknown on the host until somebody asks
+    const bool need_host = !hashed_merge || ctx->canonical_order || nC || nPara || nCand;
+    if (need_host) {
+        int* h = reinterpret_cast<int*>(ctx->h_scalar);
+        if (!hashed_merge) { // huge meshes: sort-based merge, sized on the host
+            CKC(cudaMemcpyAsync(h, w.counters.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+            CKC(cudaStreamSynchronize(st));
+            const int nDup = std::min(h[1], w.cap);
+            if (nDup > 0) {
+                if ((rc = sort_lex(ctx, w.dup.p, nullptr, nDup, w.tmp4.p, nullptr))) return rc;
+                k_merge_dups<<<nblk(nDup, 256), 256, 0, st>>>(nDup, w.dup.p, w.act.p, w.counters.p + 0, w.cap, w.counters.p + 4);
+                ++ctx->launches;
+            }
         }
-        else {
-            if ((rc = sort_lex(ctx, w.dup.p, nullptr, nDup, w.tmp4.p, nullptr))) return rc;
-            k_merge_dups<<<nblk(nDup, 256), 256, 0, st>>>(nDup, w.dup.p, w.act.p, w.counters.p + 0, w.cap, w.counters.p + 4);
-            ++ctx->launches;
-        }
-        CKC(cudaMemcpyAsync(h, w.counters.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
-        CKC(cudaStreamSynchronize(st));
-        if (h[4]) {
-            ctx->err = "constraint-set capacity exceeded (raise it with ipcgpu_set_pair_capacity)";
-            return IPCGPU_ERR_CAPACITY;
+        if ((rc = contact_sync_counts(ctx))) return rc;
+        if (ctx->canonical_order) { // deterministic output order (the reference's own order is scheduling dependent, :2176, :2282)
+            if ((rc = sort_lex(ctx, w.act.p, nullptr, w.nC, w.tmp4.p, nullptr))) return rc;
+            if ((rc = sort_lex(ctx, w.para.p, w.para_e.p, w.nP, w.tmp4.p, w.tmp2.p))) return rc;
+            if (wantCand && (rc = sort_int2(ctx, w.cand.p, w.nK, w.tmp2.p))) return rc;
         }
     }
-    const int nTot = (nDup > 0) ? h[0] : nAct;
-    if (ctx->canonical_order) { // deterministic output order (the reference's own order is scheduling dependent, :2176, :2282)
-        if ((rc = sort_lex(ctx, w.act.p, nullptr, nTot, w.tmp4.p, nullptr))) return rc;
-        if ((rc = sort_lex(ctx, w.para.p, w.para_e.p, nP, w.tmp4.p, w.tmp2.p))) return rc;
-        if (wantCand && (rc = sort_int2(ctx, w.cand.p, nK, w.tmp2.p))) return rc;
-    }
+    k_publish_counts<<<1, 32, 0, st>>>(w.counters.p, wantCand, ctx->iter.p);
+    ++ctx->launches;
     ctx->prof_end(pe);
-    w.nC = nTot;
-    w.nP = nP;
-    w.nK = wantCand ? nK : 0;
     if (nC) *nC = w.nC;
     if (nPara) *nPara = w.nP;
     if (nCand) *nCand = w.nK;

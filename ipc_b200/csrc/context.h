@@ -55,7 +55,20 @@ struct ContactWork {
     DevBuf<int2> bp_pairs; // broad-phase pair lists (PT then EE), bp_cap each
     size_t bp_cap = 0;
     int cap = 0;
-    int nC = 0, nP = 0, nK = 0; // current active / mollified / candidate counts
+    // counters (device ints): [0] active, [1] PP/PE duplicates, [2] mollified, [3] candidates, [4] overflow, [8]/[9] broad-phase pairs PT/EE,
+    // [10]/[11] active / mollified of the GLOBAL lists after the cross-rank exchange, [12] pair Hessians owned by this rank
+    int nC = 0, nP = 0, nK = 0; // host mirrors of [0], [2], [3]; -1 = not read back (device-resident iteration)
+    bool want_cand = false;
+    unsigned dup_tab = 1024;    // slots of the PP/PE duplicate-merge table
+    // barrier stage workspace, sized by the pair capacity
+    DevBuf<double> bHraw, bpartials;
+    DevBuf<int> brows, bpsd;
+    // multi-rank exchange of the pair lists (one fixed-size message per rank, see k_pack_lists)
+    int xcap = 0;
+    size_t xstride = 0;
+    DevBuf<int4> xsend, xrecv, gact, gpara;
+    DevBuf<int2> gpara_e;
+    bool lists_global = false; // gact / gpara hold the global lists of the last partitioned build
 };
 
 // device workspace of the CCD stage (ccd.cu)
@@ -66,10 +79,7 @@ struct CcdWork {
     bool wide_level_set = false;
     DevBuf<unsigned char> scratch;
     DevBuf<unsigned long long> ncand, bounds;
-    // reference swept-grid geometry (SpatialHash.hpp:589-640) of the last ipcgpu_hash_build_swept
-    double ref_lo[3] = { 0, 0, 0 }, ref_inv_h = 0.0, alpha_grid = 0.0;
-    int ref_count[3] = { 0, 0, 0 };
-    bool swept_ready = false;
+    bool swept_ready = false; // (the reference swept-grid geometry of the last build lives in IterState)
     unsigned last_survivors = 0;
     unsigned long long last_deferred = 0, last_longest_cycles = 0, last_total_cycles = 0;
     int last_warnings = 0;
@@ -84,9 +94,22 @@ struct ipcgpu_ctx {
     std::string err;
     uint64_t launches = 0;
 
-    // partition
+    // partition: tets [t_begin, t_end) are OWNED (energy, inversion filter); rows of vertices [v_begin, v_end) are owned, and the
+    // gradient/Hessian kernel runs over every tet that touches them (tet_list, halo tets duplicated) so that the CSR needs no reduction
     int rank = 0, nranks = 1;
     void* nccl_comm = nullptr;
+    int v_begin = 0, v_end = 0, n_list = 0;
+    ipcgpu::DevBuf<int> tet_list;
+    long long a_begin = 0, a_end = 0; // CSR value range of the owned rows
+
+    // device-resident scalars of the iteration in flight + pinned host mirror
+    ipcgpu::DevBuf<ipcgpu::IterState> iter;
+    ipcgpu::IterState* h_iter = nullptr;
+    double pSize = 0.0;     // mean |p| over the surface vertices (SpatialHash.hpp:603-612), computed when p is uploaded
+    bool dir_valid = false, pSize_surface = false;
+    bool energy_local[2] = { false, false }; // IterState::energy[s] still holds this rank's partial sum
+    bool a_all_dirty = false;                // a cross-rank completion filled rows this rank does not own
+    std::vector<int> h_ia;                   // host copy of the CSR row starts (value range of the owned rows)
 
     // mesh
     int nV = 0, nT = 0, energy = 0;
@@ -108,9 +131,7 @@ struct ipcgpu_ctx {
     ipcgpu::CcdWork ccd;
     size_t ccd_capacity = (size_t)1 << 23; // candidate pairs
     std::vector<int> h_SVI;                // host copy (pSize of the swept build is a serial host sum, SpatialHash.hpp:603-612)
-    std::vector<double> h_dir;             // host shadow of the last uploaded search direction
-    ipcgpu::DevBuf<double> bpartials, bHraw;
-    ipcgpu::DevBuf<int> brows;
+    double debug_prune_seed = -1.0;        // test hook, see ipcgpu_ccd_debug_seed_bound
 
     // gradient gather map (local tets)
     ipcgpu::DevBuf<int> inc_ptr, inc;
@@ -128,8 +149,7 @@ struct ipcgpu_ctx {
 
     // work / result buffers
     ipcgpu::DevBuf<double> gcont, hblk, g, e_per_tet, partials, scalar_out, inv_steps, dir;
-    ipcgpu::DevBuf<unsigned long long> min_ord;
-    double* h_scalar = nullptr; // pinned staging for scalars (4 doubles)
+    double* h_scalar = nullptr; // pinned staging for scalars
 
     // profiling: event pairs per stage (only when enabled)
     bool profiling = false;
@@ -154,6 +174,7 @@ struct ipcgpu_ctx {
     {
         ipcgpu::ElasticArgs p;
         p.nV = nV; p.nT = nT; p.t_begin = t_begin; p.t_end = t_end;
+        p.n_list = n_list; p.tet_list = (nranks > 1) ? tet_list.p : nullptr;
         p.V = V.p; p.T = T.p; p.Ainv = Ainv.p; p.vol = vol.p; p.mu = mu.p; p.lam = lam.p; p.energy = energy;
         return p;
     }

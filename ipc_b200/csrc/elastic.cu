@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(kHessTile, 8) k_elastic_grad_hess(ElasticArgs 
     extern __shared__ __align__(128) double smem[];
     double* sHb[2] = { smem, smem + kHessTile * 9 };          // two slot buffers (ping-pong)
     double* sG = smem + (NEED_H ? 2 * kHessTile * 9 : 0);     // kHessTile * 12
-    const int nLocal = p.t_end - p.t_begin;
+    const int nLocal = p.n_list;
     const int tile0 = blockIdx.x * kHessTile;
     const int t = tile0 + threadIdx.x;
     const bool active = t < nLocal;
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(kHessTile, 8) k_elastic_grad_hess(ElasticArgs 
     double W[4][3];
     double a00 = 0, a01 = 0, a02 = 0, a11 = 0, a12 = 0, a22 = 0, d01 = 0, d10 = 0, o01 = 0, d12 = 0, d21 = 0, o12 = 0, d20 = 0, d02 = 0, o02 = 0;
     if (active) {
-        const int tt = p.t_begin + t;
+        const int tt = p.tet_list ? __ldg(p.tet_list + t) : p.t_begin + t;
         load_tet(p, tt, in);
         M3 F, V;
         double s[3];
@@ -351,10 +351,10 @@ __global__ void __launch_bounds__(288) k_assemble_csr(int nSlots, const int* __r
 
 // per-vertex diagonal terms of computePrecondMtr (Optimizer.cpp:3638-3668): mass on free vertices, identity on projected
 // Dirichlet vertices (setCoeff, also IglUtils.hpp:44-53).  The diagonal is the first stored entry of an upper-triangular row.
-__global__ void __launch_bounds__(256) k_diag_mass_dbc(int nV, const int* __restrict__ ia, int base, const uint8_t* __restrict__ dbc, int projectDBC,
+__global__ void __launch_bounds__(256) k_diag_mass_dbc(int v0, int nV, const int* __restrict__ ia, int base, const uint8_t* __restrict__ dbc, int projectDBC,
     const double* __restrict__ mass, double* __restrict__ a)
 {
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = v0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nV) return;
     const bool pv = dbc && (dbc[v] == 1 || (dbc[v] == 2 && projectDBC));
 #pragma unroll
@@ -474,6 +474,27 @@ DEV double det3v(const double* a, const double* b, const double* c)
     return a[0] * (b[1] * c[2] - b[2] * c[1]) - a[1] * (b[0] * c[2] - b[2] * c[0]) + a[2] * (b[0] * c[1] - b[1] * c[0]);
 }
 
+__global__ void k_inversion_init(IterState* st)
+{
+    if (threadIdx.x == 0) st->inv_ord = 0x7ff0000000000000ull; // +inf
+}
+// Energy.cpp:576-579 on the device-resident step: "if (0 < min && min < stepSize) stepSize = min"
+__global__ void k_inversion_apply(IterState* st, int nT)
+{
+    if (threadIdx.x != 0) return;
+    const double m = ord_to_dbl(st->inv_ord), alpha = ord_to_dbl(st->step_ord);
+    if (nT > 0 && m > 0.0 && m < alpha) st->step_ord = dbl_to_ord(m);
+    st->alpha_stage[0] = ord_to_dbl(st->step_ord);
+}
+__global__ void k_step_set(IterState* st, double alpha)
+{
+    if (threadIdx.x == 0) st->step_ord = dbl_to_ord(alpha);
+}
+__global__ void k_energy_store(IterState* st, int slot, const double* __restrict__ src)
+{
+    if (threadIdx.x == 0) st->energy[slot] = *src;
+}
+
 __global__ void __launch_bounds__(256) k_inversion_step(ElasticArgs p, const double* __restrict__ dir /* interleaved 3nV */, double slack,
     double* __restrict__ per_tet, unsigned long long* __restrict__ min_ord)
 {
@@ -543,7 +564,7 @@ void reduce_sum(const double* partials, int n, double scale, double* out, cudaSt
 template <int ENERGY, bool G, bool H>
 static void launch_gh(const ElasticArgs& p, double coef, int projectSPD, double* gcont, double* hblk, cudaStream_t st)
 {
-    const int n = p.t_end - p.t_begin;
+    const int n = p.n_list;
     if (n <= 0) return;
     const int nb = (n + kHessTile - 1) / kHessTile;
     const size_t smem = (size_t)kHessTile * 8 * ((H ? 18 : 0) + (G ? 12 : 0));
@@ -581,18 +602,27 @@ void assemble_csr(int nSlots, const int* slot_v, const int* slot_u, const int* s
 }
 void diag_mass_dbc(int nV, const int* ia, int base, const uint8_t* dbc, int projectDBC, const double* mass, double* a, cudaStream_t st)
 {
-    if (nV > 0 && (dbc || mass)) k_diag_mass_dbc<<<(nV + 255) / 256, 256, 0, st>>>(nV, ia, base, dbc, projectDBC, mass, a);
+    if (nV > 0 && (dbc || mass)) k_diag_mass_dbc<<<(nV + 255) / 256, 256, 0, st>>>(0, nV, ia, base, dbc, projectDBC, mass, a);
+}
+// the same over the vertex range [v0, v1) (row-owner partition: every rank writes the diagonal terms of its own rows)
+void diag_mass_dbc_range(int v0, int v1, const int* ia, int base, const uint8_t* dbc, int projectDBC, const double* mass, double* a, cudaStream_t st)
+{
+    if (v1 > v0 && (dbc || mass)) k_diag_mass_dbc<<<(v1 - v0 + 255) / 256, 256, 0, st>>>(v0, v1, ia, base, dbc, projectDBC, mass, a);
 }
 void slot_offsets(int nSlots, const int* slot_v, const int* slot_u, const int* ia, const int* ja, int base, int* slot_off, int* err, cudaStream_t st)
 {
     if (nSlots <= 0) return;
     k_slot_offsets<<<(nSlots + 255) / 256, 256, 0, st>>>(nSlots, slot_v, slot_u, ia, ja, base, slot_off, err);
 }
-void inversion_step(const ElasticArgs& p, const double* dir, double slack, double* per_tet, unsigned long long* min_ord, cudaStream_t st)
+void inversion_step(const ElasticArgs& p, const double* dir, double slack, double* per_tet, IterState* st_dev, cudaStream_t st)
 {
+    k_inversion_init<<<1, 32, 0, st>>>(st_dev);
     const int n = p.t_end - p.t_begin;
     if (n <= 0) return;
-    k_inversion_step<<<(n + 255) / 256, 256, 0, st>>>(p, dir, slack, per_tet, min_ord);
+    k_inversion_step<<<(n + 255) / 256, 256, 0, st>>>(p, dir, slack, per_tet, &st_dev->inv_ord);
 }
+void inversion_apply(IterState* st_dev, int nT, cudaStream_t st) { k_inversion_apply<<<1, 32, 0, st>>>(st_dev, nT); }
+void step_set(IterState* st_dev, double alpha, cudaStream_t st) { k_step_set<<<1, 32, 0, st>>>(st_dev, alpha); }
+void energy_store(IterState* st_dev, int slot, const double* src, cudaStream_t st) { k_energy_store<<<1, 32, 0, st>>>(st_dev, slot, src); }
 
 } // namespace ipcgpu

@@ -5,9 +5,32 @@
 
 namespace ipcgpu {
 
+// Device-resident scalars of one Newton iteration.  Every stage reads its inputs from here and leaves its outputs here, so a whole
+// iteration is one stream of launches (and in-stream NCCL reductions) with a single read-back at the end (ipcgpu_fetch_iteration).
+struct IterState {
+    unsigned long long step_ord;      // running step-size bound (order-preserving integer image of a non-negative double)
+    unsigned long long inv_ord;       // min inversion step over this rank's tets (then over all ranks)
+    unsigned long long ccd_ord;       // running minimum of the narrow phase in flight (every pair prunes against it)
+    unsigned long long cand_range[2]; // [begin, end) of the candidate list this rank's narrow phase walks
+    unsigned long long n_full_cand;   // candidates of the last full CCD (this rank)
+    double max_t;                     // step on entry of the narrow phase in flight (max_t of every pair)
+    double alpha_grid;                // sweep length of the last swept grid (after the span rescale of SpatialHash.hpp:603-618)
+    double radius;                    // query inflation of the swept broad phase = one reference voxel
+    double ref_lo[3], ref_inv_h;      // reference swept-grid geometry (SpatialHash.hpp:589-640)
+    double alpha_stage[4];            // step after: inversion filter, partial CCD, swept-grid rescale, full CCD
+    double energy[2];                 // elastic, barrier (cross-rank sums once reduced)
+    int ref_count[3];
+    int n_set[3];                     // active / mollified / candidate counts of the last constraint set (this rank's lists)
+    int flags[8];                     // IPCGPU_FLAG_* slots (nonzero = raised); cleared by ipcgpu_fetch_iteration
+    unsigned long long ccd_stats[8];  // survivors, warnings, deferred, longest / total pair cycles, boxes (thread pass, warp pass), candidates
+};
+enum { FLAG_NONPOSITIVE_DISTANCE = 0, FLAG_SET_CAPACITY = 1, FLAG_CCD_CAPACITY = 2, FLAG_ZERO_CCD_DISTANCE = 3, FLAG_PATTERN = 4, FLAG_TI_WARNINGS = 5, FLAG_EXCHANGE_CAPACITY = 6 };
+
 struct ElasticArgs {
     int nV, nT;
-    int t_begin, t_end;      // this rank's tet range (multi-GPU partition)
+    int t_begin, t_end;      // this rank's OWNED tet range (energy, inversion filter: every tet exactly once)
+    int n_list;              // gradient/Hessian kernel: number of tets this rank assembles (all tets that touch its rows)
+    const int* tet_list;     // their ids, ascending; nullptr = the contiguous range [t_begin, t_begin + n_list)
     const double* V;         // SoA [x|y|z] current positions
     const int* T;            // SoA [v0|v1|v2|v3]
     const double* Ainv;      // SoA 9 x nT, q = 3*i+j row-major index of Dm^-1
@@ -26,7 +49,11 @@ void assemble_csr(int nSlots, const int* slot_v, const int* slot_u, const int* s
     const double* hblk, const uint8_t* dbc, int projectDBC, const double* mass, int accumulate, double* a, cudaStream_t st);
 void diag_mass_dbc(int nV, const int* ia, int base, const uint8_t* dbc, int projectDBC, const double* mass, double* a, cudaStream_t st);
 void slot_offsets(int nSlots, const int* slot_v, const int* slot_u, const int* ia, const int* ja, int base, int* slot_off, int* err, cudaStream_t st);
-void inversion_step(const ElasticArgs& p, const double* dir, double slack, double* per_tet, unsigned long long* min_ord, cudaStream_t st);
+void diag_mass_dbc_range(int v0, int v1, const int* ia, int base, const uint8_t* dbc, int projectDBC, const double* mass, double* a, cudaStream_t st);
+void inversion_step(const ElasticArgs& p, const double* dir, double slack, double* per_tet, IterState* st_dev, cudaStream_t st);
+void inversion_apply(IterState* st_dev, int nT, cudaStream_t st);          // Energy.cpp:576-579 on the device-resident step
+void step_set(IterState* st_dev, double alpha, cudaStream_t st);           // step_ord = alpha
+void energy_store(IterState* st_dev, int slot, const double* src, cudaStream_t st);
 
 
 // ---- contact ------------------------------------------------------------------------------------------
@@ -47,8 +74,13 @@ struct BarrierArgs {
     const double* Vrest;
     const uint8_t* dbc;
     const int* SE;
-    const int4* cs; int nC;          // active set (MMCVID encoding)
-    const int4* para; const int2* para_e; int nP; // mollified (nearly parallel EE) set + (eI,eJ)
+    const int4* cs; const int* nC;          // active set (MMCVID encoding) and its DEVICE-resident count
+    const int4* para; const int2* para_e; const int* nP; // mollified (nearly parallel EE) set + (eI,eJ), device count
+    // multi-rank: E and g are taken over a contiguous share [n*rank/nranks, n*(rank+1)/nranks) of each list (share = 1) or over the
+    // whole list (share = 0: the lists are already this rank's own); the Hessian is assembled by ROW OWNER: a rank processes every
+    // pair that touches a vertex in [row_lo, row_hi) and scatters only the block rows it owns
+    int rank, nranks, share;
+    int row_lo, row_hi;
     double dHat, kappa;
     int projectDBC;
     const int* ia; const int* ja; int base;
@@ -56,9 +88,10 @@ struct BarrierArgs {
 
 // barrier.cu
 void barrier_energy(const BarrierArgs& p, double* partials, int* bad, cudaStream_t st);
-int barrier_energy_blocks(int n);
+int barrier_energy_blocks();
 void barrier_gradient(const BarrierArgs& p, double* g, cudaStream_t st);
-void barrier_hessian(const BarrierArgs& p, double* a, int* err, double* Hraw /* 144 per pair */, int* rows /* 5 per pair: 4 vertex ids, then n flags */, cudaStream_t st);
+// Hraw: 144 doubles per owned pair; rows: 4 vertex ids per owned pair; psd: makePD "unchanged" flag per owned pair; n_owned: device counter
+void barrier_hessian(const BarrierArgs& p, double* a, int* err, double* Hraw, int* rows, int* psd, int* n_owned, int capacity, cudaStream_t st);
 // elastic.cu (shared fixed-order reduction)
 void reduce_sum(const double* partials, int n, double scale, double* out, cudaStream_t st);
 

@@ -31,6 +31,12 @@ SIGNATURES = {
     "ipcgpu_launch_count": (C.c_uint64, [_ctxp]),
     "ipcgpu_comm_unique_id": (C.c_int, [C.c_void_p]),
     "ipcgpu_comm_init": (C.c_int, [_ctxp, C.c_int, C.c_int, C.c_void_p]),
+    "ipcgpu_partition_info": (C.c_int, [_ctxp, _ip, _ip, _ip, _ip, _ip, _ip, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _ip]),
+    "ipcgpu_fetch_iteration": (C.c_int, [_ctxp, C.c_void_p]),
+    "ipcgpu_step_bound_set": (C.c_int, [_ctxp, C.c_double]),
+    "ipcgpu_constraint_set_sizes": (C.c_int, [_ctxp, _ip, _ip, _ip]),
+    "ipcgpu_ccd_debug_seed_bound": (C.c_int, [_ctxp, C.c_double]),
+    "ipcgpu_download_range": (C.c_int, [_ctxp, C.c_int, C.c_uint64, C.c_uint64, _dp]),
     "ipcgpu_set_mesh": (C.c_int, [_ctxp, C.c_int, C.c_int, _dp, _ip, _dp, _dp, _dp, _dp, _dp, _u8p, C.c_int]),
     "ipcgpu_set_csr": (C.c_int, [_ctxp, C.c_int, _ip, _ip, C.c_int]),
     "ipcgpu_set_state": (C.c_int, [_ctxp, _dp]),
@@ -74,6 +80,13 @@ STAGES = ["elastic_energy", "elastic_tet", "gather_gradient", "assemble_csr", "i
           "ccd_broad", "ccd_narrow", "allreduce", "ccd_root_filter"]
 
 _lib = None
+
+
+class Iteration(C.Structure):
+    """ipcgpu_iteration (include/ipcgpu.h)"""
+    _fields_ = [("energy_elastic", C.c_double), ("energy_barrier", C.c_double), ("alpha_inversion", C.c_double), ("alpha_partial_ccd", C.c_double),
+                ("alpha_swept_grid", C.c_double), ("alpha_full_ccd", C.c_double), ("alpha", C.c_double), ("n_active", C.c_int), ("n_mollified", C.c_int),
+                ("n_candidates", C.c_int), ("status", C.c_int), ("n_full_ccd_candidates", C.c_uint64), ("ti_warnings", C.c_uint64)]
 
 
 class IpcGpuError(RuntimeError):
@@ -223,9 +236,36 @@ class Context:
         self._ck(self.lib.ipcgpu_elastic_grad_hess(self.h, coef, projectSPD, projectDBC, add_mass, _d(g), _d(a)))
 
     def inversion_step(self, p, slack, alpha):
-        a = C.c_double(alpha)
-        self._ck(self.lib.ipcgpu_inversion_step(self.h, _d(f64(p)) if p is not None else None, slack, C.byref(a)))
-        return a.value
+        """alpha=None: chained on the device (no synchronisation)"""
+        a = C.c_double(alpha if alpha is not None else 0.0)
+        self._ck(self.lib.ipcgpu_inversion_step(self.h, _d(f64(p)) if p is not None else None, slack, C.byref(a) if alpha is not None else None))
+        return a.value if alpha is not None else None
+
+    def step_bound_set(self, alpha):
+        self._ck(self.lib.ipcgpu_step_bound_set(self.h, float(alpha)))
+
+    def fetch_iteration(self):
+        it = Iteration()
+        self._ck(self.lib.ipcgpu_fetch_iteration(self.h, C.byref(it)))
+        return it
+
+    def partition_info(self):
+        v = [C.c_int() for _ in range(6)]
+        a0, a1, nl = C.c_int64(), C.c_int64(), C.c_int()
+        self._ck(self.lib.ipcgpu_partition_info(self.h, *[C.byref(x) for x in v], C.byref(a0), C.byref(a1), C.byref(nl)))
+        return dict(rank=v[0].value, nranks=v[1].value, tet_begin=v[2].value, tet_end=v[3].value, row_vertex_begin=v[4].value, row_vertex_end=v[5].value,
+                    value_begin=a0.value, value_end=a1.value, n_assembled_tets=nl.value)
+
+    def ccd_debug_seed_bound(self, toi):
+        self._ck(self.lib.ipcgpu_ccd_debug_seed_bound(self.h, float(toi)))
+
+    def constraint_set_sizes(self):
+        nC, nP, nK = C.c_int(), C.c_int(), C.c_int()
+        self._ck(self.lib.ipcgpu_constraint_set_sizes(self.h, C.byref(nC), C.byref(nP), C.byref(nK)))
+        return nC.value, nP.value, nK.value
+
+    def download_range_into(self, which, offset, out):
+        self._ck(self.lib.ipcgpu_download_range(self.h, which, int(offset), int(out.size), _d(out)))
 
     # ---- contact ------------------------------------------------------------------------------
     def set_surface(self, SVI, SFEdges, SF_soa, vCoDim=None):
@@ -241,7 +281,12 @@ class Context:
     def set_pair_capacity(self, cap):
         self._ck(self.lib.ipcgpu_set_pair_capacity(self.h, int(cap)))
 
-    def constraint_set(self, dHat, getPTEE=1, fetch=True):
+    def constraint_set(self, dHat, getPTEE=1, fetch=True, sizes=True):
+        """fetch=True: returns the four lists; fetch=False, sizes=True: returns the sizes (one synchronisation);
+        fetch=False, sizes=False: nothing is read back (device-resident iteration)"""
+        if not fetch and not sizes:
+            self._ck(self.lib.ipcgpu_constraint_set(self.h, dHat, getPTEE, None, None, None))
+            return None
         nC, nP, nK = C.c_int(), C.c_int(), C.c_int()
         self._ck(self.lib.ipcgpu_constraint_set(self.h, dHat, getPTEE, C.byref(nC), C.byref(nP), C.byref(nK)))
         self.nC, self.nP, self.nK = nC.value, nP.value, nK.value
@@ -257,9 +302,9 @@ class Context:
         cand = i32(cand) if cand is not None else np.empty((0, 2), dtype=np.int32)
         self._ck(self.lib.ipcgpu_set_constraint_set(self.h, len(mm), _i(mm), len(pa), _i(pa), _i(pe), len(cand), _i(cand)))
 
-    def barrier_energy(self, dHat, kappa):
+    def barrier_energy(self, dHat, kappa, want=True):
         E = C.c_double()
-        self._ck(self.lib.ipcgpu_barrier_energy(self.h, dHat, kappa, C.byref(E)))
+        self._ck(self.lib.ipcgpu_barrier_energy(self.h, dHat, kappa, C.byref(E) if want else None))
         return E.value
 
     def barrier_gradient(self, dHat, kappa, g_inout=None):
@@ -283,20 +328,23 @@ class Context:
         self._ck(self.lib.ipcgpu_set_ccd_capacity(self.h, int(cap)))
 
     def ccd_partial(self, p, tol, err_vf, err_ee, alpha):
-        a = C.c_double(alpha)
-        self._ck(self.lib.ipcgpu_ccd_partial_ti(self.h, _d(f64(p)) if p is not None else None, tol, _d(f64(err_vf)), _d(f64(err_ee)), C.byref(a)))
-        return a.value
+        """alpha=None (here and in the next two): chained on the device, nothing is read back"""
+        a = C.c_double(alpha if alpha is not None else 0.0)
+        self._ck(self.lib.ipcgpu_ccd_partial_ti(self.h, _d(f64(p)) if p is not None else None, tol, _d(f64(err_vf)), _d(f64(err_ee)),
+                                                C.byref(a) if alpha is not None else None))
+        return a.value if alpha is not None else None
 
     def hash_build_swept(self, p, alpha, h):
-        a = C.c_double(alpha)
-        self._ck(self.lib.ipcgpu_hash_build_swept(self.h, _d(f64(p)) if p is not None else None, C.byref(a), h))
-        return a.value
+        a = C.c_double(alpha if alpha is not None else 0.0)
+        self._ck(self.lib.ipcgpu_hash_build_swept(self.h, _d(f64(p)) if p is not None else None, C.byref(a) if alpha is not None else None, h))
+        return a.value if alpha is not None else None
 
     def ccd_full(self, tol, err_vf, err_ee, alpha):
-        a = C.c_double(alpha)
+        a = C.c_double(alpha if alpha is not None else 0.0)
         n = C.c_uint64()
-        self._ck(self.lib.ipcgpu_ccd_full_ti(self.h, tol, _d(f64(err_vf)), _d(f64(err_ee)), C.byref(a), C.byref(n)))
-        return a.value, n.value
+        self._ck(self.lib.ipcgpu_ccd_full_ti(self.h, tol, _d(f64(err_vf)), _d(f64(err_ee)), C.byref(a) if alpha is not None else None,
+                                             C.byref(n) if alpha is not None else None))
+        return (a.value, n.value) if alpha is not None else None
 
     def ccd_stats(self):
         a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()

@@ -113,6 +113,19 @@ def shape_transform(V, translate=(0, 0, 0), rotate_deg=(0, 0, 0), scale=(1, 1, 1
     return (V * np.asarray(scale, dtype=float)) @ (Rx @ Ry @ Rz).T + np.asarray(translate, dtype=float)
 
 
+def affine_prestrain(m, about=None):
+    """Multiply the CURRENT state by a small fixed strain (I + E), |E| ~ 1e-3, about a point: no tet is left exactly at rest.
+    Why the parity scenes need it: IglUtils::makePD2d (IglUtils.hpp:138-177) is DISCONTINUOUS at L2 = 0 -- for L2 < 0 it returns
+    (L1 - d)^2 / L1 etc., which is not the limit of the untouched matrix as L2 -> 0- (at F = I the twist block [[mu, mu], [mu, mu]] comes
+    back halved) -- and at an exact rest state L2 = +-1e-17 is pure rounding noise of the SVD, in the reference as much as here.  Two
+    correct implementations of the same formulas (the oracle's implicit-QR SVD, the kernels' Jacobi SVD) then disagree per tet on the
+    branch.  Gaps between bodies change by a relative 1e-3, i.e. not at all at the resolution of the U(lo, hi) sqrt(dHat) placement."""
+    E = np.array([[1.0e-3, 2.0e-4, -1.0e-4], [2.0e-4, -7.0e-4, 3.0e-4], [-1.0e-4, 3.0e-4, 4.0e-4]])
+    c = m.V.mean(0) if about is None else np.asarray(about, dtype=float)
+    m.V = (m.V - c) @ (np.eye(3) + E).T + c
+    return m
+
+
 def _fcc_points(n):
     """the n points of the FCC lattice (nearest-neighbour distance 1) closest to the origin, ordered by distance then lexicographically"""
     k = int(np.ceil((n / 4.0) ** (1.0 / 3.0))) + 2
@@ -199,6 +212,7 @@ def ball_on_mat_c3(nx=200, seed=3, energy=0, dhat_rel=1e-3, gap_lo=0.2, gap_hi=1
     m = M.merge_meshes([(Vm, Tm, M.boundary_faces(Tm)), (Vb + c, Tb, SFb)], energy=energy)
     m.V = m.V_rest.copy()
     m.V[:nVm] = Vm_def
+    affine_prestrain(m)  # the ball would otherwise sit exactly at rest (see affine_prestrain)
     p = np.zeros((m.nV, 3))
     p[nVm:, 2] = -rng.uniform(0.0, 2.0, m.nV - nVm) * sq
     p += rng.normal(0, 0.05 * sq, (m.nV, 3))
@@ -219,7 +233,7 @@ def _vertex_normals(V, SF):
     return N / np.maximum(ln, 1e-300)[:, None]
 
 
-def squeeze_out_tiled(seed=4, energy=0, dhat_rel=1e-3, gap_lo=0.3, gap_hi=1.2, contact_frac=0.05, far=2.5, bodies=None):
+def squeeze_out_tiled(seed=4, energy=0, dhat_rel=1e-3, gap_lo=0.3, gap_hi=1.2, contact_frac=0.05, far=2.5, slide=0.15, bodies=None):
     """BASELINE config C4: the tet bodies of 1_squeezeOut.txt:12-15 (180,569 tets) tiled x3 (541,707 tets) with dense self-contact.
 
     No simulation is available to press the bodies together, so the squeezed state is manufactured per body from three copies:
@@ -266,7 +280,7 @@ def squeeze_out_tiled(seed=4, energy=0, dhat_rel=1e-3, gap_lo=0.3, gap_hi=1.2, c
         off[inside] = rng.uniform(gap_lo, gap_hi, int(inside.sum())) * sq
         tang = rng.standard_normal(V.shape)
         tang -= (tang * N).sum(1)[:, None] * N
-        tang *= (0.15 * el * rng.uniform(0, 1, len(V)) / np.maximum(np.linalg.norm(tang, axis=1), 1e-300))[:, None]
+        tang *= (slide * el * rng.uniform(0, 1, len(V)) / np.maximum(np.linalg.norm(tang, axis=1), 1e-300))[:, None]
         tang[~inside] = 0.0
         disp = N * off[:, None] + tang
         # repair: where pushing along diverse normals (concave creases, slivers) would invert or crush a tet, replace the displacements
@@ -296,5 +310,6 @@ def squeeze_out_tiled(seed=4, energy=0, dhat_rel=1e-3, gap_lo=0.3, gap_hi=1.2, c
     rest = [(parts[k - 1][0] if k % 3 == 1 else parts[k][0], parts[k][1], parts[k][2]) for k in range(len(parts))]
     m = M.merge_meshes(rest, energy=energy)
     m.V = np.concatenate([b[0] for b in parts])
+    affine_prestrain(m)  # copies 0 and 2 would otherwise sit exactly at rest (see affine_prestrain)
     p = np.concatenate(push) + rng.normal(0, 0.05 * sq, (m.nV, 3))
     return m, dict(dHat=dHat, p=np.ascontiguousarray(p).ravel(), n_bodies=len(placed), tile=tile)

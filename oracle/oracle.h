@@ -154,6 +154,17 @@ int orc_constraint_set_hashed(const orc_surf* s, double dHat, double voxel_size,
 int orc_ccd_full_hashed(const orc_surf* s, const double* p, double* alpha_inout, double voxel_size, double tol,
     const double err_vf[3], const double err_ee[3], long long* nPairs, int nthreads);
 
+/* ---- line-search safeguards (oracle/intersect.cpp) --------------------------------------------------------------- */
+/* igl::predicates::orient3d restated (filter + exact expansion arithmetic): +1 / 0 / -1 */
+int orc_orient3d(const double* pa, const double* pb, const double* pc, const double* pd);
+int orc_orient3d_exact(const double* pa, const double* pb, const double* pc, const double* pd);
+/* IglUtils::segTriIntersect (IglUtils.hpp:214-265) */
+int orc_seg_tri_intersect(const double* ve0, const double* ve1, const double* vt0, const double* vt1, const double* vt2);
+/* SelfCollisionHandler::checkEdgeTriIntersectionIfAny (:3254-3296): 1 = intersection free; hits = intersected triangles */
+int orc_intersection_free(const orc_surf* s, double cell, int* hits, int* tri_flags /* nSF, nullable */, int nthreads);
+/* Mesh::checkInversion (Mesh.cpp:715-763): tets with mu, lambda != 0 and det(current edge matrix) < 0 */
+int orc_count_inverted(const orc_mesh* m);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,6 +71,9 @@ class Elastic:
         lib().orc_elastic_gradient(C.byref(self.m), C.c_double(coef), projectDBC, d(g), nthreads)
         return g
 
+    def count_inverted(self):
+        return int(lib().orc_count_inverted(C.byref(self.m)))
+
     def hessian_blocks(self, coef, projectSPD=1, nthreads=1):
         H = np.empty((self.nT, 12, 12))
         lib().orc_elastic_hessian_blocks(C.byref(self.m), C.c_double(coef), projectSPD, d(H), nthreads)
@@ -246,6 +249,13 @@ class Surf:
         assert rc == 0, "oracle constraint-set capacity exceeded"
         return mm[:nC.value].copy(), pa[:nP.value].copy(), pe[:nP.value].copy(), cand[:nK.value].copy()
 
+    def intersection_free(self, cell=None, nthreads=1, flags=False):
+        """checkEdgeTriIntersectionIfAny: (ok, number of intersected surface triangles[, per-triangle flags])"""
+        hits = C.c_int()
+        fl = np.zeros(self.SF.size // 3, dtype=np.int32) if flags else None
+        ok = lib().orc_intersection_free(C.byref(self.s), C.c_double(cell if cell else self.mesh.avgEdgeLen), C.byref(hits), i(fl) if flags else None, nthreads)
+        return (bool(ok), hits.value, fl) if flags else (bool(ok), hits.value)
+
     def constraint_set_hashed(self, dHat, voxel_size, nthreads=1, cap=1 << 20):
         mm = np.empty((cap, 4), dtype=np.int32); pa = np.empty((cap, 4), dtype=np.int32); pe = np.empty((cap, 2), dtype=np.int32)
         cand = np.empty((4 * cap, 2), dtype=np.int32)
@@ -336,3 +346,14 @@ def ccd_full_hashed(surf, p, alpha, voxel_size, tol, evf, eee, nthreads=1):
     z = lib().orc_ccd_full_hashed(C.byref(surf.s), d(p), C.byref(a), C.c_double(voxel_size), C.c_double(tol), d(np.ascontiguousarray(evf)), d(np.ascontiguousarray(eee)),
                                   C.byref(n), nthreads)
     return a.value, z, n.value
+
+
+def orient3d(a, b, c, d_, exact=False):
+    a, b, c, d_ = (np.ascontiguousarray(x, dtype=np.float64) for x in (a, b, c, d_))
+    f = lib().orc_orient3d_exact if exact else lib().orc_orient3d
+    return int(f(d(a), d(b), d(c), d(d_)))
+
+
+def seg_tri_intersect(e0, e1, t0, t1, t2):
+    v = [np.ascontiguousarray(x, dtype=np.float64) for x in (e0, e1, t0, t1, t2)]
+    return int(lib().orc_seg_tri_intersect(*[d(x) for x in v]))

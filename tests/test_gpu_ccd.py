@@ -130,3 +130,51 @@ def test_ball_pile_ccd_bit_exact(gpu_ctx):
             assert orc.point_tri_d(V2[[m.SVI[-c[0] - 1]] + list(m.SF[c[1]])]) > 0
         else:
             assert orc.edge_edge_d(V2[list(m.SFEdges[c[0]]) + list(m.SFEdges[c[1]])]) > 0
+
+
+def _retry_scene():
+    """Two point-triangle pairs built so that the `toi < 1e-6 -> rerun with ms = 0, toi *= 0.8` rule of SelfCollisionHandler.cpp:759-781
+    matters: pair A (gap 1e-3, fast) hits at 1.0198e-6 (no rerun); pair B (gap 4e-6) first reports 2^-20 < 1e-6, its rerun with ms = 0
+    finds 1.25 * 2^-20 = 1.19e-6 and reports 0.8 x that = 2^-20 = 9.54e-7 -- BELOW A's impact although the rerun's box starts ABOVE it."""
+    def tri_tet(o):
+        return np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0.3, 0.3, -1.0]]) + o, np.array([[0, 2, 1, 3]])
+
+    def pt_tet(o, h):
+        return np.array([[0.3, 0.3, h], [1.3, 0.3, h + 1], [0.3, 1.3, h + 1], [-0.7, -0.7, h + 1.2]]) + o, np.array([[0, 1, 2, 3]])
+
+    d = 4e-6
+    m = M.merge_meshes([tri_tet(np.zeros(3)), pt_tet(np.zeros(3), 1e-3), tri_tet(np.array([5.0, 0, 0])), pt_tet(np.array([5.0, 0, 0]), d)])
+    p = np.zeros((m.nV, 3))
+    p[4:8, 2] = -(1e-3 - 1e-6) / 1.02e-6
+    p[12:16, 2] = -d / 1.3e-6
+    sv = lambda v: int(np.nonzero(m.SVI == v)[0][0])
+    sf = lambda vs: next(k for k, f in enumerate(m.SF) if set(f) == set(vs))
+    candA = (-sv(4) - 1, sf([0, 1, 2]))
+    candB = (-sv(12) - 1, sf([8, 9, 10]))
+    return m, p.ravel(), np.array([candA], dtype=np.int32), np.array([candB], dtype=np.int32)
+
+
+def test_ms0_retry_is_not_pruned_by_a_competing_impact(gpu_ctx):
+    """the running-minimum pruning must not cut the ms = 0 rerun, whose result is rescaled by 0.8 afterwards.  Which pair reports
+    first is a race on the device, so the test seeds the running minimum with pair A's impact (ipcgpu_ccd_debug_seed_bound) and runs pair B
+    alone: with the rerun pruned B would report nothing and the step would stay at A's 1.0198e-6; the oracle (no pruning) says 2^-20."""
+    m, p, candA, candB = _retry_scene()
+    upload(gpu_ctx, m)
+    s = orc.Surf(m)
+    evf, eee = L.Context.ti_error(m.V_soa, m.nV, None)
+    mm0 = np.empty((0, 4), dtype=np.int32)
+    pe0 = np.empty((0, 2), dtype=np.int32)
+    a_A, _ = orc.ccd_partial(s, p, candA, 1e-6, evf, eee, 1.0, 1)
+    a_B, _ = orc.ccd_partial(s, p, candB, 1e-6, evf, eee, 1.0, 1)
+    a_AB, _ = orc.ccd_partial(s, p, np.concatenate([candA, candB]), 1e-6, evf, eee, 1.0, 1)
+    assert a_B == 2.0 ** -20 and a_A > a_B and a_AB == a_B and 1.25 * a_B > a_A  # the scenario is the intended one
+    gpu_ctx.set_constraint_set(mm0, mm0, pe0, candB)
+    try:
+        gpu_ctx.ccd_debug_seed_bound(a_A)  # "pair A has already reported"
+        a = gpu_ctx.ccd_partial(p, 1e-6, evf, eee, 1.0)
+    finally:
+        gpu_ctx.ccd_debug_seed_bound(-1.0)
+    assert bits(a) == bits(a_AB), (a, a_AB)
+    # and without the hook, both pairs in one list, whatever the race
+    gpu_ctx.set_constraint_set(mm0, mm0, pe0, np.concatenate([candA, candB]))
+    assert bits(gpu_ctx.ccd_partial(p, 1e-6, evf, eee, 1.0)) == bits(a_AB)

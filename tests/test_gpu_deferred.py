@@ -1,0 +1,86 @@
+"""The device-resident iteration (every stage enqueued with NULL outputs, one ipcgpu_fetch_iteration) must give exactly what the
+synchronous calls give: same energies, same gradient / CSR values, bit-identical step after every bound -- and both match the oracle."""
+import struct
+
+import numpy as np
+import pytest
+
+import oracle as orc
+from ipc_b200 import lib as L
+from ipc_b200 import scenes
+from stagecheck import contact_pattern_pairs, rel
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(x):
+    return struct.pack("<d", float(x))
+
+
+@pytest.mark.parametrize("canonical", [1, 0])
+def test_deferred_iteration_equals_synchronous_calls(gpu_ctx, canonical):
+    ctx = gpu_ctx
+    m, info = scenes.ball_pile(4, res=8, seed=5, height=4)
+    dHat, p, kappa, dt2, tol = info["dHat"], info["p"], 1e8, 0.025 ** 2, 1e-6
+    h = m.avgEdgeLen / 3
+    ctx.set_mesh(m.V_rest_soa, m.T_soa, m.restTriInv, m.vol, m.mu, m.lam, m.mass, m.dbc, m.energy)
+    ctx.set_surface(m.SVI, m.SFEdges, m.SF_soa, m.vCoDim)
+    ctx.set_state(m.V_soa)
+    ctx.set_canonical_order(canonical)
+    evf, eee = L.Context.ti_error(m.V_soa, m.nV, None)
+    mm, pa, pe, cand = ctx.constraint_set(dHat, 1)
+    ia, ja = m.csr_pattern(1, extra_pairs=contact_pattern_pairs(m, mm, pa, pe))
+    ctx.set_csr(ia, ja, 1)
+    # synchronous reference run
+    E_el, E_b = ctx.elastic_energy(dt2), ctx.barrier_energy(dHat, kappa)
+    g, a = np.empty(3 * m.nV), np.empty(ja.size)
+    ctx.elastic_grad_hess(dt2, 1, 1, 1, g, a)
+    ctx.barrier_gradient(dHat, kappa, g)
+    ctx.barrier_hessian(dHat, kappa, 1, a)
+    a0 = ctx.inversion_step(p, 0.2, 1.0)
+    a1 = ctx.ccd_partial(None, tol, evf, eee, a0)
+    a2 = ctx.hash_build_swept(None, a1, h)
+    a3, ncand = ctx.ccd_full(tol, evf, eee, a2)
+    # the same through the device-resident chain
+    ctx.constraint_set(dHat, 1, fetch=False, sizes=False)
+    ctx.elastic_energy(dt2, 1, want=False)
+    ctx.barrier_energy(dHat, kappa, want=False)
+    ctx.elastic_grad_hess(dt2, 1, 1, 1, None, None)
+    ctx.barrier_gradient(dHat, kappa, None)
+    ctx.barrier_hessian(dHat, kappa, 1, None)
+    ctx.step_bound_set(1.0)
+    ctx.inversion_step(None, 0.2, None)
+    ctx.ccd_partial(None, tol, evf, eee, None)
+    ctx.hash_build_swept(None, None, h)
+    ctx.ccd_full(tol, evf, eee, None)
+    it = ctx.fetch_iteration()
+    assert it.status == 0 and it.ti_warnings == 0
+    assert (it.n_active, it.n_mollified, it.n_candidates) == (len(mm), len(pa), len(cand)) == ctx.constraint_set_sizes()
+    assert abs(it.energy_elastic - E_el) <= 1e-14 * abs(E_el) and abs(it.energy_barrier - E_b) <= 1e-12 * abs(E_b)
+    assert [bits(x) for x in (it.alpha_inversion, it.alpha_partial_ccd, it.alpha_swept_grid, it.alpha_full_ccd, it.alpha)] == [bits(x) for x in (a0, a1, a2, a3, a3)]
+    assert it.n_full_ccd_candidates == ncand
+    g2, a_2 = ctx.download(L.BUF_GRADIENT, 3 * m.nV), ctx.download(L.BUF_CSR_VALUES, ja.size)
+    assert rel(g2, g) <= 1e-13 and rel(a_2, a) <= 1e-13  # (atomics: summation order differs run to run)
+    # and the oracle
+    s, o = orc.Surf(m), orc.Elastic(m)
+    al, _ = o.inversion_step(p, 0.2, 1.0)
+    al, _ = orc.ccd_partial(s, p, cand, tol, evf, eee, al, 8)
+    gr, ag = orc.grid_swept(s, p, al, h)
+    al, _, _ = orc.ccd_full(s, p, gr, ag, tol, evf, eee, ag, 8)
+    assert bits(it.alpha) == bits(al)
+    ctx.set_canonical_order(1)
+
+
+def test_deferred_errors_surface_at_fetch(gpu_ctx):
+    """d <= 0 in the barrier energy (the reference exits there) is reported by the fetch when nothing was read back in between"""
+    ctx = gpu_ctx
+    m, info = scenes.ball_pile(2, res=4, seed=1, height=2)
+    ctx.set_mesh(m.V_rest_soa, m.T_soa, m.restTriInv, m.vol, m.mu, m.lam, m.mass, m.dbc, m.energy)
+    ctx.set_surface(m.SVI, m.SFEdges, m.SF_soa, m.vCoDim)
+    ctx.set_state(m.V_soa)
+    bad = np.array([[-1, 0, -1, -1]], dtype=np.int32)  # a vertex against itself: d = 0
+    ctx.set_constraint_set(bad, bad[:0], np.empty((0, 2), dtype=np.int32))
+    ctx.barrier_energy(info["dHat"], 1e3, want=False)
+    with pytest.raises(L.IpcGpuError, match="NONPOSITIVE"):
+        ctx.fetch_iteration()
+    assert ctx.fetch_iteration().status == 0  # flags are per fetch
