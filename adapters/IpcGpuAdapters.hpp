@@ -114,9 +114,44 @@ public:
     }
 };
 
-// SelfCollisionHandler<3> statics (SelfCollisionHandler.hpp:23-232): same names, same argument meaning.
+// SelfCollisionHandler<3> statics (SelfCollisionHandler.hpp:23-232): same names, same SIGNATURES, same argument meaning -- the bodies of the
+// reference's functions are replaced one for one, Optimizer.cpp is not edited.  The device keeps the sets it built last; every function that
+// the reference hands an `activeSet` checks (size + 64-bit FNV hash of the ints) that it is the device-resident one and uploads it when it
+// is not (ipcgpu_set_constraint_set), so a caller that edits or swaps the vectors between calls is still served correctly.
+struct GpuSetTag { // size + hash of a constraint list
+    size_t n;
+    uint64_t h;
+};
 struct GpuSelfCollisionHandler {
-    static IpcGpuScene* gpu; // set once by main()
+    inline static IpcGpuScene* gpu = nullptr; // set once by main()
+    using SetTag = GpuSetTag;
+    inline static SetTag active_tag{ ~size_t(0), 0 }, para_tag{ ~size_t(0), 0 }; // what the device holds
+    // host copies of the sets the device holds (the reference hands the active set and the mollified sets to DIFFERENT functions, the
+    // upload takes all of them)
+    inline static std::vector<MMCVID> last_active, last_para;
+    inline static std::vector<std::pair<int, int>> last_para_e;
+
+    static uint64_t fnv(const int* p, size_t n)
+    {
+        uint64_t h = 1469598103934665603ull;
+        for (size_t i = 0; i < n; ++i) { h ^= (uint32_t)p[i]; h *= 1099511628211ull; }
+        return h;
+    }
+    static SetTag tag_of(const std::vector<MMCVID>& s) { return { s.size(), fnv(reinterpret_cast<const int*>(s.data()), 4 * s.size()) }; }
+    // make the device-resident sets equal to what the caller holds
+    static void ensureSets(const std::vector<MMCVID>& activeSet, const std::vector<MMCVID>& para, const std::vector<std::pair<int, int>>& paraE)
+    {
+        const SetTag ta = tag_of(activeSet), tp = tag_of(para);
+        if (ta.n == active_tag.n && ta.h == active_tag.h && tp.n == para_tag.n && tp.h == para_tag.h) return;
+        IpcGpuScene::check(gpu->ctx, ipcgpu_set_constraint_set(gpu->ctx, (int)activeSet.size(), reinterpret_cast<const int*>(activeSet.data()), (int)para.size(),
+                                         reinterpret_cast<const int*>(para.data()), reinterpret_cast<const int*>(paraE.data()), 0, nullptr),
+            "ipcgpu_set_constraint_set");
+        active_tag = ta;
+        para_tag = tp;
+        last_active = activeSet;
+        last_para = para;
+        last_para_e = paraE;
+    }
 
     // :2149-2478. `sh` is unused: the broad phase lives on the device.
     static void computeConstraintSet(const Mesh<3>& mesh, const SpatialHash<3>& /*sh*/, double dHat, std::vector<MMCVID>& constraintSet,
@@ -133,25 +168,47 @@ struct GpuSelfCollisionHandler {
         IpcGpuScene::check(gpu->ctx, ipcgpu_get_constraint_set(gpu->ctx, reinterpret_cast<int*>(constraintSet.data()), reinterpret_cast<int*>(paraEEMMCVIDSet.data()),
                                          reinterpret_cast<int*>(paraEEeIeJSet.data()), getPTEE ? reinterpret_cast<int*>(cs_PTEE.data()) : nullptr),
             "ipcgpu_get_constraint_set");
+        active_tag = tag_of(constraintSet);
+        para_tag = tag_of(paraEEMMCVIDSet);
+        last_active = constraintSet;
+        last_para = paraEEMMCVIDSet;
+        last_para_e = paraEEeIeJSet;
     }
-    // energy of the sets just built: Optimizer.cpp:3290-3353 collapses to one call
-    static double barrierEnergy(double dHat, double kappa)
+    // :64-81  (appends, like the reference: Optimizer.cpp:3493 relies on it)
+    static void evaluateConstraints(const Mesh<3>&, const std::vector<MMCVID>& activeSet, Eigen::VectorXd& val, double /*coef*/ = 1.0)
     {
-        double E = 0.0;
-        IpcGpuScene::check(gpu->ctx, ipcgpu_barrier_energy(gpu->ctx, dHat, kappa, &E), "ipcgpu_barrier_energy");
-        return E;
+        ensureSets(activeSet, last_para, last_para_e);
+        const int start = (int)val.size();
+        val.conservativeResize(start + activeSet.size());
+        IpcGpuScene::check(gpu->ctx, ipcgpu_evaluate_constraints(gpu->ctx, val.data() + start, (int)activeSet.size()), "ipcgpu_evaluate_constraints");
     }
-    // :84-148 + :2990-3045 (input = b'(d) is recomputed on the device)
-    static void leftMultiplyConstraintJacobianT(const Mesh<3>&, const std::vector<MMCVID>&, const Eigen::VectorXd&, Eigen::VectorXd& output_incremental, double dHat,
-        double kappa)
+    // :84-148  out += coef * mult * input[c] * grad d_c
+    static void leftMultiplyConstraintJacobianT(const Mesh<3>&, const std::vector<MMCVID>& activeSet, const Eigen::VectorXd& input, Eigen::VectorXd& output_incremental,
+        double coef = 1.0)
     {
-        IpcGpuScene::check(gpu->ctx, ipcgpu_barrier_gradient(gpu->ctx, dHat, kappa, output_incremental.data()), "ipcgpu_barrier_gradient");
+        ensureSets(activeSet, last_para, last_para_e);
+        IpcGpuScene::check(gpu->ctx, ipcgpu_constraint_jacobian_t(gpu->ctx, input.data(), (int)activeSet.size(), coef, output_incremental.data()),
+            "ipcgpu_constraint_jacobian_t");
     }
-    // :418-561 + :3049-3201
-    static void augmentIPHessian(const Mesh<3>&, const std::vector<MMCVID>&, LinSysSolver<Eigen::VectorXi, Eigen::VectorXd>* mtr, double dHat, double kappa,
+    // :2990-3045
+    static void augmentParaEEGradient(const Mesh<3>&, const std::vector<MMCVID>& paraEEMMCVIDSet, const std::vector<std::pair<int, int>>& paraEEeIeJSet,
+        Eigen::VectorXd& grad_inc, double dHat, double coef)
+    {
+        ensureSets(std::vector<MMCVID>(last_active), paraEEMMCVIDSet, paraEEeIeJSet);
+        IpcGpuScene::check(gpu->ctx, ipcgpu_para_ee_gradient(gpu->ctx, dHat, coef, grad_inc.data()), "ipcgpu_para_ee_gradient");
+    }
+    // :418-561 (reference signature).  The device call also adds the mollified pairs' Hessian (augmentParaEEHessian, :3049-3201), so that
+    // function is a no-op below.
+    static void augmentIPHessian(const Mesh<3>&, const std::vector<MMCVID>& activeSet, LinSysSolver<Eigen::VectorXi, Eigen::VectorXd>* mtr, double dHat, double coef,
         bool projectDBC)
     {
-        IpcGpuScene::check(gpu->ctx, ipcgpu_barrier_hessian(gpu->ctx, dHat, kappa, projectDBC, mtr->get_a().data()), "ipcgpu_barrier_hessian");
+        ensureSets(activeSet, last_para, last_para_e);
+        IpcGpuScene::check(gpu->ctx, ipcgpu_barrier_hessian(gpu->ctx, dHat, coef, projectDBC, mtr->get_a().data()), "ipcgpu_barrier_hessian");
+    }
+    static void augmentParaEEHessian(const Mesh<3>&, const std::vector<MMCVID>&, const std::vector<std::pair<int, int>>&, LinSysSolver<Eigen::VectorXi, Eigen::VectorXd>*, double,
+        double, bool)
+    {
+        // already added by augmentIPHessian (one device pass over both lists)
     }
     // :690-866
     static void largestFeasibleStepSize_TightInclusion(const Mesh<3>&, const SpatialHash<3>&, const Eigen::VectorXd& searchDir, double tolerance,
@@ -172,6 +229,21 @@ struct GpuSelfCollisionHandler {
         IpcGpuScene::check(gpu->ctx, ipcgpu_ccd_full_ti(gpu->ctx, tolerance, tight_inclusion_vf_err.data(), tight_inclusion_ee_err.data(), &stepSize, nullptr),
             "ipcgpu_ccd_full_ti");
     }
+    // :3254-3340 (edge-triangle part; see include/ipcgpu.h for the point-in-tetrahedron remark)
+    static bool checkEdgeTriIntersectionIfAny(const Mesh<3>&, const SpatialHash<3>&)
+    {
+        int ok = 0;
+        IpcGpuScene::check(gpu->ctx, ipcgpu_intersection_free(gpu->ctx, &ok), "ipcgpu_intersection_free");
+        return ok != 0;
+    }
 };
+
+// Mesh<3>::checkInversion(bool mute) (Mesh.cpp:745-763) on the device state
+inline bool gpuCheckInversion(IpcGpuScene& gpu)
+{
+    int n = 0;
+    IpcGpuScene::check(gpu.ctx, ipcgpu_check_inversion(gpu.ctx, &n), "ipcgpu_check_inversion");
+    return n == 0;
+}
 
 } // namespace IPC

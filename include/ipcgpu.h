@@ -92,6 +92,8 @@ typedef struct ipcgpu_iteration {
     int status;                              /* IPCGPU_OK or the first deferred error (d <= 0, capacity, pattern) -- same on every rank */
     uint64_t n_full_ccd_candidates;          /* candidates of the last full CCD (this rank) */
     uint64_t ti_warnings;                    /* conservative early-outs of the Tight-Inclusion searches since the last fetch (should be 0) */
+    int n_inverted_tets;                     /* last ipcgpu_check_inversion (summed over ranks) */
+    int n_intersected_triangles;             /* last ipcgpu_intersection_free: surface triangles crossed by an edge (summed over ranks) */
 } ipcgpu_iteration;
 /* Synchronises once, completes the deferred cross-rank scalars (collective: every rank must call it), fills `out`, clears the
  * deferred error flags and returns out->status. */
@@ -168,8 +170,28 @@ int ipcgpu_barrier_energy(ipcgpu_ctx* ctx, double dHat, double kappa, double* E)
 /* g += kappa*J^T b' (+ mollified terms)  (leftMultiplyConstraintJacobianT :84-148, augmentParaEEGradient :2990-3045).
  * g_inout != NULL: host vector uploaded, accumulated, downloaded; NULL: the device-resident gradient is accumulated. */
 int ipcgpu_barrier_gradient(ipcgpu_ctx* ctx, double dHat, double kappa, double* g_inout);
+/* The reference's own two-step form of the barrier gradient (Optimizer.cpp:3492-3502), for a caller that keeps that code unchanged:
+ *   evaluateConstraints (:64-81): val[c] = squared distance of active pair c (n = size of the active set on this context);
+ *   leftMultiplyConstraintJacobianT (:84-148): g_inout += coef * mult_c * input[c] * grad d_c  (input = b'(d) in the reference);
+ *   augmentParaEEGradient (:2990-3045): the mollified pairs' term.
+ * ipcgpu_barrier_gradient = the three fused (b' evaluated on the device). */
+int ipcgpu_evaluate_constraints(ipcgpu_ctx* ctx, double* val, int n);
+int ipcgpu_constraint_jacobian_t(ipcgpu_ctx* ctx, const double* input, int n, double coef, double* g_inout);
+int ipcgpu_para_ee_gradient(ipcgpu_ctx* ctx, double dHat, double kappa, double* g_inout);
 /* CSR += makePD(kappa*mult*(b'' grad d grad d^T + b' hess d))  (augmentIPHessian :418-561, augmentParaEEHessian :3049-3201) */
 int ipcgpu_barrier_hessian(ipcgpu_ctx* ctx, double dHat, double kappa, int projectDBC, double* a_inout);
+
+/* ---- line-search safeguards (Optimizer.cpp:2709-2733, 2799-2811), so that a line-search trial -- step forward, checks, constraint set,
+ * energies -- is one stream ------------------------------------------------------------------------------------------------------ */
+/* Mesh::checkInversion(mute) (Mesh.cpp:715-763): number of tets with mu, lambda != 0 whose current edge matrix has det < 0 (0 = no
+ * inversion).  NULL: deferred, reported by ipcgpu_fetch_iteration. */
+int ipcgpu_check_inversion(ipcgpu_ctx* ctx, int* n_inverted);
+/* SelfCollisionHandler::checkEdgeTriIntersectionIfAny (SelfCollisionHandler.cpp:3254-3296) with the hash query of
+ * SpatialHash::queryTriangleForEdges done on the device: *ok = 1 iff no surface edge crosses a surface triangle (exact orient3d +
+ * the reference's full-pivot solve, IglUtils.hpp:214-265).  Rebuilds the static grid at the current positions.  The point-in-tetrahedron
+ * part of the reference (:3299-3337) only concerns codimension-0 components (loose points), which this path does not carry.
+ * NULL: deferred, reported by ipcgpu_fetch_iteration. */
+int ipcgpu_intersection_free(ipcgpu_ctx* ctx, int* ok);
 
 /* ---- CCD step bound (Tight-Inclusion), Optimizer.cpp:1884-2040 ----------------------------------------------------- */
 /* capacity (pairs) of the device CCD candidate list; default 2^23 */

@@ -252,6 +252,8 @@ int ccd_narrow(ipcgpu_ctx* ctx, const int2* cand, const int* n32, const unsigned
 int ccd_build_swept(ipcgpu_ctx* ctx, double h);
 int ccd_full(ipcgpu_ctx* ctx, double tol, const double* err_vf, const double* err_ee);
 int ccd_read_back(ipcgpu_ctx* ctx, double* alpha_out);
+int safeguard_inversion(ipcgpu_ctx* ctx);     // safeguard.cu
+int safeguard_intersections(ipcgpu_ctx* ctx); // safeguard.cu
 
 // deferred error flags of the iteration state -> status code (first raised flag wins) and message
 static int status_from_flags(ipcgpu_ctx* ctx, const int* f)
@@ -972,6 +974,82 @@ int ipcgpu_barrier_gradient(ipcgpu_ctx* ctx, double dHat, double kappa, double* 
     return IPCGPU_OK;
 }
 
+// host gradient in/out around a kernel that accumulates into the device gradient (addCoeff-like semantics: rank 0 contributes the input)
+static int gradient_roundtrip_begin(ipcgpu_ctx* ctx, const double* g_in)
+{
+    if (ctx->rank == 0) CK(cudaMemcpyAsync(ctx->g.p, g_in, (size_t)3 * ctx->nV * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    else CK(cudaMemsetAsync(ctx->g.p, 0, (size_t)3 * ctx->nV * sizeof(double), ctx->stream));
+    return IPCGPU_OK;
+}
+static int gradient_roundtrip_end(ipcgpu_ctx* ctx, double* g_out)
+{
+    if (ctx->nranks > 1) {
+        int rc = ipcgpu_allreduce_grad_hess(ctx, 1, 0);
+        if (rc) return rc;
+    }
+    CK(cudaMemcpyAsync(g_out, ctx->g.p, (size_t)3 * ctx->nV * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return IPCGPU_OK;
+}
+
+int ipcgpu_evaluate_constraints(ipcgpu_ctx* ctx, double* val, int n)
+{
+    REQUIRE(ctx->surface_ready, IPCGPU_ERR_STATE, "ipcgpu_set_surface first");
+    CK(cudaSetDevice(ctx->device));
+    ContactWork& w = ctx->cw;
+    if (w.nC < 0) {
+        int rc = contact_sync_counts(ctx);
+        if (rc) return rc;
+    }
+    REQUIRE(n == w.nC && (val || n == 0), IPCGPU_ERR_ARG, "ipcgpu_evaluate_constraints: n must be the size of the active set on this context");
+    ALLOC(w.bval, (size_t)std::max(w.cap, 1));
+    BarrierArgs p = barrier_args(ctx, 1.0, 1.0, 0);
+    p.cs = w.act.p; p.nC = w.counters.p + 0; // this context's own active list (what ipcgpu_get_constraint_set returns), not the exchanged one
+    evaluate_constraints(p, w.bval.p, ctx->stream);
+    ++ctx->launches;
+    CK(cudaGetLastError());
+    if (n) CK(cudaMemcpyAsync(val, w.bval.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return IPCGPU_OK;
+}
+
+int ipcgpu_constraint_jacobian_t(ipcgpu_ctx* ctx, const double* input, int n, double coef, double* g_inout)
+{
+    REQUIRE(ctx->surface_ready, IPCGPU_ERR_STATE, "ipcgpu_set_surface first");
+    REQUIRE(g_inout != nullptr, IPCGPU_ERR_ARG, "null gradient");
+    CK(cudaSetDevice(ctx->device));
+    ContactWork& w = ctx->cw;
+    if (w.nC < 0) {
+        int rc = contact_sync_counts(ctx);
+        if (rc) return rc;
+    }
+    REQUIRE(n == w.nC && (input || n == 0), IPCGPU_ERR_ARG, "ipcgpu_constraint_jacobian_t: n must be the size of the active set on this context");
+    REQUIRE(!(ctx->nranks > 1 && ctx->lists_local), IPCGPU_ERR_STATE, "per-constraint input needs the replicated sets (ipcgpu_set_contact_partition(0))");
+    ALLOC(w.bval, (size_t)std::max(w.cap, 1));
+    int rc = gradient_roundtrip_begin(ctx, g_inout);
+    if (rc) return rc;
+    if (n) CK(cudaMemcpyAsync(w.bval.p, input, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    BarrierArgs p = barrier_args(ctx, 1.0, 1.0, 0);
+    p.cs = w.act.p; p.nC = w.counters.p + 0;
+    constraint_jacobian_t(p, w.bval.p, coef, ctx->g.p, ctx->stream);
+    ++ctx->launches;
+    CK(cudaGetLastError());
+    return gradient_roundtrip_end(ctx, g_inout);
+}
+
+int ipcgpu_para_ee_gradient(ipcgpu_ctx* ctx, double dHat, double kappa, double* g_inout)
+{
+    REQUIRE(ctx->surface_ready, IPCGPU_ERR_STATE, "ipcgpu_set_surface first");
+    REQUIRE(g_inout != nullptr, IPCGPU_ERR_ARG, "null gradient");
+    CK(cudaSetDevice(ctx->device));
+    int rc = gradient_roundtrip_begin(ctx, g_inout);
+    if (rc) return rc;
+    para_gradient(barrier_args(ctx, dHat, kappa, 0), ctx->g.p, ctx->stream);
+    ++ctx->launches;
+    CK(cudaGetLastError());
+    return gradient_roundtrip_end(ctx, g_inout);
+}
+
 int ipcgpu_barrier_hessian(ipcgpu_ctx* ctx, double dHat, double kappa, int projectDBC, double* a_inout)
 {
     REQUIRE(ctx->surface_ready, IPCGPU_ERR_STATE, "ipcgpu_set_surface first");
@@ -996,6 +1074,51 @@ int ipcgpu_barrier_hessian(ipcgpu_ctx* ctx, double dHat, double kappa, int proje
             clear_flag(ctx, FLAG_SET_CAPACITY);
             return status_from_flags(ctx, only);
         }
+    }
+    return IPCGPU_OK;
+}
+
+// ---- line-search safeguards -----------------------------------------------------------------------
+static int reduce_checks(ipcgpu_ctx* ctx)
+{
+    if (ctx->nranks > 1 && ctx->checks_local) {
+        int r = g_nccl.AllReduce(ctx->iter.p->checks, ctx->iter.p->checks, 2, kNcclInt32, kNcclSum, ctx->nccl_comm, ctx->stream);
+        REQUIRE(r == 0, IPCGPU_ERR_NCCL, "ncclAllReduce(safeguard counts) failed");
+    }
+    ctx->checks_local = false;
+    return IPCGPU_OK;
+}
+
+int ipcgpu_check_inversion(ipcgpu_ctx* ctx, int* n_inverted)
+{
+    REQUIRE(ctx->maps_ready, IPCGPU_ERR_STATE, "ipcgpu_set_mesh first");
+    CK(cudaSetDevice(ctx->device));
+    int rc = safeguard_inversion(ctx);
+    REQUIRE(rc == 0, rc, "inversion check launch failed");
+    ctx->checks_local = true;
+    if (n_inverted) {
+        CK(cudaMemsetAsync(&ctx->iter.p->checks[1], 0, sizeof(int), ctx->stream)); // (the partner count is not pending: keep the sum clean)
+        if ((rc = reduce_checks(ctx))) return rc;
+        if ((rc = fetch_iter_state(ctx))) return rc;
+        *n_inverted = ctx->h_iter->checks[0];
+    }
+    return IPCGPU_OK;
+}
+
+int ipcgpu_intersection_free(ipcgpu_ctx* ctx, int* ok)
+{
+    REQUIRE(ctx->surface_ready, IPCGPU_ERR_STATE, "ipcgpu_set_surface first");
+    CK(cudaSetDevice(ctx->device));
+    cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_HASH);
+    int rc = safeguard_intersections(ctx);
+    ctx->prof_end(pe);
+    REQUIRE(rc == 0, rc, "intersection check launch failed");
+    ctx->checks_local = true;
+    if (ok) {
+        CK(cudaMemsetAsync(&ctx->iter.p->checks[0], 0, sizeof(int), ctx->stream));
+        if ((rc = reduce_checks(ctx))) return rc;
+        if ((rc = fetch_iter_state(ctx))) return rc;
+        *ok = ctx->h_iter->checks[1] == 0 ? 1 : 0;
     }
     return IPCGPU_OK;
 }
@@ -1043,7 +1166,10 @@ int ipcgpu_fetch_iteration(ipcgpu_ctx* ctx, ipcgpu_iteration* out)
         int r = g_nccl.AllReduce(ctx->iter.p->flags, ctx->iter.p->flags, 8, kNcclInt32, kNcclMax, ctx->nccl_comm, ctx->stream);
         ctx->prof_end(pe);
         REQUIRE(r == 0, IPCGPU_ERR_NCCL, "ncclAllReduce(status flags) failed");
+        int rcc = reduce_checks(ctx);
+        if (rcc) return rcc;
     }
+    ctx->checks_local = false;
     int rc = ccd_read_back(ctx, nullptr);
     if (rc) return rc;
     const IterState& h = *ctx->h_iter;
@@ -1059,6 +1185,8 @@ int ipcgpu_fetch_iteration(ipcgpu_ctx* ctx, ipcgpu_iteration* out)
     out->n_candidates = h.n_set[2];
     out->n_full_ccd_candidates = h.n_full_cand;
     out->ti_warnings = (uint64_t)h.flags[FLAG_TI_WARNINGS];
+    out->n_inverted_tets = h.checks[0];
+    out->n_intersected_triangles = h.checks[1];
     ContactWork& w = ctx->cw;
     w.nC = h.n_set[0]; w.nP = h.n_set[1]; w.nK = h.n_set[2];
     const int status = status_from_flags(ctx, h.flags);

@@ -217,6 +217,62 @@ __global__ void __launch_bounds__(128) k_barrier_gradient(BarrierArgs p, double*
 }
 
 // -----------------------------------------------------------------------------------------------------------
+// the reference's own two-step form of the gradient (Optimizer.cpp:3492-3499): evaluateConstraints (:64-81) hands the squared
+// distances of the active set to the host, which maps them through b'(d) and passes them back to leftMultiplyConstraintJacobianT
+// (:84-148): out += coef * mult_c * input_c * grad d_c.  Active set only (the mollified pairs go through augmentParaEEGradient).
+// -----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_evaluate_constraints(BarrierArgs p, double* __restrict__ val)
+{
+    const int n = *p.nC;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+        const PairStencil s = decode(p.cs[c]);
+        V3 x[4];
+        for (int k = 0; k < s.nv; ++k) x[k] = load_vertex(p.V, p.nV, s.v[k]);
+        val[c] = pair_distance(s, x);
+    }
+}
+__global__ void __launch_bounds__(128) k_constraint_jacobian_t(BarrierArgs p, const double* __restrict__ input, double coef, double* __restrict__ g)
+{
+    const ListRange lr = list_range(p, false);
+    for (int c = lr.cb + blockIdx.x * blockDim.x + threadIdx.x; c < lr.ce; c += gridDim.x * blockDim.x) {
+        const PairStencil s = decode(p.cs[c]);
+        V3 x[4];
+        for (int k = 0; k < s.nv; ++k) x[k] = load_vertex(p.V, p.nV, s.v[k]);
+        double gd[12];
+        pair_derivs(s, x, gd, false, [](int, int, double) {});
+        const double w = coef * s.mult * input[c];
+        for (int k = 0; k < s.nv; ++k)
+            for (int q = 0; q < 3; ++q) atomicAdd(g + 3 * (size_t)s.v[k] + q, w * gd[3 * k + q]);
+    }
+}
+// augmentParaEEGradient (:2990-3045) alone: the mollified pairs' share of k_barrier_gradient
+__global__ void __launch_bounds__(128) k_para_gradient(BarrierArgs p, double* __restrict__ g)
+{
+    const ListRange lr = list_range(p, false);
+    for (int c = lr.pb + blockIdx.x * blockDim.x + threadIdx.x; c < lr.pe; c += gridDim.x * blockDim.x) {
+        const int4 mm = p.para[c];
+        const PairStencil s = decode(mm);
+        V3 x[4];
+        for (int k = 0; k < s.nv; ++k) x[k] = load_vertex(p.V, p.nV, s.v[k]);
+        double gd[12];
+        const double d = pair_derivs(s, x, gd, false, [](int, int, double) {});
+        double b, db, d2b;
+        barrier_all(d, p.dHat, b, db, d2b);
+        int ev[4];
+        para_edge_stencil(mm, p.para_e[c], p.SE, ev);
+        V3 ex[4];
+        for (int k = 0; k < 4; ++k) ex[k] = load_vertex(p.V, p.nV, ev[k]);
+        double eg[12];
+        const double e = mollifier(ex, eps_x_rest(p.Vrest, p.nV, ev[0], ev[1], ev[2], ev[3]), eg, false, [](int, int, double) {});
+        for (int k = 0; k < 4; ++k)
+            for (int q = 0; q < 3; ++q) atomicAdd(g + 3 * (size_t)ev[k] + q, p.kappa * b * eg[3 * k + q]);
+        const double w = p.kappa * e * db;
+        for (int k = 0; k < s.nv; ++k)
+            for (int q = 0; q < 3; ++q) atomicAdd(g + 3 * (size_t)s.v[k] + q, w * gd[3 * k + q]);
+    }
+}
+
+// -----------------------------------------------------------------------------------------------------------
 // Hessian: makePD( kappa*mult*(b'' g g^T + b' H_d) ) scattered into the CSR (upper triangle)
 //   pass 1 (thread per pair)  : unprojected block, zero-padded to 12x12, to global memory (144 contiguous doubles per pair)
 //   pass 2 (warp per pair)    : parallel-order Jacobi eigen-solver on the 12x12 (6 disjoint rotations per round, 11 rounds
@@ -584,6 +640,9 @@ void barrier_gradient(const BarrierArgs& p, double* g, cudaStream_t st)
 {
     k_barrier_gradient<<<kSMs * 4, 128, 0, st>>>(p, g);
 }
+void evaluate_constraints(const BarrierArgs& p, double* val, cudaStream_t st) { k_evaluate_constraints<<<kSMs * 2, 256, 0, st>>>(p, val); }
+void constraint_jacobian_t(const BarrierArgs& p, const double* input, double coef, double* g, cudaStream_t st) { k_constraint_jacobian_t<<<kSMs * 4, 128, 0, st>>>(p, input, coef, g); }
+void para_gradient(const BarrierArgs& p, double* g, cudaStream_t st) { k_para_gradient<<<kSMs, 128, 0, st>>>(p, g); }
 void barrier_hessian(const BarrierArgs& p, double* a, int* flags, double* Hraw, int* rows, int* psd, int* n_owned, int capacity, cudaStream_t st)
 {
     cudaMemsetAsync(n_owned, 0, sizeof(int), st);

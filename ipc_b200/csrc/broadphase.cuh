@@ -71,7 +71,7 @@ DEV int upper_bound_u64(const unsigned long long* __restrict__ keys, int n, unsi
 struct SortedGrid {
     const unsigned long long* keys; // sorted cell keys
     const int* ids;                 // primitive id per entry
-    const Box* boxes;               // primitive boxes gathered in sorted order (coalesced candidate scan)
+    const QEntry* ent;              // quantised box + id per entry, in sorted order (coalesced 16-byte candidate scan)
     int n;
     const unsigned* tab_key;        // hash table: cell key (0xffffffff = empty)
     const int2* tab_range;          //             [first, last+1) entries of that cell in the sorted arrays
@@ -91,12 +91,34 @@ DEV int2 cell_lookup(const SortedGrid& sg, unsigned key)
     }
 }
 
+// conservative 16-bit quantisation of a box on the grid's lattice
+struct QBox {
+    int lo[3], hi[3];
+};
+DEV QBox quantize_box(const Grid& g, const Box& b)
+{
+    const double o[3] = { g.ox, g.oy, g.oz };
+    QBox q;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        q.lo[a] = min(max((int)floor((b.lo[a] - o[a]) * g.q_inv) - 1, 0), 65535);
+        q.hi[a] = min(max((int)ceil((b.hi[a] - o[a]) * g.q_inv) + 1, 0), 65535);
+    }
+    return q;
+}
+DEV bool qoverlap(const QBox& a, const uint4& e)
+{
+    // e = {lo0 | lo1 << 16, lo2 | hi0 << 16, hi1 | hi2 << 16, id}
+    const int l0 = e.x & 0xffff, l1 = e.x >> 16, l2 = e.y & 0xffff, h0 = e.y >> 16, h1 = e.z & 0xffff, h2 = e.z >> 16;
+    return !(a.lo[0] > h0 || l0 > a.hi[0] || a.lo[1] > h1 || l1 > a.hi[1] || a.lo[2] > h2 || l2 > a.hi[2]);
+}
+
 DEV bool boxes_overlap(const Box& a, const Box& b)
 {
     return !(a.lo[0] > b.hi[0] || b.lo[0] > a.hi[0] || a.lo[1] > b.hi[1] || b.lo[1] > a.hi[1] || a.lo[2] > b.hi[2] || b.lo[2] > a.hi[2]);
 }
 
-// warp-cooperative scan: calls f(hit, id, box) with hit = true on every registered primitive whose box overlaps the (already
+// warp-cooperative scan: calls f(hit, id) with hit = true on every registered primitive whose (quantised) box overlaps the (already
 // inflated) query box.  All 32 lanes must call this together and f is called by all 32 lanes together (hit = false on the lanes
 // that have nothing), so that f can aggregate its output over the warp.
 // The <= 27 cells are looked up by 27 lanes at once; the <= 9 rows (runs of consecutive entries) are then walked as ONE flattened
@@ -146,24 +168,16 @@ DEV void warp_scan_candidates(const Grid& g, const SortedGrid& sg, const Box& qb
             if (j >= inc[r - 1]) k = st[r] + (j - inc[r - 1]);
         return k;
     };
-    // software pipeline: the loads of iteration i+1 are in flight while f handles iteration i
-    Box bn = qb;
-    int idn = -1;
-    if (lane < total) {
-        const int k = locate(lane);
-        bn = sg.boxes[k];
-        idn = sg.ids[k];
-    }
+    // software pipeline: the load of iteration i+1 is in flight while f handles iteration i
+    const QBox qq = quantize_box(g, qb);
+    const uint4* __restrict__ ent = reinterpret_cast<const uint4*>(sg.ent);
+    uint4 en = make_uint4(0u, 0u, 0u, 0u);
+    if (lane < total) en = __ldg(ent + locate(lane));
     for (int j = lane; j - lane < total; j += 32) {
-        const Box b = bn;
-        const int id = idn;
+        const uint4 e = en;
         const bool in = j < total;
-        if (j + 32 < total) {
-            const int k = locate(j + 32);
-            bn = sg.boxes[k];
-            idn = sg.ids[k];
-        }
-        f(in && boxes_overlap(qb, b), id, b); // convergent: every lane calls f
+        if (j + 32 < total) en = __ldg(ent + locate(j + 32));
+        f(in && qoverlap(qq, e), (int)e.w); // convergent: every lane calls f
     }
 }
 

@@ -169,12 +169,12 @@ __global__ void __launch_bounds__(256) k_ccd_pairs_pt(const Grid* __restrict__ g
     for (int svI = q0; svI < min(q0 + kPairQueriesPerWarp, last); ++svI) {
         Box qb = vboxes[svI];
         for (int k = 0; k < 3; ++k) { qb.lo[k] -= radius; qb.hi[k] += radius; }
-        warp_scan_candidates(g, tg, qb, lane, [&](bool hit, int sfI, const Box&) { warp_push_pair(stage, out, hit, svI, sfI, lane); });
+        warp_scan_candidates(g, tg, qb, lane, [&](bool hit, int sfI) { warp_push_pair(stage, out, hit, svI, sfI, lane); });
     }
     pair_stage_flush(stage, out);
 }
 // queries are the entries of the sorted swept-edge grid itself ([first, last) = sorted positions); each walks only the entries behind it
-__global__ void __launch_bounds__(256) k_ccd_pairs_ee(const Grid* __restrict__ gp, SortedGrid eg, const IterState* __restrict__ st, int first, int last, PairOut out)
+__global__ void __launch_bounds__(256) k_ccd_pairs_ee(const Grid* __restrict__ gp, SortedGrid eg, const Box* __restrict__ eboxes, const IterState* __restrict__ st, int first, int last, PairOut out)
 {
     __shared__ PairStage stage;
     pair_stage_init(stage);
@@ -184,49 +184,52 @@ __global__ void __launch_bounds__(256) k_ccd_pairs_ee(const Grid* __restrict__ g
     const int q0 = first + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kPairQueriesPerWarp;
     for (int i = q0; i < min(q0 + kPairQueriesPerWarp, last); ++i) {
         const int eI = eg.ids[i];
-        const Box eb = eg.boxes[i];
-        Box qb = eb;
+        Box qb = eboxes[eI];
         for (int k = 0; k < 3; ++k) { qb.lo[k] -= radius; qb.hi[k] += radius; }
-        warp_scan_candidates(g, eg, qb, lane, [&](bool hit, int eJ, const Box& jb) {
-            // swept-AABB test of queryEdgeForEdgesWithBBoxCheck (SpatialHash.hpp:819-828); the boxes hold {x, x+alpha p}
-            bool sep = !hit;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) sep = sep || (jb.lo[c] - eb.hi[c] > 0.0) || (eb.lo[c] - jb.hi[c] > 0.0);
-            warp_push_pair(stage, out, !sep, min(eI, eJ), max(eI, eJ), lane);
-        }, i);
+        // (the exact swept-AABB test of queryEdgeForEdgesWithBBoxCheck is applied by k_ccd_filter_ee on the double boxes)
+        warp_scan_candidates(g, eg, qb, lane, [&](bool hit, int eJ) { warp_push_pair(stage, out, hit, min(eI, eJ), max(eI, eJ), lane); }, i);
     }
     pair_stage_flush(stage, out);
 }
 // ---- phase 2: one THREAD per pair: the reference's voxel-range overlap (its hash query) and the index filters
-__global__ void __launch_bounds__(256) k_ccd_filter_pt(SurfArgs s, const int2* __restrict__ pairs, const unsigned* __restrict__ nPairs, const int* __restrict__ vmin,
+__global__ void __launch_bounds__(256) k_ccd_filter_pt(SurfArgs s, const int2* __restrict__ pairs, const unsigned* __restrict__ nPairs, unsigned cap, const int* __restrict__ vmin,
     const int* __restrict__ vmax, CandOut out)
 {
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= *nPairs) return;
+    const unsigned nP = min(*nPairs, cap);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nP; i += gridDim.x * blockDim.x) { // grid-stride over the device-resident count
     const int svI = pairs[i].x, sfI = pairs[i].y;
     const int vI = s.SVI[svI];
     int tv[3] = { s.SF[sfI], s.SF[(size_t)s.nSF + sfI], s.SF[(size_t)2 * s.nSF + sfI] };
-    if (vI == tv[0] || vI == tv[1] || vI == tv[2]) return;
+    if (vI == tv[0] || vI == tv[1] || vI == tv[2]) continue;
     int lo[3], hi[3];
     prim_range(vmin, vmax, tv, 3, lo, hi);
-    if (!ranges_overlap(vmin + 3 * (size_t)vI, vmax + 3 * (size_t)vI, lo, hi)) return; // the reference's hash would not pair them
-    if ((cod_v(s, vI) < 3 && cod_v(s, tv[0]) < 3) || (dbc_v(s, vI) && dbc_v(s, tv[0]) && dbc_v(s, tv[1]) && dbc_v(s, tv[2]))) return;
+    if (!ranges_overlap(vmin + 3 * (size_t)vI, vmax + 3 * (size_t)vI, lo, hi)) continue; // the reference's hash would not pair them
+    if ((cod_v(s, vI) < 3 && cod_v(s, tv[0]) < 3) || (dbc_v(s, vI) && dbc_v(s, tv[0]) && dbc_v(s, tv[1]) && dbc_v(s, tv[2]))) continue;
     push_cand(out, make_int2(-svI - 1, sfI));
+    }
 }
-__global__ void __launch_bounds__(256) k_ccd_filter_ee(SurfArgs s, const int2* __restrict__ pairs, const unsigned* __restrict__ nPairs, const int* __restrict__ vmin,
-    const int* __restrict__ vmax, CandOut out)
+__global__ void __launch_bounds__(256) k_ccd_filter_ee(SurfArgs s, const int2* __restrict__ pairs, const unsigned* __restrict__ nPairs, unsigned cap, const int* __restrict__ vmin,
+    const int* __restrict__ vmax, const Box* __restrict__ eboxes, CandOut out)
 {
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= *nPairs) return;
+    const unsigned nP = min(*nPairs, cap);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nP; i += gridDim.x * blockDim.x) {
     const int eI = pairs[i].x, eJ = pairs[i].y;
     const int a[2] = { s.SE[2 * eI], s.SE[2 * eI + 1] }, b[2] = { s.SE[2 * eJ], s.SE[2 * eJ + 1] };
-    if (a[0] == b[0] || a[0] == b[1] || a[1] == b[0] || a[1] == b[1]) return;
+    if (a[0] == b[0] || a[0] == b[1] || a[1] == b[0] || a[1] == b[1]) continue;
     int qlo[3], qhi[3], lo[3], hi[3];
     prim_range(vmin, vmax, a, 2, qlo, qhi);
     prim_range(vmin, vmax, b, 2, lo, hi);
-    if (!ranges_overlap(qlo, qhi, lo, hi)) return;
-    if ((cod_v(s, a[0]) < 3 && cod_v(s, b[0]) < 3) || (dbc_v(s, a[0]) && dbc_v(s, a[1]) && dbc_v(s, b[0]) && dbc_v(s, b[1]))) return;
+    if (!ranges_overlap(qlo, qhi, lo, hi)) continue;
+    {   // swept-AABB test of queryEdgeForEdgesWithBBoxCheck (SpatialHash.hpp:819-828) on the exact boxes {x, x + alpha p} of both edges
+        const Box eb = eboxes[eI], jb = eboxes[eJ];
+        bool sep = false;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) sep = sep || (jb.lo[c] - eb.hi[c] > 0.0) || (eb.lo[c] - jb.hi[c] > 0.0);
+        if (sep) continue;
+    }
+    if ((cod_v(s, a[0]) < 3 && cod_v(s, b[0]) < 3) || (dbc_v(s, a[0]) && dbc_v(s, a[1]) && dbc_v(s, b[0]) && dbc_v(s, b[1]))) continue;
     push_cand(out, make_int2(eI, eJ));
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -981,6 +984,270 @@ __device__ int pair_ccd(bool vf, const TiPair& P, const NarrowArgs& a, DBox* buf
     return hit;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// group pass: EIGHT LANES per surviving pair (four pairs per warp).  A lane is one corner of the parameter box being evaluated, the
+// co-domain interval of a coordinate is a 3-step shuffle min/max inside the group -- the same corner-parallel evaluation as the narrow
+// levels of the warp-level pass, with the same arithmetic per corner, hence the same decisions and the same time of impact.  What
+// changes is the concurrency: the interval search is a chain of short dependent steps (evaluate a level, pick K1/K2, split), and one
+// warp per pair left three quarters of its lanes idle on the 1-4 box levels that make up almost every search, at 24 pairs in flight
+// per SM.  Four pairs per warp quadruple the searches in flight for the same registers and shared memory.  Levels are walked one box
+// at a time per group; the split pass handles eight boxes per round.  A pair whose level outgrows the group's buffer (kGrpCap boxes)
+// is handed to the warp-level pass, which restarts it.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kGrpCap = 44;       // boxes per level buffer per group (two buffers per group: 4 x 2 x 44 x 32 B = 11.3 KB per warp; static smem stays < 48 KB)
+constexpr int kGrpWarpsPerCta = 4;
+
+__device__ int ti_root_finder_grp(bool vf, const TiPair& P, const double* tol, double co_tol, double max_t, const double* err, double ms, int max_itr, DBox* sA, DBox* sB,
+    int gl, unsigned gmask, double& toi, double& out_tol, int* __restrict__ warn, const unsigned long long* best)
+{
+    const bool check_t = (max_t != 1.0);
+    const double INF = __longlong_as_double(0x7ff0000000000000ll);
+    const int ci = gl >> 2, cj = (gl >> 1) & 1, cl = gl & 1;
+    DBox* cur = sA;
+    DBox* nxt = sB;
+    if (gl == 0) cur[0] = DBox{ 0ull, 0ull, 0ull, 0u, 0u };
+    __syncwarp(gmask);
+    int n = 1;
+    double toi_skip = INF;
+    bool use_skip = false;
+    long long refine = 0;
+    double temp_toi = INF, temp_out_tol = co_tol;
+    out_tol = co_tol;
+    toi = INF;
+    unsigned long long bo_cur = best ? *reinterpret_cast<const volatile unsigned long long*>(best) : 0ull;
+    while (n > 0) {
+        Key3 k1 = { INF, INF, INF }, k2 = { INF, INF, INF };
+        unsigned p1 = 0, p2 = 0;
+        double a1max = 0.0;
+        int visited = 0;
+        // exact pruning against the running device-wide minimum (see ti_root_finder); the value used here was requested one level ago
+        double t_prune = INF;
+        if (best) {
+            t_prune = fmax(ord_to_dbl(bo_cur), 1e-6);
+            bo_cur = *reinterpret_cast<const volatile unsigned long long*>(best);
+        }
+        for (int bI = 0; bI < n; ++bI) { // one box at a time, its 8 corners on the 8 lanes (every branch below is uniform over the group)
+            const DBox b = cur[bI];
+            const int tk = b.kk & 0xff, uk = (b.kk >> 8) & 0xff, vk = (b.kk >> 16) & 0xff;
+            const double tlo = dy_lo(b.tn, tk);
+            unsigned flags = 0;
+            if (tlo < toi_skip && tlo < t_prune) {
+                ++visited;
+                const double tv = ci ? dy_hi(b.tn, tk) : tlo;
+                const double uv = cj ? dy_hi(b.un, uk) : dy_lo(b.un, uk);
+                const double vv = cl ? dy_hi(b.vn, vk) : dy_lo(b.vn, vk);
+                bool excl = false, inside = true, tolc = true;
+                double tmax = 0.0;
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc) {
+                    double pp[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) pp[k] = (P.x1[3 * k + cc] - P.x0[3 * k + cc]) * tv + P.x0[3 * k + cc];
+                    double f;
+                    if (vf) {
+                        const double pt = ((pp[2] - pp[1]) * uv + (pp[3] - pp[1]) * vv) + pp[1];
+                        f = pp[0] - pt;
+                    }
+                    else {
+                        const double pa = (pp[1] - pp[0]) * uv + pp[0];
+                        const double pb = (pp[3] - pp[2]) * vv + pp[2];
+                        f = pa - pb;
+                    }
+                    double mn = f, mx = f;
+#pragma unroll
+                    for (int o = 1; o < 8; o <<= 1) {
+                        mn = fmin(mn, __shfl_xor_sync(gmask, mn, o, 8));
+                        mx = fmax(mx, __shfl_xor_sync(gmask, mx, o, 8));
+                    }
+                    const double e = err[cc] + ms;
+                    const double tt = mx - mn;
+                    excl = excl || (mn > e || mx < -e);
+                    inside = inside && (mn >= -e && mx <= e);
+                    tolc = tolc && !(tt > co_tol);
+                    tmax = (cc == 0) ? tt : fmax(tmax, tt);
+                }
+                if (!excl) { // the co-domain box contains the origin
+                    flags = F_ZERO;
+                    const bool cond1 = pow2neg(tk) <= tol[0] && pow2neg(uk) <= tol[1] && pow2neg(vk) <= tol[2];
+                    const Key3 key = { tlo, dy_lo(b.un, uk), dy_lo(b.vn, vk) };
+                    const bool flagged = tolc || inside || cond1;
+                    if (key_less(key, k1)) { k1 = key; p1 = flagged ? 1u : 0u; a1max = tmax; }
+                    if (flagged && key_less(key, k2)) { k2 = key; p2 = cond1 ? 1u : 0u; }
+                }
+            }
+            if (gl == 0) cur[bI].kk = (b.kk & 0x00ffffffu) | flags;
+        }
+        __syncwarp(gmask);
+        if (k1.t == INF) break; // search space exhausted
+        if (p1 & 1u) { toi = k1.t; return 1; }
+        const bool has_k2 = k2.t != INF;
+        if (has_k2 && (p2 & 1u)) { toi = k2.t; return 1; }
+        if (gl == 0) atomicAdd(reinterpret_cast<unsigned long long*>(warn + 5), (unsigned long long)visited); // diagnostics: boxes of this pass
+        if (max_itr > 0) {
+            temp_toi = k1.t;
+            temp_out_tol = fmax(a1max, co_tol);
+            refine += visited;
+            if (refine > max_itr) {
+                if (gl == 0) atomicAdd(warn, 1);
+                toi = temp_toi;
+                out_tol = temp_out_tol;
+                return 1;
+            }
+        }
+        if (has_k2) {
+            if (k2.t < toi_skip) toi_skip = k2.t;
+            use_skip = true;
+        }
+        int nn = 0;
+        bool over = false, deep = false;
+        for (int base = 0; base < n; base += 8) { // split pass: one box per lane of the group
+            const int i = base + gl;
+            int nchild = 0;
+            DBox c0, c1;
+            if (i < n) {
+                const DBox b = cur[i];
+                if (b.kk & F_ZERO) {
+                    const int tk = b.kk & 0xff, uk = (b.kk >> 8) & 0xff, vk = (b.kk >> 16) & 0xff;
+                    const Key3 key = { dy_lo(b.tn, tk), dy_lo(b.un, uk), dy_lo(b.vn, vk) };
+                    if (!has_k2 || key_less(key, k2)) {
+                        const double w[3] = { pow2neg(tk), pow2neg(uk), pow2neg(vk) };
+                        int split = -1;
+                        double bestr = -1.0;
+#pragma unroll
+                        for (int d = 0; d < 3; ++d)
+                            if (w[d] > tol[d]) {
+                                const double r = w[d] / tol[d];
+                                if (r > bestr) { bestr = r; split = d; }
+                            }
+                        const int pk = split == 0 ? tk : (split == 1 ? uk : vk);
+                        if (split < 0 || pk >= 60) deep = true;
+                        else {
+                            const unsigned long long pn = split == 0 ? b.tn : (split == 1 ? b.un : b.vn);
+#pragma unroll
+                            for (int half = 0; half < 2; ++half) {
+                                const unsigned long long hn = 2 * pn + half;
+                                const int hk = pk + 1;
+                                bool keep = true;
+                                if (split == 0) { if (check_t) keep = !(dy_hi(hn, hk) < 0.0 || dy_lo(hn, hk) > max_t); }
+                                else if (vf) keep = (split == 1) ? sum_le_1(hn, hk, b.vn, vk) : sum_le_1(hn, hk, b.un, uk);
+                                if (keep) {
+                                    DBox ch = b;
+                                    ch.kk &= 0x00ffffffu;
+                                    if (split == 0) { ch.tn = hn; ch.kk = (ch.kk & ~0xffu) | (unsigned)hk; }
+                                    else if (split == 1) { ch.un = hn; ch.kk = (ch.kk & ~0xff00u) | ((unsigned)hk << 8); }
+                                    else { ch.vn = hn; ch.kk = (ch.kk & ~0xff0000u) | ((unsigned)hk << 16); }
+                                    if (nchild == 0) c0 = ch;
+                                    else c1 = ch;
+                                    ++nchild;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            int incl = nchild; // inclusive scan over the 8 lanes of the group
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+                const int y = __shfl_up_sync(gmask, incl, o, 8);
+                if (gl >= o) incl += y;
+            }
+            const int total = __shfl_sync(gmask, incl, 7, 8);
+            const int off = nn + incl - nchild;
+            if (nn + total > kGrpCap) over = true;
+            else {
+                if (nchild > 0) nxt[off] = c0;
+                if (nchild > 1) nxt[off + 1] = c1;
+            }
+            nn += total;
+            if (__any_sync(gmask, over || deep)) break;
+        }
+        if (__any_sync(gmask, deep)) { // bisection depth exhausted: the conservative per-level estimate, like the other passes
+            if (gl == 0) atomicAdd(warn, 1);
+            toi = temp_toi;
+            out_tol = temp_out_tol;
+            return 1;
+        }
+        if (__any_sync(gmask, over)) return 2; // the level outgrew the group's buffer: hand the pair to the warp-level pass
+        __syncwarp(gmask);
+        DBox* tsw = cur; cur = nxt; nxt = tsw;
+        n = nn;
+    }
+    if (use_skip) { toi = toi_skip; return 1; }
+    return 0;
+}
+
+// vertexFaceCCD_double / edgeEdgeCCD_double incl. the no_zero_toi refinement loop, for one 8-lane group; 0 / 1 / 2 (deferred)
+__device__ int ti_ccd_grp(bool vf, const TiPair& P, const double* err, double ms, double tolerance, double t_max, int max_itr, DBox* sA, DBox* sB, int gl, unsigned gmask,
+    double& toi, int* __restrict__ warn, const unsigned long long* best)
+{
+    double tolerance_in = tolerance, ms_in = ms, out_tol = tolerance;
+    bool is_impacting = false, tmp = false;
+    unsigned iter = 0;
+    do {
+        double tol[3];
+        if (vf) width_tolerances<true>(P, tolerance_in, tol);
+        else width_tolerances<false>(P, tolerance_in, tol);
+        const int rc = ti_root_finder_grp(vf, P, tol, tolerance_in, t_max, err, ms_in, max_itr, sA, sB, gl, gmask, toi, out_tol, warn, best);
+        if (rc == 2) return 2;
+        tmp = rc == 1;
+        if (iter == 0) is_impacting = tmp;
+        else toi = tmp ? toi : t_max;
+        if (tmp && toi == 0.0) {
+            if (out_tol > tolerance_in) t_max *= 0.9;
+            else if (10 * tolerance_in < ms_in) ms_in *= 0.5;
+            else tolerance_in *= 0.1;
+        }
+        ++iter;
+    } while (iter < 0x7fffffffu && tmp && toi == 0.0);
+    return is_impacting ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(32 * kGrpWarpsPerCta, 4) k_ti_groups(NarrowArgs a, const unsigned* __restrict__ survivors, const unsigned* __restrict__ nSurvPtr,
+    unsigned* __restrict__ work, unsigned* __restrict__ deferred, unsigned* __restrict__ nDeferred, unsigned long long* __restrict__ min_ord, int* __restrict__ warn)
+{
+    __shared__ DBox sLevels[kGrpWarpsPerCta][4][2][kGrpCap];
+    __shared__ TiPair sPair[kGrpWarpsPerCta][4];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int grp = lane >> 3, gl = lane & 7;
+    const unsigned gmask = 0xffu << (8 * grp);
+    DBox* sA = sLevels[wib][grp][0];
+    DBox* sB = sLevels[wib][grp][1];
+    TiPair& Ps = sPair[wib][grp];
+    const unsigned nSurv = *nSurvPtr;
+    const double max_t = a.st->max_t;
+    const unsigned long long* best = &a.st->ccd_ord;
+    for (;;) {
+        unsigned w = 0;
+        if (gl == 0) w = atomicAdd(work, 1u);
+        w = __shfl_sync(gmask, w, 0, 8);
+        if (w >= nSurv) break;
+        const unsigned idx = survivors[w];
+        bool vf;
+        {
+            int v[4];
+            TiPair Pl;
+            load_pair(a.s, a.dir, a.cand[idx], vf, v, Pl);
+            if (gl == 0) Ps = Pl;
+            __syncwarp(gmask);
+        }
+        const TiPair& P = Ps;
+        const double d = pair_distance_sqrt(vf, P);
+        const double ms = fmin(0.2 * d, 1e-6);
+        const double* err = vf ? a.err_vf : a.err_ee;
+        double toi;
+        int hit = ti_ccd_grp(vf, P, err, ms, a.tol, max_t, a.max_itr, sA, sB, gl, gmask, toi, warn, best);
+        if (hit == 1 && toi < 1e-6) { // :759-781 (no pruning here: the result is rescaled by 0.8, see pair_ccd)
+            hit = ti_ccd_grp(vf, P, err, 0.0, a.tol, max_t, a.max_itr, sA, sB, gl, gmask, toi, warn, nullptr);
+            if (hit == 1) toi *= 0.8;
+        }
+        if (gl == 0) {
+            if (hit == 2) deferred[atomicAdd(nDeferred, 1u)] = idx;
+            else if (hit == 1) atomicMin(min_ord, dbl_to_ord(toi));
+        }
+        __syncwarp(gmask);
+    }
+}
+
 // stage 1.5: one THREAD per surviving pair with a small private level buffer; pairs whose search outgrows it are deferred
 constexpr int kThreadCap = 12;
 __global__ void __launch_bounds__(128) k_ti_stage15(NarrowArgs a, const unsigned* __restrict__ survivors, const unsigned* __restrict__ nSurvPtr,
@@ -1176,7 +1443,11 @@ int ccd_narrow(ipcgpu_ctx* ctx, const int2* cand, const int* n32, const unsigned
         k_ti_stage1<<<kSMs * 16, 128, 0, st>>>(a, w.surv.p, nSurv, flags);
         ctx->prof_end(pe1);
         unsigned* nDefA = reinterpret_cast<unsigned*>(flags + 2);
-        k_ti_stage15<<<kSMs * 16, 128, 0, st>>>(a, w.surv.p, nSurv, w.surv2.p, nDefA, 10, &ist->ccd_ord, flags + 1);
+        static const int ti_mode = [] { const char* e = std::getenv("IPCGPU_TI_MODE"); return e ? std::atoi(e) : 1; }();
+        if (ti_mode == 1) // group pass (8 lanes per pair) over every survivor; flags[3] is its work counter
+            k_ti_groups<<<kSMs * 4, 32 * kGrpWarpsPerCta, 0, st>>>(a, w.surv.p, nSurv, reinterpret_cast<unsigned*>(flags + 3), w.surv2.p, nDefA, &ist->ccd_ord, flags + 1);
+        else // thread pass (one thread per pair, 10-box budget)
+            k_ti_stage15<<<kSMs * 16, 128, 0, st>>>(a, w.surv.p, nSurv, w.surv2.p, nDefA, 10, &ist->ccd_ord, flags + 1);
         k_ti_stage2<<<kStage2Ctas, 32 * kStage2WarpsPerCta, 0, st>>>(a, w.surv2.p, nDefA, work, reinterpret_cast<DBox*>(w.scratch.p), kLevelCap, &ist->ccd_ord, flags + 1);
     }
     k_ccd_finish<<<1, 32, 0, st>>>(ist, nSurv, flags, overflow, stage == 3);
@@ -1258,12 +1529,12 @@ int ccd_full(ipcgpu_ctx* ctx, double tol, const double* err_vf, const double* er
     PairOut ppt{ cw.bp_pairs.p, nPairs, (unsigned)cw.bp_cap, w.counters.p + 14 }, pee{ cw.bp_pairs.p + cw.bp_cap, nPairs + 1, (unsigned)cw.bp_cap, w.counters.p + 14 };
     if (v1 > v0 && s.nSF > 0) {
         k_ccd_pairs_pt<<<nblk(v1 - v0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(cw.grid.p, cw.vbox.p, tg, ist, v0, v1, ppt);
-        k_ccd_filter_pt<<<nblk((long long)cw.bp_cap, 256), 256, 0, st>>>(s, ppt.pairs, ppt.n, w.vmin.p, w.vmax.p, out);
+        k_ccd_filter_pt<<<kSMs * 8, 256, 0, st>>>(s, ppt.pairs, ppt.n, ppt.cap, w.vmin.p, w.vmax.p, out);
         ctx->launches += 2;
     }
     if (e1 > e0 && s.nSE > 1) {
-        k_ccd_pairs_ee<<<nblk(e1 - e0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(cw.grid.p, eg, ist, e0, e1, pee);
-        k_ccd_filter_ee<<<nblk((long long)cw.bp_cap, 256), 256, 0, st>>>(s, pee.pairs, pee.n, w.vmin.p, w.vmax.p, out);
+        k_ccd_pairs_ee<<<nblk(e1 - e0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(cw.grid.p, eg, cw.ebox.p, ist, e0, e1, pee);
+        k_ccd_filter_ee<<<kSMs * 8, 256, 0, st>>>(s, pee.pairs, pee.n, pee.cap, w.vmin.p, w.vmax.p, cw.ebox.p, out);
         ctx->launches += 2;
     }
     ctx->prof_end(pe);

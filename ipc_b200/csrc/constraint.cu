@@ -102,6 +102,7 @@ __global__ void k_grid_params(const unsigned long long* __restrict__ bounds, dou
     if (!(h > 0.0)) h = 1.0;
     g->ox = lo[0]; g->oy = lo[1]; g->oz = lo[2];
     g->inv_h = 1.0 / h;
+    g->q_inv = 65533.0 / fmax(span, 1e-300);
     g->nx = max(1, (int)floor((hi[0] - lo[0]) * g->inv_h) + 1);
     g->ny = max(1, (int)floor((hi[1] - lo[1]) * g->inv_h) + 1);
     g->nz = max(1, (int)floor((hi[2] - lo[2]) * g->inv_h) + 1);
@@ -140,10 +141,14 @@ __global__ void __launch_bounds__(256) k_build_cell_table(int n, const unsigned 
         h = (h + 1) & mask;
     }
 }
-__global__ void __launch_bounds__(256) k_gather_boxes(int n, const Box* __restrict__ boxes, const int* __restrict__ ids, Box* __restrict__ sorted)
+// entries of the sorted grid: quantised box + id (see QEntry)
+__global__ void __launch_bounds__(256) k_gather_boxes(int n, const Box* __restrict__ boxes, const int* __restrict__ ids, const Grid* __restrict__ gp, uint4* __restrict__ sorted)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) sorted[i] = boxes[ids[i]];
+    if (i >= n) return;
+    const int id = ids[i];
+    const QBox q = quantize_box(*gp, boxes[id]);
+    sorted[i] = make_uint4((unsigned)q.lo[0] | ((unsigned)q.lo[1] << 16), (unsigned)q.lo[2] | ((unsigned)q.hi[0] << 16), (unsigned)q.hi[1] | ((unsigned)q.hi[2] << 16), (unsigned)id);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -186,53 +191,46 @@ __global__ void __launch_bounds__(256) k_pairs_pt(SurfArgs s, const Grid* __rest
     pair_stage_init(stage);
     const int lane = threadIdx.x & 31;
     const Grid g = *gp;
-    const double cull = dHat * (1.0 + 1e-9) + 1e-300;
     const int q0 = first + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kPairQueriesPerWarp;
     for (int svI = q0; svI < min(q0 + kPairQueriesPerWarp, last); ++svI) {
         const V3 p = load_vertex(s.V, s.nV, s.SVI[svI]);
-        Box qb, pb;
+        Box qb;
         qb.lo[0] = p.x - radius; qb.lo[1] = p.y - radius; qb.lo[2] = p.z - radius;
         qb.hi[0] = p.x + radius; qb.hi[1] = p.y + radius; qb.hi[2] = p.z + radius;
-        pb.lo[0] = pb.hi[0] = p.x; pb.lo[1] = pb.hi[1] = p.y; pb.lo[2] = pb.hi[2] = p.z;
-        warp_scan_candidates(g, tg, qb, lane, [&](bool hit, int sfI, const Box& tb) {
-            warp_push_pair(stage, out, hit && box_gap2(pb, tb) <= cull, svI, sfI, lane);
-        });
+        warp_scan_candidates(g, tg, qb, lane, [&](bool hit, int sfI) { warp_push_pair(stage, out, hit, svI, sfI, lane); });
     }
     pair_stage_flush(stage, out);
 }
 
 // queries are the entries of the sorted edge grid itself ([first, last) = sorted positions); each walks only the entries behind it
-__global__ void __launch_bounds__(256) k_pairs_ee(const Grid* __restrict__ gp, SortedGrid eg, double dHat, double radius, int first, int last, PairOut out)
+__global__ void __launch_bounds__(256) k_pairs_ee(const Grid* __restrict__ gp, SortedGrid eg, const Box* __restrict__ eboxes, double dHat, double radius, int first, int last, PairOut out)
 {
     __shared__ PairStage stage;
     pair_stage_init(stage);
     const int lane = threadIdx.x & 31;
     const Grid g = *gp;
-    const double cull = dHat * (1.0 + 1e-9) + 1e-300;
     const int q0 = first + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kPairQueriesPerWarp;
     for (int i = q0; i < min(q0 + kPairQueriesPerWarp, last); ++i) {
         const int eI = eg.ids[i];
-        const Box eb = eg.boxes[i];
-        Box qb = eb;
+        Box qb = eboxes[eI];
         for (int k = 0; k < 3; ++k) { qb.lo[k] -= radius; qb.hi[k] += radius; }
-        warp_scan_candidates(g, eg, qb, lane, [&](bool hit, int eJ, const Box& jb) {
-            warp_push_pair(stage, out, hit && box_gap2(eb, jb) <= cull, min(eI, eJ), max(eI, eJ), lane);
-        }, i);
+        warp_scan_candidates(g, eg, qb, lane, [&](bool hit, int eJ) { warp_push_pair(stage, out, hit, min(eI, eJ), max(eI, eJ), lane); }, i);
     }
     pair_stage_flush(stage, out);
 }
 
 // ---- phase 2: exact closest-feature classification, one THREAD per surviving pair (dense, convergent)
 // (:2168-2260)
-__global__ void __launch_bounds__(128) k_classify_pt(SurfArgs s, const int2* __restrict__ pairs, const unsigned* __restrict__ nPairs, double dHat, int wantCand, CsOut out)
+__global__ void __launch_bounds__(128) k_classify_pt(SurfArgs s, const int2* __restrict__ pairs, const unsigned* __restrict__ nPairs, unsigned cap, double dHat, int wantCand, CsOut out)
 {
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= *nPairs) return;
+    // grid-stride over the device-resident pair count (a launch sized by the list CAPACITY spent more time retiring empty CTAs than working)
+    const unsigned nP = min(*nPairs, cap);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nP; i += gridDim.x * blockDim.x) {
     const int svI = pairs[i].x, sfI = pairs[i].y;
     const int vI = s.SVI[svI];
     const int a = s.SF[sfI], b = s.SF[(size_t)s.nSF + sfI], c = s.SF[(size_t)2 * s.nSF + sfI];
-    if (vI == a || vI == b || vI == c) return;
-    if ((codim_v(s, vI) < 3 && codim_v(s, a) < 3) || (is_dbc_v(s, vI) && is_dbc_v(s, a) && is_dbc_v(s, b) && is_dbc_v(s, c))) return;
+    if (vI == a || vI == b || vI == c) continue;
+    if ((codim_v(s, vI) < 3 && codim_v(s, a) < 3) || (is_dbc_v(s, vI) && is_dbc_v(s, a) && is_dbc_v(s, b) && is_dbc_v(s, c))) continue;
     const V3 p = load_vertex(s.V, s.nV, vI);
     const V3 ta = load_vertex(s.V, s.nV, a), tb_ = load_vertex(s.V, s.nV, b), tc = load_vertex(s.V, s.nV, c);
     const int ty = dType_PT(p, ta, tb_, tc);
@@ -256,17 +254,18 @@ __global__ void __launch_bounds__(128) k_classify_pt(SurfArgs s, const int2* __r
             else atomicExch(out.overflow, 1);
         }
     }
+    }
 }
 
 // (:2271-2407)
-__global__ void __launch_bounds__(128) k_classify_ee(SurfArgs s, const int2* __restrict__ pairs, const unsigned* __restrict__ nPairs, double dHat, int wantCand, CsOut out)
+__global__ void __launch_bounds__(128) k_classify_ee(SurfArgs s, const int2* __restrict__ pairs, const unsigned* __restrict__ nPairs, unsigned cap, double dHat, int wantCand, CsOut out)
 {
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= *nPairs) return;
+    const unsigned nP = min(*nPairs, cap);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nP; i += gridDim.x * blockDim.x) {
     const int eI = pairs[i].x, eJ = pairs[i].y;
     const int a0 = s.SE[2 * eI], a1 = s.SE[2 * eI + 1], b0 = s.SE[2 * eJ], b1 = s.SE[2 * eJ + 1];
-    if (a0 == b0 || a0 == b1 || a1 == b0 || a1 == b1) return;
-    if ((codim_v(s, a0) < 3 && codim_v(s, b0) < 3) || (is_dbc_v(s, a0) && is_dbc_v(s, a1) && is_dbc_v(s, b0) && is_dbc_v(s, b1))) return;
+    if (a0 == b0 || a0 == b1 || a1 == b0 || a1 == b1) continue;
+    if ((codim_v(s, a0) < 3 && codim_v(s, b0) < 3) || (is_dbc_v(s, a0) && is_dbc_v(s, a1) && is_dbc_v(s, b0) && is_dbc_v(s, b1))) continue;
     const V3 xa0 = load_vertex(s.V, s.nV, a0), xa1 = load_vertex(s.V, s.nV, a1), xb0 = load_vertex(s.V, s.nV, b0), xb1 = load_vertex(s.V, s.nV, b1);
     const int ty = dType_EE(xa0, xa1, xb0, xb1);
     const double cr = norm2(cross(xa1 - xa0, xb1 - xb0));
@@ -304,6 +303,7 @@ __global__ void __launch_bounds__(128) k_classify_ee(SurfArgs s, const int2* __r
             if ((unsigned)k < (unsigned)out.capCand) out.cand[k] = make_int2(eI, eJ);
             else atomicExch(out.overflow, 1);
         }
+    }
     }
 }
 
@@ -570,7 +570,7 @@ int contact_alloc(ipcgpu_ctx* ctx)
 }
 
 // build one sorted grid over `boxes` (n prims): (keys, vals) sorted by cell, boxes gathered into `sorted_boxes`
-static int build_grid(ipcgpu_ctx* ctx, int n, const Box* boxes, DevBuf<unsigned long long>& keys, DevBuf<int>& vals, Box* sorted_boxes, unsigned* tab_key, int2* tab_range)
+static int build_grid(ipcgpu_ctx* ctx, int n, const Box* boxes, DevBuf<unsigned long long>& keys, DevBuf<int>& vals, QEntry* sorted_entries, unsigned* tab_key, int2* tab_range)
 {
     ContactWork& w = ctx->cw;
     cudaStream_t st = ctx->stream;
@@ -582,7 +582,7 @@ static int build_grid(ipcgpu_ctx* ctx, int n, const Box* boxes, DevBuf<unsigned 
         ctx->err = std::string("cub grid sort: ") + cudaGetErrorString(e);
         return IPCGPU_ERR_CUDA;
     }
-    k_gather_boxes<<<nblk(n, 256), 256, 0, st>>>(n, boxes, vals.p, sorted_boxes);
+    k_gather_boxes<<<nblk(n, 256), 256, 0, st>>>(n, boxes, vals.p, w.grid.p, reinterpret_cast<uint4*>(sorted_entries));
     cudaMemsetAsync(tab_key, 0xff, (size_t)(w.tab_mask + 1) * sizeof(unsigned), st);
     k_build_cell_table<<<nblk(n, 256), 256, 0, st>>>(n, keys.p, tab_key, tab_range, w.tab_mask);
     ctx->launches += 4;
@@ -686,12 +686,12 @@ int contact_constraint_set(ipcgpu_ctx* ctx, double dHat, int wantCand, int* nC, 
     PairOut ppt{ w.bp_pairs.p, nPairs, (unsigned)w.bp_cap, w.counters.p + 4 }, pee{ w.bp_pairs.p + w.bp_cap, nPairs + 1, (unsigned)w.bp_cap, w.counters.p + 4 };
     if (v1 > v0 && s.nSF > 0) {
         k_pairs_pt<<<nblk(v1 - v0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(s, w.grid.p, tg, dHat, radius, v0, v1, ppt);
-        k_classify_pt<<<nblk((long long)w.bp_cap, 128), 128, 0, st>>>(s, ppt.pairs, ppt.n, dHat, wantCand, out);
+        k_classify_pt<<<kSMs * 8, 128, 0, st>>>(s, ppt.pairs, ppt.n, ppt.cap, dHat, wantCand, out);
         ctx->launches += 2;
     }
     if (e1 > e0 && s.nSE > 1) {
-        k_pairs_ee<<<nblk(e1 - e0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(w.grid.p, eg, dHat, radius, e0, e1, pee);
-        k_classify_ee<<<nblk((long long)w.bp_cap, 128), 128, 0, st>>>(s, pee.pairs, pee.n, dHat, wantCand, out);
+        k_pairs_ee<<<nblk(e1 - e0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(w.grid.p, eg, w.ebox.p, dHat, radius, e0, e1, pee);
+        k_classify_ee<<<kSMs * 8, 128, 0, st>>>(s, pee.pairs, pee.n, pee.cap, dHat, wantCand, out);
         ctx->launches += 2;
     }
     // merge PP/PE duplicates into the active list with negative multiplicities (:2434-2476)

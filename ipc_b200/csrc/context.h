@@ -42,7 +42,8 @@ struct DevBuf {
 
 // device workspace of the contact stages (constraint.cu / ccd.cu)
 struct ContactWork {
-    DevBuf<Box> vbox, ebox, tbox, tsbox, esbox; // per-primitive boxes; t/e boxes again in grid-sorted order
+    DevBuf<Box> vbox, ebox, tbox;   // per-primitive boxes (primitive order)
+    DevBuf<QEntry> tsbox, esbox;    // grid-sorted entries: quantised box + id
     DevBuf<unsigned long long> bounds, tkeys, ekeys, key_tmp, skey, skey2;
     DevBuf<Grid> grid;
     DevBuf<int> tvals, evals, val_tmp, counters, sidx, sidx2;
@@ -61,7 +62,7 @@ struct ContactWork {
     bool want_cand = false;
     unsigned dup_tab = 1024;    // slots of the PP/PE duplicate-merge table
     // barrier stage workspace, sized by the pair capacity
-    DevBuf<double> bHraw, bpartials;
+    DevBuf<double> bHraw, bpartials, bval; // (bval: per-constraint values of ipcgpu_evaluate_constraints / inputs of ..._jacobian_t)
     DevBuf<int> brows, bpsd;
     // multi-rank exchange of the pair lists (one fixed-size message per rank, see k_pack_lists)
     int xcap = 0;
@@ -109,6 +110,7 @@ struct ipcgpu_ctx {
     bool dir_valid = false, pSize_surface = false;
     bool energy_local[2] = { false, false }; // IterState::energy[s] still holds this rank's partial sum
     bool a_all_dirty = false;                // a cross-rank completion filled rows this rank does not own
+    bool checks_local = false;               // IterState::checks still holds this rank's partial counts
     std::vector<int> h_ia;                   // host copy of the CSR row starts (value range of the owned rows)
 
     // mesh

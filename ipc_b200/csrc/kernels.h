@@ -22,6 +22,7 @@ struct IterState {
     int ref_count[3];
     int n_set[3];                     // active / mollified / candidate counts of the last constraint set (this rank's lists)
     int flags[8];                     // IPCGPU_FLAG_* slots (nonzero = raised); cleared by ipcgpu_fetch_iteration
+    int checks[2];                    // line-search safeguards: inverted tets, surface triangles crossed by an edge (this rank's share, then sums)
     unsigned long long ccd_stats[8];  // survivors, warnings, deferred, longest / total pair cycles, boxes (thread pass, warp pass), candidates
 };
 enum { FLAG_NONPOSITIVE_DISTANCE = 0, FLAG_SET_CAPACITY = 1, FLAG_CCD_CAPACITY = 2, FLAG_ZERO_CCD_DISTANCE = 3, FLAG_PATTERN = 4, FLAG_TI_WARNINGS = 5, FLAG_EXCHANGE_CAPACITY = 6 };
@@ -90,6 +91,9 @@ struct BarrierArgs {
 void barrier_energy(const BarrierArgs& p, double* partials, int* bad, cudaStream_t st);
 int barrier_energy_blocks();
 void barrier_gradient(const BarrierArgs& p, double* g, cudaStream_t st);
+void evaluate_constraints(const BarrierArgs& p, double* val, cudaStream_t st);
+void constraint_jacobian_t(const BarrierArgs& p, const double* input, double coef, double* g, cudaStream_t st);
+void para_gradient(const BarrierArgs& p, double* g, cudaStream_t st);
 // Hraw: 144 doubles per owned pair; rows: 4 vertex ids per owned pair; psd: makePD "unchanged" flag per owned pair; n_owned: device counter
 void barrier_hessian(const BarrierArgs& p, double* a, int* err, double* Hraw, int* rows, int* psd, int* n_owned, int capacity, cudaStream_t st);
 // elastic.cu (shared fixed-order reduction)

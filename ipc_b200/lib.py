@@ -34,6 +34,8 @@ SIGNATURES = {
     "ipcgpu_partition_info": (C.c_int, [_ctxp, _ip, _ip, _ip, _ip, _ip, _ip, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _ip]),
     "ipcgpu_fetch_iteration": (C.c_int, [_ctxp, C.c_void_p]),
     "ipcgpu_step_bound_set": (C.c_int, [_ctxp, C.c_double]),
+    "ipcgpu_check_inversion": (C.c_int, [_ctxp, _ip]),
+    "ipcgpu_intersection_free": (C.c_int, [_ctxp, _ip]),
     "ipcgpu_constraint_set_sizes": (C.c_int, [_ctxp, _ip, _ip, _ip]),
     "ipcgpu_ccd_debug_seed_bound": (C.c_int, [_ctxp, C.c_double]),
     "ipcgpu_download_range": (C.c_int, [_ctxp, C.c_int, C.c_uint64, C.c_uint64, _dp]),
@@ -58,6 +60,9 @@ SIGNATURES = {
     "ipcgpu_barrier_energy": (C.c_int, [_ctxp, C.c_double, C.c_double, _dp]),
     "ipcgpu_barrier_gradient": (C.c_int, [_ctxp, C.c_double, C.c_double, _dp]),
     "ipcgpu_barrier_hessian": (C.c_int, [_ctxp, C.c_double, C.c_double, C.c_int, _dp]),
+    "ipcgpu_evaluate_constraints": (C.c_int, [_ctxp, _dp, C.c_int]),
+    "ipcgpu_constraint_jacobian_t": (C.c_int, [_ctxp, _dp, C.c_int, C.c_double, _dp]),
+    "ipcgpu_para_ee_gradient": (C.c_int, [_ctxp, C.c_double, C.c_double, _dp]),
     "ipcgpu_set_ccd_capacity": (C.c_int, [_ctxp, C.c_uint64]),
     "ipcgpu_ti_error": (C.c_int, [_dp, C.c_int, _dp, _dp, _dp]),
     "ipcgpu_ccd_partial_ti": (C.c_int, [_ctxp, _dp, C.c_double, _dp, _dp, _dp]),
@@ -86,7 +91,8 @@ class Iteration(C.Structure):
     """ipcgpu_iteration (include/ipcgpu.h)"""
     _fields_ = [("energy_elastic", C.c_double), ("energy_barrier", C.c_double), ("alpha_inversion", C.c_double), ("alpha_partial_ccd", C.c_double),
                 ("alpha_swept_grid", C.c_double), ("alpha_full_ccd", C.c_double), ("alpha", C.c_double), ("n_active", C.c_int), ("n_mollified", C.c_int),
-                ("n_candidates", C.c_int), ("status", C.c_int), ("n_full_ccd_candidates", C.c_uint64), ("ti_warnings", C.c_uint64)]
+                ("n_candidates", C.c_int), ("status", C.c_int), ("n_full_ccd_candidates", C.c_uint64), ("ti_warnings", C.c_uint64),
+                ("n_inverted_tets", C.c_int), ("n_intersected_triangles", C.c_int)]
 
 
 class IpcGpuError(RuntimeError):
@@ -241,6 +247,16 @@ class Context:
         self._ck(self.lib.ipcgpu_inversion_step(self.h, _d(f64(p)) if p is not None else None, slack, C.byref(a) if alpha is not None else None))
         return a.value if alpha is not None else None
 
+    def check_inversion(self, want=True):
+        n = C.c_int()
+        self._ck(self.lib.ipcgpu_check_inversion(self.h, C.byref(n) if want else None))
+        return n.value if want else None
+
+    def intersection_free(self, want=True):
+        ok = C.c_int()
+        self._ck(self.lib.ipcgpu_intersection_free(self.h, C.byref(ok) if want else None))
+        return bool(ok.value) if want else None
+
     def step_bound_set(self, alpha):
         self._ck(self.lib.ipcgpu_step_bound_set(self.h, float(alpha)))
 
@@ -309,6 +325,20 @@ class Context:
 
     def barrier_gradient(self, dHat, kappa, g_inout=None):
         self._ck(self.lib.ipcgpu_barrier_gradient(self.h, dHat, kappa, _d(g_inout)))
+        return g_inout
+
+    def evaluate_constraints(self, n):
+        val = np.empty(int(n))
+        self._ck(self.lib.ipcgpu_evaluate_constraints(self.h, _d(val), int(n)))
+        return val
+
+    def constraint_jacobian_t(self, inp, coef, g_inout):
+        inp = f64(inp)
+        self._ck(self.lib.ipcgpu_constraint_jacobian_t(self.h, _d(inp), int(inp.size), float(coef), _d(g_inout)))
+        return g_inout
+
+    def para_ee_gradient(self, dHat, kappa, g_inout):
+        self._ck(self.lib.ipcgpu_para_ee_gradient(self.h, dHat, kappa, _d(g_inout)))
         return g_inout
 
     def barrier_hessian(self, dHat, kappa, projectDBC=1, a_inout=None):

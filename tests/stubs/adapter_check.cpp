@@ -12,9 +12,14 @@ void touch(IPC::IpcGpuScene& s, const IPC::Mesh<3>& m, IPC::LinSysSolver<Eigen::
     double x = 1.0;
     using H = IPC::GpuSelfCollisionHandler;
     H::computeConstraintSet(m, sh, 1e-6, a, b, c, true, d);
-    (void)H::barrierEnergy(1e-6, 1e8);
-    H::leftMultiplyConstraintJacobianT(m, a, v, v, 1e-6, 1e8);
+    // the reference's own call sequence (Optimizer.cpp:3492-3502, 3693-3695), reference signatures (SelfCollisionHandler.hpp:23-33)
+    H::evaluateConstraints(m, a, v);
+    H::leftMultiplyConstraintJacobianT(m, a, v, v, 1e8);
+    H::augmentParaEEGradient(m, b, c, v, 1e-6, 1e8);
     H::augmentIPHessian(m, a, sol, 1e-6, 1e8, true);
+    H::augmentParaEEHessian(m, b, c, sol, 1e-6, 1e8, true);
+    (void)H::checkEdgeTriIntersectionIfAny(m, sh);
+    (void)IPC::gpuCheckInversion(s);
     H::largestFeasibleStepSize_TightInclusion(m, sh, v, 1e-6, d, d, x);
     H::hashBuildSwept(v, x, 0.1);
     H::largestFeasibleStepSize_CCD_TightInclusion(m, sh, v, 1e-6, d, x);

@@ -127,3 +127,31 @@ def test_ball_pile_sets_match_oracle(gpu_ctx):
     kappa = 1e9
     E_ref, bad = orc.Surf(m).barrier_energy(mm_r, pa_r, pe_r, info["dHat"], kappa)
     assert bad == 0 and abs(gpu_ctx.barrier_energy(info["dHat"], kappa) - E_ref) <= RTOL * abs(E_ref)
+
+
+def test_reference_two_step_gradient_form(gpu_ctx):
+    """evaluateConstraints (:64-81) -> host maps through b'(d) -> leftMultiplyConstraintJacobianT (:84-148) + augmentParaEEGradient (:2990-3045):
+    the reference's own call sequence (Optimizer.cpp:3492-3502) must give what the fused ipcgpu_barrier_gradient and the oracle give."""
+    m = stacked_cubes(0.01, n=2, seed=6, jitter=0.02, shift=(0.0, 0.0))  # has mollified (nearly parallel) pairs too
+    dHat, kappa = 0.02 ** 2, 1e4
+    upload(gpu_ctx, m)
+    mm, pa, pe, _ = gpu_ctx.constraint_set(dHat, 0)
+    assert len(mm) > 0 and len(pa) > 0
+    s = orc.Surf(m)
+    val = gpu_ctx.evaluate_constraints(len(mm))
+    assert np.all(val > 0) and np.all(val < dHat)
+    bvals = np.array([orc.barrier(d, dHat) for d in val])  # (b, b', b'')
+    mult = np.where((mm[:, 0] < 0) & (mm[:, 3] < 0), -mm[:, 3], 1)
+    E_ref, _ = s.barrier_energy(mm, pa[:0], pe[:0], dHat, kappa)
+    assert abs(kappa * float((mult * bvals[:, 0]).sum()) - E_ref) <= RTOL * abs(E_ref)
+    g0 = np.linspace(-1, 1, 3 * m.nV)
+    g = g0.copy()
+    gpu_ctx.constraint_jacobian_t(bvals[:, 1], kappa, g)
+    g_act = s.barrier_gradient(mm, pa[:0], pe[:0], dHat, kappa, g=g0.copy())
+    assert rel(g - g0, g_act - g0) <= RTOL
+    gpu_ctx.para_ee_gradient(dHat, kappa, g)
+    g_all = s.barrier_gradient(mm, pa, pe, dHat, kappa, g=g0.copy())
+    assert rel(g - g0, g_all - g0) <= RTOL
+    fused = g0.copy()
+    gpu_ctx.barrier_gradient(dHat, kappa, fused)
+    assert rel(fused - g0, g_all - g0) <= RTOL
