@@ -222,6 +222,14 @@ int ipcgpu_ccd_stats_timing(ipcgpu_ctx* ctx, uint64_t* longest_pair_cycles, uint
  * i.e. max_t of every pair, is unchanged; the result is min(toi, the pairs' impacts)); toi < 0 switches the hook off. */
 int ipcgpu_ccd_debug_seed_bound(ipcgpu_ctx* ctx, double toi);
 
+/* ---- linear-solve hand-off with the Hessian resident in HBM (LinSysSolver::factorize/solve, LinSysSolver.hpp:230-236; Optimizer.cpp:2324-2355) ----
+ * The production binding is a sparse Cholesky on the device arrays (cuDSS: INTEGRATION.md; ipcgpu_device_ptr / the ia, ja uploaded by
+ * ipcgpu_set_csr).  What this library itself provides is the hand-off and a reference solver that never leaves the device: block-Jacobi
+ * preconditioned CG on the upper-triangular CSR.  rhs == NULL solves H p = -g with the device-resident gradient; x == NULL keeps the
+ * solution on the device; adopt_as_search_dir != 0 makes it the search direction of the step-bound stages (as if uploaded by
+ * ipcgpu_set_search_dir; mean|p| of SpatialHash.hpp:603-612 is then a fixed-order device sum).  Single rank.
+ * iters / rel_residual (nullable) report the iteration count and |r| / |b|. */
+int ipcgpu_solve_pcg(ipcgpu_ctx* ctx, const double* rhs, double rel_tol, int max_iter, double* x, int adopt_as_search_dir, int* iters, double* rel_residual);
 /* LinSysSolver::setZero (LinSysSolver.hpp:348) on the device-resident value array */
 int ipcgpu_csr_set_zero(ipcgpu_ctx* ctx);
 /* cross-rank completion over NVLink (no-op on a single rank).  with_gradient: sum-allreduce of the gradient (needed every iteration).

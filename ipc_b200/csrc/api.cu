@@ -252,6 +252,9 @@ int ccd_narrow(ipcgpu_ctx* ctx, const int2* cand, const int* n32, const unsigned
 int ccd_build_swept(ipcgpu_ctx* ctx, double h);
 int ccd_full(ipcgpu_ctx* ctx, double tol, const double* err_vf, const double* err_ee);
 int ccd_read_back(ipcgpu_ctx* ctx, double* alpha_out);
+int solver_build_full_pattern(ipcgpu_ctx* ctx, const int* ia, const int* ja); // solve.cu
+int solver_pcg(ipcgpu_ctx* ctx, const double* rhs_dev, double sign, double rel_tol, int max_iter, int* iters_out, double* rel_res_out);
+int solver_adopt_direction(ipcgpu_ctx* ctx);
 int safeguard_inversion(ipcgpu_ctx* ctx);     // safeguard.cu
 int safeguard_intersections(ipcgpu_ctx* ctx); // safeguard.cu
 
@@ -435,6 +438,7 @@ int ipcgpu_set_csr(ipcgpu_ctx* ctx, int n_rows, const int* ia, const int* ja, in
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->a_all_dirty = false;
     ctx->offsets_ready = false;
+    ctx->full_pattern_ready = false;
     owned_value_range(ctx);
     return IPCGPU_OK;
 }
@@ -1123,6 +1127,39 @@ int ipcgpu_intersection_free(ipcgpu_ctx* ctx, int* ok)
     return IPCGPU_OK;
 }
 
+// ---- device-resident linear solve hand-off ----------------------------------------------------------
+int ipcgpu_solve_pcg(ipcgpu_ctx* ctx, const double* rhs, double rel_tol, int max_iter, double* x, int adopt_as_search_dir, int* iters, double* rel_residual)
+{
+    REQUIRE(ctx->nnz > 0 && ctx->n_rows == 3 * ctx->nV, IPCGPU_ERR_STATE, "ipcgpu_set_csr first");
+    REQUIRE(ctx->nranks == 1, IPCGPU_ERR_STATE, "the built-in solver runs on one rank (a distributed solver takes each rank's rows: ipcgpu_partition_info)");
+    REQUIRE(rel_tol > 0.0 && max_iter > 0, IPCGPU_ERR_ARG, "bad tolerance / iteration limit");
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->full_pattern_ready) { // once per sparsity pattern: rows of both triangles, gathered through a position map
+        std::vector<int> ia((size_t)ctx->n_rows + 1), ja((size_t)ctx->nnz);
+        CK(cudaMemcpyAsync(ia.data(), ctx->ia.p, ia.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ja.data(), ctx->ja.p, ja.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        int rc = solver_build_full_pattern(ctx, ia.data(), ja.data());
+        if (rc) return rc;
+    }
+    const double* rhs_dev = ctx->g.p;
+    double sign = -1.0; // Newton: H p = -g (Optimizer.cpp:2350-2352)
+    if (rhs) { // a host right-hand side is staged in a buffer of its own
+        ALLOC(ctx->pcg_b, (size_t)ctx->n_rows);
+        CK(cudaMemcpyAsync(ctx->pcg_b.p, rhs, (size_t)ctx->n_rows * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        rhs_dev = ctx->pcg_b.p;
+        sign = 1.0;
+    }
+    int rc = solver_pcg(ctx, rhs_dev, sign, rel_tol, max_iter, iters, rel_residual);
+    if (rc) return rc;
+    if (adopt_as_search_dir && (rc = solver_adopt_direction(ctx))) return rc;
+    if (x) {
+        CK(cudaMemcpyAsync(x, ctx->sol.p, (size_t)ctx->n_rows * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return IPCGPU_OK;
+}
+
 int ipcgpu_csr_set_zero(ipcgpu_ctx* ctx)
 {
     REQUIRE(ctx->nnz > 0, IPCGPU_ERR_STATE, "ipcgpu_set_csr first");
@@ -1192,6 +1229,12 @@ int ipcgpu_fetch_iteration(ipcgpu_ctx* ctx, ipcgpu_iteration* out)
     const int status = status_from_flags(ctx, h.flags);
     out->status = status;
     CK(cudaMemsetAsync(ctx->iter.p->flags, 0, 8 * sizeof(int), ctx->stream)); // flags are per fetch
+    if (h.grid_axis_cells > 0) { // sort width of the next iteration's grid builds: enough bits for 1.5x the cells this one wanted
+        int bits = 3;
+        while (bits < 10 && (1 << bits) - 2 < (h.grid_axis_cells * 3) / 2 + 2) ++bits;
+        w.axis_bits = bits;
+        CK(cudaMemsetAsync(&ctx->iter.p->grid_axis_cells, 0, sizeof(int), ctx->stream));
+    }
     return status;
 }
 

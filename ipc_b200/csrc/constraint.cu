@@ -89,7 +89,12 @@ __global__ void k_bounds_init(unsigned long long* bounds)
     else if (threadIdx.x < 7) bounds[threadIdx.x] = 0ull;
 }
 
-__global__ void k_grid_params(const unsigned long long* __restrict__ bounds, double radius_val, const double* __restrict__ radius_ptr, Grid* __restrict__ g)
+// axis_bits: the cell keys of this build are sorted on 3 * axis_bits bits, so the grid gets at most 2^axis_bits - 1 cells per axis (cells
+// grow when the scene would need more: the grid is only an accelerator, any cell size >= the largest inflated box is valid).  The
+// number of cells per axis the scene WANTS goes to the iteration state; the host re-tunes axis_bits from it after every fetch, so that
+// in the steady state the radix sort runs 2 passes (16 key bits) instead of 4.
+__global__ void k_grid_params(const unsigned long long* __restrict__ bounds, double radius_val, const double* __restrict__ radius_ptr, int axis_bits, Grid* __restrict__ g,
+    IterState* __restrict__ st)
 {
     if (threadIdx.x != 0) return;
     const double radius = radius_ptr ? *radius_ptr : radius_val;
@@ -100,6 +105,8 @@ __global__ void k_grid_params(const unsigned long long* __restrict__ bounds, dou
     const double span = fmax(fmax(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
     h = fmax(h, span / 1024.0); // at most 1024 cells per axis
     if (!(h > 0.0)) h = 1.0;
+    atomicMax(&st->grid_axis_cells, (int)fmin(ceil(span / h) + 1.0, 1025.0)); // what this build would like
+    h = fmax(h, span / (double)((1 << axis_bits) - 2));                       // what the sort width allows
     g->ox = lo[0]; g->oy = lo[1]; g->oz = lo[2];
     g->inv_h = 1.0 / h;
     g->q_inv = 65533.0 / fmax(span, 1e-300);
@@ -577,7 +584,7 @@ static int build_grid(ipcgpu_ctx* ctx, int n, const Box* boxes, DevBuf<unsigned 
     if (n <= 0) return 0;
     k_emit<<<nblk(n, 256), 256, 0, st>>>(n, boxes, w.grid.p, w.key_tmp.p, w.val_tmp.p);
     size_t bytes = w.cub_tmp.n;
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(w.cub_tmp.p, bytes, w.key_tmp.p, keys.p, w.val_tmp.p, vals.p, n, 0, 32, st); // <= 1025^3 cells: 31 bits
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(w.cub_tmp.p, bytes, w.key_tmp.p, keys.p, w.val_tmp.p, vals.p, n, 0, 3 * w.axis_bits, st); // cells < 2^(3 axis_bits)
     if (e != cudaSuccess) {
         ctx->err = std::string("cub grid sort: ") + cudaGetErrorString(e);
         return IPCGPU_ERR_CUDA;
@@ -610,7 +617,7 @@ int boxes_and_grid(ipcgpu_ctx* ctx, const double* dir, const double* alpha_ptr, 
     if (with_vertex_boxes && s.nSV > 0) k_boxes<<<nblk(s.nSV, 256), 256, 0, st>>>(s, 0, dir, alpha_ptr, w.vbox.p, w.bounds.p);
     if (s.nSE > 0) k_boxes<<<nblk(s.nSE, 256), 256, 0, st>>>(s, 1, dir, alpha_ptr, w.ebox.p, w.bounds.p);
     if (s.nSF > 0) k_boxes<<<nblk(s.nSF, 256), 256, 0, st>>>(s, 2, dir, alpha_ptr, w.tbox.p, w.bounds.p);
-    k_grid_params<<<1, 32, 0, st>>>(w.bounds.p, radius, radius_ptr, w.grid.p);
+    k_grid_params<<<1, 32, 0, st>>>(w.bounds.p, radius, radius_ptr, w.axis_bits, w.grid.p, ctx->iter.p);
     ctx->launches += 5;
     int rc;
     if ((rc = build_grid(ctx, s.nSF, w.tbox.p, w.tkeys, w.tvals, w.tsbox.p, w.ttab_key.p, w.ttab_start.p))) return rc;

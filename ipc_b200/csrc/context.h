@@ -61,6 +61,7 @@ struct ContactWork {
     int nC = 0, nP = 0, nK = 0; // host mirrors of [0], [2], [3]; -1 = not read back (device-resident iteration)
     bool want_cand = false;
     unsigned dup_tab = 1024;    // slots of the PP/PE duplicate-merge table
+    int axis_bits = 10;         // key bits per axis of the grid sorts (re-tuned from IterState::grid_axis_cells at every fetch)
     // barrier stage workspace, sized by the pair capacity
     DevBuf<double> bHraw, bpartials, bval; // (bval: per-constraint values of ipcgpu_evaluate_constraints / inputs of ..._jacobian_t)
     DevBuf<int> brows, bpsd;
@@ -148,6 +149,10 @@ struct ipcgpu_ctx {
     ipcgpu::DevBuf<int> ia, ja;
     ipcgpu::DevBuf<double> a;
     ipcgpu::DevBuf<int> flag; // device error flag
+    // device-resident linear solve (solve.cu): full-row structure of the symmetric matrix + PCG workspace
+    ipcgpu::DevBuf<int> fia, fja, fpos;
+    bool full_pattern_ready = false;
+    ipcgpu::DevBuf<double> sol, pcg_b, pcg_r, pcg_p, pcg_q, pcg_minv, pcg_scal, pcg_hist;
 
     // work / result buffers
     ipcgpu::DevBuf<double> gcont, hblk, g, e_per_tet, partials, scalar_out, inv_steps, dir;

@@ -22,6 +22,8 @@ struct IterState {
     int ref_count[3];
     int n_set[3];                     // active / mollified / candidate counts of the last constraint set (this rank's lists)
     int flags[8];                     // IPCGPU_FLAG_* slots (nonzero = raised); cleared by ipcgpu_fetch_iteration
+    int grid_axis_cells;              // cells per axis the broad-phase grids built since the last fetch would have liked (sort-width tuning)
+    int pad_;
     int checks[2];                    // line-search safeguards: inverted tets, surface triangles crossed by an edge (this rank's share, then sums)
     unsigned long long ccd_stats[8];  // survivors, warnings, deferred, longest / total pair cycles, boxes (thread pass, warp pass), candidates
 };

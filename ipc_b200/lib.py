@@ -72,6 +72,7 @@ SIGNATURES = {
     "ipcgpu_ccd_stats_ex": (C.c_int, [_ctxp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "ipcgpu_ccd_stats_timing": (C.c_int, [_ctxp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "ipcgpu_csr_set_zero": (C.c_int, [_ctxp]),
+    "ipcgpu_solve_pcg": (C.c_int, [_ctxp, _dp, C.c_double, C.c_int, _dp, C.c_int, _ip, _dp]),
     "ipcgpu_allreduce_grad_hess": (C.c_int, [_ctxp, C.c_int, C.c_int]),
     "ipcgpu_download": (C.c_int, [_ctxp, C.c_int, _dp, C.c_uint64]),
     "ipcgpu_device_ptr": (C.c_void_p, [_ctxp, C.c_int]),
@@ -413,6 +414,14 @@ class Context:
 
     def allreduce_grad_hess(self, with_gradient=1, with_hessian=1):
         self._ck(self.lib.ipcgpu_allreduce_grad_hess(self.h, with_gradient, with_hessian))
+
+    def solve_pcg(self, rhs=None, rel_tol=1e-8, max_iter=2000, want_x=True, adopt=False):
+        """H x = rhs (None: -gradient, both device resident); returns (x or None, iterations, relative residual)"""
+        x = np.empty(3 * self.nV) if want_x else None
+        it, res = C.c_int(), C.c_double()
+        self._ck(self.lib.ipcgpu_solve_pcg(self.h, _d(f64(rhs)) if rhs is not None else None, rel_tol, int(max_iter), _d(x) if want_x else None, int(adopt),
+                                           C.byref(it), C.byref(res)))
+        return x, it.value, res.value
 
     def csr_set_zero(self):
         self._ck(self.lib.ipcgpu_csr_set_zero(self.h))

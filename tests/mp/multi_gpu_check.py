@@ -69,6 +69,12 @@ def main():
     ctx.ccd_full(1e-6, evf, eee, None)
     it = ctx.fetch_iteration()
     part = ctx.partition_info()
+    from ipc_b200 import partition as P  # the library's partition must be the documented rule
+    vb_ = P.vertex_boundaries(m.T, m.nV, world)
+    assert (part["row_vertex_begin"], part["row_vertex_end"]) == (vb_[rank], vb_[rank + 1]), (part, vb_)
+    assert (part["tet_begin"], part["tet_end"]) == P.tet_range(m.nT, rank, world)
+    assert part["n_assembled_tets"] == len(P.assembled_tets(m.T, vb_[rank], vb_[rank + 1]))
+    assert (part["value_begin"], part["value_end"]) == P.owned_value_range(ia, 1, vb_[rank], vb_[rank + 1])
     g_def = ctx.download(L.BUF_GRADIENT, 3 * m.nV)
     a_own = np.zeros(ja.size)
     ctx.download_range_into(L.BUF_CSR_VALUES, part["value_begin"], a_own[part["value_begin"]:part["value_end"]])

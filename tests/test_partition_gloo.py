@@ -99,3 +99,55 @@ def test_contact_partition_allreduce_gloo():
     for p in procs:
         p.join(180)
     assert q.get(timeout=5) is True
+
+
+def _row_owner_worker(rank, world, port, q):
+    """The row-owner rule (ipc_b200/partition.py = csrc/api.cu build_maps): every rank assembles the tets that touch its vertex range and
+    keeps only the CSR rows (and gradient rows) it owns; the kept pieces are DISJOINT and their union is the single-process result -- no
+    reduction of the Hessian, only a gather."""
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle as orc
+    from ipc_b200 import mesh as M, partition as P
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    V, T = M.grid_tets(5, 4, 3)
+    m = M.Mesh(V, T, energy=0)
+    M.deform(m, 4)
+    ia, ja = m.csr_pattern(1)
+    b = P.vertex_boundaries(m.T, m.nV, world)
+    vb, ve = b[rank], b[rank + 1]
+    ids = P.assembled_tets(m.T, vb, ve)
+    sub = M.Mesh.__new__(M.Mesh)
+    sub.__dict__.update(m.__dict__)
+    sub.T, sub.nT = m.T[ids], len(ids)
+    sub.restTriInv, sub.vol, sub.mu, sub.lam = m.restTriInv[ids], m.vol[ids], m.mu[ids], m.lam[ids]
+    o = orc.Elastic(sub)
+    g = o.gradient(0.5, 0)
+    a = o.hessian_csr(0.5, ia, ja, 1, 1, 0)
+    a0, a1 = P.owned_value_range(ia, 1, vb, ve)
+    g_own, a_own = np.zeros_like(g), np.zeros_like(a)
+    g_own[3 * vb:3 * ve] = g[3 * vb:3 * ve]   # complete: every tet incident to an owned vertex was assembled here
+    a_own[a0:a1] = a[a0:a1]
+    tg, ta = torch.from_numpy(g_own), torch.from_numpy(a_own)
+    dist.all_reduce(tg, op=dist.ReduceOp.SUM); dist.all_reduce(ta, op=dist.ReduceOp.SUM)  # disjoint supports: this is a gather
+    cover = torch.zeros(world + 1, dtype=torch.int64); cover[rank] = len(ids); cover[world] = a1 - a0
+    dist.all_reduce(cover, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        full = orc.Elastic(m)
+        ok = (np.allclose(tg.numpy(), full.gradient(0.5, 0), rtol=0, atol=1e-13 * np.abs(tg.numpy()).max())
+              and np.allclose(ta.numpy(), full.hessian_csr(0.5, ia, ja, 1, 1, 0), rtol=0, atol=1e-13 * np.abs(ta.numpy()).max())
+              and int(cover[world]) == ja.size                       # the owned value ranges tile the whole array
+              and m.nT <= int(cover[:world].sum()) < 2 * m.nT)       # boundary tets are assembled twice, nothing is dropped
+        q.put(ok)
+    dist.destroy_process_group()
+
+
+def test_row_owner_partition_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_row_owner_worker, args=(r, 2, 29643, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+    assert q.get(timeout=5) is True
