@@ -76,11 +76,13 @@ struct SortedGrid {
     const unsigned* tab_key;        // hash table: cell key (0xffffffff = empty)
     const int2* tab_range;          //             [first, last+1) entries of that cell in the sorted arrays
     unsigned tab_mask;              // table size - 1 (power of two)
+    unsigned type_bit;              // triangles and edges share ONE sorted array and ONE table: the edge entries carry this bit above the cell key
 };
 
 DEV unsigned cell_hash(unsigned key) { return key * 2654435761u; }
 DEV int2 cell_lookup(const SortedGrid& sg, unsigned key)
 {
+    key |= sg.type_bit;
     unsigned h = cell_hash(key) & sg.tab_mask;
     for (;;) {
         const unsigned k = sg.tab_key[h];

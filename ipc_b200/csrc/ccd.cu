@@ -1383,6 +1383,8 @@ using namespace ipcgpu;
 
 static inline int nblk(long long n, int b) { return (int)((n + b - 1) / b); }
 SurfArgs surf_args(const ipcgpu_ctx* ctx); // constraint.cu
+SortedGrid tri_grid(const ipcgpu_ctx* ctx);
+SortedGrid edge_grid(const ipcgpu_ctx* ctx);
 int boxes_and_grid(ipcgpu_ctx* ctx, const double* dir, const double* alpha_ptr, double radius, const double* radius_ptr, bool with_vertex_boxes); // constraint.cu
 
 constexpr int kStage2WarpsPerCta = 4;
@@ -1523,7 +1525,7 @@ int ccd_full(ipcgpu_ctx* ctx, double tol, const double* err_vf, const double* er
     // multi-GPU: every rank sweeps a contiguous share of the query primitives (the reference's own loop decomposition, :1385, :1498)
     const int v0 = (int)((long long)s.nSV * ctx->rank / ctx->nranks), v1 = (int)((long long)s.nSV * (ctx->rank + 1) / ctx->nranks);
     const int e0 = (int)((long long)s.nSE * ctx->rank / ctx->nranks), e1 = (int)((long long)s.nSE * (ctx->rank + 1) / ctx->nranks);
-    const SortedGrid tg{ cw.tkeys.p, cw.tvals.p, cw.tsbox.p, s.nSF, cw.ttab_key.p, cw.ttab_start.p, cw.tab_mask }, eg{ cw.ekeys.p, cw.evals.p, cw.esbox.p, s.nSE, cw.etab_key.p, cw.etab_start.p, cw.tab_mask };
+    const SortedGrid tg = tri_grid(ctx), eg = edge_grid(ctx);
     CKD(cudaMemsetAsync(cw.counters.p + 8, 0, 2 * sizeof(int), st));
     unsigned* nPairs = reinterpret_cast<unsigned*>(cw.counters.p + 8);
     PairOut ppt{ cw.bp_pairs.p, nPairs, (unsigned)cw.bp_cap, w.counters.p + 14 }, pee{ cw.bp_pairs.p + cw.bp_cap, nPairs + 1, (unsigned)cw.bp_cap, w.counters.p + 14 };
@@ -1533,7 +1535,7 @@ int ccd_full(ipcgpu_ctx* ctx, double tol, const double* err_vf, const double* er
         ctx->launches += 2;
     }
     if (e1 > e0 && s.nSE > 1) {
-        k_ccd_pairs_ee<<<nblk(e1 - e0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(cw.grid.p, eg, cw.ebox.p, ist, e0, e1, pee);
+        k_ccd_pairs_ee<<<nblk(e1 - e0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(cw.grid.p, eg, cw.ebox.p, ist, s.nSF + e0, s.nSF + e1, pee); // edge entries sit behind the triangles
         k_ccd_filter_ee<<<kSMs * 8, 256, 0, st>>>(s, pee.pairs, pee.n, pee.cap, w.vmin.p, w.vmax.p, cw.ebox.p, out);
         ctx->launches += 2;
     }

@@ -115,19 +115,22 @@ __global__ void k_grid_params(const unsigned long long* __restrict__ bounds, dou
     g->nz = max(1, (int)floor((hi[2] - lo[2]) * g->inv_h) + 1);
 }
 
-// one entry per primitive: the cell of the box's lower corner
-__global__ void __launch_bounds__(256) k_emit(int n, const Box* __restrict__ boxes, const Grid* __restrict__ gp, unsigned long long* __restrict__ keys,
-    int* __restrict__ vals)
+// one entry per primitive: the cell of the box's lower corner.  Triangles [0, nT) and edges [nT, nT + nE) go into ONE array and ONE sort:
+// the edge keys carry a type bit above the cell key, so the sorted array is "all triangles by cell, then all edges by cell".
+__global__ void __launch_bounds__(256) k_emit(int nT, int nE, const Box* __restrict__ tboxes, const Box* __restrict__ eboxes, const Grid* __restrict__ gp, unsigned type_bit,
+    unsigned long long* __restrict__ keys, int* __restrict__ vals)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= nT + nE) return;
     const Grid g = *gp;
+    const bool edge = i >= nT;
+    const int id = edge ? i - nT : i;
     int c0[3], c1[3];
-    cell_range(g, boxes[i], c0, c1);
-    keys[i] = cell_key(g, c0[0], c0[1], c0[2]);
-    vals[i] = i;
+    cell_range(g, edge ? eboxes[id] : tboxes[id], c0, c1);
+    keys[i] = cell_key(g, c0[0], c0[1], c0[2]) | (edge ? (unsigned long long)type_bit : 0ull);
+    vals[i] = id;
 }
-// heads and tails of the runs of the sorted key array go into the open-addressing table (cell key -> [first, last+1))
+// heads and tails of the runs of the sorted key array go into the open-addressing table (key -> [first, last+1))
 __global__ void __launch_bounds__(256) k_build_cell_table(int n, const unsigned long long* __restrict__ keys, unsigned* __restrict__ tab_key, int2* __restrict__ tab_range,
     unsigned mask)
 {
@@ -149,12 +152,13 @@ __global__ void __launch_bounds__(256) k_build_cell_table(int n, const unsigned 
     }
 }
 // entries of the sorted grid: quantised box + id (see QEntry)
-__global__ void __launch_bounds__(256) k_gather_boxes(int n, const Box* __restrict__ boxes, const int* __restrict__ ids, const Grid* __restrict__ gp, uint4* __restrict__ sorted)
+__global__ void __launch_bounds__(256) k_gather_boxes(int nT, int nE, const Box* __restrict__ tboxes, const Box* __restrict__ eboxes, const int* __restrict__ ids,
+    const Grid* __restrict__ gp, uint4* __restrict__ sorted)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= nT + nE) return;
     const int id = ids[i];
-    const QBox q = quantize_box(*gp, boxes[id]);
+    const QBox q = quantize_box(*gp, i >= nT ? eboxes[id] : tboxes[id]); // the sorted array keeps the triangles in front
     sorted[i] = make_uint4((unsigned)q.lo[0] | ((unsigned)q.lo[1] << 16), (unsigned)q.lo[2] | ((unsigned)q.hi[0] << 16), (unsigned)q.hi[1] | ((unsigned)q.hi[2] << 16), (unsigned)id);
 }
 
@@ -538,10 +542,10 @@ int contact_alloc(ipcgpu_ctx* ctx)
 {
     ContactWork& w = ctx->cw;
     const int nSE = ctx->nSE, nSF = ctx->nSF, nSV = ctx->nSV;
-    const size_t nEnt = (size_t)std::max(std::max(nSE, nSF), 1);
+    const size_t nAll = (size_t)std::max(nSE + nSF, 1); // triangles and edges share one sorted array
     const int cap = std::max(ctx->pair_capacity, 1024);
     bool ok = w.vbox.reserve(std::max(nSV, 1)) && w.ebox.reserve(std::max(nSE, 1)) && w.tbox.reserve(std::max(nSF, 1)) && w.bounds.reserve(8) && w.grid.reserve(2)
-        && w.tsbox.reserve(std::max(nSF, 1)) && w.esbox.reserve(std::max(nSE, 1)) && w.tkeys.reserve(nEnt) && w.tvals.reserve(nEnt) && w.ekeys.reserve(nEnt) && w.evals.reserve(nEnt) && w.key_tmp.reserve(nEnt) && w.val_tmp.reserve(nEnt)
+        && w.centries.reserve(nAll) && w.ckeys.reserve(nAll) && w.cvals.reserve(nAll) && w.key_tmp.reserve(nAll) && w.val_tmp.reserve(nAll)
         && w.act.reserve(cap) && w.dup.reserve(cap) && w.para.reserve(cap) && w.para_e.reserve(cap) && w.cand.reserve((size_t)4 * cap) && w.tmp4.reserve(cap)
         && w.tmp2.reserve((size_t)4 * cap) && w.counters.reserve(16) && w.skey.reserve((size_t)4 * cap) && w.skey2.reserve((size_t)4 * cap) && w.sidx.reserve((size_t)4 * cap)
         && w.sidx2.reserve((size_t)4 * cap);
@@ -557,16 +561,16 @@ int contact_alloc(ipcgpu_ctx* ctx)
         ok = ok && w.xsend.reserve(w.xstride) && w.xrecv.reserve(w.xstride * ctx->nranks) && w.gact.reserve(cap) && w.gpara.reserve(cap) && w.gpara_e.reserve(cap);
     }
     unsigned tsz = 1024;
-    while (tsz < 2u * (unsigned)nEnt) tsz <<= 1;
+    while (tsz < 2u * (unsigned)nAll) tsz <<= 1;
     w.tab_mask = tsz - 1;
     w.bp_cap = (size_t)24 * std::max(std::max(nSE, nSV), 1024);
-    ok = ok && w.bp_pairs.reserve(2 * w.bp_cap) && w.ttab_key.reserve(tsz) && w.ttab_start.reserve(tsz) && w.etab_key.reserve(tsz) && w.etab_start.reserve(tsz);
+    ok = ok && w.bp_pairs.reserve(2 * w.bp_cap) && w.ctab_key.reserve(tsz) && w.ctab_start.reserve(tsz);
     if (!ok) {
         ctx->err = "contact workspace allocation failed";
         return IPCGPU_ERR_CUDA;
     }
     size_t b1 = 0, b2 = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, b1, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int*)nullptr, (int*)nullptr, (int)nEnt);
+    cub::DeviceRadixSort::SortPairs(nullptr, b1, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int*)nullptr, (int*)nullptr, (int)nAll);
     cub::DeviceRadixSort::SortPairs(nullptr, b2, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int*)nullptr, (int*)nullptr, 4 * cap);
     if (!w.cub_tmp.reserve(std::max(b1, b2) + 256)) {
         ctx->err = "cub temp allocation failed";
@@ -576,24 +580,39 @@ int contact_alloc(ipcgpu_ctx* ctx)
     return 0;
 }
 
-// build one sorted grid over `boxes` (n prims): (keys, vals) sorted by cell, boxes gathered into `sorted_boxes`
-static int build_grid(ipcgpu_ctx* ctx, int n, const Box* boxes, DevBuf<unsigned long long>& keys, DevBuf<int>& vals, QEntry* sorted_entries, unsigned* tab_key, int2* tab_range)
+// build the sorted grids of the triangles and the edges in ONE pass: one emit, one radix sort (cell key + type bit), one gather of the
+// quantised entries, one cell table
+static int build_grids(ipcgpu_ctx* ctx, int nT, int nE)
 {
     ContactWork& w = ctx->cw;
     cudaStream_t st = ctx->stream;
+    const int n = nT + nE;
     if (n <= 0) return 0;
-    k_emit<<<nblk(n, 256), 256, 0, st>>>(n, boxes, w.grid.p, w.key_tmp.p, w.val_tmp.p);
+    const unsigned type_bit = 1u << (3 * w.axis_bits);
+    k_emit<<<nblk(n, 256), 256, 0, st>>>(nT, nE, w.tbox.p, w.ebox.p, w.grid.p, type_bit, w.key_tmp.p, w.val_tmp.p);
     size_t bytes = w.cub_tmp.n;
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(w.cub_tmp.p, bytes, w.key_tmp.p, keys.p, w.val_tmp.p, vals.p, n, 0, 3 * w.axis_bits, st); // cells < 2^(3 axis_bits)
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(w.cub_tmp.p, bytes, w.key_tmp.p, w.ckeys.p, w.val_tmp.p, w.cvals.p, n, 0, 3 * w.axis_bits + 1, st); // cells < 2^(3 axis_bits), + type
     if (e != cudaSuccess) {
         ctx->err = std::string("cub grid sort: ") + cudaGetErrorString(e);
         return IPCGPU_ERR_CUDA;
     }
-    k_gather_boxes<<<nblk(n, 256), 256, 0, st>>>(n, boxes, vals.p, w.grid.p, reinterpret_cast<uint4*>(sorted_entries));
-    cudaMemsetAsync(tab_key, 0xff, (size_t)(w.tab_mask + 1) * sizeof(unsigned), st);
-    k_build_cell_table<<<nblk(n, 256), 256, 0, st>>>(n, keys.p, tab_key, tab_range, w.tab_mask);
+    k_gather_boxes<<<nblk(n, 256), 256, 0, st>>>(nT, nE, w.tbox.p, w.ebox.p, w.cvals.p, w.grid.p, reinterpret_cast<uint4*>(w.centries.p));
+    cudaMemsetAsync(w.ctab_key.p, 0xff, (size_t)(w.tab_mask + 1) * sizeof(unsigned), st);
+    k_build_cell_table<<<nblk(n, 256), 256, 0, st>>>(n, w.ckeys.p, w.ctab_key.p, w.ctab_start.p, w.tab_mask);
+    w.built_axis_bits = w.axis_bits;
     ctx->launches += 4;
     return 0;
+}
+// views of the combined sorted array: triangles are entries [0, nSF), edges [nSF, nSF + nSE) (positions are absolute in both views)
+SortedGrid tri_grid(const ipcgpu_ctx* ctx)
+{
+    const ContactWork& w = ctx->cw;
+    return SortedGrid{ w.ckeys.p, w.cvals.p, w.centries.p, ctx->nSF, w.ctab_key.p, w.ctab_start.p, w.tab_mask, 0u };
+}
+SortedGrid edge_grid(const ipcgpu_ctx* ctx)
+{
+    const ContactWork& w = ctx->cw;
+    return SortedGrid{ w.ckeys.p, w.cvals.p, w.centries.p, ctx->nSE, w.ctab_key.p, w.ctab_start.p, w.tab_mask, 1u << (3 * w.built_axis_bits) };
 }
 
 SurfArgs surf_args(const ipcgpu_ctx* ctx)
@@ -619,10 +638,7 @@ int boxes_and_grid(ipcgpu_ctx* ctx, const double* dir, const double* alpha_ptr, 
     if (s.nSF > 0) k_boxes<<<nblk(s.nSF, 256), 256, 0, st>>>(s, 2, dir, alpha_ptr, w.tbox.p, w.bounds.p);
     k_grid_params<<<1, 32, 0, st>>>(w.bounds.p, radius, radius_ptr, w.axis_bits, w.grid.p, ctx->iter.p);
     ctx->launches += 5;
-    int rc;
-    if ((rc = build_grid(ctx, s.nSF, w.tbox.p, w.tkeys, w.tvals, w.tsbox.p, w.ttab_key.p, w.ttab_start.p))) return rc;
-    if ((rc = build_grid(ctx, s.nSE, w.ebox.p, w.ekeys, w.evals, w.esbox.p, w.etab_key.p, w.etab_start.p))) return rc;
-    return 0;
+    return build_grids(ctx, s.nSF, s.nSE);
 }
 
 // pack this rank's lists, allgather, rebuild the global lists (called by api.cu around its ncclAllGather)
@@ -679,7 +695,7 @@ int contact_constraint_set(ipcgpu_ctx* ctx, double dHat, int wantCand, int* nC, 
     out.para = w.para.p; out.para_e = w.para_e.p; out.nPara = w.counters.p + 2; out.capPara = w.cap;
     out.cand = w.cand.p; out.nCand = w.counters.p + 3; out.capCand = 4 * w.cap;
     out.overflow = w.counters.p + 4;
-    const SortedGrid tg{ w.tkeys.p, w.tvals.p, w.tsbox.p, s.nSF, w.ttab_key.p, w.ttab_start.p, w.tab_mask }, eg{ w.ekeys.p, w.evals.p, w.esbox.p, s.nSE, w.etab_key.p, w.etab_start.p, w.tab_mask };
+    const SortedGrid tg = tri_grid(ctx), eg = edge_grid(ctx);
     // partitioned mode (ipcgpu_set_contact_partition): this rank only issues its share of the queries (the reference's own loop
     // decomposition, :2168 / :2271), so its lists hold a disjoint part of the global sets
     int v0 = 0, v1 = s.nSV, e0 = 0, e1 = s.nSE;
@@ -697,7 +713,7 @@ int contact_constraint_set(ipcgpu_ctx* ctx, double dHat, int wantCand, int* nC, 
         ctx->launches += 2;
     }
     if (e1 > e0 && s.nSE > 1) {
-        k_pairs_ee<<<nblk(e1 - e0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(w.grid.p, eg, w.ebox.p, dHat, radius, e0, e1, pee);
+        k_pairs_ee<<<nblk(e1 - e0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(w.grid.p, eg, w.ebox.p, dHat, radius, s.nSF + e0, s.nSF + e1, pee); // edge entries sit behind the triangles
         k_classify_ee<<<kSMs * 8, 128, 0, st>>>(s, pee.pairs, pee.n, pee.cap, dHat, wantCand, out);
         ctx->launches += 2;
     }

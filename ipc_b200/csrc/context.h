@@ -43,15 +43,15 @@ struct DevBuf {
 // device workspace of the contact stages (constraint.cu / ccd.cu)
 struct ContactWork {
     DevBuf<Box> vbox, ebox, tbox;   // per-primitive boxes (primitive order)
-    DevBuf<QEntry> tsbox, esbox;    // grid-sorted entries: quantised box + id
-    DevBuf<unsigned long long> bounds, tkeys, ekeys, key_tmp, skey, skey2;
+    DevBuf<QEntry> centries;        // grid-sorted entries (triangles first, then edges): quantised box + id
+    DevBuf<unsigned long long> bounds, ckeys, key_tmp, skey, skey2; // ckeys: sorted cell keys of the combined triangle + edge grid
     DevBuf<Grid> grid;
-    DevBuf<int> tvals, evals, val_tmp, counters, sidx, sidx2;
+    DevBuf<int> cvals, val_tmp, counters, sidx, sidx2;
     DevBuf<int4> act, dup, para, tmp4;
     DevBuf<int2> para_e, cand, tmp2;
     DevBuf<unsigned char> cub_tmp;
-    DevBuf<unsigned> ttab_key, etab_key; // cell hash tables of the triangle / edge grids
-    DevBuf<int2> ttab_start, etab_start; // [first, last+1) entry range per table slot
+    DevBuf<unsigned> ctab_key;  // ONE cell hash table for both grids (key = cell | type bit)
+    DevBuf<int2> ctab_start;    // [first, last+1) entry range per table slot (positions in the combined sorted array)
     unsigned tab_mask = 0;
     DevBuf<int2> bp_pairs; // broad-phase pair lists (PT then EE), bp_cap each
     size_t bp_cap = 0;
@@ -62,6 +62,7 @@ struct ContactWork {
     bool want_cand = false;
     unsigned dup_tab = 1024;    // slots of the PP/PE duplicate-merge table
     int axis_bits = 10;         // key bits per axis of the grid sorts (re-tuned from IterState::grid_axis_cells at every fetch)
+    int built_axis_bits = 10;   // ... of the grids that are currently built (position of the type bit)
     // barrier stage workspace, sized by the pair capacity
     DevBuf<double> bHraw, bpartials, bval; // (bval: per-constraint values of ipcgpu_evaluate_constraints / inputs of ..._jacobian_t)
     DevBuf<int> brows, bpsd;

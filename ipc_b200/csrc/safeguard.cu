@@ -252,6 +252,7 @@ __global__ void __launch_bounds__(256) k_count_inverted(ElasticArgs p, int* __re
 using namespace ipcgpu;
 
 SurfArgs surf_args(const ipcgpu_ctx* ctx); // constraint.cu
+SortedGrid edge_grid(const ipcgpu_ctx* ctx);
 int boxes_and_grid(ipcgpu_ctx* ctx, const double* dir, const double* alpha_ptr, double radius, const double* radius_ptr, bool with_vertex_boxes); // constraint.cu
 
 static inline int nblk(long long n, int b) { return (int)((n + b - 1) / b); }
@@ -281,7 +282,7 @@ int safeguard_intersections(ipcgpu_ctx* ctx)
     if (s.nSF == 0 || s.nSE == 0) return 0;
     int rc = boxes_and_grid(ctx, nullptr, nullptr, 0.0, nullptr, false);
     if (rc) return rc;
-    const SortedGrid eg{ w.ekeys.p, w.evals.p, w.esbox.p, s.nSE, w.etab_key.p, w.etab_start.p, w.tab_mask };
+    const SortedGrid eg = edge_grid(ctx);
     const int f0 = (int)((long long)s.nSF * ctx->rank / ctx->nranks), f1 = (int)((long long)s.nSF * (ctx->rank + 1) / ctx->nranks);
     if (f1 > f0) k_tri_edge_intersect<<<nblk(f1 - f0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(s, w.grid.p, eg, w.tbox.p, f0, f1, cnt);
     ++ctx->launches;
