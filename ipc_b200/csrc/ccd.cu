@@ -1445,12 +1445,26 @@ int ccd_narrow(ipcgpu_ctx* ctx, const int2* cand, const int* n32, const unsigned
         k_ti_stage1<<<kSMs * 16, 128, 0, st>>>(a, w.surv.p, nSurv, flags);
         ctx->prof_end(pe1);
         unsigned* nDefA = reinterpret_cast<unsigned*>(flags + 2);
-        static const int ti_mode = [] { const char* e = std::getenv("IPCGPU_TI_MODE"); return e ? std::atoi(e) : 1; }();
-        if (ti_mode == 1) // group pass (8 lanes per pair) over every survivor; flags[3] is its work counter
-            k_ti_groups<<<kSMs * 4, 32 * kGrpWarpsPerCta, 0, st>>>(a, w.surv.p, nSurv, reinterpret_cast<unsigned*>(flags + 3), w.surv2.p, nDefA, &ist->ccd_ord, flags + 1);
-        else // thread pass (one thread per pair, 10-box budget)
+        // pass A (thread per survivor, 10-box budget): the shallow majority (2-3 boxes) at 32 pairs per warp;
+        // pass G (8 lanes per pair, 4 pairs per warp): the searches pass A gave up on, unless a level outgrows the group's 44-box buffer;
+        // pass B (warp per pair): those wide searches.  IPCGPU_TI_MODE: 0 = A + B (round 1), 1 = G + B, 2 = A + G + B (default)
+        static const int ti_mode = [] { const char* e = std::getenv("IPCGPU_TI_MODE"); return e ? std::atoi(e) : 2; }();
+        unsigned* grp_work = reinterpret_cast<unsigned*>(flags + 3);
+        unsigned* nDefB = reinterpret_cast<unsigned*>(flags + 10);
+        if (ti_mode == 1) {
+            k_ti_groups<<<kSMs * 4, 32 * kGrpWarpsPerCta, 0, st>>>(a, w.surv.p, nSurv, grp_work, w.surv2.p, nDefA, &ist->ccd_ord, flags + 1);
+            k_ti_stage2<<<kStage2Ctas, 32 * kStage2WarpsPerCta, 0, st>>>(a, w.surv2.p, nDefA, work, reinterpret_cast<DBox*>(w.scratch.p), kLevelCap, &ist->ccd_ord, flags + 1);
+        }
+        else {
             k_ti_stage15<<<kSMs * 16, 128, 0, st>>>(a, w.surv.p, nSurv, w.surv2.p, nDefA, 10, &ist->ccd_ord, flags + 1);
-        k_ti_stage2<<<kStage2Ctas, 32 * kStage2WarpsPerCta, 0, st>>>(a, w.surv2.p, nDefA, work, reinterpret_cast<DBox*>(w.scratch.p), kLevelCap, &ist->ccd_ord, flags + 1);
+            if (ti_mode == 2) { // the survivor list is dead after pass A: pass G's own deferrals go there
+                k_ti_groups<<<kSMs * 4, 32 * kGrpWarpsPerCta, 0, st>>>(a, w.surv2.p, nDefA, grp_work, w.surv.p, nDefB, &ist->ccd_ord, flags + 1);
+                k_ti_stage2<<<kStage2Ctas, 32 * kStage2WarpsPerCta, 0, st>>>(a, w.surv.p, nDefB, work, reinterpret_cast<DBox*>(w.scratch.p), kLevelCap, &ist->ccd_ord, flags + 1);
+                ++ctx->launches;
+            }
+            else
+                k_ti_stage2<<<kStage2Ctas, 32 * kStage2WarpsPerCta, 0, st>>>(a, w.surv2.p, nDefA, work, reinterpret_cast<DBox*>(w.scratch.p), kLevelCap, &ist->ccd_ord, flags + 1);
+        }
     }
     k_ccd_finish<<<1, 32, 0, st>>>(ist, nSurv, flags, overflow, stage == 3);
     ctx->prof_end(pe);
