@@ -1250,7 +1250,8 @@ __global__ void __launch_bounds__(32 * kGrpWarpsPerCta, 4) k_ti_groups(NarrowArg
 
 // stage 1.5: one THREAD per surviving pair with a small private level buffer; pairs whose search outgrows it are deferred
 constexpr int kThreadCap = 12;
-__global__ void __launch_bounds__(128) k_ti_stage15(NarrowArgs a, const unsigned* __restrict__ survivors, const unsigned* __restrict__ nSurvPtr,
+template <int CAP, int OCC>
+__global__ void __launch_bounds__(128, OCC) k_ti_stage15(NarrowArgs a, const unsigned* __restrict__ survivors, const unsigned* __restrict__ nSurvPtr,
     unsigned* __restrict__ deferred, unsigned* __restrict__ nDeferred, long long budget, unsigned long long* __restrict__ min_ord, int* __restrict__ warn)
 {
     const unsigned nSurv = *nSurvPtr;
@@ -1266,9 +1267,9 @@ __global__ void __launch_bounds__(128) k_ti_stage15(NarrowArgs a, const unsigned
             int v[4];
             TiPair P;
             load_pair(a.s, a.dir, a.cand[idx], vf, v, P);
-            DBox bufA[kThreadCap], bufB[kThreadCap];
+            DBox bufA[CAP], bufB[CAP];
             double toi;
-            const int hit = pair_ccd<1>(vf, P, a, bufA, bufB, kThreadCap, 0, toi, warn, nullptr, nullptr, budget);
+            const int hit = pair_ccd<1>(vf, P, a, bufA, bufB, CAP, 0, toi, warn, nullptr, nullptr, budget);
             if (hit == 2) defer = true;
             else if (hit == 1) atomicMin(min_ord, dbl_to_ord(toi));
         }
@@ -1447,8 +1448,10 @@ int ccd_narrow(ipcgpu_ctx* ctx, const int2* cand, const int* n32, const unsigned
         unsigned* nDefA = reinterpret_cast<unsigned*>(flags + 2);
         // pass A (thread per survivor, 10-box budget): the shallow majority (2-3 boxes) at 32 pairs per warp;
         // pass G (8 lanes per pair, 4 pairs per warp): the searches pass A gave up on, unless a level outgrows the group's 44-box buffer;
-        // pass B (warp per pair): those wide searches.  IPCGPU_TI_MODE: 0 = A + B (round 1), 1 = G + B, 2 = A + G + B (default)
-        static const int ti_mode = [] { const char* e = std::getenv("IPCGPU_TI_MODE"); return e ? std::atoi(e) : 2; }();
+        // pass B (warp per pair): those wide searches.  IPCGPU_TI_MODE: 0 = A + B (default), 1 = G + B, 2 = A + G + B, 3 = A + A(48-box levels) + B.
+        // Measured on C5 (narrow phase per iteration): A + B 1.62 ms, G + B 2.02 ms, A + G + B 2.12 ms -- the four groups of a warp diverge and
+        // the hardware runs divergent paths of one warp one after the other, so pass G buys no latency hiding (kept for the record)
+        static const int ti_mode = [] { const char* e = std::getenv("IPCGPU_TI_MODE"); return e ? std::atoi(e) : 0; }();
         unsigned* grp_work = reinterpret_cast<unsigned*>(flags + 3);
         unsigned* nDefB = reinterpret_cast<unsigned*>(flags + 10);
         if (ti_mode == 1) {
@@ -1456,9 +1459,18 @@ int ccd_narrow(ipcgpu_ctx* ctx, const int2* cand, const int* n32, const unsigned
             k_ti_stage2<<<kStage2Ctas, 32 * kStage2WarpsPerCta, 0, st>>>(a, w.surv2.p, nDefA, work, reinterpret_cast<DBox*>(w.scratch.p), kLevelCap, &ist->ccd_ord, flags + 1);
         }
         else {
-            k_ti_stage15<<<kSMs * 16, 128, 0, st>>>(a, w.surv.p, nSurv, w.surv2.p, nDefA, 10, &ist->ccd_ord, flags + 1);
+            static const long long budgetA = [] { const char* e = std::getenv("IPCGPU_TI_BUDGET"); return e ? std::atoll(e) : 10ll; }();
+            static const int occA = [] { const char* e = std::getenv("IPCGPU_TI_OCC"); return e ? std::atoi(e) : 2; }(); // CTAs/SM the thread pass is compiled for (2: 255 regs, 3: 168 regs + spills)
+            if (occA == 3) k_ti_stage15<kThreadCap, 3><<<kSMs * 16, 128, 0, st>>>(a, w.surv.p, nSurv, w.surv2.p, nDefA, budgetA, &ist->ccd_ord, flags + 1);
+            else k_ti_stage15<kThreadCap, 2><<<kSMs * 16, 128, 0, st>>>(a, w.surv.p, nSurv, w.surv2.p, nDefA, budgetA, &ist->ccd_ord, flags + 1);
             if (ti_mode == 2) { // the survivor list is dead after pass A: pass G's own deferrals go there
                 k_ti_groups<<<kSMs * 4, 32 * kGrpWarpsPerCta, 0, st>>>(a, w.surv2.p, nDefA, grp_work, w.surv.p, nDefB, &ist->ccd_ord, flags + 1);
+                k_ti_stage2<<<kStage2Ctas, 32 * kStage2WarpsPerCta, 0, st>>>(a, w.surv.p, nDefB, work, reinterpret_cast<DBox*>(w.scratch.p), kLevelCap, &ist->ccd_ord, flags + 1);
+                ++ctx->launches;
+            }
+            else if (ti_mode == 3) { // second thread pass over the compacted deferrals: 48-box levels in local memory, 256-box budget
+                static const long long budgetA2 = [] { const char* e = std::getenv("IPCGPU_TI_BUDGET2"); return e ? std::atoll(e) : 256ll; }();
+                k_ti_stage15<48, 2><<<kSMs * 8, 128, 0, st>>>(a, w.surv2.p, nDefA, w.surv.p, nDefB, budgetA2, &ist->ccd_ord, flags + 1);
                 k_ti_stage2<<<kStage2Ctas, 32 * kStage2WarpsPerCta, 0, st>>>(a, w.surv.p, nDefB, work, reinterpret_cast<DBox*>(w.scratch.p), kLevelCap, &ist->ccd_ord, flags + 1);
                 ++ctx->launches;
             }
