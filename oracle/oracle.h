@@ -125,6 +125,23 @@ void orc_barrier_hessian_csr(const orc_surf* s, const int* mmcvid, int nC, const
 /* per-pair projected block, for kernel parity: kind/verts out, H row-major 12x12 (unused rows zero) */
 void orc_barrier_pair_hessian(const orc_surf* s, const int mm[4], double dHat, double kappa, double* H144, int* nvert);
 
+/* ---- lagged friction of the self-contact pairs (oracle/friction.cpp) ---------------------------------- */
+/* Optimizer.cpp:1582-1595 (lambda) + SelfCollisionHandler.cpp:2481-2527 (closest-point coordinates, tangent bases) at s->V.
+ * basis: 6 per pair = Eigen column-major Matrix<double,3,2>. */
+void orc_friction_lag(const orc_surf* s, const int* mmcvid, int nC, double dHat, double kappa, double* lambda, double* coord, double* basis);
+/* SelfCollisionHandler.cpp:2529-2596 ; s->V current, Vt = result.V_prev (SoA) */
+void orc_friction_energy(const orc_surf* s, const double* Vt, const int* mmcvid, int nC, const double* lambda, const double* coord, const double* basis,
+    double eps2, double coef, double* E);
+/* SelfCollisionHandler.cpp:2598-2735 ; g += (interleaved) */
+void orc_friction_gradient(const orc_surf* s, const double* Vt, const int* mmcvid, int nC, const double* lambda, const double* coord, const double* basis,
+    double eps2, double coef, double* g);
+/* one pair's block, row-major with leading dimension 12; project = 0 skips makePD (for the finite-difference tests) */
+void orc_friction_pair_hessian(const orc_surf* s, const double* Vt, const int mm[4], double lambda, const double coord[2], const double basis[6], double eps2,
+    double coef, int project, double* H144, int* nvert);
+/* SelfCollisionHandler.cpp:2745-2987 ; a += */
+void orc_friction_hessian_csr(const orc_surf* s, const double* Vt, const int* mmcvid, int nC, const double* lambda, const double* coord, const double* basis,
+    double eps2, double coef, int projectDBC, const int* ia, const int* ja, int index_base, double* a, int nthreads);
+
 /* ---- broad phase + CCD (oracle/ccd.cpp) -------------------------------------- */
 typedef struct {
     double lo[3]; double inv_h; int count[3];

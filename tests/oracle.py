@@ -287,6 +287,51 @@ class Surf:
                                       i(ia), i(ja), base, d(a), nthreads)
         return a
 
+    # ---- lagged friction (oracle/friction.cpp) ----
+    def friction_lag(self, mm, dHat, kappa):
+        """(lambda, coord (n,2), basis (n,6)) of the active set at the current positions"""
+        mm = np.ascontiguousarray(mm, dtype=np.int32)
+        n = len(mm)
+        lam, co, ba = np.empty(max(n, 1)), np.empty((max(n, 1), 2)), np.empty((max(n, 1), 6))
+        lib().orc_friction_lag(C.byref(self.s), i(mm), n, C.c_double(dHat), C.c_double(kappa), d(lam), d(co), d(ba))
+        return lam[:n], co[:n], ba[:n]
+
+    @staticmethod
+    def _soa(Vt):
+        return np.ascontiguousarray(np.asarray(Vt, dtype=np.float64).T).ravel() if np.ndim(Vt) == 2 else np.ascontiguousarray(Vt, dtype=np.float64)
+
+    def friction_energy(self, Vt, mm, lam, co, ba, eps2, coef):
+        mm = np.ascontiguousarray(mm, dtype=np.int32); vt = self._soa(Vt)
+        lam, co, ba = (np.ascontiguousarray(x, dtype=np.float64) for x in (lam, co, ba))
+        E = C.c_double()
+        lib().orc_friction_energy(C.byref(self.s), d(vt), i(mm), len(mm), d(lam), d(co), d(ba), C.c_double(eps2), C.c_double(coef), C.byref(E))
+        return E.value
+
+    def friction_gradient(self, Vt, mm, lam, co, ba, eps2, coef, g=None):
+        if g is None:
+            g = np.zeros(3 * self.mesh.nV)
+        mm = np.ascontiguousarray(mm, dtype=np.int32); vt = self._soa(Vt)
+        lam, co, ba = (np.ascontiguousarray(x, dtype=np.float64) for x in (lam, co, ba))
+        lib().orc_friction_gradient(C.byref(self.s), d(vt), i(mm), len(mm), d(lam), d(co), d(ba), C.c_double(eps2), C.c_double(coef), d(g))
+        return g
+
+    def friction_pair_hessian(self, Vt, mm4, lam, co, ba, eps2, coef, project=1):
+        H = np.empty(144); nv = C.c_int()
+        mm4 = np.ascontiguousarray(mm4, dtype=np.int32); vt = self._soa(Vt)
+        co, ba = np.ascontiguousarray(co, dtype=np.float64), np.ascontiguousarray(ba, dtype=np.float64)
+        lib().orc_friction_pair_hessian(C.byref(self.s), d(vt), i(mm4), C.c_double(lam), d(co), d(ba), C.c_double(eps2), C.c_double(coef), project, d(H), C.byref(nv))
+        return H.reshape(12, 12), nv.value
+
+    def friction_hessian_csr(self, Vt, mm, lam, co, ba, eps2, coef, ia, ja, base, projectDBC=1, a=None, nthreads=1):
+        ia = np.ascontiguousarray(ia, dtype=np.int32); ja = np.ascontiguousarray(ja, dtype=np.int32)
+        if a is None:
+            a = np.zeros(ja.size)
+        mm = np.ascontiguousarray(mm, dtype=np.int32); vt = self._soa(Vt)
+        lam, co, ba = (np.ascontiguousarray(x, dtype=np.float64) for x in (lam, co, ba))
+        lib().orc_friction_hessian_csr(C.byref(self.s), d(vt), i(mm), len(mm), d(lam), d(co), d(ba), C.c_double(eps2), C.c_double(coef), projectDBC,
+                                       i(ia), i(ja), base, d(a), nthreads)
+        return a
+
     def pair_hessian(self, mm4, dHat, kappa):
         H = np.empty(144); nv = C.c_int()
         mm4 = np.ascontiguousarray(mm4, dtype=np.int32)
