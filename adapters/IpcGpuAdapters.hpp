@@ -229,6 +229,68 @@ struct GpuSelfCollisionHandler {
         IpcGpuScene::check(gpu->ctx, ipcgpu_ccd_full_ti(gpu->ctx, tolerance, tight_inclusion_vf_err.data(), tight_inclusion_ee_err.data(), &stepSize, nullptr),
             "ipcgpu_ccd_full_ti");
     }
+    // ---- lagged friction (reference signatures, SelfCollisionHandler.hpp:182-208).  The reference hands V / Vt / the lagged containers to
+    // every call; the adapter uploads what it is handed (positions every call, the lagged containers when their tag changes) ------------
+    inline static SetTag fric_tag{ ~size_t(0), 0 };
+    static void ensureFriction(const std::vector<MMCVID>& constraintSet, const Eigen::VectorXd& multipliers, const std::vector<Eigen::Vector2d>& MMDistCoord,
+        const std::vector<Eigen::Matrix<double, 3, 2>>& MMTanBasis)
+    {
+        static_assert(sizeof(Eigen::Vector2d) == 2 * sizeof(double) && sizeof(Eigen::Matrix<double, 3, 2>) == 6 * sizeof(double), "fixed-size Eigen types are plain arrays");
+        SetTag t = tag_of(constraintSet);
+        t.h ^= fnv(reinterpret_cast<const int*>(multipliers.data()), 2 * constraintSet.size()) * 31u;
+        t.h ^= fnv(reinterpret_cast<const int*>(MMDistCoord.data()), 4 * constraintSet.size()) * 131u;
+        t.h ^= fnv(reinterpret_cast<const int*>(MMTanBasis.data()), 12 * constraintSet.size()) * 1031u;
+        if (t.n == fric_tag.n && t.h == fric_tag.h) return;
+        IpcGpuScene::check(gpu->ctx, ipcgpu_set_friction_data(gpu->ctx, (int)constraintSet.size(), reinterpret_cast<const int*>(constraintSet.data()), multipliers.data(),
+                                          reinterpret_cast<const double*>(MMDistCoord.data()), reinterpret_cast<const double*>(MMTanBasis.data())),
+            "ipcgpu_set_friction_data");
+        fric_tag = t;
+    }
+    // :2481-2527 -- computed on the device at the current device state, copied into the caller's containers.  The multipliers of
+    // Optimizer.cpp:1582-1591 come out of the same kernel (gpuFrictionMultipliers below), so the host loop there can go.
+    static void computeDistCoordAndTanBasis(const Mesh<3>& mesh, const std::vector<MMCVID>& constraintSet, std::vector<Eigen::Vector2d>& MMDistCoord,
+        std::vector<Eigen::Matrix<double, 3, 2>>& MMTanBasis, double dHat = 1.0, double kappa = 0.0, Eigen::VectorXd* multipliers = nullptr)
+    {
+        ensureSets(constraintSet, last_para, last_para_e);
+        IpcGpuScene::check(gpu->ctx, ipcgpu_set_state(gpu->ctx, mesh.V.data()), "ipcgpu_set_state");
+        int n = 0;
+        IpcGpuScene::check(gpu->ctx, ipcgpu_friction_lag(gpu->ctx, dHat, kappa, &n), "ipcgpu_friction_lag");
+        MMDistCoord.resize(constraintSet.size());
+        MMTanBasis.resize(constraintSet.size());
+        if (multipliers) multipliers->conservativeResize(constraintSet.size());
+        IpcGpuScene::check(gpu->ctx, ipcgpu_get_friction_data(gpu->ctx, &n, nullptr, multipliers ? multipliers->data() : nullptr, reinterpret_cast<double*>(MMDistCoord.data()),
+                                          reinterpret_cast<double*>(MMTanBasis.data())),
+            "ipcgpu_get_friction_data");
+        fric_tag = SetTag{ ~size_t(0), 0 }; // the caller may post-process its containers: re-validate at the next evaluator call
+    }
+    // :2529-2596
+    static void computeFrictionEnergy(const Eigen::MatrixXd& V, const Eigen::MatrixXd& Vt, const std::vector<MMCVID>& constraintSet, const Eigen::VectorXd& multipliers,
+        const std::vector<Eigen::Vector2d>& MMDistCoord, const std::vector<Eigen::Matrix<double, 3, 2>>& MMTanBasis, double& Ef, double eps2, double coef)
+    {
+        ensureFriction(constraintSet, multipliers, MMDistCoord, MMTanBasis);
+        IpcGpuScene::check(gpu->ctx, ipcgpu_set_state(gpu->ctx, V.data()), "ipcgpu_set_state");
+        IpcGpuScene::check(gpu->ctx, ipcgpu_set_prev_state(gpu->ctx, Vt.data()), "ipcgpu_set_prev_state");
+        IpcGpuScene::check(gpu->ctx, ipcgpu_friction_energy(gpu->ctx, eps2, coef, &Ef), "ipcgpu_friction_energy");
+    }
+    // :2598-2735
+    static void augmentFrictionGradient(const Eigen::MatrixXd& V, const Eigen::MatrixXd& Vt, const std::vector<MMCVID>& constraintSet, const Eigen::VectorXd& multipliers,
+        const std::vector<Eigen::Vector2d>& MMDistCoord, const std::vector<Eigen::Matrix<double, 3, 2>>& MMTanBasis, Eigen::VectorXd& grad_inc, double eps2, double coef)
+    {
+        ensureFriction(constraintSet, multipliers, MMDistCoord, MMTanBasis);
+        IpcGpuScene::check(gpu->ctx, ipcgpu_set_state(gpu->ctx, V.data()), "ipcgpu_set_state");
+        IpcGpuScene::check(gpu->ctx, ipcgpu_set_prev_state(gpu->ctx, Vt.data()), "ipcgpu_set_prev_state");
+        IpcGpuScene::check(gpu->ctx, ipcgpu_friction_gradient(gpu->ctx, eps2, coef, grad_inc.data()), "ipcgpu_friction_gradient");
+    }
+    // :2708-2743 (the LinSysSolver overload; the std::function overload of :2745 exists for the SQP path, which is out of scope)
+    static void augmentFrictionHessian(const Mesh<3>& mesh, const Eigen::MatrixXd& Vt, const std::vector<MMCVID>& constraintSet, const Eigen::VectorXd& multipliers,
+        const std::vector<Eigen::Vector2d>& MMDistCoord, const std::vector<Eigen::Matrix<double, 3, 2>>& MMTanBasis, LinSysSolver<Eigen::VectorXi, Eigen::VectorXd>* H_inc,
+        double eps2, double coef, bool projectDBC)
+    {
+        ensureFriction(constraintSet, multipliers, MMDistCoord, MMTanBasis);
+        IpcGpuScene::check(gpu->ctx, ipcgpu_set_state(gpu->ctx, mesh.V.data()), "ipcgpu_set_state");
+        IpcGpuScene::check(gpu->ctx, ipcgpu_set_prev_state(gpu->ctx, Vt.data()), "ipcgpu_set_prev_state");
+        IpcGpuScene::check(gpu->ctx, ipcgpu_friction_hessian(gpu->ctx, eps2, coef, projectDBC, H_inc->get_a().data()), "ipcgpu_friction_hessian");
+    }
     // :3254-3340 (edge-triangle part; see include/ipcgpu.h for the point-in-tetrahedron remark)
     static bool checkEdgeTriIntersectionIfAny(const Mesh<3>&, const SpatialHash<3>&)
     {

@@ -94,6 +94,7 @@ typedef struct ipcgpu_iteration {
     uint64_t ti_warnings;                    /* conservative early-outs of the Tight-Inclusion searches since the last fetch (should be 0) */
     int n_inverted_tets;                     /* last ipcgpu_check_inversion (summed over ranks) */
     int n_intersected_triangles;             /* last ipcgpu_intersection_free: surface triangles crossed by an edge (summed over ranks) */
+    double energy_friction, energy_inertia;  /* last ipcgpu_friction_energy / ipcgpu_inertia_energy (summed over ranks) */
 } ipcgpu_iteration;
 /* Synchronises once, completes the deferred cross-rank scalars (collective: every rank must call it), fills `out`, clears the
  * deferred error flags and returns out->status. */
@@ -180,6 +181,36 @@ int ipcgpu_constraint_jacobian_t(ipcgpu_ctx* ctx, const double* input, int n, do
 int ipcgpu_para_ee_gradient(ipcgpu_ctx* ctx, double dHat, double kappa, double* g_inout);
 /* CSR += makePD(kappa*mult*(b'' grad d grad d^T + b' hess d))  (augmentIPHessian :418-561, augmentParaEEHessian :3049-3201) */
 int ipcgpu_barrier_hessian(ipcgpu_ctx* ctx, double dHat, double kappa, int projectDBC, double* a_inout);
+
+/* ---- lagged friction of the self-contact pairs (SelfCollisionHandler.hpp: computeDistCoordAndTanBasis, computeFrictionEnergy,
+ * augmentFrictionGradient, augmentFrictionHessian; SelfCollisionHandler.cpp:2481-2987; FrictionUtils.hpp; C1 clamping, Types.hpp:42) ------ */
+/* result.V_prev: the positions at the start of the time step, against which the tangential slip is measured (Optimizer.cpp:3371).
+ * NULL = take the current device-resident state. */
+int ipcgpu_set_prev_state(ipcgpu_ctx* ctx, const double* V_prev_soa);
+/* The friction update of Optimizer.cpp:1582-1600: snapshots the active set of the last ipcgpu_constraint_set (MMActiveSet_lastH) and
+ * computes at the current positions lambda_c = -kappa b'(d_c) 2 sqrt(d_c) * multiplicity (MMLambda_lastH), the closest-point coordinates
+ * (MMDistCoord) and the tangent bases (MMTanBasis) -- computeDistCoordAndTanBasis, a serial loop in the reference.  Everything stays on the
+ * device; n_pairs (may be NULL: no synchronisation) receives the size of the lagged set. */
+int ipcgpu_friction_lag(ipcgpu_ctx* ctx, double dHat, double kappa, int* n_pairs);
+/* copies of the lagged data, for a caller that keeps the reference's containers (any pointer may be NULL): MMCVID x 4 ints, lambda,
+ * Vector2d coordinates, Matrix<double,3,2> bases column-major (6 doubles) */
+int ipcgpu_get_friction_data(ipcgpu_ctx* ctx, int* n_pairs, int* mmcvid4, double* lambda, double* coord2, double* basis6);
+/* upload host-held lagged data instead (drop-in use of only the three evaluators below with the reference's own containers) */
+int ipcgpu_set_friction_data(ipcgpu_ctx* ctx, int n_pairs, const int* mmcvid4, const double* lambda, const double* coord2, const double* basis6);
+/* computeFrictionEnergy (:2529-2596): coef * sum_c lambda_c f0(|u_c|), u_c = tangential slip since V_prev; eps2 = fricDHat, coef = selfFric */
+int ipcgpu_friction_energy(ipcgpu_ctx* ctx, double eps2, double coef, double* E);
+/* augmentFrictionGradient (:2598-2735): g += coef lambda_c f1(|u|)/|u| T^T u.  g_inout NULL = the device-resident gradient */
+int ipcgpu_friction_gradient(ipcgpu_ctx* ctx, double eps2, double coef, double* g_inout);
+/* augmentFrictionHessian (:2745-2987): CSR += makePD(T^T S T) per pair; a_inout as in ipcgpu_barrier_hessian */
+int ipcgpu_friction_hessian(ipcgpu_ctx* ctx, double eps2, double coef, int projectDBC, double* a_inout);
+
+/* ---- inertia term of Optimizer::computeEnergyVal / computeGradient (Optimizer.cpp:3227-3239, :3439-3450); the mass diagonal is the one of
+ * ipcgpu_set_mesh (also added to the Hessian diagonal by ipcgpu_elastic_grad_hess(add_mass), :3638-3668) ----------------------------- */
+int ipcgpu_set_xtilde(ipcgpu_ctx* ctx, const double* xtilde_soa);
+/* sum_v |x_v - xtilde_v|^2 m_v / 2 */
+int ipcgpu_inertia_energy(ipcgpu_ctx* ctx, double* E);
+/* g_v += m_v (x_v - xtilde_v) for every vertex that is not a projected Dirichlet vertex; g_inout NULL = the device-resident gradient */
+int ipcgpu_inertia_gradient(ipcgpu_ctx* ctx, int projectDBC, double* g_inout);
 
 /* ---- line-search safeguards (Optimizer.cpp:2709-2733, 2799-2811), so that a line-search trial -- step forward, checks, constraint set,
  * energies -- is one stream ------------------------------------------------------------------------------------------------------ */

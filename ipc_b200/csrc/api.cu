@@ -1082,6 +1082,249 @@ int ipcgpu_barrier_hessian(ipcgpu_ctx* ctx, double dHat, double kappa, int proje
     return IPCGPU_OK;
 }
 
+// ---- lagged friction of the self-contact pairs --------------------------------------------------------------
+int ipcgpu_set_prev_state(ipcgpu_ctx* ctx, const double* V_prev_soa)
+{
+    REQUIRE(ctx->nV > 0, IPCGPU_ERR_STATE, "ipcgpu_set_mesh first");
+    CK(cudaSetDevice(ctx->device));
+    ALLOC(ctx->Vprev, (size_t)3 * ctx->nV);
+    if (V_prev_soa) CK(cudaMemcpyAsync(ctx->Vprev.p, V_prev_soa, (size_t)3 * ctx->nV * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    else CK(cudaMemcpyAsync(ctx->Vprev.p, ctx->V.p, (size_t)3 * ctx->nV * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream)); // V_prev = V at the start of a step
+    ctx->prev_set = true;
+    return IPCGPU_OK;
+}
+
+static int friction_alloc(ipcgpu_ctx* ctx)
+{
+    ContactWork& w = ctx->cw;
+    const size_t cap = (size_t)std::max(ctx->pair_capacity, 1);
+    ALLOC(w.fr_cs, cap);
+    ALLOC(w.fr_n, 1);
+    ALLOC(w.fr_lambda, cap);
+    ALLOC(w.fr_coord, cap);
+    ALLOC(w.fr_basis, 6 * cap);
+    ALLOC(w.fr_partials, (size_t)friction_energy_blocks() + 8);
+    return IPCGPU_OK;
+}
+
+int ipcgpu_friction_lag(ipcgpu_ctx* ctx, double dHat, double kappa, int* n_pairs)
+{
+    REQUIRE(ctx->surface_ready, IPCGPU_ERR_STATE, "ipcgpu_set_surface first");
+    CK(cudaSetDevice(ctx->device));
+    int rc = friction_alloc(ctx);
+    if (rc) return rc;
+    ContactWork& w = ctx->cw;
+    // the lagged set is the whole active set on every rank (the global list after a partitioned build)
+    friction_lag(barrier_args(ctx, dHat, kappa, 0), w.fr_cs.p, w.fr_n.p, w.fr_lambda.p, w.fr_coord.p, w.fr_basis.p, ctx->pair_capacity,
+        &ctx->iter.p->flags[FLAG_NONPOSITIVE_DISTANCE], ctx->stream);
+    ++ctx->launches;
+    CK(cudaGetLastError());
+    w.fr_ready = true;
+    w.fr_host_n = -1;
+    if (n_pairs) {
+        CK(cudaMemcpyAsync(ctx->h_scalar, w.fr_n.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        w.fr_host_n = *reinterpret_cast<int*>(ctx->h_scalar);
+        *n_pairs = w.fr_host_n;
+    }
+    return IPCGPU_OK;
+}
+
+static int friction_host_count(ipcgpu_ctx* ctx)
+{
+    ContactWork& w = ctx->cw;
+    if (w.fr_host_n < 0) {
+        CK(cudaMemcpyAsync(ctx->h_scalar, w.fr_n.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        w.fr_host_n = *reinterpret_cast<int*>(ctx->h_scalar);
+    }
+    return IPCGPU_OK;
+}
+
+int ipcgpu_get_friction_data(ipcgpu_ctx* ctx, int* n_pairs, int* mmcvid4, double* lambda, double* coord2, double* basis6)
+{
+    REQUIRE(ctx->cw.fr_ready, IPCGPU_ERR_STATE, "ipcgpu_friction_lag / ipcgpu_set_friction_data first");
+    CK(cudaSetDevice(ctx->device));
+    int rc = friction_host_count(ctx);
+    if (rc) return rc;
+    ContactWork& w = ctx->cw;
+    const size_t n = (size_t)w.fr_host_n;
+    if (n_pairs) *n_pairs = w.fr_host_n;
+    if (n && mmcvid4) CK(cudaMemcpyAsync(mmcvid4, w.fr_cs.p, n * sizeof(int4), cudaMemcpyDeviceToHost, ctx->stream));
+    if (n && lambda) CK(cudaMemcpyAsync(lambda, w.fr_lambda.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (n && coord2) CK(cudaMemcpyAsync(coord2, w.fr_coord.p, n * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
+    if (n && basis6) CK(cudaMemcpyAsync(basis6, w.fr_basis.p, 6 * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return IPCGPU_OK;
+}
+
+int ipcgpu_set_friction_data(ipcgpu_ctx* ctx, int n_pairs, const int* mmcvid4, const double* lambda, const double* coord2, const double* basis6)
+{
+    REQUIRE(ctx->nV > 0, IPCGPU_ERR_STATE, "ipcgpu_set_mesh first");
+    REQUIRE(n_pairs >= 0 && n_pairs <= ctx->pair_capacity, IPCGPU_ERR_CAPACITY, "friction set larger than the pair capacity");
+    REQUIRE(n_pairs == 0 || (mmcvid4 && lambda && coord2 && basis6), IPCGPU_ERR_ARG, "null friction arrays");
+    CK(cudaSetDevice(ctx->device));
+    int rc = friction_alloc(ctx);
+    if (rc) return rc;
+    ContactWork& w = ctx->cw;
+    const size_t n = (size_t)n_pairs;
+    if (n) {
+        CK(cudaMemcpyAsync(w.fr_cs.p, mmcvid4, n * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(w.fr_lambda.p, lambda, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(w.fr_coord.p, coord2, n * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(w.fr_basis.p, basis6, 6 * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CK(cudaMemcpyAsync(w.fr_n.p, &n_pairs, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream)); // n_pairs lives on the caller's stack
+    w.fr_host_n = n_pairs;
+    w.fr_ready = true;
+    return IPCGPU_OK;
+}
+
+static FrictionArgs friction_args(ipcgpu_ctx* ctx, double eps2, double coef, int projectDBC)
+{
+    FrictionArgs p;
+    ContactWork& w = ctx->cw;
+    p.nV = ctx->nV; p.V = ctx->V.p; p.Vt = ctx->Vprev.p; p.dbc = ctx->has_dbc ? ctx->dbc.p : nullptr;
+    p.cs = w.fr_cs.p; p.n = w.fr_n.p; p.lambda = w.fr_lambda.p; p.coord = w.fr_coord.p; p.basis = w.fr_basis.p;
+    p.eps2 = eps2; p.coef = coef; p.projectDBC = projectDBC;
+    p.ia = ctx->ia.p; p.ja = ctx->ja.p; p.base = ctx->index_base;
+    p.rank = ctx->rank; p.nranks = ctx->nranks;
+    p.row_lo = ctx->nranks > 1 ? ctx->v_begin : 0;
+    p.row_hi = ctx->nranks > 1 ? ctx->v_end : ctx->nV;
+    return p;
+}
+#define REQUIRE_FRICTION() \
+    REQUIRE(ctx->cw.fr_ready, IPCGPU_ERR_STATE, "ipcgpu_friction_lag / ipcgpu_set_friction_data first"); \
+    REQUIRE(ctx->prev_set, IPCGPU_ERR_STATE, "ipcgpu_set_prev_state first")
+
+int ipcgpu_friction_energy(ipcgpu_ctx* ctx, double eps2, double coef, double* E)
+{
+    REQUIRE_FRICTION();
+    REQUIRE(eps2 > 0.0, IPCGPU_ERR_ARG, "fricDHat must be positive");
+    CK(cudaSetDevice(ctx->device));
+    cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_BARRIER);
+    friction_energy(friction_args(ctx, eps2, coef, 0), ctx->cw.fr_partials.p, ctx->stream);
+    reduce_sum(ctx->cw.fr_partials.p, friction_energy_blocks(), coef, ctx->scalar_out.p + 2, ctx->stream);
+    ctx->prof_end(pe);
+    ctx->launches += 2;
+    if (ctx->nranks > 1 && E) {
+        int r = g_nccl.AllReduce(ctx->scalar_out.p + 2, ctx->scalar_out.p + 2, 1, kNcclFloat64, kNcclSum, ctx->nccl_comm, ctx->stream);
+        REQUIRE(r == 0, IPCGPU_ERR_NCCL, "ncclAllReduce(friction energy) failed");
+    }
+    energy_store(ctx->iter.p, 2, ctx->scalar_out.p + 2, ctx->stream);
+    ++ctx->launches;
+    ctx->energy_local[2] = (ctx->nranks > 1 && !E);
+    CK(cudaGetLastError());
+    if (E) {
+        CK(cudaMemcpyAsync(ctx->h_scalar, ctx->scalar_out.p + 2, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        *E = ctx->h_scalar[0];
+    }
+    return IPCGPU_OK;
+}
+
+int ipcgpu_friction_gradient(ipcgpu_ctx* ctx, double eps2, double coef, double* g_inout)
+{
+    REQUIRE_FRICTION();
+    REQUIRE(eps2 > 0.0, IPCGPU_ERR_ARG, "fricDHat must be positive");
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if (g_inout && (rc = gradient_roundtrip_begin(ctx, g_inout))) return rc;
+    cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_BARRIER);
+    friction_gradient(friction_args(ctx, eps2, coef, 0), ctx->g.p, ctx->stream);
+    ctx->prof_end(pe);
+    ++ctx->launches;
+    CK(cudaGetLastError());
+    if (g_inout) return gradient_roundtrip_end(ctx, g_inout);
+    return IPCGPU_OK;
+}
+
+int ipcgpu_friction_hessian(ipcgpu_ctx* ctx, double eps2, double coef, int projectDBC, double* a_inout)
+{
+    REQUIRE_FRICTION();
+    REQUIRE(eps2 > 0.0, IPCGPU_ERR_ARG, "fricDHat must be positive");
+    REQUIRE(ctx->nnz > 0, IPCGPU_ERR_STATE, "ipcgpu_set_csr first");
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if (a_inout && (rc = upload_values(ctx, a_inout))) return rc;
+    cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_BARRIER);
+    friction_hessian(friction_args(ctx, eps2, coef, projectDBC), ctx->a.p, ctx->iter.p->flags + FLAG_PATTERN, ctx->stream);
+    ctx->prof_end(pe);
+    ++ctx->launches;
+    CK(cudaGetLastError());
+    if (a_inout) {
+        if ((rc = download_values(ctx, a_inout))) return rc;
+        if ((rc = fetch_iter_state(ctx))) return rc;
+        if (ctx->h_iter->flags[FLAG_PATTERN]) {
+            int only[8] = { 0 };
+            only[FLAG_PATTERN] = 1;
+            clear_flag(ctx, FLAG_PATTERN);
+            return status_from_flags(ctx, only);
+        }
+    }
+    return IPCGPU_OK;
+}
+
+// ---- inertia term (Optimizer.cpp:3227-3239, :3439-3450) ---------------------------------------------------------------------
+int ipcgpu_set_xtilde(ipcgpu_ctx* ctx, const double* xtilde_soa)
+{
+    REQUIRE(ctx->nV > 0, IPCGPU_ERR_STATE, "ipcgpu_set_mesh first");
+    REQUIRE(xtilde_soa != nullptr, IPCGPU_ERR_ARG, "null xTilta");
+    CK(cudaSetDevice(ctx->device));
+    ALLOC(ctx->xtilde, (size_t)3 * ctx->nV);
+    CK(cudaMemcpyAsync(ctx->xtilde.p, xtilde_soa, (size_t)3 * ctx->nV * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->xtilde_set = true;
+    return IPCGPU_OK;
+}
+
+int ipcgpu_inertia_energy(ipcgpu_ctx* ctx, double* E)
+{
+    REQUIRE(ctx->xtilde_set && ctx->has_mass, IPCGPU_ERR_STATE, "ipcgpu_set_xtilde and a mass diagonal (ipcgpu_set_mesh) first");
+    CK(cudaSetDevice(ctx->device));
+    // vertex blocks [nV r / N, nV (r+1) / N): every vertex exactly once across the ranks
+    const int v0 = (int)((long long)ctx->nV * ctx->rank / ctx->nranks), v1 = (int)((long long)ctx->nV * (ctx->rank + 1) / ctx->nranks);
+    ALLOC(ctx->in_partials, (size_t)inertia_energy_blocks(ctx->nV) + 8);
+    cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_ELASTIC_ENERGY);
+    inertia_energy(v0, v1, ctx->nV, ctx->V.p, ctx->xtilde.p, ctx->mass.p, ctx->in_partials.p, ctx->stream);
+    reduce_sum(ctx->in_partials.p, inertia_energy_blocks(v1 - v0), 1.0, ctx->scalar_out.p + 3, ctx->stream);
+    ctx->prof_end(pe);
+    ctx->launches += 2;
+    if (ctx->nranks > 1 && E) {
+        int r = g_nccl.AllReduce(ctx->scalar_out.p + 3, ctx->scalar_out.p + 3, 1, kNcclFloat64, kNcclSum, ctx->nccl_comm, ctx->stream);
+        REQUIRE(r == 0, IPCGPU_ERR_NCCL, "ncclAllReduce(inertia energy) failed");
+    }
+    energy_store(ctx->iter.p, 3, ctx->scalar_out.p + 3, ctx->stream);
+    ++ctx->launches;
+    ctx->energy_local[3] = (ctx->nranks > 1 && !E);
+    CK(cudaGetLastError());
+    if (E) {
+        CK(cudaMemcpyAsync(ctx->h_scalar, ctx->scalar_out.p + 3, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        *E = ctx->h_scalar[0];
+    }
+    return IPCGPU_OK;
+}
+
+int ipcgpu_inertia_gradient(ipcgpu_ctx* ctx, int projectDBC, double* g_inout)
+{
+    REQUIRE(ctx->xtilde_set && ctx->has_mass, IPCGPU_ERR_STATE, "ipcgpu_set_xtilde and a mass diagonal (ipcgpu_set_mesh) first");
+    CK(cudaSetDevice(ctx->device));
+    if (g_inout) CK(cudaMemcpyAsync(ctx->g.p, g_inout, (size_t)3 * ctx->nV * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    // Device-resident form with several ranks: the gradient is summed over the ranks later (ipcgpu_allreduce_grad_hess), so only rank 0 adds
+    // the per-vertex term.  Host form: every rank holds the caller's vector and adds the full term -- no reduction needed.
+    if (g_inout || ctx->nranks == 1 || ctx->rank == 0) {
+        inertia_gradient(ctx->nV, ctx->V.p, ctx->xtilde.p, ctx->mass.p, ctx->has_dbc ? ctx->dbc.p : nullptr, projectDBC, ctx->g.p, ctx->stream);
+        ++ctx->launches;
+    }
+    CK(cudaGetLastError());
+    if (g_inout) {
+        CK(cudaMemcpyAsync(g_inout, ctx->g.p, (size_t)3 * ctx->nV * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return IPCGPU_OK;
+}
+
 // ---- line-search safeguards -----------------------------------------------------------------------
 static int reduce_checks(ipcgpu_ctx* ctx)
 {
@@ -1194,7 +1437,7 @@ int ipcgpu_fetch_iteration(ipcgpu_ctx* ctx, ipcgpu_iteration* out)
         // complete the deferred scalars across ranks: locally summed energies, and the error flags (max) so that every rank returns
         // the same status
         cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_ALLREDUCE);
-        for (int s = 0; s < 2; ++s)
+        for (int s = 0; s < 4; ++s)
             if (ctx->energy_local[s]) {
                 int r = g_nccl.AllReduce(&ctx->iter.p->energy[s], &ctx->iter.p->energy[s], 1, kNcclFloat64, kNcclSum, ctx->nccl_comm, ctx->stream);
                 REQUIRE(r == 0, IPCGPU_ERR_NCCL, "ncclAllReduce(energy) failed");
@@ -1212,6 +1455,8 @@ int ipcgpu_fetch_iteration(ipcgpu_ctx* ctx, ipcgpu_iteration* out)
     const IterState& h = *ctx->h_iter;
     out->energy_elastic = h.energy[0];
     out->energy_barrier = h.energy[1];
+    out->energy_friction = h.energy[2];
+    out->energy_inertia = h.energy[3];
     out->alpha_inversion = h.alpha_stage[0];
     out->alpha_partial_ccd = h.alpha_stage[1];
     out->alpha_swept_grid = h.alpha_stage[2];

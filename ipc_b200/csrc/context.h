@@ -72,6 +72,13 @@ struct ContactWork {
     DevBuf<int4> xsend, xrecv, gact, gpara;
     DevBuf<int2> gpara_e;
     bool lists_global = false; // gact / gpara hold the global lists of the last partitioned build
+    // lagged friction data (MMActiveSet_lastH, MMLambda_lastH, MMDistCoord, MMTanBasis): snapshot taken by ipcgpu_friction_lag
+    DevBuf<int4> fr_cs;
+    DevBuf<int> fr_n;
+    DevBuf<double> fr_lambda, fr_basis, fr_partials;
+    DevBuf<double2> fr_coord;
+    int fr_host_n = -1;        // host mirror of the lagged count (-1 = not read back)
+    bool fr_ready = false;
 };
 
 // device workspace of the CCD stage (ccd.cu)
@@ -110,7 +117,7 @@ struct ipcgpu_ctx {
     ipcgpu::IterState* h_iter = nullptr;
     double pSize = 0.0;     // mean |p| over the surface vertices (SpatialHash.hpp:603-612), computed when p is uploaded
     bool dir_valid = false, pSize_surface = false;
-    bool energy_local[2] = { false, false }; // IterState::energy[s] still holds this rank's partial sum
+    bool energy_local[4] = { false, false, false, false }; // IterState::energy[s] still holds this rank's partial sum
     bool a_all_dirty = false;                // a cross-rank completion filled rows this rank does not own
     bool checks_local = false;               // IterState::checks still holds this rank's partial counts
     std::vector<int> h_ia;                   // host copy of the CSR row starts (value range of the owned rows)
@@ -118,7 +125,8 @@ struct ipcgpu_ctx {
     // mesh
     int nV = 0, nT = 0, energy = 0;
     int t_begin = 0, t_end = 0;
-    ipcgpu::DevBuf<double> V, Vsaved, Vrest, Ainv, vol, mu, lam, mass;
+    ipcgpu::DevBuf<double> V, Vsaved, Vrest, Ainv, vol, mu, lam, mass, Vprev, xtilde;
+    bool prev_set = false, xtilde_set = false; // result.V_prev (friction) / xTilta (inertia) uploaded
     ipcgpu::DevBuf<int> T;
     ipcgpu::DevBuf<uint8_t> dbc;
     bool has_mass = false, has_dbc = false, state_saved = false;
@@ -156,7 +164,7 @@ struct ipcgpu_ctx {
     ipcgpu::DevBuf<double> sol, pcg_b, pcg_r, pcg_p, pcg_q, pcg_minv, pcg_scal, pcg_hist;
 
     // work / result buffers
-    ipcgpu::DevBuf<double> gcont, hblk, g, e_per_tet, partials, scalar_out, inv_steps, dir;
+    ipcgpu::DevBuf<double> gcont, hblk, g, e_per_tet, partials, scalar_out, inv_steps, dir, in_partials;
     double* h_scalar = nullptr; // pinned staging for scalars
 
     // profiling: event pairs per stage (only when enabled)

@@ -18,7 +18,7 @@ struct IterState {
     double radius;                    // query inflation of the swept broad phase = one reference voxel
     double ref_lo[3], ref_inv_h;      // reference swept-grid geometry (SpatialHash.hpp:589-640)
     double alpha_stage[4];            // step after: inversion filter, partial CCD, swept-grid rescale, full CCD
-    double energy[2];                 // elastic, barrier (cross-rank sums once reduced)
+    double energy[4];                 // elastic, barrier, friction, inertia (cross-rank sums once reduced)
     int ref_count[3];
     int n_set[3];                     // active / mollified / candidate counts of the last constraint set (this rank's lists)
     int flags[8];                     // IPCGPU_FLAG_* slots (nonzero = raised); cleared by ipcgpu_fetch_iteration
@@ -98,10 +98,35 @@ void constraint_jacobian_t(const BarrierArgs& p, const double* input, double coe
 void para_gradient(const BarrierArgs& p, double* g, cudaStream_t st);
 // Hraw: 144 doubles per owned pair; rows: 4 vertex ids per owned pair; psd: makePD "unchanged" flag per owned pair; n_owned: device counter
 void barrier_hessian(const BarrierArgs& p, double* a, int* err, double* Hraw, int* rows, int* psd, int* n_owned, int capacity, cudaStream_t st);
+// friction.cu -- lagged friction of the self-contact pairs (SelfCollisionHandler.cpp:2481-2987)
+struct FrictionArgs {
+    int nV;
+    const double* V;       // current positions (SoA)
+    const double* Vt;      // positions at the start of the time step, result.V_prev (SoA)
+    const uint8_t* dbc;
+    const int4* cs; const int* n;   // LAGGED active set (MMActiveSet_lastH) and its device-resident size
+    const double* lambda;           // MMLambda_lastH
+    const double2* coord;           // MMDistCoord
+    const double* basis;            // MMTanBasis: 6 per pair, column-major 3x2
+    double eps2, coef;              // fricDHat, selfFric
+    int projectDBC;
+    const int* ia; const int* ja; int base;
+    int rank, nranks;               // E and g: contiguous share of the list; H: by row owner [row_lo, row_hi)
+    int row_lo, row_hi;
+};
+void friction_lag(const BarrierArgs& p, int4* cs_out, int* n_out, double* lambda, double2* coord, double* basis, int capacity, int* bad, cudaStream_t st);
+void friction_energy(const FrictionArgs& p, double* partials, cudaStream_t st);
+int friction_energy_blocks();
+void friction_gradient(const FrictionArgs& p, double* g, cudaStream_t st);
+void friction_hessian(const FrictionArgs& p, double* a, int* err, cudaStream_t st);
 // elastic.cu (shared fixed-order reduction)
 void reduce_sum(const double* partials, int n, double scale, double* out, cudaStream_t st);
 
 // misc.cu
 void step_forward(int nV, const double* x0_soa, const double* p_interleaved, double alpha, double* x_soa, cudaStream_t st);
+// inertia term of Optimizer::computeEnergyVal / computeGradient (Optimizer.cpp:3227-3239, :3439-3450)
+int inertia_energy_blocks(int nV);
+void inertia_energy(int v0, int v1, int nV, const double* x_soa, const double* xtilde_soa, const double* mass, double* partials, cudaStream_t st);
+void inertia_gradient(int nV, const double* x_soa, const double* xtilde_soa, const double* mass, const uint8_t* dbc, int projectDBC, double* g, cudaStream_t st);
 
 } // namespace ipcgpu

@@ -71,6 +71,16 @@ SIGNATURES = {
     "ipcgpu_ccd_stats": (C.c_int, [_ctxp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "ipcgpu_ccd_stats_ex": (C.c_int, [_ctxp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "ipcgpu_ccd_stats_timing": (C.c_int, [_ctxp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "ipcgpu_set_prev_state": (C.c_int, [_ctxp, _dp]),
+    "ipcgpu_friction_lag": (C.c_int, [_ctxp, C.c_double, C.c_double, _ip]),
+    "ipcgpu_get_friction_data": (C.c_int, [_ctxp, _ip, _ip, _dp, _dp, _dp]),
+    "ipcgpu_set_friction_data": (C.c_int, [_ctxp, C.c_int, _ip, _dp, _dp, _dp]),
+    "ipcgpu_friction_energy": (C.c_int, [_ctxp, C.c_double, C.c_double, _dp]),
+    "ipcgpu_friction_gradient": (C.c_int, [_ctxp, C.c_double, C.c_double, _dp]),
+    "ipcgpu_friction_hessian": (C.c_int, [_ctxp, C.c_double, C.c_double, C.c_int, _dp]),
+    "ipcgpu_set_xtilde": (C.c_int, [_ctxp, _dp]),
+    "ipcgpu_inertia_energy": (C.c_int, [_ctxp, _dp]),
+    "ipcgpu_inertia_gradient": (C.c_int, [_ctxp, C.c_int, _dp]),
     "ipcgpu_csr_set_zero": (C.c_int, [_ctxp]),
     "ipcgpu_solve_pcg": (C.c_int, [_ctxp, _dp, C.c_double, C.c_int, _dp, C.c_int, _ip, _dp]),
     "ipcgpu_allreduce_grad_hess": (C.c_int, [_ctxp, C.c_int, C.c_int]),
@@ -93,7 +103,7 @@ class Iteration(C.Structure):
     _fields_ = [("energy_elastic", C.c_double), ("energy_barrier", C.c_double), ("alpha_inversion", C.c_double), ("alpha_partial_ccd", C.c_double),
                 ("alpha_swept_grid", C.c_double), ("alpha_full_ccd", C.c_double), ("alpha", C.c_double), ("n_active", C.c_int), ("n_mollified", C.c_int),
                 ("n_candidates", C.c_int), ("status", C.c_int), ("n_full_ccd_candidates", C.c_uint64), ("ti_warnings", C.c_uint64),
-                ("n_inverted_tets", C.c_int), ("n_intersected_triangles", C.c_int)]
+                ("n_inverted_tets", C.c_int), ("n_intersected_triangles", C.c_int), ("energy_friction", C.c_double), ("energy_inertia", C.c_double)]
 
 
 class IpcGpuError(RuntimeError):
@@ -283,6 +293,52 @@ class Context:
 
     def download_range_into(self, which, offset, out):
         self._ck(self.lib.ipcgpu_download_range(self.h, which, int(offset), int(out.size), _d(out)))
+
+    # ---- friction / inertia -------------------------------------------------------------------
+    def set_prev_state(self, V_prev_soa=None):
+        self._ck(self.lib.ipcgpu_set_prev_state(self.h, _d(f64(V_prev_soa).ravel()) if V_prev_soa is not None else None))
+
+    def friction_lag(self, dHat, kappa, want=True):
+        n = C.c_int()
+        self._ck(self.lib.ipcgpu_friction_lag(self.h, dHat, kappa, C.byref(n) if want else None))
+        return n.value if want else None
+
+    def get_friction_data(self):
+        n = C.c_int()
+        self._ck(self.lib.ipcgpu_get_friction_data(self.h, C.byref(n), None, None, None, None))
+        k = max(n.value, 1)
+        mm, lam, co, ba = np.empty((k, 4), np.int32), np.empty(k), np.empty((k, 2)), np.empty((k, 6))
+        self._ck(self.lib.ipcgpu_get_friction_data(self.h, C.byref(n), _i(mm), _d(lam), _d(co), _d(ba)))
+        return mm[:n.value], lam[:n.value], co[:n.value], ba[:n.value]
+
+    def set_friction_data(self, mm, lam, co, ba):
+        mm, lam, co, ba = i32(mm), f64(lam), f64(co), f64(ba)
+        self._ck(self.lib.ipcgpu_set_friction_data(self.h, len(mm), _i(mm), _d(lam), _d(co), _d(ba)))
+
+    def friction_energy(self, eps2, coef, want=True):
+        E = C.c_double()
+        self._ck(self.lib.ipcgpu_friction_energy(self.h, eps2, coef, C.byref(E) if want else None))
+        return E.value if want else None
+
+    def friction_gradient(self, eps2, coef, g_inout=None):
+        self._ck(self.lib.ipcgpu_friction_gradient(self.h, eps2, coef, _d(g_inout)))
+        return g_inout
+
+    def friction_hessian(self, eps2, coef, projectDBC=1, a_inout=None):
+        self._ck(self.lib.ipcgpu_friction_hessian(self.h, eps2, coef, projectDBC, _d(a_inout)))
+        return a_inout
+
+    def set_xtilde(self, xtilde_soa):
+        self._ck(self.lib.ipcgpu_set_xtilde(self.h, _d(f64(xtilde_soa).ravel())))
+
+    def inertia_energy(self, want=True):
+        E = C.c_double()
+        self._ck(self.lib.ipcgpu_inertia_energy(self.h, C.byref(E) if want else None))
+        return E.value if want else None
+
+    def inertia_gradient(self, projectDBC=1, g_inout=None):
+        self._ck(self.lib.ipcgpu_inertia_gradient(self.h, projectDBC, _d(g_inout)))
+        return g_inout
 
     # ---- contact ------------------------------------------------------------------------------
     def set_surface(self, SVI, SFEdges, SF_soa, vCoDim=None):

@@ -18,6 +18,15 @@ void touch(IPC::IpcGpuScene& s, const IPC::Mesh<3>& m, IPC::LinSysSolver<Eigen::
     H::augmentParaEEGradient(m, b, c, v, 1e-6, 1e8);
     H::augmentIPHessian(m, a, sol, 1e-6, 1e8, true);
     H::augmentParaEEHessian(m, b, c, sol, 1e-6, 1e8, true);
+    // friction (SelfCollisionHandler.hpp:182-208; Optimizer.cpp:1594, 3371, 3505, 3699)
+    std::vector<Eigen::Vector2d> co;
+    std::vector<Eigen::Matrix<double, 3, 2>> ba;
+    Eigen::MatrixXd Vt;
+    H::computeDistCoordAndTanBasis(m, a, co, ba);
+    H::computeDistCoordAndTanBasis(m, a, co, ba, 1e-6, 1e8, &v);
+    H::computeFrictionEnergy(m.V, Vt, a, v, co, ba, x, 1e-9, 0.3);
+    H::augmentFrictionGradient(m.V, Vt, a, v, co, ba, v, 1e-9, 0.3);
+    H::augmentFrictionHessian(m, Vt, a, v, co, ba, sol, 1e-9, 0.3, true);
     (void)H::checkEdgeTriIntersectionIfAny(m, sh);
     (void)IPC::gpuCheckInversion(s);
     H::largestFeasibleStepSize_TightInclusion(m, sh, v, 1e-6, d, d, x);
