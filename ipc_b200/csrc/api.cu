@@ -201,6 +201,32 @@ static int build_maps(ipcgpu_ctx* ctx)
         csrc[i] = ks[i].src;
     }
     cptr.push_back((int)ks.size());
+    {
+        // Slot order = work order of k_assemble_csr (9 threads per slot, a warp covers ~3.5 slots and runs as long as its longest
+        // contribution list).  In key order every 7th slot is a diagonal block with ~23 contributions against ~5 for an off-diagonal
+        // one, so half of the warps idled most lanes for 20 iterations.  Off-diagonal slots first, then the diagonal ones (key order
+        // inside each group keeps the CSR writes local): warps see uniform list lengths.
+        const size_t nS = sv.size();
+        std::vector<int> order;
+        order.reserve(nS);
+        for (size_t i = 0; i < nS; ++i)
+            if (sv[i] != su[i]) order.push_back((int)i);
+        for (size_t i = 0; i < nS; ++i)
+            if (sv[i] == su[i]) order.push_back((int)i);
+        std::vector<int> sv2(nS), su2(nS), cptr2;
+        std::vector<unsigned> csrc2(csrc.size());
+        cptr2.reserve(nS + 1);
+        size_t pos = 0;
+        for (size_t k = 0; k < nS; ++k) {
+            const int i = order[k];
+            sv2[k] = sv[i];
+            su2[k] = su[i];
+            cptr2.push_back((int)pos);
+            for (int c = cptr[i]; c < cptr[i + 1]; ++c) csrc2[pos++] = csrc[c];
+        }
+        cptr2.push_back((int)pos);
+        sv.swap(sv2); su.swap(su2); cptr.swap(cptr2); csrc.swap(csrc2);
+    }
     ctx->nSlots = (int)sv.size();
     if (sv.empty()) { sv.push_back(0); su.push_back(0); } // keep the uploads non-empty
     bool ok = ctx->slot_v.upload(sv.data(), sv.size(), ctx->stream) && ctx->slot_u.upload(su.data(), su.size(), ctx->stream)
@@ -298,13 +324,24 @@ int ipcgpu_create(int device, ipcgpu_ctx** out)
     ctx->device = device;
     void* hi = nullptr;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess || cudaMallocHost(&ctx->h_scalar, 512) != cudaSuccess
-        || cudaMallocHost(&hi, sizeof(IterState)) != cudaSuccess || !ctx->flag.reserve(4) || !ctx->scalar_out.reserve(8) || !ctx->iter.reserve(1)
+        || cudaMallocHost(&hi, sizeof(IterState)) != cudaSuccess || !ctx->flag.reserve(4) || !ctx->scalar_out.reserve(32) || !ctx->iter.reserve(1)
         || cudaMemsetAsync(ctx->iter.p, 0, sizeof(IterState), ctx->stream) != cudaSuccess) {
         delete ctx;
         return IPCGPU_ERR_CUDA;
     }
     ctx->h_iter = static_cast<IterState*>(hi);
     std::memset(ctx->h_iter, 0, sizeof(IterState));
+    {   // optional side stream for the pair-Hessian build + projection (IPCGPU_BARRIER_OVERLAP=0 keeps everything on one stream)
+        const char* e = std::getenv("IPCGPU_BARRIER_OVERLAP");
+        if (!(e && std::atoi(e) == 0)) {
+            if (cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_inputs, cudaEventDisableTiming) != cudaSuccess
+                || cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess
+                || cudaEventCreateWithFlags(&ctx->ev_scatter, cudaEventDisableTiming) != cudaSuccess) {
+                if (ctx->side) cudaStreamDestroy(ctx->side);
+                ctx->side = nullptr; // fall back to the single-stream order
+            }
+        }
+    }
     step_set(ctx->iter.p, 1.0, ctx->stream);
     *out = ctx;
     return IPCGPU_OK;
@@ -314,7 +351,12 @@ void ipcgpu_destroy(ipcgpu_ctx* ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->side) cudaStreamSynchronize(ctx->side);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->ev_inputs) cudaEventDestroy(ctx->ev_inputs);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->ev_scatter) cudaEventDestroy(ctx->ev_scatter);
+    if (ctx->side) cudaStreamDestroy(ctx->side);
     for (auto& v : ctx->prof)
         for (auto& pr : v) {
             cudaEventDestroy(pr.first);
@@ -448,6 +490,7 @@ int ipcgpu_set_state(ipcgpu_ctx* ctx, const double* V)
     REQUIRE(ctx->nV > 0, IPCGPU_ERR_STATE, "ipcgpu_set_mesh first");
     CK(cudaSetDevice(ctx->device));
     if (V) CK(cudaMemcpyAsync(ctx->V.p, V, (size_t)3 * ctx->nV * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->mark_inputs();
     return IPCGPU_OK;
 }
 
@@ -497,6 +540,7 @@ int ipcgpu_step_forward(ipcgpu_ctx* ctx, const double* p, double alpha)
     step_forward(ctx->nV, ctx->Vsaved.p, ctx->dir.p, alpha, ctx->V.p, ctx->stream);
     ++ctx->launches;
     CK(cudaGetLastError());
+    ctx->mark_inputs();
     return IPCGPU_OK;
 }
 
@@ -835,6 +879,7 @@ int ipcgpu_constraint_set(ipcgpu_ctx* ctx, double dHat, int getPTEE, int* nC, in
         w.lists_global = true;
         CK(cudaGetLastError());
     }
+    ctx->mark_inputs();
     return rc;
 }
 
@@ -898,6 +943,7 @@ int ipcgpu_set_constraint_set(ipcgpu_ctx* ctx, int nC, const int* mm, int nP, co
     w.want_cand = nK > 0;
     ctx->lists_local = false; // uploaded sets are the global ones
     w.lists_global = false;
+    ctx->mark_inputs();
     return IPCGPU_OK;
 }
 
@@ -1063,7 +1109,19 @@ int ipcgpu_barrier_hessian(ipcgpu_ctx* ctx, double dHat, double kappa, int proje
     if (a_inout && (rc = upload_values(ctx, a_inout))) return rc;
     ContactWork& w = ctx->cw;
     cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_BARRIER);
-    barrier_hessian(barrier_args(ctx, dHat, kappa, projectDBC), ctx->a.p, ctx->iter.p->flags, w.bHraw.p, w.brows.p, w.bpsd.p, w.counters.p + 12, w.cap, ctx->stream);
+    const BarrierArgs bp = barrier_args(ctx, dHat, kappa, projectDBC);
+    if (ctx->side && ctx->inputs_marked) {
+        // build + projection on the side stream, ordered after the last change of their inputs (positions, contact sets) -- i.e. next to
+        // whatever the main stream has queued since (the elastic assembly); the scatter joins the main stream, after the elastic writes
+        CK(cudaStreamWaitEvent(ctx->side, ctx->ev_inputs, 0));
+        if (ctx->scatter_marked) CK(cudaStreamWaitEvent(ctx->side, ctx->ev_scatter, 0)); // back-to-back calls: the last scatter still reads the buffers
+        barrier_hessian_build_project(bp, ctx->iter.p->flags, w.bHraw.p, w.brows.p, w.bpsd.p, w.counters.p + 12, w.cap, ctx->side);
+        CK(cudaEventRecord(ctx->ev_join, ctx->side));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    }
+    else barrier_hessian_build_project(bp, ctx->iter.p->flags, w.bHraw.p, w.brows.p, w.bpsd.p, w.counters.p + 12, w.cap, ctx->stream);
+    barrier_hessian_scatter(bp, ctx->a.p, ctx->iter.p->flags, w.bHraw.p, w.brows.p, w.bpsd.p, w.counters.p + 12, w.cap, ctx->stream);
+    if (ctx->side && ctx->ev_scatter) ctx->scatter_marked = (cudaEventRecord(ctx->ev_scatter, ctx->stream) == cudaSuccess);
     ctx->prof_end(pe);
     ctx->launches += 3;
     CK(cudaGetLastError());
@@ -1434,20 +1492,20 @@ int ipcgpu_fetch_iteration(ipcgpu_ctx* ctx, ipcgpu_iteration* out)
     REQUIRE(out != nullptr, IPCGPU_ERR_ARG, "null output");
     CK(cudaSetDevice(ctx->device));
     if (ctx->nranks > 1) {
-        // complete the deferred scalars across ranks: locally summed energies, and the error flags (max) so that every rank returns
-        // the same status
-        cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_ALLREDUCE);
+        // complete the deferred scalars across ranks in ONE collective: locally summed energies, the error flags (so that every rank
+        // returns the same status) and the safeguard counts (round 2, first half: up to six separate NCCL calls here)
+        unsigned mask = 0;
         for (int s = 0; s < 4; ++s)
-            if (ctx->energy_local[s]) {
-                int r = g_nccl.AllReduce(&ctx->iter.p->energy[s], &ctx->iter.p->energy[s], 1, kNcclFloat64, kNcclSum, ctx->nccl_comm, ctx->stream);
-                REQUIRE(r == 0, IPCGPU_ERR_NCCL, "ncclAllReduce(energy) failed");
-                ctx->energy_local[s] = false;
-            }
-        int r = g_nccl.AllReduce(ctx->iter.p->flags, ctx->iter.p->flags, 8, kNcclInt32, kNcclMax, ctx->nccl_comm, ctx->stream);
+            if (ctx->energy_local[s]) mask |= 1u << s;
+        if (ctx->checks_local) mask |= 1u << 4;
+        cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_ALLREDUCE);
+        pack_scalars(ctx->iter.p, mask, ctx->scalar_out.p + 16, ctx->stream);
+        int r = g_nccl.AllReduce(ctx->scalar_out.p + 16, ctx->scalar_out.p + 16, 14, kNcclFloat64, kNcclSum, ctx->nccl_comm, ctx->stream);
+        unpack_scalars(ctx->iter.p, mask, ctx->scalar_out.p + 16, ctx->stream);
         ctx->prof_end(pe);
-        REQUIRE(r == 0, IPCGPU_ERR_NCCL, "ncclAllReduce(status flags) failed");
-        int rcc = reduce_checks(ctx);
-        if (rcc) return rcc;
+        ctx->launches += 2;
+        REQUIRE(r == 0, IPCGPU_ERR_NCCL, "ncclAllReduce(iteration scalars) failed");
+        for (int s = 0; s < 4; ++s) ctx->energy_local[s] = false;
     }
     ctx->checks_local = false;
     int rc = ccd_read_back(ctx, nullptr);

@@ -595,11 +595,14 @@ void barrier_gradient(const BarrierArgs& p, double* g, cudaStream_t st)
 void evaluate_constraints(const BarrierArgs& p, double* val, cudaStream_t st) { k_evaluate_constraints<<<kSMs * 2, 256, 0, st>>>(p, val); }
 void constraint_jacobian_t(const BarrierArgs& p, const double* input, double coef, double* g, cudaStream_t st) { k_constraint_jacobian_t<<<kSMs * 4, 128, 0, st>>>(p, input, coef, g); }
 void para_gradient(const BarrierArgs& p, double* g, cudaStream_t st) { k_para_gradient<<<kSMs, 128, 0, st>>>(p, g); }
-void barrier_hessian(const BarrierArgs& p, double* a, int* flags, double* Hraw, int* rows, int* psd, int* n_owned, int capacity, cudaStream_t st)
+void barrier_hessian_build_project(const BarrierArgs& p, int* flags, double* Hraw, int* rows, int* psd, int* n_owned, int capacity, cudaStream_t st)
 {
     cudaMemsetAsync(n_owned, 0, sizeof(int), st);
     k_barrier_hessian_build<<<kSMs * 8, 64, 0, st>>>(p, Hraw, rows, n_owned, capacity, flags);
     k_barrier_hessian_project<<<kSMs * 4, 32 * kProjWarps, 0, st>>>(n_owned, capacity, Hraw, psd);
+}
+void barrier_hessian_scatter(const BarrierArgs& p, double* a, int* flags, const double* Hraw, const int* rows, const int* psd, const int* n_owned, int capacity, cudaStream_t st)
+{
     k_barrier_hessian_scatter<<<kSMs * 4, 32 * kScatWarps, 0, st>>>(p, n_owned, capacity, Hraw, rows, psd, a, flags + FLAG_PATTERN);
 }
 

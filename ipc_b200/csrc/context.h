@@ -101,6 +101,16 @@ struct CcdWork {
 struct ipcgpu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    // side stream: the build + projection of the pair Hessians (latency-bound, a fraction of one wave) run next to the elastic assembly;
+    // ev_inputs marks, on the main stream, the last point at which their inputs (positions, contact sets) changed
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_inputs = nullptr, ev_join = nullptr, ev_scatter = nullptr; // (ev_scatter: the previous scatter has read the pair Hessians)
+    bool scatter_marked = false;
+    bool inputs_marked = false;
+    void mark_inputs()
+    {
+        if (ev_inputs) inputs_marked = (cudaEventRecord(ev_inputs, stream) == cudaSuccess);
+    }
     std::string err;
     uint64_t launches = 0;
 

@@ -468,6 +468,7 @@ __global__ void __launch_bounds__(256) k_gather_gradient(int nV, const int* __re
 // one thread per block-slot (vertex pair v<=u of the mesh topology); contributions are summed in
 // ascending tet order (the reference's vFLoc order), then written to the three CSR rows.
 // ---------------------------------------------------------------------------------------------
+template <int UNROLL>
 __global__ void __launch_bounds__(288) k_assemble_csr(int nSlots, const int* __restrict__ slot_v, const int* __restrict__ slot_u,
     const int* __restrict__ slot_off /* 3 per slot */, const int* __restrict__ con_ptr, const unsigned* __restrict__ con_src,
     const double* __restrict__ hblk, const uint8_t* __restrict__ dbc, int projectDBC, const double* __restrict__ mass,
@@ -487,7 +488,9 @@ __global__ void __launch_bounds__(288) k_assemble_csr(int nSlots, const int* __r
     double h = 0.0;
     if (!dropped) {
         const int b = con_ptr[sIdx], e = con_ptr[sIdx + 1];
-        for (int k = b; k < e; ++k) h += hblk[__ldg(con_src + k) + q]; // (an explicit 8-deep load batch was measured slower: 0.41 vs 0.34 ms)
+        // (round 1: an explicit 8-deep load batch was slower -- but slot lists were then mixed 5- and 23-long inside a warp)
+#pragma unroll UNROLL
+        for (int k = b; k < e; ++k) h += hblk[__ldg(con_src + k) + q];
     }
     int r, c;
     if (diag) { r = (q < 3) ? 0 : (q < 5 ? 1 : 2); c = (q < 3) ? q : (q < 5 ? q - 3 : 0); }
@@ -761,7 +764,10 @@ void assemble_csr(int nSlots, const int* slot_v, const int* slot_u, const int* s
     const double* hblk, const uint8_t* dbc, int projectDBC, const double* mass, int accumulate, double* a, cudaStream_t st)
 {
     if (nSlots <= 0) return;
-    k_assemble_csr<<<(int)(((long long)nSlots * 9 + 287) / 288), 288, 0, st>>>(nSlots, slot_v, slot_u, slot_off, con_ptr, con_src, hblk, dbc, projectDBC, mass, accumulate, a);
+    static const int unroll = [] { const char* e = std::getenv("IPCGPU_ASM_UNROLL"); return e ? std::atoi(e) : 4; }();
+    const int nb = (int)(((long long)nSlots * 9 + 287) / 288);
+    if (unroll >= 4) k_assemble_csr<4><<<nb, 288, 0, st>>>(nSlots, slot_v, slot_u, slot_off, con_ptr, con_src, hblk, dbc, projectDBC, mass, accumulate, a);
+    else k_assemble_csr<1><<<nb, 288, 0, st>>>(nSlots, slot_v, slot_u, slot_off, con_ptr, con_src, hblk, dbc, projectDBC, mass, accumulate, a);
 }
 void diag_mass_dbc(int nV, const int* ia, int base, const uint8_t* dbc, int projectDBC, const double* mass, double* a, cudaStream_t st)
 {
@@ -787,5 +793,25 @@ void inversion_step(const ElasticArgs& p, const double* dir, double slack, doubl
 void inversion_apply(IterState* st_dev, int nT, cudaStream_t st) { k_inversion_apply<<<1, 32, 0, st>>>(st_dev, nT); }
 void step_set(IterState* st_dev, double alpha, cudaStream_t st) { k_step_set<<<1, 32, 0, st>>>(st_dev, alpha); }
 void energy_store(IterState* st_dev, int slot, const double* src, cudaStream_t st) { k_energy_store<<<1, 32, 0, st>>>(st_dev, slot, src); }
+
+// Deferred cross-rank scalars of one iteration in ONE collective: the energies that are still local sums, the error flags and the
+// safeguard counts are packed into 14 doubles, sum-all-reduced, and unpacked (a flag is raised iff any rank raised it; integer counts
+// are exact in a double).  local_mask bit s: energy s is a local partial sum; bit 4: the safeguard counts are local.
+__global__ void k_pack_scalars(const IterState* __restrict__ st, unsigned local_mask, double* __restrict__ buf)
+{
+    const int i = threadIdx.x;
+    if (i < 4) buf[i] = ((local_mask >> i) & 1u) ? st->energy[i] : 0.0;
+    else if (i < 12) buf[i] = (double)st->flags[i - 4];
+    else if (i < 14) buf[i] = ((local_mask >> 4) & 1u) ? (double)st->checks[i - 12] : 0.0;
+}
+__global__ void k_unpack_scalars(IterState* __restrict__ st, unsigned local_mask, const double* __restrict__ buf)
+{
+    const int i = threadIdx.x;
+    if (i < 4) { if ((local_mask >> i) & 1u) st->energy[i] = buf[i]; }
+    else if (i < 12) st->flags[i - 4] = (int)fmin(buf[i], 2147483647.0);
+    else if (i < 14) { if ((local_mask >> 4) & 1u) st->checks[i - 12] = (int)buf[i]; }
+}
+void pack_scalars(const IterState* st_dev, unsigned local_mask, double* buf, cudaStream_t st) { k_pack_scalars<<<1, 32, 0, st>>>(st_dev, local_mask, buf); }
+void unpack_scalars(IterState* st_dev, unsigned local_mask, const double* buf, cudaStream_t st) { k_unpack_scalars<<<1, 32, 0, st>>>(st_dev, local_mask, buf); }
 
 } // namespace ipcgpu

@@ -57,6 +57,8 @@ void inversion_step(const ElasticArgs& p, const double* dir, double slack, doubl
 void inversion_apply(IterState* st_dev, int nT, cudaStream_t st);          // Energy.cpp:576-579 on the device-resident step
 void step_set(IterState* st_dev, double alpha, cudaStream_t st);           // step_ord = alpha
 void energy_store(IterState* st_dev, int slot, const double* src, cudaStream_t st);
+void pack_scalars(const IterState* st_dev, unsigned local_mask, double* buf, cudaStream_t st);   // deferred cross-rank scalars -> 14 doubles
+void unpack_scalars(IterState* st_dev, unsigned local_mask, const double* buf, cudaStream_t st);
 
 
 // ---- contact ------------------------------------------------------------------------------------------
@@ -97,7 +99,8 @@ void evaluate_constraints(const BarrierArgs& p, double* val, cudaStream_t st);
 void constraint_jacobian_t(const BarrierArgs& p, const double* input, double coef, double* g, cudaStream_t st);
 void para_gradient(const BarrierArgs& p, double* g, cudaStream_t st);
 // Hraw: 144 doubles per owned pair; rows: 4 vertex ids per owned pair; psd: makePD "unchanged" flag per owned pair; n_owned: device counter
-void barrier_hessian(const BarrierArgs& p, double* a, int* err, double* Hraw, int* rows, int* psd, int* n_owned, int capacity, cudaStream_t st);
+void barrier_hessian_build_project(const BarrierArgs& p, int* flags, double* Hraw, int* rows, int* psd, int* n_owned, int capacity, cudaStream_t st);
+void barrier_hessian_scatter(const BarrierArgs& p, double* a, int* flags, const double* Hraw, const int* rows, const int* psd, const int* n_owned, int capacity, cudaStream_t st);
 // friction.cu -- lagged friction of the self-contact pairs (SelfCollisionHandler.cpp:2481-2987)
 struct FrictionArgs {
     int nV;
