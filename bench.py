@@ -199,6 +199,7 @@ def main():
     ap.add_argument("--scene", default="c5", choices=["c5", "pile"], help="c5 = 146 x sphere1K.msh FCC pile (BASELINE C5 as specified), pile = round-1 synthetic column pile")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity check against the oracle (rank 0, before the warm-up)")
+    ap.add_argument("--eager", action="store_true", help="enqueue every launch of the timed steps one by one instead of replaying the captured CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -281,7 +282,10 @@ def main():
     def step_e2e():
         ctx.set_state(hV.array)        # H2D: positions
         ctx.set_search_dir(hp.array)   # H2D: search direction
-        enqueue_iteration()
+        if stats.get("graph") is not None:
+            ctx.graph_launch(stats["graph"])
+        else:
+            enqueue_iteration()
         it = ctx.fetch_iteration()
         ctx.download_into(L.BUF_GRADIENT, hg.array)                      # D2H: gradient
         ctx.download_range_into(L.BUF_CSR_VALUES, own0, ha.array[own0:own1])  # D2H: the CSR values of the rows this rank owns
@@ -323,15 +327,28 @@ def main():
             assert ok, parity
 
     # ---- device-resident timing --------------------------------------------------------------------
+    # The iteration is captured ONCE into a CUDA graph (every argument that changes between iterations lives in device memory) and
+    # replayed: one cudaGraphLaunch + one fetch per step.  --eager times the same calls enqueued one by one instead.
     for _ in range(args.warmup):
         step_device()
+    graph = None
+    if not args.eager:
+        ctx.capture_begin()
+        enqueue_iteration()
+        graph = ctx.capture_end()
+
+        def step_device():  # noqa: F811 -- the replayed form of the function above
+            ctx.graph_launch(graph)
+            stats["it"] = ctx.fetch_iteration()
+
+        for _ in range(args.warmup):
+            step_device()
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
         time.sleep(0.5)
     n0 = ctx.launch_count()
-    ctx.profile(1)
     barrier()
     ctx.timer_start()
     for _ in range(args.steps):
@@ -339,13 +356,25 @@ def main():
     ms_total = ctx.timer_stop()
     barrier()
     launches = ctx.launch_count() - n0
-    prof = ctx.profile_read()
-    ctx.profile(0)
     ms_step = ms_total / args.steps
     it = stats["it"]
     ccd_stats = ctx.ccd_stats() + ctx.ccd_stats_ex() + ctx.ccd_stats_timing()
 
+    # ---- per-stage table (CUDA-event pairs around every stage): a separate, eagerly enqueued pass of the same K steps -- event records
+    # cannot live inside a replayed graph.  The rooflines below take their kernel times from this pass (same kernels, same inputs).
+    ctx.profile(1)
+    barrier()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        enqueue_iteration()
+        ctx.fetch_iteration()
+    eager_profiled_ms = ctx.timer_stop() / args.steps
+    barrier()
+    prof = ctx.profile_read()
+    ctx.profile(0)
+
     # ---- end-to-end timing (host buffers through the C ABI) -----------------------------------------
+    stats["graph"] = graph
     for _ in range(2):
         step_e2e()
     barrier()
@@ -396,8 +425,11 @@ def main():
                        "energy_elastic_barrier": [it.energy_elastic, it.energy_barrier],
                        "full_ccd_candidates_survivors_warnings_deferred_boxesThreadPass_boxesWarpPass_longestPairCycles_totalCycles": list(ccd_stats),
                        "l2": "working set (78 doubles/tet = %.0f MB + CSR %.0f MB) exceeds the 126 MB L2" % (m.nT * 624 / 1e6, nnz * 8 / 1e6),
-                       "mode": "device-resident iteration: every stage enqueued with NULL outputs, one ipcgpu_fetch_iteration per step; "
-                               "canonical_order=0, contact_partition=1",
+                       "mode": ("device-resident iteration: every stage in its NULL-output form, one ipcgpu_fetch_iteration per step; canonical_order=0, "
+                                "contact_partition=1; " + ("the iteration is captured once into a CUDA graph and replayed (one cudaGraphLaunch per step)"
+                                                           if graph is not None else "launches enqueued one by one (--eager)")),
+                       "eager_profiled_ms_per_step": eager_profiled_ms,
+                       "stage_ms_source": "a separate eagerly enqueued pass of the same steps with CUDA-event pairs around every stage (events cannot be recorded inside a replayed graph)",
                        "partition": (f"{world} rank(s): tets block-partitioned (energy, inversion); gradient/Hessian by row owner (rank 0 assembles {local_tets} tets, "
                                      f"CSR values [{own0},{own1}) of {nnz}); queries of both broad phases partitioned; NCCL: allgather of the pair lists, "
                                      "sum-allreduce of the gradient, min-allreduce of each step bound; no Hessian reduction")},

@@ -102,6 +102,21 @@ int ipcgpu_fetch_iteration(ipcgpu_ctx* ctx, ipcgpu_iteration* out);
 /* start value of the device-resident step bound (Optimizer.cpp:1884: alpha = 1) */
 int ipcgpu_step_bound_set(ipcgpu_ctx* ctx, double alpha);
 
+/* ---- CUDA graphs of device-resident call sequences ---------------------------------------------------------------------
+ * Everything between ipcgpu_capture_begin and ipcgpu_capture_end is recorded instead of executed (every call in between must be in its
+ * NULL-output form: nothing may synchronise or copy to the host) and replayed by ipcgpu_graph_launch as ONE launch.  What a graph bakes
+ * in: the host scalars handed to the calls (dHat, kappa, coef, tolerances, Tight-Inclusion errors, voxel size) and the device buffers.
+ * What it does not: positions (ipcgpu_set_state), search direction (ipcgpu_set_search_dir), previous state / xTilta, the contact sets,
+ * list sizes and step bounds -- they live in device memory and are read at replay time.  So one capture serves every Newton iteration
+ * of a solve; capture again after ipcgpu_set_mesh / _set_surface / _set_csr / _set_*_capacity / _comm_init / _set_canonical_order /
+ * _set_contact_partition (older graphs are refused with IPCGPU_ERR_STATE) or when dHat / kappa change.  Run the sequence once eagerly
+ * before capturing it (lazy allocations).  Collective: with several ranks every rank captures and launches the same sequence.
+ * ipcgpu_fetch_iteration stays outside the graph. */
+int ipcgpu_capture_begin(ipcgpu_ctx* ctx);
+int ipcgpu_capture_end(ipcgpu_ctx* ctx, int* graph_id);
+int ipcgpu_graph_launch(ipcgpu_ctx* ctx, int graph_id);
+int ipcgpu_graph_destroy(ipcgpu_ctx* ctx, int graph_id);
+
 /* ---- scene (once per scene; replaces what Mesh<3> precomputes, Mesh.cpp:415-527, :661-671) ------- */
 int ipcgpu_set_mesh(ipcgpu_ctx* ctx, int nV, int nT,
     const double* V_rest_soa, const int* tets_soa,

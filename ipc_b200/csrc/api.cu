@@ -331,9 +331,10 @@ int ipcgpu_create(int device, ipcgpu_ctx** out)
     }
     ctx->h_iter = static_cast<IterState*>(hi);
     std::memset(ctx->h_iter, 0, sizeof(IterState));
-    {   // optional side stream for the pair-Hessian build + projection (IPCGPU_BARRIER_OVERLAP=0 keeps everything on one stream)
+    {   // optional side stream for the pair-Hessian build + projection (IPCGPU_BARRIER_OVERLAP=1; off by default: with eagerly enqueued
+        // launches the extra event calls cost more host time than the overlap wins -- measured 4.54 ms against 4.69 ms per iteration on C5)
         const char* e = std::getenv("IPCGPU_BARRIER_OVERLAP");
-        if (!(e && std::atoi(e) == 0)) {
+        if (e && std::atoi(e) == 1) {
             if (cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_inputs, cudaEventDisableTiming) != cudaSuccess
                 || cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess
                 || cudaEventCreateWithFlags(&ctx->ev_scatter, cudaEventDisableTiming) != cudaSuccess) {
@@ -353,6 +354,10 @@ void ipcgpu_destroy(ipcgpu_ctx* ctx)
     cudaSetDevice(ctx->device);
     if (ctx->side) cudaStreamSynchronize(ctx->side);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto& r : ctx->graphs) {
+        if (r.exec) cudaGraphExecDestroy(r.exec);
+        if (r.graph) cudaGraphDestroy(r.graph);
+    }
     if (ctx->ev_inputs) cudaEventDestroy(ctx->ev_inputs);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->ev_scatter) cudaEventDestroy(ctx->ev_scatter);
@@ -390,6 +395,7 @@ int ipcgpu_comm_unique_id(void* id128)
 
 int ipcgpu_comm_init(ipcgpu_ctx* ctx, int rank, int nranks, const void* id128)
 {
+    ++ctx->epoch; // graphs captured before this call are refused (buffers, partition or list order may change)
     REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, IPCGPU_ERR_ARG, "bad rank/nranks");
     CK(cudaSetDevice(ctx->device));
     ctx->rank = rank;
@@ -429,6 +435,7 @@ int ipcgpu_partition_info(ipcgpu_ctx* ctx, int* rank, int* nranks, int* tet_begi
 int ipcgpu_set_mesh(ipcgpu_ctx* ctx, int nV, int nT, const double* Vrest, const int* tets, const double* restTriInv, const double* vol,
     const double* mu, const double* lam, const double* mass, const uint8_t* dbc, int energy)
 {
+    ++ctx->epoch; // graphs captured before this call are refused (buffers, partition or list order may change)
     REQUIRE(nV > 0 && nT >= 0 && Vrest && tets && restTriInv && vol && mu && lam, IPCGPU_ERR_ARG, "ipcgpu_set_mesh: null or empty input");
     REQUIRE(energy == IPCGPU_NEOHOOKEAN || energy == IPCGPU_FIXED_COROT, IPCGPU_ERR_ARG, "unknown energy type");
     CK(cudaSetDevice(ctx->device));
@@ -465,6 +472,7 @@ int ipcgpu_set_mesh(ipcgpu_ctx* ctx, int nV, int nT, const double* Vrest, const 
 
 int ipcgpu_set_csr(ipcgpu_ctx* ctx, int n_rows, const int* ia, const int* ja, int index_base)
 {
+    ++ctx->epoch; // graphs captured before this call are refused (buffers, partition or list order may change)
     REQUIRE(n_rows > 0 && ia && ja && (index_base == 0 || index_base == 1), IPCGPU_ERR_ARG, "ipcgpu_set_csr: bad arguments");
     REQUIRE(ctx->nV > 0 && n_rows == 3 * ctx->nV, IPCGPU_ERR_ARG, "ipcgpu_set_csr: n_rows must be 3*nV of the mesh set before");
     CK(cudaSetDevice(ctx->device));
@@ -516,6 +524,11 @@ static int upload_dir(ipcgpu_ctx* ctx, const double* p)
             pSize += std::abs(p[3 * (size_t)v + 2]);
         }
         ctx->pSize = ctx->nSV > 0 ? pSize / (double)((long long)ctx->nSV * 3) : 0.0;
+        // the swept-grid kernel reads it from device memory, so that a captured graph stays valid when the direction changes
+        ALLOC(ctx->pSize_dev, 1);
+        double* hp = ctx->h_scalar + 32; // pinned staging slot of its own (the copy is asynchronous)
+        *hp = ctx->pSize;
+        CK(cudaMemcpyAsync(ctx->pSize_dev.p, hp, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         ctx->pSize_surface = ctx->surface_ready;
         ctx->dir_valid = true; // (no synchronisation: like every host input of the deferred mode, p must stay untouched until the next fetch)
     }
@@ -708,6 +721,7 @@ int ipcgpu_inversion_step(ipcgpu_ctx* ctx, const double* p, double slack, double
 // ---- contact ---------------------------------------------------------------------------------------------
 int ipcgpu_set_surface(ipcgpu_ctx* ctx, int nSV, const int* SVI, int nSE, const int* SE, int nSF, const int* SF, const int* vCoDim)
 {
+    ++ctx->epoch; // graphs captured before this call are refused (buffers, partition or list order may change)
     REQUIRE(ctx->nV > 0, IPCGPU_ERR_STATE, "ipcgpu_set_mesh first");
     REQUIRE(nSV >= 0 && nSE >= 0 && nSF >= 0 && (nSV == 0 || SVI) && (nSE == 0 || SE) && (nSF == 0 || SF), IPCGPU_ERR_ARG, "ipcgpu_set_surface: bad arguments");
     CK(cudaSetDevice(ctx->device));
@@ -731,6 +745,7 @@ int ipcgpu_set_surface(ipcgpu_ctx* ctx, int nSV, const int* SVI, int nSE, const 
 
 int ipcgpu_set_ccd_capacity(ipcgpu_ctx* ctx, uint64_t capacity)
 {
+    ++ctx->epoch; // graphs captured before this call are refused (buffers, partition or list order may change)
     REQUIRE(capacity > 0 && capacity < 0xffffffffull, IPCGPU_ERR_ARG, "capacity out of range");
     ctx->ccd_capacity = (size_t)capacity;
     if (ctx->surface_ready) return ccd_alloc(ctx);
@@ -852,6 +867,7 @@ int ipcgpu_ccd_stats_timing(ipcgpu_ctx* ctx, uint64_t* longest_pair_cycles, uint
 
 int ipcgpu_set_pair_capacity(ipcgpu_ctx* ctx, int capacity)
 {
+    ++ctx->epoch; // graphs captured before this call are refused (buffers, partition or list order may change)
     REQUIRE(capacity > 0, IPCGPU_ERR_ARG, "capacity must be positive");
     ctx->pair_capacity = capacity;
     if (ctx->surface_ready) return contact_alloc(ctx);
@@ -885,12 +901,14 @@ int ipcgpu_constraint_set(ipcgpu_ctx* ctx, double dHat, int getPTEE, int* nC, in
 
 int ipcgpu_set_canonical_order(ipcgpu_ctx* ctx, int enable)
 {
+    ++ctx->epoch; // graphs captured before this call are refused (buffers, partition or list order may change)
     ctx->canonical_order = enable != 0;
     return IPCGPU_OK;
 }
 
 int ipcgpu_set_contact_partition(ipcgpu_ctx* ctx, int enable)
 {
+    ++ctx->epoch; // graphs captured before this call are refused (buffers, partition or list order may change)
     ctx->partition_contact = enable != 0;
     return IPCGPU_OK;
 }
@@ -1383,6 +1401,111 @@ int ipcgpu_inertia_gradient(ipcgpu_ctx* ctx, int projectDBC, double* g_inout)
     return IPCGPU_OK;
 }
 
+// ---- CUDA graphs of device-resident call sequences ----------------------------------------------------------------------------
+// An iteration in the NULL-output form is ~65 launches whose arguments do not change while the scene, the pattern, dHat / kappa and
+// the tolerances stay the same: positions, search direction, list sizes and step bounds all live in device memory.  Enqueued one by
+// one the front of the iteration (grid builds: ~25 kernels of 3-15 us) is bound by the host's launch rate; captured once and
+// replayed, the whole sequence is one cudaGraphLaunch.
+static ipcgpu_ctx::HostState snapshot_host_state(const ipcgpu_ctx* ctx)
+{
+    ipcgpu_ctx::HostState h;
+    for (int s = 0; s < 4; ++s) h.energy_local[s] = ctx->energy_local[s];
+    h.checks_local = ctx->checks_local;
+    h.lists_local = ctx->lists_local;
+    h.lists_global = ctx->cw.lists_global;
+    h.want_cand = ctx->cw.want_cand;
+    h.swept_ready = ctx->ccd.swept_ready;
+    h.fr_ready = ctx->cw.fr_ready;
+    h.inputs_marked = false; // events recorded inside a capture cannot be waited on outside of it
+    h.scatter_marked = false;
+    h.nC = ctx->cw.nC; h.nP = ctx->cw.nP; h.nK = ctx->cw.nK; h.fr_host_n = ctx->cw.fr_host_n;
+    return h;
+}
+static void apply_host_state(ipcgpu_ctx* ctx, const ipcgpu_ctx::HostState& h)
+{
+    for (int s = 0; s < 4; ++s) ctx->energy_local[s] = h.energy_local[s];
+    ctx->checks_local = h.checks_local;
+    ctx->lists_local = h.lists_local;
+    ctx->cw.lists_global = h.lists_global;
+    ctx->cw.want_cand = h.want_cand;
+    ctx->ccd.swept_ready = h.swept_ready;
+    ctx->cw.fr_ready = h.fr_ready;
+    ctx->inputs_marked = h.inputs_marked;
+    ctx->scatter_marked = h.scatter_marked;
+    ctx->cw.nC = h.nC; ctx->cw.nP = h.nP; ctx->cw.nK = h.nK; ctx->cw.fr_host_n = h.fr_host_n;
+}
+
+int ipcgpu_capture_begin(ipcgpu_ctx* ctx)
+{
+    REQUIRE(!ctx->capturing, IPCGPU_ERR_STATE, "a capture is already in progress");
+    REQUIRE(!ctx->profiling, IPCGPU_ERR_STATE, "switch the stage timers off (ipcgpu_profile(ctx, 0)) before capturing");
+    CK(cudaSetDevice(ctx->device));
+    ctx->inputs_marked = false;  // the side-stream fork of the pair Hessians must hang on an event recorded INSIDE the capture
+    ctx->scatter_marked = false;
+    ctx->launches_at_capture = ctx->launches;
+    ctx->dirty_at_capture = ctx->a_all_dirty;
+    CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    ctx->capturing = true;
+    return IPCGPU_OK;
+}
+
+int ipcgpu_capture_end(ipcgpu_ctx* ctx, int* graph_id)
+{
+    REQUIRE(ctx->capturing, IPCGPU_ERR_STATE, "no capture in progress");
+    REQUIRE(graph_id != nullptr, IPCGPU_ERR_ARG, "null graph id");
+    ctx->capturing = false;
+    ipcgpu_ctx::GraphRec rec;
+    cudaError_t e = cudaStreamEndCapture(ctx->stream, &rec.graph);
+    if (e != cudaSuccess || rec.graph == nullptr) {
+        cudaGetLastError();
+        ctx->err = std::string("stream capture failed (a call inside the capture synchronised or copied to the host? use NULL outputs): ") + cudaGetErrorString(e);
+        return IPCGPU_ERR_CUDA;
+    }
+    e = cudaGraphInstantiate(&rec.exec, rec.graph, 0);
+    if (e != cudaSuccess) {
+        cudaGraphDestroy(rec.graph);
+        ctx->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e);
+        return IPCGPU_ERR_CUDA;
+    }
+    rec.launches = ctx->launches - ctx->launches_at_capture;
+    rec.epoch = ctx->epoch;
+    rec.dirty_at_begin = ctx->dirty_at_capture;
+    rec.hs = snapshot_host_state(ctx);
+    ctx->launches = ctx->launches_at_capture; // nothing ran yet
+    ctx->inputs_marked = false;
+    ctx->scatter_marked = false;
+    ctx->graphs.push_back(rec);
+    *graph_id = (int)ctx->graphs.size() - 1;
+    return IPCGPU_OK;
+}
+
+int ipcgpu_graph_launch(ipcgpu_ctx* ctx, int graph_id)
+{
+    REQUIRE(graph_id >= 0 && graph_id < (int)ctx->graphs.size() && ctx->graphs[graph_id].exec, IPCGPU_ERR_ARG, "unknown graph id");
+    REQUIRE(!ctx->capturing, IPCGPU_ERR_STATE, "a capture is in progress");
+    const ipcgpu_ctx::GraphRec& rec = ctx->graphs[graph_id];
+    REQUIRE(rec.epoch == ctx->epoch, IPCGPU_ERR_STATE, "the scene, pattern, partition or capacities changed since this graph was captured: capture it again");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->a_all_dirty && !rec.dirty_at_begin) // a cross-rank completion filled rows the captured clear does not cover
+        CK(cudaMemsetAsync(ctx->a.p, 0, (size_t)ctx->nnz * sizeof(double), ctx->stream));
+    CK(cudaGraphLaunch(rec.exec, ctx->stream));
+    ctx->a_all_dirty = false;
+    apply_host_state(ctx, rec.hs);
+    ctx->launches += rec.launches;
+    return IPCGPU_OK;
+}
+
+int ipcgpu_graph_destroy(ipcgpu_ctx* ctx, int graph_id)
+{
+    REQUIRE(graph_id >= 0 && graph_id < (int)ctx->graphs.size(), IPCGPU_ERR_ARG, "unknown graph id");
+    ipcgpu_ctx::GraphRec& rec = ctx->graphs[graph_id];
+    if (rec.exec) cudaGraphExecDestroy(rec.exec);
+    if (rec.graph) cudaGraphDestroy(rec.graph);
+    rec.exec = nullptr;
+    rec.graph = nullptr;
+    return IPCGPU_OK;
+}
+
 // ---- line-search safeguards -----------------------------------------------------------------------
 static int reduce_checks(ipcgpu_ctx* ctx)
 {
@@ -1543,6 +1666,7 @@ int ipcgpu_fetch_iteration(ipcgpu_ctx* ctx, ipcgpu_iteration* out)
 
 int ipcgpu_profile(ipcgpu_ctx* ctx, int enable)
 {
+    REQUIRE(!ctx->capturing, IPCGPU_ERR_STATE, "stage timers cannot be switched inside a capture");
     CK(cudaStreamSynchronize(ctx->stream));
     for (int s = 0; s < IPCGPU_STAGE_COUNT; ++s) {
         for (auto& pr : ctx->prof[s]) {

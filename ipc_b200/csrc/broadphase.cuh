@@ -192,7 +192,7 @@ struct PairOut {
     unsigned cap;
     int* overflow;
 };
-constexpr int kPairStageCap = 2048;     // pairs staged per CTA (16 KB)
+constexpr int kPairStageCap = 4096;     // pairs staged per CTA (32 KB)
 constexpr int kPairQueriesPerWarp = 8;  // queries handled by one warp of the pair-finding kernels
 struct PairStage {
     int2 buf[kPairStageCap];

@@ -82,9 +82,10 @@ __global__ void __launch_bounds__(256) k_swept_bounds(SurfArgs s, const double* 
 
 // SpatialHash.hpp:603-618 on the device-resident step: spanSize = alpha * mean|p| / h ; if (spanSize > 1) alpha /= spanSize.
 // (pSize is the reference's serial host sum over the surface vertices, computed when the search direction is uploaded.)
-__global__ void k_swept_alpha(IterState* st, double pSize, double h, unsigned long long* __restrict__ bounds)
+__global__ void k_swept_alpha(IterState* st, const double* __restrict__ pSize_ptr, double h, unsigned long long* __restrict__ bounds)
 {
     if (threadIdx.x != 0) return;
+    const double pSize = *pSize_ptr;
     double alpha = ord_to_dbl(st->step_ord);
     const double span = alpha * pSize / h;
     if (span > 1) alpha /= span;
@@ -1387,6 +1388,8 @@ SurfArgs surf_args(const ipcgpu_ctx* ctx); // constraint.cu
 SortedGrid tri_grid(const ipcgpu_ctx* ctx);
 SortedGrid edge_grid(const ipcgpu_ctx* ctx);
 int boxes_and_grid(ipcgpu_ctx* ctx, const double* dir, const double* alpha_ptr, double radius, const double* radius_ptr, bool with_vertex_boxes); // constraint.cu
+int pairs_mode();                                                                                                                                  // constraint.cu
+void cell_pairs_ee(const ipcgpu::Grid* gp, const ipcgpu::SortedGrid& eg, double radius_val, const double* radius_ptr, int first, int last, const ipcgpu::PairOut& out, cudaStream_t st);
 
 constexpr int kStage2WarpsPerCta = 4;
 constexpr int kStage2Ctas = 148 * 6; // persistent: 6 CTAs x 4 warps per SM
@@ -1522,7 +1525,7 @@ int ccd_build_swept(ipcgpu_ctx* ctx, double h)
         return IPCGPU_ERR_STATE;
     }
     cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_CCD_BROAD);
-    k_swept_alpha<<<1, 32, 0, st>>>(ist, ctx->pSize, h, w.bounds.p);
+    k_swept_alpha<<<1, 32, 0, st>>>(ist, ctx->pSize_dev.p, h, w.bounds.p);
     // bbox of V and of the displaced surface vertices (:627-628)
     k_swept_bounds<<<nblk(std::max(s.nV, s.nSV), 256), 256, 0, st>>>(s, ctx->dir.p, ist, w.bounds.p);
     k_refgrid_params<<<1, 32, 0, st>>>(ist, w.bounds.p, h);
@@ -1561,7 +1564,8 @@ int ccd_full(ipcgpu_ctx* ctx, double tol, const double* err_vf, const double* er
         ctx->launches += 2;
     }
     if (e1 > e0 && s.nSE > 1) {
-        k_ccd_pairs_ee<<<nblk(e1 - e0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(cw.grid.p, eg, cw.ebox.p, ist, s.nSF + e0, s.nSF + e1, pee); // edge entries sit behind the triangles
+        if (pairs_mode() == 0) k_ccd_pairs_ee<<<nblk(e1 - e0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(cw.grid.p, eg, cw.ebox.p, ist, s.nSF + e0, s.nSF + e1, pee); // edge entries sit behind the triangles
+        else cell_pairs_ee(cw.grid.p, eg, 0.0, &ist->radius, s.nSF + e0, s.nSF + e1, pee, st);
         k_ccd_filter_ee<<<kSMs * 8, 256, 0, st>>>(s, pee.pairs, pee.n, pee.cap, w.vmin.p, w.vmax.p, cw.ebox.p, out);
         ctx->launches += 2;
     }

@@ -230,6 +230,156 @@ __global__ void __launch_bounds__(256) k_pairs_ee(const Grid* __restrict__ gp, S
     pair_stage_flush(stage, out);
 }
 
+// ---- cell-centric edge-edge pair finding (round 2, second half) ------------------------------------------------------------------
+// The warp-per-query kernels above spend ~2 warp instructions per box test (flattened-index arithmetic, entry load, ballot/append per
+// 32 tests plus ~150 instructions of set-up per query) and are ISSUE-bound (542 K edge queries x ~450 instructions = 0.35 ms).  Here a
+// warp takes 32 CONSECUTIVE entries of the sorted edge grid as queries ("A"); consecutive entries share their cell, so the partner
+// entries ("B") of a whole run of queries are fetched once: a lane holds one B entry and tests it against every query of the run, whose
+// inflated quantised boxes sit in shared memory (one broadcast LDS.128 + LDS.64 and ~8 integer instructions per test, 16-bit SIMD min for
+// two axes at a time).  Hits are rare and appended lane by lane.  One-sided like the query kernels: a pair is reported from the entry with
+// the smaller sorted position, so only cells at or behind the run's own cell are visited.
+//   Which cells: a query registered in cell c (lower corner of its box) and inflated by `radius` covers cells c0'..c1' with
+//   c - 1 <= c0' <= c and c1' <= c0' + 1; its partners are registered in [c0' - 1, c1'] (broadphase.cuh).  The run uses the union over
+//   its queries, computed conservatively from the quantised boxes and clamped to the provable superset [c - 2, c + 1] per axis.
+struct alignas(16) AEntry {
+    unsigned L01, H01, lo2, hi2; // inflated quantised box: (lo0 | lo1 << 16), (hi0 | hi1 << 16), lo2, hi2
+    int pos, id, pad0, pad1;     // 32 bytes: two 128-bit shared-memory loads
+};
+constexpr int kCellPairWarps = 8;
+DEV void lane_push_pair(PairStage& st, const PairOut& o, int a, int b)
+{
+    const unsigned i = atomicAdd(&st.count, 1u);
+    if (i < (unsigned)kPairStageCap) st.buf[i] = make_int2(a, b);
+    else {
+        const unsigned gi = atomicAdd(o.n, 1u);
+        if (gi < o.cap) o.pairs[gi] = make_int2(a, b);
+        else atomicExch(o.overflow, 1);
+    }
+}
+__global__ void __launch_bounds__(32 * kCellPairWarps) k_cell_pairs_ee(const Grid* __restrict__ gp, SortedGrid eg, double radius_val, const double* __restrict__ radius_ptr,
+    int first, int last, PairOut out)
+{
+    __shared__ PairStage stage;
+    __shared__ AEntry sA[kCellPairWarps][32];
+    pair_stage_init(stage);
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const Grid g = *gp;
+    const double radius = radius_ptr ? *radius_ptr : radius_val;
+    const unsigned rq = (unsigned)min((int)ceil(radius * g.q_inv) + 1, 65535);
+    const unsigned rq2 = rq | (rq << 16);
+    const double cell_per_q = g.inv_h / g.q_inv; // quantisation steps -> cells
+    const uint4* __restrict__ ent = reinterpret_cast<const uint4*>(eg.ent);
+    AEntry* A = sA[wib];
+    const int pos = first + (blockIdx.x * kCellPairWarps + wib) * 32 + lane;
+    const bool valid = pos < last;
+    unsigned key = 0xffffffffu;
+    int cl[3] = { 0, 0, 0 }, ch[3] = { 0, 0, 0 }; // conservative cell range of the inflated box
+    if (valid) {
+        const uint4 e = __ldg(ent + pos);
+        key = (unsigned)eg.keys[pos] & ~eg.type_bit;
+        AEntry a;
+        a.L01 = __vsubus2(e.x, rq2);                                  // lo0, lo1 - rq (saturating)
+        a.H01 = __vaddus2(__funnelshift_r(e.y, e.z, 16), rq2);       // hi0, hi1 + rq
+        const unsigned lo2 = e.y & 0xffffu, hi2 = e.z >> 16;
+        a.lo2 = lo2 > rq ? lo2 - rq : 0u;
+        a.hi2 = min(hi2 + rq, 65535u);
+        a.pos = pos;
+        a.id = (int)e.w;
+        a.pad0 = a.pad1 = 0;
+        A[lane] = a;
+        cl[0] = (int)floor((double)(a.L01 & 0xffffu) * cell_per_q); ch[0] = (int)floor((double)(a.H01 & 0xffffu) * cell_per_q);
+        cl[1] = (int)floor((double)(a.L01 >> 16) * cell_per_q);     ch[1] = (int)floor((double)(a.H01 >> 16) * cell_per_q);
+        cl[2] = (int)floor((double)a.lo2 * cell_per_q);             ch[2] = (int)floor((double)a.hi2 * cell_per_q);
+    }
+    __syncwarp();
+    unsigned remaining = __ballot_sync(full, valid);
+    while (remaining) {
+        const int leader = __ffs(remaining) - 1;
+        const unsigned k0 = __shfl_sync(full, key, leader);
+        const unsigned m = __ballot_sync(full, valid && key == k0); // the run: consecutive lanes (the array is sorted by cell)
+        remaining &= ~m;
+        const int a_lo = leader, a_hi = 32 - __clz(m);              // lanes [a_lo, a_hi)
+        const int p_lo = __shfl_sync(full, pos, leader);
+        // the run's own cell and the union of its queries' ranges, clamped to [c - 2, c + 1] and to the grid
+        const int cx = (int)(k0 % (unsigned)g.nx), cy = (int)((k0 / (unsigned)g.nx) % (unsigned)g.ny), cz = (int)(k0 / ((unsigned)g.nx * (unsigned)g.ny));
+        const bool in = (m >> lane) & 1u;
+        int lo[3], hi[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = __reduce_min_sync(full, in ? cl[a] : 0x7fffffff) - 1;
+            hi[a] = __reduce_max_sync(full, in ? ch[a] : -1);
+        }
+        const int xlo = max(max(lo[0], cx - 2), 0), xhi = min(min(hi[0], cx + 1), g.nx - 1);
+        const int ylo = max(max(lo[1], cy - 2), 0), yhi = min(min(hi[1], cy + 1), g.ny - 1);
+        const int zhi = min(min(hi[2], cz + 1), g.nz - 1);
+        // rows at or behind the own cell: r = 0 own row (cells cx..xhi); then (y' in (cy, yhi], z' = cz); then (y' in [ylo, yhi], z' in (cz, zhi])
+        const int nUp = max(yhi - cy, 0), nY = max(yhi - ylo + 1, 0), nZ = max(zhi - cz, 0);
+        const int nRows = 1 + nUp + nY * nZ; // <= 1 + 1 + 4 = 6
+        // lane 4 r + dx looks up cell dx of row r
+        int2 mine = make_int2(0x7fffffff, -1);
+        {
+            const int r = lane >> 2, dx = lane & 3;
+            if (r < nRows) {
+                int y, z, xs;
+                if (r == 0) { y = cy; z = cz; xs = cx; }
+                else if (r <= nUp) { y = cy + r; z = cz; xs = xlo; }
+                else { const int q = r - 1 - nUp; z = cz + 1 + q / nY; y = ylo + q % nY; xs = xlo; }
+                if (xs + dx <= xhi) mine = cell_lookup(eg, (unsigned)cell_key(g, xs + dx, y, z));
+            }
+        }
+        // run of row L % 8 (rows 0..5): cells of one row are consecutive keys => consecutive entries
+        const int rr = lane & 7;
+        int rs = 0x7fffffff, re = -1;
+#pragma unroll
+        for (int dx = 0; dx < 4; ++dx) {
+            rs = min(rs, __shfl_sync(full, mine.x, (4 * rr + dx) & 31));
+            re = max(re, __shfl_sync(full, mine.y, (4 * rr + dx) & 31));
+        }
+        if (rr == 0) rs = max(rs, p_lo + 1); // own row: nothing at or before the run's first query is ever needed
+        const int rlen = (lane < 6 && lane < nRows && re > rs) ? re - rs : 0;
+        int incl = rlen;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            const int t = __shfl_up_sync(full, incl, o);
+            if (lane >= o) incl += t;
+        }
+        int inc[6], st[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            inc[r] = __shfl_sync(full, incl, r);
+            st[r] = __shfl_sync(full, rs, r);
+        }
+        const int total = inc[5];
+        auto locate = [&](int j) {
+            int k = st[0] + j;
+#pragma unroll
+            for (int r = 1; r < 6; ++r)
+                if (j >= inc[r - 1]) k = st[r] + (j - inc[r - 1]);
+            return k;
+        };
+        int kn = (lane < total) ? locate(lane) : 0;
+        uint4 en = make_uint4(0u, 0u, 0u, 0u);
+        if (lane < total) en = __ldg(ent + kn);
+        for (int j = lane; j - lane < total; j += 32) {
+            const uint4 e = en;
+            const int bpos = kn;
+            const bool have = j < total;
+            if (j + 32 < total) { kn = locate(j + 32); en = __ldg(ent + kn); }
+            if (have) {
+                const unsigned bL01 = e.x, bH01 = __funnelshift_r(e.y, e.z, 16), blo2 = e.y & 0xffffu, bhi2 = e.z >> 16;
+                for (int a = a_lo; a < a_hi; ++a) {
+                    const AEntry q = A[a]; // same address on every lane: broadcast
+                    const bool hit = __vminu2(q.L01, bH01) == q.L01 && __vminu2(bL01, q.H01) == bL01 && q.lo2 <= bhi2 && blo2 <= q.hi2 && bpos > q.pos;
+                    if (hit) lane_push_pair(stage, out, min(q.id, (int)e.w), max(q.id, (int)e.w));
+                }
+            }
+        }
+        __syncwarp();
+    }
+    pair_stage_flush(stage, out);
+}
+
 // ---- phase 2: exact closest-feature classification, one THREAD per surviving pair (dense, convergent)
 // (:2168-2260)
 __global__ void __launch_bounds__(128) k_classify_pt(SurfArgs s, const int2* __restrict__ pairs, const unsigned* __restrict__ nPairs, unsigned cap, double dHat, int wantCand, CsOut out)
@@ -480,6 +630,16 @@ using namespace ipcgpu;
     } while (0)
 
 static inline int nblk(long long n, int b) { return (int)((n + b - 1) / b); }
+// IPCGPU_PAIRS_MODE: 1 (default) = cell-centric edge-edge pair finding, 0 = the warp-per-query kernel of round 1
+int pairs_mode()
+{
+    static const int mode = [] { const char* e = std::getenv("IPCGPU_PAIRS_MODE"); return e ? std::atoi(e) : 1; }();
+    return mode;
+}
+void cell_pairs_ee(const Grid* gp, const SortedGrid& eg, double radius_val, const double* radius_ptr, int first, int last, const PairOut& out, cudaStream_t st)
+{
+    if (last > first) k_cell_pairs_ee<<<nblk(last - first, 32 * kCellPairWarps), 32 * kCellPairWarps, 0, st>>>(gp, eg, radius_val, radius_ptr, first, last, out);
+}
 
 // stable radix sort of (keys, idx) pairs, result back in (keys, idx)
 static int sort_pass(ipcgpu_ctx* ctx, int n)
@@ -713,7 +873,8 @@ int contact_constraint_set(ipcgpu_ctx* ctx, double dHat, int wantCand, int* nC, 
         ctx->launches += 2;
     }
     if (e1 > e0 && s.nSE > 1) {
-        k_pairs_ee<<<nblk(e1 - e0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(w.grid.p, eg, w.ebox.p, dHat, radius, s.nSF + e0, s.nSF + e1, pee); // edge entries sit behind the triangles
+        if (pairs_mode() == 0) k_pairs_ee<<<nblk(e1 - e0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(w.grid.p, eg, w.ebox.p, dHat, radius, s.nSF + e0, s.nSF + e1, pee); // edge entries sit behind the triangles
+        else cell_pairs_ee(w.grid.p, eg, radius, nullptr, s.nSF + e0, s.nSF + e1, pee, st);
         k_classify_ee<<<kSMs * 8, 128, 0, st>>>(s, pee.pairs, pee.n, pee.cap, dHat, wantCand, out);
         ctx->launches += 2;
     }

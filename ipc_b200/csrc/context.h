@@ -175,6 +175,26 @@ struct ipcgpu_ctx {
 
     // work / result buffers
     ipcgpu::DevBuf<double> gcont, hblk, g, e_per_tet, partials, scalar_out, inv_steps, dir, in_partials;
+    ipcgpu::DevBuf<double> pSize_dev; // mean |p| of the uploaded search direction, read by the swept-grid kernel from device memory (graph replay)
+
+    // CUDA graphs of device-resident call sequences (ipcgpu_capture_begin / _end / ipcgpu_graph_launch).  A captured sequence mutates a
+    // few host-side state words (which scalars are still rank-local, which lists are global ...); they are snapshotted at the end of the
+    // capture and re-applied at every replay.  `epoch` is bumped by every call that may reallocate or re-partition: older graphs are refused.
+    struct HostState {
+        bool energy_local[4], checks_local, lists_local, lists_global, want_cand, swept_ready, fr_ready, inputs_marked, scatter_marked;
+        int nC, nP, nK, fr_host_n;
+    };
+    struct GraphRec {
+        cudaGraphExec_t exec = nullptr;
+        cudaGraph_t graph = nullptr;
+        uint64_t launches = 0, epoch = 0;
+        bool dirty_at_begin = false;
+        HostState hs;
+    };
+    std::vector<GraphRec> graphs;
+    bool capturing = false;
+    uint64_t epoch = 0, launches_at_capture = 0;
+    bool dirty_at_capture = false;
     double* h_scalar = nullptr; // pinned staging for scalars
 
     // profiling: event pairs per stage (only when enabled)

@@ -260,6 +260,9 @@ int solver_adopt_direction(ipcgpu_ctx* ctx)
         pSize /= (double)((long long)ctx->nSV * 3);
     }
     ctx->pSize = pSize;
+    if (!ctx->pSize_dev.reserve(1)) return IPCGPU_ERR_CUDA;
+    CKS(cudaMemcpyAsync(ctx->pSize_dev.p, &ctx->pSize, sizeof(double), cudaMemcpyHostToDevice, st));
+    CKS(cudaStreamSynchronize(st));
     ctx->pSize_surface = ctx->surface_ready;
     ctx->dir_valid = true;
     return 0;

@@ -81,6 +81,10 @@ SIGNATURES = {
     "ipcgpu_set_xtilde": (C.c_int, [_ctxp, _dp]),
     "ipcgpu_inertia_energy": (C.c_int, [_ctxp, _dp]),
     "ipcgpu_inertia_gradient": (C.c_int, [_ctxp, C.c_int, _dp]),
+    "ipcgpu_capture_begin": (C.c_int, [_ctxp]),
+    "ipcgpu_capture_end": (C.c_int, [_ctxp, _ip]),
+    "ipcgpu_graph_launch": (C.c_int, [_ctxp, C.c_int]),
+    "ipcgpu_graph_destroy": (C.c_int, [_ctxp, C.c_int]),
     "ipcgpu_csr_set_zero": (C.c_int, [_ctxp]),
     "ipcgpu_solve_pcg": (C.c_int, [_ctxp, _dp, C.c_double, C.c_int, _dp, C.c_int, _ip, _dp]),
     "ipcgpu_allreduce_grad_hess": (C.c_int, [_ctxp, C.c_int, C.c_int]),
@@ -293,6 +297,21 @@ class Context:
 
     def download_range_into(self, which, offset, out):
         self._ck(self.lib.ipcgpu_download_range(self.h, which, int(offset), int(out.size), _d(out)))
+
+    # ---- CUDA graphs of device-resident call sequences -----------------------------------------
+    def capture_begin(self):
+        self._ck(self.lib.ipcgpu_capture_begin(self.h))
+
+    def capture_end(self):
+        gid = C.c_int(-1)
+        self._ck(self.lib.ipcgpu_capture_end(self.h, C.byref(gid)))
+        return gid.value
+
+    def graph_launch(self, gid):
+        self._ck(self.lib.ipcgpu_graph_launch(self.h, int(gid)))
+
+    def graph_destroy(self, gid):
+        self._ck(self.lib.ipcgpu_graph_destroy(self.h, int(gid)))
 
     # ---- friction / inertia -------------------------------------------------------------------
     def set_prev_state(self, V_prev_soa=None):
