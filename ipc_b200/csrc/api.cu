@@ -331,10 +331,11 @@ int ipcgpu_create(int device, ipcgpu_ctx** out)
     }
     ctx->h_iter = static_cast<IterState*>(hi);
     std::memset(ctx->h_iter, 0, sizeof(IterState));
-    {   // optional side stream for the pair-Hessian build + projection (IPCGPU_BARRIER_OVERLAP=1; off by default: with eagerly enqueued
-        // launches the extra event calls cost more host time than the overlap wins -- measured 4.54 ms against 4.69 ms per iteration on C5)
+    {   // side stream for the pair-Hessian build + projection (IPCGPU_BARRIER_OVERLAP=0 keeps everything on one stream).  Replayed from a
+        // graph the overlap wins 0.11 ms per iteration on C5 (4.10 -> 3.99 ms); enqueued eagerly the extra event calls cost about as much
+        // host time as the overlap wins
         const char* e = std::getenv("IPCGPU_BARRIER_OVERLAP");
-        if (e && std::atoi(e) == 1) {
+        if (!(e && std::atoi(e) == 0)) {
             if (cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_inputs, cudaEventDisableTiming) != cudaSuccess
                 || cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess
                 || cudaEventCreateWithFlags(&ctx->ev_scatter, cudaEventDisableTiming) != cudaSuccess) {

@@ -249,8 +249,7 @@ DEV double dy_lo(unsigned long long n, int k) { return (double)n * pow2neg(k); }
 DEV double dy_hi(unsigned long long n, int k) { return (double)(n + 1) * pow2neg(k); }
 
 // co-domain test of one box: returns zero_in; sets box_in and max/each true_tol   (oracle: origin_in_box)
-template <bool VF>
-DEV bool origin_in_box(const TiPair& P, const DBox& b, const double* err, double ms, bool& box_in, double* true_tol)
+DEV bool origin_in_box(bool VF, const TiPair& P, const DBox& b, const double* err, double ms, bool& box_in, double* true_tol)
 {
     const int tk = b.kk & 0xff, uk = (b.kk >> 8) & 0xff, vk = (b.kk >> 16) & 0xff;
     const double tv[2] = { dy_lo(b.tn, tk), dy_hi(b.tn, tk) }, uv[2] = { dy_lo(b.un, uk), dy_hi(b.un, uk) }, vv[2] = { dy_lo(b.vn, vk), dy_hi(b.vn, vk) };
@@ -292,8 +291,7 @@ DEV bool origin_in_box(const TiPair& P, const DBox& b, const double* err, double
 
 DEV double linf3(const double* a, const double* b) { return fmax(fmax(fabs(a[0] - b[0]), fabs(a[1] - b[1])), fabs(a[2] - b[2])); }
 
-template <bool VF>
-DEV void width_tolerances(const TiPair& P, double tolerance, double* tol)
+DEV void width_tolerances(bool VF, const TiPair& P, double tolerance, double* tol)
 {
     double ps[4][3], pe[4][3];
 #pragma unroll
@@ -388,7 +386,7 @@ __global__ void __launch_bounds__(128) k_ti_stage1(NarrowArgs a, unsigned* __res
             DBox root = { 0ull, 0ull, 0ull, 0u, 0u };
             bool box_in;
             double tt[3];
-            alive = vf ? origin_in_box<true>(P, root, a.err_vf, ms, box_in, tt) : origin_in_box<false>(P, root, a.err_ee, ms, box_in, tt);
+            alive = origin_in_box(vf, P, root, vf ? a.err_vf : a.err_ee, ms, box_in, tt);
         }
     }
     // warp-aggregated append of the survivors
@@ -469,8 +467,8 @@ template <int W> DEV void group_scan(int v, int lane, int& incl, int& total)
 }
 
 // result codes of the root finder: 0 no collision, 1 collision (toi set), 2 deferred (W = 1 only: level buffer too small)
-template <bool VF, int W>
-__device__ int ti_root_finder(const TiPair& P, const double* tol, double co_tol, double max_t, const double* err, double ms, int max_itr, DBox* bufA,
+template <int W>
+__device__ int ti_root_finder(bool VF, const TiPair& P, const double* tol, const double* inv_tol, double co_tol, double max_t, const double* err, double ms, int max_itr, DBox* bufA,
     DBox* bufB, int gcap, int lane, double& toi, double& out_tol, int* __restrict__ warn, DBox* sA = nullptr, DBox* sB = nullptr, long long thread_budget = 0,
     const unsigned long long* best = nullptr)
 {
@@ -522,7 +520,7 @@ __device__ int ti_root_finder(const TiPair& P, const double* tol, double co_tol,
                     vis = true;
                     bool box_in;
                     double tt[3];
-                    if (origin_in_box<VF>(P, b, err, ms, box_in, tt)) {
+                    if (origin_in_box(VF, P, b, err, ms, box_in, tt)) {
                         flags = F_ZERO;
                         const bool tol_cond = tt[0] <= co_tol && tt[1] <= co_tol && tt[2] <= co_tol;
                         const bool cond1 = pow2neg(tk) <= tol[0] && pow2neg(uk) <= tol[1] && pow2neg(vk) <= tol[2];
@@ -596,7 +594,7 @@ __device__ int ti_root_finder(const TiPair& P, const double* tol, double co_tol,
 #pragma unroll
                         for (int d = 0; d < 3; ++d)
                             if (w[d] > tol[d]) {
-                                const double r = w[d] / tol[d];
+                                const double r = inv_tol[d] * w[d]; // = w[d] / tol[d] bit for bit: w[d] is a power of two (see ti_ccd)
                                 if (r > best) { best = r; split = d; }
                             }
                         const int pk = split == 0 ? tk : (split == 1 ? uk : vk);
@@ -677,8 +675,7 @@ __device__ int ti_root_finder(const TiPair& P, const double* tol, double co_tol,
 // one 2-step exchange per level.  Levels of >= kWideLevel boxes switch to one box per lane.  The split pass is always one box per
 // lane with a warp scan.  Level buffers live in shared memory.  Same arithmetic per corner, same decisions => same result as the
 // box-parallel variant.  Returns -1 when a level outgrows the shared-memory buffer (the caller restarts with the box-parallel variant).
-template <bool VF>
-__device__ int ti_root_finder_cp(const TiPair& P, const double* tol, double co_tol, double max_t, const double* err, double ms, int max_itr, DBox* sA, DBox* sB,
+__device__ int ti_root_finder_cp(bool VF, const TiPair& P, const double* tol, const double* inv_tol, double co_tol, double max_t, const double* err, double ms, int max_itr, DBox* sA, DBox* sB,
     int lane, double& toi, double& out_tol, int* __restrict__ warn, const unsigned long long* best)
 {
     const bool check_t = (max_t != 1.0);
@@ -726,7 +723,7 @@ __device__ int ti_root_finder_cp(const TiPair& P, const double* tol, double co_t
                         vis = true;
                         bool box_in;
                         double tt[3];
-                        if (origin_in_box<VF>(P, b, err, ms, box_in, tt)) {
+                        if (origin_in_box(VF, P, b, err, ms, box_in, tt)) {
                             flags = F_ZERO;
                             const bool tol_cond = tt[0] <= co_tol && tt[1] <= co_tol && tt[2] <= co_tol;
                             const bool cond1 = pow2neg(tk) <= tol[0] && pow2neg(uk) <= tol[1] && pow2neg(vk) <= tol[2];
@@ -860,7 +857,7 @@ __device__ int ti_root_finder_cp(const TiPair& P, const double* tol, double co_t
 #pragma unroll
                             for (int d = 0; d < 3; ++d)
                                 if (w[d] > tol[d]) {
-                                    const double r = w[d] / tol[d];
+                                    const double r = inv_tol[d] * w[d]; // = w[d] / tol[d] bit for bit: w[d] is a power of two (see ti_ccd)
                                     if (r > best) { best = r; split = d; }
                                 }
                             const int pk = split == 0 ? tk : (split == 1 ? uk : vk);
@@ -916,38 +913,44 @@ __device__ int ti_root_finder_cp(const TiPair& P, const double* tol, double co_t
     return 0;
 }
 
-// out-of-line instances for the warp-level pass: four inlined copies (VF/EE x the two calls of pair_ccd) of both root finders cost
-// 255 registers plus spills and an instruction footprint that starves the fetch unit
-template <bool VF>
-__device__ __noinline__ int ti_root_finder_cp_call(const TiPair& P, const double* tol, double co_tol, double max_t, const double* err, double ms, int max_itr, DBox* sA,
-    DBox* sB, int lane, double& toi, double& out_tol, int* __restrict__ warn, const unsigned long long* best)
+// out-of-line instances for the warp-level pass.  Round 2, second half: ncu on k_ti_stage2 showed "no instruction" as the largest stall
+// (3.4 per issued instruction): 16 K SASS instructions -- VF and EE template copies of both root finders, each inlined at two call sites
+// (first run and ms = 0 retry) -- with four warps per CTA at unrelated program counters.  VF / EE is now a run-time flag tested inside the
+// corner evaluation (a few instructions differ), the retry is a second trip through ONE call site, and the split rule multiplies by exact
+// reciprocals instead of dividing (below): one copy of each root finder.
+__device__ __noinline__ int ti_root_finder_cp_call(bool vf, const TiPair& P, const double* tol, const double* inv_tol, double co_tol, double max_t, const double* err, double ms,
+    int max_itr, DBox* sA, DBox* sB, int lane, double& toi, double& out_tol, int* __restrict__ warn, const unsigned long long* best)
 {
-    return ti_root_finder_cp<VF>(P, tol, co_tol, max_t, err, ms, max_itr, sA, sB, lane, toi, out_tol, warn, best);
+    return ti_root_finder_cp(vf, P, tol, inv_tol, co_tol, max_t, err, ms, max_itr, sA, sB, lane, toi, out_tol, warn, best);
 }
-template <bool VF>
-__device__ __noinline__ int ti_root_finder_warp_call(const TiPair& P, const double* tol, double co_tol, double max_t, const double* err, double ms, int max_itr, DBox* bufA,
-    DBox* bufB, int cap, int lane, double& toi, double& out_tol, int* __restrict__ warn, const unsigned long long* best)
+__device__ __noinline__ int ti_root_finder_warp_call(bool vf, const TiPair& P, const double* tol, const double* inv_tol, double co_tol, double max_t, const double* err, double ms,
+    int max_itr, DBox* bufA, DBox* bufB, int cap, int lane, double& toi, double& out_tol, int* __restrict__ warn, const unsigned long long* best)
 {
-    return ti_root_finder<VF, 32>(P, tol, co_tol, max_t, err, ms, max_itr, bufA, bufB, cap, lane, toi, out_tol, warn, nullptr, nullptr, 0, best);
+    return ti_root_finder<32>(vf, P, tol, inv_tol, co_tol, max_t, err, ms, max_itr, bufA, bufB, cap, lane, toi, out_tol, warn, nullptr, nullptr, 0, best);
 }
 
 // vertexFaceCCD_double / edgeEdgeCCD_double including the no_zero_toi refinement loop; returns 0 / 1 / 2 (deferred)
-template <bool VF, int W>
-__device__ int ti_ccd(const TiPair& P, const double* err, double ms, double tolerance, double t_max, int max_itr, DBox* bufA, DBox* bufB, int cap, int lane,
+template <int W>
+__device__ int ti_ccd(bool vf, const TiPair& P, const double* err, double ms, double tolerance, double t_max, int max_itr, DBox* bufA, DBox* bufB, int cap, int lane,
     double& toi, int* __restrict__ warn, DBox* sA = nullptr, DBox* sB = nullptr, long long thread_budget = 0, const unsigned long long* best = nullptr)
 {
     double tolerance_in = tolerance, ms_in = ms, out_tol = tolerance;
     bool is_impacting = false, tmp = false;
     unsigned iter = 0;
     do {
-        double tol[3];
-        width_tolerances<VF>(P, tolerance_in, tol);
+        double tol[3], inv_tol[3];
+        width_tolerances(vf, P, tolerance_in, tol);
+        // The split rule compares width / tolerance per axis.  Every width is a power of two, and x -> x * 2^-k commutes with rounding
+        // (no overflow / underflow here: tolerances are ~1e-9 .. 1e-3 or inf for a static axis), so 2^-k / tol == (1 / tol) * 2^-k bit
+        // for bit: one division per axis and search instead of three per box.
+#pragma unroll
+        for (int d = 0; d < 3; ++d) inv_tol[d] = 1.0 / tol[d];
         int rc;
         if (W == 32 && sA) {
-            rc = ti_root_finder_cp_call<VF>(P, tol, tolerance_in, t_max, err, ms_in, max_itr, sA, sB, lane, toi, out_tol, warn, best);
-            if (rc == -1) rc = ti_root_finder_warp_call<VF>(P, tol, tolerance_in, t_max, err, ms_in, max_itr, bufA, bufB, cap, lane, toi, out_tol, warn, best);
+            rc = ti_root_finder_cp_call(vf, P, tol, inv_tol, tolerance_in, t_max, err, ms_in, max_itr, sA, sB, lane, toi, out_tol, warn, best);
+            if (rc == -1) rc = ti_root_finder_warp_call(vf, P, tol, inv_tol, tolerance_in, t_max, err, ms_in, max_itr, bufA, bufB, cap, lane, toi, out_tol, warn, best);
         }
-        else rc = ti_root_finder<VF, W>(P, tol, tolerance_in, t_max, err, ms_in, max_itr, bufA, bufB, cap, lane, toi, out_tol, warn, sA, sB, thread_budget, best);
+        else rc = ti_root_finder<W>(vf, P, tol, inv_tol, tolerance_in, t_max, err, ms_in, max_itr, bufA, bufB, cap, lane, toi, out_tol, warn, sA, sB, thread_budget, best);
         if (rc == 2) return 2;
         tmp = rc == 1;
         if (iter == 0) is_impacting = tmp;
@@ -968,19 +971,23 @@ __device__ int pair_ccd(bool vf, const TiPair& P, const NarrowArgs& a, DBox* buf
     DBox* sA = nullptr, DBox* sB = nullptr, long long thread_budget = 0)
 {
     const double d = pair_distance_sqrt(vf, P);
-    const double ms = fmin(0.2 * d, 1e-6);
     const double max_t = a.st->max_t;                 // canonical semantics: every pair sees the step on entry
-    const unsigned long long* best = &a.st->ccd_ord;  // running device-wide minimum
-    int hit = vf ? ti_ccd<true, W>(P, a.err_vf, ms, a.tol, max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn, sA, sB, thread_budget, best)
-                 : ti_ccd<false, W>(P, a.err_ee, ms, a.tol, max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn, sA, sB, thread_budget, best);
-    if (hit == 2) return 2;
-    if (hit && toi < 1e-6) { // :759-781
-        // no pruning against the running minimum here: this result is rescaled by 0.8 afterwards, so a box starting in
-        // [best, 1.25 best) can still lower the global step (the exactness argument of ti_root_finder only covers unscaled results)
-        hit = vf ? ti_ccd<true, W>(P, a.err_vf, 0.0, a.tol, max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn, sA, sB, thread_budget, nullptr)
-                 : ti_ccd<false, W>(P, a.err_ee, 0.0, a.tol, max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn, sA, sB, thread_budget, nullptr);
+    const double* err = vf ? a.err_vf : a.err_ee;
+    int hit = 0;
+    // first trip: ms = min(0.2 d, 1e-6), pruned against the running device-wide minimum; second trip (:759-781, only after a hit with
+    // toi < 1e-6): ms = 0, result scaled by 0.8 and NOT pruned -- a box starting in [best, 1.25 best) can still lower the global step
+    // (the exactness argument of ti_root_finder only covers unscaled results).  One call site for both.
+#pragma unroll 1
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const double ms = attempt ? 0.0 : fmin(0.2 * d, 1e-6);
+        const unsigned long long* best = attempt ? nullptr : &a.st->ccd_ord;
+        hit = ti_ccd<W>(vf, P, err, ms, a.tol, max_t, a.max_itr, bufA, bufB, cap, lane, toi, warn, sA, sB, thread_budget, best);
         if (hit == 2) return 2;
-        if (hit) toi *= 0.8;
+        if (attempt == 1) {
+            if (hit) toi *= 0.8;
+            break;
+        }
+        if (!(hit && toi < 1e-6)) break;
     }
     return hit;
 }
@@ -998,7 +1005,7 @@ __device__ int pair_ccd(bool vf, const TiPair& P, const NarrowArgs& a, DBox* buf
 constexpr int kGrpCap = 44;       // boxes per level buffer per group (two buffers per group: 4 x 2 x 44 x 32 B = 11.3 KB per warp; static smem stays < 48 KB)
 constexpr int kGrpWarpsPerCta = 4;
 
-__device__ int ti_root_finder_grp(bool vf, const TiPair& P, const double* tol, double co_tol, double max_t, const double* err, double ms, int max_itr, DBox* sA, DBox* sB,
+__device__ int ti_root_finder_grp(bool vf, const TiPair& P, const double* tol, const double* inv_tol, double co_tol, double max_t, const double* err, double ms, int max_itr, DBox* sA, DBox* sB,
     int gl, unsigned gmask, double& toi, double& out_tol, int* __restrict__ warn, const unsigned long long* best)
 {
     const bool check_t = (max_t != 1.0);
@@ -1117,7 +1124,7 @@ __device__ int ti_root_finder_grp(bool vf, const TiPair& P, const double* tol, d
 #pragma unroll
                         for (int d = 0; d < 3; ++d)
                             if (w[d] > tol[d]) {
-                                const double r = w[d] / tol[d];
+                                const double r = inv_tol[d] * w[d]; // = w[d] / tol[d] bit for bit: w[d] is a power of two (see ti_ccd)
                                 if (r > bestr) { bestr = r; split = d; }
                             }
                         const int pk = split == 0 ? tk : (split == 1 ? uk : vk);
@@ -1186,9 +1193,10 @@ __device__ int ti_ccd_grp(bool vf, const TiPair& P, const double* err, double ms
     unsigned iter = 0;
     do {
         double tol[3];
-        if (vf) width_tolerances<true>(P, tolerance_in, tol);
-        else width_tolerances<false>(P, tolerance_in, tol);
-        const int rc = ti_root_finder_grp(vf, P, tol, tolerance_in, t_max, err, ms_in, max_itr, sA, sB, gl, gmask, toi, out_tol, warn, best);
+        width_tolerances(vf, P, tolerance_in, tol);
+        double inv_tol[3];
+        for (int d = 0; d < 3; ++d) inv_tol[d] = 1.0 / tol[d];
+        const int rc = ti_root_finder_grp(vf, P, tol, inv_tol, tolerance_in, t_max, err, ms_in, max_itr, sA, sB, gl, gmask, toi, out_tol, warn, best);
         if (rc == 2) return 2;
         tmp = rc == 1;
         if (iter == 0) is_impacting = tmp;
@@ -1390,6 +1398,9 @@ SortedGrid edge_grid(const ipcgpu_ctx* ctx);
 int boxes_and_grid(ipcgpu_ctx* ctx, const double* dir, const double* alpha_ptr, double radius, const double* radius_ptr, bool with_vertex_boxes); // constraint.cu
 int pairs_mode();                                                                                                                                  // constraint.cu
 void cell_pairs_ee(const ipcgpu::Grid* gp, const ipcgpu::SortedGrid& eg, double radius_val, const double* radius_ptr, int first, int last, const ipcgpu::PairOut& out, cudaStream_t st);
+void cell_pairs_pt(const ipcgpu::Grid* gp, const ipcgpu::SortedGrid& vg, const ipcgpu::SortedGrid& tg, double radius_val, const double* radius_ptr, int first, int last,
+    const ipcgpu::PairOut& out, cudaStream_t st);
+SortedGrid vertex_grid(const ipcgpu_ctx* ctx);
 
 constexpr int kStage2WarpsPerCta = 4;
 constexpr int kStage2Ctas = 148 * 6; // persistent: 6 CTAs x 4 warps per SM
@@ -1559,7 +1570,8 @@ int ccd_full(ipcgpu_ctx* ctx, double tol, const double* err_vf, const double* er
     unsigned* nPairs = reinterpret_cast<unsigned*>(cw.counters.p + 8);
     PairOut ppt{ cw.bp_pairs.p, nPairs, (unsigned)cw.bp_cap, w.counters.p + 14 }, pee{ cw.bp_pairs.p + cw.bp_cap, nPairs + 1, (unsigned)cw.bp_cap, w.counters.p + 14 };
     if (v1 > v0 && s.nSF > 0) {
-        k_ccd_pairs_pt<<<nblk(v1 - v0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(cw.grid.p, cw.vbox.p, tg, ist, v0, v1, ppt);
+        if (pairs_mode() == 0 || cw.built_vertices != s.nSV) k_ccd_pairs_pt<<<nblk(v1 - v0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(cw.grid.p, cw.vbox.p, tg, ist, v0, v1, ppt);
+        else cell_pairs_pt(cw.grid.p, vertex_grid(ctx), tg, 0.0, &ist->radius, s.nSF + s.nSE + v0, s.nSF + s.nSE + v1, ppt, st);
         k_ccd_filter_pt<<<kSMs * 8, 256, 0, st>>>(s, ppt.pairs, ppt.n, ppt.cap, w.vmin.p, w.vmax.p, out);
         ctx->launches += 2;
     }

@@ -117,17 +117,19 @@ __global__ void k_grid_params(const unsigned long long* __restrict__ bounds, dou
 
 // one entry per primitive: the cell of the box's lower corner.  Triangles [0, nT) and edges [nT, nT + nE) go into ONE array and ONE sort:
 // the edge keys carry a type bit above the cell key, so the sorted array is "all triangles by cell, then all edges by cell".
-__global__ void __launch_bounds__(256) k_emit(int nT, int nE, const Box* __restrict__ tboxes, const Box* __restrict__ eboxes, const Grid* __restrict__ gp, unsigned type_bit,
-    unsigned long long* __restrict__ keys, int* __restrict__ vals)
+// Surface vertices (their points / swept boxes) follow as a third segment [nT + nE, nT + nE + nV) with the next type bit: the queries of
+// the cell-centric point-triangle kernel are then sorted by cell as well.
+__global__ void __launch_bounds__(256) k_emit(int nT, int nE, int nV, const Box* __restrict__ tboxes, const Box* __restrict__ eboxes, const Box* __restrict__ vboxes,
+    const Grid* __restrict__ gp, unsigned type_bit, unsigned long long* __restrict__ keys, int* __restrict__ vals)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nT + nE) return;
+    if (i >= nT + nE + nV) return;
     const Grid g = *gp;
-    const bool edge = i >= nT;
-    const int id = edge ? i - nT : i;
+    const int type = i >= nT + nE ? 2 : (i >= nT ? 1 : 0);
+    const int id = type == 2 ? i - nT - nE : (type == 1 ? i - nT : i);
     int c0[3], c1[3];
-    cell_range(g, edge ? eboxes[id] : tboxes[id], c0, c1);
-    keys[i] = cell_key(g, c0[0], c0[1], c0[2]) | (edge ? (unsigned long long)type_bit : 0ull);
+    cell_range(g, type == 2 ? vboxes[id] : (type == 1 ? eboxes[id] : tboxes[id]), c0, c1);
+    keys[i] = cell_key(g, c0[0], c0[1], c0[2]) | ((unsigned long long)type * type_bit);
     vals[i] = id;
 }
 // heads and tails of the runs of the sorted key array go into the open-addressing table (key -> [first, last+1))
@@ -152,13 +154,13 @@ __global__ void __launch_bounds__(256) k_build_cell_table(int n, const unsigned 
     }
 }
 // entries of the sorted grid: quantised box + id (see QEntry)
-__global__ void __launch_bounds__(256) k_gather_boxes(int nT, int nE, const Box* __restrict__ tboxes, const Box* __restrict__ eboxes, const int* __restrict__ ids,
-    const Grid* __restrict__ gp, uint4* __restrict__ sorted)
+__global__ void __launch_bounds__(256) k_gather_boxes(int nT, int nE, int nV, const Box* __restrict__ tboxes, const Box* __restrict__ eboxes, const Box* __restrict__ vboxes,
+    const int* __restrict__ ids, const Grid* __restrict__ gp, uint4* __restrict__ sorted)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nT + nE) return;
+    if (i >= nT + nE + nV) return;
     const int id = ids[i];
-    const QBox q = quantize_box(*gp, i >= nT ? eboxes[id] : tboxes[id]); // the sorted array keeps the triangles in front
+    const QBox q = quantize_box(*gp, i >= nT + nE ? vboxes[id] : (i >= nT ? eboxes[id] : tboxes[id])); // sorted array: triangles, then edges, then vertices
     sorted[i] = make_uint4((unsigned)q.lo[0] | ((unsigned)q.lo[1] << 16), (unsigned)q.lo[2] | ((unsigned)q.hi[0] << 16), (unsigned)q.hi[1] | ((unsigned)q.hi[2] << 16), (unsigned)id);
 }
 
@@ -372,6 +374,112 @@ __global__ void __launch_bounds__(32 * kCellPairWarps) k_cell_pairs_ee(const Gri
                     const AEntry q = A[a]; // same address on every lane: broadcast
                     const bool hit = __vminu2(q.L01, bH01) == q.L01 && __vminu2(bL01, q.H01) == bL01 && q.lo2 <= bhi2 && blo2 <= q.hi2 && bpos > q.pos;
                     if (hit) lane_push_pair(stage, out, min(q.id, (int)e.w), max(q.id, (int)e.w));
+                }
+            }
+        }
+        __syncwarp();
+    }
+    pair_stage_flush(stage, out);
+}
+
+// The point-triangle twin: queries = 32 consecutive entries of the sorted VERTEX segment (points, or swept vertex boxes for the CCD),
+// partners = triangle entries of every cell a query of the run can see (both sides: up to 4 x 4 rows of <= 4 cells; typically 3 x 3 x 3).
+// Rows are walked one after the other (a row of three cells holds about one warp-load of triangles); the first load of the next row is
+// issued before the current row is tested.
+__global__ void __launch_bounds__(32 * kCellPairWarps) k_cell_pairs_pt(const Grid* __restrict__ gp, SortedGrid vg, SortedGrid tg, double radius_val,
+    const double* __restrict__ radius_ptr, int first, int last, PairOut out)
+{
+    __shared__ PairStage stage;
+    __shared__ AEntry sA[kCellPairWarps][32];
+    pair_stage_init(stage);
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const Grid g = *gp;
+    const double radius = radius_ptr ? *radius_ptr : radius_val;
+    const unsigned rq = (unsigned)min((int)ceil(radius * g.q_inv) + 1, 65535);
+    const unsigned rq2 = rq | (rq << 16);
+    const double cell_per_q = g.inv_h / g.q_inv;
+    const uint4* __restrict__ ent = reinterpret_cast<const uint4*>(tg.ent);
+    AEntry* A = sA[wib];
+    const int pos = first + (blockIdx.x * kCellPairWarps + wib) * 32 + lane;
+    const bool valid = pos < last;
+    unsigned key = 0xffffffffu;
+    int cl[3] = { 0, 0, 0 }, ch[3] = { 0, 0, 0 };
+    if (valid) {
+        const uint4 e = __ldg(ent + pos);
+        key = (unsigned)vg.keys[pos] & ~vg.type_bit;
+        AEntry a;
+        a.L01 = __vsubus2(e.x, rq2);
+        a.H01 = __vaddus2(__funnelshift_r(e.y, e.z, 16), rq2);
+        const unsigned lo2 = e.y & 0xffffu, hi2 = e.z >> 16;
+        a.lo2 = lo2 > rq ? lo2 - rq : 0u;
+        a.hi2 = min(hi2 + rq, 65535u);
+        a.pos = pos;
+        a.id = (int)e.w;
+        a.pad0 = a.pad1 = 0;
+        A[lane] = a;
+        cl[0] = (int)floor((double)(a.L01 & 0xffffu) * cell_per_q); ch[0] = (int)floor((double)(a.H01 & 0xffffu) * cell_per_q);
+        cl[1] = (int)floor((double)(a.L01 >> 16) * cell_per_q);     ch[1] = (int)floor((double)(a.H01 >> 16) * cell_per_q);
+        cl[2] = (int)floor((double)a.lo2 * cell_per_q);             ch[2] = (int)floor((double)a.hi2 * cell_per_q);
+    }
+    __syncwarp();
+    unsigned remaining = __ballot_sync(full, valid);
+    while (remaining) {
+        const int leader = __ffs(remaining) - 1;
+        const unsigned k0 = __shfl_sync(full, key, leader);
+        const unsigned m = __ballot_sync(full, valid && key == k0);
+        remaining &= ~m;
+        const int a_lo = leader, a_hi = 32 - __clz(m);
+        const int cx = (int)(k0 % (unsigned)g.nx), cy = (int)((k0 / (unsigned)g.nx) % (unsigned)g.ny), cz = (int)(k0 / ((unsigned)g.nx * (unsigned)g.ny));
+        const bool in = (m >> lane) & 1u;
+        int lo[3], hi[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = __reduce_min_sync(full, in ? cl[a] : 0x7fffffff) - 1;
+            hi[a] = __reduce_max_sync(full, in ? ch[a] : -1);
+        }
+        const int xlo = max(max(lo[0], cx - 2), 0), xhi = min(min(hi[0], cx + 1), g.nx - 1);
+        const int ylo = max(max(lo[1], cy - 2), 0), yhi = min(min(hi[1], cy + 1), g.ny - 1);
+        const int zlo = max(max(lo[2], cz - 2), 0), zhi = min(min(hi[2], cz + 1), g.nz - 1);
+        const int nY = max(yhi - ylo + 1, 0), nZ = max(zhi - zlo + 1, 0);
+        const int nRows = nY * nZ; // <= 16
+        for (int rbase = 0; rbase < nRows; rbase += 8) { // cell-table lookups of 8 rows x 4 cells at a time
+            int2 mine = make_int2(0x7fffffff, -1);
+            {
+                const int r = rbase + (lane >> 2), dx = lane & 3;
+                if (r < nRows && xlo + dx <= xhi) mine = cell_lookup(tg, (unsigned)cell_key(g, xlo + dx, ylo + r % nY, zlo + r / nY));
+            }
+            // run of the lane's row = [min start, max end) over its 4 cells (consecutive keys => consecutive entries)
+            int rs = mine.x, re = mine.y;
+#pragma unroll
+            for (int o = 1; o < 4; o <<= 1) {
+                rs = min(rs, __shfl_xor_sync(full, rs, o));
+                re = max(re, __shfl_xor_sync(full, re, o));
+            }
+            const int rows_here = min(nRows - rbase, 8);
+            // first chunk of row 0 of this group in flight
+            int cs = __shfl_sync(full, rs, 0), ce = __shfl_sync(full, re, 0);
+            uint4 en = make_uint4(0u, 0u, 0u, 0u);
+            if (ce > cs && lane < ce - cs) en = __ldg(ent + cs + lane); // (an empty row is [INT_MAX, -1): no index arithmetic on it)
+            for (int r = 0; r < rows_here; ++r) {
+                const int s0 = cs, e0 = ce;
+                uint4 e = en;
+                if (r + 1 < rows_here) { // next row's first chunk
+                    cs = __shfl_sync(full, rs, 4 * (r + 1));
+                    ce = __shfl_sync(full, re, 4 * (r + 1));
+                    if (ce > cs && lane < ce - cs) en = __ldg(ent + cs + lane);
+                }
+                const int len = e0 > s0 ? e0 - s0 : 0;
+                for (int jj = lane; jj - lane < len; jj += 32) {
+                    if (jj >= 32 && jj < len) e = __ldg(ent + s0 + jj); // rows longer than one warp-load (rare)
+                    if (jj < len) {
+                        const unsigned bL01 = e.x, bH01 = __funnelshift_r(e.y, e.z, 16), blo2 = e.y & 0xffffu, bhi2 = e.z >> 16;
+                        for (int a = a_lo; a < a_hi; ++a) {
+                            const AEntry q = A[a];
+                            const bool hit = __vminu2(q.L01, bH01) == q.L01 && __vminu2(bL01, q.H01) == bL01 && q.lo2 <= bhi2 && blo2 <= q.hi2;
+                            if (hit) lane_push_pair(stage, out, q.id, (int)e.w);
+                        }
+                    }
                 }
             }
         }
@@ -636,6 +744,10 @@ int pairs_mode()
     static const int mode = [] { const char* e = std::getenv("IPCGPU_PAIRS_MODE"); return e ? std::atoi(e) : 1; }();
     return mode;
 }
+void cell_pairs_pt(const Grid* gp, const SortedGrid& vg, const SortedGrid& tg, double radius_val, const double* radius_ptr, int first, int last, const PairOut& out, cudaStream_t st)
+{
+    if (last > first) k_cell_pairs_pt<<<nblk(last - first, 32 * kCellPairWarps), 32 * kCellPairWarps, 0, st>>>(gp, vg, tg, radius_val, radius_ptr, first, last, out);
+}
 void cell_pairs_ee(const Grid* gp, const SortedGrid& eg, double radius_val, const double* radius_ptr, int first, int last, const PairOut& out, cudaStream_t st)
 {
     if (last > first) k_cell_pairs_ee<<<nblk(last - first, 32 * kCellPairWarps), 32 * kCellPairWarps, 0, st>>>(gp, eg, radius_val, radius_ptr, first, last, out);
@@ -702,7 +814,7 @@ int contact_alloc(ipcgpu_ctx* ctx)
 {
     ContactWork& w = ctx->cw;
     const int nSE = ctx->nSE, nSF = ctx->nSF, nSV = ctx->nSV;
-    const size_t nAll = (size_t)std::max(nSE + nSF, 1); // triangles and edges share one sorted array
+    const size_t nAll = (size_t)std::max(nSE + nSF + nSV, 1); // triangles, edges and surface vertices share one sorted array
     const int cap = std::max(ctx->pair_capacity, 1024);
     bool ok = w.vbox.reserve(std::max(nSV, 1)) && w.ebox.reserve(std::max(nSE, 1)) && w.tbox.reserve(std::max(nSF, 1)) && w.bounds.reserve(8) && w.grid.reserve(2)
         && w.centries.reserve(nAll) && w.ckeys.reserve(nAll) && w.cvals.reserve(nAll) && w.key_tmp.reserve(nAll) && w.val_tmp.reserve(nAll)
@@ -742,21 +854,22 @@ int contact_alloc(ipcgpu_ctx* ctx)
 
 // build the sorted grids of the triangles and the edges in ONE pass: one emit, one radix sort (cell key + type bit), one gather of the
 // quantised entries, one cell table
-static int build_grids(ipcgpu_ctx* ctx, int nT, int nE)
+static int build_grids(ipcgpu_ctx* ctx, int nT, int nE, int nV)
 {
     ContactWork& w = ctx->cw;
     cudaStream_t st = ctx->stream;
-    const int n = nT + nE;
+    const int n = nT + nE + nV;
+    w.built_vertices = nV;
     if (n <= 0) return 0;
     const unsigned type_bit = 1u << (3 * w.axis_bits);
-    k_emit<<<nblk(n, 256), 256, 0, st>>>(nT, nE, w.tbox.p, w.ebox.p, w.grid.p, type_bit, w.key_tmp.p, w.val_tmp.p);
+    k_emit<<<nblk(n, 256), 256, 0, st>>>(nT, nE, nV, w.tbox.p, w.ebox.p, w.vbox.p, w.grid.p, type_bit, w.key_tmp.p, w.val_tmp.p);
     size_t bytes = w.cub_tmp.n;
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(w.cub_tmp.p, bytes, w.key_tmp.p, w.ckeys.p, w.val_tmp.p, w.cvals.p, n, 0, 3 * w.axis_bits + 1, st); // cells < 2^(3 axis_bits), + type
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(w.cub_tmp.p, bytes, w.key_tmp.p, w.ckeys.p, w.val_tmp.p, w.cvals.p, n, 0, 3 * w.axis_bits + 2, st); // cells < 2^(3 axis_bits), + 2 type bits
     if (e != cudaSuccess) {
         ctx->err = std::string("cub grid sort: ") + cudaGetErrorString(e);
         return IPCGPU_ERR_CUDA;
     }
-    k_gather_boxes<<<nblk(n, 256), 256, 0, st>>>(nT, nE, w.tbox.p, w.ebox.p, w.cvals.p, w.grid.p, reinterpret_cast<uint4*>(w.centries.p));
+    k_gather_boxes<<<nblk(n, 256), 256, 0, st>>>(nT, nE, nV, w.tbox.p, w.ebox.p, w.vbox.p, w.cvals.p, w.grid.p, reinterpret_cast<uint4*>(w.centries.p));
     cudaMemsetAsync(w.ctab_key.p, 0xff, (size_t)(w.tab_mask + 1) * sizeof(unsigned), st);
     k_build_cell_table<<<nblk(n, 256), 256, 0, st>>>(n, w.ckeys.p, w.ctab_key.p, w.ctab_start.p, w.tab_mask);
     w.built_axis_bits = w.axis_bits;
@@ -773,6 +886,12 @@ SortedGrid edge_grid(const ipcgpu_ctx* ctx)
 {
     const ContactWork& w = ctx->cw;
     return SortedGrid{ w.ckeys.p, w.cvals.p, w.centries.p, ctx->nSE, w.ctab_key.p, w.ctab_start.p, w.tab_mask, 1u << (3 * w.built_axis_bits) };
+}
+
+SortedGrid vertex_grid(const ipcgpu_ctx* ctx) // surface-vertex entries [nSF + nSE, nSF + nSE + built_vertices) of the combined sorted array
+{
+    const ContactWork& w = ctx->cw;
+    return SortedGrid{ w.ckeys.p, w.cvals.p, w.centries.p, w.built_vertices, w.ctab_key.p, w.ctab_start.p, w.tab_mask, 2u << (3 * w.built_axis_bits) };
 }
 
 SurfArgs surf_args(const ipcgpu_ctx* ctx)
@@ -798,7 +917,7 @@ int boxes_and_grid(ipcgpu_ctx* ctx, const double* dir, const double* alpha_ptr, 
     if (s.nSF > 0) k_boxes<<<nblk(s.nSF, 256), 256, 0, st>>>(s, 2, dir, alpha_ptr, w.tbox.p, w.bounds.p);
     k_grid_params<<<1, 32, 0, st>>>(w.bounds.p, radius, radius_ptr, w.axis_bits, w.grid.p, ctx->iter.p);
     ctx->launches += 5;
-    return build_grids(ctx, s.nSF, s.nSE);
+    return build_grids(ctx, s.nSF, s.nSE, (with_vertex_boxes && pairs_mode() != 0) ? s.nSV : 0);
 }
 
 // pack this rank's lists, allgather, rebuild the global lists (called by api.cu around its ncclAllGather)
@@ -844,7 +963,7 @@ int contact_constraint_set(ipcgpu_ctx* ctx, double dHat, int wantCand, int* nC, 
     const double radius = sqrt(dHat);
     cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_HASH);
     int rc;
-    if ((rc = boxes_and_grid(ctx, nullptr, nullptr, radius, nullptr, false))) return rc;
+    if ((rc = boxes_and_grid(ctx, nullptr, nullptr, radius, nullptr, pairs_mode() != 0))) return rc; // (vertex entries for the cell-centric PT kernel)
     ctx->prof_end(pe);
 
     pe = ctx->prof_begin(IPCGPU_STAGE_CONSTRAINT_SET);
@@ -868,7 +987,8 @@ int contact_constraint_set(ipcgpu_ctx* ctx, double dHat, int wantCand, int* nC, 
     unsigned* nPairs = reinterpret_cast<unsigned*>(w.counters.p + 8); // [8] PT pairs, [9] EE pairs
     PairOut ppt{ w.bp_pairs.p, nPairs, (unsigned)w.bp_cap, w.counters.p + 4 }, pee{ w.bp_pairs.p + w.bp_cap, nPairs + 1, (unsigned)w.bp_cap, w.counters.p + 4 };
     if (v1 > v0 && s.nSF > 0) {
-        k_pairs_pt<<<nblk(v1 - v0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(s, w.grid.p, tg, dHat, radius, v0, v1, ppt);
+        if (pairs_mode() == 0 || w.built_vertices != s.nSV) k_pairs_pt<<<nblk(v1 - v0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(s, w.grid.p, tg, dHat, radius, v0, v1, ppt);
+        else cell_pairs_pt(w.grid.p, vertex_grid(ctx), tg, radius, nullptr, s.nSF + s.nSE + v0, s.nSF + s.nSE + v1, ppt, st); // vertex entries: by sorted position
         k_classify_pt<<<kSMs * 8, 128, 0, st>>>(s, ppt.pairs, ppt.n, ppt.cap, dHat, wantCand, out);
         ctx->launches += 2;
     }
