@@ -259,15 +259,21 @@ def main():
     part = ctx.partition_info()
     own0, own1 = part["value_begin"], part["value_end"]  # CSR values of the rows this rank owns (everything on one rank)
 
-    def enqueue_iteration():
-        """one Newton iteration's hot path, NULL outputs everywhere: one uninterrupted stream, nothing read back"""
+    def enqueue_iteration(download=False):
+        """one Newton iteration's hot path, NULL outputs everywhere: one uninterrupted stream, nothing read back.
+        download=True (the e2e form): the gradient and the CSR rows this rank owns start travelling to the pinned host buffers on the copy
+        stream as soon as they are final, next to the step-bound stages that follow (joined by the fetch)"""
         ctx.constraint_set(dHat, 1, fetch=False, sizes=False)
-        ctx.elastic_energy(DT2, 1, want=False)
         ctx.barrier_energy(dHat, KAPPA, want=False)
-        ctx.elastic_grad_hess(DT2, 1, 1, 1, None, None)   # zeroes the value array first (LinSysSolver::setZero)
+        # computeEnergyVal + computeGradient + computePrecondMtr of the elastic term in ONE pass over the tets (one SVD per tet, like the
+        # reference's F / SVD cache between them); zeroes the value array first (LinSysSolver::setZero)
+        ctx.elastic_energy_grad_hess(DT2, 1, 1, 1, None, None)
         ctx.barrier_gradient(dHat, KAPPA, None)
         ctx.barrier_hessian(dHat, KAPPA, 1, None)
         ctx.allreduce_grad_hess(1, 0)  # one NCCL sum of the gradient; the Hessian is complete per row owner (no-op on a single rank)
+        if download:
+            ctx.download_range_async(L.BUF_GRADIENT, 0, hg.array)                         # D2H: gradient
+            ctx.download_range_async(L.BUF_CSR_VALUES, own0, ha.array[own0:own1])       # D2H: the CSR values of the rows this rank owns
         ctx.step_bound_set(1.0)
         ctx.inversion_step(None, 0.2, None)
         ctx.ccd_partial(None, TI_TOL, err_vf, err_ee, None)
@@ -282,14 +288,11 @@ def main():
     def step_e2e():
         ctx.set_state(hV.array)        # H2D: positions
         ctx.set_search_dir(hp.array)   # H2D: search direction
-        if stats.get("graph") is not None:
-            ctx.graph_launch(stats["graph"])
+        if stats.get("graph_e2e") is not None:
+            ctx.graph_launch(stats["graph_e2e"])
         else:
-            enqueue_iteration()
-        it = ctx.fetch_iteration()
-        ctx.download_into(L.BUF_GRADIENT, hg.array)                      # D2H: gradient
-        ctx.download_range_into(L.BUF_CSR_VALUES, own0, ha.array[own0:own1])  # D2H: the CSR values of the rows this rank owns
-        stats["it_e2e"] = it
+            enqueue_iteration(download=True)
+        stats["it_e2e"] = ctx.fetch_iteration()  # joins the copy stream: gradient and CSR rows are in the host buffers
 
     # ---- parity of exactly this mode at exactly this size, inside the run (rank 0 asserts; every rank takes part in the collectives)
     parity = None
@@ -374,9 +377,16 @@ def main():
     ctx.profile(0)
 
     # ---- end-to-end timing (host buffers through the C ABI) -----------------------------------------
-    stats["graph"] = graph
+    step_e2e()  # eager once (creates the copy stream), then the e2e form of the iteration is captured like the device-resident one
+    if graph is not None:
+        ctx.capture_begin()
+        enqueue_iteration(download=True)
+        stats["graph_e2e"] = ctx.capture_end()
     for _ in range(2):
         step_e2e()
+    if rank == 0:  # the host buffers hold what the device holds
+        assert np.array_equal(hg.array, ctx.download(L.BUF_GRADIENT, 3 * m.nV)), "e2e gradient copy differs"
+        assert np.array_equal(ha.array[own0:own1], ctx.download(L.BUF_CSR_VALUES, nnz)[own0:own1]), "e2e CSR copy differs"
     barrier()
     t0 = time.perf_counter()
     e2e_steps = max(3, min(args.steps, 10))
@@ -449,7 +459,9 @@ def main():
                                     "note": "latency/ALU-bound interval search on the surviving pairs (SURVEY 8d): the vertex data is L2-resident and the "
                                             "critical path is the deepest pair, so the HBM fraction only says how far from a pure streaming pass the stage is"},
             "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(2 * 3 * m.nV * 8), "d2h_bytes_per_step": int((3 * m.nV + (own1 - own0)) * 8 + 120),
-                    "note": "host clock around: H2D of x and p, the whole iteration, D2H of the gradient and of the CSR values of the rows this rank owns (rank 0's byte counts)"},
+                    "note": "host clock around: H2D of x and p (pinned), the whole iteration (graph replay), D2H of the gradient and of the CSR values of the rows "
+                            "this rank owns (rank 0's byte counts) -- forked onto a copy stream as soon as they are final, i.e. next to the step-bound stages, "
+                            "and joined by the fetch; checked equal to the device arrays after the warm-up"},
             "parity": parity,
             "gpu_launches": int(launches), "clocks": clocks,
         }

@@ -152,6 +152,11 @@ int ipcgpu_elastic_hessian(ipcgpu_ctx* ctx, double coef, int redoSVD, int projec
  * on top.  Results stay on the device when the pointers are NULL. */
 int ipcgpu_elastic_grad_hess(ipcgpu_ctx* ctx, double coef, int projectSPD, int projectDBC, int add_mass,
     double* g, double* a);
+/* ... and computeEnergyVal in the same pass: the reference caches F / U / sigma / V between computeEnergyVal(redoSVD = 2) and the gradient /
+ * Hessian of the same state (Optimizer.hpp:115-116); here the energy is a by-product of the kernel that already holds the singular values
+ * (one SVD per tet and iteration instead of two).  E NULL: the energy stays on the device (ipcgpu_fetch_iteration). */
+int ipcgpu_elastic_energy_grad_hess(ipcgpu_ctx* ctx, double coef, int projectSPD, int projectDBC, int add_mass,
+    double* E, double* g, double* a);
 /* Energy::filterStepSize (Energy.cpp:565-581); alpha_inout == NULL: the device-resident step */
 int ipcgpu_inversion_step(ipcgpu_ctx* ctx, const double* p_interleaved, double slack, double* alpha_inout);
 
@@ -285,6 +290,11 @@ int ipcgpu_allreduce_grad_hess(ipcgpu_ctx* ctx, int with_gradient, int with_hess
 int ipcgpu_download(ipcgpu_ctx* ctx, int which, double* dst, uint64_t count);
 /* count entries starting at `offset` (e.g. the CSR values of the rows this rank owns: ipcgpu_partition_info) */
 int ipcgpu_download_range(ipcgpu_ctx* ctx, int which, uint64_t offset, uint64_t count, double* dst);
+/* The same without waiting: the copy is forked onto the context's copy stream behind everything enqueued so far and runs next to whatever
+ * the main stream does afterwards (a host solver wants the Hessian, the step-bound stages that follow do not touch it).  dst must be pinned
+ * (ipcgpu_host_alloc) and must not be read before the next ipcgpu_fetch_iteration / ipcgpu_sync, which join the copy stream.  May be
+ * captured into a graph (call it once outside a capture first). */
+int ipcgpu_download_range_async(ipcgpu_ctx* ctx, int which, uint64_t offset, uint64_t count, double* dst_pinned);
 /* raw device pointer of a result buffer (for a device-side linear solver) */
 void* ipcgpu_device_ptr(ipcgpu_ctx* ctx, int which);
 

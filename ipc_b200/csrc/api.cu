@@ -89,9 +89,23 @@ int nccl_min_u64(ipcgpu_ctx* ctx, unsigned long long* word)
     return IPCGPU_OK;
 }
 
+// make the main stream wait for the copies ipcgpu_download_range_async forked off (a graph edge when capturing)
+static int join_copy_stream(ipcgpu_ctx* ctx)
+{
+    if (!ctx->copy_pending) return IPCGPU_OK;
+    CK(cudaEventRecord(ctx->ev_copy_join, ctx->copy));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_join, 0));
+    ctx->copy_pending = false;
+    return IPCGPU_OK;
+}
+
 // one D2H copy of the iteration state + stream synchronisation
 int fetch_iter_state(ipcgpu_ctx* ctx)
 {
+    {
+        int rcj = join_copy_stream(ctx);
+        if (rcj) return rcj;
+    }
     CK(cudaMemcpyAsync(ctx->h_iter, ctx->iter.p, sizeof(IterState), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return IPCGPU_OK;
@@ -354,6 +368,12 @@ void ipcgpu_destroy(ipcgpu_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->side) cudaStreamSynchronize(ctx->side);
+    if (ctx->copy) {
+        cudaStreamSynchronize(ctx->copy);
+        cudaStreamDestroy(ctx->copy);
+        cudaEventDestroy(ctx->ev_copy_fork);
+        cudaEventDestroy(ctx->ev_copy_join);
+    }
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto& r : ctx->graphs) {
         if (r.exec) cudaGraphExecDestroy(r.exec);
@@ -382,6 +402,8 @@ int ipcgpu_host_alloc(void** ptr, uint64_t bytes) { return cudaMallocHost(ptr, b
 int ipcgpu_host_free(void* ptr) { return cudaFreeHost(ptr) == cudaSuccess ? IPCGPU_OK : IPCGPU_ERR_CUDA; }
 int ipcgpu_sync(ipcgpu_ctx* ctx)
 {
+    int rcj = join_copy_stream(ctx);
+    if (rcj) return rcj;
     CK(cudaStreamSynchronize(ctx->stream));
     return IPCGPU_OK;
 }
@@ -593,7 +615,7 @@ static int zero_values(ipcgpu_ctx* ctx)
     return IPCGPU_OK;
 }
 
-static int run_grad_hess(ipcgpu_ctx* ctx, double coef, int projectSPD, int projectDBC, bool need_g, bool need_h, int add_mass)
+static int run_grad_hess(ipcgpu_ctx* ctx, double coef, int projectSPD, int projectDBC, bool need_g, bool need_h, int add_mass, bool with_energy = false)
 {
     REQUIRE(ctx->maps_ready, IPCGPU_ERR_STATE, "ipcgpu_set_mesh first");
     if (need_h) {
@@ -601,9 +623,22 @@ static int run_grad_hess(ipcgpu_ctx* ctx, double coef, int projectSPD, int proje
         if (rc) return rc;
     }
     cudaEvent_t pe = ctx->prof_begin(IPCGPU_STAGE_ELASTIC_TET);
-    elastic_grad_hess(ctx->eargs(), coef, projectSPD, need_g, need_h, ctx->gcont.p, ctx->hblk.p, ctx->stream);
+    double* e_part = nullptr;
+    if (with_energy) { // psi * vol per CTA, summed in fixed order below (computeEnergyVal at the same state: the SVD is shared)
+        ALLOC(ctx->e_partials2, (size_t)elastic_grad_hess_blocks(ctx->n_list) + 8);
+        e_part = ctx->e_partials2.p;
+    }
+    elastic_grad_hess(ctx->eargs(), coef, projectSPD, need_g, need_h, ctx->gcont.p, ctx->hblk.p, ctx->stream, e_part);
     ctx->prof_end(pe);
     ++ctx->launches;
+    if (with_energy) {
+        pe = ctx->prof_begin(IPCGPU_STAGE_ELASTIC_ENERGY);
+        reduce_sum(e_part, elastic_grad_hess_blocks(ctx->n_list), coef, ctx->scalar_out.p, ctx->stream);
+        energy_store(ctx->iter.p, 0, ctx->scalar_out.p, ctx->stream);
+        ctx->prof_end(pe);
+        ctx->launches += 2;
+        ctx->energy_local[0] = ctx->nranks > 1;
+    }
     if (need_g) {
         // owned vertices gather their complete sums (every incident tet is in this rank's list); the other rows are written as zeros
         pe = ctx->prof_begin(IPCGPU_STAGE_GATHER_GRADIENT);
@@ -686,6 +721,35 @@ int ipcgpu_elastic_grad_hess(ipcgpu_ctx* ctx, double coef, int projectSPD, int p
     if (g) CK(cudaMemcpyAsync(g, ctx->g.p, (size_t)3 * ctx->nV * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (a) CK(cudaMemcpyAsync(a, ctx->a.p, (size_t)ctx->nnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (g || a) CK(cudaStreamSynchronize(ctx->stream));
+    return IPCGPU_OK;
+}
+
+int ipcgpu_elastic_energy_grad_hess(ipcgpu_ctx* ctx, double coef, int projectSPD, int projectDBC, int add_mass, double* E, double* g, double* a)
+{
+    CK(cudaSetDevice(ctx->device));
+    REQUIRE(ctx->nnz > 0, IPCGPU_ERR_STATE, "ipcgpu_set_csr first");
+    // the value array is rebuilt from scratch (LinSysSolver::setZero, then addCoeff of every term): slots that no local tet touches
+    // -- contact-only blocks of the augmented pattern -- must not keep last iteration's values
+    int rc = zero_values(ctx);
+    if (rc) return rc;
+    if ((rc = run_grad_hess(ctx, coef, projectSPD, projectDBC, true, true, add_mass, true))) return rc;
+    if (ctx->nranks > 1 && (g || a)) {
+        rc = ipcgpu_allreduce_grad_hess(ctx, g ? 1 : 0, a ? 1 : 0);
+        if (rc) return rc;
+    }
+    if (g) CK(cudaMemcpyAsync(g, ctx->g.p, (size_t)3 * ctx->nV * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (a) CK(cudaMemcpyAsync(a, ctx->a.p, (size_t)ctx->nnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (E) { // host result requested: complete it across the ranks now
+        if (ctx->nranks > 1) {
+            int r = g_nccl.AllReduce(&ctx->iter.p->energy[0], &ctx->iter.p->energy[0], 1, kNcclFloat64, kNcclSum, ctx->nccl_comm, ctx->stream);
+            REQUIRE(r == 0, IPCGPU_ERR_NCCL, "ncclAllReduce(energy) failed");
+            ctx->energy_local[0] = false;
+        }
+        CK(cudaMemcpyAsync(ctx->h_scalar, &ctx->iter.p->energy[0], sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        *E = ctx->h_scalar[0];
+    }
+    else if (g || a) CK(cudaStreamSynchronize(ctx->stream));
     return IPCGPU_OK;
 }
 
@@ -1454,6 +1518,10 @@ int ipcgpu_capture_end(ipcgpu_ctx* ctx, int* graph_id)
 {
     REQUIRE(ctx->capturing, IPCGPU_ERR_STATE, "no capture in progress");
     REQUIRE(graph_id != nullptr, IPCGPU_ERR_ARG, "null graph id");
+    {
+        int rcj = join_copy_stream(ctx); // a forked copy branch must rejoin the capturing stream
+        if (rcj) return rcj;
+    }
     ctx->capturing = false;
     ipcgpu_ctx::GraphRec rec;
     cudaError_t e = cudaStreamEndCapture(ctx->stream, &rec.graph);
@@ -1731,6 +1799,28 @@ static int buf_info(ipcgpu_ctx* ctx, int which, double** p, uint64_t* n)
 }
 
 int ipcgpu_download(ipcgpu_ctx* ctx, int which, double* dst, uint64_t count) { return ipcgpu_download_range(ctx, which, 0, count, dst); }
+
+int ipcgpu_download_range_async(ipcgpu_ctx* ctx, int which, uint64_t offset, uint64_t count, double* dst_pinned)
+{
+    double* p;
+    uint64_t n;
+    REQUIRE(buf_info(ctx, which, &p, &n) == 0, IPCGPU_ERR_ARG, "unknown buffer id");
+    REQUIRE((dst_pinned || count == 0) && offset + count <= n, IPCGPU_ERR_ARG, "download: bad destination or range");
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->copy) {
+        REQUIRE(!ctx->capturing, IPCGPU_ERR_STATE, "call ipcgpu_download_range_async once outside a capture first (it creates the copy stream)");
+        CK(cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->ev_copy_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->ev_copy_join, cudaEventDisableTiming));
+    }
+    if (count == 0) return IPCGPU_OK;
+    // everything enqueued so far produces the buffer: the copy starts after it and runs next to whatever follows on the main stream
+    CK(cudaEventRecord(ctx->ev_copy_fork, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->copy, ctx->ev_copy_fork, 0));
+    CK(cudaMemcpyAsync(dst_pinned, p + offset, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy));
+    ctx->copy_pending = true;
+    return IPCGPU_OK;
+}
 
 int ipcgpu_download_range(ipcgpu_ctx* ctx, int which, uint64_t offset, uint64_t count, double* dst)
 {

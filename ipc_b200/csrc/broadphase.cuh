@@ -69,7 +69,7 @@ DEV int upper_bound_u64(const unsigned long long* __restrict__ keys, int n, unsi
 // open-addressing table (cell key -> index of the first entry of that cell) replaces binary searches: the <= 27 cell lookups of a
 // query run on 27 lanes at once.
 struct SortedGrid {
-    const unsigned long long* keys; // sorted cell keys
+    const unsigned* keys;           // sorted cell keys (cell | type bits: 32 bits, so the radix sort moves half the key bytes)
     const int* ids;                 // primitive id per entry
     const QEntry* ent;              // quantised box + id per entry, in sorted order (coalesced 16-byte candidate scan)
     int n;

@@ -1460,7 +1460,7 @@ int ccd_narrow(ipcgpu_ctx* ctx, const int2* cand, const int* n32, const unsigned
         k_ti_stage1<<<kSMs * 16, 128, 0, st>>>(a, w.surv.p, nSurv, flags);
         ctx->prof_end(pe1);
         unsigned* nDefA = reinterpret_cast<unsigned*>(flags + 2);
-        // pass A (thread per survivor, 10-box budget): the shallow majority (2-3 boxes) at 32 pairs per warp;
+        // pass A (thread per survivor, 24-box budget): the shallow majority (2-3 boxes) at 32 pairs per warp;
         // pass G (8 lanes per pair, 4 pairs per warp): the searches pass A gave up on, unless a level outgrows the group's 44-box buffer;
         // pass B (warp per pair): those wide searches.  IPCGPU_TI_MODE: 0 = A + B (default), 1 = G + B, 2 = A + G + B, 3 = A + A(48-box levels) + B.
         // Measured on C5 (narrow phase per iteration): A + B 1.62 ms, G + B 2.02 ms, A + G + B 2.12 ms -- the four groups of a warp diverge and
@@ -1473,7 +1473,8 @@ int ccd_narrow(ipcgpu_ctx* ctx, const int2* cand, const int* n32, const unsigned
             k_ti_stage2<<<kStage2Ctas, 32 * kStage2WarpsPerCta, 0, st>>>(a, w.surv2.p, nDefA, work, reinterpret_cast<DBox*>(w.scratch.p), kLevelCap, &ist->ccd_ord, flags + 1);
         }
         else {
-            static const long long budgetA = [] { const char* e = std::getenv("IPCGPU_TI_BUDGET"); return e ? std::atoll(e) : 10ll; }();
+            static const long long budgetA = [] { const char* e = std::getenv("IPCGPU_TI_BUDGET"); return e ? std::atoll(e) : 24ll; }(); // boxes a thread may evaluate before it hands its pair on
+            // (C5 after the code-size refactor, narrow phase per iteration: 10 -> 1.33 ms, 16 -> 1.11, 24 -> 1.05, 32 -> 1.09, 64 -> 1.23, 128 -> 1.42)
             static const int occA = [] { const char* e = std::getenv("IPCGPU_TI_OCC"); return e ? std::atoi(e) : 2; }(); // CTAs/SM the thread pass is compiled for (2: 255 regs, 3: 168 regs + spills)
             if (occA == 3) k_ti_stage15<kThreadCap, 3><<<kSMs * 16, 128, 0, st>>>(a, w.surv.p, nSurv, w.surv2.p, nDefA, budgetA, &ist->ccd_ord, flags + 1);
             else k_ti_stage15<kThreadCap, 2><<<kSMs * 16, 128, 0, st>>>(a, w.surv.p, nSurv, w.surv2.p, nDefA, budgetA, &ist->ccd_ord, flags + 1);

@@ -120,7 +120,7 @@ __global__ void k_grid_params(const unsigned long long* __restrict__ bounds, dou
 // Surface vertices (their points / swept boxes) follow as a third segment [nT + nE, nT + nE + nV) with the next type bit: the queries of
 // the cell-centric point-triangle kernel are then sorted by cell as well.
 __global__ void __launch_bounds__(256) k_emit(int nT, int nE, int nV, const Box* __restrict__ tboxes, const Box* __restrict__ eboxes, const Box* __restrict__ vboxes,
-    const Grid* __restrict__ gp, unsigned type_bit, unsigned long long* __restrict__ keys, int* __restrict__ vals)
+    const Grid* __restrict__ gp, unsigned type_bit, unsigned* __restrict__ keys, int* __restrict__ vals)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nT + nE + nV) return;
@@ -129,18 +129,18 @@ __global__ void __launch_bounds__(256) k_emit(int nT, int nE, int nV, const Box*
     const int id = type == 2 ? i - nT - nE : (type == 1 ? i - nT : i);
     int c0[3], c1[3];
     cell_range(g, type == 2 ? vboxes[id] : (type == 1 ? eboxes[id] : tboxes[id]), c0, c1);
-    keys[i] = cell_key(g, c0[0], c0[1], c0[2]) | ((unsigned long long)type * type_bit);
+    keys[i] = (unsigned)cell_key(g, c0[0], c0[1], c0[2]) | ((unsigned)type * type_bit);
     vals[i] = id;
 }
 // heads and tails of the runs of the sorted key array go into the open-addressing table (key -> [first, last+1))
-__global__ void __launch_bounds__(256) k_build_cell_table(int n, const unsigned long long* __restrict__ keys, unsigned* __restrict__ tab_key, int2* __restrict__ tab_range,
+__global__ void __launch_bounds__(256) k_build_cell_table(int n, const unsigned* __restrict__ keys, unsigned* __restrict__ tab_key, int2* __restrict__ tab_range,
     unsigned mask)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const unsigned key = (unsigned)keys[i];
-    const bool head = (i == 0) || (unsigned)keys[i - 1] != key;
-    const bool tail = (i == n - 1) || (unsigned)keys[i + 1] != key;
+    const unsigned key = keys[i];
+    const bool head = (i == 0) || keys[i - 1] != key;
+    const bool tail = (i == n - 1) || keys[i + 1] != key;
     if (!head && !tail) return;
     unsigned h = cell_hash(key) & mask;
     for (;;) {
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(32 * kCellPairWarps) k_cell_pairs_ee(const Gri
     int cl[3] = { 0, 0, 0 }, ch[3] = { 0, 0, 0 }; // conservative cell range of the inflated box
     if (valid) {
         const uint4 e = __ldg(ent + pos);
-        key = (unsigned)eg.keys[pos] & ~eg.type_bit;
+        key = eg.keys[pos] & ~eg.type_bit;
         AEntry a;
         a.L01 = __vsubus2(e.x, rq2);                                  // lo0, lo1 - rq (saturating)
         a.H01 = __vaddus2(__funnelshift_r(e.y, e.z, 16), rq2);       // hi0, hi1 + rq
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(32 * kCellPairWarps) k_cell_pairs_pt(const Gri
     int cl[3] = { 0, 0, 0 }, ch[3] = { 0, 0, 0 };
     if (valid) {
         const uint4 e = __ldg(ent + pos);
-        key = (unsigned)vg.keys[pos] & ~vg.type_bit;
+        key = vg.keys[pos] & ~vg.type_bit;
         AEntry a;
         a.L01 = __vsubus2(e.x, rq2);
         a.H01 = __vaddus2(__funnelshift_r(e.y, e.z, 16), rq2);
@@ -842,7 +842,7 @@ int contact_alloc(ipcgpu_ctx* ctx)
         return IPCGPU_ERR_CUDA;
     }
     size_t b1 = 0, b2 = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, b1, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int*)nullptr, (int*)nullptr, (int)nAll);
+    cub::DeviceRadixSort::SortPairs(nullptr, b1, (unsigned*)nullptr, (unsigned*)nullptr, (int*)nullptr, (int*)nullptr, (int)nAll);
     cub::DeviceRadixSort::SortPairs(nullptr, b2, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int*)nullptr, (int*)nullptr, 4 * cap);
     if (!w.cub_tmp.reserve(std::max(b1, b2) + 256)) {
         ctx->err = "cub temp allocation failed";

@@ -44,7 +44,8 @@ struct DevBuf {
 struct ContactWork {
     DevBuf<Box> vbox, ebox, tbox;   // per-primitive boxes (primitive order)
     DevBuf<QEntry> centries;        // grid-sorted entries (triangles first, then edges): quantised box + id
-    DevBuf<unsigned long long> bounds, ckeys, key_tmp, skey, skey2; // ckeys: sorted cell keys of the combined triangle + edge grid
+    DevBuf<unsigned long long> bounds, skey, skey2;
+    DevBuf<unsigned> ckeys, key_tmp; // ckeys: sorted 32-bit cell keys (cell | type bits) of the combined triangle + edge + vertex grid
     DevBuf<Grid> grid;
     DevBuf<int> cvals, val_tmp, counters, sidx, sidx2;
     DevBuf<int4> act, dup, para, tmp4;
@@ -105,6 +106,11 @@ struct ipcgpu_ctx {
     // side stream: the build + projection of the pair Hessians (latency-bound, a fraction of one wave) run next to the elastic assembly;
     // ev_inputs marks, on the main stream, the last point at which their inputs (positions, contact sets) changed
     cudaStream_t side = nullptr;
+    // copy stream: ipcgpu_download_range_async forks it off the main stream, so that a result (gradient, CSR values) travels to the host
+    // while the later stages of the iteration run; joined by ipcgpu_fetch_iteration / ipcgpu_sync / ipcgpu_capture_end
+    cudaStream_t copy = nullptr;
+    cudaEvent_t ev_copy_fork = nullptr, ev_copy_join = nullptr;
+    bool copy_pending = false;
     cudaEvent_t ev_inputs = nullptr, ev_join = nullptr, ev_scatter = nullptr; // (ev_scatter: the previous scatter has read the pair Hessians)
     bool scatter_marked = false;
     bool inputs_marked = false;
@@ -175,7 +181,7 @@ struct ipcgpu_ctx {
     ipcgpu::DevBuf<double> sol, pcg_b, pcg_r, pcg_p, pcg_q, pcg_minv, pcg_scal, pcg_hist;
 
     // work / result buffers
-    ipcgpu::DevBuf<double> gcont, hblk, g, e_per_tet, partials, scalar_out, inv_steps, dir, in_partials;
+    ipcgpu::DevBuf<double> gcont, hblk, g, e_per_tet, partials, scalar_out, inv_steps, dir, in_partials, e_partials2;
     ipcgpu::DevBuf<double> pSize_dev; // mean |p| of the uploaded search direction, read by the swept-grid kernel from device memory (graph replay)
 
     // CUDA graphs of device-resident call sequences (ipcgpu_capture_begin / _end / ipcgpu_graph_launch).  A captured sequence mutates a
@@ -223,6 +229,7 @@ struct ipcgpu_ctx {
         p.nV = nV; p.nT = nT; p.t_begin = t_begin; p.t_end = t_end;
         p.n_list = n_list; p.tet_list = (nranks > 1) ? tet_list.p : nullptr;
         p.V = V.p; p.T = T.p; p.Ainv = Ainv.p; p.vol = vol.p; p.mu = mu.p; p.lam = lam.p; p.energy = energy;
+        p.e_row_lo = (nranks > 1) ? v_begin : 0; p.e_row_hi = (nranks > 1) ? v_end : nV;
         return p;
     }
 };

@@ -131,164 +131,27 @@ DEV void tma_store_tile(void* gdst, const void* ssrc, unsigned bytes)
 // as the slot is computed; only two such regions live in shared memory at a time (9 KB instead of 46 KB per CTA), which lifts the
 // shared-memory occupancy limit of the first version of this kernel.
 // block slots of a tet in emission order: (a, b) local vertex pair, offset of the slot inside a tile (in units of 64 doubles), length
-__constant__ int c_slot_a[10] = { 0, 0, 0, 0, 1, 1, 1, 2, 2, 3 };
-__constant__ int c_slot_b[10] = { 0, 1, 2, 3, 1, 2, 3, 2, 3, 3 };
-__constant__ int c_slot_o[10] = { 0, 24, 33, 42, 6, 51, 60, 12, 69, 18 };
 
-// ROLLED variant of the gradient/Hessian kernel: identical arithmetic, but the ten 3x3 vertex blocks are produced by ONE loop body
-// (W = G V staged in shared memory and indexed at run time) instead of ten unrolled copies.  ncu on the unrolled kernel: 6.6 k SASS
-// instructions executed once per thread, "no instruction" the second largest stall (1.9 per issue): the body streams through the
-// instruction cache.  The rolled body is ~1/3 of that.
-template <int ENERGY, bool NEED_G>
-__global__ void __launch_bounds__(kHessTile, 8) k_elastic_grad_hess_rolled(ElasticArgs p, double coef, int projectSPD,
-    double* __restrict__ gcont /* 12 per LOCAL tet */, double* __restrict__ hblk /* tile-major, 78 per LOCAL tet */)
+// TILES 64-tet tiles per CTA: the warps of a CTA walk the (6.6 k instruction) body in step -- every slot ends in a CTA barrier -- so a larger CTA
+// means fewer distinct instruction streams per SM competing for the instruction caches (ncu, round 1: "no instruction" 1.9 stalls per issue
+// with eight independent 64-thread CTAs per SM).  The tile layout of the output does not change: half-CTA h works on tile blockIdx.x * TILES + h.
+template <int ENERGY, bool NEED_G, bool NEED_H, int TILES>
+__global__ void __launch_bounds__(kHessTile * TILES, 8 / TILES) k_elastic_grad_hess(ElasticArgs p, double coef, int projectSPD,
+    double* __restrict__ gcont /* 12 per LOCAL tet */, double* __restrict__ hblk /* tile-major, 78 per LOCAL tet */, double* __restrict__ e_partials /* nullable */)
 {
-    extern __shared__ __align__(128) double smem[];
-    double* sHb[2] = { smem, smem + kHessTile * 9 };   // two slot buffers (ping-pong)
-    double* sW = smem + 2 * kHessTile * 9;             // W staged SoA: sW[(3a+k)*64 + t]
-    double* sG = sW + kHessTile * 12;                  // kHessTile * 12
-    const int nLocal = p.n_list;
-    const int tile0 = blockIdx.x * kHessTile;
-    const int t = tile0 + threadIdx.x;
-    const bool active = t < nLocal;
-    const int ntile = min(kHessTile, nLocal - tile0);
-    M3 U;
-    int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
-    double a00 = 0, a01 = 0, a02 = 0, a11 = 0, a12 = 0, a22 = 0, d01 = 0, d10 = 0, o01 = 0, d12 = 0, d21 = 0, o12 = 0, d20 = 0, d02 = 0, o02 = 0;
-    if (active) {
-        TetIn in;
-        const int tt = p.tet_list ? __ldg(p.tet_list + t) : p.t_begin + t;
-        load_tet(p, tt, in);
-        v0 = in.v[0]; v1 = in.v[1]; v2 = in.v[2]; v3 = in.v[3];
-        M3 F, V;
-        double s[3];
-        def_grad(in, F);
-        svd3<true>(F, U, s, V);
-        const double w = coef * in.vol;
-        if (NEED_G) {
-            M3 P;
-            pk1<ENERGY>(F, U, s, V, in.mu, in.lam, P);
-            double* g = sG + threadIdx.x * 12;
-            double g0 = 0.0, g1 = 0.0, g2 = 0.0;
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                double a = w * (in.A(i, 0) * P(0, 0) + in.A(i, 1) * P(0, 1) + in.A(i, 2) * P(0, 2));
-                double b = w * (in.A(i, 0) * P(1, 0) + in.A(i, 1) * P(1, 1) + in.A(i, 2) * P(1, 2));
-                double c = w * (in.A(i, 0) * P(2, 0) + in.A(i, 1) * P(2, 1) + in.A(i, 2) * P(2, 2));
-                g[3 + 3 * i] = a;
-                g[4 + 3 * i] = b;
-                g[5 + 3 * i] = c;
-                g0 -= a;
-                g1 -= b;
-                g2 -= c;
-            }
-            g[0] = g0;
-            g[1] = g1;
-            g[2] = g2;
-        }
-        SigmaDerivs sd;
-        sigma_derivs<ENERGY>(s, in.mu, in.lam, sd);
-        if (projectSPD) make_pd3(sd.A);
-        double bd0[3], bd1[3], bo[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const int cp = (c + 1) % 3;
-            double right = sd.dE[c] + sd.dE[cp];
-            const double sum = s[c] + s[cp];
-            right /= 2.0 * ((sum < 1.0e-6) ? 1.0e-6 : sum);
-            double pp = sd.BL[c] + right, qq = sd.BL[c] - right, rr = pp;
-            if (projectSPD) make_pd2(pp, qq, rr);
-            bd0[c] = pp;
-            bd1[c] = rr;
-            bo[c] = qq;
-        }
-        a00 = w * sd.A[0]; a01 = w * sd.A[1]; a02 = w * sd.A[2]; a11 = w * sd.A[3]; a12 = w * sd.A[4]; a22 = w * sd.A[5];
-        d01 = w * bd0[0]; d10 = w * bd1[0]; o01 = w * bo[0];
-        d12 = w * bd0[1]; d21 = w * bd1[1]; o12 = w * bo[1];
-        d20 = w * bd0[2]; d02 = w * bd1[2]; o02 = w * bo[2];
-#pragma unroll
-        for (int l = 0; l < 3; ++l) {
-            double s0 = 0.0;
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                const double v = in.A(a, 0) * V(0, l) + in.A(a, 1) * V(1, l) + in.A(a, 2) * V(2, l);
-                sW[(3 * (a + 1) + l) * kHessTile + threadIdx.x] = v;
-                s0 -= v;
-            }
-            sW[l * kHessTile + threadIdx.x] = s0;
-        }
-    }
-#pragma unroll 1
-    for (int slot = 0; slot < 10; ++slot) {
-        const int a = c_slot_a[slot], b = c_slot_b[slot], o = c_slot_o[slot];
-        const int len = (a == b) ? 6 : 9;
-        double* buf = sHb[slot & 1];
-        if (active) {
-            const double wa0 = sW[(3 * a) * kHessTile + threadIdx.x], wa1 = sW[(3 * a + 1) * kHessTile + threadIdx.x], wa2 = sW[(3 * a + 2) * kHessTile + threadIdx.x];
-            const double wb0 = sW[(3 * b) * kHessTile + threadIdx.x], wb1 = sW[(3 * b + 1) * kHessTile + threadIdx.x], wb2 = sW[(3 * b + 2) * kHessTile + threadIdx.x];
-            M3 Ht;
-            Ht(0, 0) = a00 * wa0 * wb0 + d01 * wa1 * wb1 + d02 * wa2 * wb2;
-            Ht(1, 1) = a11 * wa1 * wb1 + d10 * wa0 * wb0 + d12 * wa2 * wb2;
-            Ht(2, 2) = a22 * wa2 * wb2 + d20 * wa0 * wb0 + d21 * wa1 * wb1;
-            Ht(0, 1) = a01 * wa0 * wb1 + o01 * wa1 * wb0;
-            Ht(1, 0) = a01 * wa1 * wb0 + o01 * wa0 * wb1;
-            Ht(0, 2) = a02 * wa0 * wb2 + o02 * wa2 * wb0;
-            Ht(2, 0) = a02 * wa2 * wb0 + o02 * wa0 * wb2;
-            Ht(1, 2) = a12 * wa1 * wb2 + o12 * wa2 * wb1;
-            Ht(2, 1) = a12 * wa2 * wb1 + o12 * wa1 * wb2;
-            M3 Tm;
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int m = 0; m < 3; ++m) Tm(i, m) = U(i, 0) * Ht(0, m) + U(i, 1) * Ht(1, m) + U(i, 2) * Ht(2, m);
-            double h[9];
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int r = 0; r < 3; ++r) h[3 * i + r] = Tm(i, 0) * U(r, 0) + Tm(i, 1) * U(r, 1) + Tm(i, 2) * U(r, 2);
-            double* oo = buf + threadIdx.x * len;
-            if (a == b) {
-                oo[0] = h[0]; oo[1] = h[1]; oo[2] = h[2]; oo[3] = h[4]; oo[4] = h[5]; oo[5] = h[8];
-            }
-            else {
-                const int va = a == 0 ? v0 : (a == 1 ? v1 : v2), vb = b == 1 ? v1 : (b == 2 ? v2 : v3);
-                if (va > vb) { // rows must belong to the smaller global vertex: store the transpose
-                    oo[0] = h[0]; oo[1] = h[3]; oo[2] = h[6]; oo[3] = h[1]; oo[4] = h[4]; oo[5] = h[7]; oo[6] = h[2]; oo[7] = h[5]; oo[8] = h[8];
-                }
-                else {
-#pragma unroll
-                    for (int q = 0; q < 9; ++q) oo[q] = h[q];
-                }
-            }
-        }
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            tma_store_tile(hblk + (size_t)blockIdx.x * (kHessTile * 78) + (size_t)o * kHessTile, buf, (unsigned)ntile * (unsigned)len * 8u);
-            asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
-        }
-        __syncthreads();
-    }
-    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (NEED_G) tma_store_tile(gcont + (size_t)tile0 * 12, sG, (unsigned)ntile * 12u * 8u);
-        asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
-    }
-}
-
-template <int ENERGY, bool NEED_G, bool NEED_H>
-__global__ void __launch_bounds__(kHessTile, 8) k_elastic_grad_hess(ElasticArgs p, double coef, int projectSPD,
-    double* __restrict__ gcont /* 12 per LOCAL tet */, double* __restrict__ hblk /* tile-major, 78 per LOCAL tet */)
-{
-    extern __shared__ __align__(128) double smem[];
+    double e_tet = 0.0; // fused energy: psi * vol of this thread's tet (computeEnergyVal at the same state shares the SVD, like the reference's cache)
+    extern __shared__ __align__(128) double smem_all[];
+    const int sub = threadIdx.x / kHessTile, tx = threadIdx.x % kHessTile; // tile of this CTA, thread inside the tile
+    constexpr int kSmemPerTile = kHessTile * ((NEED_H ? 18 : 0) + (NEED_G ? 12 : 0));
+    double* smem = smem_all + sub * kSmemPerTile;
     double* sHb[2] = { smem, smem + kHessTile * 9 };          // two slot buffers (ping-pong)
     double* sG = smem + (NEED_H ? 2 * kHessTile * 9 : 0);     // kHessTile * 12
     const int nLocal = p.n_list;
-    const int tile0 = blockIdx.x * kHessTile;
-    const int t = tile0 + threadIdx.x;
+    const int tileI = blockIdx.x * TILES + sub;
+    const int tile0 = tileI * kHessTile;
+    const int t = tile0 + tx;
     const bool active = t < nLocal;
-    const int ntile = min(kHessTile, nLocal - tile0);
+    const int ntile = max(min(kHessTile, nLocal - tile0), 0);
     TetIn in;
     M3 U;
     double W[4][3];
@@ -301,12 +164,16 @@ __global__ void __launch_bounds__(kHessTile, 8) k_elastic_grad_hess(ElasticArgs 
         def_grad(in, F);
         svd3<true>(F, U, s, V);
         const double w = coef * in.vol;
+        if (e_partials) {
+            const int vmin = min(min(in.v[0], in.v[1]), min(in.v[2], in.v[3]));
+            if (vmin >= p.e_row_lo && vmin < p.e_row_hi) e_tet = psi<ENERGY>(s, in.mu, in.lam) * in.vol;
+        }
 
         if (NEED_G) {
             M3 P;
             pk1<ENERGY>(F, U, s, V, in.mu, in.lam, P);
             // g[3(i+1)+k] = w * sum_j A(i,j) P(k,j) ; g[k] = -sum_i   (IglUtils.cpp:656-667)
-            double* g = sG + threadIdx.x * 12;
+            double* g = sG + tx * 12;
             double g0 = 0.0, g1 = 0.0, g2 = 0.0;
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
@@ -394,7 +261,7 @@ __global__ void __launch_bounds__(kHessTile, 8) k_elastic_grad_hess(ElasticArgs 
                     for (int i = 0; i < 3; ++i)
 #pragma unroll
                         for (int m = 0; m < 3; ++m) Tm(i, m) = U(i, 0) * Ht(0, m) + U(i, 1) * Ht(1, m) + U(i, 2) * Ht(2, m);
-                    double* oo = buf + threadIdx.x * len;
+                    double* oo = buf + tx * len;
                     if (a == b) {
                         int q = 0;
 #pragma unroll
@@ -416,8 +283,8 @@ __global__ void __launch_bounds__(kHessTile, 8) k_elastic_grad_hess(ElasticArgs 
                 // ship this slot: generic-proxy writes -> async-proxy fence -> CTA barrier -> one elected TMA store
                 asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
                 __syncthreads();
-                if (threadIdx.x == 0) {
-                    tma_store_tile(hblk + (size_t)blockIdx.x * (kHessTile * 78) + (size_t)o * kHessTile, buf, (unsigned)ntile * (unsigned)len * 8u);
+                if (tx == 0 && ntile > 0) {
+                    tma_store_tile(hblk + (size_t)tileI * (kHessTile * 78) + (size_t)o * kHessTile, buf, (unsigned)ntile * (unsigned)len * 8u);
                     asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory"); // the other buffer's store has been read out
                 }
                 __syncthreads();
@@ -427,9 +294,21 @@ __global__ void __launch_bounds__(kHessTile, 8) k_elastic_grad_hess(ElasticArgs 
     }
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     __syncthreads();
-    if (threadIdx.x == 0) {
-        if (NEED_G) tma_store_tile(gcont + (size_t)tile0 * 12, sG, (unsigned)ntile * 12u * 8u);
+    if (tx == 0) {
+        if (NEED_G && ntile > 0) tma_store_tile(gcont + (size_t)tile0 * 12, sG, (unsigned)ntile * 12u * 8u);
         asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+    }
+    if (e_partials) { // fixed-order CTA sum: warp sums, then warp 0 adds them in warp order
+        __shared__ double sE[2 * TILES];
+        const double ws = warp_sum(e_tet);
+        if ((threadIdx.x & 31) == 0) sE[threadIdx.x >> 5] = ws;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double acc = 0.0;
+#pragma unroll
+            for (int i = 0; i < 2 * TILES; ++i) acc += sE[i];
+            e_partials[blockIdx.x] = acc;
+        }
     }
 }
 
@@ -716,42 +595,46 @@ void elastic_energy(const ElasticArgs& p, double* e_per_tet, double* partials, d
 int elastic_energy_blocks(int nTets) { return (nTets + 255) / 256; }
 void reduce_sum(const double* partials, int n, double scale, double* out, cudaStream_t st) { k_reduce_sum<<<1, 1024, 0, st>>>(partials, n, scale, out); }
 
+static int tet_tiles()
+{
+    static const int tiles = [] { const char* e = std::getenv("IPCGPU_TET_TILES"); const int v = e ? std::atoi(e) : 1; return (v == 1 || v == 2 || v == 4) ? v : 1; }();
+    return tiles; // 64-tet tiles per CTA of the gradient/Hessian kernel (1, 2 and 4 measured equal on C5: 0.307 / 0.311 / 0.305 ms)
+}
+int elastic_grad_hess_blocks(int n_list)
+{
+    const int nb = (n_list + kHessTile - 1) / kHessTile, t = tet_tiles();
+    return (nb + t - 1) / t;
+}
 template <int ENERGY, bool G, bool H>
-static void launch_gh(const ElasticArgs& p, double coef, int projectSPD, double* gcont, double* hblk, cudaStream_t st)
+static void launch_gh(const ElasticArgs& p, double coef, int projectSPD, double* gcont, double* hblk, cudaStream_t st, double* e_partials)
 {
     const int n = p.n_list;
     if (n <= 0) return;
     const int nb = (n + kHessTile - 1) / kHessTile;
-    static const int variant = [] { const char* e = std::getenv("IPCGPU_TET_KERNEL"); return e ? std::atoi(e) : 0; }(); // 0 = unrolled (default: measured 2 % faster), 1 = rolled
-    if (H && variant == 1) {
-        const size_t smem_r = (size_t)kHessTile * 8 * (18 + 12 + 12);
-        static bool attr_r = false;
-        if (!attr_r) {
-            cudaFuncSetAttribute(k_elastic_grad_hess_rolled<ENERGY, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r);
-            attr_r = true;
-        }
-        k_elastic_grad_hess_rolled<ENERGY, G><<<nb, kHessTile, smem_r, st>>>(p, coef, projectSPD, gcont, hblk);
-        return;
-    }
     const size_t smem = (size_t)kHessTile * 8 * ((H ? 18 : 0) + (G ? 12 : 0));
+    const int tiles = tet_tiles();
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(k_elastic_grad_hess<ENERGY, G, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_elastic_grad_hess<ENERGY, G, H, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_elastic_grad_hess<ENERGY, G, H, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * smem));
+        cudaFuncSetAttribute(k_elastic_grad_hess<ENERGY, G, H, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * smem));
         attr_set = true;
     }
-    k_elastic_grad_hess<ENERGY, G, H><<<nb, kHessTile, smem, st>>>(p, coef, projectSPD, gcont, hblk);
+    if (tiles == 1) k_elastic_grad_hess<ENERGY, G, H, 1><<<nb, kHessTile, smem, st>>>(p, coef, projectSPD, gcont, hblk, e_partials);
+    else if (tiles == 2) k_elastic_grad_hess<ENERGY, G, H, 2><<<(nb + 1) / 2, 2 * kHessTile, 2 * smem, st>>>(p, coef, projectSPD, gcont, hblk, e_partials);
+    else k_elastic_grad_hess<ENERGY, G, H, 4><<<(nb + 3) / 4, 4 * kHessTile, 4 * smem, st>>>(p, coef, projectSPD, gcont, hblk, e_partials);
 }
-void elastic_grad_hess(const ElasticArgs& p, double coef, int projectSPD, bool need_g, bool need_h, double* gcont, double* hblk, cudaStream_t st)
+void elastic_grad_hess(const ElasticArgs& p, double coef, int projectSPD, bool need_g, bool need_h, double* gcont, double* hblk, cudaStream_t st, double* e_partials)
 {
     if (p.energy == 0) {
-        if (need_g && need_h) launch_gh<0, true, true>(p, coef, projectSPD, gcont, hblk, st);
-        else if (need_g) launch_gh<0, true, false>(p, coef, projectSPD, gcont, hblk, st);
-        else if (need_h) launch_gh<0, false, true>(p, coef, projectSPD, gcont, hblk, st);
+        if (need_g && need_h) launch_gh<0, true, true>(p, coef, projectSPD, gcont, hblk, st, e_partials);
+        else if (need_g) launch_gh<0, true, false>(p, coef, projectSPD, gcont, hblk, st, e_partials);
+        else if (need_h) launch_gh<0, false, true>(p, coef, projectSPD, gcont, hblk, st, e_partials);
     }
     else {
-        if (need_g && need_h) launch_gh<1, true, true>(p, coef, projectSPD, gcont, hblk, st);
-        else if (need_g) launch_gh<1, true, false>(p, coef, projectSPD, gcont, hblk, st);
-        else if (need_h) launch_gh<1, false, true>(p, coef, projectSPD, gcont, hblk, st);
+        if (need_g && need_h) launch_gh<1, true, true>(p, coef, projectSPD, gcont, hblk, st, e_partials);
+        else if (need_g) launch_gh<1, true, false>(p, coef, projectSPD, gcont, hblk, st, e_partials);
+        else if (need_h) launch_gh<1, false, true>(p, coef, projectSPD, gcont, hblk, st, e_partials);
     }
 }
 

@@ -41,12 +41,15 @@ struct ElasticArgs {
     const double* mu;
     const double* lam;
     int energy;              // 0 NH, 1 FCR
+    int e_row_lo, e_row_hi;  // fused energy of the gradient/Hessian kernel: a tet is counted by the rank that owns its smallest vertex
 };
 
 // elastic.cu
 void elastic_energy(const ElasticArgs& p, double* e_per_tet, double* partials, double coef, double* out, cudaStream_t st);
 int elastic_energy_blocks(int nTets);
-void elastic_grad_hess(const ElasticArgs& p, double coef, int projectSPD, bool need_g, bool need_h, double* gcont, double* hblk, cudaStream_t st);
+// e_partials != nullptr: the kernel also leaves one partial sum of psi * vol per CTA there (elastic_grad_hess_blocks of them)
+void elastic_grad_hess(const ElasticArgs& p, double coef, int projectSPD, bool need_g, bool need_h, double* gcont, double* hblk, cudaStream_t st, double* e_partials = nullptr);
+int elastic_grad_hess_blocks(int n_list);
 void gather_gradient(int nV, const int* inc_ptr, const int* inc, const double* gcont, const uint8_t* dbc, int projectDBC, int accumulate, double* g, cudaStream_t st);
 void assemble_csr(int nSlots, const int* slot_v, const int* slot_u, const int* slot_off, const int* con_ptr, const unsigned* con_src,
     const double* hblk, const uint8_t* dbc, int projectDBC, const double* mass, int accumulate, double* a, cudaStream_t st);

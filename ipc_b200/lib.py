@@ -39,6 +39,7 @@ SIGNATURES = {
     "ipcgpu_constraint_set_sizes": (C.c_int, [_ctxp, _ip, _ip, _ip]),
     "ipcgpu_ccd_debug_seed_bound": (C.c_int, [_ctxp, C.c_double]),
     "ipcgpu_download_range": (C.c_int, [_ctxp, C.c_int, C.c_uint64, C.c_uint64, _dp]),
+    "ipcgpu_download_range_async": (C.c_int, [_ctxp, C.c_int, C.c_uint64, C.c_uint64, _dp]),
     "ipcgpu_set_mesh": (C.c_int, [_ctxp, C.c_int, C.c_int, _dp, _ip, _dp, _dp, _dp, _dp, _dp, _u8p, C.c_int]),
     "ipcgpu_set_csr": (C.c_int, [_ctxp, C.c_int, _ip, _ip, C.c_int]),
     "ipcgpu_set_state": (C.c_int, [_ctxp, _dp]),
@@ -49,6 +50,7 @@ SIGNATURES = {
     "ipcgpu_elastic_gradient": (C.c_int, [_ctxp, C.c_double, C.c_int, C.c_int, _dp]),
     "ipcgpu_elastic_hessian": (C.c_int, [_ctxp, C.c_double, C.c_int, C.c_int, C.c_int, _dp]),
     "ipcgpu_elastic_grad_hess": (C.c_int, [_ctxp, C.c_double, C.c_int, C.c_int, C.c_int, _dp, _dp]),
+    "ipcgpu_elastic_energy_grad_hess": (C.c_int, [_ctxp, C.c_double, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp]),
     "ipcgpu_inversion_step": (C.c_int, [_ctxp, _dp, C.c_double, _dp]),
     "ipcgpu_set_surface": (C.c_int, [_ctxp, C.c_int, _ip, C.c_int, _ip, C.c_int, _ip, _ip]),
     "ipcgpu_set_pair_capacity": (C.c_int, [_ctxp, C.c_int]),
@@ -256,6 +258,12 @@ class Context:
     def elastic_grad_hess(self, coef, projectSPD=1, projectDBC=1, add_mass=0, g=None, a=None):
         self._ck(self.lib.ipcgpu_elastic_grad_hess(self.h, coef, projectSPD, projectDBC, add_mass, _d(g), _d(a)))
 
+    def elastic_energy_grad_hess(self, coef, projectSPD=1, projectDBC=1, add_mass=0, g=None, a=None, want_energy=False):
+        """fused computeEnergyVal + computeGradient + computePrecondMtr (one SVD per tet); returns E when want_energy"""
+        E = C.c_double()
+        self._ck(self.lib.ipcgpu_elastic_energy_grad_hess(self.h, coef, projectSPD, projectDBC, add_mass, C.byref(E) if want_energy else None, _d(g), _d(a)))
+        return E.value if want_energy else None
+
     def inversion_step(self, p, slack, alpha):
         """alpha=None: chained on the device (no synchronisation)"""
         a = C.c_double(alpha if alpha is not None else 0.0)
@@ -294,6 +302,10 @@ class Context:
         nC, nP, nK = C.c_int(), C.c_int(), C.c_int()
         self._ck(self.lib.ipcgpu_constraint_set_sizes(self.h, C.byref(nC), C.byref(nP), C.byref(nK)))
         return nC.value, nP.value, nK.value
+
+    def download_range_async(self, which, offset, out):
+        """out: a PinnedArray view; valid after the next fetch_iteration() / sync()"""
+        self._ck(self.lib.ipcgpu_download_range_async(self.h, which, int(offset), int(out.size), _d(out)))
 
     def download_range_into(self, which, offset, out):
         self._ck(self.lib.ipcgpu_download_range(self.h, which, int(offset), int(out.size), _d(out)))

@@ -177,3 +177,29 @@ def test_partial_tile_odd_tet_count(gpu_ctx, drop):
     H_ref = orc.Elastic(m).hessian_blocks(coef, 1)
     for t in range(m.nT):
         assert np.abs(orc.blocks78_to_dense(h78[t], m.T[t]) - H_ref[t]).max() <= 1e-10 * np.abs(H_ref[t]).max(), t
+
+
+def test_fused_energy_gradient_hessian_equals_the_separate_calls(gpu_ctx):
+    """ipcgpu_elastic_energy_grad_hess: the energy as a by-product of the gradient/Hessian kernel (one SVD per tet) equals
+    ipcgpu_elastic_energy and the oracle; gradient and CSR values are those of ipcgpu_elastic_grad_hess."""
+    for et in (0, 1):
+        V, T = M.grid_tets(9, 8, 7)
+        m = M.Mesh(V, T, energy=et)
+        M.deform(m, 3)
+        ctx = gpu_ctx
+        ctx.set_mesh(m.V_rest_soa, m.T_soa, m.restTriInv, m.vol, m.mu, m.lam, m.mass, m.dbc, m.energy)
+        ia, ja = m.csr_pattern(1)
+        ctx.set_csr(ia, ja, 1)
+        ctx.set_state(m.V_soa)
+        coef = 0.025 ** 2
+        E_sep = ctx.elastic_energy(coef)
+        g0, a0 = np.empty(3 * m.nV), np.empty(ja.size)
+        ctx.elastic_grad_hess(coef, 1, 1, 1, g0, a0)
+        g1, a1 = np.empty(3 * m.nV), np.empty(ja.size)
+        E_fused = ctx.elastic_energy_grad_hess(coef, 1, 1, 1, g1, a1, want_energy=True)
+        E_ref, _ = orc.Elastic(m).energy(coef)
+        assert abs(E_fused - E_sep) <= 1e-13 * abs(E_sep) and abs(E_fused - E_ref) <= 1e-10 * abs(E_ref)
+        assert np.array_equal(g0, g1) and np.array_equal(a0, a1)
+        # deferred form: the energy arrives with the fetch
+        ctx.elastic_energy_grad_hess(coef, 1, 1, 1, None, None)
+        assert abs(ctx.fetch_iteration().energy_elastic - E_fused) <= 1e-15 * abs(E_fused)
