@@ -236,6 +236,11 @@ def main():
     ctx.set_csr(ia, ja, 1)
     nnz = ja.size
     n_active, n_para, n_cand = len(mm), len(pa), len(cand)
+    if world > 1:  # message of the pair-list exchange: 4x the per-rank share of the contact set the pattern was just built from, at least 4096 pairs
+        xcap = 4096
+        while xcap < 4 * max(n_active, n_para) // world + 1024:
+            xcap *= 2
+        ctx.set_exchange_capacity(min(xcap, 1 << 16))
     ctx.set_contact_partition(1)  # timed steps: every rank builds and processes only its share of the contact sets
     ctx.set_canonical_order(0)    # the sets are consumed on the device: no need for the canonical sort (the reference's order is arbitrary too)
 

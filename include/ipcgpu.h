@@ -166,6 +166,11 @@ int ipcgpu_inversion_step(ipcgpu_ctx* ctx, const double* p_interleaved, double s
 int ipcgpu_set_surface(ipcgpu_ctx* ctx, int nSV, const int* SVI, int nSE, const int* SFEdges, int nSF, const int* SF_soa, const int* vCoDim);
 /* capacity (entries) of the device-side pair lists; default 2^20. IPCGPU_ERR_CAPACITY is returned when exceeded. */
 int ipcgpu_set_pair_capacity(ipcgpu_ctx* ctx, int capacity);
+/* Multi-rank, partitioned build (ipcgpu_set_contact_partition(1)): every rank ships its part of the active / mollified lists in ONE fixed-size
+ * message (sizes are device-resident, so the message cannot be sized per call); this is its capacity in pairs per rank and list (default and
+ * maximum 65,536 = 2.6 MB per rank).  A driver that knows the size of the contact set (it just rebuilt the sparsity pattern from it) sets a
+ * few times its per-rank share; exceeding it raises IPCGPU_ERR_CAPACITY at the fetch, never truncation. */
+int ipcgpu_set_exchange_capacity(ipcgpu_ctx* ctx, int pairs_per_rank);
 /* SelfCollisionHandler::computeConstraintSet (SelfCollisionHandler.cpp:2149-2478) with the broad phase of
  * SpatialHash::build/query* (SpatialHash.hpp:46-229, 375-421) done on the device. The sets stay on the device (they feed the
  * barrier_* calls and the partial CCD); sizes are returned.  Output order is canonical: every list sorted lexicographically. */

@@ -930,6 +930,15 @@ int ipcgpu_ccd_stats_timing(ipcgpu_ctx* ctx, uint64_t* longest_pair_cycles, uint
     return IPCGPU_OK;
 }
 
+int ipcgpu_set_exchange_capacity(ipcgpu_ctx* ctx, int pairs_per_rank)
+{
+    ++ctx->epoch; // graphs captured before this call are refused (the message buffers change)
+    REQUIRE(pairs_per_rank > 0, IPCGPU_ERR_ARG, "capacity must be positive");
+    ctx->exchange_capacity = pairs_per_rank;
+    if (ctx->surface_ready) return contact_alloc(ctx);
+    return IPCGPU_OK;
+}
+
 int ipcgpu_set_pair_capacity(ipcgpu_ctx* ctx, int capacity)
 {
     ++ctx->epoch; // graphs captured before this call are refused (buffers, partition or list order may change)

@@ -828,7 +828,7 @@ int contact_alloc(ipcgpu_ctx* ctx)
     // barrier stage needs no host-side size
     ok = ok && w.bHraw.reserve((size_t)cap * 144) && w.brows.reserve((size_t)cap * 4) && w.bpsd.reserve(cap) && w.bpartials.reserve(1024);
     if (ctx->nranks > 1) { // exchange of the pair lists between ranks (ipcgpu_set_contact_partition)
-        w.xcap = std::min(cap, 1 << 16);
+        w.xcap = std::max(1, std::min(std::min(cap, 1 << 16), ctx->exchange_capacity)); // pairs per rank and list in one message (ipcgpu_set_exchange_capacity)
         w.xstride = 1 + 2 * (size_t)w.xcap + (size_t)(w.xcap + 1) / 2;
         ok = ok && w.xsend.reserve(w.xstride) && w.xrecv.reserve(w.xstride * ctx->nranks) && w.gact.reserve(cap) && w.gpara.reserve(cap) && w.gpara_e.reserve(cap);
     }

@@ -154,6 +154,7 @@ struct ipcgpu_ctx {
     ipcgpu::DevBuf<int> SVI, SE, SF, vCoDim;
     bool has_codim = false, surface_ready = false;
     int pair_capacity = 1 << 20;
+    int exchange_capacity = 1 << 16; // pairs per rank and list in the fixed-size message of the cross-rank pair-list exchange
     bool canonical_order = true; // sort the contact lists lexicographically after the build
     bool partition_contact = false, lists_local = false; // multi-rank: build only this rank's share of the contact sets
     ipcgpu::ContactWork cw;

@@ -54,6 +54,7 @@ SIGNATURES = {
     "ipcgpu_inversion_step": (C.c_int, [_ctxp, _dp, C.c_double, _dp]),
     "ipcgpu_set_surface": (C.c_int, [_ctxp, C.c_int, _ip, C.c_int, _ip, C.c_int, _ip, _ip]),
     "ipcgpu_set_pair_capacity": (C.c_int, [_ctxp, C.c_int]),
+    "ipcgpu_set_exchange_capacity": (C.c_int, [_ctxp, C.c_int]),
     "ipcgpu_constraint_set": (C.c_int, [_ctxp, C.c_double, C.c_int, _ip, _ip, _ip]),
     "ipcgpu_set_contact_partition": (C.c_int, [_ctxp, C.c_int]),
     "ipcgpu_set_canonical_order": (C.c_int, [_ctxp, C.c_int]),
@@ -381,6 +382,9 @@ class Context:
 
     def set_contact_partition(self, enable):
         self._ck(self.lib.ipcgpu_set_contact_partition(self.h, int(enable)))
+
+    def set_exchange_capacity(self, pairs_per_rank):
+        self._ck(self.lib.ipcgpu_set_exchange_capacity(self.h, int(pairs_per_rank)))
 
     def set_pair_capacity(self, cap):
         self._ck(self.lib.ipcgpu_set_pair_capacity(self.h, int(cap)))

@@ -173,3 +173,41 @@ def test_captured_graph_replays_the_iteration_at_new_states(gpu_ctx):
     ctx.graph_destroy(gid)
     ctx.set_state(m.V_soa)
     ctx.set_canonical_order(1)
+
+
+def test_async_download_on_the_copy_stream_eager_and_captured(gpu_ctx):
+    """ipcgpu_download_range_async: the copy is forked behind what produced the buffer and joined by the fetch -- also as part of a graph"""
+    ctx = gpu_ctx
+    m, info = scenes.ball_pile(2, res=6, seed=1, height=2)
+    dt2 = 0.025 ** 2
+    ctx.set_mesh(m.V_rest_soa, m.T_soa, m.restTriInv, m.vol, m.mu, m.lam, m.mass, m.dbc, m.energy)
+    ia, ja = m.csr_pattern(1)
+    ctx.set_csr(ia, ja, 1)
+    ctx.set_state(m.V_soa)
+    hg, ha = L.PinnedArray(3 * m.nV), L.PinnedArray(ja.size)
+    g_ref, a_ref = np.empty(3 * m.nV), np.empty(ja.size)
+    ctx.elastic_grad_hess(dt2, 1, 1, 1, g_ref, a_ref)
+
+    def enqueue():
+        ctx.elastic_energy_grad_hess(dt2, 1, 1, 1, None, None)
+        ctx.download_range_async(L.BUF_GRADIENT, 0, hg.array)
+        ctx.download_range_async(L.BUF_CSR_VALUES, 100, ha.array[100:])
+        ctx.elastic_energy(dt2, 1, want=False)  # later work on the main stream next to the copies
+
+    hg.array[:] = 0; ha.array[:] = 0
+    enqueue()
+    ctx.fetch_iteration()
+    assert np.array_equal(hg.array, g_ref) and np.array_equal(ha.array[100:], a_ref[100:]) and not ha.array[:100].any()
+    ctx.capture_begin()
+    enqueue()
+    gid = ctx.capture_end()
+    V2 = m.V * 1.01
+    ctx.set_state(np.ascontiguousarray(V2.T).ravel())
+    hg.array[:] = 0; ha.array[:] = 0
+    ctx.graph_launch(gid)
+    ctx.fetch_iteration()
+    g2, a2 = np.empty(3 * m.nV), np.empty(ja.size)
+    ctx.elastic_grad_hess(dt2, 1, 1, 1, g2, a2)
+    assert np.array_equal(hg.array, g2) and np.array_equal(ha.array[100:], a2[100:]) and not np.array_equal(g2, g_ref)
+    ctx.graph_destroy(gid)
+    hg.free(); ha.free()
