@@ -68,29 +68,22 @@ DEV int upper_bound_u64(const unsigned long long* __restrict__ keys, int n, unsi
 // every partner starts in [q0-1, q1] per axis: at most 3x3 rows of <= 3 consecutive cells.  Entries are sorted by cell key; an
 // open-addressing table (cell key -> index of the first entry of that cell) replaces binary searches: the <= 27 cell lookups of a
 // query run on 27 lanes at once.
+constexpr int kGridCellsLog2 = 20;                  // the grid holds at most 2^20 cells (k_grid_params enlarges the cells beyond that)
+constexpr unsigned kGridCells = 1u << kGridCellsLog2;
 struct SortedGrid {
-    const unsigned* keys;           // sorted cell keys (cell | type bits: 32 bits, so the radix sort moves half the key bytes)
-    const int* ids;                 // primitive id per entry
-    const QEntry* ent;              // quantised box + id per entry, in sorted order (coalesced 16-byte candidate scan)
+    const unsigned* keys;   // per entry: type << 20 | cell, ascending (counting sort by cell: round 2, second half)
+    const int* ids;         // primitive id per entry
+    const QEntry* ent;      // quantised box + id per entry, in sorted order (coalesced 16-byte candidate scan)
     int n;
-    const unsigned* tab_key;        // hash table: cell key (0xffffffff = empty)
-    const int2* tab_range;          //             [first, last+1) entries of that cell in the sorted arrays
-    unsigned tab_mask;              // table size - 1 (power of two)
-    unsigned type_bit;              // triangles and edges share ONE sorted array and ONE table: the edge entries carry this bit above the cell key
+    const int* cell_off;    // DENSE table: entries of cell c of type t are positions [cell_off[t << 20 | c], cell_off[(t << 20 | c) + 1])
+    unsigned type_bit;      // type << 20: triangles 0, edges 1, surface vertices 2 share ONE sorted array and ONE table
 };
 
-DEV unsigned cell_hash(unsigned key) { return key * 2654435761u; }
-DEV int2 cell_lookup(const SortedGrid& sg, unsigned key)
+// entries registered in one cell: two adjacent words of the dense offset table (an empty cell is an empty range AT its place in the order)
+DEV int2 cell_lookup(const SortedGrid& sg, unsigned cell)
 {
-    key |= sg.type_bit;
-    unsigned h = cell_hash(key) & sg.tab_mask;
-    for (;;) {
-        const unsigned k = sg.tab_key[h];
-        const int2 r = sg.tab_range[h]; // issued together with the key: one memory latency per probe
-        if (k == key) return r;
-        if (k == 0xffffffffu) return make_int2(0x7fffffff, -1);
-        h = (h + 1) & sg.tab_mask;
-    }
+    const unsigned i = sg.type_bit | cell;
+    return make_int2(__ldg(sg.cell_off + i), __ldg(sg.cell_off + i + 1));
 }
 
 // conservative 16-bit quantisation of a box on the grid's lattice

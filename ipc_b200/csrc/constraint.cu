@@ -105,22 +105,34 @@ __global__ void k_grid_params(const unsigned long long* __restrict__ bounds, dou
     const double span = fmax(fmax(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
     h = fmax(h, span / 1024.0); // at most 1024 cells per axis
     if (!(h > 0.0)) h = 1.0;
-    atomicMax(&st->grid_axis_cells, (int)fmin(ceil(span / h) + 1.0, 1025.0)); // what this build would like
-    h = fmax(h, span / (double)((1 << axis_bits) - 2));                       // what the sort width allows
+    (void)axis_bits;
+    // the dense cell table holds kGridCells cells: enlarge the cells until the grid fits (any cell size >= the largest inflated box is valid)
+    int nx, ny, nz;
+    for (int it = 0; it < 64; ++it) {
+        const double inv = 1.0 / h;
+        nx = max(1, (int)floor((hi[0] - lo[0]) * inv) + 1);
+        ny = max(1, (int)floor((hi[1] - lo[1]) * inv) + 1);
+        nz = max(1, (int)floor((hi[2] - lo[2]) * inv) + 1);
+        if ((unsigned long long)nx * ny * nz <= (unsigned long long)kGridCells) break;
+        h *= 1.1;
+    }
+    atomicMax(&st->grid_axis_cells, max(nx, max(ny, nz)));
     g->ox = lo[0]; g->oy = lo[1]; g->oz = lo[2];
     g->inv_h = 1.0 / h;
     g->q_inv = 65533.0 / fmax(span, 1e-300);
-    g->nx = max(1, (int)floor((hi[0] - lo[0]) * g->inv_h) + 1);
-    g->ny = max(1, (int)floor((hi[1] - lo[1]) * g->inv_h) + 1);
-    g->nz = max(1, (int)floor((hi[2] - lo[2]) * g->inv_h) + 1);
+    g->nx = nx; g->ny = ny; g->nz = nz;
 }
 
-// one entry per primitive: the cell of the box's lower corner.  Triangles [0, nT) and edges [nT, nT + nE) go into ONE array and ONE sort:
-// the edge keys carry a type bit above the cell key, so the sorted array is "all triangles by cell, then all edges by cell".
-// Surface vertices (their points / swept boxes) follow as a third segment [nT + nE, nT + nE + nV) with the next type bit: the queries of
-// the cell-centric point-triangle kernel are then sorted by cell as well.
-__global__ void __launch_bounds__(256) k_emit(int nT, int nE, int nV, const Box* __restrict__ tboxes, const Box* __restrict__ eboxes, const Box* __restrict__ vboxes,
-    const Grid* __restrict__ gp, unsigned type_bit, unsigned* __restrict__ keys, int* __restrict__ vals)
+// Counting sort by cell (round 2, second half; before: CUB radix sort of (cell | type, id) pairs + an open-addressing cell table).
+// One entry per primitive, registered in the cell of its box's lower corner; key = type << 20 | cell with type 0 triangles, 1 edges,
+// 2 surface vertices, so the sorted array is "all triangles by cell, then all edges, then all vertices".
+//   k_cell_count   : key of every primitive, its slot inside the cell from an atomic counter;
+//   exclusive scan : counters -> DENSE offset table (two adjacent loads replace a hash probe per cell);
+//   k_cell_scatter : primitive -> position offset[key] + slot: key, id and the quantised box (QEntry) are written in one go.
+// The order of the entries inside a cell is whatever the atomics produced; nothing depends on it (pairs are reported from the entry with
+// the smaller position, whichever that is; the output lists are order-free already).
+__global__ void __launch_bounds__(256) k_cell_count(int nT, int nE, int nV, const Box* __restrict__ tboxes, const Box* __restrict__ eboxes, const Box* __restrict__ vboxes,
+    const Grid* __restrict__ gp, int* __restrict__ cnt, unsigned* __restrict__ key_of, int* __restrict__ slot_of)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nT + nE + nV) return;
@@ -129,39 +141,24 @@ __global__ void __launch_bounds__(256) k_emit(int nT, int nE, int nV, const Box*
     const int id = type == 2 ? i - nT - nE : (type == 1 ? i - nT : i);
     int c0[3], c1[3];
     cell_range(g, type == 2 ? vboxes[id] : (type == 1 ? eboxes[id] : tboxes[id]), c0, c1);
-    keys[i] = (unsigned)cell_key(g, c0[0], c0[1], c0[2]) | ((unsigned)type * type_bit);
-    vals[i] = id;
+    const unsigned key = ((unsigned)type << kGridCellsLog2) | (unsigned)cell_key(g, c0[0], c0[1], c0[2]);
+    key_of[i] = key;
+    slot_of[i] = atomicAdd(cnt + key, 1);
 }
-// heads and tails of the runs of the sorted key array go into the open-addressing table (key -> [first, last+1))
-__global__ void __launch_bounds__(256) k_build_cell_table(int n, const unsigned* __restrict__ keys, unsigned* __restrict__ tab_key, int2* __restrict__ tab_range,
-    unsigned mask)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const unsigned key = keys[i];
-    const bool head = (i == 0) || keys[i - 1] != key;
-    const bool tail = (i == n - 1) || keys[i + 1] != key;
-    if (!head && !tail) return;
-    unsigned h = cell_hash(key) & mask;
-    for (;;) {
-        const unsigned old = atomicCAS(tab_key + h, 0xffffffffu, key);
-        if (old == 0xffffffffu || old == key) {
-            if (head) tab_range[h].x = i;
-            if (tail) tab_range[h].y = i + 1;
-            return;
-        }
-        h = (h + 1) & mask;
-    }
-}
-// entries of the sorted grid: quantised box + id (see QEntry)
-__global__ void __launch_bounds__(256) k_gather_boxes(int nT, int nE, int nV, const Box* __restrict__ tboxes, const Box* __restrict__ eboxes, const Box* __restrict__ vboxes,
-    const int* __restrict__ ids, const Grid* __restrict__ gp, uint4* __restrict__ sorted)
+__global__ void __launch_bounds__(256) k_cell_scatter(int nT, int nE, int nV, const Box* __restrict__ tboxes, const Box* __restrict__ eboxes, const Box* __restrict__ vboxes,
+    const Grid* __restrict__ gp, const int* __restrict__ off, const unsigned* __restrict__ key_of, const int* __restrict__ slot_of, unsigned* __restrict__ keys,
+    int* __restrict__ ids, uint4* __restrict__ sorted)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nT + nE + nV) return;
-    const int id = ids[i];
-    const QBox q = quantize_box(*gp, i >= nT + nE ? vboxes[id] : (i >= nT ? eboxes[id] : tboxes[id])); // sorted array: triangles, then edges, then vertices
-    sorted[i] = make_uint4((unsigned)q.lo[0] | ((unsigned)q.lo[1] << 16), (unsigned)q.lo[2] | ((unsigned)q.hi[0] << 16), (unsigned)q.hi[1] | ((unsigned)q.hi[2] << 16), (unsigned)id);
+    const int type = i >= nT + nE ? 2 : (i >= nT ? 1 : 0);
+    const int id = type == 2 ? i - nT - nE : (type == 1 ? i - nT : i);
+    const unsigned key = key_of[i];
+    const int pos = off[key] + slot_of[i];
+    const QBox q = quantize_box(*gp, type == 2 ? vboxes[id] : (type == 1 ? eboxes[id] : tboxes[id]));
+    keys[pos] = key;
+    ids[pos] = id;
+    sorted[pos] = make_uint4((unsigned)q.lo[0] | ((unsigned)q.lo[1] << 16), (unsigned)q.lo[2] | ((unsigned)q.hi[0] << 16), (unsigned)q.hi[1] | ((unsigned)q.hi[2] << 16), (unsigned)id);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -279,7 +276,7 @@ __global__ void __launch_bounds__(32 * kCellPairWarps) k_cell_pairs_ee(const Gri
     int cl[3] = { 0, 0, 0 }, ch[3] = { 0, 0, 0 }; // conservative cell range of the inflated box
     if (valid) {
         const uint4 e = __ldg(ent + pos);
-        key = eg.keys[pos] & ~eg.type_bit;
+        key = eg.keys[pos] & (kGridCells - 1u);
         AEntry a;
         a.L01 = __vsubus2(e.x, rq2);                                  // lo0, lo1 - rq (saturating)
         a.H01 = __vaddus2(__funnelshift_r(e.y, e.z, 16), rq2);       // hi0, hi1 + rq
@@ -318,27 +315,21 @@ __global__ void __launch_bounds__(32 * kCellPairWarps) k_cell_pairs_ee(const Gri
         // rows at or behind the own cell: r = 0 own row (cells cx..xhi); then (y' in (cy, yhi], z' = cz); then (y' in [ylo, yhi], z' in (cz, zhi])
         const int nUp = max(yhi - cy, 0), nY = max(yhi - ylo + 1, 0), nZ = max(zhi - cz, 0);
         const int nRows = 1 + nUp + nY * nZ; // <= 1 + 1 + 4 = 6
-        // lane 4 r + dx looks up cell dx of row r
-        int2 mine = make_int2(0x7fffffff, -1);
-        {
-            const int r = lane >> 2, dx = lane & 3;
-            if (r < nRows) {
-                int y, z, xs;
-                if (r == 0) { y = cy; z = cz; xs = cx; }
-                else if (r <= nUp) { y = cy + r; z = cz; xs = xlo; }
-                else { const int q = r - 1 - nUp; z = cz + 1 + q / nY; y = ylo + q % nY; xs = xlo; }
-                if (xs + dx <= xhi) mine = cell_lookup(eg, (unsigned)cell_key(g, xs + dx, y, z));
+        // lane r < nRows: the run of row r = entries of its cells xs..xhi -- consecutive cells are consecutive in the sorted array, so the run is
+        // two loads from the dense offset table (first cell's start, last cell's end)
+        int rs = 0x7fffffff, re = -1;
+        if (lane < nRows) {
+            const int r = lane;
+            int y, z, xs;
+            if (r == 0) { y = cy; z = cz; xs = cx; }
+            else if (r <= nUp) { y = cy + r; z = cz; xs = xlo; }
+            else { const int q = r - 1 - nUp; z = cz + 1 + q / nY; y = ylo + q % nY; xs = xlo; }
+            if (xs <= xhi) {
+                rs = cell_lookup(eg, (unsigned)cell_key(g, xs, y, z)).x;
+                re = cell_lookup(eg, (unsigned)cell_key(g, xhi, y, z)).y;
             }
         }
-        // run of row L % 8 (rows 0..5): cells of one row are consecutive keys => consecutive entries
-        const int rr = lane & 7;
-        int rs = 0x7fffffff, re = -1;
-#pragma unroll
-        for (int dx = 0; dx < 4; ++dx) {
-            rs = min(rs, __shfl_sync(full, mine.x, (4 * rr + dx) & 31));
-            re = max(re, __shfl_sync(full, mine.y, (4 * rr + dx) & 31));
-        }
-        if (rr == 0) rs = max(rs, p_lo + 1); // own row: nothing at or before the run's first query is ever needed
+        if (lane == 0) rs = max(rs, p_lo + 1); // own row: nothing at or before the run's first query is ever needed
         const int rlen = (lane < 6 && lane < nRows && re > rs) ? re - rs : 0;
         int incl = rlen;
 #pragma unroll
@@ -407,7 +398,7 @@ __global__ void __launch_bounds__(32 * kCellPairWarps) k_cell_pairs_pt(const Gri
     int cl[3] = { 0, 0, 0 }, ch[3] = { 0, 0, 0 };
     if (valid) {
         const uint4 e = __ldg(ent + pos);
-        key = vg.keys[pos] & ~vg.type_bit;
+        key = vg.keys[pos] & (kGridCells - 1u);
         AEntry a;
         a.L01 = __vsubus2(e.x, rq2);
         a.H01 = __vaddus2(__funnelshift_r(e.y, e.z, 16), rq2);
@@ -443,30 +434,24 @@ __global__ void __launch_bounds__(32 * kCellPairWarps) k_cell_pairs_pt(const Gri
         const int zlo = max(max(lo[2], cz - 2), 0), zhi = min(min(hi[2], cz + 1), g.nz - 1);
         const int nY = max(yhi - ylo + 1, 0), nZ = max(zhi - zlo + 1, 0);
         const int nRows = nY * nZ; // <= 16
-        for (int rbase = 0; rbase < nRows; rbase += 8) { // cell-table lookups of 8 rows x 4 cells at a time
-            int2 mine = make_int2(0x7fffffff, -1);
-            {
-                const int r = rbase + (lane >> 2), dx = lane & 3;
-                if (r < nRows && xlo + dx <= xhi) mine = cell_lookup(tg, (unsigned)cell_key(g, xlo + dx, ylo + r % nY, zlo + r / nY));
+        {
+            // lane r < nRows (<= 16): the run of row r, two loads from the dense offset table
+            int rs = 0x7fffffff, re = -1;
+            if (lane < nRows && xlo <= xhi) {
+                const int y = ylo + lane % nY, z = zlo + lane / nY;
+                rs = cell_lookup(tg, (unsigned)cell_key(g, xlo, y, z)).x;
+                re = cell_lookup(tg, (unsigned)cell_key(g, xhi, y, z)).y;
             }
-            // run of the lane's row = [min start, max end) over its 4 cells (consecutive keys => consecutive entries)
-            int rs = mine.x, re = mine.y;
-#pragma unroll
-            for (int o = 1; o < 4; o <<= 1) {
-                rs = min(rs, __shfl_xor_sync(full, rs, o));
-                re = max(re, __shfl_xor_sync(full, re, o));
-            }
-            const int rows_here = min(nRows - rbase, 8);
-            // first chunk of row 0 of this group in flight
+            // first chunk of row 0 in flight
             int cs = __shfl_sync(full, rs, 0), ce = __shfl_sync(full, re, 0);
             uint4 en = make_uint4(0u, 0u, 0u, 0u);
             if (ce > cs && lane < ce - cs) en = __ldg(ent + cs + lane); // (an empty row is [INT_MAX, -1): no index arithmetic on it)
-            for (int r = 0; r < rows_here; ++r) {
+            for (int r = 0; r < nRows; ++r) {
                 const int s0 = cs, e0 = ce;
                 uint4 e = en;
-                if (r + 1 < rows_here) { // next row's first chunk
-                    cs = __shfl_sync(full, rs, 4 * (r + 1));
-                    ce = __shfl_sync(full, re, 4 * (r + 1));
+                if (r + 1 < nRows) { // next row's first chunk
+                    cs = __shfl_sync(full, rs, r + 1);
+                    ce = __shfl_sync(full, re, r + 1);
                     if (ce > cs && lane < ce - cs) en = __ldg(ent + cs + lane);
                 }
                 const int len = e0 > s0 ? e0 - s0 : 0;
@@ -832,17 +817,14 @@ int contact_alloc(ipcgpu_ctx* ctx)
         w.xstride = 1 + 2 * (size_t)w.xcap + (size_t)(w.xcap + 1) / 2;
         ok = ok && w.xsend.reserve(w.xstride) && w.xrecv.reserve(w.xstride * ctx->nranks) && w.gact.reserve(cap) && w.gpara.reserve(cap) && w.gpara_e.reserve(cap);
     }
-    unsigned tsz = 1024;
-    while (tsz < 2u * (unsigned)nAll) tsz <<= 1;
-    w.tab_mask = tsz - 1;
     w.bp_cap = (size_t)24 * std::max(std::max(nSE, nSV), 1024);
-    ok = ok && w.bp_pairs.reserve(2 * w.bp_cap) && w.ctab_key.reserve(tsz) && w.ctab_start.reserve(tsz);
+    ok = ok && w.bp_pairs.reserve(2 * w.bp_cap) && w.cell_cnt.reserve((size_t)3 * kGridCells + 8) && w.cell_off.reserve((size_t)3 * kGridCells + 8);
     if (!ok) {
         ctx->err = "contact workspace allocation failed";
         return IPCGPU_ERR_CUDA;
     }
     size_t b1 = 0, b2 = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, b1, (unsigned*)nullptr, (unsigned*)nullptr, (int*)nullptr, (int*)nullptr, (int)nAll);
+    cub::DeviceScan::ExclusiveSum(nullptr, b1, (int*)nullptr, (int*)nullptr, (int)(3 * kGridCells + 1)); // dense cell-offset table
     cub::DeviceRadixSort::SortPairs(nullptr, b2, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int*)nullptr, (int*)nullptr, 4 * cap);
     if (!w.cub_tmp.reserve(std::max(b1, b2) + 256)) {
         ctx->err = "cub temp allocation failed";
@@ -861,18 +843,17 @@ static int build_grids(ipcgpu_ctx* ctx, int nT, int nE, int nV)
     const int n = nT + nE + nV;
     w.built_vertices = nV;
     if (n <= 0) return 0;
-    const unsigned type_bit = 1u << (3 * w.axis_bits);
-    k_emit<<<nblk(n, 256), 256, 0, st>>>(nT, nE, nV, w.tbox.p, w.ebox.p, w.vbox.p, w.grid.p, type_bit, w.key_tmp.p, w.val_tmp.p);
+    const size_t nTab = (size_t)3 * kGridCells + 1;
+    cudaMemsetAsync(w.cell_cnt.p, 0, nTab * sizeof(int), st);
+    k_cell_count<<<nblk(n, 256), 256, 0, st>>>(nT, nE, nV, w.tbox.p, w.ebox.p, w.vbox.p, w.grid.p, w.cell_cnt.p, w.key_tmp.p, w.val_tmp.p);
     size_t bytes = w.cub_tmp.n;
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(w.cub_tmp.p, bytes, w.key_tmp.p, w.ckeys.p, w.val_tmp.p, w.cvals.p, n, 0, 3 * w.axis_bits + 2, st); // cells < 2^(3 axis_bits), + 2 type bits
+    cudaError_t e = cub::DeviceScan::ExclusiveSum(w.cub_tmp.p, bytes, w.cell_cnt.p, w.cell_off.p, (int)nTab, st);
     if (e != cudaSuccess) {
-        ctx->err = std::string("cub grid sort: ") + cudaGetErrorString(e);
+        ctx->err = std::string("cub cell-offset scan: ") + cudaGetErrorString(e);
         return IPCGPU_ERR_CUDA;
     }
-    k_gather_boxes<<<nblk(n, 256), 256, 0, st>>>(nT, nE, nV, w.tbox.p, w.ebox.p, w.vbox.p, w.cvals.p, w.grid.p, reinterpret_cast<uint4*>(w.centries.p));
-    cudaMemsetAsync(w.ctab_key.p, 0xff, (size_t)(w.tab_mask + 1) * sizeof(unsigned), st);
-    k_build_cell_table<<<nblk(n, 256), 256, 0, st>>>(n, w.ckeys.p, w.ctab_key.p, w.ctab_start.p, w.tab_mask);
-    w.built_axis_bits = w.axis_bits;
+    k_cell_scatter<<<nblk(n, 256), 256, 0, st>>>(nT, nE, nV, w.tbox.p, w.ebox.p, w.vbox.p, w.grid.p, w.cell_off.p, w.key_tmp.p, w.val_tmp.p, w.ckeys.p, w.cvals.p,
+        reinterpret_cast<uint4*>(w.centries.p));
     ctx->launches += 4;
     return 0;
 }
@@ -880,18 +861,18 @@ static int build_grids(ipcgpu_ctx* ctx, int nT, int nE, int nV)
 SortedGrid tri_grid(const ipcgpu_ctx* ctx)
 {
     const ContactWork& w = ctx->cw;
-    return SortedGrid{ w.ckeys.p, w.cvals.p, w.centries.p, ctx->nSF, w.ctab_key.p, w.ctab_start.p, w.tab_mask, 0u };
+    return SortedGrid{ w.ckeys.p, w.cvals.p, w.centries.p, ctx->nSF, w.cell_off.p, 0u };
 }
 SortedGrid edge_grid(const ipcgpu_ctx* ctx)
 {
     const ContactWork& w = ctx->cw;
-    return SortedGrid{ w.ckeys.p, w.cvals.p, w.centries.p, ctx->nSE, w.ctab_key.p, w.ctab_start.p, w.tab_mask, 1u << (3 * w.built_axis_bits) };
+    return SortedGrid{ w.ckeys.p, w.cvals.p, w.centries.p, ctx->nSE, w.cell_off.p, 1u << kGridCellsLog2 };
 }
 
 SortedGrid vertex_grid(const ipcgpu_ctx* ctx) // surface-vertex entries [nSF + nSE, nSF + nSE + built_vertices) of the combined sorted array
 {
     const ContactWork& w = ctx->cw;
-    return SortedGrid{ w.ckeys.p, w.cvals.p, w.centries.p, w.built_vertices, w.ctab_key.p, w.ctab_start.p, w.tab_mask, 2u << (3 * w.built_axis_bits) };
+    return SortedGrid{ w.ckeys.p, w.cvals.p, w.centries.p, w.built_vertices, w.cell_off.p, 2u << kGridCellsLog2 };
 }
 
 SurfArgs surf_args(const ipcgpu_ctx* ctx)

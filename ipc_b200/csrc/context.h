@@ -51,9 +51,7 @@ struct ContactWork {
     DevBuf<int4> act, dup, para, tmp4;
     DevBuf<int2> para_e, cand, tmp2;
     DevBuf<unsigned char> cub_tmp;
-    DevBuf<unsigned> ctab_key;  // ONE cell hash table for both grids (key = cell | type bit)
-    DevBuf<int2> ctab_start;    // [first, last+1) entry range per table slot (positions in the combined sorted array)
-    unsigned tab_mask = 0;
+    DevBuf<int> cell_cnt, cell_off; // dense per-(type, cell) counters and their exclusive prefix sum: entry range of a cell = two adjacent offsets
     DevBuf<int2> bp_pairs; // broad-phase pair lists (PT then EE), bp_cap each
     size_t bp_cap = 0;
     int cap = 0;
