@@ -1259,7 +1259,7 @@ __global__ void __launch_bounds__(32 * kGrpWarpsPerCta, 4) k_ti_groups(NarrowArg
 
 // stage 1.5: one THREAD per surviving pair with a small private level buffer; pairs whose search outgrows it are deferred
 constexpr int kThreadCap = 12;
-template <int CAP, int OCC>
+template <int CAP, int OCC, bool SMEM = false>
 __global__ void __launch_bounds__(128, OCC) k_ti_stage15(NarrowArgs a, const unsigned* __restrict__ survivors, const unsigned* __restrict__ nSurvPtr,
     unsigned* __restrict__ deferred, unsigned* __restrict__ nDeferred, long long budget, unsigned long long* __restrict__ min_ord, int* __restrict__ warn)
 {
@@ -1276,7 +1276,18 @@ __global__ void __launch_bounds__(128, OCC) k_ti_stage15(NarrowArgs a, const uns
             int v[4];
             TiPair P;
             load_pair(a.s, a.dir, a.cand[idx], vf, v, P);
-            DBox bufA[CAP], bufB[CAP];
+            // level buffers: in LOCAL memory they cost ~20 % of this kernel's stall samples (ncu source view: the flag test and the
+            // integer->double conversions right behind the box loads; 100 KB of stack per CTA thrashes the L1).  SMEM = true keeps them in
+            // shared memory, one padded slab per thread ((CAP * 32 + 8)-byte stride: the lanes' 64-bit words fall into distinct bank pairs).
+            DBox lA[SMEM ? 1 : CAP], lB[SMEM ? 1 : CAP];
+            DBox* bufA = lA;
+            DBox* bufB = lB;
+            if (SMEM) {
+                extern __shared__ __align__(16) unsigned char s_lvl[];
+                constexpr int kSlab = CAP * (int)sizeof(DBox) + 8;
+                bufA = reinterpret_cast<DBox*>(s_lvl + (size_t)threadIdx.x * kSlab);
+                bufB = reinterpret_cast<DBox*>(s_lvl + (size_t)(blockDim.x + threadIdx.x) * kSlab);
+            }
             double toi;
             const int hit = pair_ccd<1>(vf, P, a, bufA, bufB, CAP, 0, toi, warn, nullptr, nullptr, budget);
             if (hit == 2) defer = true;
@@ -1402,6 +1413,11 @@ void cell_pairs_pt(const ipcgpu::Grid* gp, const ipcgpu::SortedGrid& vg, const i
     const ipcgpu::PairOut& out, cudaStream_t st);
 SortedGrid vertex_grid(const ipcgpu_ctx* ctx);
 
+static bool lvl_smem() // IPCGPU_TI_LVL_SMEM=1: level buffers of the thread pass in shared memory
+{
+    static const bool v = [] { const char* e = std::getenv("IPCGPU_TI_LVL_SMEM"); return e ? std::atoi(e) != 0 : false; }();
+    return v;
+}
 constexpr int kStage2WarpsPerCta = 4;
 constexpr int kStage2Ctas = 148 * 6; // persistent: 6 CTAs x 4 warps per SM
 constexpr int kLevelCap = 4096;      // boxes per BFS level buffer (2 buffers per warp)
@@ -1476,7 +1492,23 @@ int ccd_narrow(ipcgpu_ctx* ctx, const int2* cand, const int* n32, const unsigned
             static const long long budgetA = [] { const char* e = std::getenv("IPCGPU_TI_BUDGET"); return e ? std::atoll(e) : 24ll; }(); // boxes a thread may evaluate before it hands its pair on
             // (C5 after the code-size refactor, narrow phase per iteration: 10 -> 1.33 ms, 16 -> 1.11, 24 -> 1.05, 32 -> 1.09, 64 -> 1.23, 128 -> 1.42)
             static const int occA = [] { const char* e = std::getenv("IPCGPU_TI_OCC"); return e ? std::atoi(e) : 2; }(); // CTAs/SM the thread pass is compiled for (2: 255 regs, 3: 168 regs + spills)
+            static const int capA = [] { const char* e = std::getenv("IPCGPU_TI_CAP"); return e ? std::atoi(e) : kThreadCap; }(); // boxes per level buffer of the thread pass
             if (occA == 3) k_ti_stage15<kThreadCap, 3><<<kSMs * 16, 128, 0, st>>>(a, w.surv.p, nSurv, w.surv2.p, nDefA, budgetA, &ist->ccd_ord, flags + 1);
+            else if (lvl_smem() && capA == 8) {
+                constexpr int bytes = 2 * 128 * (8 * (int)sizeof(DBox) + 8);
+                static bool attr = false;
+                if (!attr) { cudaFuncSetAttribute(k_ti_stage15<8, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); attr = true; }
+                k_ti_stage15<8, 2, true><<<kSMs * 16, 128, bytes, st>>>(a, w.surv.p, nSurv, w.surv2.p, nDefA, budgetA, &ist->ccd_ord, flags + 1);
+            }
+            else if (lvl_smem() && capA == kThreadCap) {
+                constexpr int bytes = 2 * 128 * (kThreadCap * (int)sizeof(DBox) + 8);
+                static bool attr = false;
+                if (!attr) { cudaFuncSetAttribute(k_ti_stage15<kThreadCap, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); attr = true; }
+                k_ti_stage15<kThreadCap, 2, true><<<kSMs * 16, 128, bytes, st>>>(a, w.surv.p, nSurv, w.surv2.p, nDefA, budgetA, &ist->ccd_ord, flags + 1);
+            }
+            else if (capA == 8) k_ti_stage15<8, 2><<<kSMs * 16, 128, 0, st>>>(a, w.surv.p, nSurv, w.surv2.p, nDefA, budgetA, &ist->ccd_ord, flags + 1);
+            else if (capA == 6) k_ti_stage15<6, 2><<<kSMs * 16, 128, 0, st>>>(a, w.surv.p, nSurv, w.surv2.p, nDefA, budgetA, &ist->ccd_ord, flags + 1);
+            else if (capA == 16) k_ti_stage15<16, 2><<<kSMs * 16, 128, 0, st>>>(a, w.surv.p, nSurv, w.surv2.p, nDefA, budgetA, &ist->ccd_ord, flags + 1);
             else k_ti_stage15<kThreadCap, 2><<<kSMs * 16, 128, 0, st>>>(a, w.surv.p, nSurv, w.surv2.p, nDefA, budgetA, &ist->ccd_ord, flags + 1);
             if (ti_mode == 2) { // the survivor list is dead after pass A: pass G's own deferrals go there
                 k_ti_groups<<<kSMs * 4, 32 * kGrpWarpsPerCta, 0, st>>>(a, w.surv2.p, nDefA, grp_work, w.surv.p, nDefB, &ist->ccd_ord, flags + 1);

@@ -1,6 +1,6 @@
 // abi_driver.cpp -- a C++ caller of the C ABI (include/ipcgpu.h), no Python in the loop: what the reference-side adapters do.
 // Reads a scene (binary, written by tests/test_gpu_cpp_driver.py), drives one Newton iteration's hot path through libipcgpu.so twice --
-// once with host outputs (synchronous calls), once device-resident with a single ipcgpu_fetch_iteration -- and writes the results back
+// once with host outputs (synchronous calls), once device-resident as a replayed CUDA graph with a single ipcgpu_fetch_iteration -- and writes the results back
 // for the test to compare with the oracle.   build: g++ -std=c++17 -I include tests/cpp/abi_driver.cpp -L ipc_b200 -lipcgpu -o abi_driver
 #include "ipcgpu.h"
 #include <cstdint>
@@ -68,19 +68,31 @@ int main(int argc, char** argv)
     CHECK(ipcgpu_check_inversion(ctx, &n_inv));
     CHECK(ipcgpu_intersection_free(ctx, &ok));
 
-    // ---- the same iteration device-resident: NULL outputs, one fetch --------------------------------------------------
-    CHECK(ipcgpu_constraint_set(ctx, dHat, 1, nullptr, nullptr, nullptr));
-    CHECK(ipcgpu_elastic_energy(ctx, dt2, 1, nullptr));
-    CHECK(ipcgpu_barrier_energy(ctx, dHat, kappa, nullptr));
-    CHECK(ipcgpu_elastic_grad_hess(ctx, dt2, 1, 1, 1, nullptr, nullptr));
-    CHECK(ipcgpu_barrier_gradient(ctx, dHat, kappa, nullptr));
-    CHECK(ipcgpu_barrier_hessian(ctx, dHat, kappa, 1, nullptr));
-    CHECK(ipcgpu_step_bound_set(ctx, 1.0));
-    CHECK(ipcgpu_inversion_step(ctx, nullptr, 0.2, nullptr));
-    CHECK(ipcgpu_ccd_partial_ti(ctx, nullptr, tol, evf, eee, nullptr));
-    CHECK(ipcgpu_hash_build_swept(ctx, nullptr, nullptr, voxel));
-    CHECK(ipcgpu_ccd_full_ti(ctx, tol, evf, eee, nullptr, nullptr));
+    // ---- the same iteration device-resident, the way a Newton loop runs it: NULL outputs everywhere, the sequence captured ONCE into a CUDA
+    // graph (after one eager run) and replayed with one launch + one fetch per iteration -------------------------------------------------
+    auto enqueue = [&]() -> int {
+        CHECK(ipcgpu_constraint_set(ctx, dHat, 1, nullptr, nullptr, nullptr));
+        CHECK(ipcgpu_barrier_energy(ctx, dHat, kappa, nullptr));
+        CHECK(ipcgpu_elastic_energy_grad_hess(ctx, dt2, 1, 1, 1, nullptr, nullptr, nullptr)); // computeEnergyVal + computeGradient + computePrecondMtr, one SVD per tet
+        CHECK(ipcgpu_barrier_gradient(ctx, dHat, kappa, nullptr));
+        CHECK(ipcgpu_barrier_hessian(ctx, dHat, kappa, 1, nullptr));
+        CHECK(ipcgpu_step_bound_set(ctx, 1.0));
+        CHECK(ipcgpu_inversion_step(ctx, nullptr, 0.2, nullptr));
+        CHECK(ipcgpu_ccd_partial_ti(ctx, nullptr, tol, evf, eee, nullptr));
+        CHECK(ipcgpu_hash_build_swept(ctx, nullptr, nullptr, voxel));
+        CHECK(ipcgpu_ccd_full_ti(ctx, tol, evf, eee, nullptr, nullptr));
+        return 0;
+    };
     ipcgpu_iteration it;
+    if (enqueue()) return 1; // eager once (lazy allocations)
+    CHECK(ipcgpu_fetch_iteration(ctx, &it));
+    int graph = -1;
+    CHECK(ipcgpu_capture_begin(ctx));
+    if (enqueue()) return 1;
+    CHECK(ipcgpu_capture_end(ctx, &graph));
+    CHECK(ipcgpu_set_state(ctx, V.data()));      // what changes between iterations travels through device memory
+    CHECK(ipcgpu_set_search_dir(ctx, p.data()));
+    CHECK(ipcgpu_graph_launch(ctx, graph));
     CHECK(ipcgpu_fetch_iteration(ctx, &it));
     std::vector<double> g2(3 * (size_t)nV), a2(nnz);
     CHECK(ipcgpu_download(ctx, IPCGPU_BUF_GRADIENT, g2.data(), g2.size()));
