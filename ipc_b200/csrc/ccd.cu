@@ -1413,9 +1413,9 @@ void cell_pairs_pt(const ipcgpu::Grid* gp, const ipcgpu::SortedGrid& vg, const i
     const ipcgpu::PairOut& out, cudaStream_t st);
 SortedGrid vertex_grid(const ipcgpu_ctx* ctx);
 
-static bool lvl_smem() // IPCGPU_TI_LVL_SMEM=1: level buffers of the thread pass in shared memory
+static bool lvl_smem() // level buffers of the thread pass in shared memory (IPCGPU_TI_LVL_SMEM=0: thread-local memory)
 {
-    static const bool v = [] { const char* e = std::getenv("IPCGPU_TI_LVL_SMEM"); return e ? std::atoi(e) != 0 : false; }();
+    static const bool v = [] { const char* e = std::getenv("IPCGPU_TI_LVL_SMEM"); return e ? std::atoi(e) != 0 : true; }();
     return v;
 }
 constexpr int kStage2WarpsPerCta = 4;
@@ -1492,7 +1492,8 @@ int ccd_narrow(ipcgpu_ctx* ctx, const int2* cand, const int* n32, const unsigned
             static const long long budgetA = [] { const char* e = std::getenv("IPCGPU_TI_BUDGET"); return e ? std::atoll(e) : 24ll; }(); // boxes a thread may evaluate before it hands its pair on
             // (C5 after the code-size refactor, narrow phase per iteration: 10 -> 1.33 ms, 16 -> 1.11, 24 -> 1.05, 32 -> 1.09, 64 -> 1.23, 128 -> 1.42)
             static const int occA = [] { const char* e = std::getenv("IPCGPU_TI_OCC"); return e ? std::atoi(e) : 2; }(); // CTAs/SM the thread pass is compiled for (2: 255 regs, 3: 168 regs + spills)
-            static const int capA = [] { const char* e = std::getenv("IPCGPU_TI_CAP"); return e ? std::atoi(e) : kThreadCap; }(); // boxes per level buffer of the thread pass
+            static const int capA = [] { const char* e = std::getenv("IPCGPU_TI_CAP"); return e ? std::atoi(e) : 8; }(); // boxes per level buffer of the thread pass
+            // (C5, narrow phase per iteration: local memory 12 boxes 1.044 ms, 8 boxes 1.035, 6 boxes 1.024; shared memory 12 boxes 1.029, 8 boxes 1.006)
             if (occA == 3) k_ti_stage15<kThreadCap, 3><<<kSMs * 16, 128, 0, st>>>(a, w.surv.p, nSurv, w.surv2.p, nDefA, budgetA, &ist->ccd_ord, flags + 1);
             else if (lvl_smem() && capA == 8) {
                 constexpr int bytes = 2 * 128 * (8 * (int)sizeof(DBox) + 8);
