@@ -26,14 +26,41 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ALG_BYTES_PER_TET = 208 + 624 + 96  # read stencil+material, write 78 upper-triangular scalars + 12 gradient scalars
-# dram__bytes_read.sum + dram__bytes_write.sum of k_elastic_grad_hess<NH,g,H> from the `ncu --set full` capture of this same
-# command (profiles/r01b_prof_k_elastic_grad_hess.summary.csv: 117.7 MB + 727.7 MB over 1,002,000 tets)
-NCU_DRAM_BYTES_PER_TET = (117.712128e6 + 727.696128e6) / 1002000
 ALG_BYTES_PER_CCD_CANDIDATE = 208  # 8 B candidate + 4 vertices x (x, p) x 24 B + 8 B result
-NCU_TRAFFIC_SOURCE = "ncu --set full, profiles/r01b_prof_k_elastic_grad_hess.summary.csv (bytes per tet x tets this rank assembles)"
-# figures of the committed ncu captures that go with the roofline objects (see profiles/)
-NCU_TET = {"fp64_pipe_pct": 50.5, "issue_slots_pct": 38.0, "warps_active_pct": 23.7, "source": "profiles/r01b_prof_k_elastic_grad_hess.summary.csv"}
-NCU_TI = {"kernel": "k_ti_stage2", "fp64_pipe_pct": 10.7, "issue_slots_pct": 22.5, "warps_active_pct": 12.0, "source": "profiles/r01b_prof_k_ti_stage2.summary.csv"}
+
+
+def ncu_summary(name):
+    """figures of a committed `ncu --set full` capture (profiles/<name>.summary.csv, written by profiles/summarize.py from the .ncu-rep of the
+    same bench command): DRAM bytes per launch, FP64-pipe / issue-slot / active-warp percentages, duration"""
+    path = os.path.join(ROOT, "profiles", name + ".summary.csv")
+    out = {"source": "profiles/" + name + ".summary.csv"}
+    try:
+        import csv
+        rows = {r[0]: (r[1], r[2]) for r in csv.reader(open(path)) if len(r) >= 3}
+    except OSError:
+        return None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+    def val(key):
+        unit, v = rows.get(key, ("", ""))
+        try:
+            return float(v) * scale.get(unit, 1.0)
+        except ValueError:
+            return None
+    rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
+    out["dram_bytes"] = (rd + wr) if rd is not None and wr is not None else None
+    out["fp64_pipe_pct"] = val("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active")
+    out["issue_slots_pct"] = val("sm__issue_active.avg.pct_of_peak_sustained_elapsed")
+    out["warps_active_pct"] = val("sm__warps_active.avg.pct_of_peak_sustained_active")
+    out["duration_us"] = val("gpu__time_duration.sum")
+    out["grid"] = rows.get("Grid Size", ("", ""))[1]
+    return out
+
+
+# committed captures of the dominant kernels (profiles/capture_r02.sh); the round-1 captures are the fallback
+NCU_TET = ncu_summary("r02_prof_k_elastic_grad_hess") or ncu_summary("r01b_prof_k_elastic_grad_hess")
+NCU_ASM = ncu_summary("r02_prof_k_assemble_csr")
+NCU_TI = {k: ncu_summary("r02_prof_" + k) or ncu_summary("r02l_prof_" + k) for k in ("k_ti_stage15", "k_ti_stage2")}
 DT2 = 0.025 ** 2
 
 
@@ -451,11 +478,16 @@ def main():
             "stage_ms": {k: v[0] / args.steps for k, v in prof.items()},
             "sum_stage_ms": sum(v[0] for k, v in prof.items() if k != "ccd_root_filter") / args.steps,
             "roofline": {"bound": "hbm", "kernel": "k_elastic_grad_hess<NH,g,H>", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                         "frac": achieved / peak_gbs, "traffic": NCU_DRAM_BYTES_PER_TET * local_tets, "peak_source": peak_src,
+                         "frac": achieved / peak_gbs, "traffic": (NCU_TET["dram_bytes"] / m.nT * local_tets) if NCU_TET and NCU_TET.get("dram_bytes") else None,
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_tet": ALG_BYTES_PER_TET, "algorithmic_bytes_per_launch": ALG_BYTES_PER_TET * local_tets,
-                         "traffic_source": NCU_TRAFFIC_SOURCE, "kernel_ms": tet_ms / max(tet_n, 1), "ncu": NCU_TET},
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the committed `ncu --set full` capture of this command at N = 1 "
+                                           "(1,000,246 tets per launch), scaled to the tets this rank assembles",
+                         "kernel_ms": tet_ms / max(tet_n, 1), "ncu": NCU_TET},
             "roofline_hessian_to_csr": {"bound": "hbm", "kernel": "k_elastic_grad_hess + k_gather_gradient + k_assemble_csr + k_diag_mass_dbc (what the CSR sink sees)",
-                                        "achieved": h2s, "peak": peak_gbs, "unit": "GB/s", "frac": h2s / peak_gbs, "traffic": None,
+                                        "achieved": h2s, "peak": peak_gbs, "unit": "GB/s", "frac": h2s / peak_gbs,
+                                        "traffic": ((NCU_TET["dram_bytes"] + NCU_ASM["dram_bytes"]) / m.nT * local_tets) if NCU_TET and NCU_ASM and NCU_TET.get("dram_bytes") and NCU_ASM.get("dram_bytes") else None,
+                                        "ncu_assemble": NCU_ASM,
                                         "algorithmic_bytes_per_tet": ALG_BYTES_PER_TET, "path_ms_per_step": h2s_ms},
             "roofline_ccd_narrow": {"bound": "hbm", "kernel": "k_ti_stage1 + k_ti_stage15 + k_ti_stage2 (whole Tight-Inclusion narrow phase, partial + full CCD)",
                                     "achieved": nar, "peak": peak_gbs, "unit": "GB/s", "frac": nar / peak_gbs, "traffic": None,

@@ -110,7 +110,8 @@ int ipcgpu_step_bound_set(ipcgpu_ctx* ctx, double alpha);
  * list sizes and step bounds -- they live in device memory and are read at replay time.  So one capture serves every Newton iteration
  * of a solve; capture again after ipcgpu_set_mesh / _set_surface / _set_csr / _set_*_capacity / _comm_init / _set_canonical_order /
  * _set_contact_partition (older graphs are refused with IPCGPU_ERR_STATE) or when dHat / kappa change.  Run the sequence once eagerly
- * before capturing it (lazy allocations).  Collective: with several ranks every rank captures and launches the same sequence.
+ * before capturing it (lazy allocations), with ipcgpu_set_canonical_order(ctx, 0): the canonical sort of the contact lists needs their sizes
+ * on the host.  Collective: with several ranks every rank captures and launches the same sequence.
  * ipcgpu_fetch_iteration stays outside the graph. */
 int ipcgpu_capture_begin(ipcgpu_ctx* ctx);
 int ipcgpu_capture_end(ipcgpu_ctx* ctx, int* graph_id);
@@ -157,6 +158,12 @@ int ipcgpu_elastic_grad_hess(ipcgpu_ctx* ctx, double coef, int projectSPD, int p
  * (one SVD per tet and iteration instead of two).  E NULL: the energy stays on the device (ipcgpu_fetch_iteration). */
 int ipcgpu_elastic_energy_grad_hess(ipcgpu_ctx* ctx, double coef, int projectSPD, int projectDBC, int add_mass,
     double* E, double* g, double* a);
+/* Layout of the per-tet Hessian blocks between the per-tet kernel and the CSR assembly.  0 (default): tile-major, one
+ * TMA bulk store per tile and block slot, the assembly gathers the 72-byte blocks through an index list; the only layout in which
+ * ipcgpu_download(IPCGPU_BUF_TET_HESSIANS) is available.  1: slot-major -- every block is written where the contributions of its CSR block
+ * slot are contiguous and the assembly streams them (measured slower on C5: the scattered block writes cost the per-tet kernel 0.13 ms, the
+ * streaming assembly wins 0.03 ms).  Results are identical bit for bit. */
+int ipcgpu_set_hessian_layout(ipcgpu_ctx* ctx, int layout);
 /* Energy::filterStepSize (Energy.cpp:565-581); alpha_inout == NULL: the device-resident step */
 int ipcgpu_inversion_step(ipcgpu_ctx* ctx, const double* p_interleaved, double slack, double* alpha_inout);
 

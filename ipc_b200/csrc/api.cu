@@ -186,6 +186,7 @@ static int build_maps(ipcgpu_ctx* ctx)
         uint64_t key;
         unsigned src;
         unsigned tet;
+        unsigned slot10; // block slot of the tet: 0..3 diagonal blocks, 4..9 the vertex pairs (0,1)(0,2)(0,3)(1,2)(1,3)(2,3)
     };
     std::vector<KS> ks;
     ks.reserve((size_t)10 * nL);
@@ -197,15 +198,15 @@ static int build_maps(ipcgpu_ctx* ctx)
         // tile-major block addresses (elastic.cu): (l/64)*64*78 + o*64 + (l%64)*len
         const unsigned tl = (unsigned)l, tile_base = (tl / 64u) * (64u * 78u), tin = tl % 64u;
         for (int a = 0; a < 4; ++a)
-            if (v[a] >= vb && v[a] < ve) ks.push_back({ ((uint64_t)v[a] << 32) | (uint32_t)v[a], tile_base + 6u * a * 64u + tin * 6u, tl });
+            if (v[a] >= vb && v[a] < ve) ks.push_back({ ((uint64_t)v[a] << 32) | (uint32_t)v[a], tile_base + 6u * a * 64u + tin * 6u, tl, (unsigned)a });
         for (int q = 0; q < 6; ++q) {
             const int lo = std::min(v[pa[q]], v[pb[q]]), hi = std::max(v[pa[q]], v[pb[q]]);
-            if (lo >= vb && lo < ve) ks.push_back({ ((uint64_t)lo << 32) | (uint32_t)hi, tile_base + (24u + 9u * q) * 64u + tin * 9u, tl });
+            if (lo >= vb && lo < ve) ks.push_back({ ((uint64_t)lo << 32) | (uint32_t)hi, tile_base + (24u + 9u * q) * 64u + tin * 9u, tl, 4u + (unsigned)q });
         }
     }
     std::sort(ks.begin(), ks.end(), [](const KS& a, const KS& b) { return a.key < b.key || (a.key == b.key && (a.tet < b.tet || (a.tet == b.tet && a.src < b.src))); });
     std::vector<int> sv, su, cptr;
-    std::vector<unsigned> csrc(std::max<size_t>(ks.size(), 1));
+    std::vector<unsigned> csrc(std::max<size_t>(ks.size(), 1)), cwho(std::max<size_t>(ks.size(), 1)); // cwho: 10 * local tet + block slot of the contribution
     for (size_t i = 0; i < ks.size(); ++i) {
         if (i == 0 || ks[i].key != ks[i - 1].key) {
             sv.push_back((int)(ks[i].key >> 32));
@@ -213,6 +214,7 @@ static int build_maps(ipcgpu_ctx* ctx)
             cptr.push_back((int)i);
         }
         csrc[i] = ks[i].src;
+        cwho[i] = ks[i].tet * 10u + ks[i].slot10;
     }
     cptr.push_back((int)ks.size());
     {
@@ -228,7 +230,7 @@ static int build_maps(ipcgpu_ctx* ctx)
         for (size_t i = 0; i < nS; ++i)
             if (sv[i] == su[i]) order.push_back((int)i);
         std::vector<int> sv2(nS), su2(nS), cptr2;
-        std::vector<unsigned> csrc2(csrc.size());
+        std::vector<unsigned> csrc2(csrc.size()), cwho2(cwho.size());
         cptr2.reserve(nS + 1);
         size_t pos = 0;
         for (size_t k = 0; k < nS; ++k) {
@@ -236,19 +238,38 @@ static int build_maps(ipcgpu_ctx* ctx)
             sv2[k] = sv[i];
             su2[k] = su[i];
             cptr2.push_back((int)pos);
-            for (int c = cptr[i]; c < cptr[i + 1]; ++c) csrc2[pos++] = csrc[c];
+            for (int c = cptr[i]; c < cptr[i + 1]; ++c) { csrc2[pos] = csrc[c]; cwho2[pos] = cwho[c]; ++pos; }
         }
         cptr2.push_back((int)pos);
-        sv.swap(sv2); su.swap(su2); cptr.swap(cptr2); csrc.swap(csrc2);
+        sv.swap(sv2); su.swap(su2); cptr.swap(cptr2); csrc.swap(csrc2); cwho.swap(cwho2);
+    }
+    // slot-major intermediate: the contributions of a slot are contiguous (ascending tet order inside the slot), 6 doubles per diagonal and
+    // 9 per off-diagonal contribution; hdst tells the per-tet kernel where each of a tet's ten blocks goes (0xffffffff: a row this rank does
+    // not own), cbase where a slot's run starts
+    std::vector<unsigned> hdst((size_t)10 * std::max(nL, 1), 0xffffffffu), cbase(sv.size() + 1, 0u);
+    {
+        uint64_t run = 0;
+        for (size_t k = 0; k < sv.size() && !ks.empty(); ++k) {
+            cbase[k] = (unsigned)run;
+            const unsigned len = (sv[k] == su[k]) ? 6u : 9u;
+            for (int c = cptr[k]; c < cptr[k + 1]; ++c) {
+                hdst[cwho[c]] = (unsigned)run;
+                run += len;
+            }
+        }
+        cbase[sv.size()] = (unsigned)run;
+        REQUIRE(run < 0xffffffffull, IPCGPU_ERR_CAPACITY, "slot-major intermediate too large for 32-bit offsets");
     }
     ctx->nSlots = (int)sv.size();
     if (sv.empty()) { sv.push_back(0); su.push_back(0); } // keep the uploads non-empty
     bool ok = ctx->slot_v.upload(sv.data(), sv.size(), ctx->stream) && ctx->slot_u.upload(su.data(), su.size(), ctx->stream)
         && ctx->con_ptr.upload(cptr.data(), cptr.size(), ctx->stream) && ctx->con_src.upload(csrc.data(), csrc.size(), ctx->stream)
-        && ctx->slot_off.reserve((size_t)3 * std::max(1, ctx->nSlots));
+        && ctx->slot_off.reserve((size_t)3 * std::max(1, ctx->nSlots)) && ctx->hdst.upload(hdst.data(), hdst.size(), ctx->stream)
+        && ctx->cbase.upload(cbase.data(), cbase.size(), ctx->stream);
     REQUIRE(ok, IPCGPU_ERR_CUDA, "upload of Hessian scatter map failed");
     ALLOC(ctx->gcont, (size_t)12 * std::max(1, nL));
     ALLOC(ctx->hblk, (size_t)78 * 64 * ((size_t)(std::max(1, nL) + 63) / 64));
+    ALLOC(ctx->hcon, (size_t)78 * std::max(1, nL));
     ALLOC(ctx->partials, (size_t)std::max(1, elastic_energy_blocks(ctx->t_end - ctx->t_begin)) + 8);
     CK(cudaStreamSynchronize(ctx->stream)); // host vectors go out of scope
     ctx->maps_ready = true;
@@ -345,6 +366,10 @@ int ipcgpu_create(int device, ipcgpu_ctx** out)
     }
     ctx->h_iter = static_cast<IterState*>(hi);
     std::memset(ctx->h_iter, 0, sizeof(IterState));
+    {
+        const char* e = std::getenv("IPCGPU_HESS_LAYOUT");
+        if (e) ctx->hess_layout = std::atoi(e) == 0 ? 0 : 1;
+    }
     {   // side stream for the pair-Hessian build + projection (IPCGPU_BARRIER_OVERLAP=0 keeps everything on one stream).  Replayed from a
         // graph the overlap wins 0.11 ms per iteration on C5 (4.10 -> 3.99 ms); enqueued eagerly the extra event calls cost about as much
         // host time as the overlap wins
@@ -628,7 +653,9 @@ static int run_grad_hess(ipcgpu_ctx* ctx, double coef, int projectSPD, int proje
         ALLOC(ctx->e_partials2, (size_t)elastic_grad_hess_blocks(ctx->n_list) + 8);
         e_part = ctx->e_partials2.p;
     }
-    elastic_grad_hess(ctx->eargs(), coef, projectSPD, need_g, need_h, ctx->gcont.p, ctx->hblk.p, ctx->stream, e_part);
+    const bool slot_major = need_h && ctx->hess_layout == 1;
+    elastic_grad_hess(ctx->eargs(), coef, projectSPD, need_g, need_h, ctx->gcont.p, ctx->hblk.p, ctx->stream, e_part, slot_major ? ctx->hdst.p : nullptr, ctx->hcon.p);
+    ctx->hblk_valid = need_h && !slot_major;
     ctx->prof_end(pe);
     ++ctx->launches;
     if (with_energy) {
@@ -648,8 +675,12 @@ static int run_grad_hess(ipcgpu_ctx* ctx, double coef, int projectSPD, int proje
     }
     if (need_h) {
         pe = ctx->prof_begin(IPCGPU_STAGE_ASSEMBLE_CSR);
-        assemble_csr(ctx->nSlots, ctx->slot_v.p, ctx->slot_u.p, ctx->slot_off.p, ctx->con_ptr.p, ctx->con_src.p, ctx->hblk.p,
-            ctx->has_dbc ? ctx->dbc.p : nullptr, projectDBC, nullptr, 1, ctx->a.p, ctx->stream);
+        if (slot_major)
+            assemble_slot_major(ctx->nSlots, ctx->slot_v.p, ctx->slot_u.p, ctx->slot_off.p, ctx->cbase.p, ctx->hcon.p, ctx->has_dbc ? ctx->dbc.p : nullptr, projectDBC, 1, ctx->a.p,
+                ctx->stream);
+        else
+            assemble_csr(ctx->nSlots, ctx->slot_v.p, ctx->slot_u.p, ctx->slot_off.p, ctx->con_ptr.p, ctx->con_src.p, ctx->hblk.p,
+                ctx->has_dbc ? ctx->dbc.p : nullptr, projectDBC, nullptr, 1, ctx->a.p, ctx->stream);
         // per-vertex diagonal terms (mass, Dirichlet identity) of the owned rows
         const double* m = (add_mass && ctx->has_mass) ? ctx->mass.p : nullptr;
         diag_mass_dbc_range(ctx->v_begin, ctx->v_end, ctx->ia.p, ctx->index_base, ctx->has_dbc ? ctx->dbc.p : nullptr, projectDBC, m, ctx->a.p, ctx->stream);
@@ -927,6 +958,14 @@ int ipcgpu_ccd_stats_timing(ipcgpu_ctx* ctx, uint64_t* longest_pair_cycles, uint
 {
     if (longest_pair_cycles) *longest_pair_cycles = ctx->ccd.last_longest_cycles;
     if (total_pair_cycles) *total_pair_cycles = ctx->ccd.last_total_cycles;
+    return IPCGPU_OK;
+}
+
+int ipcgpu_set_hessian_layout(ipcgpu_ctx* ctx, int layout)
+{
+    ++ctx->epoch; // graphs captured before this call are refused (another kernel pair)
+    REQUIRE(layout == 0 || layout == 1, IPCGPU_ERR_ARG, "layout: 0 tile-major (per-tet blocks downloadable), 1 slot-major");
+    ctx->hess_layout = layout;
     return IPCGPU_OK;
 }
 
@@ -1800,7 +1839,7 @@ static int buf_info(ipcgpu_ctx* ctx, int which, double** p, uint64_t* n)
     case IPCGPU_BUF_GRADIENT: *p = ctx->g.p; *n = (uint64_t)3 * ctx->nV; return 0;
     case IPCGPU_BUF_CSR_VALUES: *p = ctx->a.p; *n = (uint64_t)ctx->nnz; return 0;
     case IPCGPU_BUF_ENERGY_PER_TET: *p = ctx->e_per_tet.p; *n = (uint64_t)ctx->nT; return 0;
-    case IPCGPU_BUF_TET_HESSIANS: *p = ctx->hblk.p; *n = 78 * 64 * ((nL + 63) / 64); return 0; /* tile-major, see elastic.cu */
+    case IPCGPU_BUF_TET_HESSIANS: *p = ctx->hblk.p; *n = 78 * 64 * ((nL + 63) / 64); return ctx->hblk_valid ? 0 : 2; /* tile-major, see elastic.cu */
     case IPCGPU_BUF_TET_GRADIENTS: *p = ctx->gcont.p; *n = 12 * nL; return 0;
     case IPCGPU_BUF_INVERSION_STEPS: *p = ctx->inv_steps.p; *n = (uint64_t)ctx->nT; return 0;
     default: return 1;
@@ -1835,7 +1874,11 @@ int ipcgpu_download_range(ipcgpu_ctx* ctx, int which, uint64_t offset, uint64_t 
 {
     double* p;
     uint64_t n;
-    REQUIRE(buf_info(ctx, which, &p, &n) == 0, IPCGPU_ERR_ARG, "unknown buffer id");
+    {
+        const int bi = buf_info(ctx, which, &p, &n);
+        REQUIRE(bi != 2, IPCGPU_ERR_STATE, "the per-tet Hessian blocks are only kept by the tile-major layout: ipcgpu_set_hessian_layout(ctx, 0) before the Hessian call");
+        REQUIRE(bi == 0, IPCGPU_ERR_ARG, "unknown buffer id");
+    }
     REQUIRE((dst || count == 0) && offset + count <= n, IPCGPU_ERR_ARG, "download: bad destination or range");
     if (count) CK(cudaMemcpyAsync(dst, p + offset, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

@@ -166,7 +166,10 @@ struct ipcgpu_ctx {
     // Hessian slots (mesh-topology vertex pairs v<=u touched by local tets) and contributions
     int nSlots = 0;
     ipcgpu::DevBuf<int> slot_v, slot_u, slot_off, con_ptr;
-    ipcgpu::DevBuf<unsigned> con_src;
+    ipcgpu::DevBuf<unsigned> con_src, hdst, cbase; // hdst / cbase: slot-major intermediate (destination of each tet block / start of each slot's run)
+    ipcgpu::DevBuf<double> hcon;                   // the slot-major intermediate itself: contributions of a CSR block slot contiguous
+    int hess_layout = 0;                           // 0 tile-major hblk + index-list assembly (default: faster), 1 slot-major hcon + streaming assembly
+    bool hblk_valid = false;
     bool maps_ready = false, offsets_ready = false;
 
     // CSR

@@ -137,8 +137,10 @@ DEV void tma_store_tile(void* gdst, const void* ssrc, unsigned bytes)
 // with eight independent 64-thread CTAs per SM).  The tile layout of the output does not change: half-CTA h works on tile blockIdx.x * TILES + h.
 template <int ENERGY, bool NEED_G, bool NEED_H, int TILES>
 __global__ void __launch_bounds__(kHessTile * TILES, 8 / TILES) k_elastic_grad_hess(ElasticArgs p, double coef, int projectSPD,
-    double* __restrict__ gcont /* 12 per LOCAL tet */, double* __restrict__ hblk /* tile-major, 78 per LOCAL tet */, double* __restrict__ e_partials /* nullable */)
+    double* __restrict__ gcont /* 12 per LOCAL tet */, double* __restrict__ hblk /* tile-major, 78 per LOCAL tet */, double* __restrict__ e_partials /* nullable */,
+    const unsigned* __restrict__ hdst /* nullable: slot-major destinations, 10 per LOCAL tet */, double* __restrict__ hcon)
 {
+    __shared__ unsigned sDst[TILES][kHessTile]; // slot-major output: destination of this slot's block of every tet of the tile
     double e_tet = 0.0; // fused energy: psi * vol of this thread's tet (computeEnergyVal at the same state shares the SVD, like the reference's cache)
     extern __shared__ __align__(128) double smem_all[];
     const int sub = threadIdx.x / kHessTile, tx = threadIdx.x % kHessTile; // tile of this CTA, thread inside the tile
@@ -280,6 +282,22 @@ __global__ void __launch_bounds__(kHessTile * TILES, 8 / TILES) k_elastic_grad_h
                             }
                     }
                 }
+                if (hdst) {
+                    // SLOT-MAJOR output (round 2, second half): every block goes to the place where the contributions of its CSR block slot
+                    // are contiguous, so the assembly streams them instead of gathering 72-byte pieces through an index list.  The tile's
+                    // blocks of this slot sit in shared memory; 64 threads write them out element by element (a warp store covers 3.5
+                    // blocks = 3.5 contiguous runs).
+                    const int kSlotIdx = (a == b) ? a : (a == 0 ? 3 + b : (a == 1 ? 5 + b : 9)); // (folded after unrolling; the order of build_maps)
+                    sDst[sub][tx] = active ? __ldg(hdst + (size_t)t * 10 + kSlotIdx) : 0xffffffffu;
+                    __syncthreads();
+                    for (int e = tx; e < kHessTile * len; e += kHessTile) {
+                        const int tt = e / len, q = e - tt * len;
+                        const unsigned d = sDst[sub][tt];
+                        if (d != 0xffffffffu) hcon[(size_t)d + q] = buf[e];
+                    }
+                    __syncthreads();
+                }
+                else {
                 // ship this slot: generic-proxy writes -> async-proxy fence -> CTA barrier -> one elected TMA store
                 asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
                 __syncthreads();
@@ -288,6 +306,7 @@ __global__ void __launch_bounds__(kHessTile * TILES, 8 / TILES) k_elastic_grad_h
                     asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory"); // the other buffer's store has been read out
                 }
                 __syncthreads();
+                }
                 ++slot;
             }
         }
@@ -381,6 +400,41 @@ __global__ void __launch_bounds__(288) k_assemble_csr(int nSlots, const int* __r
     }
     else a[o] = h;
     (void)mass;
+}
+
+// The same over the SLOT-MAJOR intermediate: the contributions of slot s are the `cnt` consecutive blocks at cbase[s] (6 doubles each for a
+// diagonal slot, 9 otherwise), in ascending tet order -- a streaming read (every line is used completely by the 3.5 slots of a warp), no
+// index list, the loads of consecutive contributions independent of each other.
+template <int UNROLL>
+__global__ void __launch_bounds__(288) k_assemble_slot_major(int nSlots, const int* __restrict__ slot_v, const int* __restrict__ slot_u, const int* __restrict__ slot_off /* 3 per slot */,
+    const unsigned* __restrict__ cbase, const double* __restrict__ hcon, const uint8_t* __restrict__ dbc, int projectDBC, int accumulate, double* __restrict__ a)
+{
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int sIdx = (int)(tid / 9), q = (int)(tid - 9ll * sIdx);
+    if (sIdx >= nSlots) return;
+    const int v = slot_v[sIdx], u = slot_u[sIdx];
+    const bool diag = (v == u);
+    if (diag && q >= 6) return;
+    const bool pv = dbc && (dbc[v] == 1 || (dbc[v] == 2 && projectDBC));
+    const bool pu = dbc && (dbc[u] == 1 || (dbc[u] == 2 && projectDBC));
+    const bool dropped = pv || pu;
+    double h = 0.0;
+    if (!dropped) {
+        const int len = diag ? 6 : 9;
+        const double* src = hcon + cbase[sIdx] + q;
+        const double* end = hcon + cbase[sIdx + 1];
+#pragma unroll UNROLL
+        for (; src < end; src += len) h += *src;
+    }
+    int r, c;
+    if (diag) { r = (q < 3) ? 0 : (q < 5 ? 1 : 2); c = (q < 3) ? q : (q < 5 ? q - 3 : 0); }
+    else { r = q / 3; c = q - 3 * r; }
+    const int o = slot_off[3 * sIdx + r] + c;
+    if (accumulate) {
+        if (!dropped) a[o] += h;
+        else if (diag) a[o] = 0.0;
+    }
+    else a[o] = h;
 }
 
 // per-vertex diagonal terms of computePrecondMtr (Optimizer.cpp:3638-3668): mass on free vertices, identity on projected
@@ -606,7 +660,7 @@ int elastic_grad_hess_blocks(int n_list)
     return (nb + t - 1) / t;
 }
 template <int ENERGY, bool G, bool H>
-static void launch_gh(const ElasticArgs& p, double coef, int projectSPD, double* gcont, double* hblk, cudaStream_t st, double* e_partials)
+static void launch_gh(const ElasticArgs& p, double coef, int projectSPD, double* gcont, double* hblk, cudaStream_t st, double* e_partials, const unsigned* hdst, double* hcon)
 {
     const int n = p.n_list;
     if (n <= 0) return;
@@ -620,21 +674,21 @@ static void launch_gh(const ElasticArgs& p, double coef, int projectSPD, double*
         cudaFuncSetAttribute(k_elastic_grad_hess<ENERGY, G, H, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * smem));
         attr_set = true;
     }
-    if (tiles == 1) k_elastic_grad_hess<ENERGY, G, H, 1><<<nb, kHessTile, smem, st>>>(p, coef, projectSPD, gcont, hblk, e_partials);
-    else if (tiles == 2) k_elastic_grad_hess<ENERGY, G, H, 2><<<(nb + 1) / 2, 2 * kHessTile, 2 * smem, st>>>(p, coef, projectSPD, gcont, hblk, e_partials);
-    else k_elastic_grad_hess<ENERGY, G, H, 4><<<(nb + 3) / 4, 4 * kHessTile, 4 * smem, st>>>(p, coef, projectSPD, gcont, hblk, e_partials);
+    if (tiles == 1) k_elastic_grad_hess<ENERGY, G, H, 1><<<nb, kHessTile, smem, st>>>(p, coef, projectSPD, gcont, hblk, e_partials, hdst, hcon);
+    else if (tiles == 2) k_elastic_grad_hess<ENERGY, G, H, 2><<<(nb + 1) / 2, 2 * kHessTile, 2 * smem, st>>>(p, coef, projectSPD, gcont, hblk, e_partials, hdst, hcon);
+    else k_elastic_grad_hess<ENERGY, G, H, 4><<<(nb + 3) / 4, 4 * kHessTile, 4 * smem, st>>>(p, coef, projectSPD, gcont, hblk, e_partials, hdst, hcon);
 }
-void elastic_grad_hess(const ElasticArgs& p, double coef, int projectSPD, bool need_g, bool need_h, double* gcont, double* hblk, cudaStream_t st, double* e_partials)
+void elastic_grad_hess(const ElasticArgs& p, double coef, int projectSPD, bool need_g, bool need_h, double* gcont, double* hblk, cudaStream_t st, double* e_partials, const unsigned* hdst, double* hcon)
 {
     if (p.energy == 0) {
-        if (need_g && need_h) launch_gh<0, true, true>(p, coef, projectSPD, gcont, hblk, st, e_partials);
-        else if (need_g) launch_gh<0, true, false>(p, coef, projectSPD, gcont, hblk, st, e_partials);
-        else if (need_h) launch_gh<0, false, true>(p, coef, projectSPD, gcont, hblk, st, e_partials);
+        if (need_g && need_h) launch_gh<0, true, true>(p, coef, projectSPD, gcont, hblk, st, e_partials, hdst, hcon);
+        else if (need_g) launch_gh<0, true, false>(p, coef, projectSPD, gcont, hblk, st, e_partials, hdst, hcon);
+        else if (need_h) launch_gh<0, false, true>(p, coef, projectSPD, gcont, hblk, st, e_partials, hdst, hcon);
     }
     else {
-        if (need_g && need_h) launch_gh<1, true, true>(p, coef, projectSPD, gcont, hblk, st, e_partials);
-        else if (need_g) launch_gh<1, true, false>(p, coef, projectSPD, gcont, hblk, st, e_partials);
-        else if (need_h) launch_gh<1, false, true>(p, coef, projectSPD, gcont, hblk, st, e_partials);
+        if (need_g && need_h) launch_gh<1, true, true>(p, coef, projectSPD, gcont, hblk, st, e_partials, hdst, hcon);
+        else if (need_g) launch_gh<1, true, false>(p, coef, projectSPD, gcont, hblk, st, e_partials, hdst, hcon);
+        else if (need_h) launch_gh<1, false, true>(p, coef, projectSPD, gcont, hblk, st, e_partials, hdst, hcon);
     }
 }
 
@@ -651,6 +705,13 @@ void assemble_csr(int nSlots, const int* slot_v, const int* slot_u, const int* s
     const int nb = (int)(((long long)nSlots * 9 + 287) / 288);
     if (unroll >= 4) k_assemble_csr<4><<<nb, 288, 0, st>>>(nSlots, slot_v, slot_u, slot_off, con_ptr, con_src, hblk, dbc, projectDBC, mass, accumulate, a);
     else k_assemble_csr<1><<<nb, 288, 0, st>>>(nSlots, slot_v, slot_u, slot_off, con_ptr, con_src, hblk, dbc, projectDBC, mass, accumulate, a);
+}
+void assemble_slot_major(int nSlots, const int* slot_v, const int* slot_u, const int* slot_off, const unsigned* cbase, const double* hcon, const uint8_t* dbc, int projectDBC,
+    int accumulate, double* a, cudaStream_t st)
+{
+    if (nSlots <= 0) return;
+    const int nb = (int)(((long long)nSlots * 9 + 287) / 288);
+    k_assemble_slot_major<4><<<nb, 288, 0, st>>>(nSlots, slot_v, slot_u, slot_off, cbase, hcon, dbc, projectDBC, accumulate, a);
 }
 void diag_mass_dbc(int nV, const int* ia, int base, const uint8_t* dbc, int projectDBC, const double* mass, double* a, cudaStream_t st)
 {

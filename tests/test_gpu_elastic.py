@@ -59,7 +59,14 @@ def test_energy_gradient_hessian_parity(gpu_ctx, et, inverted):
     for projectSPD in (1, 0):
         H_ref = o.hessian_blocks(coef, projectSPD)
         a = np.zeros(ja.size)
+        gpu_ctx.set_hessian_layout(0)  # tile-major: the only layout that keeps the per-tet blocks
+        a_tile = np.zeros_like(a)
+        gpu_ctx.elastic_hessian(coef, 1, projectSPD, 1, a_tile)
+        gpu_ctx.set_hessian_layout(1)  # slot-major: same CSR values, bit for bit (same summation order)
         gpu_ctx.elastic_hessian(coef, 1, projectSPD, 1, a)
+        assert np.array_equal(a, a_tile)
+        gpu_ctx.set_hessian_layout(0)
+        gpu_ctx.elastic_hessian(coef, 1, projectSPD, 1, np.zeros_like(a))
         h78 = L.untile_hessians(gpu_ctx.download(L.BUF_TET_HESSIANS, 78 * 64 * ((m.nT + 63) // 64)), m.nT)
         worst = 0.0
         for t in range(m.nT):
