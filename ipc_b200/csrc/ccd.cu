@@ -1408,9 +1408,10 @@ SortedGrid tri_grid(const ipcgpu_ctx* ctx);
 SortedGrid edge_grid(const ipcgpu_ctx* ctx);
 int boxes_and_grid(ipcgpu_ctx* ctx, const double* dir, const double* alpha_ptr, double radius, const double* radius_ptr, bool with_vertex_boxes); // constraint.cu
 int pairs_mode();                                                                                                                                  // constraint.cu
-void cell_pairs_ee(const ipcgpu::Grid* gp, const ipcgpu::SortedGrid& eg, double radius_val, const double* radius_ptr, int first, int last, const ipcgpu::PairOut& out, cudaStream_t st);
-void cell_pairs_pt(const ipcgpu::Grid* gp, const ipcgpu::SortedGrid& vg, const ipcgpu::SortedGrid& tg, double radius_val, const double* radius_ptr, int first, int last,
+void cell_pairs_ee(const ipcgpu::Grid* gp, const ipcgpu::SortedGrid& eg, const ipcgpu::SurfArgs& s, double radius_val, const double* radius_ptr, int first, int last,
     const ipcgpu::PairOut& out, cudaStream_t st);
+void cell_pairs_pt(const ipcgpu::Grid* gp, const ipcgpu::SortedGrid& vg, const ipcgpu::SortedGrid& tg, const ipcgpu::SurfArgs& s, double radius_val, const double* radius_ptr,
+    int first, int last, const ipcgpu::PairOut& out, cudaStream_t st);
 SortedGrid vertex_grid(const ipcgpu_ctx* ctx);
 
 static bool lvl_smem() // level buffers of the thread pass in shared memory (IPCGPU_TI_LVL_SMEM=0: thread-local memory)
@@ -1605,13 +1606,13 @@ int ccd_full(ipcgpu_ctx* ctx, double tol, const double* err_vf, const double* er
     PairOut ppt{ cw.bp_pairs.p, nPairs, (unsigned)cw.bp_cap, w.counters.p + 14 }, pee{ cw.bp_pairs.p + cw.bp_cap, nPairs + 1, (unsigned)cw.bp_cap, w.counters.p + 14 };
     if (v1 > v0 && s.nSF > 0) {
         if (pairs_mode() == 0 || cw.built_vertices != s.nSV) k_ccd_pairs_pt<<<nblk(v1 - v0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(cw.grid.p, cw.vbox.p, tg, ist, v0, v1, ppt);
-        else cell_pairs_pt(cw.grid.p, vertex_grid(ctx), tg, 0.0, &ist->radius, s.nSF + s.nSE + v0, s.nSF + s.nSE + v1, ppt, st);
+        else cell_pairs_pt(cw.grid.p, vertex_grid(ctx), tg, s, 0.0, &ist->radius, s.nSF + s.nSE + v0, s.nSF + s.nSE + v1, ppt, st);
         k_ccd_filter_pt<<<kSMs * 8, 256, 0, st>>>(s, ppt.pairs, ppt.n, ppt.cap, w.vmin.p, w.vmax.p, out);
         ctx->launches += 2;
     }
     if (e1 > e0 && s.nSE > 1) {
         if (pairs_mode() == 0) k_ccd_pairs_ee<<<nblk(e1 - e0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(cw.grid.p, eg, cw.ebox.p, ist, s.nSF + e0, s.nSF + e1, pee); // edge entries sit behind the triangles
-        else cell_pairs_ee(cw.grid.p, eg, 0.0, &ist->radius, s.nSF + e0, s.nSF + e1, pee, st);
+        else cell_pairs_ee(cw.grid.p, eg, s, 0.0, &ist->radius, s.nSF + e0, s.nSF + e1, pee, st);
         k_ccd_filter_ee<<<kSMs * 8, 256, 0, st>>>(s, pee.pairs, pee.n, pee.cap, w.vmin.p, w.vmax.p, cw.ebox.p, out);
         ctx->launches += 2;
     }

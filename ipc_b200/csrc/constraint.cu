@@ -255,8 +255,8 @@ DEV void lane_push_pair(PairStage& st, const PairOut& o, int a, int b)
         else atomicExch(o.overflow, 1);
     }
 }
-__global__ void __launch_bounds__(32 * kCellPairWarps) k_cell_pairs_ee(const Grid* __restrict__ gp, SortedGrid eg, double radius_val, const double* __restrict__ radius_ptr,
-    int first, int last, PairOut out)
+__global__ void __launch_bounds__(32 * kCellPairWarps) k_cell_pairs_ee(const Grid* __restrict__ gp, SortedGrid eg, const int* __restrict__ SE, double radius_val,
+    const double* __restrict__ radius_ptr, int first, int last, PairOut out)
 {
     __shared__ PairStage stage;
     __shared__ AEntry sA[kCellPairWarps][32];
@@ -285,7 +285,11 @@ __global__ void __launch_bounds__(32 * kCellPairWarps) k_cell_pairs_ee(const Gri
         a.hi2 = min(hi2 + rq, 65535u);
         a.pos = pos;
         a.id = (int)e.w;
-        a.pad0 = a.pad1 = 0;
+        {   // the edge's two vertices ride along: pairs of edges that share a vertex are dropped right here (the exact stages drop them
+            // anyway, SelfCollisionHandler.cpp:2294; between neighbouring edges of a mesh they are the bulk of all overlapping boxes)
+            const int2 av = __ldg(reinterpret_cast<const int2*>(SE) + a.id);
+            a.pad0 = av.x; a.pad1 = av.y;
+        }
         A[lane] = a;
         cl[0] = (int)floor((double)(a.L01 & 0xffffu) * cell_per_q); ch[0] = (int)floor((double)(a.H01 & 0xffffu) * cell_per_q);
         cl[1] = (int)floor((double)(a.L01 >> 16) * cell_per_q);     ch[1] = (int)floor((double)(a.H01 >> 16) * cell_per_q);
@@ -358,12 +362,15 @@ __global__ void __launch_bounds__(32 * kCellPairWarps) k_cell_pairs_ee(const Gri
             const uint4 e = en;
             const int bpos = kn;
             const bool have = j < total;
+            int2 bv = make_int2(-1, -1);
+            if (have) bv = __ldg(reinterpret_cast<const int2*>(SE) + (int)e.w); // the partner's vertices (in flight next to the next entry)
             if (j + 32 < total) { kn = locate(j + 32); en = __ldg(ent + kn); }
             if (have) {
                 const unsigned bL01 = e.x, bH01 = __funnelshift_r(e.y, e.z, 16), blo2 = e.y & 0xffffu, bhi2 = e.z >> 16;
                 for (int a = a_lo; a < a_hi; ++a) {
                     const AEntry q = A[a]; // same address on every lane: broadcast
-                    const bool hit = __vminu2(q.L01, bH01) == q.L01 && __vminu2(bL01, q.H01) == bL01 && q.lo2 <= bhi2 && blo2 <= q.hi2 && bpos > q.pos;
+                    const bool hit = __vminu2(q.L01, bH01) == q.L01 && __vminu2(bL01, q.H01) == bL01 && q.lo2 <= bhi2 && blo2 <= q.hi2 && bpos > q.pos
+                        && q.pad0 != bv.x && q.pad0 != bv.y && q.pad1 != bv.x && q.pad1 != bv.y;
                     if (hit) lane_push_pair(stage, out, min(q.id, (int)e.w), max(q.id, (int)e.w));
                 }
             }
@@ -377,8 +384,8 @@ __global__ void __launch_bounds__(32 * kCellPairWarps) k_cell_pairs_ee(const Gri
 // partners = triangle entries of every cell a query of the run can see (both sides: up to 4 x 4 rows of <= 4 cells; typically 3 x 3 x 3).
 // Rows are walked one after the other (a row of three cells holds about one warp-load of triangles); the first load of the next row is
 // issued before the current row is tested.
-__global__ void __launch_bounds__(32 * kCellPairWarps) k_cell_pairs_pt(const Grid* __restrict__ gp, SortedGrid vg, SortedGrid tg, double radius_val,
-    const double* __restrict__ radius_ptr, int first, int last, PairOut out)
+__global__ void __launch_bounds__(32 * kCellPairWarps) k_cell_pairs_pt(const Grid* __restrict__ gp, SortedGrid vg, SortedGrid tg, const int* __restrict__ SVI,
+    const int* __restrict__ SF, int nSF, double radius_val, const double* __restrict__ radius_ptr, int first, int last, PairOut out)
 {
     __shared__ PairStage stage;
     __shared__ AEntry sA[kCellPairWarps][32];
@@ -407,7 +414,8 @@ __global__ void __launch_bounds__(32 * kCellPairWarps) k_cell_pairs_pt(const Gri
         a.hi2 = min(hi2 + rq, 65535u);
         a.pos = pos;
         a.id = (int)e.w;
-        a.pad0 = a.pad1 = 0;
+        a.pad0 = __ldg(SVI + a.id); // the vertex itself: a triangle that contains it is no partner (:2184), and those are most overlapping boxes
+        a.pad1 = 0;
         A[lane] = a;
         cl[0] = (int)floor((double)(a.L01 & 0xffffu) * cell_per_q); ch[0] = (int)floor((double)(a.H01 & 0xffffu) * cell_per_q);
         cl[1] = (int)floor((double)(a.L01 >> 16) * cell_per_q);     ch[1] = (int)floor((double)(a.H01 >> 16) * cell_per_q);
@@ -459,9 +467,11 @@ __global__ void __launch_bounds__(32 * kCellPairWarps) k_cell_pairs_pt(const Gri
                     if (jj >= 32 && jj < len) e = __ldg(ent + s0 + jj); // rows longer than one warp-load (rare)
                     if (jj < len) {
                         const unsigned bL01 = e.x, bH01 = __funnelshift_r(e.y, e.z, 16), blo2 = e.y & 0xffffu, bhi2 = e.z >> 16;
+                        const int t0 = __ldg(SF + (int)e.w), t1 = __ldg(SF + nSF + (int)e.w), t2 = __ldg(SF + 2 * (size_t)nSF + (int)e.w);
                         for (int a = a_lo; a < a_hi; ++a) {
                             const AEntry q = A[a];
-                            const bool hit = __vminu2(q.L01, bH01) == q.L01 && __vminu2(bL01, q.H01) == bL01 && q.lo2 <= bhi2 && blo2 <= q.hi2;
+                            const bool hit = __vminu2(q.L01, bH01) == q.L01 && __vminu2(bL01, q.H01) == bL01 && q.lo2 <= bhi2 && blo2 <= q.hi2
+                                && q.pad0 != t0 && q.pad0 != t1 && q.pad0 != t2;
                             if (hit) lane_push_pair(stage, out, q.id, (int)e.w);
                         }
                     }
@@ -729,13 +739,15 @@ int pairs_mode()
     static const int mode = [] { const char* e = std::getenv("IPCGPU_PAIRS_MODE"); return e ? std::atoi(e) : 1; }();
     return mode;
 }
-void cell_pairs_pt(const Grid* gp, const SortedGrid& vg, const SortedGrid& tg, double radius_val, const double* radius_ptr, int first, int last, const PairOut& out, cudaStream_t st)
+void cell_pairs_pt(const Grid* gp, const SortedGrid& vg, const SortedGrid& tg, const SurfArgs& s, double radius_val, const double* radius_ptr, int first, int last,
+    const PairOut& out, cudaStream_t st)
 {
-    if (last > first) k_cell_pairs_pt<<<nblk(last - first, 32 * kCellPairWarps), 32 * kCellPairWarps, 0, st>>>(gp, vg, tg, radius_val, radius_ptr, first, last, out);
+    if (last > first)
+        k_cell_pairs_pt<<<nblk(last - first, 32 * kCellPairWarps), 32 * kCellPairWarps, 0, st>>>(gp, vg, tg, s.SVI, s.SF, s.nSF, radius_val, radius_ptr, first, last, out);
 }
-void cell_pairs_ee(const Grid* gp, const SortedGrid& eg, double radius_val, const double* radius_ptr, int first, int last, const PairOut& out, cudaStream_t st)
+void cell_pairs_ee(const Grid* gp, const SortedGrid& eg, const SurfArgs& s, double radius_val, const double* radius_ptr, int first, int last, const PairOut& out, cudaStream_t st)
 {
-    if (last > first) k_cell_pairs_ee<<<nblk(last - first, 32 * kCellPairWarps), 32 * kCellPairWarps, 0, st>>>(gp, eg, radius_val, radius_ptr, first, last, out);
+    if (last > first) k_cell_pairs_ee<<<nblk(last - first, 32 * kCellPairWarps), 32 * kCellPairWarps, 0, st>>>(gp, eg, s.SE, radius_val, radius_ptr, first, last, out);
 }
 
 // stable radix sort of (keys, idx) pairs, result back in (keys, idx)
@@ -969,13 +981,13 @@ int contact_constraint_set(ipcgpu_ctx* ctx, double dHat, int wantCand, int* nC, 
     PairOut ppt{ w.bp_pairs.p, nPairs, (unsigned)w.bp_cap, w.counters.p + 4 }, pee{ w.bp_pairs.p + w.bp_cap, nPairs + 1, (unsigned)w.bp_cap, w.counters.p + 4 };
     if (v1 > v0 && s.nSF > 0) {
         if (pairs_mode() == 0 || w.built_vertices != s.nSV) k_pairs_pt<<<nblk(v1 - v0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(s, w.grid.p, tg, dHat, radius, v0, v1, ppt);
-        else cell_pairs_pt(w.grid.p, vertex_grid(ctx), tg, radius, nullptr, s.nSF + s.nSE + v0, s.nSF + s.nSE + v1, ppt, st); // vertex entries: by sorted position
+        else cell_pairs_pt(w.grid.p, vertex_grid(ctx), tg, s, radius, nullptr, s.nSF + s.nSE + v0, s.nSF + s.nSE + v1, ppt, st); // vertex entries: by sorted position
         k_classify_pt<<<kSMs * 8, 128, 0, st>>>(s, ppt.pairs, ppt.n, ppt.cap, dHat, wantCand, out);
         ctx->launches += 2;
     }
     if (e1 > e0 && s.nSE > 1) {
         if (pairs_mode() == 0) k_pairs_ee<<<nblk(e1 - e0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(w.grid.p, eg, w.ebox.p, dHat, radius, s.nSF + e0, s.nSF + e1, pee); // edge entries sit behind the triangles
-        else cell_pairs_ee(w.grid.p, eg, radius, nullptr, s.nSF + e0, s.nSF + e1, pee, st);
+        else cell_pairs_ee(w.grid.p, eg, s, radius, nullptr, s.nSF + e0, s.nSF + e1, pee, st);
         k_classify_ee<<<kSMs * 8, 128, 0, st>>>(s, pee.pairs, pee.n, pee.cap, dHat, wantCand, out);
         ctx->launches += 2;
     }
