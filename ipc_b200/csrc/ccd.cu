@@ -1304,6 +1304,239 @@ __global__ void __launch_bounds__(128, OCC) k_ti_stage15(NarrowArgs a, const uns
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Thread pass with LANE-LEVEL REFILL (round 2, second half).  ncu on k_ti_stage15: 7.4 of 32 lanes active per issued instruction -- a lane whose
+// search ended after two boxes waited for the lane of its warp that used its whole 24-box budget.  Here the search is a resumable state
+// machine: one loop iteration = ONE LEVEL of one lane's breadth-first search (the body of ti_root_finder's level loop, same arithmetic, same
+// decisions); a lane whose pair is finished takes the next survivor from a work counter in the same iteration.  The no_zero_toi loop of
+// ti_ccd and the ms = 0 retry of pair_ccd are states of the same machine.
+// ------------------------------------------------------------------------------------------------------------------
+struct Bfs1 {
+    DBox* cur;
+    DBox* nxt;
+    int n;
+    double toi_skip;
+    bool use_skip;
+    long long refine;
+    double temp_toi, temp_out_tol;
+    unsigned long long bo_cur;
+};
+DEV void bfs1_init(Bfs1& b, DBox* bufA, DBox* bufB, double co_tol, const unsigned long long* best)
+{
+    const double INF = __longlong_as_double(0x7ff0000000000000ll);
+    b.cur = bufA; b.nxt = bufB;
+    b.cur[0] = DBox{ 0ull, 0ull, 0ull, 0u, 0u };
+    b.n = 1;
+    b.toi_skip = INF; b.use_skip = false; b.refine = 0;
+    b.temp_toi = INF; b.temp_out_tol = co_tol;
+    b.bo_cur = best ? *reinterpret_cast<const volatile unsigned long long*>(best) : 0ull;
+}
+// one level of ti_root_finder<1>: 0 no collision, 1 collision (toi set), 2 deferred, 3 go on with the next level
+DEV int bfs1_level(bool VF, const TiPair& P, const double* tol, const double* inv_tol, double co_tol, double max_t, const double* err, double ms, int max_itr,
+    int cap, long long thread_budget, const unsigned long long* best, Bfs1& b, double& toi, double& out_tol, int* __restrict__ warn)
+{
+    const bool check_t = (max_t != 1.0);
+    const double INF = __longlong_as_double(0x7ff0000000000000ll);
+    double t_prune = INF;
+    if (best) {
+        t_prune = fmax(ord_to_dbl(b.bo_cur), 1e-6);
+        b.bo_cur = *reinterpret_cast<const volatile unsigned long long*>(best);
+    }
+    Key3 k1 = { INF, INF, INF }, k2 = { INF, INF, INF };
+    unsigned p1 = 0, p2 = 0;
+    double a1 = 0.0;
+    int visited = 0;
+    for (int i = 0; i < b.n; ++i) {
+        DBox bx = b.cur[i];
+        const int tk = bx.kk & 0xff, uk = (bx.kk >> 8) & 0xff, vk = (bx.kk >> 16) & 0xff;
+        const double tlo = dy_lo(bx.tn, tk);
+        unsigned flags = 0;
+        if (tlo < b.toi_skip && tlo < t_prune) {
+            ++visited;
+            bool box_in;
+            double tt[3];
+            if (origin_in_box(VF, P, bx, err, ms, box_in, tt)) {
+                flags = F_ZERO;
+                const bool tol_cond = tt[0] <= co_tol && tt[1] <= co_tol && tt[2] <= co_tol;
+                const bool cond1 = pow2neg(tk) <= tol[0] && pow2neg(uk) <= tol[1] && pow2neg(vk) <= tol[2];
+                const Key3 key = { tlo, dy_lo(bx.un, uk), dy_lo(bx.vn, vk) };
+                const unsigned mp1 = (tol_cond || box_in || cond1) ? 1u : 0u;
+                if (key_less(key, k1)) { k1 = key; p1 = mp1; a1 = fmax(fmax(tt[0], tt[1]), tt[2]); }
+                if (mp1 && key_less(key, k2)) { k2 = key; p2 = cond1 ? 1u : 0u; }
+            }
+        }
+        b.cur[i].kk = (bx.kk & 0x00ffffffu) | flags;
+    }
+    if (k1.t == INF) { // nothing at this level contains the origin: the search space is exhausted
+        if (b.use_skip) { toi = b.toi_skip; return 1; }
+        return 0;
+    }
+    if (p1 & 1u) { toi = k1.t; return 1; }
+    const bool has_k2 = k2.t != INF;
+    if (has_k2 && (p2 & 1u)) { toi = k2.t; return 1; }
+    atomicAdd(reinterpret_cast<unsigned long long*>(warn + 5), (unsigned long long)visited); // diagnostics: boxes evaluated by the thread pass
+    if (b.refine + visited > thread_budget) return 2; // over budget: handed to the warp pass
+    if (max_itr > 0) {
+        b.temp_toi = k1.t;
+        b.temp_out_tol = fmax(a1, co_tol);
+        b.refine += visited;
+        if (b.refine > max_itr) {
+            atomicAdd(warn, 1);
+            toi = b.temp_toi;
+            out_tol = b.temp_out_tol;
+            return 1;
+        }
+    }
+    if (has_k2) {
+        if (k2.t < b.toi_skip) b.toi_skip = k2.t;
+        b.use_skip = true;
+    }
+    int nn = 0;
+    for (int i = 0; i < b.n; ++i) {
+        const DBox bx = b.cur[i];
+        if (!(bx.kk & F_ZERO)) continue;
+        const int tk = bx.kk & 0xff, uk = (bx.kk >> 8) & 0xff, vk = (bx.kk >> 16) & 0xff;
+        const Key3 key = { dy_lo(bx.tn, tk), dy_lo(bx.un, uk), dy_lo(bx.vn, vk) };
+        if (has_k2 && !key_less(key, k2)) continue;
+        const double w[3] = { pow2neg(tk), pow2neg(uk), pow2neg(vk) };
+        int split = -1;
+        double bestr = -1.0;
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+            if (w[d] > tol[d]) {
+                const double r = inv_tol[d] * w[d]; // = w[d] / tol[d] bit for bit (see ti_ccd)
+                if (r > bestr) { bestr = r; split = d; }
+            }
+        const int pk = split == 0 ? tk : (split == 1 ? uk : vk);
+        if (split < 0 || pk >= 60) return 2; // bisection overflow: the warp pass handles it like the iteration overflow
+        const unsigned long long pn = split == 0 ? bx.tn : (split == 1 ? bx.un : bx.vn);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const unsigned long long hn = 2 * pn + half;
+            const int hk = pk + 1;
+            bool keep = true;
+            if (split == 0) { if (check_t) keep = !(dy_hi(hn, hk) < 0.0 || dy_lo(hn, hk) > max_t); }
+            else if (VF) keep = (split == 1) ? sum_le_1(hn, hk, bx.vn, vk) : sum_le_1(hn, hk, bx.un, uk);
+            if (keep) {
+                if (nn >= cap) return 2; // the level outgrew the buffer
+                DBox c = bx;
+                c.kk &= 0x00ffffffu;
+                if (split == 0) { c.tn = hn; c.kk = (c.kk & ~0xffu) | (unsigned)hk; }
+                else if (split == 1) { c.un = hn; c.kk = (c.kk & ~0xff00u) | ((unsigned)hk << 8); }
+                else { c.vn = hn; c.kk = (c.kk & ~0xff0000u) | ((unsigned)hk << 16); }
+                b.nxt[nn++] = c;
+            }
+        }
+    }
+    DBox* t = b.cur; b.cur = b.nxt; b.nxt = t;
+    b.n = nn;
+    if (nn == 0) {
+        if (b.use_skip) { toi = b.toi_skip; return 1; }
+        return 0;
+    }
+    return 3;
+}
+
+template <int CAP>
+__global__ void __launch_bounds__(128, 2) k_ti_stage15_refill(NarrowArgs a, const unsigned* __restrict__ survivors, const unsigned* __restrict__ nSurvPtr, unsigned* __restrict__ work,
+    unsigned* __restrict__ deferred, unsigned* __restrict__ nDeferred, long long budget, unsigned long long* __restrict__ min_ord, int* __restrict__ warn)
+{
+    extern __shared__ __align__(16) unsigned char s_lvl[];
+    constexpr int kSlab = CAP * (int)sizeof(DBox) + 8;
+    DBox* bufA = reinterpret_cast<DBox*>(s_lvl + (size_t)threadIdx.x * kSlab);
+    DBox* bufB = reinterpret_cast<DBox*>(s_lvl + (size_t)(blockDim.x + threadIdx.x) * kSlab);
+    const unsigned nSurv = *nSurvPtr;
+    const double max_t0 = a.st->max_t;
+    const unsigned long long* best0 = &a.st->ccd_ord;
+    const int lane = threadIdx.x & 31;
+    // per-lane state of pair_ccd / ti_ccd / the root finder
+    bool busy = false, vf = false;
+    unsigned idx = 0;
+    TiPair P;
+    Bfs1 bf;
+    int attempt = 0;
+    unsigned iter = 0;
+    bool is_impacting = false;
+    double dist = 0.0, ms_in = 0.0, tolerance_in = 0.0, t_max = 0.0, out_tol = 0.0, toi = 0.0;
+    double tol[3] = { 0, 0, 0 }, inv_tol[3] = { 0, 0, 0 };
+    const double* err = a.err_vf;
+    const unsigned long long* best = nullptr;
+    bool drained = false;
+    for (;;) {
+        if (!busy && !drained) { // take the next survivor (one atomic per warp and round)
+            const unsigned m = __activemask();
+            const int leader = __ffs(m) - 1;
+            unsigned base = 0;
+            if (lane == leader) base = atomicAdd(work, (unsigned)__popc(m));
+            base = __shfl_sync(m, base, leader);
+            const unsigned w = base + __popc(m & ((1u << lane) - 1u));
+            if (w < nSurv) {
+                idx = survivors[w];
+                int v[4];
+                load_pair(a.s, a.dir, a.cand[idx], vf, v, P);
+                err = vf ? a.err_vf : a.err_ee;
+                dist = pair_distance_sqrt(vf, P);
+                attempt = 0;
+                // ti_ccd entry state of the first trip (pair_ccd): ms = min(0.2 d, 1e-6), pruned against the running minimum
+                ms_in = fmin(0.2 * dist, 1e-6); tolerance_in = a.tol; t_max = max_t0; out_tol = a.tol; iter = 0; is_impacting = false; best = best0;
+                width_tolerances(vf, P, tolerance_in, tol);
+#pragma unroll
+                for (int d = 0; d < 3; ++d) inv_tol[d] = 1.0 / tol[d];
+                bfs1_init(bf, bufA, bufB, tolerance_in, best);
+                out_tol = tolerance_in;
+                busy = true;
+            }
+            else drained = true;
+        }
+        __syncwarp();
+        if (__all_sync(0xffffffffu, !busy)) break; // the lanes of a warp leave together: all idle and the list exhausted
+        if (busy) {
+            const int rc = bfs1_level(vf, P, tol, inv_tol, tolerance_in, t_max, err, ms_in, a.max_itr, CAP, budget, best, bf, toi, out_tol, warn);
+            if (rc != 3) {
+                bool restart = false, finished = false;
+                int hit = 0;
+                if (rc == 2) { deferred[atomicAdd(nDeferred, 1u)] = idx; finished = true; }
+                else { // ti_ccd: the no_zero_toi refinement loop around the root finder
+                    const bool tmp = rc == 1;
+                    if (iter == 0) is_impacting = tmp;
+                    else toi = tmp ? toi : t_max;
+                    if (tmp && toi == 0.0) {
+                        if (out_tol > tolerance_in) t_max *= 0.9;
+                        else if (10 * tolerance_in < ms_in) ms_in *= 0.5;
+                        else tolerance_in *= 0.1;
+                        ++iter;
+                        restart = true;
+                    }
+                    else {
+                        hit = is_impacting ? 1 : 0;
+                        // pair_ccd: second trip (:759-781) only after a hit with toi < 1e-6: ms = 0, not pruned, result scaled by 0.8
+                        if (attempt == 0 && hit && toi < 1e-6) {
+                            attempt = 1;
+                            ms_in = 0.0; tolerance_in = a.tol; t_max = max_t0; iter = 0; is_impacting = false; best = nullptr;
+                            restart = true;
+                        }
+                        else {
+                            if (attempt == 1 && hit) toi *= 0.8;
+                            finished = true;
+                        }
+                    }
+                }
+                if (restart) {
+                    width_tolerances(vf, P, tolerance_in, tol);
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) inv_tol[d] = 1.0 / tol[d];
+                    bfs1_init(bf, bufA, bufB, tolerance_in, best);
+                    out_tol = tolerance_in;
+                }
+                if (finished) {
+                    if (hit == 1) atomicMin(min_ord, dbl_to_ord(toi));
+                    busy = false;
+                }
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128, 3) k_ti_stage2(NarrowArgs a, const unsigned* __restrict__ survivors, const unsigned* __restrict__ nSurvPtr, unsigned* __restrict__ work,
     DBox* __restrict__ scratch, int cap, unsigned long long* __restrict__ min_ord, int* __restrict__ warn)
 {
@@ -1406,14 +1639,20 @@ static inline int nblk(long long n, int b) { return (int)((n + b - 1) / b); }
 SurfArgs surf_args(const ipcgpu_ctx* ctx); // constraint.cu
 SortedGrid tri_grid(const ipcgpu_ctx* ctx);
 SortedGrid edge_grid(const ipcgpu_ctx* ctx);
-int boxes_and_grid(ipcgpu_ctx* ctx, const double* dir, const double* alpha_ptr, double radius, const double* radius_ptr, bool with_vertex_boxes); // constraint.cu
+int boxes_and_grid(ipcgpu_ctx* ctx, const double* dir, const double* alpha_ptr, double radius, const double* radius_ptr, bool with_vertex_boxes, const int* vmin,
+    const int* vmax); // constraint.cu
 int pairs_mode();                                                                                                                                  // constraint.cu
-void cell_pairs_ee(const ipcgpu::Grid* gp, const ipcgpu::SortedGrid& eg, const ipcgpu::SurfArgs& s, double radius_val, const double* radius_ptr, int first, int last,
-    const ipcgpu::PairOut& out, cudaStream_t st);
-void cell_pairs_pt(const ipcgpu::Grid* gp, const ipcgpu::SortedGrid& vg, const ipcgpu::SortedGrid& tg, const ipcgpu::SurfArgs& s, double radius_val, const double* radius_ptr,
+void cell_pairs_ee(const ipcgpu::Grid* gp, const ipcgpu::SortedGrid& eg, const ipcgpu::SurfArgs& s, double radius_val, const double* radius_ptr, const ipcgpu::IterState* vox,
     int first, int last, const ipcgpu::PairOut& out, cudaStream_t st);
+void cell_pairs_pt(const ipcgpu::Grid* gp, const ipcgpu::SortedGrid& vg, const ipcgpu::SortedGrid& tg, const ipcgpu::SurfArgs& s, double radius_val, const double* radius_ptr,
+    const ipcgpu::IterState* vox, int first, int last, const ipcgpu::PairOut& out, cudaStream_t st);
 SortedGrid vertex_grid(const ipcgpu_ctx* ctx);
 
+static bool refill_mode() // thread pass with lane-level refill (IPCGPU_TI_REFILL=0: one pair per lane and grid-stride round)
+{
+    static const bool v = [] { const char* e = std::getenv("IPCGPU_TI_REFILL"); return e ? std::atoi(e) != 0 : true; }();
+    return v;
+}
 static bool lvl_smem() // level buffers of the thread pass in shared memory (IPCGPU_TI_LVL_SMEM=0: thread-local memory)
 {
     static const bool v = [] { const char* e = std::getenv("IPCGPU_TI_LVL_SMEM"); return e ? std::atoi(e) != 0 : true; }();
@@ -1496,6 +1735,12 @@ int ccd_narrow(ipcgpu_ctx* ctx, const int2* cand, const int* n32, const unsigned
             static const int capA = [] { const char* e = std::getenv("IPCGPU_TI_CAP"); return e ? std::atoi(e) : 8; }(); // boxes per level buffer of the thread pass
             // (C5, narrow phase per iteration: local memory 12 boxes 1.044 ms, 8 boxes 1.035, 6 boxes 1.024; shared memory 12 boxes 1.029, 8 boxes 1.006)
             if (occA == 3) k_ti_stage15<kThreadCap, 3><<<kSMs * 16, 128, 0, st>>>(a, w.surv.p, nSurv, w.surv2.p, nDefA, budgetA, &ist->ccd_ord, flags + 1);
+            else if (refill_mode()) {
+                constexpr int bytes = 2 * 128 * (8 * (int)sizeof(DBox) + 8);
+                static bool attr = false;
+                if (!attr) { cudaFuncSetAttribute(k_ti_stage15_refill<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); attr = true; }
+                k_ti_stage15_refill<8><<<kSMs * 2, 128, bytes, st>>>(a, w.surv.p, nSurv, grp_work, w.surv2.p, nDefA, budgetA, &ist->ccd_ord, flags + 1);
+            }
             else if (lvl_smem() && capA == 8) {
                 constexpr int bytes = 2 * 128 * (8 * (int)sizeof(DBox) + 8);
                 static bool attr = false;
@@ -1578,7 +1823,7 @@ int ccd_build_swept(ipcgpu_ctx* ctx, double h)
     if (s.nSV > 0) k_ref_ranges<<<nblk(s.nSV, 256), 256, 0, st>>>(s, ctx->dir.p, ist, w.vmin.p, w.vmax.p);
     ctx->launches += 4;
     // coarse accelerator grid over the swept boxes; pairs sharing a reference voxel are at most one voxel apart per axis
-    int rc = boxes_and_grid(ctx, ctx->dir.p, &ist->alpha_grid, 0.0, &ist->radius, true);
+    int rc = boxes_and_grid(ctx, ctx->dir.p, &ist->alpha_grid, 0.0, &ist->radius, true, w.vmin.p, w.vmax.p);
     ctx->prof_end(pe);
     if (rc) return rc;
     CKD(cudaGetLastError());
@@ -1606,13 +1851,13 @@ int ccd_full(ipcgpu_ctx* ctx, double tol, const double* err_vf, const double* er
     PairOut ppt{ cw.bp_pairs.p, nPairs, (unsigned)cw.bp_cap, w.counters.p + 14 }, pee{ cw.bp_pairs.p + cw.bp_cap, nPairs + 1, (unsigned)cw.bp_cap, w.counters.p + 14 };
     if (v1 > v0 && s.nSF > 0) {
         if (pairs_mode() == 0 || cw.built_vertices != s.nSV) k_ccd_pairs_pt<<<nblk(v1 - v0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(cw.grid.p, cw.vbox.p, tg, ist, v0, v1, ppt);
-        else cell_pairs_pt(cw.grid.p, vertex_grid(ctx), tg, s, 0.0, &ist->radius, s.nSF + s.nSE + v0, s.nSF + s.nSE + v1, ppt, st);
+        else cell_pairs_pt(cw.grid.p, vertex_grid(ctx), tg, s, 0.0, &ist->radius, cw.built_voxel_entries ? ist : nullptr, s.nSF + s.nSE + v0, s.nSF + s.nSE + v1, ppt, st);
         k_ccd_filter_pt<<<kSMs * 8, 256, 0, st>>>(s, ppt.pairs, ppt.n, ppt.cap, w.vmin.p, w.vmax.p, out);
         ctx->launches += 2;
     }
     if (e1 > e0 && s.nSE > 1) {
         if (pairs_mode() == 0) k_ccd_pairs_ee<<<nblk(e1 - e0, 8 * kPairQueriesPerWarp), 256, 0, st>>>(cw.grid.p, eg, cw.ebox.p, ist, s.nSF + e0, s.nSF + e1, pee); // edge entries sit behind the triangles
-        else cell_pairs_ee(cw.grid.p, eg, s, 0.0, &ist->radius, s.nSF + e0, s.nSF + e1, pee, st);
+        else cell_pairs_ee(cw.grid.p, eg, s, 0.0, &ist->radius, cw.built_voxel_entries ? ist : nullptr, s.nSF + e0, s.nSF + e1, pee, st);
         k_ccd_filter_ee<<<kSMs * 8, 256, 0, st>>>(s, pee.pairs, pee.n, pee.cap, w.vmin.p, w.vmax.p, cw.ebox.p, out);
         ctx->launches += 2;
     }

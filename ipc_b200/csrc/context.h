@@ -63,6 +63,7 @@ struct ContactWork {
     int axis_bits = 10;         // key bits per axis of the grid sorts (re-tuned from IterState::grid_axis_cells at every fetch)
     int built_axis_bits = 10;   // ... of the grids that are currently built (position of the type bit)
     int built_vertices = 0;     // surface-vertex entries in the combined sorted array (0: the build carried none)
+    bool built_voxel_entries = false; // the entries of the current grid carry reference-voxel ranges (swept grid) instead of quantised boxes
     // barrier stage workspace, sized by the pair capacity
     DevBuf<double> bHraw, bpartials, bval; // (bval: per-constraint values of ipcgpu_evaluate_constraints / inputs of ..._jacobian_t)
     DevBuf<int> brows, bpsd;
