@@ -1439,7 +1439,7 @@ DEV int bfs1_level(bool VF, const TiPair& P, const double* tol, const double* in
 
 template <int CAP>
 __global__ void __launch_bounds__(128, 2) k_ti_stage15_refill(NarrowArgs a, const unsigned* __restrict__ survivors, const unsigned* __restrict__ nSurvPtr, unsigned* __restrict__ work,
-    unsigned* __restrict__ deferred, unsigned* __restrict__ nDeferred, long long budget, unsigned long long* __restrict__ min_ord, int* __restrict__ warn)
+    unsigned* __restrict__ deferred, unsigned* __restrict__ nDeferred, long long budget, unsigned long long* __restrict__ min_ord, int* __restrict__ warn, int refill_batch)
 {
     extern __shared__ __align__(16) unsigned char s_lvl[];
     constexpr int kSlab = CAP * (int)sizeof(DBox) + 8;
@@ -1463,7 +1463,13 @@ __global__ void __launch_bounds__(128, 2) k_ti_stage15_refill(NarrowArgs a, cons
     const unsigned long long* best = nullptr;
     bool drained = false;
     for (;;) {
-        if (!busy && !drained) { // take the next survivor (one atomic per warp and round)
+        // Refill in batches: fetching a pair is two dependent rounds of global loads (candidate -> vertex ids -> positions, directions), and the
+        // whole warp waits for them -- refilling whenever any lane is idle made every iteration pay that latency (ncu: long scoreboard 3.0 per
+        // issued instruction).  Lanes wait until kRefillBatch of them are idle (or nothing is running).
+        __syncwarp();
+        const unsigned idle_m = __ballot_sync(0xffffffffu, !busy && !drained);
+        const bool refill_now = __popc(idle_m) >= refill_batch || __ballot_sync(0xffffffffu, busy) == 0u;
+        if (!busy && !drained && refill_now) { // take the next survivor (one atomic per warp and round)
             const unsigned m = __activemask();
             const int leader = __ffs(m) - 1;
             unsigned base = 0;
@@ -1739,7 +1745,8 @@ int ccd_narrow(ipcgpu_ctx* ctx, const int2* cand, const int* n32, const unsigned
                 constexpr int bytes = 2 * 128 * (8 * (int)sizeof(DBox) + 8);
                 static bool attr = false;
                 if (!attr) { cudaFuncSetAttribute(k_ti_stage15_refill<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); attr = true; }
-                k_ti_stage15_refill<8><<<kSMs * 2, 128, bytes, st>>>(a, w.surv.p, nSurv, grp_work, w.surv2.p, nDefA, budgetA, &ist->ccd_ord, flags + 1);
+                static const int batch = [] { const char* e = std::getenv("IPCGPU_TI_REFILL_BATCH"); return e ? std::atoi(e) : 16; }(); // (1 .. 32 measured within 1.5 % of each other)
+                k_ti_stage15_refill<8><<<kSMs * 2, 128, bytes, st>>>(a, w.surv.p, nSurv, grp_work, w.surv2.p, nDefA, budgetA, &ist->ccd_ord, flags + 1, batch);
             }
             else if (lvl_smem() && capA == 8) {
                 constexpr int bytes = 2 * 128 * (8 * (int)sizeof(DBox) + 8);
