@@ -264,24 +264,50 @@ struct alignas(16) AEntry {
     int pos, id, pad0, pad1;     // 32 bytes: two 128-bit shared-memory loads
 };
 constexpr int kCellPairWarps = 8;
-DEV void lane_push_pair(PairStage& st, const PairOut& o, int a, int b)
+// Hits are staged PER WARP (ncu on the first version, which staged per CTA: 20 % of the stall samples sat behind the CTA barrier of the final
+// flush -- the eight warps of a CTA finish their chunks at very different times) and flushed by the warp itself with one global atomic.
+constexpr int kWarpStageCap = 256; // pairs per warp (2 KB)
+struct WarpStage {
+    int2 buf[kWarpStageCap];
+    unsigned count;
+};
+DEV void lane_push_pair(WarpStage& ws, const PairOut& o, int a, int b)
 {
-    const unsigned i = atomicAdd(&st.count, 1u);
-    if (i < (unsigned)kPairStageCap) st.buf[i] = make_int2(a, b);
-    else {
+    const unsigned i = atomicAdd(&ws.count, 1u);
+    if (i < (unsigned)kWarpStageCap) ws.buf[i] = make_int2(a, b);
+    else { // stage full (a very dense neighbourhood between two flushes): straight to the global list
         const unsigned gi = atomicAdd(o.n, 1u);
         if (gi < o.cap) o.pairs[gi] = make_int2(a, b);
         else atomicExch(o.overflow, 1);
     }
 }
+// all 32 lanes; flushes when the stage is at least `threshold` full
+DEV void warp_stage_flush(WarpStage& ws, const PairOut& o, int lane, unsigned threshold)
+{
+    __syncwarp();
+    const unsigned n = min(ws.count, (unsigned)kWarpStageCap);
+    if (n < threshold || n == 0u) return;
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(o.n, n);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (unsigned i = lane; i < n; i += 32) {
+        if (base + i < o.cap) o.pairs[base + i] = ws.buf[i];
+        else atomicExch(o.overflow, 1);
+    }
+    __syncwarp();
+    if (lane == 0) ws.count = 0;
+    __syncwarp();
+}
 __global__ void __launch_bounds__(32 * kCellPairWarps) k_cell_pairs_ee(const Grid* __restrict__ gp, SortedGrid eg, const int* __restrict__ SE, double radius_val,
     const double* __restrict__ radius_ptr, const IterState* __restrict__ vox, int first, int last, PairOut out)
 {
-    __shared__ PairStage stage;
+    __shared__ WarpStage sStage[kCellPairWarps];
     __shared__ AEntry sA[kCellPairWarps][32];
-    pair_stage_init(stage);
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    WarpStage& stage = sStage[wib];
+    if (lane == 0) stage.count = 0;
+    __syncwarp();
     const Grid g = *gp;
     // Two kinds of entry boxes (k_cell_scatter): quantised double boxes (static grid: the query is inflated by `radius` in lattice steps) or
     // ranges of reference voxels (swept grid, vox != nullptr: ranges overlap <=> the reference's hash query pairs the two primitives, no
@@ -403,9 +429,9 @@ __global__ void __launch_bounds__(32 * kCellPairWarps) k_cell_pairs_ee(const Gri
                 }
             }
         }
-        __syncwarp();
+        warp_stage_flush(stage, out, lane, kWarpStageCap / 2); // (also the warp-level barrier before the queries' slots are reused)
     }
-    pair_stage_flush(stage, out);
+    warp_stage_flush(stage, out, lane, 1u);
 }
 
 // The point-triangle twin: queries = 32 consecutive entries of the sorted VERTEX segment (points, or swept vertex boxes for the CCD),
@@ -415,11 +441,13 @@ __global__ void __launch_bounds__(32 * kCellPairWarps) k_cell_pairs_ee(const Gri
 __global__ void __launch_bounds__(32 * kCellPairWarps) k_cell_pairs_pt(const Grid* __restrict__ gp, SortedGrid vg, SortedGrid tg, const int* __restrict__ SVI,
     const int* __restrict__ SF, int nSF, double radius_val, const double* __restrict__ radius_ptr, const IterState* __restrict__ vox, int first, int last, PairOut out)
 {
-    __shared__ PairStage stage;
+    __shared__ WarpStage sStage[kCellPairWarps];
     __shared__ AEntry sA[kCellPairWarps][32];
-    pair_stage_init(stage);
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    WarpStage& stage = sStage[wib];
+    if (lane == 0) stage.count = 0;
+    __syncwarp();
     const Grid g = *gp;
     // Two kinds of entry boxes (k_cell_scatter): quantised double boxes (static grid: the query is inflated by `radius` in lattice steps) or
     // ranges of reference voxels (swept grid, vox != nullptr: ranges overlap <=> the reference's hash query pairs the two primitives, no
@@ -515,9 +543,9 @@ __global__ void __launch_bounds__(32 * kCellPairWarps) k_cell_pairs_pt(const Gri
                 }
             }
         }
-        __syncwarp();
+        warp_stage_flush(stage, out, lane, kWarpStageCap / 2); // (also the warp-level barrier before the queries' slots are reused)
     }
-    pair_stage_flush(stage, out);
+    warp_stage_flush(stage, out, lane, 1u);
 }
 
 // ---- phase 2: exact closest-feature classification, one THREAD per surviving pair (dense, convergent)

@@ -6,6 +6,8 @@ who owns what (which CSR rows to fetch from which rank) and for the CPU-side tes
   assembly  : rank r assembles every tet that touches one of its vertices (boundary tets are assembled by both neighbours) and keeps
               the blocks (v, u), v <= u, whose ROW vertex v it owns; the owned rows of the CSR are then complete without any reduction
   contact   : a pair is assembled by every rank that owns one of its stencil vertices; each keeps the block rows it owns
+  fused E   : in ipcgpu_elastic_energy_grad_hess a tet's energy is counted by the rank that owns its SMALLEST vertex: every tet exactly once,
+              and that rank assembles the tet anyway
 """
 import numpy as np
 
@@ -37,3 +39,9 @@ def assembled_tets(T, vb, ve):
 def owned_value_range(ia, index_base, vb, ve):
     """[begin, end) of the CSR values of rows 3*vb .. 3*ve-1"""
     return int(ia[3 * vb]) - index_base, int(ia[3 * ve]) - index_base
+
+
+def energy_tets(T, vb, ve):
+    """ids of the tets whose energy rank [vb, ve) counts in the fused energy + gradient + Hessian pass: smallest vertex owned"""
+    vmin = np.asarray(T).min(axis=1)
+    return np.nonzero((vmin >= vb) & (vmin < ve))[0]

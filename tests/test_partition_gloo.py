@@ -151,3 +151,20 @@ def test_row_owner_partition_gloo():
     for p in procs:
         p.join(120)
     assert q.get(timeout=5) is True
+
+
+def test_fused_energy_ownership_counts_every_tet_once_and_inside_the_assembled_set():
+    """the rule of ipcgpu_elastic_energy_grad_hess on several ranks (kernels.h: ElasticArgs::e_row_lo / e_row_hi)"""
+    from ipc_b200 import mesh as M, partition as P
+    V, T = M.grid_tets(7, 6, 5)
+    rng = np.random.default_rng(0)
+    T = T[rng.permutation(len(T))]
+    nV = len(V)
+    for world in (1, 2, 3, 8):
+        b = P.vertex_boundaries(T, nV, world)
+        seen = np.zeros(len(T), dtype=int)
+        for r in range(world):
+            mine = P.energy_tets(T, b[r], b[r + 1])
+            seen[mine] += 1
+            assert np.isin(mine, P.assembled_tets(T, b[r], b[r + 1])).all()  # the rank that counts a tet also runs the kernel on it
+        assert (seen == 1).all()
