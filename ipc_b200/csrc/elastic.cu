@@ -135,8 +135,8 @@ DEV void tma_store_tile(void* gdst, const void* ssrc, unsigned bytes)
 // TILES 64-tet tiles per CTA: the warps of a CTA walk the (6.6 k instruction) body in step -- every slot ends in a CTA barrier -- so a larger CTA
 // means fewer distinct instruction streams per SM competing for the instruction caches (ncu, round 1: "no instruction" 1.9 stalls per issue
 // with eight independent 64-thread CTAs per SM).  The tile layout of the output does not change: half-CTA h works on tile blockIdx.x * TILES + h.
-template <int ENERGY, bool NEED_G, bool NEED_H, int TILES>
-__global__ void __launch_bounds__(kHessTile * TILES, 8 / TILES) k_elastic_grad_hess(ElasticArgs p, double coef, int projectSPD,
+template <int ENERGY, bool NEED_G, bool NEED_H, int TILES, int MINB = 8>
+__global__ void __launch_bounds__(kHessTile * TILES, MINB / TILES) k_elastic_grad_hess(ElasticArgs p, double coef, int projectSPD,
     double* __restrict__ gcont /* 12 per LOCAL tet */, double* __restrict__ hblk /* tile-major, 78 per LOCAL tet */, double* __restrict__ e_partials /* nullable */,
     const unsigned* __restrict__ hdst /* nullable: slot-major destinations, 10 per LOCAL tet */, double* __restrict__ hcon)
 {
@@ -674,7 +674,23 @@ static void launch_gh(const ElasticArgs& p, double coef, int projectSPD, double*
         cudaFuncSetAttribute(k_elastic_grad_hess<ENERGY, G, H, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * smem));
         attr_set = true;
     }
-    if (tiles == 1) k_elastic_grad_hess<ENERGY, G, H, 1><<<nb, kHessTile, smem, st>>>(p, coef, projectSPD, gcont, hblk, e_partials, hdst, hcon);
+    static const int minb = [] { const char* e = std::getenv("IPCGPU_TET_MINB"); return e ? std::atoi(e) : 8; }(); // CTAs/SM the kernel is compiled for: 8 = 128 registers
+    if (tiles == 1 && minb == 10) {
+        static bool a10 = false;
+        if (!a10) { cudaFuncSetAttribute(k_elastic_grad_hess<ENERGY, G, H, 1, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); a10 = true; }
+        k_elastic_grad_hess<ENERGY, G, H, 1, 10><<<nb, kHessTile, smem, st>>>(p, coef, projectSPD, gcont, hblk, e_partials, hdst, hcon);
+    }
+    else if (tiles == 1 && minb == 12) {
+        static bool a12 = false;
+        if (!a12) { cudaFuncSetAttribute(k_elastic_grad_hess<ENERGY, G, H, 1, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); a12 = true; }
+        k_elastic_grad_hess<ENERGY, G, H, 1, 12><<<nb, kHessTile, smem, st>>>(p, coef, projectSPD, gcont, hblk, e_partials, hdst, hcon);
+    }
+    else if (tiles == 1 && minb == 6) {
+        static bool a6 = false;
+        if (!a6) { cudaFuncSetAttribute(k_elastic_grad_hess<ENERGY, G, H, 1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); a6 = true; }
+        k_elastic_grad_hess<ENERGY, G, H, 1, 6><<<nb, kHessTile, smem, st>>>(p, coef, projectSPD, gcont, hblk, e_partials, hdst, hcon);
+    }
+    else if (tiles == 1) k_elastic_grad_hess<ENERGY, G, H, 1><<<nb, kHessTile, smem, st>>>(p, coef, projectSPD, gcont, hblk, e_partials, hdst, hcon);
     else if (tiles == 2) k_elastic_grad_hess<ENERGY, G, H, 2><<<(nb + 1) / 2, 2 * kHessTile, 2 * smem, st>>>(p, coef, projectSPD, gcont, hblk, e_partials, hdst, hcon);
     else k_elastic_grad_hess<ENERGY, G, H, 4><<<(nb + 3) / 4, 4 * kHessTile, 4 * smem, st>>>(p, coef, projectSPD, gcont, hblk, e_partials, hdst, hcon);
 }
