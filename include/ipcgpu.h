@@ -274,6 +274,32 @@ int ipcgpu_hash_build_swept(ipcgpu_ctx* ctx, const double* p_interleaved /* NULL
 /* largestFeasibleStepSize_CCD_TightInclusion (SelfCollisionHandler.cpp:1370-1630) over the candidates of the swept hash.
  * n_candidates (may be NULL) receives the number of PT+EE pairs sent to the narrow phase. */
 int ipcgpu_ccd_full_ti(ipcgpu_ctx* ctx, double tolerance, const double err_vf[3], const double err_ee[3], double* alpha_inout, uint64_t* n_candidates);
+/* ---- kinematic mesh obstacle: MeshCO<3> (src/CollisionObject/MeshCO.hpp:39-233; SURVEY 8 row f3, barrier / Tight-Inclusion path) --------------------
+ * An obstacle is a triangle mesh without degrees of freedom (MeshCO's Base::V, edges, Base::F).  It rides at the TAIL of the mesh's arrays: the
+ * caller appends the obstacle's vertices to the vertex arrays of ipcgpu_set_mesh (rest = current positions, Dirichlet flag 1, mass 0, no
+ * tetrahedron uses them) and its vertices / edges / triangles, re-indexed, to the arrays of ipcgpu_set_surface, then names the first obstacle
+ * vertex here.  From then on the contact stages -- ipcgpu_contact_constraint_set, barrier energy / gradient / Hessian, evaluate_constraints,
+ * J^T, partial and full CCD, ipcgpu_intersection_free -- cover the mesh against itself AND the mesh against the obstacle:
+ *   - pairs of the mesh with the obstacle follow MeshCO.cpp: no Dirichlet / codimension filter (MeshCO.cpp:1795-2100), a mesh vertex and an
+ *     obstacle vertex closest to each other form ONE point-point entry however they were found (:1831, :1919, :2168-2190), the full pair
+ *     stencil is differentiated and projected (makePD of the 6x6 / 9x9 / 12x12 block, :430-560) and only the mesh vertices' rows and columns
+ *     are scattered (the obstacle's rows are Dirichlet rows of the system: identity);  pairs inside the obstacle do not exist;
+ *   - entries are reported in the self-contact encoding over the merged numbering (an obstacle vertex k is vertex first_obstacle_vertex + k);
+ *     adapters/IpcGpuAdapters.hpp splits them into the SelfCollisionHandler's and MeshCO's own MMCVID lists;
+ *   - step bounds: one minimum over both kinds of pairs (the reference takes MeshCO's bound, then the self-contact bound, each with the
+ *     running step as max_t: the same minimum).  ee_through_vf_routine != 0 (what the reference does, MeshCO.cpp:900-940 and :1609-1655):
+ *     Tight-Inclusion evaluates a mesh-edge / obstacle-edge pair with vertexFaceCCD_double on the four points in edge order, edge-edge error
+ *     bound and initial distance; 0: with edgeEdgeCCD_double.
+ * Everything sized by the vertex count (positions, search direction, gradient, CSR rows) includes the tail: the obstacle's search direction is
+ * zero, its gradient rows are Dirichlet rows (whatever the barrier terms add there is discarded with them), its CSR rows hold the identity; because the tail's rows come last and no mesh row has a column in them,
+ * the mesh's own upper-triangular CSR values are a PREFIX of the value array.  first_obstacle_vertex < 0 or >= nV removes the obstacle.
+ * Not covered: friction against the obstacle (MeshCO's friction overrides), the CTCD variants, SQP. */
+int ipcgpu_set_obstacle_tail(ipcgpu_ctx* ctx, int first_obstacle_vertex, int ee_through_vf_routine);
+/* MeshCO::move / Base::V after a scripted motion: new positions of the obstacle's vertices, SoA [x | y | z] over the obstacle's own count;
+ * current and rest positions of the tail are both replaced (an obstacle has no rest shape: compute_eps_x(mesh, Base::V, ...) uses its current
+ * edge lengths, MeshCollisionUtils.hpp:2976-2981) */
+int ipcgpu_set_obstacle_positions(ipcgpu_ctx* ctx, const double* Vo_soa);
+
 /* diagnostics of the last narrow phase: candidates tested, pairs surviving the root box, conservative early-outs (should be 0) */
 int ipcgpu_ccd_stats(ipcgpu_ctx* ctx, uint64_t* candidates, uint64_t* survivors, uint64_t* warnings);
 /* more diagnostics: pairs handed from the thread-level to the warp-level pass, parameter boxes evaluated by each pass */

@@ -491,6 +491,7 @@ int ipcgpu_set_mesh(ipcgpu_ctx* ctx, int nV, int nT, const double* Vrest, const 
     ctx->nV = nV;
     ctx->nT = nT;
     ctx->energy = energy;
+    ctx->nVdof = 0x7fffffff; // a new mesh has no obstacle tail until ipcgpu_set_obstacle_tail names one
     ctx->h_T.assign(tets, tets + (size_t)4 * nT);
     ctx->h_ia.clear();
     ctx->nnz = 0;
@@ -836,6 +837,44 @@ int ipcgpu_set_surface(ipcgpu_ctx* ctx, int nSV, const int* SVI, int nSE, const 
     if (rc) return rc;
     if ((rc = ccd_alloc(ctx))) return rc;
     ctx->surface_ready = true;
+    return IPCGPU_OK;
+}
+
+int ipcgpu_set_obstacle_tail(ipcgpu_ctx* ctx, int first_obstacle_vertex, int ee_through_vf_routine)
+{
+    ++ctx->epoch; // graphs captured before this call are refused (the pair rules change)
+    REQUIRE(ctx->nV > 0, IPCGPU_ERR_STATE, "ipcgpu_set_mesh first");
+    if (first_obstacle_vertex < 0 || first_obstacle_vertex >= ctx->nV) { // no obstacle
+        ctx->nVdof = 0x7fffffff;
+        ctx->ee_as_vf = ee_through_vf_routine ? 1 : 0;
+        return IPCGPU_OK;
+    }
+    REQUIRE(first_obstacle_vertex > 0, IPCGPU_ERR_ARG, "the mesh needs at least one vertex of its own");
+    for (size_t i = 0; i < ctx->h_T.size(); ++i) REQUIRE(ctx->h_T[i] < first_obstacle_vertex, IPCGPU_ERR_ARG, "a tetrahedron uses an obstacle vertex");
+    REQUIRE(ctx->has_dbc, IPCGPU_ERR_STATE, "the obstacle's vertices must be flagged Dirichlet (1) in ipcgpu_set_mesh: their rows never reach the system");
+    {
+        std::vector<uint8_t> tail((size_t)(ctx->nV - first_obstacle_vertex));
+        CK(cudaMemcpyAsync(tail.data(), ctx->dbc.p + first_obstacle_vertex, tail.size(), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (uint8_t f : tail) REQUIRE(f == 1, IPCGPU_ERR_ARG, "the obstacle's vertices must be flagged Dirichlet (1) in ipcgpu_set_mesh");
+    }
+    ctx->nVdof = first_obstacle_vertex;
+    ctx->ee_as_vf = ee_through_vf_routine ? 1 : 0;
+    return IPCGPU_OK;
+}
+
+int ipcgpu_set_obstacle_positions(ipcgpu_ctx* ctx, const double* Vo_soa)
+{
+    REQUIRE(ctx->nV > 0 && ctx->nVdof < ctx->nV, IPCGPU_ERR_STATE, "ipcgpu_set_obstacle_tail first");
+    REQUIRE(Vo_soa, IPCGPU_ERR_ARG, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    const size_t nVo = (size_t)(ctx->nV - ctx->nVdof);
+    // current AND rest positions: the obstacle has no rest shape of its own, compute_eps_x takes its current edge lengths
+    // (MeshCollisionUtils.hpp:2976-2981); SoA with the stride of the whole vertex array
+    for (double* dst : { ctx->V.p, ctx->Vrest.p })
+        CK(cudaMemcpy2DAsync(dst + ctx->nVdof, (size_t)ctx->nV * sizeof(double), Vo_soa, nVo * sizeof(double), nVo * sizeof(double), 3, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream)); // (pageable host memory)
+    ctx->mark_inputs();
     return IPCGPU_OK;
 }
 

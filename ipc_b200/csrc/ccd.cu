@@ -205,7 +205,9 @@ __global__ void __launch_bounds__(256) k_ccd_filter_pt(SurfArgs s, const int2* _
     int lo[3], hi[3];
     prim_range(vmin, vmax, tv, 3, lo, hi);
     if (!ranges_overlap(vmin + 3 * (size_t)vI, vmax + 3 * (size_t)vI, lo, hi)) continue; // the reference's hash would not pair them
-    if ((cod_v(s, vI) < 3 && cod_v(s, tv[0]) < 3) || (dbc_v(s, vI) && dbc_v(s, tv[0]) && dbc_v(s, tv[1]) && dbc_v(s, tv[2]))) continue;
+    const bool oP = obstacle_vertex(s, vI), oT = obstacle_vertex(s, tv[0]); // mesh-obstacle pairs are not filtered (MeshCO.cpp:1396-1570)
+    if (oP && oT) continue;
+    if (!oP && !oT && ((cod_v(s, vI) < 3 && cod_v(s, tv[0]) < 3) || (dbc_v(s, vI) && dbc_v(s, tv[0]) && dbc_v(s, tv[1]) && dbc_v(s, tv[2])))) continue;
     push_cand(out, make_int2(-svI - 1, sfI));
     }
 }
@@ -228,7 +230,9 @@ __global__ void __launch_bounds__(256) k_ccd_filter_ee(SurfArgs s, const int2* _
         for (int c = 0; c < 3; ++c) sep = sep || (jb.lo[c] - eb.hi[c] > 0.0) || (eb.lo[c] - jb.hi[c] > 0.0);
         if (sep) continue;
     }
-    if ((cod_v(s, a[0]) < 3 && cod_v(s, b[0]) < 3) || (dbc_v(s, a[0]) && dbc_v(s, a[1]) && dbc_v(s, b[0]) && dbc_v(s, b[1]))) continue;
+    const bool oA = obstacle_vertex(s, a[0]), oB = obstacle_vertex(s, b[0]); // (MeshCO.cpp:1576-1660)
+    if (oA && oB) continue;
+    if (!oA && !oB && ((cod_v(s, a[0]) < 3 && cod_v(s, b[0]) < 3) || (dbc_v(s, a[0]) && dbc_v(s, a[1]) && dbc_v(s, b[0]) && dbc_v(s, b[1])))) continue;
     push_cand(out, make_int2(eI, eJ));
     }
 }
@@ -238,7 +242,12 @@ __global__ void __launch_bounds__(256) k_ccd_filter_ee(SurfArgs s, const int2* _
 // ------------------------------------------------------------------------------------------------------------------
 struct TiPair {
     double x0[12], x1[12]; // 4 vertices at t=0 / t=1 ; VF: (p,t0,t1,t2)  EE: (a0,a1,b0,b1)
+    // 1: an edge pair of the mesh and the obstacle that runs through the vertex-face ROUTINE on its four points in edge order (MeshCO.cpp:900-940,
+    // :1609-1655 call vertexFaceCCD_double there) while its initial distance and its error bound stay the edge-edge ones
+    int ee_metric;
 };
+// the routine flag `vf` says which inclusion function runs; distance and error bound follow the kind of the PAIR
+DEV bool vf_metric(bool vf, const TiPair& P) { return vf && !P.ee_metric; }
 struct DBox { // parameter box: [n/2^k, (n+1)/2^k] per axis; kk = tk | uk<<8 | vk<<16 | flags<<24
     unsigned long long tn, un, vn;
     unsigned kk;
@@ -336,6 +345,11 @@ DEV void load_pair(const SurfArgs& s, const double* __restrict__ dir, int2 c, bo
     else {
         v[0] = s.SE[2 * c.x]; v[1] = s.SE[2 * c.x + 1]; v[2] = s.SE[2 * c.y]; v[3] = s.SE[2 * c.y + 1];
     }
+    P.ee_metric = 0;
+    if (!vf && s.ee_as_vf && obstacle_vertex(s, v[0]) != obstacle_vertex(s, v[2])) { // (mesh edge first: its sorted index is the smaller one)
+        vf = true;
+        P.ee_metric = 1;
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k)
 #pragma unroll
@@ -349,7 +363,7 @@ DEV void load_pair(const SurfArgs& s, const double* __restrict__ dir, int2 c, bo
 DEV double pair_distance_sqrt(bool vf, const TiPair& P)
 {
     const V3 a = { P.x0[0], P.x0[1], P.x0[2] }, b = { P.x0[3], P.x0[4], P.x0[5] }, c = { P.x0[6], P.x0[7], P.x0[8] }, d = { P.x0[9], P.x0[10], P.x0[11] };
-    return sqrt(vf ? point_tri_d(a, b, c, d) : edge_edge_d(a, b, c, d));
+    return sqrt(vf_metric(vf, P) ? point_tri_d(a, b, c, d) : edge_edge_d(a, b, c, d));
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -386,7 +400,7 @@ __global__ void __launch_bounds__(128) k_ti_stage1(NarrowArgs a, unsigned* __res
             DBox root = { 0ull, 0ull, 0ull, 0u, 0u };
             bool box_in;
             double tt[3];
-            alive = origin_in_box(vf, P, root, vf ? a.err_vf : a.err_ee, ms, box_in, tt);
+            alive = origin_in_box(vf, P, root, vf_metric(vf, P) ? a.err_vf : a.err_ee, ms, box_in, tt);
         }
     }
     // warp-aggregated append of the survivors
@@ -972,7 +986,7 @@ __device__ int pair_ccd(bool vf, const TiPair& P, const NarrowArgs& a, DBox* buf
 {
     const double d = pair_distance_sqrt(vf, P);
     const double max_t = a.st->max_t;                 // canonical semantics: every pair sees the step on entry
-    const double* err = vf ? a.err_vf : a.err_ee;
+    const double* err = vf_metric(vf, P) ? a.err_vf : a.err_ee;
     int hit = 0;
     // first trip: ms = min(0.2 d, 1e-6), pruned against the running device-wide minimum; second trip (:759-781, only after a hit with
     // toi < 1e-6): ms = 0, result scaled by 0.8 and NOT pruned -- a box starting in [best, 1.25 best) can still lower the global step
@@ -1242,7 +1256,7 @@ __global__ void __launch_bounds__(32 * kGrpWarpsPerCta, 4) k_ti_groups(NarrowArg
         const TiPair& P = Ps;
         const double d = pair_distance_sqrt(vf, P);
         const double ms = fmin(0.2 * d, 1e-6);
-        const double* err = vf ? a.err_vf : a.err_ee;
+        const double* err = vf_metric(vf, P) ? a.err_vf : a.err_ee;
         double toi;
         int hit = ti_ccd_grp(vf, P, err, ms, a.tol, max_t, a.max_itr, sA, sB, gl, gmask, toi, warn, best);
         if (hit == 1 && toi < 1e-6) { // :759-781 (no pruning here: the result is rescaled by 0.8, see pair_ccd)
@@ -1480,7 +1494,7 @@ __global__ void __launch_bounds__(128, 2) k_ti_stage15_refill(NarrowArgs a, cons
                 idx = survivors[w];
                 int v[4];
                 load_pair(a.s, a.dir, a.cand[idx], vf, v, P);
-                err = vf ? a.err_vf : a.err_ee;
+                err = vf_metric(vf, P) ? a.err_vf : a.err_ee;
                 dist = pair_distance_sqrt(vf, P);
                 attempt = 0;
                 // ti_ccd entry state of the first trip (pair_ccd): ms = min(0.2 d, 1e-6), pruned against the running minimum

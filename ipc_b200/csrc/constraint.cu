@@ -559,7 +559,10 @@ __global__ void __launch_bounds__(128) k_classify_pt(SurfArgs s, const int2* __r
     const int vI = s.SVI[svI];
     const int a = s.SF[sfI], b = s.SF[(size_t)s.nSF + sfI], c = s.SF[(size_t)2 * s.nSF + sfI];
     if (vI == a || vI == b || vI == c) continue;
-    if ((codim_v(s, vI) < 3 && codim_v(s, a) < 3) || (is_dbc_v(s, vI) && is_dbc_v(s, a) && is_dbc_v(s, b) && is_dbc_v(s, c))) continue;
+    // mesh against itself: the self-contact filter (:2184-2190); mesh against the obstacle: none (MeshCO.cpp:1803-1990); inside the obstacle: no pairs
+    const bool oP = obstacle_vertex(s, vI), oT = obstacle_vertex(s, a);
+    if (oP && oT) continue;
+    if (!oP && !oT && ((codim_v(s, vI) < 3 && codim_v(s, a) < 3) || (is_dbc_v(s, vI) && is_dbc_v(s, a) && is_dbc_v(s, b) && is_dbc_v(s, c)))) continue;
     const V3 p = load_vertex(s.V, s.nV, vI);
     const V3 ta = load_vertex(s.V, s.nV, a), tb_ = load_vertex(s.V, s.nV, b), tc = load_vertex(s.V, s.nV, c);
     const int ty = dType_PT(p, ta, tb_, tc);
@@ -574,6 +577,9 @@ __global__ void __launch_bounds__(128) k_classify_pt(SurfArgs s, const int2* __r
     case 5: d = d_PE(p, tc, ta); q = make_int4(-vI - 1, c, a, -1); break;
     default: d = d_PT(p, ta, tb_, tc); q = make_int4(-vI - 1, a, b, c);
     }
+    // an obstacle point against a mesh vertex is the same entry as that mesh vertex against the obstacle point: MeshCO writes both
+    // (-meshV - 1, obstacleV, -1, .) and counts them together (MeshCO.cpp:1831, :1919, :2168-2190)
+    if (ty <= 2 && oP) q = make_int4(-q.y - 1, vI, -1, -1);
     if (d < dHat) {
         if (q.w >= 0) push4(out.act, out.nAct, out.capAct, out.overflow, q);
         else push4(out.dup, out.nDup, out.capDup, out.overflow, q);
@@ -594,7 +600,9 @@ __global__ void __launch_bounds__(128) k_classify_ee(SurfArgs s, const int2* __r
     const int eI = pairs[i].x, eJ = pairs[i].y;
     const int a0 = s.SE[2 * eI], a1 = s.SE[2 * eI + 1], b0 = s.SE[2 * eJ], b1 = s.SE[2 * eJ + 1];
     if (a0 == b0 || a0 == b1 || a1 == b0 || a1 == b1) continue;
-    if ((codim_v(s, a0) < 3 && codim_v(s, b0) < 3) || (is_dbc_v(s, a0) && is_dbc_v(s, a1) && is_dbc_v(s, b0) && is_dbc_v(s, b1))) continue;
+    const bool oA = obstacle_vertex(s, a0), oB = obstacle_vertex(s, b0); // (:2294-2300; MeshCO.cpp:1996-2030)
+    if (oA && oB) continue;
+    if (!oA && !oB && ((codim_v(s, a0) < 3 && codim_v(s, b0) < 3) || (is_dbc_v(s, a0) && is_dbc_v(s, a1) && is_dbc_v(s, b0) && is_dbc_v(s, b1)))) continue;
     const V3 xa0 = load_vertex(s.V, s.nV, a0), xa1 = load_vertex(s.V, s.nV, a1), xb0 = load_vertex(s.V, s.nV, b0), xb1 = load_vertex(s.V, s.nV, b1);
     const int ty = dType_EE(xa0, xa1, xb0, xb1);
     const double cr = norm2(cross(xa1 - xa0, xb1 - xb0));
@@ -961,6 +969,7 @@ SurfArgs surf_args(const ipcgpu_ctx* ctx)
     SurfArgs s;
     s.nV = ctx->nV; s.V = ctx->V.p; s.Vrest = ctx->Vrest.p; s.dbc = ctx->has_dbc ? ctx->dbc.p : nullptr;
     s.vCoDim = ctx->has_codim ? ctx->vCoDim.p : nullptr;
+    s.nVdof = ctx->nVdof; s.ee_as_vf = ctx->ee_as_vf;
     s.nSV = ctx->nSV; s.SVI = ctx->SVI.p; s.nSE = ctx->nSE; s.SE = ctx->SE.p; s.nSF = ctx->nSF; s.SF = ctx->SF.p;
     return s;
 }

@@ -150,6 +150,8 @@ struct ipcgpu_ctx {
 
     // surface (Mesh::SVI / SFEdges / SF) and contact workspace
     int nSV = 0, nSE = 0, nSF = 0;
+    int nVdof = 0x7fffffff;  // first obstacle vertex (ipcgpu_set_obstacle_tail): vertices from here on have no degrees of freedom; INT_MAX = no obstacle
+    int ee_as_vf = 1;        // Tight-Inclusion of mesh-obstacle edge pairs through the vertex-face routine, as MeshCO.cpp:1609 calls it
     ipcgpu::DevBuf<int> SVI, SE, SF, vCoDim;
     bool has_codim = false, surface_ready = false;
     int pair_capacity = 1 << 20;

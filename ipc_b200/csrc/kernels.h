@@ -78,7 +78,13 @@ struct SurfArgs {
     int nSV; const int* SVI;
     int nSE; const int* SE;   // interleaved (first, second)   [Mesh::SFEdges]
     int nSF; const int* SF;   // SoA [v0|v1|v2]                [Mesh::SF column-major]
+    // kinematic obstacle (MeshCO): vertices >= nVdof belong to a triangle mesh without degrees of freedom that rides at the tail of the vertex
+    // arrays (ipcgpu_set_obstacle_tail; INT_MAX = none).  Pairs between the mesh and the obstacle follow MeshCO.cpp, pairs inside the obstacle
+    // do not exist.  ee_as_vf: Tight-Inclusion evaluates mesh-obstacle edge pairs through the vertex-face routine (MeshCO.cpp:1609)
+    int nVdof, ee_as_vf;
 };
+// which body a surface primitive belongs to is decided by any one of its vertices (primitives do not straddle bodies)
+__device__ __forceinline__ bool obstacle_vertex(const SurfArgs& s, int v) { return v >= s.nVdof; }
 
 struct BarrierArgs {
     int nV;

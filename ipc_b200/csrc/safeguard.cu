@@ -208,7 +208,10 @@ __global__ void __launch_bounds__(256) k_tri_edge_intersect(SurfArgs s, const Gr
             const int e0 = s.SE[2 * e], e1 = s.SE[2 * e + 1];
             if (e0 == tv[0] || e0 == tv[1] || e0 == tv[2] || e1 == tv[0] || e1 == tv[1] || e1 == tv[2]) return;
             const int cod_e = s.vCoDim ? s.vCoDim[e0] : 3;
-            if ((cod_f < 3 && cod_e < 3) || (tri_dbc && s.dbc[e0] && s.dbc[e1])) return; // :3281-3284
+            // mesh against itself: :3281-3284; mesh against the obstacle: every pair (MeshCO.cpp:2611-2678); inside the obstacle: none
+            const bool oT = obstacle_vertex(s, tv[0]), oE = obstacle_vertex(s, e0);
+            if (oT && oE) return;
+            if (!oT && !oE && ((cod_f < 3 && cod_e < 3) || (tri_dbc && s.dbc[e0] && s.dbc[e1]))) return;
             double p0[3], p1[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {

@@ -75,6 +75,8 @@ SIGNATURES = {
     "ipcgpu_ccd_stats": (C.c_int, [_ctxp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "ipcgpu_ccd_stats_ex": (C.c_int, [_ctxp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "ipcgpu_ccd_stats_timing": (C.c_int, [_ctxp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "ipcgpu_set_obstacle_tail": (C.c_int, [_ctxp, C.c_int, C.c_int]),
+    "ipcgpu_set_obstacle_positions": (C.c_int, [_ctxp, _dp]),
     "ipcgpu_set_prev_state": (C.c_int, [_ctxp, _dp]),
     "ipcgpu_friction_lag": (C.c_int, [_ctxp, C.c_double, C.c_double, _ip]),
     "ipcgpu_get_friction_data": (C.c_int, [_ctxp, _ip, _ip, _dp, _dp, _dp]),
@@ -377,6 +379,15 @@ class Context:
     def set_surface(self, SVI, SFEdges, SF_soa, vCoDim=None):
         SVI, SE, SF = i32(SVI).ravel(), i32(SFEdges).ravel(), i32(SF_soa).ravel()
         self._ck(self.lib.ipcgpu_set_surface(self.h, SVI.size, _i(SVI), SE.size // 2, _i(SE), SF.size // 3, _i(SF), _i(i32(vCoDim))))
+
+    def set_obstacle_tail(self, first_obstacle_vertex, ee_through_vf_routine=1):
+        """MeshCO hand-off: vertices from first_obstacle_vertex on are a kinematic obstacle (ipc_b200/obstacle.py builds the merged arrays);
+        a negative value removes the obstacle"""
+        self._ck(self.lib.ipcgpu_set_obstacle_tail(self.h, int(first_obstacle_vertex), int(ee_through_vf_routine)))
+
+    def set_obstacle_positions(self, Vo):
+        """Vo: (nVo, 3) new positions of the obstacle's vertices (MeshCO::move)"""
+        self._ck(self.lib.ipcgpu_set_obstacle_positions(self.h, _d(f64(np.ascontiguousarray(np.asarray(Vo, dtype=np.float64).T).ravel()))))
 
     def set_canonical_order(self, enable):
         self._ck(self.lib.ipcgpu_set_canonical_order(self.h, int(enable)))

@@ -313,3 +313,65 @@ def squeeze_out_tiled(seed=4, energy=0, dhat_rel=1e-3, gap_lo=0.3, gap_hi=1.2, c
     affine_prestrain(m)  # copies 0 and 2 would otherwise sit exactly at rest (see affine_prestrain)
     p = np.concatenate(push) + rng.normal(0, 0.05 * sq, (m.nV, 3))
     return m, dict(dHat=dHat, p=np.ascontiguousarray(p).ravel(), n_bodies=len(placed), tile=tile)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# a mesh next to a kinematic obstacle (row f3: MeshCO) -- test scene, seeded
+# ---------------------------------------------------------------------------------------------------------------------------------
+def surface_of(V, T):
+    """(V, E, F) of the boundary surface of a tet mesh with compact vertex numbering: what MeshCO loads from an .obj
+    (MeshCO.cpp:37-80: Base::V, Base::F, edges collected from F like Mesh::SFEdges)."""
+    SF = M.boundary_faces(np.asarray(T, dtype=np.int32))
+    used = np.unique(SF)
+    remap = -np.ones(len(V), dtype=np.int64)
+    remap[used] = np.arange(len(used))
+    F = remap[SF].astype(np.int32)
+    return np.ascontiguousarray(V[used], dtype=np.float64), M.surface_edges(F), F
+
+
+def balls_on_obstacle(n_balls=3, res=4, plate=12, seed=7, energy=0, dhat_rel=1e-3, gap_lo=0.3, gap_hi=1.2, plate_angle=0.37):
+    """A short column of rounded balls (self contact between them) whose lowest ball hovers U(gap_lo, gap_hi) sqrt(dHat) over an obstacle
+    plate, with a second obstacle body -- a rotated ball surface -- just beside the column.  The obstacle is ONE triangle mesh with two
+    components.  The search direction pushes the column down and toward the side body by 2-4 sqrt(dHat), so both step bounds bite.
+    Returns (mesh, info) with info["obstacle"] = dict(V, E, F) in the obstacle's own numbering."""
+    rng = np.random.default_rng(seed)
+    radius = 0.5
+    Vb, Tb = M.superball_tets(res, radius, 6.0)
+    ext = np.array([3.0, 3.0, n_balls * 2.0 * radius + 0.2])
+    dHat = dhat_rel ** 2 * float((ext ** 2).sum())
+    sq = np.sqrt(dHat)
+    parts, z = [], 0.0
+    for _ in range(n_balls):
+        th = rng.uniform(0, 2 * np.pi)
+        R = np.array([[np.cos(th), -np.sin(th), 0.0], [np.sin(th), np.cos(th), 0.0], [0.0, 0.0, 1.0]])
+        parts.append((Vb @ R.T + np.array([rng.normal(0, 0.01), rng.normal(0, 0.01), z]), Tb))
+        z += 2.0 * radius + rng.uniform(gap_lo, gap_hi) * sq
+    m = M.merge_meshes(parts, energy=energy)
+    local = m.V_rest - np.array([0.0, 0.0, 0.0])
+    m.V = m.V_rest + 0.004 * radius * np.stack([np.sin(5 * local[:, 1]), np.sin(5 * local[:, 0]), 0 * local[:, 2]], axis=1)
+    # obstacle 1: a plate under the column, slightly bumpy and rotated about z so that its edges are generically not parallel to the balls'
+    h = 3.0 / plate
+    Vp, Tp = M.grid_tets(plate, plate, 1, h=h, origin=(-1.5, -1.5, -h))
+    th = plate_angle  # 0: the plate's edges are parallel to the grid edges of the balls' flat poles (mollified entries)
+    Rz = np.array([[np.cos(th), -np.sin(th), 0.0], [np.sin(th), np.cos(th), 0.0], [0.0, 0.0, 1.0]])
+    Vp = Vp @ Rz.T
+    if plate_angle != 0.0:
+        Vp[:, 2] += 0.2 * sq * np.sin(3.1 * Vp[:, 0]) * np.cos(2.3 * Vp[:, 1])
+    Vp[:, 2] += m.V[:, 2].min() - rng.uniform(gap_lo, gap_hi) * sq - Vp[:, 2].max()
+    # obstacle 2: a ball surface beside the lowest ball of the column
+    th2 = 0.9
+    Ry = np.array([[np.cos(th2), 0.0, np.sin(th2)], [0.0, 1.0, 0.0], [-np.sin(th2), 0.0, np.cos(th2)]])
+    Vs = Vb @ Ry.T
+    low = m.V[: Vb.shape[0]]
+    Vs += np.array([low[:, 0].max() - Vs[:, 0].min() + rng.uniform(gap_lo, gap_hi) * sq, 0.013, low[:, 2].mean() - Vs[:, 2].mean() + 0.021])
+    V1, E1, F1 = surface_of(Vp, Tp)
+    V2, E2, F2 = surface_of(Vs, Tb)
+    Vo = np.concatenate([V1, V2])
+    Fo = np.concatenate([F1, F2 + len(V1)]).astype(np.int32)
+    Eo = M.surface_edges(Fo)
+    p = np.zeros((m.nV, 3))
+    p[:, 2] = -3.0 * sq * rng.uniform(0.6, 1.0, m.nV)
+    p[:, 0] = 2.0 * sq * rng.uniform(0.6, 1.0, m.nV)
+    p += rng.normal(0, 0.1 * sq, (m.nV, 3))
+    info = dict(dHat=dHat, p=np.ascontiguousarray(p).ravel(), obstacle=dict(V=Vo, E=Eo, F=Fo))
+    return m, info

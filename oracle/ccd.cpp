@@ -26,6 +26,7 @@
 #include <cstring>
 #include <limits>
 #include <atomic>
+#include <cstdlib>
 #include <vector>
 
 namespace {
@@ -161,6 +162,9 @@ bool root_finder(bool vf, const double* x0, const double* x1, const double tol[3
     toi = std::numeric_limits<double>::infinity();
     bool overflow = false;
     TiStat stat;
+    /* diagnostics only (sizing the GPU passes, never set by tests): ORC_TI_DIAG_PRUNE=<t> skips boxes that start at or after max(t, 1e-6), the
+     * GPU's pruning rule against the running minimum in the limit of an instantly known final step */
+    static const double diag_prune = [] { const char* e = std::getenv("ORC_TI_DIAG_PRUNE"); return e ? std::atof(e) : -1.0; }();
     while (!level.empty() && !overflow) {
         ++stat.levels;
         stat.width = std::max<long long>(stat.width, (long long)level.size());
@@ -176,6 +180,7 @@ bool root_finder(bool vf, const double* x0, const double* x1, const double tol[3
         for (const Box3& cur : level) {
             const double t_lo = lo_of(cur.t);
             if (!(t_lo < toi_skip)) continue;
+            if (diag_prune >= 0.0 && !(t_lo < std::max(diag_prune, 1e-6))) continue;
             ++refine;
             ++stat.boxes;
             bool box_in;

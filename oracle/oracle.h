@@ -171,6 +171,28 @@ int orc_constraint_set_hashed(const orc_surf* s, double dHat, double voxel_size,
 int orc_ccd_full_hashed(const orc_surf* s, const double* p, double* alpha_inout, double voxel_size, double tol,
     const double err_vf[3], const double err_ee[3], long long* nPairs, int nthreads);
 
+/* ---- kinematic mesh obstacles: MeshCO<3> (oracle/meshco.cpp) ------------------------------------------------------ */
+typedef struct {
+    int nV; const double* V;  /* SoA positions (Base::V) */
+    int nE; const int* E;     /* interleaved (first, second) (MeshCO::edges) */
+    int nF; const int* F;     /* SoA [v0|v1|v2] (Base::F column-major) */
+} orc_obstacle;
+/* MeshCO.cpp:1795-2223 in MeshCO's MMCVID encoding (negative = mesh vertex, non-negative = obstacle vertex); cand = cs_PTEE */
+int orc_meshco_constraint_set(const orc_surf* s, const orc_obstacle* o, double dHat, int cap, int* mmcvid, int* nC, int capP, int* para, int* para_eIeJ, int* nPara,
+    int capK, int* cand, int* nCand, int nthreads);
+/* the same entries in the self-contact encoding over the merged vertex numbering (obstacle vertex k = nV + k, obstacle edge j = nSE + j) */
+void orc_meshco_to_merged(int nV, int nSE, const int* mmcvid, int nC, int* out, const int* para_eIeJ, int nP, int* para_e_out);
+/* Optimizer.cpp:3268-3289 / :3480-3491 / :3686-3689 with MeshCO.cpp:83-200, :407-586, :2226-2520; g and the CSR are the MESH's */
+int orc_meshco_energy(const orc_surf* s, const orc_obstacle* o, const int* mmcvid, int nC, const int* para, const int* para_eIeJ, int nPara, double dHat, double kappa, double* E);
+void orc_meshco_gradient(const orc_surf* s, const orc_obstacle* o, const int* mmcvid, int nC, const int* para, const int* para_eIeJ, int nPara, double dHat, double kappa, double* g);
+void orc_meshco_hessian_csr(const orc_surf* s, const orc_obstacle* o, const int* mmcvid, int nC, const int* para, const int* para_eIeJ, int nPara, double dHat, double kappa,
+    int projectDBC, const int* ia, const int* ja, int index_base, double* a, int nthreads);
+/* MeshCO.cpp:742-980 and :1388-1668; ee_as_vf = 1: edge-edge pairs through the vertex-face routine, as the reference calls it */
+int orc_meshco_ccd_partial(const orc_surf* s, const orc_obstacle* o, const double* p, const int* cand, int nCand, double tol, const double evf[3], const double eee[3],
+    int ee_as_vf, double* alpha_inout, int nthreads);
+int orc_meshco_ccd_full(const orc_surf* s, const orc_obstacle* o, const double* p, double tol, const double evf[3], const double eee[3], int ee_as_vf, double* alpha_inout,
+    long long* nPairs, int nthreads);
+
 /* ---- line-search safeguards (oracle/intersect.cpp) --------------------------------------------------------------- */
 /* igl::predicates::orient3d restated (filter + exact expansion arithmetic): +1 / 0 / -1 */
 int orc_orient3d(const double* pa, const double* pb, const double* pc, const double* pd);

@@ -402,3 +402,75 @@ def orient3d(a, b, c, d_, exact=False):
 def seg_tri_intersect(e0, e1, t0, t1, t2):
     v = [np.ascontiguousarray(x, dtype=np.float64) for x in (e0, e1, t0, t1, t2)]
     return int(lib().orc_seg_tri_intersect(*[d(x) for x in v]))
+
+
+# ---- kinematic mesh obstacles: MeshCO<3> (oracle/meshco.cpp) ----------------------------------------------------------------------
+class OrcObstacle(C.Structure):
+    _fields_ = [("nV", C.c_int), ("V", _dp), ("nE", C.c_int), ("E", _ip), ("nF", C.c_int), ("F", _ip)]
+
+
+class Obstacle:
+    """A triangle mesh without degrees of freedom next to a Surf: V (nVo x 3), E (nEo x 2), F (nFo x 3), the obstacle's own indices."""
+
+    def __init__(self, surf, V, E, F):
+        self.surf = surf
+        self.Vo = np.ascontiguousarray(np.asarray(V, dtype=np.float64).T).ravel()
+        self.E = np.ascontiguousarray(E, dtype=np.int32).ravel()
+        self.F = np.ascontiguousarray(np.asarray(F, dtype=np.int32).T).ravel()
+        self.nV, self.nE, self.nF = len(V), len(E), len(F)
+        self.o = OrcObstacle(self.nV, d(self.Vo), self.nE, i(self.E), self.nF, i(self.F))
+
+    def constraint_set(self, dHat, nthreads=1, cap=1 << 18):
+        mm = np.empty((cap, 4), dtype=np.int32); pa = np.empty((cap, 4), dtype=np.int32); pe = np.empty((cap, 2), dtype=np.int32)
+        cand = np.empty((4 * cap, 2), dtype=np.int32)
+        nC, nP, nK = C.c_int(), C.c_int(), C.c_int()
+        rc = lib().orc_meshco_constraint_set(C.byref(self.surf.s), C.byref(self.o), C.c_double(dHat), cap, i(mm), C.byref(nC), cap, i(pa), i(pe), C.byref(nP),
+                                             4 * cap, i(cand), C.byref(nK), nthreads)
+        assert rc == 0, "oracle constraint-set capacity exceeded"
+        return mm[:nC.value].copy(), pa[:nP.value].copy(), pe[:nP.value].copy(), cand[:nK.value].copy()
+
+    def to_merged(self, mm, pe):
+        """MeshCO entries -> self-contact entries over the merged numbering (what the GPU library reports)"""
+        mm = np.ascontiguousarray(mm, dtype=np.int32); pe = np.ascontiguousarray(pe, dtype=np.int32)
+        out = np.empty_like(mm); pe_out = np.empty_like(pe)
+        lib().orc_meshco_to_merged(self.surf.mesh.nV, self.surf.SE.size // 2, i(mm), len(mm), i(out), i(pe), len(pe), i(pe_out))
+        return out, pe_out
+
+    def _sets(self, mm, pa, pe):
+        return tuple(np.ascontiguousarray(x, dtype=np.int32) for x in (mm, pa, pe))
+
+    def energy(self, mm, pa, pe, dHat, kappa):
+        mm, pa, pe = self._sets(mm, pa, pe)
+        E = C.c_double()
+        bad = lib().orc_meshco_energy(C.byref(self.surf.s), C.byref(self.o), i(mm), len(mm), i(pa), i(pe), len(pa), C.c_double(dHat), C.c_double(kappa), C.byref(E))
+        return E.value, bad
+
+    def gradient(self, mm, pa, pe, dHat, kappa, g=None):
+        mm, pa, pe = self._sets(mm, pa, pe)
+        if g is None:
+            g = np.zeros(3 * self.surf.mesh.nV)
+        lib().orc_meshco_gradient(C.byref(self.surf.s), C.byref(self.o), i(mm), len(mm), i(pa), i(pe), len(pa), C.c_double(dHat), C.c_double(kappa), d(g))
+        return g
+
+    def hessian_csr(self, mm, pa, pe, dHat, kappa, ia, ja, base, projectDBC=1, a=None, nthreads=1):
+        mm, pa, pe = self._sets(mm, pa, pe)
+        ia = np.ascontiguousarray(ia, dtype=np.int32); ja = np.ascontiguousarray(ja, dtype=np.int32)
+        if a is None:
+            a = np.zeros(ja.size)
+        lib().orc_meshco_hessian_csr(C.byref(self.surf.s), C.byref(self.o), i(mm), len(mm), i(pa), i(pe), len(pa), C.c_double(dHat), C.c_double(kappa), projectDBC,
+                                     i(ia), i(ja), base, d(a), nthreads)
+        return a
+
+    def ccd_partial(self, p, cand, tol, evf, eee, alpha, ee_as_vf=1, nthreads=1):
+        p = np.ascontiguousarray(p, dtype=np.float64); cand = np.ascontiguousarray(cand, dtype=np.int32)
+        a = C.c_double(alpha)
+        z = lib().orc_meshco_ccd_partial(C.byref(self.surf.s), C.byref(self.o), d(p), i(cand), len(cand), C.c_double(tol), d(np.ascontiguousarray(evf)),
+                                         d(np.ascontiguousarray(eee)), ee_as_vf, C.byref(a), nthreads)
+        return a.value, z
+
+    def ccd_full(self, p, tol, evf, eee, alpha, ee_as_vf=1, nthreads=1):
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        a = C.c_double(alpha); n = C.c_longlong()
+        z = lib().orc_meshco_ccd_full(C.byref(self.surf.s), C.byref(self.o), d(p), C.c_double(tol), d(np.ascontiguousarray(evf)), d(np.ascontiguousarray(eee)), ee_as_vf,
+                                      C.byref(a), C.byref(n), nthreads)
+        return a.value, z, n.value
