@@ -375,3 +375,28 @@ def balls_on_obstacle(n_balls=3, res=4, plate=12, seed=7, energy=0, dhat_rel=1e-
     p += rng.normal(0, 0.1 * sq, (m.nV, 3))
     info = dict(dHat=dHat, p=np.ascontiguousarray(p).ravel(), obstacle=dict(V=Vo, E=Eo, F=Fo))
     return m, info
+
+
+def ball_on_obstacle_mat(nx=200, seed=3, energy=0, dhat_rel=1e-3, gap_lo=0.2, gap_hi=1.5):
+    """BASELINE config C3's pair of bodies with the mat as a kinematic OBSTACLE (what 12_sphereOnMat.txt would be with the mat loaded through
+    `meshCO`): the mesh is input/tetMeshes/sphere1K.msh alone, the obstacle is the surface of the nx x nx x 1 mat (nx = 200: 80,802 vertices,
+    160,800 triangles).  Same placement, gap and search direction as ball_on_mat_c3.  Returns (mesh, info) with info["obstacle"]."""
+    rng = np.random.default_rng(seed)
+    h = 1.0 / nx
+    Vm, Tm = M.grid_tets(nx, nx, 1, h=h)
+    Vb, Tb, SFb = msh.load_asset("sphere1K")
+    radius = 0.15
+    Vb = shape_transform(Vb - 0.5 * (Vb.max(0) + Vb.min(0)), rotate_deg=(90, 0, 45), scale=(2 * radius,) * 3)
+    ext = np.array([1.0, 1.0, h + 2 * radius])
+    dHat = dhat_rel ** 2 * float((ext ** 2).sum())
+    sq = np.sqrt(dHat)
+    gap = rng.uniform(gap_lo, gap_hi) * sq
+    Vm_def = Vm + 0.02 * h * rng.standard_normal((Vm.shape[0], 3)) * np.array([1.0, 1.0, 0.2])
+    c = np.array([0.5 + 0.31 * h, 0.5 - 0.17 * h, Vm_def[:, 2].max() + gap - Vb[:, 2].min()])
+    m = M.merge_meshes([(Vb + c, Tb, SFb)], energy=energy)
+    affine_prestrain(m)
+    Vo, Eo, Fo = surface_of(Vm_def, Tm)
+    p = np.zeros((m.nV, 3))
+    p[:, 2] = -rng.uniform(0.0, 2.0, m.nV) * sq
+    p += rng.normal(0, 0.05 * sq, (m.nV, 3))
+    return m, dict(dHat=dHat, p=np.ascontiguousarray(p).ravel(), gap=gap, obstacle=dict(V=Vo, E=Eo, F=Fo))

@@ -1,5 +1,6 @@
 // Instantiates every adapter against the restated reference interface (syntax/semantic check only: g++ -fsyntax-only).
 #include "IpcGpuAdapters.hpp"
+#include "IpcGpuMeshCO.hpp"
 template class IPC::GpuElasticEnergy<3>;
 void touch(IPC::IpcGpuScene& s, const IPC::Mesh<3>& m, IPC::LinSysSolver<Eigen::VectorXi, Eigen::VectorXd>* sol, const IPC::SpatialHash<3>& sh)
 {
@@ -32,4 +33,27 @@ void touch(IPC::IpcGpuScene& s, const IPC::Mesh<3>& m, IPC::LinSysSolver<Eigen::
     H::largestFeasibleStepSize_TightInclusion(m, sh, v, 1e-6, d, d, x);
     H::hashBuildSwept(v, x, 0.1);
     H::largestFeasibleStepSize_CCD_TightInclusion(m, sh, v, 1e-6, d, x);
+    // kinematic obstacle: MeshCO's signatures (MeshCO.hpp:56-181) over the merged device pass
+    using O = IPC::GpuMeshCO;
+    Eigen::MatrixXd Vo;
+    Eigen::MatrixXi Fo;
+    O::attach(s, m, Vo, Fo, c, IPCGPU_NEOHOOKEAN);
+    O::setPattern(sol, 1);
+    O::setState(m);
+    O::moved(Vo);
+    std::vector<double> pd = O::padDirection(v);
+    O::computeConstraintSet(m, sh, 1e-6, a, b, c, true, d);
+    O::computeSelfConstraintSet(m, sh, 1e-6, a, b, c, true, d);
+    O::evaluateConstraints(m, a, v);
+    O::leftMultiplyConstraintJacobianT(m, a, v, v, 1e8);
+    O::augmentIPHessian(m, a, sol, 1e-6, 1e8, true);
+    O::augmentParaEEHessian(m, b, c, sol, 1e-6, 1e8, true);
+    O::largestFeasibleStepSize_TightInclusion(m, sh, v, 1e-6, d, x);
+    O::largestFeasibleStepSize_CCD_TightInclusion(m, sh, v, 1e-6, x);
+    (void)O::checkEdgeTriIntersectionIfAny(m, sh);
+    O::fetchValues(sol);
+    O::fetchGradient(v);
+    int q[4] = { 0, 1, 2, 3 };
+    (void)O::toMerged(O::toMeshCO(q).data.data());
+    (void)pd;
 }

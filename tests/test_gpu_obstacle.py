@@ -161,3 +161,38 @@ def test_tail_is_validated(gpu_ctx):
         gpu_ctx.set_mesh(m.V_rest_soa, m.T_soa, m.restTriInv, m.vol, m.mu, m.lam, m.mass, np.ones(m.nV, dtype=np.uint8), m.energy)
         gpu_ctx.set_obstacle_tail(m.nV - 1)
     remove_obstacle(gpu_ctx)
+
+
+@pytest.mark.skipif(not __import__("ipc_b200.msh", fromlist=["msh"]).have_asset("sphere1K"), reason="assets/_ref cache missing")
+def test_c3_ball_over_the_mat_as_obstacle(ctx):
+    """BASELINE config C3's bodies with the 200 x 200 mat as the obstacle (80,802 obstacle vertices, 161,600 triangles against sphere1K.msh)"""
+    m, info = scenes.ball_on_obstacle_mat(200)
+    ob = info["obstacle"]
+    s = orc.Surf(m)
+    o = orc.Obstacle(s, ob["V"], ob["E"], ob["F"])
+    M2 = OB.with_obstacle(m, ob["V"], ob["E"], ob["F"])
+    dHat, p = info["dHat"], info["p"]
+    upload(ctx, M2)
+    mm, pa, pe, cand = ctx.constraint_set(dHat, 1)
+    (smm, spa, spe), (cmm, cpa, cpe) = OB.split_sets(mm, pa, pe, m.nV, len(m.SFEdges))
+    mm_o, pa_o, pe_o, cand_o = o.constraint_set(dHat, NTH)
+    assert len(smm) == 0 and len(mm_o) > 50 and np.array_equal(lex(cmm), mm_o)
+    sc, cc = OB.split_candidates(cand, len(m.SVI), len(m.SF), len(m.SFEdges))
+    assert len(sc) == 0 and np.array_equal(lex(cc), cand_o)
+    E_ref = o.energy(mm_o, pa_o, pe_o, dHat, KAPPA)[0]
+    assert abs(ctx.barrier_energy(dHat, KAPPA) - E_ref) <= 1e-10 * abs(E_ref)
+    g = np.zeros(3 * M2.nV)
+    ctx.barrier_gradient(dHat, KAPPA, g)
+    assert rel(g[: 3 * m.nV], o.gradient(mm_o, pa_o, pe_o, dHat, KAPPA)) <= 1e-10
+    evf, eee = L.Context.ti_error(m.V_soa, m.nV, None)
+    p2 = OB.pad_direction(p, M2.nV)
+    a = ctx.ccd_partial(p2, 1e-6, evf, eee, 1.0)
+    a_co, z = o.ccd_partial(p, cand_o, 1e-6, evf, eee, 1.0, nthreads=NTH)
+    assert not z and a_co < 1.0 and bits(a) == bits(a_co)
+    # the full CCD from the untouched step: every swept mesh primitive against the mat
+    hvox = m.avgEdgeLen / 3.0
+    ag = ctx.hash_build_swept(p2, 1.0, hvox)
+    a2, ncand = ctx.ccd_full(1e-6, evf, eee, ag)
+    a2_co, z, npairs = o.ccd_full(p, 1e-6, evf, eee, ag, nthreads=NTH)
+    assert not z and npairs > 0 and ncand > 0 and bits(a2) == bits(a2_co), (a2, a2_co)
+    assert ctx.ccd_stats()[2] == 0 and ctx.intersection_free()
