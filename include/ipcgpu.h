@@ -293,7 +293,8 @@ int ipcgpu_ccd_full_ti(ipcgpu_ctx* ctx, double tolerance, const double err_vf[3]
  * Everything sized by the vertex count (positions, search direction, gradient, CSR rows) includes the tail: the obstacle's search direction is
  * zero, its gradient rows are Dirichlet rows (whatever the barrier terms add there is discarded with them), its CSR rows hold the identity; because the tail's rows come last and no mesh row has a column in them,
  * the mesh's own upper-triangular CSR values are a PREFIX of the value array.  first_obstacle_vertex < 0 or >= nV removes the obstacle.
- * Not covered: friction against the obstacle (MeshCO's friction overrides), the CTCD variants, SQP. */
+ * Friction: the reference implements none against a MeshCO (CollisionObject.h:403-423 throw "not implemented"); ipcgpu_friction_lag lags the pairs
+ * that touch the obstacle with a zero normal force, so the friction terms stay those of the mesh's own pairs.  Not covered: the CTCD variants, SQP. */
 int ipcgpu_set_obstacle_tail(ipcgpu_ctx* ctx, int first_obstacle_vertex, int ee_through_vf_routine);
 /* MeshCO::move / Base::V after a scripted motion: new positions of the obstacle's vertices, SoA [x | y | z] over the obstacle's own count;
  * current and rest positions of the tail are both replaced (an obstacle has no rest shape: compute_eps_x(mesh, Base::V, ...) uses its current

@@ -1122,6 +1122,7 @@ static BarrierArgs barrier_args(ipcgpu_ctx* ctx, double dHat, double kappa, int 
     BarrierArgs p;
     ContactWork& w = ctx->cw;
     p.nV = ctx->nV; p.V = ctx->V.p; p.Vrest = ctx->Vrest.p; p.dbc = ctx->has_dbc ? ctx->dbc.p : nullptr; p.SE = ctx->SE.p;
+    p.nVdof = ctx->nVdof;
     // one rank: the lists as built.  Several ranks: the GLOBAL lists (replicated build, or partitioned build + exchange); energy and
     // gradient take a contiguous share of them, the Hessian goes by row owner.
     if (ctx->nranks > 1 && w.lists_global) {

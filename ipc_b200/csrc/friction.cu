@@ -82,6 +82,10 @@ __global__ void __launch_bounds__(128) k_friction_lag(BarrierArgs p, int4* __res
         double lam = db;
         lam *= -p.kappa * 2.0 * sqrt(d);
         if (mm.x < 0 && mm.w < -1) lam *= (double)(-mm.w); // PP or PE duplication (Optimizer.cpp:1588-1591)
+        // no friction against a mesh obstacle: the reference's MeshCO does not implement the friction functions (CollisionObject.h:403-423 throw),
+        // Optimizer.cpp:1582-1600 lags the self-contact set only.  A zero normal force switches the pair's E / g / H off.
+        for (int k = 0; k < s.nv; ++k)
+            if (s.v[k] >= p.nVdof) lam = 0.0;
         double c0 = 0.0, c1 = 0.0;
         V3 b0, b1;
         if (s.kind == 0) {        // PT: FrictionUtils.hpp:24-46

@@ -102,6 +102,7 @@ struct BarrierArgs {
     double dHat, kappa;
     int projectDBC;
     const int* ia; const int* ja; int base;
+    int nVdof; // first obstacle vertex (SurfArgs::nVdof)
 };
 
 // barrier.cu

@@ -196,3 +196,30 @@ def test_c3_ball_over_the_mat_as_obstacle(ctx):
     a2_co, z, npairs = o.ccd_full(p, 1e-6, evf, eee, ag, nthreads=NTH)
     assert not z and npairs > 0 and ncand > 0 and bits(a2) == bits(a2_co), (a2, a2_co)
     assert ctx.ccd_stats()[2] == 0 and ctx.intersection_free()
+
+
+def test_no_friction_against_the_obstacle(ctx):
+    """MeshCO does not implement the friction functions (CollisionObject.h:403-423): with an obstacle attached the lagged friction terms are those
+    of the mesh's own pairs; the obstacle's pairs are lagged with a zero normal force"""
+    from test_oracle_friction import COEF
+    m, info, ob, s, o, M2 = build(0.37, res=6, plate=20)
+    dHat = info["dHat"]
+    rng = np.random.default_rng(3)
+    Vt = m.V - 0.3 * np.sqrt(dHat) * rng.standard_normal(m.V.shape)
+    upload(ctx, M2)
+    ctx.set_prev_state(np.ascontiguousarray(np.concatenate([Vt, ob["V"]]).T).ravel())
+    mm, _, _, _ = ctx.constraint_set(dHat, 0)
+    n = ctx.friction_lag(dHat, KAPPA)
+    assert n == len(mm)
+    mm_l, lam, co, ba = ctx.get_friction_data()
+    cross = np.array([OB.involves_obstacle(q, m.nV) for q in mm_l])
+    assert cross.any() and (~cross).any() and np.all(lam[cross] == 0.0) and np.all(lam[~cross] > 0.0)
+    mm_s, _, _, _ = s.constraint_set(dHat, NTH)
+    lam_r, co_r, ba_r = s.friction_lag(mm_s, dHat, KAPPA)
+    eps2 = 1e-2 * dHat
+    E = ctx.friction_energy(eps2, COEF)
+    E_r = s.friction_energy(Vt, mm_s, lam_r, co_r, ba_r, eps2, COEF)
+    assert E_r > 0 and abs(E - E_r) <= 1e-10 * abs(E_r)
+    g = ctx.friction_gradient(eps2, COEF, np.zeros(3 * M2.nV))
+    g_r = s.friction_gradient(Vt, mm_s, lam_r, co_r, ba_r, eps2, COEF)
+    assert rel(g[: 3 * m.nV], g_r) <= 1e-10 and np.all(g[3 * m.nV:] == 0.0)
