@@ -566,13 +566,17 @@ static int upload_dir(ipcgpu_ctx* ctx, const double* p)
     if (p) {
         CK(cudaMemcpyAsync(ctx->dir.p, p, (size_t)3 * ctx->nV * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         double pSize = 0;
+        // (mesh.SVI: with an obstacle attached the surface vertices of the tail do not count -- SpatialHash::build sees the mesh alone)
+        int nMeshSV = 0;
         for (int i = 0; i < ctx->nSV; ++i) {
             const int v = ctx->h_SVI[i];
+            if (v >= ctx->nVdof) continue;
+            ++nMeshSV;
             pSize += std::abs(p[3 * (size_t)v]);
             pSize += std::abs(p[3 * (size_t)v + 1]);
             pSize += std::abs(p[3 * (size_t)v + 2]);
         }
-        ctx->pSize = ctx->nSV > 0 ? pSize / (double)((long long)ctx->nSV * 3) : 0.0;
+        ctx->pSize = nMeshSV > 0 ? pSize / (double)((long long)nMeshSV * 3) : 0.0;
         // the swept-grid kernel reads it from device memory, so that a captured graph stays valid when the direction changes
         ALLOC(ctx->pSize_dev, 1);
         double* hp = ctx->h_scalar + 32; // pinned staging slot of its own (the copy is asynchronous)
@@ -847,6 +851,7 @@ int ipcgpu_set_obstacle_tail(ipcgpu_ctx* ctx, int first_obstacle_vertex, int ee_
     if (first_obstacle_vertex < 0 || first_obstacle_vertex >= ctx->nV) { // no obstacle
         ctx->nVdof = 0x7fffffff;
         ctx->ee_as_vf = ee_through_vf_routine ? 1 : 0;
+        ctx->pSize_surface = false;
         return IPCGPU_OK;
     }
     REQUIRE(first_obstacle_vertex > 0, IPCGPU_ERR_ARG, "the mesh needs at least one vertex of its own");
@@ -860,6 +865,7 @@ int ipcgpu_set_obstacle_tail(ipcgpu_ctx* ctx, int first_obstacle_vertex, int ee_
     }
     ctx->nVdof = first_obstacle_vertex;
     ctx->ee_as_vf = ee_through_vf_routine ? 1 : 0;
+    ctx->pSize_surface = false; // the mean |p| of the swept build is taken over the MESH's surface vertices: upload the direction again
     return IPCGPU_OK;
 }
 

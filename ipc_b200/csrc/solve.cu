@@ -130,11 +130,12 @@ __global__ void k_pcg_roll(double* scal, double* history, int it)
     }
 }
 // mean |p| over the surface vertices (SpatialHash.hpp:603-612) for a direction that was produced on the device: fixed-order two-level sum
-__global__ void __launch_bounds__(256) k_psize(int nSV, const int* __restrict__ SVI, const double* __restrict__ p, double* __restrict__ partials)
+__global__ void __launch_bounds__(256) k_psize(int nSV, const int* __restrict__ SVI, int nVdof, const double* __restrict__ p, double* __restrict__ partials)
 {
     double s = 0.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nSV; i += gridDim.x * blockDim.x) {
         const int v = SVI[i];
+        if (v >= nVdof) continue; // the obstacle's surface vertices do not count (SpatialHash::build sees the mesh alone)
         s += fabs(p[3 * (size_t)v]) + fabs(p[3 * (size_t)v + 1]) + fabs(p[3 * (size_t)v + 2]);
     }
     s = warp_sum(s);
@@ -251,13 +252,15 @@ int solver_adopt_direction(ipcgpu_ctx* ctx)
     if (ctx->nSV > 0) {
         const int nb = 64;
         if (!ctx->pcg_scal.reserve(8) || !ctx->partials.reserve(nb + 8)) return IPCGPU_ERR_CUDA;
-        k_psize<<<nb, 256, 0, st>>>(ctx->nSV, ctx->SVI.p, ctx->dir.p, ctx->partials.p);
+        k_psize<<<nb, 256, 0, st>>>(ctx->nSV, ctx->SVI.p, ctx->nVdof, ctx->dir.p, ctx->partials.p);
         ++ctx->launches;
         std::vector<double> hp(nb);
         CKS(cudaMemcpyAsync(hp.data(), ctx->partials.p, nb * sizeof(double), cudaMemcpyDeviceToHost, st));
         CKS(cudaStreamSynchronize(st));
         for (double v : hp) pSize += v;
-        pSize /= (double)((long long)ctx->nSV * 3);
+        long long nMeshSV = 0;
+        for (int v : ctx->h_SVI) nMeshSV += v < ctx->nVdof ? 1 : 0;
+        pSize = nMeshSV > 0 ? pSize / (double)(nMeshSV * 3) : 0.0;
     }
     ctx->pSize = pSize;
     if (!ctx->pSize_dev.reserve(1)) return IPCGPU_ERR_CUDA;

@@ -360,7 +360,9 @@ void orc_grid_swept(const orc_surf* s, const double* p, double* alpha, double h,
     double pSize = 0;
     for (int i = 0; i < s->nSV; ++i) {
         int v = s->SVI[i];
-        pSize += std::abs(p[3 * (size_t)v]) + std::abs(p[3 * (size_t)v + 1]) + std::abs(p[3 * (size_t)v + 2]);
+        pSize += std::abs(p[3 * (size_t)v]);     /* three separate accumulations, in this order (SpatialHash.hpp:605-611): the sum is order-sensitive */
+        pSize += std::abs(p[3 * (size_t)v + 1]);
+        pSize += std::abs(p[3 * (size_t)v + 2]);
     }
     pSize /= (double)(s->nSV * 3);
     const double span = *alpha * pSize / h;

@@ -223,3 +223,14 @@ def test_no_friction_against_the_obstacle(ctx):
     g = ctx.friction_gradient(eps2, COEF, np.zeros(3 * M2.nV))
     g_r = s.friction_gradient(Vt, mm_s, lam_r, co_r, ba_r, eps2, COEF)
     assert rel(g[: 3 * m.nV], g_r) <= 1e-10 and np.all(g[3 * m.nV:] == 0.0)
+
+
+def test_swept_grid_step_ignores_the_obstacle(ctx):
+    """SpatialHash::build rescales the step by the mean |p| over mesh.SVI (SpatialHash.hpp:603-618): the obstacle's vertices must not dilute it"""
+    m, info, ob, s, o, M2 = build(0.37, res=4)
+    upload(ctx, M2)
+    p = 40.0 * info["p"]
+    hvox = m.avgEdgeLen / 3.0
+    ag = ctx.hash_build_swept(OB.pad_direction(p, M2.nV), 1.0, hvox)
+    g = orc.grid_swept(s, p, 1.0, hvox)
+    assert g[1] < 1.0 and bits(ag) == bits(g[1]), (ag, g[1])
