@@ -177,3 +177,47 @@ def test_step_bounds_against_the_merged_self_contact_oracle():
     oz = orc.Obstacle(s, Vz, ob["E"], ob["F"])
     a_z, z = oz.ccd_partial(p, cand, 1e-6, evf, eee, 1.0, nthreads=NTH)
     assert z and a_z == 0.0
+
+
+def test_encoding_translation_of_every_kind_and_empty_lists():
+    """ipc_b200/obstacle.py (host mirror of adapters/IpcGpuMeshCO.hpp) against the oracle's translation, on hand-built entries of all six kinds"""
+    import ctypes as C
+    nV, nSE = 100, 40
+    co = np.array([[3, 7, 5, 9],          # EE  (mesh edge 3-7, obstacle edge 5-9)
+                   [-12, 4, -1, -3],      # PP  (mesh vertex 11, obstacle vertex 4, found three times)
+                   [-12, 4, 6, -2],       # PE  (mesh vertex 11, obstacle edge 4-6, twice)
+                   [-12, 4, 6, 8],        # PT
+                   [-2, -5, -9, 17],      # TP  (obstacle vertex 17, mesh triangle 1-4-8)
+                   [-2, -5, 17, -1]],     # EP  (obstacle vertex 17, mesh edge 1-4)
+                  dtype=np.int32)
+    pe = np.array([[2, 5], [-1, -1]], dtype=np.int32)
+    out = np.empty_like(co)
+    pe_out = np.empty_like(pe)
+    orc.lib().orc_meshco_to_merged(nV, nSE, orc.i(co), len(co), orc.i(out), orc.i(pe), len(pe), orc.i(pe_out))
+    expect = np.array([[3, 7, 105, 109], [-12, 104, -1, -3], [-12, 104, 106, -2], [-12, 104, 106, 108], [-118, 1, 4, 8], [-118, 1, 4, -1]], dtype=np.int32)
+    assert np.array_equal(out, expect) and np.array_equal(pe_out, [[2, 45], [-1, -1]])
+    assert all(OB.involves_obstacle(q, nV) for q in out)
+    assert np.array_equal(np.array([OB.merged_to_meshco(q, nV) for q in out], dtype=np.int32), co)
+    assert not OB.involves_obstacle([-12, 13, 14, 15], nV) and not OB.involves_obstacle([1, 2, 3, 4], nV)
+    # splitting: the mesh's own entries stay as they are, the obstacle's are translated; mollified pairs by their edge pair as well
+    mm = np.concatenate([out, [[-12, 13, 14, 15], [1, 2, 3, 4]]]).astype(np.int32)
+    pa = np.array([[-4, 105, -1, -1], [5, 6, 7, 8]], dtype=np.int32)
+    pe2 = np.array([[2, 45], [-1, -1]], dtype=np.int32)
+    (smm, spa, spe), (cmm, cpa, cpe) = OB.split_sets(mm, pa, pe2, nV, nSE)
+    assert np.array_equal(smm, [[-12, 13, 14, 15], [1, 2, 3, 4]]) and np.array_equal(cmm, co)
+    assert np.array_equal(spa, [[5, 6, 7, 8]]) and np.array_equal(spe, [[-1, -1]]) and np.array_equal(cpa, [[-4, 5, -1, -1]]) and np.array_equal(cpe, [[2, 5]])
+    sc, cc = OB.split_candidates([[-3, 4], [-3, 64], [-53, 4], [7, 9], [7, 49]], n_mesh_sv=50, n_mesh_tris=60, n_mesh_edges=40)
+    assert np.array_equal(sc, [[-3, 4], [7, 9]]) and np.array_equal(cc, [[-3, 4], [-5, -3], [7, 9]])
+    e = np.zeros((0, 4), np.int32)
+    (a, b, c), (d, f, g) = OB.split_sets(e, e, np.zeros((0, 2), np.int32), nV, nSE)
+    assert all(len(x) == 0 for x in (a, b, c, d, f, g))
+    # an obstacle out of reach: empty sets, the step stays what it was
+    m, info, ob, s, o = scene(0.37)
+    far = orc.Obstacle(s, ob["V"] + np.array([0.0, 0.0, -10.0]), ob["E"], ob["F"])
+    mm0, pa0, pe0, cand0 = far.constraint_set(info["dHat"], NTH)
+    assert len(mm0) == len(pa0) == len(cand0) == 0
+    evf, eee = orc.ti_error(s.V, m.nV, None)
+    assert far.ccd_partial(info["p"], cand0, 1e-6, evf, eee, 0.7, nthreads=NTH) == (0.7, 0)
+    a_full, z, npairs = far.ccd_full(info["p"], 1e-6, evf, eee, 0.7, nthreads=NTH)
+    assert (a_full, z, npairs) == (0.7, 0, 0)
+    assert far.energy(mm0, pa0, pe0, info["dHat"], KAPPA) == (0.0, 0)
