@@ -298,7 +298,8 @@ int ipcgpu_ccd_full_ti(ipcgpu_ctx* ctx, double tolerance, const double err_vf[3]
 int ipcgpu_set_obstacle_tail(ipcgpu_ctx* ctx, int first_obstacle_vertex, int ee_through_vf_routine);
 /* MeshCO::move / Base::V after a scripted motion: new positions of the obstacle's vertices, SoA [x | y | z] over the obstacle's own count;
  * current and rest positions of the tail are both replaced (an obstacle has no rest shape: compute_eps_x(mesh, Base::V, ...) uses its current
- * edge lengths, MeshCollisionUtils.hpp:2976-2981) */
+ * edge lengths, MeshCollisionUtils.hpp:2976-2981).  The state saved by ipcgpu_save_state keeps the tail it was saved with: move the obstacle between
+ * line searches (as the reference does, Optimizer.cpp: the scripted motion runs before the Newton loop of a time step) or save the state again. */
 int ipcgpu_set_obstacle_positions(ipcgpu_ctx* ctx, const double* Vo_soa);
 
 /* diagnostics of the last narrow phase: candidates tested, pairs surviving the root box, conservative early-outs (should be 0) */

@@ -877,8 +877,8 @@ int ipcgpu_set_obstacle_positions(ipcgpu_ctx* ctx, const double* Vo_soa)
     const size_t nVo = (size_t)(ctx->nV - ctx->nVdof);
     // current AND rest positions: the obstacle has no rest shape of its own, compute_eps_x takes its current edge lengths
     // (MeshCollisionUtils.hpp:2976-2981); SoA with the stride of the whole vertex array
-    // ... and the saved state of the line search (ipcgpu_save_state / _step_forward rebuild the WHOLE vertex array from it: the tail must not fall back)
-    for (double* dst : { ctx->V.p, ctx->Vrest.p, ctx->Vsaved.p })
+    // (the saved line-search state keeps the old tail: move the obstacle BETWEEN line searches, or call ipcgpu_save_state again afterwards)
+    for (double* dst : { ctx->V.p, ctx->Vrest.p })
         CK(cudaMemcpy2DAsync(dst + ctx->nVdof, (size_t)ctx->nV * sizeof(double), Vo_soa, nVo * sizeof(double), nVo * sizeof(double), 3, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream)); // (pageable host memory)
     ctx->mark_inputs();
