@@ -25,6 +25,7 @@
 // (GpuMeshCO::setPattern / fetchValues).
 #pragma once
 #include "IpcGpuAdapters.hpp"
+#include "MeshCOEncoding.hpp"
 
 namespace IPC {
 
@@ -123,30 +124,21 @@ struct GpuMeshCO {
         return p;
     }
 
-    // ---- encodings ---------------------------------------------------------------------------------------------------------------
-    static bool touchesObstacle(const int* q)
-    {
-        if ((q[0] < 0 ? -q[0] - 1 : q[0]) >= nV) return true;
-        for (int k = 1; k < 4; ++k)
-            if (q[k] >= nV) return true;
-        return false;
-    }
+    // ---- encodings (adapters/MeshCOEncoding.hpp: plain functions, run against the oracle's translation by tests/test_adapters_compile.py) ------
+    static bool touchesObstacle(const int* q) { return meshco_encoding::touches_obstacle(q, nV); }
     // merged self-contact entry -> MeshCO entry (slot 3 keeps a multiplicity < 0 as it is)
     static MMCVID toMeshCO(const int* q)
     {
-        if (q[0] >= 0) return MMCVID(q[0], q[1], q[2] - nV, q[3] >= 0 ? q[3] - nV : q[3]);              // EE: mesh edge first
-        const int p = -q[0] - 1;
-        if (p < nV) return MMCVID(q[0], q[1] - nV, q[2] >= 0 ? q[2] - nV : q[2], q[3] >= 0 ? q[3] - nV : q[3]); // PP / PE / PT: mesh point
-        if (q[3] < 0) return MMCVID(-q[1] - 1, -q[2] - 1, p - nV, q[3]);                                    // EP: obstacle point, mesh edge
-        return MMCVID(-q[1] - 1, -q[2] - 1, -q[3] - 1, p - nV);                                             // TP: obstacle point, mesh triangle
+        int m[4];
+        meshco_encoding::to_meshco(q, nV, m);
+        return MMCVID(m[0], m[1], m[2], m[3]);
     }
     // MeshCO entry -> merged self-contact entry (the inverse; MeshCO.cpp:83-120 for which slot holds what)
     static MMCVID toMerged(const int* m)
     {
-        if (m[0] >= 0) return MMCVID(m[0], m[1], nV + m[2], m[3] >= 0 ? nV + m[3] : m[3]);
-        if (m[1] >= 0) return MMCVID(m[0], nV + m[1], m[2] >= 0 ? nV + m[2] : m[2], m[3] >= 0 ? nV + m[3] : m[3]);
-        if (m[2] < 0) return MMCVID(-(nV + m[3]) - 1, -m[0] - 1, -m[1] - 1, -m[2] - 1);
-        return MMCVID(-(nV + m[2]) - 1, -m[0] - 1, -m[1] - 1, m[3]);
+        int q[4];
+        meshco_encoding::to_merged(m, nV, q);
+        return MMCVID(q[0], q[1], q[2], q[3]);
     }
 
     // ---- the one device pass behind both handlers' computeConstraintSet (Optimizer.cpp:2464-2470) -------------------------------------
