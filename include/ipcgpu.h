@@ -294,7 +294,8 @@ int ipcgpu_ccd_full_ti(ipcgpu_ctx* ctx, double tolerance, const double err_vf[3]
  * zero, its gradient rows are Dirichlet rows (whatever the barrier terms add there is discarded with them), its CSR rows hold the identity; because the tail's rows come last and no mesh row has a column in them,
  * the mesh's own upper-triangular CSR values are a PREFIX of the value array.  first_obstacle_vertex < 0 or >= nV removes the obstacle.
  * Friction: the reference implements none against a MeshCO (CollisionObject.h:403-423 throw "not implemented"); ipcgpu_friction_lag lags the pairs
- * that touch the obstacle with a zero normal force, so the friction terms stay those of the mesh's own pairs.  Not covered: the CTCD variants, SQP. */
+ * that touch the obstacle with a zero normal force, so the friction terms stay those of the mesh's own pairs.  Not covered: the CTCD variants, SQP, and scenes that switch self contact off (Config.cpp:480
+ * `selfCollisionOff`) while keeping an obstacle: the mesh's own pairs are always part of the pass. */
 int ipcgpu_set_obstacle_tail(ipcgpu_ctx* ctx, int first_obstacle_vertex, int ee_through_vf_routine);
 /* MeshCO::move / Base::V after a scripted motion: new positions of the obstacle's vertices, SoA [x | y | z] over the obstacle's own count;
  * current and rest positions of the tail are both replaced (an obstacle has no rest shape: compute_eps_x(mesh, Base::V, ...) uses its current
