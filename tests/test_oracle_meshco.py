@@ -221,3 +221,24 @@ def test_encoding_translation_of_every_kind_and_empty_lists():
     a_full, z, npairs = far.ccd_full(info["p"], 1e-6, evf, eee, 0.7, nthreads=NTH)
     assert (a_full, z, npairs) == (0.7, 0, 0)
     assert far.energy(mm0, pa0, pe0, info["dHat"], KAPPA) == (0.0, 0)
+
+
+def test_row_owner_partition_with_an_obstacle_tail():
+    """ipc_b200/partition.py (mirror of the library's rule) on a mesh with an obstacle at the tail: the tail's vertices touch no tetrahedron, so they
+    all fall to the last rank, every tetrahedron is still assembled, and the solver's own values (the CSR prefix) split between the ranks as before"""
+    from ipc_b200 import partition as P
+    m, info, ob, s, o = scene(0.37)
+    M2 = OB.with_obstacle(m, ob["V"], ob["E"], ob["F"])
+    ia, ja = M2.csr_pattern(1)
+    ia0, _ = m.csr_pattern(1)
+    for world in (2, 3, 8):
+        b = P.vertex_boundaries(M2.T, M2.nV, world)
+        b0 = P.vertex_boundaries(m.T, m.nV, world)
+        assert b[:-1] == b0[:-1] and b[-1] == M2.nV and b[-2] <= m.nV  # same cuts; only the last range grows by the tail
+        seen = np.zeros(m.nT, dtype=int)
+        for r in range(world):
+            seen[P.assembled_tets(M2.T, b[r], b[r + 1])] += 1
+        assert seen.min() >= 1
+        lo, hi = P.owned_value_range(ia, 1, b[world - 1], b[world])
+        lo0, hi0 = P.owned_value_range(ia0, 1, b0[world - 1], b0[world])
+        assert lo == lo0 and hi == hi0 + 6 * len(ob["V"])  # the tail's identity blocks: 3 + 2 + 1 values per vertex, after the mesh's values
