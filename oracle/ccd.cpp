@@ -147,6 +147,12 @@ extern "C" void orc_ti_stats(long long* out72, int reset)
         }
 }
 
+/* The library pops boxes of one level in ascending t_lo and leaves the order of boxes with EQUAL t_lo to its heap (unspecified).  The oracle
+ * (and the GPU) fix it to ascending (u_lo, v_lo).  orc_ti_debug_tie_order(1) reverses that choice -- the opposite admissible order -- so that
+ * tests can measure whether a result depends on it (tests/test_oracle_ccd.py::test_tie_order_of_equal_times_does_not_change_the_results). */
+static std::atomic<int> g_tie_reversed{ 0 };
+extern "C" void orc_ti_debug_tie_order(int reversed) { g_tie_reversed.store(reversed ? 1 : 0); }
+
 /* interval_root_finder_double_horizontal_tree with the canonical in-level order */
 bool root_finder(bool vf, const double* x0, const double* x1, const double tol[3], double co_tol, double max_t, const double err[3], double ms,
     int max_itr, double& toi, double& out_tol)
@@ -168,12 +174,13 @@ bool root_finder(bool vf, const double* x0, const double* x1, const double tol[3
     while (!level.empty() && !overflow) {
         ++stat.levels;
         stat.width = std::max<long long>(stat.width, (long long)level.size());
-        std::sort(level.begin(), level.end(), [](const Box3& a, const Box3& b) {
+        const bool rev = g_tie_reversed.load(std::memory_order_relaxed) != 0;
+        std::sort(level.begin(), level.end(), [rev](const Box3& a, const Box3& b) {
             double ta = lo_of(a.t), tb = lo_of(b.t);
             if (ta != tb) return ta < tb;
             double ua = lo_of(a.u), ub = lo_of(b.u);
-            if (ua != ub) return ua < ub;
-            return lo_of(a.v) < lo_of(b.v);
+            if (ua != ub) return rev ? ua > ub : ua < ub;
+            return rev ? lo_of(a.v) > lo_of(b.v) : lo_of(a.v) < lo_of(b.v);
         });
         bool this_level_less_tol = true, find_level_root = false;
         next.clear();

@@ -156,3 +156,56 @@ def test_ball_on_mat_config_c3():
             assert orc.point_tri_d(V2[[m.SVI[-c[0] - 1]] + list(m.SF[c[1]])]) > 0
         else:
             assert orc.edge_edge_d(V2[list(m.SFEdges[c[0]]) + list(m.SFEdges[c[1]])]) > 0
+
+
+def test_tie_order_of_equal_times_does_not_change_the_results():
+    """Tight-Inclusion leaves the order of boxes with equal t_lo inside a level to its heap; the oracle and the GPU fix it (ascending u_lo, v_lo).
+    A result that depended on that choice would make "bit-exact against the oracle" weaker than "bit-exact against the library".  Measured here:
+    with the opposite admissible order (descending) every time of impact is the same bit pattern -- on random pairs, on grazing / symmetric
+    configurations built to create ties, and on every CCD candidate of a ball pile and of an obstacle scene."""
+    rng = np.random.default_rng(11)
+    cases = []
+    for _ in range(400):
+        x0 = rng.standard_normal((4, 3))
+        cases.append((x0, x0 + 0.8 * rng.standard_normal((4, 3))))
+    for _ in range(200):  # symmetric set-ups: a point above the centroid / an edge across the middle of another, moving straight in (ties in u, v)
+        h = rng.uniform(0.01, 0.5)
+        tri = np.array([[0.0, 0.0, 0.0], [1.0, 0.0, 0.0], [0.0, 1.0, 0.0]])
+        pnt = np.array([[1 / 3, 1 / 3, h]])
+        x0 = np.concatenate([pnt, tri])
+        x1 = x0.copy()
+        x1[0, 2] -= rng.uniform(0.5, 2.0) * h * 2
+        cases.append((x0, x1))
+        e = np.array([[-1.0, 0.0, 0.0], [1.0, 0.0, 0.0], [0.0, -1.0, h], [0.0, 1.0, h]])
+        e1 = e.copy()
+        e1[2:, 2] -= rng.uniform(0.5, 2.0) * h * 2
+        cases.append((e, e1))
+
+    def run_all():
+        out = []
+        for x0, x1 in cases:
+            for kind in ("vf", "ee"):
+                hit, toi, tol = orc.ti(kind, x0, x1, ERR, 1e-6)
+                out.append((hit, np.float64(toi).view(np.uint64) if hit else 0))
+        return out
+
+    try:
+        orc.lib().orc_ti_debug_tie_order(0)
+        canonical = run_all()
+        m, info = scenes.ball_pile(4, res=8, seed=5, height=4)
+        s = orc.Surf(m)
+        evf, eee = orc.ti_error(s.V, m.nV, info["p"])
+        _, _, _, cand = s.constraint_set(info["dHat"], 8)
+        a_pile = orc.ccd_partial(s, info["p"], cand, 1e-6, evf, eee, 1.0, 8)
+        g, ag = orc.grid_swept(s, info["p"], a_pile[0], m.avgEdgeLen / 3)
+        f_pile = orc.ccd_full(s, info["p"], g, ag, 1e-6, evf, eee, ag, nthreads=8)
+        orc.lib().orc_ti_debug_tie_order(1)
+        reversed_ = run_all()
+        a_pile_r = orc.ccd_partial(s, info["p"], cand, 1e-6, evf, eee, 1.0, 8)
+        f_pile_r = orc.ccd_full(s, info["p"], g, ag, 1e-6, evf, eee, ag, nthreads=8)
+    finally:
+        orc.lib().orc_ti_debug_tie_order(0)
+    assert sum(h for h, _ in canonical) > 300
+    differing = [k for k, (a, b) in enumerate(zip(canonical, reversed_)) if a != b]
+    assert not differing, (len(differing), differing[:5])
+    assert a_pile == a_pile_r and f_pile == f_pile_r
