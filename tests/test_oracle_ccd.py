@@ -209,3 +209,44 @@ def test_tie_order_of_equal_times_does_not_change_the_results():
     differing = [k for k, (a, b) in enumerate(zip(canonical, reversed_)) if a != b]
     assert not differing, (len(differing), differing[:5])
     assert a_pile == a_pile_r and f_pile == f_pile_r
+
+
+def test_time_of_impact_is_tight_as_well_as_conservative():
+    """Quantitative pin of the restated search against the geometry itself (no library needed): with minimum separation ms and tolerance delta the
+    returned time lies between the first instant the exact distance reaches sqrt(3) (ms + O(delta)) and the first instant it reaches ms: the
+    inclusion test asks whether the difference vector enters the CUBE of half-width ms (+ error bound) around the origin, whose corners are
+    sqrt(3) ms away.  (Conservative: never later than contact at separation ms.  Tight: not earlier than cube and co-domain tolerance allow.)"""
+    from scipy.optimize import brentq
+    rng = np.random.default_rng(21)
+    ms, delta = 1e-3, 1e-6
+    checked = 0
+    for _ in range(300):
+        x0 = rng.standard_normal((4, 3))
+        x1 = x0 + 0.8 * rng.standard_normal((4, 3))
+        disp = np.abs(x1 - x0).max()
+        for kind in ("vf", "ee"):
+            f = orc.point_tri_d if kind == "vf" else orc.edge_edge_d
+            dist = lambda t: np.sqrt(f(x0 + t * (x1 - x0)))
+
+            def first_time(thr):
+                ts = np.linspace(0.0, 1.0, 1501)
+                v = np.array([dist(t) - thr for t in ts])
+                k = np.nonzero(v <= 0)[0]
+                if len(k) == 0:
+                    return None
+                if k[0] == 0:
+                    return 0.0
+                return brentq(lambda t: dist(t) - thr, ts[k[0] - 1], ts[k[0]], xtol=1e-13)
+
+            if dist(0.0) <= ms + 1e-4:
+                continue  # starts in contact: not the case under test
+            hit, toi, _ = orc.ti(kind, x0, x1, ERR, ms, tol=delta)
+            t_contact = first_time(ms)
+            t_early = first_time(np.sqrt(3.0) * (ms + 4.0 * delta))  # the eps-cube's corner, widened by the co-domain tolerance and the error bound
+            if t_contact is not None:
+                assert hit, "a trajectory that reaches the minimum separation must be reported"
+                assert toi <= t_contact + 1e-12
+            if hit:
+                assert t_early is not None and toi >= t_early - 2.0 * delta / max(disp, 1e-3), (kind, toi, t_early, t_contact)
+                checked += 1
+    assert checked > 40
