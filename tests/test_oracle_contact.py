@@ -284,3 +284,56 @@ def test_pair_hessians_are_translation_invariant():
         # the projected matrix is a fixed point of the reduced projection
         assert np.abs(Q.T @ make_pd(Q @ H @ Q.T) @ Q - H).max() <= 1e-9 * scale
     assert len(kinds) >= 3  # several stencil types were exercised
+
+
+def test_dtype_against_an_independent_closest_feature_search():
+    """dType_PT / dType_EE (MeshCollisionUtils.hpp, restated branch for branch in the oracle and the kernels) decide which distance formula a pair
+    gets, hence the constraint set.  Independent check: the squared distances to every sub-feature, each from its own closed form with the
+    closest point constrained to the feature's INTERIOR (vertex: always valid; edge: parameter in (0,1); triangle: barycentric coordinates > 0;
+    edge-edge: both parameters in (0,1)); the valid feature with the smallest distance is the closest feature and must be the reported type,
+    with the same distance."""
+    rng = np.random.default_rng(17)
+
+    def pp(a, b):
+        return ((a - b) ** 2).sum()
+
+    def pe(p, a, b):  # interior projection only
+        e = b - a
+        t = (p - a) @ e / (e @ e)
+        return ((p - (a + t * e)) ** 2).sum() if 0.0 < t < 1.0 else np.inf
+
+    def pt(p, a, b, c):
+        n = np.cross(b - a, c - a)
+        q = p - ((p - a) @ n) / (n @ n) * n
+        M = np.array([b - a, c - a]).T
+        uv, *_ = np.linalg.lstsq(M, q - a, rcond=None)
+        return ((p - q) ** 2).sum() if uv[0] > 0 and uv[1] > 0 and uv.sum() < 1 else np.inf
+
+    def ee(a0, a1, b0, b1):
+        u, v, w = a1 - a0, b1 - b0, a0 - b0
+        A = np.array([[u @ u, -(u @ v)], [-(u @ v), v @ v]])
+        if abs(np.linalg.det(A)) < 1e-12 * (u @ u) * (v @ v):
+            return np.inf
+        s, t = np.linalg.solve(A, np.array([-(u @ w), v @ w]))
+        return ((a0 + s * u - b0 - t * v) ** 2).sum() if 0 < s < 1 and 0 < t < 1 else np.inf
+
+    seen_pt, seen_ee = set(), set()
+    for _ in range(3000):
+        X = rng.standard_normal((4, 3)) * rng.choice([0.3, 1.0, 3.0])
+        p, a, b, c = X
+        cand = [pp(p, a), pp(p, b), pp(p, c), pe(p, a, b), pe(p, b, c), pe(p, c, a), pt(p, a, b, c)]  # the reference's numbering 0..6
+        k = int(np.argmin(cand))
+        srt = np.sort(cand)
+        if srt[1] - srt[0] > 1e-9 * (1 + srt[0]):  # (skip exact ties between features)
+            assert orc.dType_PT(X) == k, (orc.dType_PT(X), k, cand)
+            assert abs(orc.point_tri_d(X) - cand[k]) <= 1e-12 * (1 + cand[k])
+            seen_pt.add(k)
+        a0, a1, b0, b1 = X
+        cand = [pp(a0, b0), pp(a0, b1), pe(a0, b0, b1), pp(a1, b0), pp(a1, b1), pe(a1, b0, b1), pe(b0, a0, a1), pe(b1, a0, a1), ee(a0, a1, b0, b1)]
+        k = int(np.argmin(cand))
+        srt = np.sort(cand)
+        if srt[1] - srt[0] > 1e-9 * (1 + srt[0]):
+            assert orc.dType_EE(X) == k, (orc.dType_EE(X), k, cand)
+            assert abs(orc.edge_edge_d(X) - cand[k]) <= 1e-12 * (1 + cand[k])
+            seen_ee.add(k)
+    assert seen_pt == set(range(7)) and seen_ee == set(range(9))
