@@ -217,3 +217,38 @@ def test_csr_pattern_matches_reference_layout():
     ia2 = np.empty(3 * m.nV + 1, dtype=np.int32); ja2 = np.empty(nnz, dtype=np.int32)
     orc.lib().orc_csr_pattern(m.nV, orc.i(ptr), orc.i(nbr), 1, orc.i(ia2), orc.i(ja2))
     assert np.array_equal(ia, ia2) and np.array_equal(ja, ja2)
+
+
+def test_makePD2d_is_the_reference_formula_not_the_eigenvalue_clamp():
+    """IglUtils::makePD2d (IglUtils.hpp:138-177) returns v v^T / L1 with v = (L1 - d, b) where the projection onto the positive eigen-direction would be
+    L1 v v^T / |v|^2.  The oracle (and the kernels) restate the formula as it stands -- DESIGN.md 3.4; this test records the difference so that nobody
+    "fixes" one side only."""
+    import ctypes as C
+    M = np.array([1.0, 2.0, 2.0, -1.0])
+    out = M.copy()
+    orc.lib().orc_makePD2d(orc.d(out))
+    L1 = np.sqrt(5.0)
+    v = np.array([L1 + 1.0, 2.0])
+    assert np.allclose(out.reshape(2, 2), np.outer(v, v) / L1, rtol=1e-14)
+    exact = L1 * np.outer(v, v) / (v @ v)
+    assert np.abs(out.reshape(2, 2) - exact).max() > 1.0  # far from the eigenvalue clamp, yet positive semi-definite
+    assert np.linalg.eigvalsh(out.reshape(2, 2)).min() >= -1e-12
+    # the twist block at rest, [[mu, mu], [mu, mu]] with L2 = -0: comes back halved, whereas L2 = +0 leaves it untouched (the discontinuity)
+    mu = 3.0
+    for eps, factor in ((+1e-12, 0.5), (-1e-12, 1.0)):  # off-diagonal a hair above / below the diagonal: L2 = -+1e-12
+        B = np.array([mu, mu + eps, mu + eps, mu])
+        orc.lib().orc_makePD2d(orc.d(B))
+        assert np.allclose(B, factor * mu, rtol=1e-9)
+    # through dP/dF: whenever a block is projected the result differs from the exact PSD projection of the 9 x 9 matrix
+    rng = np.random.default_rng(4)
+    worst = 0.0
+    for _ in range(200):
+        F = np.eye(3) + 0.6 * rng.standard_normal((3, 3))
+        if np.linalg.det(F) <= 0.05:
+            continue
+        H = orc.dPdF(0, F, 3.6e4, 1.4e5, 1.0, 0)
+        Hp = orc.dPdF(0, F, 3.6e4, 1.4e5, 1.0, 1)
+        w, Q = np.linalg.eigh((H + H.T) / 2)
+        assert np.linalg.eigvalsh((Hp + Hp.T) / 2).min() >= -1e-9 * np.abs(H).max()  # it IS positive semi-definite
+        worst = max(worst, np.abs(Hp - (Q * np.maximum(w, 0)) @ Q.T).max() / np.abs(H).max())
+    assert worst > 0.05
