@@ -252,3 +252,35 @@ def test_makePD2d_is_the_reference_formula_not_the_eigenvalue_clamp():
         assert np.linalg.eigvalsh((Hp + Hp.T) / 2).min() >= -1e-9 * np.abs(H).max()  # it IS positive semi-definite
         worst = max(worst, np.abs(Hp - (Q * np.maximum(w, 0)) @ Q.T).max() / np.abs(H).max())
     assert worst > 0.05
+
+
+def test_inversion_step_is_the_smallest_positive_root():
+    """Energy::filterStepSize / getSmallestPositiveRealCubicRoot (Energy.cpp:565-581, get_feasible_steps.cpp): per tet the step is the SMALLEST positive
+    root of the cubic  det(X + t P) = slack * det(X)  -- checked against numpy's companion-matrix roots of the cubic interpolated through four
+    exact determinants (an independent route: the oracle and the kernel use Cardano's formulas in complex arithmetic)."""
+    m = small_mesh(0)
+    rng = np.random.default_rng(9)
+    p = rng.standard_normal(3 * m.nV) * 0.8
+    slack = 0.2
+    a, per = orc.Elastic(m).inversion_step(p, slack, 1e30)
+    P = p.reshape(-1, 3)
+
+    def dets(t):
+        x = (m.V + t * P)[m.T]
+        return np.linalg.det(np.stack([x[:, 1] - x[:, 0], x[:, 2] - x[:, 0], x[:, 3] - x[:, 0]], axis=2))
+
+    ts = np.array([0.0, 1.0, 2.0, 3.0])
+    D = np.stack([dets(t) for t in ts])  # (4, nT): a cubic in t per tet, interpolated exactly by four samples
+    coef = np.linalg.solve(np.vander(ts, 4), D)  # rows: t^3, t^2, t, 1
+    n_roots = 0
+    for t in range(m.nT):
+        c = coef[:, t].copy()
+        c[3] -= slack * D[0, t]
+        r = np.roots(c)
+        pos = sorted(x.real for x in r if abs(x.imag) <= 1e-9 * max(1.0, abs(x)) and x.real > 0)
+        if pos:
+            n_roots += 1
+            assert abs(per[t] - pos[0]) <= 1e-8 * pos[0], (t, per[t], pos)
+        else:
+            assert per[t] > 1e19  # no positive root: no bound from this tet
+    assert n_roots > m.nT // 4 and a == per.min()
